@@ -1,0 +1,187 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures under tests/golden/ from the REAL reference.
+
+Run in the build container only (needs /root/reference, which does not exist on the GPU box):
+
+    python tests/golden/make_golden.py
+
+The reference is imported unmodified with 4 import shims (tests/golden/_shims: timm.models.layers,
+easydict, tensorboardX; plus collections.Iterable alias).  Weights come from oracle.synth (seeded
+per key), so only OUTPUTS are stored.  Stochastic ops (DropPath, Dropout2d) are either disabled
+(p = 0) or fed explicit per-sample multipliers through the shim, so fixtures are deterministic.
+"""
+import collections
+import collections.abc
+import os
+import sys
+import tempfile
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = os.environ.get("CMX_REFERENCE", "/root/reference")
+
+collections.Iterable = collections.abc.Iterable  # utils/transforms.py:13
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(HERE, "_shims"))
+sys.path.insert(0, REF)
+os.chdir(tempfile.mkdtemp())  # config.py computes cwd-relative dirs
+
+from config import config  # noqa: E402  (reference)
+from models.builder import EncoderDecoder  # noqa: E402  (reference)
+from models.decoders.MLPDecoder import DecoderHead  # noqa: E402
+from timm.models.layers import DropPath  # noqa: E402  (shim)
+from utils import metric as ref_metric  # noqa: E402
+
+from oracle import cmx_ref  # noqa: E402
+from oracle.synth import synth_inputs, synth_state_dict  # noqa: E402
+
+torch.set_num_threads(os.cpu_count() or 1)
+
+
+def build_reference(backbone: str, num_classes: int, train_built: bool):
+    config.backbone = backbone
+    config.num_classes = num_classes
+    config.pretrained_model = None
+    crit = nn.CrossEntropyLoss(reduction="mean", ignore_index=255) if train_built else None
+    if backbone in ("mit_b4", "mit_b5"):
+        # reference builder crashes for b4/b5: assemble backbone + DecoderHead by hand
+        config.backbone = "mit_b2"
+        m = EncoderDecoder(cfg=config, criterion=crit, norm_layer=nn.BatchNorm2d)
+        from models.encoders import dual_segformer
+        m.backbone = getattr(dual_segformer, backbone)()
+        m.decode_head = DecoderHead(in_channels=[64, 128, 320, 512], num_classes=num_classes,
+                                    norm_layer=nn.BatchNorm2d, embed_dim=config.decoder_embed_dim)
+        if train_built:
+            m.init_weights(config, pretrained=None)
+        config.backbone = backbone
+        return m
+    return EncoderDecoder(cfg=config, criterion=crit, norm_layer=nn.BatchNorm2d)
+
+
+def disable_stochastic(m):
+    for mod in m.modules():
+        if isinstance(mod, DropPath):
+            mod.drop_prob = 0.0
+    m.decode_head.dropout.p = 0.0
+
+
+def case(name, backbone, num_classes, B, H, W, sub=1, stochastic=False):
+    spec = cmx_ref.MIT_SPECS[backbone]
+    sd = synth_state_dict(spec, num_classes, seed=0)
+    rgb, x, gt = synth_inputs(B, H, W, num_classes, seed=1)
+    out = {}
+
+    # ---- eval-built model (criterion=None => decoder BN eps 1e-5, eval.py:97) : logits
+    m = build_reference(backbone, num_classes, train_built=False)
+    ref_keys = list(m.state_dict().keys())
+    assert ref_keys == list(sd.keys()), "oracle schema order/name mismatch vs reference state_dict"
+    for k, v in m.state_dict().items():
+        assert tuple(v.shape) == tuple(sd[k].shape), k
+    m.load_state_dict(sd, strict=True)
+    m.eval()
+    with torch.no_grad():
+        logits = m(rgb, x)
+    out["eval_logits"] = logits[:, :, ::sub, ::sub].numpy()
+    out["eval_exp_score0_sum"] = np.float64(torch.exp(logits[0]).double().sum().item())  # evaluator.py:393
+
+    # ---- train-built model (criterion given => init_weights => decoder BN eps 1e-3), train mode
+    m = build_reference(backbone, num_classes, train_built=True)
+    m.load_state_dict(sd, strict=True)
+    m.train()
+    if not stochastic:
+        disable_stochastic(m)
+    if stochastic:
+        g = torch.Generator().manual_seed(7)
+        forced = {}
+        rgb_p, ext_p = cmx_ref.drop_path_probs(spec)
+        scales = {}
+        for s in range(4):
+            for pre, probs in (("block", rgb_p), ("extra_block", ext_p)):
+                for i in range(spec.depths[s]):
+                    blk = getattr(m.backbone, f"{pre}{s + 1}")[i]
+                    p = probs[s][i]
+                    if not isinstance(blk.drop_path, DropPath):
+                        assert p == 0.0
+                        continue
+                    assert abs(blk.drop_path.drop_prob - p) < 1e-12, (pre, s, i, blk.drop_path.drop_prob, p)
+                    # exaggerate the drop probability so that at least some samples are dropped
+                    pp = 0.4
+                    sa = (torch.rand(B, generator=g) >= pp).float() / (1 - pp)
+                    sm = (torch.rand(B, generator=g) >= pp).float() / (1 - pp)
+                    forced[id(blk.drop_path)] = [sa, sm]
+                    scales[f"backbone.{pre}{s + 1}.{i}"] = torch.stack([sa, sm])
+        DropPath.forced = forced
+        dmask = (torch.rand(B, config.decoder_embed_dim, generator=g) >= 0.1).float() / 0.9
+
+        class ForcedDropout2d(nn.Module):
+            p = 0.0
+
+            def forward(self, t):
+                return t * dmask[:, :, None, None]
+        m.decode_head.dropout = ForcedDropout2d()
+        for k, v in scales.items():
+            out["dp::" + k] = v.numpy()
+        out["dropout_scale"] = dmask.numpy()
+    loss = m(rgb, x, gt)
+    loss.backward()
+    DropPath.forced = None
+    out["train_loss"] = np.float64(loss.item())
+    names = [n for n, _ in m.named_parameters()]
+    out["grad_norms"] = np.array([p.grad.double().norm().item() for _, p in m.named_parameters()])
+    out["grad_names"] = np.array(names)
+    keep = ["backbone.patch_embed1.proj.bias", "backbone.extra_block1.0.attn.sr.bias",
+            "backbone.block2.1.attn.q.bias", "backbone.block3.1.mlp.dwconv.dwconv.weight",
+            "backbone.FRMs.1.spatial_weights.mlp.2.weight", "backbone.FRMs.2.channel_weights.mlp.2.bias",
+            "backbone.FFMs.0.cross.cross_attn.kv1.weight", "backbone.FFMs.3.channel_emb.norm.weight",
+            "backbone.FFMs.1.cross.norm2.bias", "decode_head.linear_pred.weight",
+            "decode_head.linear_fuse.1.weight", "backbone.extra_norm4.weight"]
+    pd = dict(m.named_parameters())
+    for k in keep:
+        out["grad::" + k] = pd[k].grad.numpy()
+    post = m.state_dict()
+    for k in ("backbone.FFMs.0.channel_emb.channel_embed.4.running_mean",
+              "backbone.FFMs.2.channel_emb.norm.running_var",
+              "decode_head.linear_fuse.1.running_mean", "decode_head.linear_fuse.1.running_var",
+              "decode_head.linear_fuse.1.num_batches_tracked"):
+        out["post::" + k] = post[k].numpy()
+    out["meta"] = np.array([backbone, str(num_classes), str(B), str(H), str(W), str(sub), str(int(stochastic))])
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **out)
+    print(f"{name}: loss={loss.item():.6f} logits std={logits.std().item():.4f} -> {os.path.getsize(path)/1e3:.0f} kB")
+
+
+def metric_cases():
+    rng = np.random.default_rng(3)
+    out = {}
+    for i, (n_cl, shape) in enumerate([(9, (480, 640)), (5, (37, 53)), (40, (64, 64)), (9, (1, 1))]):
+        pred = rng.integers(0, n_cl, shape).astype(np.int64)
+        gt = rng.integers(0, n_cl, shape).astype(np.uint8)
+        gt[rng.random(shape) < 0.1] = 255
+        if i == 2:
+            gt[gt == 7] = 0  # an absent class -> nan IoU path
+            pred[pred == 7] = 1
+        hist, labeled, correct = ref_metric.hist_info(n_cl, pred, gt)
+        sc = ref_metric.compute_score(hist, correct, labeled)
+        out[f"c{i}_n"] = np.int64(n_cl)
+        out[f"c{i}_pred"] = pred.astype(np.uint8)
+        out[f"c{i}_gt"] = gt
+        out[f"c{i}_hist"] = hist.astype(np.int64)
+        out[f"c{i}_labeled"] = np.int64(labeled)
+        out[f"c{i}_correct"] = np.int64(correct)
+        out[f"c{i}_iou"] = np.asarray(sc[0], dtype=np.float64)
+        out[f"c{i}_scores"] = np.asarray(sc[1:], dtype=np.float64)
+    np.savez_compressed(os.path.join(HERE, "metric.npz"), **out)
+    print("metric: ok")
+
+
+if __name__ == "__main__":
+    metric_cases()
+    case("b2_small", "mit_b2", 9, 2, 64, 96)
+    case("b2_small_stochastic", "mit_b2", 9, 2, 64, 96, stochastic=True)
+    case("b0_odd", "mit_b0", 5, 1, 96, 160)
+    case("b4_small", "mit_b4", 5, 1, 64, 64)
+    case("b2_mfnet", "mit_b2", 9, 1, 480, 640, sub=8)
