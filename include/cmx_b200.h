@@ -1,0 +1,203 @@
+/* cmx_b200 — C ABI of the B200-native CMX RGB-X segmentation hot path.
+ *
+ * The reference (ynalcakan/RGBX_Semantic_Segmentation) is pure Python/PyTorch and has NO FFI of its
+ * own; the boundary a user sees is `models/builder.py::EncoderDecoder` (builder.py:14-253) and
+ * `utils/metric.py::hist_info` (metric.py:8-15).  This header is the thin C ABI *below* that
+ * boundary (last row): every entry point replaces the ATen/cuDNN/cuBLAS call(s) that
+ * the cited reference line issues.  Conventions:
+ *   - plain pointers + sizes; all pointers are DEVICE pointers unless stated; caller owns every
+ *     buffer (incl. workspaces); kernels never allocate, never synchronise, and enqueue on `stream`
+ *     (a cudaStream_t passed as void*).
+ *   - return 0 on success, <0 for argument errors, >0 = cudaError_t; message via cmx_last_error().
+ *   - activations are token-major ("NLC" == NHWC): row = b*H*W + h*W + w, channels contiguous,
+ *     `ld*` = row stride in elements.  dtype tags: CMX_BF16 = 0, CMX_F32 = 1.
+ */
+#ifndef CMX_B200_H
+#define CMX_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* cmx_last_error(void);
+int cmx_version(void);
+/* number of kernel launches issued through this library by the calling process (bench `gpu_launches`) */
+long long cmx_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * GEMM  C[M,N] = residual + row_scale[row/rows_per_sample] * act(alpha * A.B + bias)
+ * Replaces every nn.Linear / 1x1 conv / patchified conv / bmm of the path:
+ *   dual_segformer.py:68,72 (fc1, fc2) :119-135 (q, sr, kv, q@k^T, attn@v, proj) :219 (patch embed proj)
+ *   net_utils.py:79-83, 206-212, 274-279, 325-328 ; MLPDecoder.py:18, 76, 79 ; and their autograd
+ *   backward (dgrad / wgrad).
+ * A(m,k): trans_a==0 -> A[m*lda + k]  ("K-major"),  trans_a==1 -> A[k*lda + m]  ("MN-major")
+ * B(k,n): trans_b==0 -> B[n*ldb + k]  (nn.Linear weight layout [N,K]),  trans_b==1 -> B[k*ldb + n]
+ * A, B are bf16.  C dtype = c_dtype; residual dtype = r_dtype.  bias fp32[N] or NULL.
+ * batch: two-level (b1,b2) with element strides; batch1=batch2=1 for a plain GEMM.
+ * split_k>1 or accumulate!=0: C must be fp32 and is accumulated with atomic adds (caller zeroes it).
+ * impl: 0 = auto (tcgen05/TMA kernel when eligible, else generic tensor-core fallback),
+ *       1 = force generic fallback, 2 = require tcgen05 (error if not eligible).
+ */
+typedef struct CmxGemm {
+  const void* A;
+  const void* B;
+  void* C;
+  const float* bias;
+  const void* residual;
+  const float* row_scale;
+  int64_t M, N, K;
+  int64_t lda, ldb, ldc, ldr;
+  int32_t trans_a, trans_b;
+  int32_t batch1, batch2;
+  int64_t sA1, sA2, sB1, sB2, sC1, sC2;
+  int32_t c_dtype, r_dtype;
+  int32_t act;
+  float alpha;
+  int32_t accumulate;
+  int32_t split_k;
+  int32_t rows_per_sample;
+  int32_t impl;
+} CmxGemm;
+int cmx_gemm(const CmxGemm* g, void* stream);
+/* which implementation cmx_gemm would pick: 2 = tcgen05, 1 = fallback */
+int cmx_gemm_which(const CmxGemm* g);
+
+/* ---- LayerNorm (dual_segformer.py:177-178, 123, 221-223, 382-383; net_utils.py:279-280) ------ */
+int cmx_layernorm_fwd(const void* x, int x_dtype, int64_t ldx, const float* gamma, const float* beta, float eps,
+                      void* y, int y_dtype, int64_t ldy, float* mean, float* rstd, int64_t M, int C, void* stream);
+/* dx = dres + LN'(dy + dy2);  dx_bf = bf16(dx * scale[row / rows_per_sample]) (optional);
+ * dgamma/dbeta (fp32[C]) are ACCUMULATED (atomic). dy_dtype applies to dy; dy2 is bf16; dres fp32. */
+int cmx_layernorm_bwd(const void* dy, int dy_dtype, int64_t lddy, const void* dy2, int64_t lddy2,
+                      const void* x, int x_dtype, int64_t ldx, const float* mean, const float* rstd,
+                      const float* gamma, const float* dres, int64_t lddres,
+                      void* dx, int dx_dtype, int64_t lddx, void* dx_bf, int64_t lddxbf,
+                      const float* scale, int rows_per_sample,
+                      float* dgamma, float* dbeta, int64_t M, int C, void* stream);
+
+/* ---- BatchNorm2d over token-major [M,C] (net_utils.py:318,321; MLPDecoder.py:52-53) ----------- */
+int cmx_colstats(const void* x, int x_dtype, int64_t ldx, double* sum, double* sumsq, int64_t M, int C, void* stream);
+int cmx_bn_finalize(const double* sum, const double* sumsq, int64_t count, float eps, float momentum,
+                    float* running_mean, float* running_var, int64_t* num_batches_tracked,
+                    float* mean, float* invstd, int C, void* stream);
+int cmx_bn_eval_stats(const float* running_mean, const float* running_var, float eps, float* mean, float* invstd,
+                      int C, void* stream);
+/* y = mask[b,c] * relu?( (x-mean)*invstd*gamma+beta + residual ) */
+int cmx_bn_apply(const void* x, int x_dtype, int64_t ldx, const float* mean, const float* invstd,
+                 const float* gamma, const float* beta, const void* residual, int r_dtype, int64_t ldr,
+                 int relu, const float* mask, int rows_per_sample,
+                 void* y, int y_dtype, int64_t ldy, int64_t M, int C, void* stream);
+/* backward of cmx_bn_apply in batch-statistics mode. Pass 1 accumulates sum_dy / sum_dy_xhat (double[C]). */
+int cmx_bn_bwd_reduce(const void* dy, int dy_dtype, int64_t lddy, const void* x, int x_dtype, int64_t ldx,
+                      const float* mean, const float* invstd, const float* gamma, const float* beta,
+                      const void* residual, int r_dtype, int64_t ldr,
+                      int relu, const float* mask, int rows_per_sample,
+                      double* sum_dy, double* sum_dy_xhat, int64_t M, int C, void* stream);
+/* Pass 2: dx (and dres = effective dy, optional); dgamma/dbeta accumulated into fp32[C]. */
+int cmx_bn_bwd_apply(const void* dy, int dy_dtype, int64_t lddy, const void* x, int x_dtype, int64_t ldx,
+                     const float* mean, const float* invstd, const float* gamma, const float* beta,
+                     const void* residual, int r_dtype, int64_t ldr,
+                     int relu, const float* mask, int rows_per_sample,
+                     const double* sum_dy, const double* sum_dy_xhat,
+                     void* dx, int dx_dtype, int64_t lddx, void* dres, int dres_dtype, int64_t lddres,
+                     float* dgamma, float* dbeta, int64_t M, int C, void* stream);
+
+/* ---- depthwise 3x3 (pad 1) + bias + activation on NHWC bf16 (dual_segformer.py:25-33,69-70;
+ *      net_utils.py:314-315).  w: fp32 [C,9] (== Conv2d weight [C,1,3,3]).  flip: correlate with the
+ *      180-degree rotated kernel (data-gradient).  */
+int cmx_dwconv3x3_fwd(const void* x, int64_t ldx, const float* w, const float* bias, int act, int flip,
+                      void* y, int64_t ldy, int B, int H, int W, int C, void* stream);
+/* du = dy * act'(conv(x)+b) -> bf16; dW[C,9], db[C] accumulated (fp32 atomics). */
+int cmx_dwconv3x3_bwd_pre(const void* x, int64_t ldx, const float* w, const float* bias, int act,
+                          const void* dy, int64_t lddy, void* du, int64_t lddu, float* dw, float* db,
+                          int B, int H, int W, int C, void* stream);
+
+/* ---- layout movers ---------------------------------------------------------------------------- */
+/* stage-1 OverlapPatchEmbed input: NCHW fp32 image -> bf16 im2col rows [B*Ho*Wo, kpad],
+ * column = (kh*k+kw)*Cin+ci (dual_segformer.py:219, conv k=7 s=4 p=3) */
+int cmx_im2col_nchw(const float* x, void* col, int B, int Cin, int H, int W, int k, int s, int p,
+                    int Ho, int Wo, int kpad, void* stream);
+/* NHWC bf16 -> im2col rows [B*Ho*Wo, k*k*C] (stage 2-4 patch embeds k=3 s=2 p=1; SR conv k=s=R p=0) */
+int cmx_im2col_nhwc(const void* x, int64_t ldx, void* col, int B, int H, int W, int C, int k, int s, int p,
+                    int Ho, int Wo, void* stream);
+/* adjoint of cmx_im2col_nhwc (gather form): dx[b,y,x,:] = add + sum of dcol entries */
+int cmx_col2im_nhwc(const void* dcol, const void* add, int add_dtype, int64_t ldadd, void* dx, int dx_dtype,
+                    int64_t lddx, int B, int H, int W, int C, int k, int s, int p, int Ho, int Wo, void* stream);
+/* Conv2d weight [Co,Ci,kh,kw] fp32 -> bf16 [Co,kpad] with column (kh*kw_+kw)*Ci+ci, and the adjoint
+ * (fp32 [Co,kpad] grad -> ACCUMULATED into [Co,Ci,kh,kw]) */
+int cmx_convw_pack(const float* w, void* wp, int Co, int Ci, int kh, int kw, int kpad, void* stream);
+int cmx_convw_unpack_grad(const float* gp, float* gw, int Co, int Ci, int kh, int kw, int kpad, void* stream);
+/* fp32 -> bf16 cast (weights), optionally many at once is done by the caller on a flat buffer */
+int cmx_cast_f32_bf16(const float* x, void* y, int64_t n, void* stream);
+int cmx_cast_bf16_f32(const void* x, float* y, int64_t n, void* stream);
+/* column sums of a [M,N] matrix (bias gradients): out[n] += sum_m x[m,n] */
+int cmx_colsum(const void* x, int x_dtype, int64_t ldx, float* out, int64_t M, int N, void* stream);
+/* dy *= (y > 0)   (ReLU backward, in place on bf16) */
+int cmx_relu_bwd(void* dy, int64_t lddy, const void* y, int64_t ldy, int64_t M, int N, void* stream);
+/* out = a*x + b*y elementwise on fp32 flat buffers (grad scaling) */
+int cmx_axpby_f32(float a, const float* x, float b, const float* y, float* out, int64_t n, void* stream);
+
+/* ---- softmax ---------------------------------------------------------------------------------- */
+/* row softmax of fp32 S [rows, n] (ld) -> bf16 P  (dual_segformer.py:131) and its backward
+ * dS = scale * P .* (dP - rowsum(P.*dP)) -> bf16 */
+int cmx_softmax_rows_fwd(const float* s, int64_t lds, void* p, int64_t ldp, int64_t rows, int n, void* stream);
+int cmx_softmax_rows_bwd(const void* p, int64_t ldp, const float* dp, int64_t lddp, float scale,
+                         void* ds, int64_t ldds, int64_t rows, int n, void* stream);
+/* FFM context softmax over dim -2 of [nb, d, d] fp32 (net_utils.py:207,209): P = softmax_rows-index(scale*C)
+ * writes fp32 P and bf16 P^T-free copy; backward dC = scale * P .* (dP - colsum(P.*dP)) */
+int cmx_softmax_dim2_fwd(const float* c, float scale, float* p32, void* p16, int nb, int d, void* stream);
+int cmx_softmax_dim2_bwd(const float* p32, const float* dp, float scale, void* dc16, int nb, int d, void* stream);
+
+/* ---- FRM (net_utils.py:22-30, 79-83, 147-152) ------------------------------------------------- */
+/* global avg + max pool per (b,c) of x1|x2 packed as one [B*HW, C2] matrix (C2 = 2C). y[b] = [avg(C2) | max(C2)],
+ * argmax (row index within the sample) saved for backward. */
+int cmx_pool_avgmax_fwd(const void* x, int64_t ldx, float* y, int32_t* argmax, int B, int HW, int C2, void* stream);
+/* dx[row,c] += dy_avg[b,c]/HW + (row==argmax[b,c]) * dy_max[b,c]   (dx fp32, in place) */
+int cmx_pool_avgmax_bwd(const float* dy, const int32_t* argmax, float* dx, int64_t lddx, int B, int HW, int C2, void* stream);
+/* small-M fp32 linear: y = act(x W^T + b), x [Mb,K], W [N,K]; act: 0 none, 1 relu, 3 sigmoid */
+int cmx_smallm_linear_fwd(const float* x, const float* w, const float* b, int act, float* y, int Mb, int N, int K, void* stream);
+/* backward: given dy (grad wrt y) and y: dpre = dy*act'(y); dx = dpre W ; dW += dpre^T x ; db += colsum(dpre) */
+int cmx_smallm_linear_bwd(const float* dy, const float* y, int act, const float* x, const float* w,
+                          float* dx, float* dw, float* db, float* dpre_ws, int Mb, int N, int K, void* stream);
+/* sw = sigmoid(t W2^T + b2) ([M,2], saved);  r1 = a1 + .5*(cw1[b,:]+sw1)*a2 ; r2 = a2 + .5*(cw0[b,:]+sw0)*a1
+ * a = [a1|a2] bf16 [M,2C] ; t bf16 [M,C] ; cw fp32 [B,2C] ; w2 fp32 [2,C] */
+int cmx_frm_rectify_fwd(const void* a, int64_t lda, const void* t, int64_t ldt, const float* w2, const float* b2,
+                        const float* cw, float* sw, void* r1, int64_t ldr1, void* r2, int64_t ldr2,
+                        int B, int HW, int C, void* stream);
+/* backward: dr1, dr2 fp32 [M,C] -> da fp32 [M,2C] (written), dt bf16 [M,C] (relu-masked by t>0),
+ * dcw fp32[B,2C], dw2 fp32[2,C], db2 fp32[2] ACCUMULATED */
+int cmx_frm_rectify_bwd(const float* dr1, int64_t lddr1, const float* dr2, int64_t lddr2,
+                        const void* a, int64_t lda, const void* t, int64_t ldt, const float* w2,
+                        const float* cw, const float* sw, float* da, int64_t ldda, void* dt, int64_t lddt,
+                        float* dcw, float* dw2, float* db2, int B, int HW, int C, void* stream);
+
+/* ---- decoder (MLPDecoder.py:66-77) ------------------------------------------------------------- */
+/* out[b,y,x,:] (fp32) = bias + z0[b,y,x,:] + sum_i bilinear(z_i)[b,y,x,:]  (align_corners=False) */
+int cmx_upsample_sum_fwd(const void* z0, const void* z1, const void* z2, const void* z3,
+                         int H0, int W0, int H1, int W1, int H2, int W2, int H3, int W3,
+                         const float* bias, float* out, int B, int C, void* stream);
+/* adjoint for ONE source: dz[b,yi,xi,:] = sum_{y,x} w(y,x;yi,xi) * dout[b,y,x,:]  (bf16 in, bf16 out) */
+int cmx_upsample_bwd(const void* dout, int Ho, int Wo, void* dz, int Hi, int Wi, int B, int C, void* stream);
+
+/* ---- loss / logits / metric (builder.py:233,249; evaluator.py:393; utils/metric.py:8-15) ------- */
+/* low-res logits [B,h,w,ncls] fp32 (channels-last) -> bilinear x to [H,W] -> CE(ignore) .
+ * acc[0] += sum of -log p (double), acc[1] += valid count (double). If dlogits != NULL also accumulates the
+ * UNNORMALISED gradient sum_{pixels} w * (softmax - onehot) into dlogits [B,h,w,ncls] fp32. */
+int cmx_ce_upsampled_fwd_bwd(const float* logits, const int64_t* label, int ignore_index, double* acc,
+                             float* dlogits, int B, int h, int w, int H, int W, int ncls, void* stream);
+/* loss = acc[0]/acc[1];  dlogits_out(bf16/f32) = dlogits * gscale/acc[1] */
+int cmx_ce_finalize(const double* acc, float* loss, const float* dlogits, const float* gscale,
+                    void* dlogits_out, int out_dtype, int64_t n, void* stream);
+/* low-res channels-last logits -> full-res NCHW fp32 logits (eval output of EncoderDecoder.forward) */
+int cmx_logits_upsample_nchw(const float* logits, float* out, int B, int h, int w, int H, int W, int ncls, void* stream);
+/* confusion matrix: hist[n_cl*gt+pred] += 1 for 0<=gt<n_cl (int64), stats[0]=labeled, stats[1]=correct.
+ * pred_dtype/gt_dtype: 0 = uint8, 1 = int32, 2 = int64.  */
+int cmx_confusion(const void* pred, int pred_dtype, const void* gt, int gt_dtype, int64_t n, int n_cl,
+                  int64_t* hist, int64_t* stats, void* stream);
+/* fused argmax over channel of NCHW fp32 scores [ncls,H*W] (one image) + confusion; pred_out optional (uint8) */
+int cmx_argmax_confusion(const float* scores, const void* gt, int gt_dtype, int64_t npix, int n_cl,
+                         uint8_t* pred_out, int64_t* hist, int64_t* stats, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

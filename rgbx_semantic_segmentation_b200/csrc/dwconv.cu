@@ -1,0 +1,269 @@
+// Depthwise 3x3 (pad 1) + bias + activation on channels-last bf16 — the Mix-FFN DWConv+GELU
+// (dual_segformer.py:25-33, 69-70) and the FFM ChannelEmbed DWConv+ReLU (net_utils.py:314-315),
+// computed directly in the token-major layout (no NLC<->NCHW copies).  Memory-bound: each thread
+// owns VEC channels x TW consecutive pixels of one image row and slides a 3 x (TW+2) register window,
+// 16-byte (8-byte for VEC=4) accesses, per-CTA weights staged in shared memory (tap-major).
+#include "common.cuh"
+#include "../../include/cmx_b200.h"
+#include <atomic>
+extern std::atomic<long long> g_cmx_launches;
+
+template <int ACT>
+__device__ __forceinline__ float act_f(float u) {
+  if (ACT == CMX_ACT_RELU) return fmaxf(u, 0.f);
+  if (ACT == CMX_ACT_GELU) return gelu_f(u);
+  return u;
+}
+template <int ACT>
+__device__ __forceinline__ float act_grad_f(float u) {
+  if (ACT == CMX_ACT_RELU) return u > 0.f ? 1.f : 0.f;
+  if (ACT == CMX_ACT_GELU) return gelu_grad_f(u);
+  return 1.f;
+}
+
+template <int VEC> struct VecIO;
+template <> struct VecIO<8> {
+  static __device__ __forceinline__ void ld(const bf16* p, float* f) { load8(p, f); }
+  static __device__ __forceinline__ void st(bf16* p, const float* f) { store8(p, f); }
+};
+template <> struct VecIO<4> {
+  static __device__ __forceinline__ void ld(const bf16* p, float* f) { load4(p, f); }
+  static __device__ __forceinline__ void st(bf16* p, const float* f) { store4(p, f); }
+};
+
+constexpr int DW_CG = 32;  // channel groups per CTA (threadIdx.x)
+constexpr int DW_PY = 8;   // pixel strips per CTA (threadIdx.y)
+
+// ------------------------------------------------------------------------------------------------
+// forward / data-gradient (FLIP) kernel
+// ------------------------------------------------------------------------------------------------
+template <int ACT, bool FLIP, int TW>
+__global__ void __launch_bounds__(DW_CG* DW_PY) dwconv_fwd_kernel(const bf16* __restrict__ x, long ldx, const float* __restrict__ w,
+                                                                  const float* __restrict__ bias, bf16* __restrict__ y, long ldy,
+                                                                  int B, int H, int W, int C) {
+  constexpr int VEC = 8;
+  __shared__ __align__(16) float sw[9][DW_CG * VEC];
+  __shared__ __align__(16) float sb[DW_CG * VEC];
+  const int cbase = blockIdx.x * DW_CG * VEC;
+  for (int i = threadIdx.y * DW_CG + threadIdx.x; i < 9 * DW_CG * VEC; i += DW_CG * DW_PY) {
+    const int tap = i / (DW_CG * VEC), cl = i % (DW_CG * VEC);
+    const int c = cbase + cl;
+    const int t = FLIP ? 8 - tap : tap;
+    sw[tap][cl] = c < C ? w[c * 9 + t] : 0.f;
+  }
+  for (int i = threadIdx.y * DW_CG + threadIdx.x; i < DW_CG * VEC; i += DW_CG * DW_PY) {
+    const int c = cbase + i;
+    sb[i] = (bias && c < C) ? bias[c] : 0.f;
+  }
+  __syncthreads();
+  const int cl = threadIdx.x * VEC;
+  const int c = cbase + cl;
+  if (c >= C) return;
+  const int strips_w = (W + TW - 1) / TW;
+  const long nstrips = (long)B * H * strips_w;
+  for (long s = (long)blockIdx.y * DW_PY + threadIdx.y; s < nstrips; s += (long)gridDim.y * DW_PY) {
+    const int xs = (int)(s % strips_w) * TW;
+    const long t = s / strips_w;
+    const int yy = (int)(t % H);
+    const int b = (int)(t / H);
+    float acc[TW][VEC];
+#pragma unroll
+    for (int p = 0; p < TW; p++)
+#pragma unroll
+      for (int i = 0; i < VEC; i++) acc[p][i] = sb[cl + i];
+#pragma unroll
+    for (int dy = -1; dy <= 1; dy++) {
+      const int y2 = yy + dy;
+      if (y2 < 0 || y2 >= H) continue;
+      const bf16* rowp = x + ((long)(b * H + y2) * W) * ldx + c;
+      float in[TW + 2][VEC];
+#pragma unroll
+      for (int j = 0; j < TW + 2; j++) {
+        const int x2 = xs + j - 1;
+        if (x2 >= 0 && x2 < W) VecIO<VEC>::ld(rowp + (long)x2 * ldx, in[j]);
+        else {
+#pragma unroll
+          for (int i = 0; i < VEC; i++) in[j][i] = 0.f;
+        }
+      }
+#pragma unroll
+      for (int dx = 0; dx < 3; dx++) {
+        float wv[VEC];
+#pragma unroll
+        for (int i = 0; i < VEC; i++) wv[i] = sw[(dy + 1) * 3 + dx][cl + i];
+#pragma unroll
+        for (int p = 0; p < TW; p++)
+#pragma unroll
+          for (int i = 0; i < VEC; i++) acc[p][i] = fmaf(wv[i], in[p + dx][i], acc[p][i]);
+      }
+    }
+#pragma unroll
+    for (int p = 0; p < TW; p++) {
+      const int x2 = xs + p;
+      if (x2 < W) {
+        float o[VEC];
+#pragma unroll
+        for (int i = 0; i < VEC; i++) o[i] = act_f<ACT>(acc[p][i]);
+        VecIO<VEC>::st(y + ((long)(b * H + yy) * W + x2) * ldy + c, o);
+      }
+    }
+  }
+}
+
+CMX_API int cmx_dwconv3x3_fwd(const void* x, int64_t ldx, const float* w, const float* bias, int act, int flip, void* y,
+                              int64_t ldy, int B, int H, int W, int C, void* stream) {
+  CMX_REQUIRE(C % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0, "dwconv3x3: C and ld must be multiples of 8 (C=%d)", C);
+  cudaStream_t st = (cudaStream_t)stream;
+  constexpr int TW = 4;
+  const long nstrips = (long)B * H * ((W + TW - 1) / TW);
+  if (nstrips == 0) return 0;
+  const int gx = cdiv(C, DW_CG * 8);
+  long gy = (nstrips + DW_PY - 1) / DW_PY;
+  const long cap = (148L * 16 + gx - 1) / gx;  // ~16 CTAs per SM worth of work in flight, grid-stride beyond
+  if (gy > cap) gy = cap;
+  dim3 grid(gx, (unsigned)gy), block(DW_CG, DW_PY);
+#define DW_L(ACTv, FLIPv) \
+  dwconv_fwd_kernel<ACTv, FLIPv, TW><<<grid, block, 0, st>>>((const bf16*)x, ldx, w, bias, (bf16*)y, ldy, B, H, W, C)
+  if (flip) { CMX_REQUIRE(act == CMX_ACT_NONE, "dwconv3x3: flip is for the data gradient (no activation)"); DW_L(CMX_ACT_NONE, true); }
+  else if (act == CMX_ACT_GELU) DW_L(CMX_ACT_GELU, false);
+  else if (act == CMX_ACT_RELU) DW_L(CMX_ACT_RELU, false);
+  else DW_L(CMX_ACT_NONE, false);
+#undef DW_L
+  g_cmx_launches++;
+  CMX_CHECK_LAUNCH("dwconv3x3_fwd");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward, part 1: recompute u = conv(x)+b, du = dy * act'(u) (written bf16), and reduce
+// dW[c,tap] = sum du * x(p+tap), db[c] = sum du.  VEC = 4 channels, TW = 2 pixels per thread.
+// ------------------------------------------------------------------------------------------------
+template <int ACT>
+__global__ void __launch_bounds__(DW_CG* DW_PY) dwconv_bwd_pre_kernel(const bf16* __restrict__ x, long ldx, const float* __restrict__ w,
+                                                                      const float* __restrict__ bias, const bf16* __restrict__ dy,
+                                                                      long lddy, bf16* __restrict__ du, long lddu,
+                                                                      float* __restrict__ dw, float* __restrict__ db, int B, int H,
+                                                                      int W, int C) {
+  constexpr int VEC = 4, TW = 2;
+  __shared__ __align__(16) float sw[9][DW_CG * VEC];
+  __shared__ __align__(16) float sb[DW_CG * VEC];
+  __shared__ float sacc[10][DW_CG * VEC];
+  const int cbase = blockIdx.x * DW_CG * VEC;
+  for (int i = threadIdx.y * DW_CG + threadIdx.x; i < 9 * DW_CG * VEC; i += DW_CG * DW_PY) {
+    const int tap = i / (DW_CG * VEC), cl = i % (DW_CG * VEC);
+    const int c = cbase + cl;
+    sw[tap][cl] = c < C ? w[c * 9 + tap] : 0.f;
+  }
+  for (int i = threadIdx.y * DW_CG + threadIdx.x; i < 10 * DW_CG * VEC; i += DW_CG * DW_PY) (&sacc[0][0])[i] = 0.f;
+  for (int i = threadIdx.y * DW_CG + threadIdx.x; i < DW_CG * VEC; i += DW_CG * DW_PY) {
+    const int c = cbase + i;
+    sb[i] = (bias && c < C) ? bias[c] : 0.f;
+  }
+  __syncthreads();
+  const int cl = threadIdx.x * VEC;
+  const int c = cbase + cl;
+  float gw[9][VEC], gb[VEC];
+#pragma unroll
+  for (int t = 0; t < 9; t++)
+#pragma unroll
+    for (int i = 0; i < VEC; i++) gw[t][i] = 0.f;
+#pragma unroll
+  for (int i = 0; i < VEC; i++) gb[i] = 0.f;
+
+  if (c < C) {
+    const int strips_w = (W + TW - 1) / TW;
+    const long nstrips = (long)B * H * strips_w;
+    for (long s = (long)blockIdx.y * DW_PY + threadIdx.y; s < nstrips; s += (long)gridDim.y * DW_PY) {
+      const int xs = (int)(s % strips_w) * TW;
+      const long t = s / strips_w;
+      const int yy = (int)(t % H);
+      const int b = (int)(t / H);
+      float in[3][TW + 2][VEC];
+      float acc[TW][VEC];
+#pragma unroll
+      for (int p = 0; p < TW; p++)
+#pragma unroll
+        for (int i = 0; i < VEC; i++) acc[p][i] = sb[cl + i];
+#pragma unroll
+      for (int r = 0; r < 3; r++) {
+        const int y2 = yy + r - 1;
+        const bool rok = (y2 >= 0 && y2 < H);
+        const bf16* rowp = x + ((long)(b * H + (rok ? y2 : 0)) * W) * ldx + c;
+#pragma unroll
+        for (int j = 0; j < TW + 2; j++) {
+          const int x2 = xs + j - 1;
+          if (rok && x2 >= 0 && x2 < W) VecIO<VEC>::ld(rowp + (long)x2 * ldx, in[r][j]);
+          else {
+#pragma unroll
+            for (int i = 0; i < VEC; i++) in[r][j][i] = 0.f;
+          }
+        }
+#pragma unroll
+        for (int dx = 0; dx < 3; dx++)
+#pragma unroll
+          for (int p = 0; p < TW; p++)
+#pragma unroll
+            for (int i = 0; i < VEC; i++) acc[p][i] = fmaf(sw[r * 3 + dx][cl + i], in[r][p + dx][i], acc[p][i]);
+      }
+#pragma unroll
+      for (int p = 0; p < TW; p++) {
+        const int x2 = xs + p;
+        if (x2 < W) {
+          const long row = (long)(b * H + yy) * W + x2;
+          float g[VEC];
+          VecIO<VEC>::ld(dy + row * lddy + c, g);
+#pragma unroll
+          for (int i = 0; i < VEC; i++) {
+            g[i] *= act_grad_f<ACT>(acc[p][i]);
+            gb[i] += g[i];
+          }
+          VecIO<VEC>::st(du + row * lddu + c, g);
+#pragma unroll
+          for (int r = 0; r < 3; r++)
+#pragma unroll
+            for (int dx = 0; dx < 3; dx++)
+#pragma unroll
+              for (int i = 0; i < VEC; i++) gw[r * 3 + dx][i] = fmaf(g[i], in[r][p + dx][i], gw[r * 3 + dx][i]);
+        }
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < 9; t++)
+#pragma unroll
+      for (int i = 0; i < VEC; i++) atomicAdd(&sacc[t][cl + i], gw[t][i]);
+#pragma unroll
+    for (int i = 0; i < VEC; i++) atomicAdd(&sacc[9][cl + i], gb[i]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.y * DW_CG + threadIdx.x; i < 10 * DW_CG * VEC; i += DW_CG * DW_PY) {
+    const int t = i / (DW_CG * VEC), l = i % (DW_CG * VEC);
+    const int cc = cbase + l;
+    if (cc < C) {
+      if (t < 9) atomicAdd(dw + cc * 9 + t, sacc[t][l]);
+      else if (db) atomicAdd(db + cc, sacc[9][l]);
+    }
+  }
+}
+
+CMX_API int cmx_dwconv3x3_bwd_pre(const void* x, int64_t ldx, const float* w, const float* bias, int act, const void* dy,
+                                  int64_t lddy, void* du, int64_t lddu, float* dw, float* db, int B, int H, int W, int C,
+                                  void* stream) {
+  CMX_REQUIRE(C % 4 == 0 && ldx % 4 == 0 && lddy % 4 == 0 && lddu % 4 == 0, "dwconv3x3_bwd_pre: C/ld %% 4");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long nstrips = (long)B * H * ((W + 1) / 2);
+  if (nstrips == 0) return 0;
+  const int gx = cdiv(C, DW_CG * 4);
+  long gy = (nstrips + DW_PY - 1) / DW_PY;
+  const long cap = (148L * 8 + gx - 1) / gx;
+  if (gy > cap) gy = cap;
+  dim3 grid(gx, (unsigned)gy), block(DW_CG, DW_PY);
+#define DW_B(ACTv) \
+  dwconv_bwd_pre_kernel<ACTv><<<grid, block, 0, st>>>((const bf16*)x, ldx, w, bias, (const bf16*)dy, lddy, (bf16*)du, lddu, dw, db, B, H, W, C)
+  if (act == CMX_ACT_GELU) DW_B(CMX_ACT_GELU);
+  else if (act == CMX_ACT_RELU) DW_B(CMX_ACT_RELU);
+  else DW_B(CMX_ACT_NONE);
+#undef DW_B
+  g_cmx_launches++;
+  CMX_CHECK_LAUNCH("dwconv3x3_bwd_pre");
+  return 0;
+}

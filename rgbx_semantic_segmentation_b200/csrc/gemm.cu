@@ -1,0 +1,563 @@
+// GEMM for the CMX hot path on sm_100a.
+//
+//  * gemm_tc_kernel  — tcgen05.mma (UMMA 128xBNx16, bf16 -> fp32 in TMEM), operands staged by TMA
+//    (cp.async.bulk.tensor, SWIZZLE_128B) through an mbarrier ring, warp-specialised:
+//    warp 0 = TMA producer, warp 1 = MMA issuer + TMEM allocator, warps 2-5 = epilogue
+//    (tcgen05.ld 32x32b -> bias/act/DropPath-scale/residual -> vectorised stores or fp32 red.add).
+//    Operands may be K-major or MN-major (dgrad uses B MN-major = the untouched [N,K] weight,
+//    wgrad uses A and B MN-major = activations as stored), so no transposed copies exist in HBM.
+//  * gemm_wmma_kernel — generic strided/batched tensor-core fallback (mma.sync via WMMA) for the
+//    shapes the TMA path cannot take (tiny N such as num_classes, odd strides, batched views).
+#include "common.cuh"
+#include "../../include/cmx_b200.h"
+#include <cuda.h>
+#include <mma.h>
+#include <atomic>
+#include <stdlib.h>
+#include <string.h>
+
+extern std::atomic<long long> g_cmx_launches;
+
+// ------------------------------------------------------------------------------------------------
+// Epilogue shared by both kernels
+// ------------------------------------------------------------------------------------------------
+struct Epi {
+  void* C;
+  long ldc;
+  const float* bias;
+  const void* res;
+  long ldr;
+  const float* row_scale;
+  int rows_per_sample;
+  int c_dtype, r_dtype, act, atomic;
+  float alpha;
+  long M, N;
+};
+
+__device__ __forceinline__ float epi_scalar(const Epi& e, long row, long col, float acc) {
+  float v = acc * e.alpha;
+  if (e.bias) v += e.bias[col];
+  if (e.act == CMX_ACT_RELU) v = fmaxf(v, 0.f);
+  else if (e.act == CMX_ACT_GELU) v = gelu_f(v);
+  if (e.row_scale) v *= e.row_scale[row / e.rows_per_sample];
+  if (e.res) {
+    if (e.r_dtype == CMX_F32) v += reinterpret_cast<const float*>(e.res)[row * e.ldr + col];
+    else v += __bfloat162float(reinterpret_cast<const bf16*>(e.res)[row * e.ldr + col]);
+  }
+  return v;
+}
+__device__ __forceinline__ void epi_store_scalar(const Epi& e, long row, long col, float acc) {
+  float v = epi_scalar(e, row, col, acc);
+  if (e.c_dtype == CMX_F32) {
+    float* p = reinterpret_cast<float*>(e.C) + row * e.ldc + col;
+    if (e.atomic) atomicAdd(p, v); else *p = v;
+  } else {
+    reinterpret_cast<bf16*>(e.C)[row * e.ldc + col] = __float2bfloat16(v);
+  }
+}
+// 8 consecutive columns, all in range, 16B-aligned addresses (checked on the host)
+__device__ __forceinline__ void epi_store_vec8(const Epi& e, long row, long col, float* v) {
+  float rs = e.row_scale ? e.row_scale[row / e.rows_per_sample] : 1.f;
+  float b[8];
+  if (e.bias) load8(e.bias + col, b);
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    float t = v[i] * e.alpha;
+    if (e.bias) t += b[i];
+    if (e.act == CMX_ACT_RELU) t = fmaxf(t, 0.f);
+    else if (e.act == CMX_ACT_GELU) t = gelu_f(t);
+    v[i] = t * rs;
+  }
+  if (e.res) {
+    float r[8];
+    if (e.r_dtype == CMX_F32) load8(reinterpret_cast<const float*>(e.res) + row * e.ldr + col, r);
+    else load8(reinterpret_cast<const bf16*>(e.res) + row * e.ldr + col, r);
+#pragma unroll
+    for (int i = 0; i < 8; i++) v[i] += r[i];
+  }
+  if (e.c_dtype == CMX_F32) {
+    float* p = reinterpret_cast<float*>(e.C) + row * e.ldc + col;
+    if (e.atomic) {
+      atomicAdd(reinterpret_cast<float4*>(p), make_float4(v[0], v[1], v[2], v[3]));
+      atomicAdd(reinterpret_cast<float4*>(p + 4), make_float4(v[4], v[5], v[6], v[7]));
+    } else {
+      store8(p, v);
+    }
+  } else {
+    store8(reinterpret_cast<bf16*>(e.C) + row * e.ldc + col, v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers (mbarrier / TMA / tcgen05)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  int spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) break;
+    if (++spins > (1 << 22)) __trap();  // watchdog: turn a protocol bug into an error, not a hang
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptor, SWIZZLE_128B, sm_100 version field = 1
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
+         (1ull << 46) | (2ull << 61);
+}
+
+// ------------------------------------------------------------------------------------------------
+// tcgen05 GEMM kernel.  One 128 x BN output tile per CTA (grid.x = N tiles, grid.y = M tiles,
+// grid.z = split-K slices).  BK = 64 bf16 = one 128-byte swizzle atom.
+// ------------------------------------------------------------------------------------------------
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 64;
+constexpr int TC_THREADS = 192;
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                            const __grid_constant__ CUtensorMap tmB, Epi epi,
+                                                            int k_blocks_total, int k_blocks_per_split, int stages) {
+  extern __shared__ uint8_t smem_raw[];
+  constexpr uint32_t A_BYTES = TC_BM * TC_BK * 2;
+  constexpr uint32_t B_BYTES = BN * TC_BK * 2;
+  constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr uint32_t TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + stages * STAGE_BYTES;  // full[stages], empty[stages], tmem_full, tmem_ptr
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (stages + s); };
+  const uint32_t tmem_full_bar = bar_base + 16u * stages;
+  const uint32_t tmem_ptr_addr = tmem_full_bar + 8u;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BN;
+  const int m0 = blockIdx.y * TC_BM;
+  const int kb_begin = blockIdx.z * k_blocks_per_split;
+  int kb_end = kb_begin + k_blocks_per_split;
+  if (kb_end > k_blocks_total) kb_end = k_blocks_total;
+  const int nkb = kb_end - kb_begin;  // >= 1 by construction on the host
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+    for (int s = 0; s < stages; s++) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr));
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      for (int i = 0; i < nkb; i++) {
+        const int s = i % stages;
+        const uint32_t ph = (uint32_t)(i / stages) & 1u;
+        mbar_wait(empty_bar(s), ph ^ 1u);
+        mbar_expect_tx(full_bar(s), STAGE_BYTES);
+        const uint32_t sa = smem_base + s * STAGE_BYTES;
+        const uint32_t sb = sa + A_BYTES;
+        const int k = (kb_begin + i) * TC_BK;
+        if (!A_MN) {
+          tma_load_2d(sa, &tmA, full_bar(s), k, m0);
+        } else {
+#pragma unroll
+          for (int c = 0; c < TC_BM / 64; c++) tma_load_2d(sa + c * 8192, &tmA, full_bar(s), m0 + c * 64, k);
+        }
+        if (!B_MN) {
+          tma_load_2d(sb, &tmB, full_bar(s), k, n0);
+        } else {
+#pragma unroll
+          for (int c = 0; c < BN / 64; c++) tma_load_2d(sb + c * 8192, &tmB, full_bar(s), n0 + c * 64, k);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+                                 ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      for (int i = 0; i < nkb; i++) {
+        const int s = i % stages;
+        const uint32_t ph = (uint32_t)(i / stages) & 1u;
+        mbar_wait(full_bar(s), ph);
+        tc_fence_after();
+        const uint32_t sa = smem_base + s * STAGE_BYTES;
+        const uint32_t sb = sa + A_BYTES;
+#pragma unroll
+        for (int k = 0; k < TC_BK / 16; k++) {
+          // K-major: 16 bf16 = 32 B inside the 128 B swizzle row; MN-major: 16 K-rows of 128 B = 2048 B
+          const uint64_t da = A_MN ? umma_desc(sa + k * 2048, 8192, 1024) : umma_desc(sa + k * 32, 16, 1024);
+          const uint64_t db = B_MN ? umma_desc(sb + k * 2048, 8192, 1024) : umma_desc(sb + k * 32, 16, 1024);
+          tc_mma_bf16(tmem_base, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
+        }
+        tc_commit(empty_bar(s));  // frees the smem slot once the MMAs that read it retire
+      }
+      tc_commit(tmem_full_bar);
+    }
+  } else {
+    // ================= epilogue: warps 2..5, TMEM lane quarter = warp % 4 =================
+    const int q = warp & 3;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const long row = (long)m0 + q * 32 + lane;
+    const bool row_ok = row < epi.M;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; c++) {
+      uint32_t r[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
+      tmem_wait_ld();
+      if (row_ok) {
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
+          const long col = (long)n0 + c * 32 + g * 8;
+          if (col < epi.N) {
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) v[j] = __uint_as_float(r[g * 8 + j]);
+            epi_store_vec8(epi, row, col, v);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Generic fallback: 64x64x32 tiles, 4 warps, WMMA bf16 16x16x16, arbitrary strides + 2-level batch.
+// ------------------------------------------------------------------------------------------------
+struct GenArgs {
+  const bf16* A;
+  const bf16* B;
+  long sAm, sAk, sBk, sBn;  // element strides of A(m,k) and B(k,n)
+  long K;
+  int batch2;
+  long sA1, sA2, sB1, sB2, sC1, sC2;
+  long k_per_split;
+};
+
+constexpr int GB = 64, GK = 32;
+
+__global__ void __launch_bounds__(128) gemm_wmma_kernel(GenArgs g, Epi epi) {
+  using namespace nvcuda;
+  __shared__ __align__(32) bf16 As[GB][GK + 8];
+  __shared__ __align__(32) bf16 Bs[GK][GB + 8];
+  __shared__ __align__(32) float Cs[GB][GB + 4];
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int wm = warp >> 1, wn = warp & 1;
+  const long m0 = (long)blockIdx.y * GB, n0 = (long)blockIdx.x * GB;
+  int zb = blockIdx.z;
+  const int nsplit = (int)((g.K + g.k_per_split - 1) / g.k_per_split);
+  const int split = zb % nsplit;
+  zb /= nsplit;
+  const int b2 = zb % g.batch2, b1 = zb / g.batch2;
+  const bf16* A = g.A + b1 * g.sA1 + b2 * g.sA2;
+  const bf16* B = g.B + b1 * g.sB1 + b2 * g.sB2;
+  Epi e = epi;
+  if (e.c_dtype == CMX_F32) e.C = reinterpret_cast<float*>(e.C) + b1 * g.sC1 + b2 * g.sC2;
+  else e.C = reinterpret_cast<bf16*>(e.C) + b1 * g.sC1 + b2 * g.sC2;
+
+  wmma::fragment<wmma::accumulator, 16, 16, 16, float> acc[2][2];
+#pragma unroll
+  for (int i = 0; i < 2; i++)
+#pragma unroll
+    for (int j = 0; j < 2; j++) wmma::fill_fragment(acc[i][j], 0.f);
+
+  const long k_begin = (long)split * g.k_per_split;
+  long k_end = k_begin + g.k_per_split;
+  if (k_end > g.K) k_end = g.K;
+  const bool a_kfast = (g.sAk == 1);  // iterate the contiguous index fastest for coalescing
+  const bool b_nfast = (g.sBn == 1);
+  const bf16 zero = __float2bfloat16(0.f);
+
+  for (long k0 = k_begin; k0 < k_end; k0 += GK) {
+    for (int i = tid; i < GB * GK; i += 128) {
+      int m, k;
+      if (a_kfast) { m = i / GK; k = i % GK; } else { k = i / GB; m = i % GB; }
+      const long gm = m0 + m, gk = k0 + k;
+      As[m][k] = (gm < epi.M && gk < k_end) ? A[gm * g.sAm + gk * g.sAk] : zero;
+    }
+    for (int i = tid; i < GK * GB; i += 128) {
+      int k, n;
+      if (b_nfast) { k = i / GB; n = i % GB; } else { n = i / GK; k = i % GK; }
+      const long gk = k0 + k, gn = n0 + n;
+      Bs[k][n] = (gn < epi.N && gk < k_end) ? B[gk * g.sBk + gn * g.sBn] : zero;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < GK; kk += 16) {
+      wmma::fragment<wmma::matrix_a, 16, 16, 16, bf16, wmma::row_major> fa[2];
+      wmma::fragment<wmma::matrix_b, 16, 16, 16, bf16, wmma::row_major> fb[2];
+#pragma unroll
+      for (int i = 0; i < 2; i++) wmma::load_matrix_sync(fa[i], &As[wm * 32 + i * 16][kk], GK + 8);
+#pragma unroll
+      for (int j = 0; j < 2; j++) wmma::load_matrix_sync(fb[j], &Bs[kk][wn * 32 + j * 16], GB + 8);
+#pragma unroll
+      for (int i = 0; i < 2; i++)
+#pragma unroll
+        for (int j = 0; j < 2; j++) wmma::mma_sync(acc[i][j], fa[i], fb[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 2; i++)
+#pragma unroll
+    for (int j = 0; j < 2; j++)
+      wmma::store_matrix_sync(&Cs[wm * 32 + i * 16][wn * 32 + j * 16], acc[i][j], GB + 4, wmma::mem_row_major);
+  __syncthreads();
+  for (int i = tid; i < GB * GB; i += 128) {
+    const int m = i / GB, n = i % GB;
+    const long gm = m0 + m, gn = n0 + n;
+    if (gm < epi.M && gn < epi.N) epi_store_scalar(e, gm, gn, Cs[m][n]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess) return nullptr;
+    fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+// 2-D bf16 tensor map: dim0 = contiguous extent, dim1 = strided extent (row stride ld elements)
+static int make_map(CUtensorMap* tm, const void* ptr, uint64_t dim0, uint64_t dim1, uint64_t ld, uint32_t box0,
+                    uint32_t box1) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) CMX_FAIL(-2, "cuTensorMapEncodeTiled unavailable");
+  cuuint64_t dims[2] = {dim0, dim1};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {box0, box1};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) CMX_FAIL(-3, "cuTensorMapEncodeTiled failed (%d): dims %llu x %llu ld %llu box %u x %u", (int)r,
+                                  (unsigned long long)dim0, (unsigned long long)dim1, (unsigned long long)ld, box0, box1);
+  return 0;
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+static bool tc_eligible(const CmxGemm* g) {
+  if (g->batch1 != 1 || g->batch2 != 1) return false;
+  if (g->M < 1 || g->N < 8 || g->K < 8) return false;
+  if ((g->N % 8) || (g->lda % 8) || (g->ldb % 8) || (g->ldc % 8)) return false;
+  if (!aligned16(g->A) || !aligned16(g->B) || !aligned16(g->C)) return false;
+  if (g->residual && ((g->ldr % 8) || !aligned16(g->residual))) return false;
+  if (g->bias && !aligned16(g->bias)) return false;
+  if (g->trans_a && !g->trans_b) return false;                       // (MN, K) combination not instantiated
+  if (!g->trans_a && (g->K % 8)) return false;                       // K-major rows: 16 B multiple
+  if (g->trans_a && (g->M % 8)) return false;
+  if (g->trans_b && (g->N % 8)) return false;
+  if (!g->trans_b && (g->K % 8)) return false;
+  if ((g->split_k > 1 || g->accumulate) && g->c_dtype != CMX_F32) return false;
+  return true;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+static int launch_tc(const CmxGemm* g, const Epi& epi, cudaStream_t st) {
+  CUtensorMap tmA, tmB;
+  int rc;
+  if (!A_MN) rc = make_map(&tmA, g->A, g->K, g->M, g->lda, TC_BK, TC_BM);
+  else rc = make_map(&tmA, g->A, g->M, g->K, g->lda, 64, TC_BK);
+  if (rc) return rc;
+  if (!B_MN) rc = make_map(&tmB, g->B, g->K, g->N, g->ldb, TC_BK, BN);
+  else rc = make_map(&tmB, g->B, g->N, g->K, g->ldb, 64, TC_BK);
+  if (rc) return rc;
+  const int kb_total = cdiv(g->K, TC_BK);
+  int split = g->split_k > 1 ? g->split_k : 1;
+  if (split > kb_total) split = kb_total;
+  int kb_per = cdiv(kb_total, split);
+  split = cdiv(kb_total, kb_per);  // no empty slices
+  constexpr int STAGE_BYTES = (TC_BM + BN) * TC_BK * 2;
+  int max_stages = (200 * 1024) / STAGE_BYTES;
+  if (max_stages > 6) max_stages = 6;
+  int stages = kb_per < max_stages ? kb_per : max_stages;
+  if (stages < 1) stages = 1;
+  const size_t smem = (size_t)stages * STAGE_BYTES + 1024 + 16 * stages + 64;
+  static bool attr_done = false;
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN>;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) CMX_FAIL((int)e, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_done = true;
+  }
+  Epi e2 = epi;
+  e2.atomic = (split > 1 || g->accumulate) ? 1 : 0;
+  dim3 grid(cdiv(g->N, BN), cdiv(g->M, TC_BM), split);
+  kern<<<grid, TC_THREADS, smem, st>>>(tmA, tmB, e2, kb_total, kb_per, stages);
+  g_cmx_launches++;
+  CMX_CHECK_LAUNCH("gemm_tc_kernel");
+  return 0;
+}
+
+static int pick_bn(const CmxGemm* g) {
+  const long N = g->N;
+  if (g->trans_b) {  // MN-major B tiles are built from 64-wide chunks
+    if (N <= 64) return 64;
+    if (N <= 128) return 128;
+    if (N % 256 == 0 || N > 512) return 256;
+    return 128;
+  }
+  if (N <= 64) return 64;
+  if (N <= 128) return 128;
+  if (N % 160 == 0 && N % 256 != 0) return 160;
+  return 256;
+}
+
+static int dispatch_tc(const CmxGemm* g, const Epi& epi, cudaStream_t st) {
+  const int bn = pick_bn(g);
+  const bool a = g->trans_a != 0, b = g->trans_b != 0;
+#define TC_CASE(BNv)                                                     \
+  if (bn == BNv) {                                                       \
+    if (!a && !b) return launch_tc<BNv, false, false>(g, epi, st);       \
+    if (!a && b) return launch_tc<BNv, false, true>(g, epi, st);         \
+    return launch_tc<BNv, true, true>(g, epi, st);                       \
+  }
+  TC_CASE(64)
+  TC_CASE(128)
+  TC_CASE(256)
+#undef TC_CASE
+  if (bn == 160) return launch_tc<160, false, false>(g, epi, st);
+  CMX_FAIL(-4, "no tcgen05 instantiation for BN=%d", bn);
+}
+
+static int force_impl_env() {
+  static int v = -1;
+  if (v < 0) {
+    const char* s = getenv("CMX_GEMM_IMPL");
+    v = 0;
+    if (s && !strcmp(s, "fallback")) v = 1;
+    if (s && !strcmp(s, "tc")) v = 2;
+  }
+  return v;
+}
+
+CMX_API int cmx_gemm_which(const CmxGemm* g) {
+  int impl = g->impl ? g->impl : force_impl_env();
+  if (impl == 1) return 1;
+  return tc_eligible(g) ? 2 : 1;
+}
+
+CMX_API int cmx_gemm(const CmxGemm* g, void* stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  CMX_REQUIRE(g && g->A && g->B && g->C, "cmx_gemm: null operand");
+  CMX_REQUIRE(g->M > 0 && g->N > 0 && g->K > 0, "cmx_gemm: empty problem %ld x %ld x %ld", (long)g->M, (long)g->N, (long)g->K);
+  CMX_REQUIRE(g->batch1 >= 1 && g->batch2 >= 1, "cmx_gemm: bad batch");
+  CMX_REQUIRE(!((g->split_k > 1 || g->accumulate) && g->c_dtype != CMX_F32), "cmx_gemm: split-K/accumulate needs fp32 C");
+  CMX_REQUIRE(!(g->row_scale && g->rows_per_sample <= 0), "cmx_gemm: row_scale needs rows_per_sample");
+  Epi epi;
+  epi.C = g->C; epi.ldc = g->ldc; epi.bias = g->bias; epi.res = g->residual; epi.ldr = g->ldr;
+  epi.row_scale = g->row_scale; epi.rows_per_sample = g->rows_per_sample > 0 ? g->rows_per_sample : 1;
+  epi.c_dtype = g->c_dtype; epi.r_dtype = g->r_dtype; epi.act = g->act;
+  epi.atomic = (g->split_k > 1 || g->accumulate) ? 1 : 0;
+  epi.alpha = g->alpha; epi.M = g->M; epi.N = g->N;
+
+  int impl = g->impl ? g->impl : force_impl_env();
+  const bool elig = tc_eligible(g);
+  if (impl == 2 && !elig) CMX_FAIL(-5, "cmx_gemm: tcgen05 path required but problem not eligible");
+  if (impl != 1 && elig) return dispatch_tc(g, epi, st);
+
+  GenArgs a;
+  a.A = reinterpret_cast<const bf16*>(g->A);
+  a.B = reinterpret_cast<const bf16*>(g->B);
+  a.sAm = g->trans_a ? 1 : g->lda; a.sAk = g->trans_a ? g->lda : 1;
+  a.sBk = g->trans_b ? g->ldb : 1; a.sBn = g->trans_b ? 1 : g->ldb;
+  a.K = g->K; a.batch2 = g->batch2;
+  a.sA1 = g->sA1; a.sA2 = g->sA2; a.sB1 = g->sB1; a.sB2 = g->sB2; a.sC1 = g->sC1; a.sC2 = g->sC2;
+  int split = g->split_k > 1 ? g->split_k : 1;
+  long kper = ((g->K + split - 1) / split + GK - 1) / GK * GK;
+  a.k_per_split = kper;
+  split = (int)((g->K + kper - 1) / kper);
+  epi.atomic = (split > 1 || g->accumulate) ? 1 : 0;
+  dim3 grid(cdiv(g->N, GB), cdiv(g->M, GB), (unsigned)(g->batch1 * g->batch2 * split));
+  CMX_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "cmx_gemm fallback: grid too large");
+  gemm_wmma_kernel<<<grid, 128, 0, st>>>(a, epi);
+  g_cmx_launches++;
+  CMX_CHECK_LAUNCH("gemm_wmma_kernel");
+  return 0;
+}

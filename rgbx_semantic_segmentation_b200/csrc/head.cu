@@ -1,0 +1,406 @@
+// Decoder-side streaming kernels: fused bilinear-upsample + sum of the four per-stage embeddings
+// (MLPDecoder.py:66-77 with linear_fuse applied per stage at native resolution — the 2048-channel
+// concat is never materialised), its adjoint, the single-pass upsample x4 + cross-entropy loss with
+// in-kernel gradient scatter (builder.py:233,249), eval logits upsample, and the confusion matrix /
+// argmax metric (utils/metric.py:8-15).
+#include "common.cuh"
+#include "../../include/cmx_b200.h"
+#include <atomic>
+extern std::atomic<long long> g_cmx_launches;
+
+#define LAUNCH_DONE(name)      \
+  do {                         \
+    g_cmx_launches++;          \
+    CMX_CHECK_LAUNCH(name);    \
+    return 0;                  \
+  } while (0)
+
+// ---- out = bias + z0 + sum_i bilinear(z_i) ---------------------------------------------------------------
+struct UpSrc {
+  const bf16* z;
+  int H, W;
+  float sh, sw;  // in/out scale (fp32, as PyTorch computes it)
+};
+__global__ void __launch_bounds__(256) upsample_sum_kernel(const bf16* __restrict__ z0, UpSrc s1, UpSrc s2, UpSrc s3,
+                                                           const float* __restrict__ bias, float* __restrict__ out, int B, int H0,
+                                                           int W0, int C) {
+  const int c8 = C >> 3;
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long total = (long)B * H0 * W0 * c8;
+  if (idx >= total) return;
+  const int c = (int)(idx % c8) * 8;
+  const long pix = idx / c8;
+  const int x = (int)(pix % W0);
+  const int y = (int)((pix / W0) % H0);
+  const int b = (int)(pix / ((long)W0 * H0));
+  float acc[8];
+  if (bias) load8(bias + c, acc);
+  else {
+#pragma unroll
+    for (int i = 0; i < 8; i++) acc[i] = 0.f;
+  }
+  {
+    float v[8];
+    load8(z0 + pix * C + c, v);
+#pragma unroll
+    for (int i = 0; i < 8; i++) acc[i] += v[i];
+  }
+  const UpSrc srcs[3] = {s1, s2, s3};
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    const UpSrc& s = srcs[k];
+    if (!s.z) continue;
+    int y0, y1, x0, x1;
+    float ly, lx;
+    bilin_src(y, s.sh, s.H, y0, y1, ly);
+    bilin_src(x, s.sw, s.W, x0, x1, lx);
+    const bf16* base = s.z + (long)b * s.H * s.W * C + c;
+    float v00[8], v01[8], v10[8], v11[8];
+    load8(base + ((long)y0 * s.W + x0) * C, v00);
+    load8(base + ((long)y0 * s.W + x1) * C, v01);
+    load8(base + ((long)y1 * s.W + x0) * C, v10);
+    load8(base + ((long)y1 * s.W + x1) * C, v11);
+    const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+#pragma unroll
+    for (int i = 0; i < 8; i++) acc[i] += w00 * v00[i] + w01 * v01[i] + w10 * v10[i] + w11 * v11[i];
+  }
+  store8(out + pix * C + c, acc);
+}
+CMX_API int cmx_upsample_sum_fwd(const void* z0, const void* z1, const void* z2, const void* z3, int H0, int W0, int H1, int W1,
+                                 int H2, int W2, int H3, int W3, const float* bias, float* out, int B, int C, void* stream) {
+  CMX_REQUIRE(C % 8 == 0, "upsample_sum: C %% 8");
+  const long total = (long)B * H0 * W0 * (C >> 3);
+  if (total == 0) return 0;
+  UpSrc s1{(const bf16*)z1, H1, W1, (float)H1 / (float)H0, (float)W1 / (float)W0};
+  UpSrc s2{(const bf16*)z2, H2, W2, (float)H2 / (float)H0, (float)W2 / (float)W0};
+  UpSrc s3{(const bf16*)z3, H3, W3, (float)H3 / (float)H0, (float)W3 / (float)W0};
+  upsample_sum_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)z0, s1, s2, s3, bias, out, B, H0, W0, C);
+  LAUNCH_DONE("upsample_sum_fwd");
+}
+
+// ---- adjoint of one bilinear source (gather over the output pixels whose stencil touches (yi,xi)) -------
+__global__ void __launch_bounds__(256) upsample_bwd_kernel(const bf16* __restrict__ dout, int Ho, int Wo, bf16* __restrict__ dz, int Hi,
+                                                           int Wi, int B, int C, float sh, float sw) {
+  const int c8 = C >> 3;
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long total = (long)B * Hi * Wi * c8;
+  if (idx >= total) return;
+  const int c = (int)(idx % c8) * 8;
+  const long pix = idx / c8;
+  const int xi = (int)(pix % Wi);
+  const int yi = (int)((pix / Wi) % Hi);
+  const int b = (int)(pix / ((long)Wi * Hi));
+  // candidate output range: src = (dst+0.5)*s-0.5 in (yi-1, yi+1)  =>  dst in ((yi-0.5)/s-0.5, (yi+1.5)/s-0.5), +-1 slack
+  const float rh = 1.f / sh, rw = 1.f / sw;
+  int ylo = (int)floorf((yi - 0.5f) * rh - 0.5f) - 1, yhi = (int)ceilf((yi + 1.5f) * rh - 0.5f) + 1;
+  int xlo = (int)floorf((xi - 0.5f) * rw - 0.5f) - 1, xhi = (int)ceilf((xi + 1.5f) * rw - 0.5f) + 1;
+  if (ylo < 0) ylo = 0;
+  if (xlo < 0) xlo = 0;
+  if (yhi > Ho - 1) yhi = Ho - 1;
+  if (xhi > Wo - 1) xhi = Wo - 1;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) acc[i] = 0.f;
+  for (int y = ylo; y <= yhi; y++) {
+    int y0, y1;
+    float ly;
+    bilin_src(y, sh, Hi, y0, y1, ly);
+    const float wy = (y0 == yi ? 1.f - ly : 0.f) + (y1 == yi ? ly : 0.f);
+    if (wy == 0.f) continue;
+    for (int x = xlo; x <= xhi; x++) {
+      int x0, x1;
+      float lx;
+      bilin_src(x, sw, Wi, x0, x1, lx);
+      const float wx = (x0 == xi ? 1.f - lx : 0.f) + (x1 == xi ? lx : 0.f);
+      if (wx == 0.f) continue;
+      float v[8];
+      load8(dout + (((long)b * Ho + y) * Wo + x) * C + c, v);
+      const float w = wy * wx;
+#pragma unroll
+      for (int i = 0; i < 8; i++) acc[i] = fmaf(w, v[i], acc[i]);
+    }
+  }
+  store8(dz + pix * C + c, acc);
+}
+CMX_API int cmx_upsample_bwd(const void* dout, int Ho, int Wo, void* dz, int Hi, int Wi, int B, int C, void* stream) {
+  CMX_REQUIRE(C % 8 == 0, "upsample_bwd: C %% 8");
+  const long total = (long)B * Hi * Wi * (C >> 3);
+  if (total == 0) return 0;
+  upsample_bwd_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)dout, Ho, Wo, (bf16*)dz, Hi, Wi, B, C,
+                                                                         (float)Hi / (float)Ho, (float)Wi / (float)Wo);
+  LAUNCH_DONE("upsample_bwd");
+}
+
+// ---- fused bilinear upsample + cross entropy (+ gradient scatter) ----------------------------------------
+// CTA = 32 x 8 threads covering a 32 x 8 full-resolution tile.  The low-res window the tile touches is
+// staged in shared memory (logits in, gradient accumulator out); MAXC classes.
+constexpr int CE_MAXC = 16;
+constexpr int CE_TW = 32, CE_TH = 8;
+
+__global__ void __launch_bounds__(256) ce_upsampled_kernel(const float* __restrict__ logits, const int64_t* __restrict__ label,
+                                                           int ignore_index, double* __restrict__ acc, float* __restrict__ dlogits,
+                                                           int h, int w, int H, int W, int ncls, float sh, float sw, int cap) {
+  extern __shared__ float s_dyn[];  // [cap] low-res logits window, [cap] gradient accumulator
+  float* s_l = s_dyn;
+  float* s_g = s_dyn + cap;
+  __shared__ float s_red[8];
+  __shared__ int s_cnt[8];
+  const int b = blockIdx.z;
+  const int X0 = blockIdx.x * CE_TW, Y0 = blockIdx.y * CE_TH;
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  // low-res window [ly0, ly1] x [lx0, lx1] touched by this tile
+  int ly0, t1, lx0;
+  float tf;
+  bilin_src(Y0, sh, h, ly0, t1, tf);
+  bilin_src(X0, sw, w, lx0, t1, tf);
+  int ylast = Y0 + CE_TH - 1, xlast = X0 + CE_TW - 1;
+  if (ylast > H - 1) ylast = H - 1;
+  if (xlast > W - 1) xlast = W - 1;
+  int ly1, lx1, t0;
+  bilin_src(ylast, sh, h, t0, ly1, tf);
+  bilin_src(xlast, sw, w, t0, lx1, tf);
+  const int nh = ly1 - ly0 + 1, nw = lx1 - lx0 + 1;
+  if (nh * nw * ncls > cap) __trap();  // host sizing bug
+  for (int i = tid; i < nh * nw * ncls; i += 256) {
+    const int k = i % ncls;
+    const int xx = (i / ncls) % nw;
+    const int yy = i / (ncls * nw);
+    s_l[i] = logits[(((long)b * h + ly0 + yy) * w + lx0 + xx) * ncls + k];
+    s_g[i] = 0.f;
+  }
+  __syncthreads();
+  const int x = X0 + threadIdx.x, y = Y0 + threadIdx.y;
+  float loss = 0.f;
+  int valid = 0;
+  if (x < W && y < H) {
+    const long lab = label[((long)b * H + y) * W + x];
+    if (lab != ignore_index) {
+      int y0, y1, x0, x1;
+      float ly, lx;
+      bilin_src(y, sh, h, y0, y1, ly);
+      bilin_src(x, sw, w, x0, x1, lx);
+      const int o00 = ((y0 - ly0) * nw + (x0 - lx0)) * ncls, o01 = ((y0 - ly0) * nw + (x1 - lx0)) * ncls;
+      const int o10 = ((y1 - ly0) * nw + (x0 - lx0)) * ncls, o11 = ((y1 - ly0) * nw + (x1 - lx0)) * ncls;
+      const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+      float v[CE_MAXC];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int k = 0; k < CE_MAXC; k++) {
+        if (k < ncls) {
+          v[k] = w00 * s_l[o00 + k] + w01 * s_l[o01 + k] + w10 * s_l[o10 + k] + w11 * s_l[o11 + k];
+          mx = fmaxf(mx, v[k]);
+        }
+      }
+      float sum = 0.f, picked = 0.f;
+#pragma unroll
+      for (int k = 0; k < CE_MAXC; k++) {
+        if (k < ncls) {
+          if (k == (int)lab) picked = v[k];
+          v[k] = expf(v[k] - mx);
+          sum += v[k];
+        }
+      }
+      loss = logf(sum) + mx - picked;
+      valid = 1;
+      if (dlogits) {
+        const float inv = 1.f / sum;
+#pragma unroll
+        for (int k = 0; k < CE_MAXC; k++) {
+          if (k < ncls) {
+            const float g = v[k] * inv - (k == (int)lab ? 1.f : 0.f);
+            atomicAdd(&s_g[o00 + k], w00 * g);
+            atomicAdd(&s_g[o01 + k], w01 * g);
+            atomicAdd(&s_g[o10 + k], w10 * g);
+            atomicAdd(&s_g[o11 + k], w11 * g);
+          }
+        }
+      }
+    }
+  }
+  // block reduction of loss / count
+  loss = warp_sum(loss);
+  valid = __reduce_add_sync(0xffffffffu, valid);
+  if (threadIdx.x == 0) { s_red[threadIdx.y] = loss; s_cnt[threadIdx.y] = valid; }
+  __syncthreads();
+  if (tid == 0) {
+    double l = 0.;
+    int n = 0;
+    for (int i = 0; i < 8; i++) { l += (double)s_red[i]; n += s_cnt[i]; }
+    if (n) { atomicAdd(acc, l); atomicAdd(acc + 1, (double)n); }
+  }
+  if (dlogits) {
+    for (int i = tid; i < nh * nw * ncls; i += 256) {
+      const int k = i % ncls;
+      const int xx = (i / ncls) % nw;
+      const int yy = i / (ncls * nw);
+      const float g = s_g[i];
+      if (g != 0.f) atomicAdd(dlogits + (((long)b * h + ly0 + yy) * w + lx0 + xx) * ncls + k, g);
+    }
+  }
+}
+CMX_API int cmx_ce_upsampled_fwd_bwd(const float* logits, const int64_t* label, int ignore_index, double* acc, float* dlogits, int B,
+                                     int h, int w, int H, int W, int ncls, void* stream) {
+  CMX_REQUIRE(ncls >= 1 && ncls <= CE_MAXC, "ce: ncls=%d > %d unsupported", ncls, CE_MAXC);
+  CMX_REQUIRE(H >= h && W >= w, "ce: only upsampling supported");
+  if (B == 0) return 0;
+  const float sh = (float)h / (float)H, sw = (float)w / (float)W;
+  const int nh_max = (int)((CE_TH - 1) * sh) + 3, nw_max = (int)((CE_TW - 1) * sw) + 3;
+  const int cap = nh_max * nw_max * ncls;
+  const size_t smem = (size_t)cap * 2 * sizeof(float);
+  CMX_REQUIRE(smem <= 48 * 1024, "ce: low-res window too large for shared memory");
+  dim3 grid(cdiv(W, CE_TW), cdiv(H, CE_TH), B), block(32, 8);
+  ce_upsampled_kernel<<<grid, block, smem, (cudaStream_t)stream>>>(logits, label, ignore_index, acc, dlogits, h, w, H, W, ncls, sh, sw, cap);
+  LAUNCH_DONE("ce_upsampled_fwd_bwd");
+}
+template <typename TO>
+__global__ void __launch_bounds__(256) ce_finalize_kernel(const double* __restrict__ acc, float* __restrict__ loss,
+                                                          const float* __restrict__ dlogits, const float* __restrict__ gscale,
+                                                          TO* __restrict__ out, long n) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0 && loss) *loss = (float)(acc[0] / acc[1]);  // all-ignored batch -> 0/0 = NaN, like torch
+  if (i < n && out) {
+    const float s = (gscale ? *gscale : 1.f) / (float)acc[1];
+    st1(out + i, dlogits[i] * s);
+  }
+}
+CMX_API int cmx_ce_finalize(const double* acc, float* loss, const float* dlogits, const float* gscale, void* dlogits_out,
+                            int out_dtype, int64_t n, void* stream) {
+  const long nn = dlogits_out ? n : 1;
+  if (out_dtype == CMX_F32) ce_finalize_kernel<float><<<cdiv(nn, 256), 256, 0, (cudaStream_t)stream>>>(acc, loss, dlogits, gscale, (float*)dlogits_out, n);
+  else ce_finalize_kernel<bf16><<<cdiv(nn, 256), 256, 0, (cudaStream_t)stream>>>(acc, loss, dlogits, gscale, (bf16*)dlogits_out, n);
+  LAUNCH_DONE("ce_finalize");
+}
+
+// ---- eval: low-res channels-last logits -> full-res NCHW ------------------------------------------------
+__global__ void __launch_bounds__(256) logits_upsample_nchw_kernel(const float* __restrict__ logits, float* __restrict__ out, int B, int h,
+                                                                   int w, int H, int W, int ncls, float sh, float sw) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long total = (long)B * H * W;
+  if (idx >= total) return;
+  const int x = (int)(idx % W);
+  const int y = (int)((idx / W) % H);
+  const int b = (int)(idx / ((long)W * H));
+  int y0, y1, x0, x1;
+  float ly, lx;
+  bilin_src(y, sh, h, y0, y1, ly);
+  bilin_src(x, sw, w, x0, x1, lx);
+  const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+  const float* p00 = logits + (((long)b * h + y0) * w + x0) * ncls;
+  const float* p01 = logits + (((long)b * h + y0) * w + x1) * ncls;
+  const float* p10 = logits + (((long)b * h + y1) * w + x0) * ncls;
+  const float* p11 = logits + (((long)b * h + y1) * w + x1) * ncls;
+  for (int k = 0; k < ncls; k++)
+    out[(((long)b * ncls + k) * H + y) * W + x] = w00 * p00[k] + w01 * p01[k] + w10 * p10[k] + w11 * p11[k];
+}
+CMX_API int cmx_logits_upsample_nchw(const float* logits, float* out, int B, int h, int w, int H, int W, int ncls, void* stream) {
+  const long total = (long)B * H * W;
+  if (total == 0) return 0;
+  logits_upsample_nchw_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(logits, out, B, h, w, H, W, ncls,
+                                                                                 (float)h / (float)H, (float)w / (float)W);
+  LAUNCH_DONE("logits_upsample_nchw");
+}
+
+// ---- confusion matrix (integer, bit-exact) -----------------------------------------------------------------
+constexpr int CF_MAXCL = 64;  // n_cl^2 <= 4096 shared-memory bins
+template <typename TP, typename TG>
+__global__ void __launch_bounds__(256) confusion_kernel(const TP* __restrict__ pred, const TG* __restrict__ gt, long n, int n_cl,
+                                                        unsigned long long* __restrict__ hist, unsigned long long* __restrict__ stats) {
+  __shared__ unsigned int sh[CF_MAXCL * CF_MAXCL];
+  __shared__ unsigned int s_lab, s_cor;
+  for (int i = threadIdx.x; i < n_cl * n_cl; i += blockDim.x) sh[i] = 0;
+  if (threadIdx.x == 0) { s_lab = 0; s_cor = 0; }
+  __syncthreads();
+  unsigned int lab = 0, cor = 0;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const long g = (long)gt[i];
+    if (g >= 0 && g < n_cl) {
+      const long p = (long)pred[i];
+      lab++;
+      if (p == g) cor++;
+      // numpy bincount(n_cl*gt+pred, minlength=n_cl^2): predictions are class ids in [0, n_cl)
+      if (p >= 0 && p < n_cl) atomicAdd(&sh[g * n_cl + p], 1u);
+    }
+  }
+  lab = __reduce_add_sync(0xffffffffu, lab);
+  cor = __reduce_add_sync(0xffffffffu, cor);
+  if ((threadIdx.x & 31) == 0) { atomicAdd(&s_lab, lab); atomicAdd(&s_cor, cor); }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n_cl * n_cl; i += blockDim.x)
+    if (sh[i]) atomicAdd(hist + i, (unsigned long long)sh[i]);
+  if (threadIdx.x == 0) { atomicAdd(stats, (unsigned long long)s_lab); atomicAdd(stats + 1, (unsigned long long)s_cor); }
+}
+template <typename TP>
+static void confusion_launch(const TP* pred, const void* gt, int gt_dtype, long n, int n_cl, int64_t* hist, int64_t* stats, cudaStream_t st) {
+  int grid = cdiv(n, 256 * 8);
+  if (grid > 148 * 4) grid = 148 * 4;
+  if (grid < 1) grid = 1;
+  auto* h = reinterpret_cast<unsigned long long*>(hist);
+  auto* s = reinterpret_cast<unsigned long long*>(stats);
+  if (gt_dtype == 0) confusion_kernel<TP, uint8_t><<<grid, 256, 0, st>>>(pred, (const uint8_t*)gt, n, n_cl, h, s);
+  else if (gt_dtype == 1) confusion_kernel<TP, int32_t><<<grid, 256, 0, st>>>(pred, (const int32_t*)gt, n, n_cl, h, s);
+  else confusion_kernel<TP, int64_t><<<grid, 256, 0, st>>>(pred, (const int64_t*)gt, n, n_cl, h, s);
+}
+CMX_API int cmx_confusion(const void* pred, int pred_dtype, const void* gt, int gt_dtype, int64_t n, int n_cl, int64_t* hist,
+                          int64_t* stats, void* stream) {
+  CMX_REQUIRE(n_cl >= 1 && n_cl <= CF_MAXCL, "confusion: n_cl=%d unsupported (max %d)", n_cl, CF_MAXCL);
+  CMX_REQUIRE(pred_dtype >= 0 && pred_dtype <= 2 && gt_dtype >= 0 && gt_dtype <= 2, "confusion: bad dtype tag");
+  if (n == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (pred_dtype == 0) confusion_launch<uint8_t>((const uint8_t*)pred, gt, gt_dtype, n, n_cl, hist, stats, st);
+  else if (pred_dtype == 1) confusion_launch<int32_t>((const int32_t*)pred, gt, gt_dtype, n, n_cl, hist, stats, st);
+  else confusion_launch<int64_t>((const int64_t*)pred, gt, gt_dtype, n, n_cl, hist, stats, st);
+  LAUNCH_DONE("confusion");
+}
+
+// fused argmax (first maximum, like numpy/torch argmax) + confusion for one [ncls, npix] score map
+template <typename TG>
+__global__ void __launch_bounds__(256) argmax_confusion_kernel(const float* __restrict__ scores, const TG* __restrict__ gt, long npix,
+                                                               int n_cl, uint8_t* __restrict__ pred_out,
+                                                               unsigned long long* __restrict__ hist, unsigned long long* __restrict__ stats) {
+  __shared__ unsigned int sh[CF_MAXCL * CF_MAXCL];
+  __shared__ unsigned int s_lab, s_cor;
+  for (int i = threadIdx.x; i < n_cl * n_cl; i += blockDim.x) sh[i] = 0;
+  if (threadIdx.x == 0) { s_lab = 0; s_cor = 0; }
+  __syncthreads();
+  unsigned int lab = 0, cor = 0;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (long)gridDim.x * blockDim.x) {
+    float best = scores[i];
+    int p = 0;
+    for (int k = 1; k < n_cl; k++) {
+      const float v = scores[(long)k * npix + i];
+      if (v > best) { best = v; p = k; }
+    }
+    if (pred_out) pred_out[i] = (uint8_t)p;
+    if (gt) {
+      const long g = (long)gt[i];
+      if (g >= 0 && g < n_cl) {
+        lab++;
+        if (p == g) cor++;
+        atomicAdd(&sh[g * n_cl + p], 1u);
+      }
+    }
+  }
+  lab = __reduce_add_sync(0xffffffffu, lab);
+  cor = __reduce_add_sync(0xffffffffu, cor);
+  if ((threadIdx.x & 31) == 0) { atomicAdd(&s_lab, lab); atomicAdd(&s_cor, cor); }
+  __syncthreads();
+  if (gt) {
+    for (int i = threadIdx.x; i < n_cl * n_cl; i += blockDim.x)
+      if (sh[i]) atomicAdd(hist + i, (unsigned long long)sh[i]);
+    if (threadIdx.x == 0) { atomicAdd(stats, (unsigned long long)s_lab); atomicAdd(stats + 1, (unsigned long long)s_cor); }
+  }
+}
+CMX_API int cmx_argmax_confusion(const float* scores, const void* gt, int gt_dtype, int64_t npix, int n_cl, uint8_t* pred_out,
+                                 int64_t* hist, int64_t* stats, void* stream) {
+  CMX_REQUIRE(n_cl >= 1 && n_cl <= CF_MAXCL, "argmax_confusion: n_cl=%d unsupported", n_cl);
+  if (npix == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  int grid = cdiv(npix, 256 * 4);
+  if (grid > 148 * 4) grid = 148 * 4;
+  auto* h = reinterpret_cast<unsigned long long*>(hist);
+  auto* s = reinterpret_cast<unsigned long long*>(stats);
+  if (gt_dtype == 0) argmax_confusion_kernel<uint8_t><<<grid, 256, 0, st>>>(scores, (const uint8_t*)gt, npix, n_cl, pred_out, h, s);
+  else if (gt_dtype == 1) argmax_confusion_kernel<int32_t><<<grid, 256, 0, st>>>(scores, (const int32_t*)gt, npix, n_cl, pred_out, h, s);
+  else argmax_confusion_kernel<int64_t><<<grid, 256, 0, st>>>(scores, (const int64_t*)gt, npix, n_cl, pred_out, h, s);
+  LAUNCH_DONE("argmax_confusion");
+}

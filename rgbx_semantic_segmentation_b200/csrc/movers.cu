@@ -1,0 +1,366 @@
+// Layout movers and small streaming kernels: im2col / col2im for the overlapped patch embeds and the
+// spatial-reduction conv, conv-weight packing, casts, column sums (bias grads), ReLU backward,
+// row softmax (self-attention) and dim -2 softmax (FFM cross-attention context).
+#include "common.cuh"
+#include "../../include/cmx_b200.h"
+#include <atomic>
+extern std::atomic<long long> g_cmx_launches;
+
+#define LAUNCH_DONE(name)      \
+  do {                         \
+    g_cmx_launches++;          \
+    CMX_CHECK_LAUNCH(name);    \
+    return 0;                  \
+  } while (0)
+
+// ---- stage-1 im2col from the NCHW fp32 image ------------------------------------------------------
+__global__ void __launch_bounds__(256) im2col_nchw_kernel(const float* __restrict__ x, bf16* __restrict__ col, int B, int Cin, int H,
+                                                          int W, int k, int s, int p, int Ho, int Wo, int kpad) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long total = (long)B * Ho * Wo * kpad;
+  if (idx >= total) return;
+  const int j = (int)(idx % kpad);
+  const long row = idx / kpad;
+  float v = 0.f;
+  if (j < k * k * Cin) {
+    const int ci = j % Cin, tap = j / Cin;
+    const int kh = tap / k, kw = tap % k;
+    const int ox = (int)(row % Wo);
+    const int oy = (int)((row / Wo) % Ho);
+    const int b = (int)(row / ((long)Wo * Ho));
+    const int iy = oy * s - p + kh, ix = ox * s - p + kw;
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = x[(((long)b * Cin + ci) * H + iy) * W + ix];
+  }
+  col[idx] = __float2bfloat16(v);
+}
+CMX_API int cmx_im2col_nchw(const float* x, void* col, int B, int Cin, int H, int W, int k, int s, int p, int Ho, int Wo,
+                            int kpad, void* stream) {
+  CMX_REQUIRE(kpad >= k * k * Cin, "im2col_nchw: kpad too small");
+  const long total = (long)B * Ho * Wo * kpad;
+  if (total == 0) return 0;
+  im2col_nchw_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(x, (bf16*)col, B, Cin, H, W, k, s, p, Ho, Wo, kpad);
+  LAUNCH_DONE("im2col_nchw");
+}
+
+// ---- NHWC bf16 im2col (8 channels per thread) ------------------------------------------------------
+__global__ void __launch_bounds__(256) im2col_nhwc_kernel(const bf16* __restrict__ x, long ldx, bf16* __restrict__ col, int B, int H,
+                                                          int W, int C, int k, int s, int p, int Ho, int Wo) {
+  const int c8 = C >> 3;
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long total = (long)B * Ho * Wo * k * k * c8;
+  if (idx >= total) return;
+  const int cg = (int)(idx % c8);
+  long t = idx / c8;
+  const int tap = (int)(t % (k * k));
+  const long row = t / (k * k);
+  const int kh = tap / k, kw = tap % k;
+  const int ox = (int)(row % Wo);
+  const int oy = (int)((row / Wo) % Ho);
+  const int b = (int)(row / ((long)Wo * Ho));
+  const int iy = oy * s - p + kh, ix = ox * s - p + kw;
+  uint4 v = make_uint4(0, 0, 0, 0);
+  if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = *reinterpret_cast<const uint4*>(x + ((long)(b * H + iy) * W + ix) * ldx + cg * 8);
+  *reinterpret_cast<uint4*>(col + (row * (k * k) + tap) * C + cg * 8) = v;
+}
+CMX_API int cmx_im2col_nhwc(const void* x, int64_t ldx, void* col, int B, int H, int W, int C, int k, int s, int p, int Ho,
+                            int Wo, void* stream) {
+  CMX_REQUIRE(C % 8 == 0 && ldx % 8 == 0, "im2col_nhwc: C %% 8");
+  const long total = (long)B * Ho * Wo * k * k * (C >> 3);
+  if (total == 0) return 0;
+  im2col_nhwc_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, ldx, (bf16*)col, B, H, W, C, k, s, p, Ho, Wo);
+  LAUNCH_DONE("im2col_nhwc");
+}
+
+// ---- col2im (adjoint of im2col_nhwc), gather form -------------------------------------------------
+template <typename TA, typename TO>
+__global__ void __launch_bounds__(256) col2im_nhwc_kernel(const bf16* __restrict__ dcol, const TA* __restrict__ add, long ldadd,
+                                                          TO* __restrict__ dx, long lddx, int B, int H, int W, int C, int k, int s,
+                                                          int p, int Ho, int Wo) {
+  const int c8 = C >> 3;
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long total = (long)B * H * W * c8;
+  if (idx >= total) return;
+  const int cg = (int)(idx % c8);
+  const long pix = idx / c8;
+  const int ix = (int)(pix % W);
+  const int iy = (int)((pix / W) % H);
+  const int b = (int)(pix / ((long)W * H));
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) acc[i] = 0.f;
+  if (add) load8(add + pix * ldadd + cg * 8, acc);
+  for (int kh = 0; kh < k; kh++) {
+    const int ty = iy + p - kh;
+    if (ty < 0 || ty % s) continue;
+    const int oy = ty / s;
+    if (oy >= Ho) continue;
+    for (int kw = 0; kw < k; kw++) {
+      const int tx = ix + p - kw;
+      if (tx < 0 || tx % s) continue;
+      const int ox = tx / s;
+      if (ox >= Wo) continue;
+      float v[8];
+      load8(dcol + ((((long)b * Ho + oy) * Wo + ox) * (k * k) + kh * k + kw) * C + cg * 8, v);
+#pragma unroll
+      for (int i = 0; i < 8; i++) acc[i] += v[i];
+    }
+  }
+  store8(dx + pix * lddx + cg * 8, acc);
+}
+CMX_API int cmx_col2im_nhwc(const void* dcol, const void* add, int add_dtype, int64_t ldadd, void* dx, int dx_dtype, int64_t lddx,
+                            int B, int H, int W, int C, int k, int s, int p, int Ho, int Wo, void* stream) {
+  CMX_REQUIRE(C % 8 == 0 && lddx % 8 == 0, "col2im_nhwc: C %% 8");
+  const long total = (long)B * H * W * (C >> 3);
+  if (total == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid(cdiv(total, 256));
+#define C2I(TA, TO) col2im_nhwc_kernel<TA, TO><<<grid, 256, 0, st>>>((const bf16*)dcol, (const TA*)add, ldadd, (TO*)dx, lddx, B, H, W, C, k, s, p, Ho, Wo)
+  if (add_dtype == CMX_F32 && dx_dtype == CMX_F32) C2I(float, float);
+  else if (add_dtype == CMX_F32) C2I(float, bf16);
+  else if (dx_dtype == CMX_F32) C2I(bf16, float);
+  else C2I(bf16, bf16);
+#undef C2I
+  LAUNCH_DONE("col2im_nhwc");
+}
+
+// ---- conv weight pack / grad unpack ------------------------------------------------------------------
+__global__ void convw_pack_kernel(const float* __restrict__ w, bf16* __restrict__ wp, int Co, int Ci, int kh, int kw, int kpad) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long)Co * kpad) return;
+  const int j = (int)(idx % kpad);
+  const int co = (int)(idx / kpad);
+  float v = 0.f;
+  if (j < kh * kw * Ci) {
+    const int ci = j % Ci, tap = j / Ci;
+    v = w[((long)co * Ci + ci) * (kh * kw) + tap];
+  }
+  wp[idx] = __float2bfloat16(v);
+}
+CMX_API int cmx_convw_pack(const float* w, void* wp, int Co, int Ci, int kh, int kw, int kpad, void* stream) {
+  const long n = (long)Co * kpad;
+  convw_pack_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(w, (bf16*)wp, Co, Ci, kh, kw, kpad);
+  LAUNCH_DONE("convw_pack");
+}
+__global__ void convw_unpack_grad_kernel(const float* __restrict__ gp, float* __restrict__ gw, int Co, int Ci, int kh, int kw, int kpad) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int K = kh * kw * Ci;
+  if (idx >= (long)Co * K) return;
+  const int j = (int)(idx % K);
+  const int co = (int)(idx / K);
+  const int ci = j % Ci, tap = j / Ci;
+  gw[((long)co * Ci + ci) * (kh * kw) + tap] += gp[(long)co * kpad + j];
+}
+CMX_API int cmx_convw_unpack_grad(const float* gp, float* gw, int Co, int Ci, int kh, int kw, int kpad, void* stream) {
+  const long n = (long)Co * kh * kw * Ci;
+  convw_unpack_grad_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(gp, gw, Co, Ci, kh, kw, kpad);
+  LAUNCH_DONE("convw_unpack_grad");
+}
+
+// ---- casts / axpby -----------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ y, long n) {
+  const long i = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (i + 8 <= n) {
+    float f[8];
+    load8(x + i, f);
+    store8(y + i, f);
+  } else {
+    for (long j = i; j < n; j++) y[j] = __float2bfloat16(x[j]);
+  }
+}
+CMX_API int cmx_cast_f32_bf16(const float* x, void* y, int64_t n, void* stream) {
+  if (n == 0) return 0;
+  CMX_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0, "cast: pointers must be 16B aligned");
+  cast_f32_bf16_kernel<<<cdiv(cdiv(n, 8), 256), 256, 0, (cudaStream_t)stream>>>(x, (bf16*)y, n);
+  LAUNCH_DONE("cast_f32_bf16");
+}
+__global__ void __launch_bounds__(256) cast_bf16_f32_kernel(const bf16* __restrict__ x, float* __restrict__ y, long n) {
+  const long i = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (i + 8 <= n) {
+    float f[8];
+    load8(x + i, f);
+    store8(y + i, f);
+  } else {
+    for (long j = i; j < n; j++) y[j] = __bfloat162float(x[j]);
+  }
+}
+CMX_API int cmx_cast_bf16_f32(const void* x, float* y, int64_t n, void* stream) {
+  if (n == 0) return 0;
+  CMX_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0, "cast: pointers must be 16B aligned");
+  cast_bf16_f32_kernel<<<cdiv(cdiv(n, 8), 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, y, n);
+  LAUNCH_DONE("cast_bf16_f32");
+}
+__global__ void __launch_bounds__(256) axpby_kernel(float a, const float* __restrict__ x, float b, const float* __restrict__ y,
+                                                    float* __restrict__ out, long n) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float v = a * x[i];
+  if (y) v += b * y[i];
+  out[i] = v;
+}
+CMX_API int cmx_axpby_f32(float a, const float* x, float b, const float* y, float* out, int64_t n, void* stream) {
+  if (n == 0) return 0;
+  axpby_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(a, x, b, y, out, n);
+  LAUNCH_DONE("axpby");
+}
+
+// ---- column sum (bias gradients): out[n] += sum_m x[m,n] ----------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, long ldx, float* __restrict__ out, long M, int N,
+                                                     int rows_per_cta) {
+  __shared__ float s1[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
+  const long r0 = (long)blockIdx.y * rows_per_cta;
+  long r1 = r0 + rows_per_cta;
+  if (r1 > M) r1 = M;
+  float a = 0.f;
+  if (c < N)
+    for (long r = r0 + ty; r < r1; r += 8) a += ld1(x + r * ldx + c);
+  s1[ty][tx] = a;
+  __syncthreads();
+  if (ty == 0 && c < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; i++) t += s1[i][tx];
+    atomicAdd(out + c, t);
+  }
+}
+CMX_API int cmx_colsum(const void* x, int x_dtype, int64_t ldx, float* out, int64_t M, int N, void* stream) {
+  if (M == 0 || N == 0) return 0;
+  const int rows_per_cta = 512;
+  dim3 grid(cdiv(N, 32), cdiv(M, rows_per_cta));
+  CMX_REQUIRE(grid.y <= 65535, "colsum: M too large");
+  if (x_dtype == CMX_F32) colsum_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)x, ldx, out, M, N, rows_per_cta);
+  else colsum_kernel<bf16><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, ldx, out, M, N, rows_per_cta);
+  LAUNCH_DONE("colsum");
+}
+
+// ---- ReLU backward in place ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) relu_bwd_kernel(bf16* __restrict__ dy, long lddy, const bf16* __restrict__ y, long ldy, long M,
+                                                       int N) {
+  const int n8 = N >> 3;
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= M * n8) return;
+  const long row = idx / n8;
+  const int c = (int)(idx % n8) * 8;
+  float d[8], v[8];
+  load8(dy + row * lddy + c, d);
+  load8(y + row * ldy + c, v);
+#pragma unroll
+  for (int i = 0; i < 8; i++) d[i] = v[i] > 0.f ? d[i] : 0.f;
+  store8(dy + row * lddy + c, d);
+}
+CMX_API int cmx_relu_bwd(void* dy, int64_t lddy, const void* y, int64_t ldy, int64_t M, int N, void* stream) {
+  CMX_REQUIRE(N % 8 == 0 && lddy % 8 == 0 && ldy % 8 == 0, "relu_bwd: N %% 8");
+  if (M == 0) return 0;
+  relu_bwd_kernel<<<cdiv(M * (N >> 3), 256), 256, 0, (cudaStream_t)stream>>>((bf16*)dy, lddy, (const bf16*)y, ldy, M, N);
+  LAUNCH_DONE("relu_bwd");
+}
+
+// ---- row softmax (self-attention probabilities); one warp per row, n <= 1024 ----------------------------
+constexpr int SM_MAXJ = 32;
+__global__ void __launch_bounds__(256) softmax_rows_fwd_kernel(const float* __restrict__ s, long lds, bf16* __restrict__ p, long ldp,
+                                                               long rows, int n) {
+  const int lane = threadIdx.x & 31;
+  const long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* sr = s + row * lds;
+  float v[SM_MAXJ];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < SM_MAXJ; j++) {
+    const int c = lane + 32 * j;
+    v[j] = c < n ? sr[c] : -INFINITY;
+    mx = fmaxf(mx, v[j]);
+  }
+  mx = warp_max(mx);
+  float sum = 0.f;
+#pragma unroll
+  for (int j = 0; j < SM_MAXJ; j++) {
+    const int c = lane + 32 * j;
+    v[j] = c < n ? __expf(v[j] - mx) : 0.f;
+    sum += v[j];
+  }
+  const float inv = 1.f / warp_sum(sum);
+  bf16* pr = p + row * ldp;
+#pragma unroll
+  for (int j = 0; j < SM_MAXJ; j++) {
+    const int c = lane + 32 * j;
+    if (c < n) pr[c] = __float2bfloat16(v[j] * inv);
+  }
+}
+CMX_API int cmx_softmax_rows_fwd(const float* s, int64_t lds, void* p, int64_t ldp, int64_t rows, int n, void* stream) {
+  CMX_REQUIRE(n > 0 && n <= 32 * SM_MAXJ, "softmax_rows: n=%d unsupported", n);
+  if (rows == 0) return 0;
+  softmax_rows_fwd_kernel<<<cdiv(rows, 8), 256, 0, (cudaStream_t)stream>>>(s, lds, (bf16*)p, ldp, rows, n);
+  LAUNCH_DONE("softmax_rows_fwd");
+}
+__global__ void __launch_bounds__(256) softmax_rows_bwd_kernel(const bf16* __restrict__ p, long ldp, const float* __restrict__ dp,
+                                                               long lddp, float scale, bf16* __restrict__ ds, long ldds, long rows,
+                                                               int n) {
+  const int lane = threadIdx.x & 31;
+  const long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float pv[SM_MAXJ], dv[SM_MAXJ];
+  float dot = 0.f;
+#pragma unroll
+  for (int j = 0; j < SM_MAXJ; j++) {
+    const int c = lane + 32 * j;
+    pv[j] = c < n ? __bfloat162float(p[row * ldp + c]) : 0.f;
+    dv[j] = c < n ? dp[row * lddp + c] : 0.f;
+    dot += pv[j] * dv[j];
+  }
+  dot = warp_sum(dot);
+#pragma unroll
+  for (int j = 0; j < SM_MAXJ; j++) {
+    const int c = lane + 32 * j;
+    if (c < n) ds[row * ldds + c] = __float2bfloat16(scale * pv[j] * (dv[j] - dot));
+  }
+}
+CMX_API int cmx_softmax_rows_bwd(const void* p, int64_t ldp, const float* dp, int64_t lddp, float scale, void* ds, int64_t ldds,
+                                 int64_t rows, int n, void* stream) {
+  CMX_REQUIRE(n > 0 && n <= 32 * SM_MAXJ, "softmax_rows_bwd: n=%d unsupported", n);
+  if (rows == 0) return 0;
+  softmax_rows_bwd_kernel<<<cdiv(rows, 8), 256, 0, (cudaStream_t)stream>>>((const bf16*)p, ldp, dp, lddp, scale, (bf16*)ds, ldds, rows, n);
+  LAUNCH_DONE("softmax_rows_bwd");
+}
+
+// ---- softmax over dim -2 of [nb, d, d] (FFM context, d = 64): thread per column ------------------------
+__global__ void softmax_dim2_fwd_kernel(const float* __restrict__ c, float scale, float* __restrict__ p32, bf16* __restrict__ p16, int d) {
+  const int col = threadIdx.x;
+  const long base = (long)blockIdx.x * d * d;
+  if (col >= d) return;
+  float mx = -INFINITY;
+  for (int i = 0; i < d; i++) mx = fmaxf(mx, c[base + (long)i * d + col] * scale);
+  float sum = 0.f;
+  for (int i = 0; i < d; i++) sum += __expf(c[base + (long)i * d + col] * scale - mx);
+  const float inv = 1.f / sum;
+  for (int i = 0; i < d; i++) {
+    const float v = __expf(c[base + (long)i * d + col] * scale - mx) * inv;
+    p32[base + (long)i * d + col] = v;
+    p16[base + (long)i * d + col] = __float2bfloat16(v);
+  }
+}
+CMX_API int cmx_softmax_dim2_fwd(const float* c, float scale, float* p32, void* p16, int nb, int d, void* stream) {
+  CMX_REQUIRE(d > 0 && d <= 1024, "softmax_dim2: d");
+  if (nb == 0) return 0;
+  softmax_dim2_fwd_kernel<<<nb, ((d + 31) / 32) * 32, 0, (cudaStream_t)stream>>>(c, scale, p32, (bf16*)p16, d);
+  LAUNCH_DONE("softmax_dim2_fwd");
+}
+__global__ void softmax_dim2_bwd_kernel(const float* __restrict__ p32, const float* __restrict__ dp, float scale, bf16* __restrict__ dc16, int d) {
+  const int col = threadIdx.x;
+  const long base = (long)blockIdx.x * d * d;
+  if (col >= d) return;
+  float dot = 0.f;
+  for (int i = 0; i < d; i++) dot += p32[base + (long)i * d + col] * dp[base + (long)i * d + col];
+  for (int i = 0; i < d; i++) {
+    const long o = base + (long)i * d + col;
+    dc16[o] = __float2bfloat16(scale * p32[o] * (dp[o] - dot));
+  }
+}
+CMX_API int cmx_softmax_dim2_bwd(const float* p32, const float* dp, float scale, void* dc16, int nb, int d, void* stream) {
+  CMX_REQUIRE(d > 0 && d <= 1024, "softmax_dim2_bwd: d");
+  if (nb == 0) return 0;
+  softmax_dim2_bwd_kernel<<<nb, ((d + 31) / 32) * 32, 0, (cudaStream_t)stream>>>(p32, dp, scale, (bf16*)dc16, d);
+  LAUNCH_DONE("softmax_dim2_bwd");
+}

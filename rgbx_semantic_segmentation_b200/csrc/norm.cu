@@ -1,0 +1,520 @@
+// LayerNorm (fwd/bwd) and BatchNorm (batch-stat reduction, apply, bwd) on token-major [M,C] matrices.
+// Memory-bound kernels: one warp per row for LayerNorm (row cached in registers, 8/16-byte accesses),
+// channel-coalesced column reductions with double atomics for BatchNorm statistics.
+#include "common.cuh"
+#include "../../include/cmx_b200.h"
+#include <atomic>
+extern std::atomic<long long> g_cmx_launches;
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm forward: C % 4 == 0, C <= 1024.  Lane l owns elements {4*(l + 32*j) .. +3}.
+// ------------------------------------------------------------------------------------------------
+constexpr int LN_MAXJ = 4;  // 4 * 32 lanes * 4 = 512 channels (max embed dim of MiT-B0..B5)
+
+template <typename TX, typename TY>
+__global__ void __launch_bounds__(256) ln_fwd_kernel(const TX* __restrict__ x, long ldx, const float* __restrict__ gamma,
+                                                     const float* __restrict__ beta, float eps, TY* __restrict__ y, long ldy,
+                                                     float* __restrict__ mean, float* __restrict__ rstd, long M, int C) {
+  const int lane = threadIdx.x & 31;
+  const long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const TX* xr = x + row * ldx;
+  float v[LN_MAXJ][4];
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < LN_MAXJ; j++) {
+    const int c = 4 * (lane + 32 * j);
+    if (c < C) {
+      load4(xr + c, v[j]);
+      s += v[j][0] + v[j][1] + v[j][2] + v[j][3];
+    }
+  }
+  const float mu = warp_sum(s) / (float)C;
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < LN_MAXJ; j++) {
+    const int c = 4 * (lane + 32 * j);
+    if (c < C) {
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const float d = v[j][i] - mu;
+        q += d * d;
+      }
+    }
+  }
+  const float rs = rsqrtf(warp_sum(q) / (float)C + eps);
+  if (lane == 0) {
+    if (mean) mean[row] = mu;
+    if (rstd) rstd[row] = rs;
+  }
+  TY* yr = y + row * ldy;
+#pragma unroll
+  for (int j = 0; j < LN_MAXJ; j++) {
+    const int c = 4 * (lane + 32 * j);
+    if (c < C) {
+      float g[4], b[4], o[4];
+      load4(gamma + c, g);
+      load4(beta + c, b);
+#pragma unroll
+      for (int i = 0; i < 4; i++) o[i] = (v[j][i] - mu) * rs * g[i] + b[i];
+      store4(yr + c, o);
+    }
+  }
+}
+
+CMX_API int cmx_layernorm_fwd(const void* x, int x_dtype, int64_t ldx, const float* gamma, const float* beta, float eps,
+                              void* y, int y_dtype, int64_t ldy, float* mean, float* rstd, int64_t M, int C, void* stream) {
+  CMX_REQUIRE(C % 4 == 0 && C <= 4 * 32 * LN_MAXJ && C > 0, "layernorm: C=%d unsupported", C);
+  CMX_REQUIRE(ldx % 4 == 0 && ldy % 4 == 0, "layernorm: ld must be a multiple of 4");
+  if (M == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int wpb = 8;
+  dim3 grid(cdiv(M, wpb));
+#define LN_F(TX, TY) ln_fwd_kernel<TX, TY><<<grid, wpb * 32, 0, st>>>((const TX*)x, ldx, gamma, beta, eps, (TY*)y, ldy, mean, rstd, M, C)
+  if (x_dtype == CMX_F32 && y_dtype == CMX_BF16) LN_F(float, bf16);
+  else if (x_dtype == CMX_F32 && y_dtype == CMX_F32) LN_F(float, float);
+  else if (x_dtype == CMX_BF16 && y_dtype == CMX_BF16) LN_F(bf16, bf16);
+  else LN_F(bf16, float);
+#undef LN_F
+  g_cmx_launches++;
+  CMX_CHECK_LAUNCH("ln_fwd");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm backward.  Each CTA walks rows grid-stride, each warp one row at a time; per-lane
+// dgamma/dbeta partials stay in registers, are combined across the CTA's warps in shared memory and
+// flushed with one atomicAdd per channel per CTA.
+// ------------------------------------------------------------------------------------------------
+template <typename TDY, typename TX, typename TDX>
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const TDY* __restrict__ dy, long lddy, const bf16* __restrict__ dy2, long lddy2,
+                                                     const TX* __restrict__ x, long ldx, const float* __restrict__ mean,
+                                                     const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                                     const float* __restrict__ dres, long lddres, TDX* __restrict__ dx, long lddx,
+                                                     bf16* __restrict__ dxbf, long lddxbf, const float* __restrict__ scale,
+                                                     int rows_per_sample, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                     long M, int C) {
+  __shared__ float sh_g[1024];
+  __shared__ float sh_b[1024];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int nwarp = blockDim.x >> 5;
+  for (int i = threadIdx.x; i < C; i += blockDim.x) { sh_g[i] = 0.f; sh_b[i] = 0.f; }
+  __syncthreads();
+  float ag[LN_MAXJ][4], ab[LN_MAXJ][4], gm[LN_MAXJ][4];
+#pragma unroll
+  for (int j = 0; j < LN_MAXJ; j++) {
+    const int c = 4 * (lane + 32 * j);
+#pragma unroll
+    for (int i = 0; i < 4; i++) { ag[j][i] = 0.f; ab[j][i] = 0.f; gm[j][i] = 0.f; }
+    if (c < C) load4(gamma + c, gm[j]);
+  }
+  for (long row = (long)blockIdx.x * nwarp + warp; row < M; row += (long)gridDim.x * nwarp) {
+    const float mu = mean[row], rs = rstd[row];
+    float g[LN_MAXJ][4], xh[LN_MAXJ][4];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < LN_MAXJ; j++) {
+      const int c = 4 * (lane + 32 * j);
+      if (c < C) {
+        float d[4], xv[4];
+        load4(dy + row * lddy + c, d);
+        if (dy2) {
+          float d2[4];
+          load4(dy2 + row * lddy2 + c, d2);
+#pragma unroll
+          for (int i = 0; i < 4; i++) d[i] += d2[i];
+        }
+        load4(x + row * ldx + c, xv);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          xh[j][i] = (xv[i] - mu) * rs;
+          ag[j][i] += d[i] * xh[j][i];
+          ab[j][i] += d[i];
+          g[j][i] = d[i] * gm[j][i];
+          s1 += g[j][i];
+          s2 += g[j][i] * xh[j][i];
+        }
+      }
+    }
+    s1 = warp_sum(s1) / (float)C;
+    s2 = warp_sum(s2) / (float)C;
+    const float sc = (scale && dxbf) ? scale[row / rows_per_sample] : 1.f;
+#pragma unroll
+    for (int j = 0; j < LN_MAXJ; j++) {
+      const int c = 4 * (lane + 32 * j);
+      if (c < C) {
+        float o[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) o[i] = rs * (g[j][i] - s1 - xh[j][i] * s2);
+        if (dres) {
+          float r[4];
+          load4(dres + row * lddres + c, r);
+#pragma unroll
+          for (int i = 0; i < 4; i++) o[i] += r[i];
+        }
+        if (dx) store4(dx + row * lddx + c, o);
+        if (dxbf) {
+#pragma unroll
+          for (int i = 0; i < 4; i++) o[i] *= sc;
+          store4(dxbf + row * lddxbf + c, o);
+        }
+      }
+    }
+  }
+  if (dgamma) {
+#pragma unroll
+    for (int j = 0; j < LN_MAXJ; j++) {
+      const int c = 4 * (lane + 32 * j);
+      if (c < C) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          atomicAdd(&sh_g[c + i], ag[j][i]);
+          atomicAdd(&sh_b[c + i], ab[j][i]);
+        }
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < C; i += blockDim.x) {
+      atomicAdd(dgamma + i, sh_g[i]);
+      atomicAdd(dbeta + i, sh_b[i]);
+    }
+  }
+}
+
+CMX_API int cmx_layernorm_bwd(const void* dy, int dy_dtype, int64_t lddy, const void* dy2, int64_t lddy2, const void* x,
+                              int x_dtype, int64_t ldx, const float* mean, const float* rstd, const float* gamma,
+                              const float* dres, int64_t lddres, void* dx, int dx_dtype, int64_t lddx, void* dx_bf,
+                              int64_t lddxbf, const float* scale, int rows_per_sample, float* dgamma, float* dbeta, int64_t M,
+                              int C, void* stream) {
+  CMX_REQUIRE(C % 4 == 0 && C <= 4 * 32 * LN_MAXJ && C > 0, "layernorm_bwd: C=%d unsupported", C);
+  CMX_REQUIRE((dgamma == nullptr) == (dbeta == nullptr), "layernorm_bwd: dgamma/dbeta must come together");
+  if (M == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  int grid = cdiv(M, 8);
+  if (grid > 148 * 8) grid = 148 * 8;
+  if (rows_per_sample <= 0) rows_per_sample = 1;
+#define LN_B(TDY, TX, TDX)                                                                                              \
+  ln_bwd_kernel<TDY, TX, TDX><<<grid, 256, 0, st>>>((const TDY*)dy, lddy, (const bf16*)dy2, lddy2, (const TX*)x, ldx, mean, \
+                                                    rstd, gamma, dres, lddres, (TDX*)dx, lddx, (bf16*)dx_bf, lddxbf, scale, \
+                                                    rows_per_sample, dgamma, dbeta, M, C)
+  const int key = dy_dtype * 4 + x_dtype * 2 + dx_dtype;
+  switch (key) {
+    case 0: LN_B(bf16, bf16, bf16); break;
+    case 1: LN_B(bf16, bf16, float); break;
+    case 2: LN_B(bf16, float, bf16); break;
+    case 3: LN_B(bf16, float, float); break;
+    case 4: LN_B(float, bf16, bf16); break;
+    case 5: LN_B(float, bf16, float); break;
+    case 6: LN_B(float, float, bf16); break;
+    default: LN_B(float, float, float); break;
+  }
+#undef LN_B
+  g_cmx_launches++;
+  CMX_CHECK_LAUNCH("ln_bwd");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Column statistics (sum, sum of squares) in double.  Block = 32 channel lanes x 8 row lanes.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) colstats_kernel(const T* __restrict__ x, long ldx, double* __restrict__ sum,
+                                                       double* __restrict__ sumsq, long M, int C, int rows_per_cta) {
+  __shared__ float s1[8][33], s2[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
+  const long r0 = (long)blockIdx.y * rows_per_cta;
+  long r1 = r0 + rows_per_cta;
+  if (r1 > M) r1 = M;
+  float a = 0.f, b = 0.f;
+  if (c < C)
+    for (long r = r0 + ty; r < r1; r += 8) {
+      const float v = ld1(x + r * ldx + c);
+      a += v;
+      b += v * v;
+    }
+  s1[ty][tx] = a;
+  s2[ty][tx] = b;
+  __syncthreads();
+  if (ty == 0 && c < C) {
+    double da = 0., db = 0.;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { da += (double)s1[i][tx]; db += (double)s2[i][tx]; }
+    atomicAdd(sum + c, da);
+    atomicAdd(sumsq + c, db);
+  }
+}
+
+CMX_API int cmx_colstats(const void* x, int x_dtype, int64_t ldx, double* sum, double* sumsq, int64_t M, int C, void* stream) {
+  if (M == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int rows_per_cta = 256;
+  dim3 grid(cdiv(C, 32), cdiv(M, rows_per_cta));
+  CMX_REQUIRE(grid.y <= 65535, "colstats: M too large");
+  if (x_dtype == CMX_F32) colstats_kernel<float><<<grid, 256, 0, st>>>((const float*)x, ldx, sum, sumsq, M, C, rows_per_cta);
+  else colstats_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)x, ldx, sum, sumsq, M, C, rows_per_cta);
+  g_cmx_launches++;
+  CMX_CHECK_LAUNCH("colstats");
+  return 0;
+}
+
+__global__ void bn_finalize_kernel(const double* sum, const double* sumsq, long count, float eps, float momentum,
+                                   float* running_mean, float* running_var, int64_t* nbt, float* mean, float* invstd, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0 && nbt) *nbt += 1;
+  if (c >= C) return;
+  const double m = sum[c] / (double)count;
+  double var = sumsq[c] / (double)count - m * m;
+  if (var < 0.) var = 0.;
+  mean[c] = (float)m;
+  invstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+  if (running_mean) {
+    const double unbiased = count > 1 ? var * (double)count / (double)(count - 1) : var;
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)m;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+  }
+}
+
+CMX_API int cmx_bn_finalize(const double* sum, const double* sumsq, int64_t count, float eps, float momentum,
+                            float* running_mean, float* running_var, int64_t* num_batches_tracked, float* mean, float* invstd,
+                            int C, void* stream) {
+  bn_finalize_kernel<<<cdiv(C, 128), 128, 0, (cudaStream_t)stream>>>(sum, sumsq, count, eps, momentum, running_mean,
+                                                                    running_var, num_batches_tracked, mean, invstd, C);
+  g_cmx_launches++;
+  CMX_CHECK_LAUNCH("bn_finalize");
+  return 0;
+}
+
+__global__ void bn_eval_stats_kernel(const float* rm, const float* rv, float eps, float* mean, float* invstd, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  mean[c] = rm[c];
+  invstd[c] = 1.0f / sqrtf(rv[c] + eps);
+}
+CMX_API int cmx_bn_eval_stats(const float* running_mean, const float* running_var, float eps, float* mean, float* invstd, int C,
+                              void* stream) {
+  bn_eval_stats_kernel<<<cdiv(C, 128), 128, 0, (cudaStream_t)stream>>>(running_mean, running_var, eps, mean, invstd, C);
+  g_cmx_launches++;
+  CMX_CHECK_LAUNCH("bn_eval_stats");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// BN apply (+ residual, ReLU, Dropout2d mask):  thread = 4 consecutive channels of one row
+// ------------------------------------------------------------------------------------------------
+template <typename TX, typename TR, typename TY>
+__global__ void __launch_bounds__(256) bn_apply_kernel(const TX* __restrict__ x, long ldx, const float* __restrict__ mean,
+                                                       const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                                       const float* __restrict__ beta, const TR* __restrict__ res, long ldr,
+                                                       int relu, const float* __restrict__ mask, int rows_per_sample,
+                                                       TY* __restrict__ y, long ldy, long M, int C) {
+  const int c4 = C >> 2;
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= M * c4) return;
+  const long row = idx / c4;
+  const int c = (int)(idx % c4) * 4;
+  float v[4], mu[4], is[4], g[4], b[4];
+  load4(x + row * ldx + c, v);
+  load4(mean + c, mu);
+  load4(invstd + c, is);
+  load4(gamma + c, g);
+  load4(beta + c, b);
+#pragma unroll
+  for (int i = 0; i < 4; i++) v[i] = (v[i] - mu[i]) * is[i] * g[i] + b[i];
+  if (res) {
+    float r[4];
+    load4(res + row * ldr + c, r);
+#pragma unroll
+    for (int i = 0; i < 4; i++) v[i] += r[i];
+  }
+  if (relu) {
+#pragma unroll
+    for (int i = 0; i < 4; i++) v[i] = fmaxf(v[i], 0.f);
+  }
+  if (mask) {
+    float mk[4];
+    load4(mask + (row / rows_per_sample) * C + c, mk);
+#pragma unroll
+    for (int i = 0; i < 4; i++) v[i] *= mk[i];
+  }
+  store4(y + row * ldy + c, v);
+}
+
+template <typename TX, typename TR>
+static void bn_apply_launch2(int y_dtype, const TX* x, long ldx, const float* mean, const float* invstd, const float* gamma,
+                             const float* beta, const TR* res, long ldr, int relu, const float* mask, int rps, void* y, long ldy,
+                             long M, int C, cudaStream_t st) {
+  const long n = M * (C >> 2);
+  dim3 grid(cdiv(n, 256));
+  if (y_dtype == CMX_F32)
+    bn_apply_kernel<TX, TR, float><<<grid, 256, 0, st>>>(x, ldx, mean, invstd, gamma, beta, res, ldr, relu, mask, rps, (float*)y, ldy, M, C);
+  else
+    bn_apply_kernel<TX, TR, bf16><<<grid, 256, 0, st>>>(x, ldx, mean, invstd, gamma, beta, res, ldr, relu, mask, rps, (bf16*)y, ldy, M, C);
+}
+
+CMX_API int cmx_bn_apply(const void* x, int x_dtype, int64_t ldx, const float* mean, const float* invstd, const float* gamma,
+                         const float* beta, const void* residual, int r_dtype, int64_t ldr, int relu, const float* mask,
+                         int rows_per_sample, void* y, int y_dtype, int64_t ldy, int64_t M, int C, void* stream) {
+  CMX_REQUIRE(C % 4 == 0, "bn_apply: C %% 4");
+  if (M == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (rows_per_sample <= 0) rows_per_sample = 1;
+  if (x_dtype == CMX_F32) {
+    if (r_dtype == CMX_F32) bn_apply_launch2<float, float>(y_dtype, (const float*)x, ldx, mean, invstd, gamma, beta, (const float*)residual, ldr, relu, mask, rows_per_sample, y, ldy, M, C, st);
+    else bn_apply_launch2<float, bf16>(y_dtype, (const float*)x, ldx, mean, invstd, gamma, beta, (const bf16*)residual, ldr, relu, mask, rows_per_sample, y, ldy, M, C, st);
+  } else {
+    if (r_dtype == CMX_F32) bn_apply_launch2<bf16, float>(y_dtype, (const bf16*)x, ldx, mean, invstd, gamma, beta, (const float*)residual, ldr, relu, mask, rows_per_sample, y, ldy, M, C, st);
+    else bn_apply_launch2<bf16, bf16>(y_dtype, (const bf16*)x, ldx, mean, invstd, gamma, beta, (const bf16*)residual, ldr, relu, mask, rows_per_sample, y, ldy, M, C, st);
+  }
+  g_cmx_launches++;
+  CMX_CHECK_LAUNCH("bn_apply");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// BN backward.  Effective upstream gradient g = dy * mask * [out > 0 if relu], out = bn(x)+res.
+// pass 1: sum_g, sum_g_xhat per channel (double).  pass 2: dx = gamma*invstd*(g - sum_g/M - xhat*sum_g_xhat/M).
+// ------------------------------------------------------------------------------------------------
+template <typename TDY, typename TX, typename TR>
+__device__ __forceinline__ float bn_eff_grad(const TDY* dy, long lddy, const TX* x, long ldx, const TR* res, long ldr, long row,
+                                             int c, float mu, float is, float g, float b, int relu, const float* mask, int rps,
+                                             int C, float& xhat) {
+  const float xv = ld1(x + row * ldx + c);
+  xhat = (xv - mu) * is;
+  float d = ld1(dy + row * lddy + c);
+  if (mask) d *= mask[(row / rps) * C + c];
+  if (relu) {
+    float o = xhat * g + b;
+    if (res) o += ld1(res + row * ldr + c);
+    if (o <= 0.f) d = 0.f;
+  }
+  return d;
+}
+
+template <typename TDY, typename TX, typename TR>
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const TDY* __restrict__ dy, long lddy, const TX* __restrict__ x, long ldx,
+                                                            const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                            const TR* __restrict__ res, long ldr, int relu,
+                                                            const float* __restrict__ mask, int rps, double* __restrict__ sum_dy,
+                                                            double* __restrict__ sum_dy_xhat, long M, int C, int rows_per_cta) {
+  __shared__ float s1[8][33], s2[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
+  const long r0 = (long)blockIdx.y * rows_per_cta;
+  long r1 = r0 + rows_per_cta;
+  if (r1 > M) r1 = M;
+  float a = 0.f, b = 0.f;
+  if (c < C) {
+    const float mu = mean[c], is = invstd[c], g = gamma[c], be = beta[c];
+    for (long r = r0 + ty; r < r1; r += 8) {
+      float xh;
+      const float d = bn_eff_grad(dy, lddy, x, ldx, res, ldr, r, c, mu, is, g, be, relu, mask, rps, C, xh);
+      a += d;
+      b += d * xh;
+    }
+  }
+  s1[ty][tx] = a;
+  s2[ty][tx] = b;
+  __syncthreads();
+  if (ty == 0 && c < C) {
+    double da = 0., db = 0.;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { da += (double)s1[i][tx]; db += (double)s2[i][tx]; }
+    atomicAdd(sum_dy + c, da);
+    atomicAdd(sum_dy_xhat + c, db);
+  }
+}
+
+template <typename TDY, typename TX, typename TR, typename TDX>
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const TDY* __restrict__ dy, long lddy, const TX* __restrict__ x, long ldx,
+                                                           const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                           const TR* __restrict__ res, long ldr, int relu,
+                                                           const float* __restrict__ mask, int rps,
+                                                           const double* __restrict__ sum_dy, const double* __restrict__ sum_dy_xhat,
+                                                           TDX* __restrict__ dx, long lddx, TDX* __restrict__ dres, long lddres,
+                                                           float* __restrict__ dgamma, float* __restrict__ dbeta, long M, int C) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < C && blockIdx.y == 0 && dgamma) {
+    // fold the parameter gradients into the first C threads of the grid
+    atomicAdd(dgamma + idx, (float)sum_dy_xhat[idx]);
+    atomicAdd(dbeta + idx, (float)sum_dy[idx]);
+  }
+  if (idx >= M * C) return;
+  const long row = idx / C;
+  const int c = (int)(idx % C);
+  const float mu = mean[c], is = invstd[c], g = gamma[c], be = beta[c];
+  float xh;
+  const float d = bn_eff_grad(dy, lddy, x, ldx, res, ldr, row, c, mu, is, g, be, relu, mask, rps, C, xh);
+  const float m1 = (float)(sum_dy[c] / (double)M), m2 = (float)(sum_dy_xhat[c] / (double)M);
+  st1(dx + row * lddx + c, g * is * (d - m1 - xh * m2));
+  if (dres) st1(dres + row * lddres + c, d);
+}
+
+#define BN_DISPATCH3(MACRO)                                                          \
+  do {                                                                               \
+    const int key = dy_dtype * 4 + x_dtype * 2 + r_dtype;                            \
+    switch (key) {                                                                   \
+      case 0: MACRO(bf16, bf16, bf16); break;                                        \
+      case 1: MACRO(bf16, bf16, float); break;                                       \
+      case 2: MACRO(bf16, float, bf16); break;                                       \
+      case 3: MACRO(bf16, float, float); break;                                      \
+      case 4: MACRO(float, bf16, bf16); break;                                       \
+      case 5: MACRO(float, bf16, float); break;                                      \
+      case 6: MACRO(float, float, bf16); break;                                      \
+      default: MACRO(float, float, float); break;                                    \
+    }                                                                                \
+  } while (0)
+
+CMX_API int cmx_bn_bwd_reduce(const void* dy, int dy_dtype, int64_t lddy, const void* x, int x_dtype, int64_t ldx,
+                              const float* mean, const float* invstd, const float* gamma, const float* beta,
+                              const void* residual, int r_dtype, int64_t ldr, int relu, const float* mask, int rows_per_sample,
+                              double* sum_dy, double* sum_dy_xhat, int64_t M, int C, void* stream) {
+  if (M == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (rows_per_sample <= 0) rows_per_sample = 1;
+  const int rows_per_cta = 256;
+  dim3 grid(cdiv(C, 32), cdiv(M, rows_per_cta));
+  CMX_REQUIRE(grid.y <= 65535, "bn_bwd_reduce: M too large");
+#define BN_R(TDY, TX, TR)                                                                                                   \
+  bn_bwd_reduce_kernel<TDY, TX, TR><<<grid, 256, 0, st>>>((const TDY*)dy, lddy, (const TX*)x, ldx, mean, invstd, gamma, beta, \
+                                                          (const TR*)residual, ldr, relu, mask, rows_per_sample, sum_dy,     \
+                                                          sum_dy_xhat, M, C, rows_per_cta)
+  BN_DISPATCH3(BN_R);
+#undef BN_R
+  g_cmx_launches++;
+  CMX_CHECK_LAUNCH("bn_bwd_reduce");
+  return 0;
+}
+
+CMX_API int cmx_bn_bwd_apply(const void* dy, int dy_dtype, int64_t lddy, const void* x, int x_dtype, int64_t ldx,
+                             const float* mean, const float* invstd, const float* gamma, const float* beta, const void* residual,
+                             int r_dtype, int64_t ldr, int relu, const float* mask, int rows_per_sample, const double* sum_dy,
+                             const double* sum_dy_xhat, void* dx, int dx_dtype, int64_t lddx, void* dres, int dres_dtype,
+                             int64_t lddres, float* dgamma, float* dbeta, int64_t M, int C, void* stream) {
+  if (M == 0) return 0;
+  CMX_REQUIRE(!dres || dres_dtype == dx_dtype, "bn_bwd_apply: dres dtype must equal dx dtype");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (rows_per_sample <= 0) rows_per_sample = 1;
+  dim3 grid(cdiv(M * C, 256));
+#define BN_A(TDY, TX, TR)                                                                                                       \
+  do {                                                                                                                          \
+    if (dx_dtype == CMX_F32)                                                                                                    \
+      bn_bwd_apply_kernel<TDY, TX, TR, float><<<grid, 256, 0, st>>>((const TDY*)dy, lddy, (const TX*)x, ldx, mean, invstd, gamma, \
+                                                                    beta, (const TR*)residual, ldr, relu, mask, rows_per_sample,  \
+                                                                    sum_dy, sum_dy_xhat, (float*)dx, lddx, (float*)dres, lddres,  \
+                                                                    dgamma, dbeta, M, C);                                         \
+    else                                                                                                                        \
+      bn_bwd_apply_kernel<TDY, TX, TR, bf16><<<grid, 256, 0, st>>>((const TDY*)dy, lddy, (const TX*)x, ldx, mean, invstd, gamma,  \
+                                                                   beta, (const TR*)residual, ldr, relu, mask, rows_per_sample,   \
+                                                                   sum_dy, sum_dy_xhat, (bf16*)dx, lddx, (bf16*)dres, lddres,     \
+                                                                   dgamma, dbeta, M, C);                                          \
+  } while (0)
+  BN_DISPATCH3(BN_A);
+#undef BN_A
+  g_cmx_launches++;
+  CMX_CHECK_LAUNCH("bn_bwd_apply");
+  return 0;
+}

@@ -1,0 +1,380 @@
+"""Thin Python wrappers over the C ABI (include/cmx_b200.h).  torch is used only for device memory
+and the current stream; every function below enqueues hand-written sm_100a kernels and raises
+RuntimeError on a non-zero return code.  There is no CPU path."""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import CmxGemm
+
+BF16, F32 = 0, 1
+ACT_NONE, ACT_RELU, ACT_GELU, ACT_SIGMOID = 0, 1, 2, 3
+NUM_SMS = 148
+
+
+def _dt(t):
+    if t.dtype == torch.bfloat16:
+        return BF16
+    if t.dtype == torch.float32:
+        return F32
+    raise TypeError("cmx_b200: unsupported dtype %s" % t.dtype)
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ld(t):
+    assert t.dim() == 2 and (t.stride(1) == 1 or t.shape[1] == 1), "need a row-major 2-D view"
+    return t.stride(0)
+
+
+def _cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("cmx_b200: tensors must live on a CUDA device (no CPU fallback exists)")
+
+
+def launch_count():
+    return int(_lib.load().cmx_launch_count())
+
+
+# ------------------------------------------------------------------------------------------------
+# GEMM
+# ------------------------------------------------------------------------------------------------
+def _auto_split(M, N, K, want):
+    if not want:
+        return 1
+    tiles = ((M + 127) // 128) * ((N + 127) // 128)
+    s = (2 * NUM_SMS) // max(tiles, 1)
+    return max(1, min(s, K // 512 if K >= 1024 else 1))
+
+
+def gemm_raw(A, B, C, M, N, K, lda, ldb, ldc, *, a_off=0, b_off=0, c_off=0, trans_a=False, trans_b=False, bias=None,
+             residual=None, ldr=0, r_off=0, row_scale=None, rows_per_sample=0, act=ACT_NONE, alpha=1.0, split_k=1,
+             accumulate=False, batch=(1, 1), sA=(0, 0), sB=(0, 0), sC=(0, 0), impl=0):
+    """A, B, C (and residual) are base tensors; *_off are element offsets into them."""
+    _cuda(A, B, C)
+    assert A.dtype == torch.bfloat16 and B.dtype == torch.bfloat16
+    g = CmxGemm()
+    g.A = A.data_ptr() + 2 * a_off
+    g.B = B.data_ptr() + 2 * b_off
+    g.C = C.data_ptr() + C.element_size() * c_off
+    g.bias = _p(bias)
+    g.residual = None if residual is None else residual.data_ptr() + residual.element_size() * r_off
+    g.row_scale = _p(row_scale)
+    g.M, g.N, g.K = M, N, K
+    g.lda, g.ldb, g.ldc, g.ldr = lda, ldb, ldc, ldr
+    g.trans_a, g.trans_b = int(trans_a), int(trans_b)
+    g.batch1, g.batch2 = batch
+    g.sA1, g.sA2 = sA
+    g.sB1, g.sB2 = sB
+    g.sC1, g.sC2 = sC
+    g.c_dtype = _dt(C)
+    g.r_dtype = _dt(residual) if residual is not None else F32
+    g.act = act
+    g.alpha = alpha
+    g.accumulate = int(accumulate)
+    g.split_k = split_k
+    g.rows_per_sample = rows_per_sample
+    g.impl = impl
+    _lib.check(_lib.load().cmx_gemm(ctypes.byref(g), _stream()), "gemm")
+    return C
+
+
+def mm(a, b, out, *, ta=False, tb=False, bias=None, residual=None, row_scale=None, rows_per_sample=0, act=ACT_NONE,
+       alpha=1.0, accumulate=False, split_k=None, impl=0):
+    """out[M,N] = residual + row_scale * act(alpha * op(a) @ op(b) + bias) on 2-D row-major views.
+    ta=False: a is [M,K]; ta=True: a is stored [K,M].  tb=False: b is [N,K] (nn.Linear weight layout);
+    tb=True: b is stored [K,N].  accumulate=True adds into fp32 `out` (split-K chosen automatically)."""
+    if ta:
+        K, M = a.shape
+    else:
+        M, K = a.shape
+    if tb:
+        Kb, N = b.shape
+    else:
+        N, Kb = b.shape
+    assert K == Kb, (a.shape, b.shape, ta, tb)
+    assert tuple(out.shape) == (M, N), (out.shape, M, N)
+    if split_k is None:
+        split_k = _auto_split(M, N, K, accumulate)
+    return gemm_raw(a, b, out, M, N, K, _ld(a), _ld(b), _ld(out), trans_a=ta, trans_b=tb, bias=bias, residual=residual,
+                    ldr=_ld(residual) if residual is not None else 0, row_scale=row_scale, rows_per_sample=rows_per_sample,
+                    act=act, alpha=alpha, split_k=split_k, accumulate=accumulate, impl=impl)
+
+
+def gemm_which(M, N, K, lda, ldb, ldc, trans_a=False, trans_b=False, c_dtype=BF16, ptr=256):
+    g = CmxGemm()
+    g.A = g.B = g.C = ptr
+    g.M, g.N, g.K, g.lda, g.ldb, g.ldc = M, N, K, lda, ldb, ldc
+    g.trans_a, g.trans_b, g.batch1, g.batch2, g.c_dtype = int(trans_a), int(trans_b), 1, 1, c_dtype
+    return int(_lib.load().cmx_gemm_which(ctypes.byref(g)))
+
+
+# ------------------------------------------------------------------------------------------------
+# normalisation
+# ------------------------------------------------------------------------------------------------
+def layernorm_fwd(x, gamma, beta, eps, y, mean=None, rstd=None):
+    M, C = x.shape
+    _cuda(x, y)
+    _lib.check(_lib.load().cmx_layernorm_fwd(x.data_ptr(), _dt(x), _ld(x), gamma.data_ptr(), beta.data_ptr(), eps,
+                                             y.data_ptr(), _dt(y), _ld(y), _p(mean), _p(rstd), M, C, _stream()), "layernorm_fwd")
+    return y
+
+
+def layernorm_bwd(dy, x, mean, rstd, gamma, *, dy2=None, dres=None, dx=None, dx_bf=None, scale=None, rows_per_sample=0,
+                  dgamma=None, dbeta=None):
+    M, C = x.shape
+    _lib.check(_lib.load().cmx_layernorm_bwd(
+        dy.data_ptr(), _dt(dy), _ld(dy), _p(dy2), _ld(dy2) if dy2 is not None else 0, x.data_ptr(), _dt(x), _ld(x),
+        mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(), _p(dres), _ld(dres) if dres is not None else 0,
+        _p(dx), _dt(dx) if dx is not None else F32, _ld(dx) if dx is not None else 0,
+        _p(dx_bf), _ld(dx_bf) if dx_bf is not None else 0, _p(scale), rows_per_sample,
+        _p(dgamma), _p(dbeta), M, C, _stream()), "layernorm_bwd")
+
+
+def colstats(x, sum_, sumsq):
+    M, C = x.shape
+    _lib.check(_lib.load().cmx_colstats(x.data_ptr(), _dt(x), _ld(x), sum_.data_ptr(), sumsq.data_ptr(), M, C, _stream()), "colstats")
+
+
+def bn_finalize(sum_, sumsq, count, eps, momentum, running_mean, running_var, nbt, mean, invstd):
+    C = mean.numel()
+    _lib.check(_lib.load().cmx_bn_finalize(sum_.data_ptr(), sumsq.data_ptr(), count, eps, momentum, _p(running_mean),
+                                           _p(running_var), _p(nbt), mean.data_ptr(), invstd.data_ptr(), C, _stream()), "bn_finalize")
+
+
+def bn_eval_stats(running_mean, running_var, eps, mean, invstd):
+    _lib.check(_lib.load().cmx_bn_eval_stats(running_mean.data_ptr(), running_var.data_ptr(), eps, mean.data_ptr(),
+                                             invstd.data_ptr(), mean.numel(), _stream()), "bn_eval_stats")
+
+
+def bn_apply(x, mean, invstd, gamma, beta, y, *, residual=None, relu=False, mask=None, rows_per_sample=0):
+    M, C = x.shape
+    _lib.check(_lib.load().cmx_bn_apply(x.data_ptr(), _dt(x), _ld(x), mean.data_ptr(), invstd.data_ptr(), gamma.data_ptr(),
+                                        beta.data_ptr(), _p(residual), _dt(residual) if residual is not None else F32,
+                                        _ld(residual) if residual is not None else 0, int(relu), _p(mask), rows_per_sample,
+                                        y.data_ptr(), _dt(y), _ld(y), M, C, _stream()), "bn_apply")
+    return y
+
+
+def bn_bwd(dy, x, mean, invstd, gamma, beta, dx, dgamma, dbeta, ws, *, residual=None, relu=False, mask=None,
+           rows_per_sample=0, dres=None):
+    """ws: zeroed double[2*C] workspace.  dx (and dres = effective upstream grad) share a dtype."""
+    M, C = x.shape
+    s1, s2 = ws[:C], ws[C:]
+    common = (dy.data_ptr(), _dt(dy), _ld(dy), x.data_ptr(), _dt(x), _ld(x), mean.data_ptr(), invstd.data_ptr(),
+              gamma.data_ptr(), beta.data_ptr(), _p(residual), _dt(residual) if residual is not None else F32,
+              _ld(residual) if residual is not None else 0, int(relu), _p(mask), rows_per_sample)
+    lib = _lib.load()
+    _lib.check(lib.cmx_bn_bwd_reduce(*common, s1.data_ptr(), s2.data_ptr(), M, C, _stream()), "bn_bwd_reduce")
+    _lib.check(lib.cmx_bn_bwd_apply(*common, s1.data_ptr(), s2.data_ptr(), dx.data_ptr(), _dt(dx), _ld(dx), _p(dres),
+                                    _dt(dres) if dres is not None else _dt(dx), _ld(dres) if dres is not None else 0,
+                                    _p(dgamma), _p(dbeta), M, C, _stream()), "bn_bwd_apply")
+
+
+# ------------------------------------------------------------------------------------------------
+# depthwise conv
+# ------------------------------------------------------------------------------------------------
+def dwconv3x3_fwd(x, w, bias, act, y, B, H, W, flip=False):
+    C = x.shape[1]
+    _lib.check(_lib.load().cmx_dwconv3x3_fwd(x.data_ptr(), _ld(x), w.data_ptr(), _p(bias), act, int(flip), y.data_ptr(), _ld(y),
+                                             B, H, W, C, _stream()), "dwconv3x3_fwd")
+    return y
+
+
+def dwconv3x3_bwd_pre(x, w, bias, act, dy, du, dw, db, B, H, W):
+    C = x.shape[1]
+    _lib.check(_lib.load().cmx_dwconv3x3_bwd_pre(x.data_ptr(), _ld(x), w.data_ptr(), _p(bias), act, dy.data_ptr(), _ld(dy),
+                                                 du.data_ptr(), _ld(du), dw.data_ptr(), _p(db), B, H, W, C, _stream()),
+               "dwconv3x3_bwd_pre")
+
+
+# ------------------------------------------------------------------------------------------------
+# movers
+# ------------------------------------------------------------------------------------------------
+def im2col_nchw(x, col, k, s, p, Ho, Wo):
+    B, Cin, H, W = x.shape
+    assert x.is_contiguous() and x.dtype == torch.float32
+    _lib.check(_lib.load().cmx_im2col_nchw(x.data_ptr(), col.data_ptr(), B, Cin, H, W, k, s, p, Ho, Wo, col.shape[1], _stream()),
+               "im2col_nchw")
+    return col
+
+
+def im2col_nhwc(x, col, B, H, W, k, s, p, Ho, Wo):
+    C = x.shape[1]
+    _lib.check(_lib.load().cmx_im2col_nhwc(x.data_ptr(), _ld(x), col.data_ptr(), B, H, W, C, k, s, p, Ho, Wo, _stream()), "im2col_nhwc")
+    return col
+
+
+def col2im_nhwc(dcol, dx, B, H, W, k, s, p, Ho, Wo, add=None):
+    C = dx.shape[1]
+    _lib.check(_lib.load().cmx_col2im_nhwc(dcol.data_ptr(), _p(add), _dt(add) if add is not None else F32,
+                                           _ld(add) if add is not None else 0, dx.data_ptr(), _dt(dx), _ld(dx), B, H, W, C, k, s, p,
+                                           Ho, Wo, _stream()), "col2im_nhwc")
+    return dx
+
+
+def convw_pack(w, wp):
+    Co, Ci, kh, kw = w.shape
+    _lib.check(_lib.load().cmx_convw_pack(w.data_ptr(), wp.data_ptr(), Co, Ci, kh, kw, wp.shape[1], _stream()), "convw_pack")
+    return wp
+
+
+def convw_unpack_grad(gp, gw):
+    Co, Ci, kh, kw = gw.shape
+    _lib.check(_lib.load().cmx_convw_unpack_grad(gp.data_ptr(), gw.data_ptr(), Co, Ci, kh, kw, gp.shape[1], _stream()), "convw_unpack_grad")
+
+
+def cast_f32_bf16(x, y):
+    _lib.check(_lib.load().cmx_cast_f32_bf16(x.data_ptr(), y.data_ptr(), x.numel(), _stream()), "cast_f32_bf16")
+    return y
+
+
+def cast_bf16_f32(x, y):
+    _lib.check(_lib.load().cmx_cast_bf16_f32(x.data_ptr(), y.data_ptr(), x.numel(), _stream()), "cast_bf16_f32")
+    return y
+
+
+def colsum(x, out):
+    M, N = x.shape
+    _lib.check(_lib.load().cmx_colsum(x.data_ptr(), _dt(x), _ld(x), out.data_ptr(), M, N, _stream()), "colsum")
+
+
+def relu_bwd_(dy, y):
+    M, N = dy.shape
+    _lib.check(_lib.load().cmx_relu_bwd(dy.data_ptr(), _ld(dy), y.data_ptr(), _ld(y), M, N, _stream()), "relu_bwd")
+    return dy
+
+
+def axpby(a, x, b, y, out):
+    _lib.check(_lib.load().cmx_axpby_f32(a, x.data_ptr(), b, _p(y), out.data_ptr(), x.numel(), _stream()), "axpby")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# softmax
+# ------------------------------------------------------------------------------------------------
+def softmax_rows_fwd(s, p):
+    rows, n = s.shape
+    _lib.check(_lib.load().cmx_softmax_rows_fwd(s.data_ptr(), _ld(s), p.data_ptr(), _ld(p), rows, n, _stream()), "softmax_rows_fwd")
+    return p
+
+
+def softmax_rows_bwd(p, dp, scale, ds):
+    rows, n = p.shape
+    _lib.check(_lib.load().cmx_softmax_rows_bwd(p.data_ptr(), _ld(p), dp.data_ptr(), _ld(dp), scale, ds.data_ptr(), _ld(ds), rows, n,
+                                                _stream()), "softmax_rows_bwd")
+    return ds
+
+
+def softmax_dim2_fwd(c, scale, p32, p16):
+    nb, d, _ = c.shape
+    _lib.check(_lib.load().cmx_softmax_dim2_fwd(c.data_ptr(), scale, p32.data_ptr(), p16.data_ptr(), nb, d, _stream()), "softmax_dim2_fwd")
+
+
+def softmax_dim2_bwd(p32, dp, scale, dc16):
+    nb, d, _ = p32.shape
+    _lib.check(_lib.load().cmx_softmax_dim2_bwd(p32.data_ptr(), dp.data_ptr(), scale, dc16.data_ptr(), nb, d, _stream()), "softmax_dim2_bwd")
+
+
+# ------------------------------------------------------------------------------------------------
+# FRM
+# ------------------------------------------------------------------------------------------------
+def pool_avgmax_fwd(x, y, argmax, B, HW):
+    C2 = x.shape[1]
+    _lib.check(_lib.load().cmx_pool_avgmax_fwd(x.data_ptr(), _ld(x), y.data_ptr(), argmax.data_ptr(), B, HW, C2, _stream()), "pool_avgmax_fwd")
+
+
+def pool_avgmax_bwd(dy, argmax, dx, B, HW):
+    C2 = dx.shape[1]
+    _lib.check(_lib.load().cmx_pool_avgmax_bwd(dy.data_ptr(), argmax.data_ptr(), dx.data_ptr(), _ld(dx), B, HW, C2, _stream()), "pool_avgmax_bwd")
+
+
+def smallm_linear_fwd(x, w, b, act, y):
+    Mb, K = x.shape
+    N = w.shape[0]
+    _lib.check(_lib.load().cmx_smallm_linear_fwd(x.data_ptr(), w.data_ptr(), _p(b), act, y.data_ptr(), Mb, N, K, _stream()), "smallm_linear_fwd")
+    return y
+
+
+def smallm_linear_bwd(dy, y, act, x, w, dx, dw, db, ws):
+    Mb, K = x.shape
+    N = w.shape[0]
+    _lib.check(_lib.load().cmx_smallm_linear_bwd(dy.data_ptr(), y.data_ptr(), act, x.data_ptr(), w.data_ptr(), _p(dx), _p(dw), _p(db),
+                                                 ws.data_ptr(), Mb, N, K, _stream()), "smallm_linear_bwd")
+
+
+def frm_rectify_fwd(a, t, w2, b2, cw, sw, r1, r2, B, HW):
+    C = t.shape[1]
+    _lib.check(_lib.load().cmx_frm_rectify_fwd(a.data_ptr(), _ld(a), t.data_ptr(), _ld(t), w2.data_ptr(), b2.data_ptr(), cw.data_ptr(),
+                                               sw.data_ptr(), r1.data_ptr(), _ld(r1), r2.data_ptr(), _ld(r2), B, HW, C, _stream()),
+               "frm_rectify_fwd")
+
+
+def frm_rectify_bwd(dr1, dr2, a, t, w2, cw, sw, da, dt, dcw, dw2, db2, B, HW):
+    C = t.shape[1]
+    _lib.check(_lib.load().cmx_frm_rectify_bwd(dr1.data_ptr(), _ld(dr1), dr2.data_ptr(), _ld(dr2), a.data_ptr(), _ld(a), t.data_ptr(),
+                                               _ld(t), w2.data_ptr(), cw.data_ptr(), sw.data_ptr(), da.data_ptr(), _ld(da),
+                                               dt.data_ptr(), _ld(dt), dcw.data_ptr(), dw2.data_ptr(), db2.data_ptr(), B, HW, C,
+                                               _stream()), "frm_rectify_bwd")
+
+
+# ------------------------------------------------------------------------------------------------
+# decoder / loss / metric
+# ------------------------------------------------------------------------------------------------
+def upsample_sum_fwd(zs, sizes, bias, out, B, C):
+    """zs: [z0, z1, z2, z3] bf16 (z0 at output resolution; later entries may be None); sizes: [(H,W)]*4"""
+    z = list(zs) + [None] * (4 - len(zs))
+    sz = list(sizes) + [(1, 1)] * (4 - len(sizes))
+    _lib.check(_lib.load().cmx_upsample_sum_fwd(_p(z[0]), _p(z[1]), _p(z[2]), _p(z[3]), sz[0][0], sz[0][1], sz[1][0], sz[1][1],
+                                                sz[2][0], sz[2][1], sz[3][0], sz[3][1], _p(bias), out.data_ptr(), B, C, _stream()),
+               "upsample_sum_fwd")
+    return out
+
+
+def upsample_bwd(dout, Ho, Wo, dz, Hi, Wi, B, C):
+    _lib.check(_lib.load().cmx_upsample_bwd(dout.data_ptr(), Ho, Wo, dz.data_ptr(), Hi, Wi, B, C, _stream()), "upsample_bwd")
+    return dz
+
+
+def ce_upsampled(logits, label, ignore_index, acc, dlogits, B, h, w, H, W, ncls):
+    assert label.dtype == torch.int64 and label.is_contiguous()
+    _lib.check(_lib.load().cmx_ce_upsampled_fwd_bwd(logits.data_ptr(), label.data_ptr(), ignore_index, acc.data_ptr(), _p(dlogits),
+                                                    B, h, w, H, W, ncls, _stream()), "ce_upsampled_fwd_bwd")
+
+
+def ce_finalize(acc, loss, dlogits=None, gscale=None, out=None):
+    n = dlogits.numel() if dlogits is not None else 0
+    _lib.check(_lib.load().cmx_ce_finalize(acc.data_ptr(), _p(loss), _p(dlogits), _p(gscale), _p(out),
+                                           _dt(out) if out is not None else F32, n, _stream()), "ce_finalize")
+
+
+def logits_upsample_nchw(logits, out, B, h, w, H, W, ncls):
+    _lib.check(_lib.load().cmx_logits_upsample_nchw(logits.data_ptr(), out.data_ptr(), B, h, w, H, W, ncls, _stream()), "logits_upsample_nchw")
+    return out
+
+
+_INT_TAG = {torch.uint8: 0, torch.int32: 1, torch.int64: 2}
+
+
+def confusion(pred, gt, n_cl, hist, stats):
+    _cuda(pred, gt, hist, stats)
+    assert pred.is_contiguous() and gt.is_contiguous() and pred.numel() == gt.numel()
+    _lib.check(_lib.load().cmx_confusion(pred.data_ptr(), _INT_TAG[pred.dtype], gt.data_ptr(), _INT_TAG[gt.dtype], pred.numel(), n_cl,
+                                         hist.data_ptr(), stats.data_ptr(), _stream()), "confusion")
+
+
+def argmax_confusion(scores, gt, n_cl, hist, stats, pred_out=None):
+    """scores: [n_cl, H, W] fp32 contiguous (one image); gt may be None (argmax only)."""
+    _cuda(scores)
+    assert scores.is_contiguous() and scores.dtype == torch.float32 and scores.shape[0] == n_cl
+    npix = scores[0].numel()
+    _lib.check(_lib.load().cmx_argmax_confusion(scores.data_ptr(), _p(gt), _INT_TAG[gt.dtype] if gt is not None else 0, npix, n_cl,
+                                                _p(pred_out), _p(hist), _p(stats), _stream()), "argmax_confusion")

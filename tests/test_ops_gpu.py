@@ -1,0 +1,400 @@
+"""GPU parity tests, kernel by kernel, through the C ABI (ctypes) against plain PyTorch fp32 references
+of the same op on the same seeded inputs.  Tolerances: bf16 storage => 2^-8 relative on outputs of
+magnitude ~1; fp32 paths 1e-4/1e-5; integer paths bit-exact."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    from rgbx_semantic_segmentation_b200 import ops
+
+DEV = "cuda"
+bf = torch.bfloat16
+
+
+def rnd(*shape, scale=1.0, dtype=torch.float32, seed=None):
+    if seed is not None:
+        torch.manual_seed(seed)
+    return (torch.randn(*shape, device=DEV) * scale).to(dtype)
+
+
+def close(a, b, rtol, atol, what=""):
+    a, b = a.float(), b.float()
+    err = (a - b).abs()
+    tol = atol + rtol * b.abs()
+    bad = err > tol
+    assert not bad.any(), "%s: %d/%d mismatches, max err %.4g (ref max %.4g)" % (
+        what, int(bad.sum()), bad.numel(), float(err.max()), float(b.abs().max()))
+
+
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("impl", [1])
+@pytest.mark.parametrize("M,N,K,ta,tb", [
+    (300, 64, 64, False, False), (130, 9, 512, False, False), (257, 72, 100, False, False),
+    (192, 96, 333, True, True), (100, 64, 40, False, True), (64, 2, 64, False, False)])
+def test_gemm_fallback(M, N, K, ta, tb, impl):
+    torch.manual_seed(0)
+    a = rnd(K, M, dtype=bf) if ta else rnd(M, K, dtype=bf)
+    b = rnd(K, N, dtype=bf) if tb else rnd(N, K, dtype=bf)
+    bias = rnd(N)
+    res = rnd(M, N)
+    out = torch.empty(M, N, device=DEV, dtype=torch.float32)
+    ops.mm(a, b, out, ta=ta, tb=tb, bias=bias, residual=res, act=ops.ACT_RELU, alpha=0.5, impl=impl)
+    A = a.float().t() if ta else a.float()
+    Bm = b.float() if tb else b.float().t()
+    ref = res + torch.relu(0.5 * (A @ Bm) + bias)
+    close(out, ref, 1e-4, 1e-3 * K ** 0.5 / 8, "gemm fallback")
+
+
+def test_gemm_fallback_batched_splitk():
+    torch.manual_seed(1)
+    B1, B2, M, N, K = 2, 3, 70, 40, 900
+    a = rnd(B1, B2, K, M, dtype=bf)   # stored [K, M]  (trans_a)
+    b = rnd(B1, B2, K, N, dtype=bf)   # stored [K, N]  (trans_b)
+    out = torch.zeros(B1, B2, M, N, device=DEV)
+    ops.gemm_raw(a, b, out, M, N, K, M, N, N, trans_a=True, trans_b=True, batch=(B1, B2), sA=(B2 * K * M, K * M),
+                 sB=(B2 * K * N, K * N), sC=(B2 * M * N, M * N), split_k=4, accumulate=True, alpha=0.125)
+    ref = 0.125 * torch.matmul(a.float().transpose(-1, -2), b.float())
+    close(out, ref, 1e-4, 2e-3, "batched split-K")
+
+
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("C,xdt,ydt", [(64, torch.float32, bf), (320, torch.float32, torch.float32), (512, bf, bf), (160, bf, torch.float32)])
+def test_layernorm_fwd_bwd(C, xdt, ydt):
+    torch.manual_seed(2)
+    M = 777
+    x = rnd(M, C, scale=2.0).add_(0.5).to(xdt)
+    g = (1 + 0.1 * rnd(C))
+    b = 0.1 * rnd(C)
+    y = torch.empty(M, C, device=DEV, dtype=ydt)
+    mean = torch.empty(M, device=DEV)
+    rstd = torch.empty(M, device=DEV)
+    ops.layernorm_fwd(x, g, b, 1e-6, y, mean, rstd)
+    xr = x.float().requires_grad_(True)
+    gr, br = g.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    ref = F.layer_norm(xr, (C,), gr, br, 1e-6)
+    close(y, ref, 1e-2 if ydt == bf else 1e-5, 1e-2 if ydt == bf else 1e-5, "ln fwd")
+    # backward with two upstream grads, residual grad, per-sample scale on the bf16 copy
+    dy = rnd(M, C, dtype=bf)
+    dy2 = rnd(M, C, dtype=bf)
+    dres = rnd(M, C)
+    rows_per_sample = 111
+    scale = torch.tensor([1.0, 0.0, 1.5, 1.0, 2.0, 1.0, 0.5], device=DEV)
+    dx = torch.empty(M, C, device=DEV)
+    dxbf = torch.empty(M, C, device=DEV, dtype=bf)
+    dg = torch.zeros(C, device=DEV)
+    db = torch.zeros(C, device=DEV)
+    ops.layernorm_bwd(dy, x, mean, rstd, g, dy2=dy2, dres=dres, dx=dx, dx_bf=dxbf, scale=scale, rows_per_sample=rows_per_sample,
+                      dgamma=dg, dbeta=db)
+    up = dy.float() + dy2.float()
+    ref.backward(up)
+    close(dx, xr.grad + dres, 1e-3, 2e-3, "ln dx")
+    sc = scale.repeat_interleave(rows_per_sample)[:M, None]
+    close(dxbf, (xr.grad + dres) * sc, 1e-2, 2e-2, "ln dx bf16")
+    close(dg, gr.grad, 1e-3, 1e-2, "ln dgamma")
+    close(db, br.grad, 1e-3, 1e-2, "ln dbeta")
+
+
+# ---------------------------------------------------------------------------------------------
+def test_batchnorm_train_fwd_bwd():
+    torch.manual_seed(3)
+    B, HW, C = 3, 50, 64
+    M = B * HW
+    x = rnd(M, C, scale=1.5) + 0.3
+    res = rnd(M, C, dtype=bf)
+    g = 1 + 0.1 * rnd(C)
+    b = 0.1 * rnd(C)
+    mask = ((torch.rand(B, C, device=DEV) > 0.2).float() / 0.8)
+    rm, rv = torch.zeros(C, device=DEV), torch.ones(C, device=DEV)
+    nbt = torch.zeros((), dtype=torch.int64, device=DEV)
+    ws = torch.zeros(2 * C, dtype=torch.float64, device=DEV)
+    mean, invstd = torch.empty(C, device=DEV), torch.empty(C, device=DEV)
+    ops.colstats(x, ws[:C], ws[C:])
+    ops.bn_finalize(ws[:C], ws[C:], M, 1e-3, 0.1, rm, rv, nbt, mean, invstd)
+    y = torch.empty(M, C, device=DEV, dtype=bf)
+    ops.bn_apply(x, mean, invstd, g, b, y, residual=res, relu=True, mask=mask, rows_per_sample=HW)
+    xr = x.clone().requires_grad_(True)
+    gr, br = g.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    rm2, rv2 = torch.zeros(C, device=DEV), torch.ones(C, device=DEV)
+    xb = F.batch_norm(xr.t().reshape(1, C, M), rm2, rv2, gr, br, True, 0.1, 1e-3).reshape(C, M).t()
+    ref = torch.relu(xb + res.float()) * mask.repeat_interleave(HW, 0)
+    close(y, ref, 1e-2, 1e-2, "bn apply")
+    close(rm, rm2, 1e-5, 1e-6, "running mean")
+    close(rv, rv2, 1e-5, 1e-6, "running var")
+    assert int(nbt) == 1
+    dy = rnd(M, C, dtype=bf)
+    ref.backward(dy.float())
+    dx = torch.empty(M, C, device=DEV)
+    dres = torch.empty(M, C, device=DEV)
+    dg, db = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV)
+    ws.zero_()
+    ops.bn_bwd(dy, x, mean, invstd, g, b, dx, dg, db, ws, residual=res, relu=True, mask=mask, rows_per_sample=HW, dres=dres)
+    close(dx, xr.grad, 1e-3, 1e-3, "bn dx")
+    close(dg, gr.grad, 1e-3, 1e-2, "bn dgamma")
+    close(db, br.grad, 1e-3, 1e-2, "bn dbeta")
+
+
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("act", [2, 1, 0])
+@pytest.mark.parametrize("B,H,W,C", [(2, 15, 20, 256), (1, 7, 5, 64), (2, 30, 41, 1280)])
+def test_dwconv(act, B, H, W, C):
+    torch.manual_seed(4)
+    x = rnd(B * H * W, C, dtype=bf)
+    w = rnd(C, 1, 3, 3, scale=0.3)
+    bias = rnd(C, scale=0.1)
+    y = torch.empty_like(x)
+    ops.dwconv3x3_fwd(x, w, bias, act, y, B, H, W)
+    xr = x.float().reshape(B, H, W, C).permute(0, 3, 1, 2).requires_grad_(True)
+    wr, br = w.clone().requires_grad_(True), bias.clone().requires_grad_(True)
+    u = F.conv2d(xr, wr, br, padding=1, groups=C)
+    ref = F.gelu(u) if act == 2 else (F.relu(u) if act == 1 else u)
+    close(y, ref.permute(0, 2, 3, 1).reshape(-1, C), 1e-2, 1e-2, "dwconv fwd")
+    dy = rnd(B * H * W, C, dtype=bf)
+    ref.backward(dy.float().reshape(B, H, W, C).permute(0, 3, 1, 2))
+    du = torch.empty_like(x)
+    dw, db = torch.zeros(C, 9, device=DEV), torch.zeros(C, device=DEV)
+    ops.dwconv3x3_bwd_pre(x, w, bias, act, dy, du, dw, db, B, H, W)
+    dx = torch.empty_like(x)
+    ops.dwconv3x3_fwd(du, w, None, 0, dx, B, H, W, flip=True)
+    close(dx, xr.grad.permute(0, 2, 3, 1).reshape(-1, C), 2e-2, 2e-2, "dwconv dx")
+    n = (B * H * W) ** 0.5
+    close(dw.reshape(C, 1, 3, 3), wr.grad, 1e-2, 2e-2 * n, "dwconv dw")
+    close(db, br.grad, 1e-2, 2e-2 * n, "dwconv db")
+
+
+# ---------------------------------------------------------------------------------------------
+def test_im2col_paths():
+    torch.manual_seed(5)
+    B, H, W = 2, 37, 50
+    img = rnd(B, 3, H, W)
+    Ho, Wo = (H + 6 - 7) // 4 + 1, (W + 6 - 7) // 4 + 1
+    col = torch.empty(B * Ho * Wo, 160, device=DEV, dtype=bf)
+    ops.im2col_nchw(img, col, 7, 4, 3, Ho, Wo)
+    w = rnd(64, 3, 7, 7, scale=0.1)
+    wp = torch.empty(64, 160, device=DEV, dtype=bf)
+    ops.convw_pack(w, wp)
+    got = col.float() @ wp.float().t()
+    ref = F.conv2d(img.to(bf).float(), w.to(bf).float(), stride=4, padding=3).permute(0, 2, 3, 1).reshape(-1, 64)
+    close(got, ref, 1e-3, 1e-3, "im2col_nchw + pack == conv")
+    # NHWC 3x3 s2 p1 and its adjoint
+    C = 64
+    x = rnd(B * H * W, C, dtype=bf)
+    Ho, Wo = (H + 2 - 3) // 2 + 1, (W + 2 - 3) // 2 + 1
+    col = torch.empty(B * Ho * Wo, 9 * C, device=DEV, dtype=bf)
+    ops.im2col_nhwc(x, col, B, H, W, 3, 2, 1, Ho, Wo)
+    xr = x.float().reshape(B, H, W, C).permute(0, 3, 1, 2).requires_grad_(True)
+    unf = F.unfold(xr, 3, padding=1, stride=2)  # [B, C*9, L] with (c, kh, kw) ordering
+    ref = unf.reshape(B, C, 9, Ho * Wo).permute(0, 3, 2, 1).reshape(B * Ho * Wo, 9 * C)
+    assert torch.equal(col.float(), ref.detach())
+    dcol = rnd(B * Ho * Wo, 9 * C, dtype=bf)
+    ref.backward(dcol.float())
+    add = rnd(B * H * W, C)
+    dx = torch.empty(B * H * W, C, device=DEV)
+    ops.col2im_nhwc(dcol, dx, B, H, W, 3, 2, 1, Ho, Wo, add=add)
+    close(dx, xr.grad.permute(0, 2, 3, 1).reshape(-1, C) + add, 1e-5, 1e-5, "col2im")
+    # SR patchify k=s=4, H not divisible
+    Hk, Wk = (H - 4) // 4 + 1, (W - 4) // 4 + 1
+    col = torch.empty(B * Hk * Wk, 16 * C, device=DEV, dtype=bf)
+    ops.im2col_nhwc(x, col, B, H, W, 4, 4, 0, Hk, Wk)
+    unf = F.unfold(x.float().reshape(B, H, W, C).permute(0, 3, 1, 2), 4, stride=4)
+    ref = unf.reshape(B, C, 16, Hk * Wk).permute(0, 3, 2, 1).reshape(B * Hk * Wk, 16 * C)
+    assert torch.equal(col.float(), ref)
+    # conv weight grad unpack
+    gp = rnd(64, 160)
+    gw = torch.ones(64, 3, 7, 7, device=DEV)
+    ops.convw_unpack_grad(gp, gw)
+    ref = 1 + gp[:, :147].reshape(64, 7, 7, 3).permute(0, 3, 1, 2)
+    close(gw, ref, 0, 1e-6, "unpack grad")
+
+
+def test_casts_colsum_relu():
+    torch.manual_seed(6)
+    x = rnd(1003)
+    pad = torch.empty(1008, device=DEV, dtype=bf)
+    ops.cast_f32_bf16(x, pad[:1003])
+    assert torch.equal(pad[:1003], x.to(bf))
+    m = rnd(999, 72, dtype=bf)
+    out = torch.ones(72, device=DEV)
+    ops.colsum(m, out)
+    close(out, 1 + m.float().sum(0), 1e-4, 1e-3, "colsum")
+    y = rnd(40, 64, dtype=bf)
+    dy = rnd(40, 64, dtype=bf)
+    ref = dy.float() * (y.float() > 0)
+    ops.relu_bwd_(dy, y)
+    assert torch.equal(dy.float(), ref)
+
+
+def test_softmax_kernels():
+    torch.manual_seed(7)
+    rows, n = 1000, 300
+    s = rnd(rows, n, scale=3.0)
+    p = torch.empty(rows, n, device=DEV, dtype=bf)
+    ops.softmax_rows_fwd(s, p)
+    ref = torch.softmax(s, -1)
+    close(p, ref, 1e-2, 1e-4, "softmax rows")
+    dp = rnd(rows, n)
+    ds = torch.empty(rows, n, device=DEV, dtype=bf)
+    ops.softmax_rows_bwd(p, dp, 0.125, ds)
+    pf = p.float()
+    refd = 0.125 * pf * (dp - (pf * dp).sum(-1, keepdim=True))
+    close(ds, refd, 1e-2, 1e-4, "softmax rows bwd")
+    nb, d = 6, 64
+    c = rnd(nb, d, d, scale=20.0)
+    p32 = torch.empty(nb, d, d, device=DEV)
+    p16 = torch.empty(nb, d, d, device=DEV, dtype=bf)
+    ops.softmax_dim2_fwd(c, 0.125, p32, p16)
+    ref = torch.softmax(c * 0.125, dim=-2)
+    close(p32, ref, 1e-4, 1e-6, "softmax dim2")
+    close(p16, ref, 1e-2, 1e-5, "softmax dim2 bf16")
+    dpp = rnd(nb, d, d)
+    dc = torch.empty(nb, d, d, device=DEV, dtype=bf)
+    ops.softmax_dim2_bwd(p32, dpp, 0.125, dc)
+    refd = 0.125 * p32 * (dpp - (p32 * dpp).sum(-2, keepdim=True))
+    close(dc, refd, 1e-2, 1e-5, "softmax dim2 bwd")
+
+
+# ---------------------------------------------------------------------------------------------
+def test_frm_kernels():
+    torch.manual_seed(8)
+    B, HW, C = 3, 77, 64
+    M = B * HW
+    a = rnd(M, 2 * C, dtype=bf)
+    y = torch.empty(B, 4 * C, device=DEV)
+    am = torch.empty(B, 2 * C, device=DEV, dtype=torch.int32)
+    ops.pool_avgmax_fwd(a, y, am, B, HW)
+    af = a.float().reshape(B, HW, 2 * C)
+    close(y[:, :2 * C], af.mean(1), 1e-5, 1e-5, "avg pool")
+    assert torch.equal(y[:, 2 * C:], af.amax(1))
+    assert torch.equal(am.long(), af.argmax(1)) or torch.equal(torch.gather(af, 1, am.long()[:, None])[:, 0], af.amax(1))
+    # small-M MLP
+    w0, b0 = rnd(4 * C, 4 * C, scale=0.1), rnd(4 * C, scale=0.1)
+    hid = torch.empty(B, 4 * C, device=DEV)
+    ops.smallm_linear_fwd(y, w0, b0, 1, hid)
+    yr = y.clone().requires_grad_(True)
+    w0r, b0r = w0.clone().requires_grad_(True), b0.clone().requires_grad_(True)
+    refh = torch.relu(F.linear(yr, w0r, b0r))
+    close(hid, refh, 1e-4, 1e-4, "smallm fwd")
+    dh = rnd(B, 4 * C)
+    refh.backward(dh)
+    dx = torch.empty(B, 4 * C, device=DEV)
+    dw, db = torch.zeros_like(w0), torch.zeros_like(b0)
+    ws = torch.empty(B, 4 * C, device=DEV)
+    ops.smallm_linear_bwd(dh, hid, 1, y, w0, dx, dw, db, ws)
+    close(dx, yr.grad, 1e-4, 1e-4, "smallm dx")
+    close(dw, w0r.grad, 1e-4, 1e-4, "smallm dw")
+    close(db, b0r.grad, 1e-4, 1e-4, "smallm db")
+    # pool backward
+    dyp = rnd(B, 4 * C)
+    dxa = torch.zeros(M, 2 * C, device=DEV)
+    ops.pool_avgmax_bwd(dyp, am, dxa, B, HW)
+    ar = a.float().reshape(B, HW, 2 * C).requires_grad_(True)
+    (torch.cat([ar.mean(1), ar.amax(1)], 1) * dyp).sum().backward()
+    close(dxa, ar.grad.reshape(M, 2 * C), 1e-5, 1e-6, "pool bwd")
+    # rectify
+    t = torch.relu(rnd(M, C)).to(bf)
+    w2, b2 = rnd(2, C, scale=0.2), rnd(2, scale=0.1)
+    cw = torch.sigmoid(rnd(B, 2 * C))
+    sw = torch.empty(M, 2, device=DEV)
+    r1 = torch.empty(M, C, device=DEV, dtype=bf)
+    r2 = torch.empty(M, C, device=DEV, dtype=bf)
+    ops.frm_rectify_fwd(a, t, w2, b2, cw, sw, r1, r2, B, HW)
+    a1 = a[:, :C].float().clone().requires_grad_(True)
+    a2 = a[:, C:].float().clone().requires_grad_(True)
+    tr = t.float().clone().requires_grad_(True)
+    w2r, b2r, cwr = w2.clone().requires_grad_(True), b2.clone().requires_grad_(True), cw.clone().requires_grad_(True)
+    swr = torch.sigmoid(tr @ w2r.t() + b2r)
+    cwm = cwr.repeat_interleave(HW, 0)
+    o1 = a1 + 0.5 * cwm[:, C:] * a2 + 0.5 * swr[:, 1:2] * a2
+    o2 = a2 + 0.5 * cwm[:, :C] * a1 + 0.5 * swr[:, 0:1] * a1
+    close(sw, swr, 1e-4, 1e-5, "spatial weights")
+    close(r1, o1, 1e-2, 1e-2, "rectify out1")
+    close(r2, o2, 1e-2, 1e-2, "rectify out2")
+    d1, d2 = rnd(M, C), rnd(M, C)
+    (o1 * d1 + o2 * d2).sum().backward()
+    da = torch.empty(M, 2 * C, device=DEV)
+    dt = torch.empty(M, C, device=DEV, dtype=bf)
+    dcw, dw2, db2 = torch.zeros(B, 2 * C, device=DEV), torch.zeros(2, C, device=DEV), torch.zeros(2, device=DEV)
+    ops.frm_rectify_bwd(d1, d2, a, t, w2, cw, sw, da, dt, dcw, dw2, db2, B, HW)
+    close(da[:, :C], a1.grad, 1e-4, 1e-4, "rectify da1")
+    close(da[:, C:], a2.grad, 1e-4, 1e-4, "rectify da2")
+    close(dt, tr.grad * (t.float() > 0), 1e-2, 1e-3, "rectify dt")
+    close(dcw, cwr.grad, 1e-3, 1e-3, "rectify dcw")
+    close(dw2, w2r.grad, 1e-3, 1e-3, "rectify dw2")
+    close(db2, b2r.grad, 1e-3, 1e-3, "rectify db2")
+
+
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("sizes", [[(24, 32), (12, 16), (6, 8), (3, 4)], [(45, 80), (23, 40), (12, 20), (6, 10)]])
+def test_upsample_sum_and_adjoint(sizes):
+    torch.manual_seed(9)
+    B, C = 2, 64
+    zs = [rnd(B * h * w, C, dtype=bf) for h, w in sizes]
+    bias = rnd(C)
+    H0, W0 = sizes[0]
+    out = torch.empty(B * H0 * W0, C, device=DEV)
+    ops.upsample_sum_fwd(zs, sizes, bias, out, B, C)
+    zr = [z.float().reshape(B, h, w, C).permute(0, 3, 1, 2).requires_grad_(True) for z, (h, w) in zip(zs, sizes)]
+    ref = zr[0] + bias[None, :, None, None]
+    for z in zr[1:]:
+        ref = ref + F.interpolate(z, size=(H0, W0), mode="bilinear", align_corners=False)
+    close(out, ref.permute(0, 2, 3, 1).reshape(-1, C), 1e-5, 1e-5, "upsample sum")
+    dout = rnd(B * H0 * W0, C, dtype=bf)
+    ref.backward(dout.float().reshape(B, H0, W0, C).permute(0, 3, 1, 2))
+    for i in (1, 2, 3):
+        h, w = sizes[i]
+        dz = torch.empty(B * h * w, C, device=DEV, dtype=bf)
+        ops.upsample_bwd(dout, H0, W0, dz, h, w, B, C)
+        close(dz, zr[i].grad.permute(0, 2, 3, 1).reshape(-1, C), 1e-2, 2e-2, "upsample adjoint %d" % i)
+
+
+@pytest.mark.parametrize("h,w,H,W,ncls", [(12, 16, 48, 64, 9), (23, 40, 90, 160, 5), (5, 7, 19, 27, 9)])
+def test_ce_upsampled(h, w, H, W, ncls):
+    torch.manual_seed(10)
+    B = 2
+    logits = rnd(B, h, w, ncls, scale=2.0)
+    label = torch.randint(0, ncls, (B, H, W), device=DEV)
+    label[torch.rand(B, H, W, device=DEV) < 0.1] = 255
+    label[:, :3] = 255
+    acc = torch.zeros(2, dtype=torch.float64, device=DEV)
+    dl = torch.zeros_like(logits)
+    ops.ce_upsampled(logits, label, 255, acc, dl, B, h, w, H, W, ncls)
+    loss = torch.empty((), device=DEV)
+    gs = torch.tensor(2.0, device=DEV)
+    dout = torch.empty_like(logits)
+    ops.ce_finalize(acc, loss, dl, gs, dout)
+    lr = logits.permute(0, 3, 1, 2).clone().requires_grad_(True)
+    up = F.interpolate(lr, size=(H, W), mode="bilinear", align_corners=False)
+    ref = F.cross_entropy(up, label, ignore_index=255)
+    (2.0 * ref).backward()
+    assert abs(float(loss) - float(ref)) < 1e-5 * max(1, abs(float(ref)))
+    assert float(acc[1]) == float((label != 255).sum())
+    close(dout, lr.grad.permute(0, 2, 3, 1), 1e-3, 1e-6, "ce dlogits")
+    full = torch.empty(B, ncls, H, W, device=DEV)
+    ops.logits_upsample_nchw(logits, full, B, h, w, H, W, ncls)
+    close(full, up, 1e-5, 1e-5, "logits upsample")
+
+
+def test_confusion_bit_exact():
+    from oracle import metric_ref
+    rng = np.random.default_rng(0)
+    for n_cl, shape in [(9, (480, 640)), (5, (37, 53)), (40, (64, 64)), (9, (1, 1))]:
+        pred = rng.integers(0, n_cl, shape).astype(np.int64)
+        gt = rng.integers(0, n_cl, shape).astype(np.uint8)
+        gt[rng.random(shape) < 0.1] = 255
+        h_ref, lab, cor = metric_ref.hist_info(n_cl, pred, gt)
+        hist = torch.zeros(n_cl, n_cl, dtype=torch.int64, device=DEV)
+        stats = torch.zeros(2, dtype=torch.int64, device=DEV)
+        ops.confusion(torch.from_numpy(pred).to(DEV), torch.from_numpy(gt).to(DEV), n_cl, hist, stats)
+        assert np.array_equal(hist.cpu().numpy(), h_ref)
+        assert stats.tolist() == [lab, cor]
+        scores = torch.randn(n_cl, *shape, device=DEV)
+        hist.zero_(); stats.zero_()
+        pred8 = torch.empty(shape, dtype=torch.uint8, device=DEV)
+        ops.argmax_confusion(scores, torch.from_numpy(gt).to(DEV), n_cl, hist, stats, pred8)
+        p_ref = scores.cpu().numpy().argmax(0)
+        h_ref, lab, cor = metric_ref.hist_info(n_cl, p_ref, gt)
+        assert np.array_equal(pred8.cpu().numpy(), p_ref)
+        assert np.array_equal(hist.cpu().numpy(), h_ref) and stats.tolist() == [lab, cor]
