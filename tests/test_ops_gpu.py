@@ -291,7 +291,9 @@ def test_frm_kernels():
     dxa = torch.zeros(M, 2 * C, device=DEV)
     ops.pool_avgmax_bwd(dyp, am, dxa, B, HW)
     ar = a.float().reshape(B, HW, 2 * C).requires_grad_(True)
-    (torch.cat([ar.mean(1), ar.amax(1)], 1) * dyp).sum().backward()
+    # the reference pools with nn.AdaptiveMaxPool2d (net_utils.py:15): gradient goes to the FIRST maximum
+    mx = F.adaptive_max_pool2d(ar.permute(0, 2, 1).reshape(B, 2 * C, HW, 1), 1).reshape(B, 2 * C)
+    (torch.cat([ar.mean(1), mx], 1) * dyp).sum().backward()
     close(dxa, ar.grad.reshape(M, 2 * C), 1e-5, 1e-6, "pool bwd")
     # rectify
     t = torch.relu(rnd(M, C)).to(bf)
