@@ -144,7 +144,7 @@ def frm(sd: SD, p: str, x1: Tensor, x2: Tensor) -> Tuple[Tensor, Tensor]:
     B, C, H, W = x1.shape
     x = torch.cat((x1, x2), dim=1)
     avg = x.mean(dim=(2, 3))
-    mx = x.amax(dim=(2, 3))
+    mx = F.adaptive_max_pool2d(x, 1).flatten(1)  # nn.AdaptiveMaxPool2d(1): gradient goes to the first maximum
     y = torch.cat((avg, mx), dim=1)
     y = F.relu(F.linear(y, sd[p + ".channel_weights.mlp.0.weight"], sd[p + ".channel_weights.mlp.0.bias"]))
     y = torch.sigmoid(F.linear(y, sd[p + ".channel_weights.mlp.2.weight"], sd[p + ".channel_weights.mlp.2.bias"]))
@@ -233,31 +233,46 @@ def ffm(sd: SD, p: str, x1: Tensor, x2: Tensor, heads: int, training: bool, new_
 def backbone(sd: SD, spec: MitSpec, rgb: Tensor, x: Tensor, training: bool = False,
              new_stats: Optional[SD] = None,
              dp_scales: Optional[Dict[str, Tuple[Tensor, Tensor]]] = None,
-             p: str = "backbone") -> List[Tensor]:
+             p: str = "backbone", trace: Optional[Dict[str, Tensor]] = None) -> List[Tensor]:
     """dual_segformer.py:366-442.  ``dp_scales`` maps a block prefix (e.g.
     ``backbone.block1.2``) to its (attn, mlp) per-sample DropPath multipliers."""
     B = rgb.shape[0]
     outs = []
     x_rgb, x_e = rgb, x
+
+    def tr(key, t, nchw=False):
+        if trace is not None:
+            t = t.detach()
+            trace[key] = t.permute(0, 2, 3, 1).reshape(-1, t.shape[1]) if nchw else t.reshape(-1, t.shape[-1])
+
     for s in range(4):
         k, st = (7, 4) if s == 0 else (3, 2)
         x_rgb, H, W = overlap_patch_embed(sd, f"{p}.patch_embed{s + 1}", x_rgb, k, st)
         x_e, _, _ = overlap_patch_embed(sd, f"{p}.extra_patch_embed{s + 1}", x_e, k, st)
+        tr(f"{p}.patch_embed{s + 1}", x_rgb)
+        tr(f"{p}.extra_patch_embed{s + 1}", x_e)
         for i in range(spec.depths[s]):
             bp = f"{p}.block{s + 1}.{i}"
             x_rgb = block(sd, bp, x_rgb, H, W, spec.num_heads[s], spec.sr_ratios[s],
                           None if dp_scales is None else dp_scales.get(bp))
+            tr(bp, x_rgb)
         for i in range(spec.depths[s]):
             bp = f"{p}.extra_block{s + 1}.{i}"
             x_e = block(sd, bp, x_e, H, W, spec.num_heads[s], spec.sr_ratios[s],
                         None if dp_scales is None else dp_scales.get(bp))
+            tr(bp, x_e)
         C = spec.embed_dims[s]
         x_rgb = F.layer_norm(x_rgb, (C,), sd[f"{p}.norm{s + 1}.weight"], sd[f"{p}.norm{s + 1}.bias"], 1e-6)
         x_e = F.layer_norm(x_e, (C,), sd[f"{p}.extra_norm{s + 1}.weight"], sd[f"{p}.extra_norm{s + 1}.bias"], 1e-6)
         x_rgb = x_rgb.reshape(B, H, W, -1).permute(0, 3, 1, 2).contiguous()
         x_e = x_e.reshape(B, H, W, -1).permute(0, 3, 1, 2).contiguous()
+        tr(f"{p}.norm{s + 1}", x_rgb, True)
+        tr(f"{p}.extra_norm{s + 1}", x_e, True)
         x_rgb, x_e = frm(sd, f"{p}.FRMs.{s}", x_rgb, x_e)
+        tr(f"{p}.FRMs.{s}.out1", x_rgb, True)
+        tr(f"{p}.FRMs.{s}.out2", x_e, True)
         outs.append(ffm(sd, f"{p}.FFMs.{s}", x_rgb, x_e, spec.num_heads[s], training, new_stats))
+        tr(f"{p}.FFMs.{s}", outs[-1], True)
     return outs
 
 
@@ -287,18 +302,20 @@ def decoder_head(sd: SD, feats: Sequence[Tensor], training: bool = False, bn_eps
 
 def encode_decode(sd: SD, spec: MitSpec, rgb: Tensor, x: Tensor, training: bool = False,
                   decoder_bn_eps: float = 1e-5, new_stats: Optional[SD] = None,
-                  dp_scales=None, dropout_scale=None) -> Tensor:
+                  dp_scales=None, dropout_scale=None, trace=None) -> Tensor:
     """models/builder.py:212-238 — backbone → decoder → bilinear to input size."""
-    feats = backbone(sd, spec, rgb, x, training, new_stats, dp_scales)
+    feats = backbone(sd, spec, rgb, x, training, new_stats, dp_scales, trace=trace)
     out = decoder_head(sd, feats, training, decoder_bn_eps, 0.1, new_stats, dropout_scale)
+    if trace is not None:
+        trace["decode_head.logits"] = out.detach().permute(0, 2, 3, 1).reshape(-1, out.shape[1])
     return F.interpolate(out, size=rgb.shape[2:], mode="bilinear", align_corners=False)
 
 
 def forward(sd: SD, spec: MitSpec, rgb: Tensor, x: Tensor, label: Optional[Tensor] = None,
             training: bool = False, decoder_bn_eps: float = 1e-5, ignore_index: int = 255,
-            new_stats: Optional[SD] = None, dp_scales=None, dropout_scale=None) -> Tensor:
+            new_stats: Optional[SD] = None, dp_scales=None, dropout_scale=None, trace=None) -> Tensor:
     """models/builder.py:240-253 with criterion = CrossEntropyLoss(mean, ignore 255) (train.py:72-73)."""
-    out = encode_decode(sd, spec, rgb, x, training, decoder_bn_eps, new_stats, dp_scales, dropout_scale)
+    out = encode_decode(sd, spec, rgb, x, training, decoder_bn_eps, new_stats, dp_scales, dropout_scale, trace)
     if label is not None:
         return F.cross_entropy(out, label.long(), ignore_index=ignore_index, reduction="mean")
     return out

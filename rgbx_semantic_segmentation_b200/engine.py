@@ -1,0 +1,773 @@
+"""Execution engine of the CMX hot path: explicit forward + hand-derived backward of the dual-branch
+MiT encoder, FRM/FFM fusion, MLP decoder and CE loss, expressed as a sequence of sm_100a kernel
+launches (ops.py) over token-major bf16 activations with an fp32 residual stream.
+
+Reference semantics restated here (file:line of ynalcakan/RGBX_Semantic_Segmentation):
+  encoder  models/encoders/dual_segformer.py:366-442 (stage loop), :116-138 (SR attention),
+           :67-74 (Mix-FFN), :176-180 (Block), :217-225 (OverlapPatchEmbed)
+  fusion   models/net_utils.py:22-30, 79-83, 147-152 (FRM); :199-214, 273-281, 323-329, 376-384 (FFM)
+  decoder  models/decoders/MLPDecoder.py:59-81   loss  models/builder.py:233, 249 (CE, ignore 255)
+
+Design notes
+  * parameters are views into ONE flat fp32 buffer (so one cast kernel makes the bf16 operand copies and
+    one memset clears all gradients); gradients are accumulated by the wgrad kernels straight into a flat
+    fp32 buffer with the same layout.
+  * training runs forward AND backward inside `forward_backward` (so the whole step is one stream of
+    launches that can be captured in a single CUDA graph); autograd only hands the finished gradients
+    to the parameters.
+  * linear_fuse (1x1 conv over the 2048-channel concat) is applied per stage at native resolution —
+    bilinear interpolation commutes with a per-pixel linear map — so the concat tensor never exists.
+"""
+import torch
+
+from . import ops
+from .ops import ACT_GELU, ACT_NONE, ACT_RELU, ACT_SIGMOID
+
+bf16 = torch.bfloat16
+f32 = torch.float32
+
+
+def conv_out(n, k, s, p):
+    return (n + 2 * p - k) // s + 1
+
+
+class _NS:
+    """plain attribute bag for saved activations"""
+    pass
+
+
+class Engine:
+    ALIGN = 64  # elements; keeps every parameter 256-byte aligned in the fp32 buffer (128 B in bf16)
+
+    def __init__(self, model):
+        self.model = model
+        bb = model.backbone
+        self.dims, self.heads, self.depths, self.srs = bb.embed_dims, bb.num_heads, bb.depths, bb.sr_ratios
+        self.embed = model.decode_head.linear_pred.in_channels
+        self.ncls = model.decode_head.num_classes
+        self.names = [n for n, _ in model.named_parameters()]
+        self.flat_p = None
+        self.forced_dp = None        # test hook: {block prefix: tensor[2,B]}
+        self.forced_dropout = None   # test hook: tensor[B, E]
+        self.stochastic = True       # DropPath / Dropout2d active in training mode
+        self.trace = None            # debug hook: dict filled with fp32 copies of intermediate activations
+
+    # ------------------------------------------------------------------------------------------
+    # flat parameter / gradient storage
+    # ------------------------------------------------------------------------------------------
+    def _flatten(self, device):
+        params = dict(self.model.named_parameters())
+        off, total = {}, 0
+        for n in self.names:
+            off[n] = total
+            total += (params[n].numel() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        flat = torch.zeros(total, device=device, dtype=f32)
+        for n in self.names:
+            p = params[n]
+            v = flat[off[n]:off[n] + p.numel()].view(p.shape)
+            v.copy_(p.data)
+            p.data = v
+        self.off, self.total = off, total
+        self.shape = {n: tuple(params[n].shape) for n in self.names}
+        self.flat_p = flat
+        self.flat_g = torch.zeros(total, device=device, dtype=f32)
+        self.flat_w = torch.zeros(total, device=device, dtype=bf16)
+        self.params = params
+        self.packed = {}
+        self.buffers = dict(self.model.named_buffers())
+        # DropPath table (block prefix, probability) — device tensor built once (graph capture forbids H2D)
+        self._dp_keys, probs = [], []
+        for s in range(4):
+            for pre in ("block", "extra_block"):
+                for i, blk in enumerate(getattr(self.model.backbone, f"{pre}{s + 1}")):
+                    p = getattr(blk.drop_path, "drop_prob", 0.0)
+                    if p > 0:
+                        self._dp_keys.append(f"backbone.{pre}{s + 1}.{i}")
+                        probs.append(p)
+        self._dp_pt = torch.tensor(probs, dtype=f32).view(-1, 1, 1).to(device) if probs else None
+
+    def _ensure_flat(self, device):
+        """(Re)build the flat storage when the parameters moved (model.to()/.cuda() re-creates p.data)."""
+        if self.flat_p is not None and self.flat_p.device == device:
+            first, last = self.names[0], self.names[-1]
+            if (self.params[first].data_ptr() == self.flat_p.data_ptr() + 4 * self.off[first] and
+                    self.params[last].data_ptr() == self.flat_p.data_ptr() + 4 * self.off[last]):
+                return
+        for n, p in self.model.named_parameters():
+            if p.device != device:
+                raise RuntimeError("cmx_b200: parameter %s is on %s but the inputs are on %s — call model.cuda() first"
+                                   % (n, p.device, device))
+            break
+        self._flatten(device)
+
+    def P(self, name):
+        o = self.off[name]
+        return self.flat_p[o:o + self._numel(name)].view(self.shape[name])
+
+    def G(self, name):
+        o = self.off[name]
+        return self.flat_g[o:o + self._numel(name)].view(self.shape[name])
+
+    def W(self, name):
+        """bf16 copy of a Linear / 1x1-conv weight as a 2-D [out, in] matrix"""
+        o = self.off[name]
+        s = self.shape[name]
+        return self.flat_w[o:o + self._numel(name)].view(s[0], -1)
+
+    def G2(self, name):
+        s = self.shape[name]
+        return self.G(name).view(s[0], -1)
+
+    def _numel(self, name):
+        n = 1
+        for d in self.shape[name]:
+            n *= d
+        return n
+
+    def refresh_weights(self):
+        """fp32 master -> bf16 operand copies (one flat cast) + (kh,kw,ci)-packed conv weights"""
+        ops.cast_f32_bf16(self.flat_p, self.flat_w)
+        for n in self.names:
+            s = self.shape[n]
+            if len(s) == 4 and s[2] > 1 and s[1] > 1:  # real (non-depthwise, non-1x1) convs: patch embeds, SR
+                k = s[1] * s[2] * s[3]
+                kpad = (k + 7) // 8 * 8
+                if n not in self.packed:
+                    self.packed[n] = torch.empty(s[0], kpad, device=self.flat_p.device, dtype=bf16)
+                ops.convw_pack(self.P(n), self.packed[n])
+
+    # ------------------------------------------------------------------------------------------
+    # small helpers
+    # ------------------------------------------------------------------------------------------
+    def E(self, *shape, dtype=bf16):
+        return torch.empty(*shape, device=self.dev, dtype=dtype)
+
+    def Z(self, *shape, dtype=f32):
+        return torch.zeros(*shape, device=self.dev, dtype=dtype)
+
+    def tr(self, key, t):
+        if self.trace is not None:
+            self.trace[key] = t.detach().float().clone()
+
+    def linear_wgrad(self, dy, x, wname, bname=None):
+        """dW[out,in] += dy[tok,out]^T x[tok,in];  db += colsum(dy)"""
+        ops.mm(dy, x, self.G2(wname), ta=True, tb=True, accumulate=True)
+        if bname is not None:
+            ops.colsum(dy, self.G(bname))
+
+    # ------------------------------------------------------------------------------------------
+    # stochastic-depth / dropout multipliers
+    # ------------------------------------------------------------------------------------------
+    def _make_dp(self, B, training):
+        if not training:
+            return {}, None
+        if self.forced_dp is not None or self.forced_dropout is not None:
+            dp = {k: v.to(self.dev, f32).contiguous() for k, v in (self.forced_dp or {}).items()}
+            dm = None if self.forced_dropout is None else self.forced_dropout.to(self.dev, f32).contiguous()
+            return dp, dm
+        if not self.stochastic:
+            return {}, None
+        dp = {}
+        if self._dp_keys:
+            pt = self._dp_pt
+            u = torch.rand(len(self._dp_keys), 2, B, device=self.dev)
+            sc = (u >= pt).to(f32) / (1.0 - pt)
+            for j, k in enumerate(self._dp_keys):
+                dp[k] = sc[j]
+        dm = None
+        drop = self.model.decode_head.dropout
+        if drop is not None and drop.p > 0:
+            dm = (torch.rand(B, self.embed, device=self.dev) >= drop.p).to(f32) / (1.0 - drop.p)
+        return dp, dm
+
+    # ------------------------------------------------------------------------------------------
+    # OverlapPatchEmbed
+    # ------------------------------------------------------------------------------------------
+    def pe_fwd(self, name, inp, s, B, H, W, save):
+        C = self.dims[s]
+        if s == 0:
+            k, st, pd = 7, 4, 3
+            Ho, Wo = conv_out(H, k, st, pd), conv_out(W, k, st, pd)
+            wp = self.packed[name + ".proj.weight"]
+            col = self.E(B * Ho * Wo, wp.shape[1])
+            ops.im2col_nchw(inp, col, k, st, pd, Ho, Wo)
+        else:
+            k, st, pd = 3, 2, 1
+            Ho, Wo = conv_out(H, k, st, pd), conv_out(W, k, st, pd)
+            wp = self.packed[name + ".proj.weight"]
+            col = self.E(B * Ho * Wo, wp.shape[1])
+            ops.im2col_nhwc(inp, col, B, H, W, k, st, pd, Ho, Wo)
+        M = B * Ho * Wo
+        y = self.E(M, C, dtype=f32)
+        ops.mm(col, wp, y, bias=self.P(name + ".proj.bias"))
+        x0 = self.E(M, C, dtype=f32)
+        mean, rstd = (self.E(M, dtype=f32), self.E(M, dtype=f32)) if save else (None, None)
+        ops.layernorm_fwd(y, self.P(name + ".norm.weight"), self.P(name + ".norm.bias"), 1e-5, x0, mean, rstd)
+        c = _NS()
+        c.name, c.s, c.col, c.y, c.mean, c.rstd, c.Ho, c.Wo, c.H, c.W, c.wp = name, s, col, y, mean, rstd, Ho, Wo, H, W, wp
+        return x0, Ho, Wo, c
+
+    def pe_bwd(self, c, dx0, B):
+        """returns dcol (bf16) for stages >= 1 (the caller scatters it with col2im), None for stage 0"""
+        name = c.name
+        M, C = c.y.shape
+        dy = self.E(M, C)
+        ops.layernorm_bwd(dx0, c.y, c.mean, c.rstd, self.P(name + ".norm.weight"), dx=dy,
+                          dgamma=self.G(name + ".norm.weight"), dbeta=self.G(name + ".norm.bias"))
+        gp = self.Z(C, c.wp.shape[1])
+        ops.mm(dy, c.col, gp, ta=True, tb=True, accumulate=True)
+        ops.convw_unpack_grad(gp, self.G(name + ".proj.weight"))
+        ops.colsum(dy, self.G(name + ".proj.bias"))
+        if c.s == 0:
+            return None
+        dcol = self.E(M, c.wp.shape[1])
+        ops.mm(dy, c.wp, dcol, tb=True)
+        return dcol
+
+    # ------------------------------------------------------------------------------------------
+    # transformer Block
+    # ------------------------------------------------------------------------------------------
+    def block_fwd(self, p, x, B, H, W, s, dp, save):
+        C, heads, R = self.dims[s], self.heads[s], self.srs[s]
+        d = C // heads
+        N = H * W
+        M = B * N
+        scale = d ** -0.5
+        c = _NS()
+        c.p, c.s, c.H, c.W, c.x, c.dp = p, s, H, W, x, dp
+        st = (lambda: self.E(M, dtype=f32)) if save else (lambda: None)
+        xn1 = self.E(M, C)
+        c.m1, c.r1 = st(), st()
+        ops.layernorm_fwd(x, self.P(p + ".norm1.weight"), self.P(p + ".norm1.bias"), 1e-6, xn1, c.m1, c.r1)
+        q = self.E(M, C)
+        ops.mm(xn1, self.W(p + ".attn.q.weight"), q, bias=self.P(p + ".attn.q.bias"))
+        if R > 1:
+            Hk, Wk = conv_out(H, R, R, 0), conv_out(W, R, R, 0)
+            Nk = Hk * Wk
+            wsr = self.packed[p + ".attn.sr.weight"]
+            pat = self.E(B * Nk, wsr.shape[1])
+            ops.im2col_nhwc(xn1, pat, B, H, W, R, R, 0, Hk, Wk)
+            sr = self.E(B * Nk, C, dtype=f32)
+            ops.mm(pat, wsr, sr, bias=self.P(p + ".attn.sr.bias"))
+            srn = self.E(B * Nk, C)
+            c.ms, c.rs = (self.E(B * Nk, dtype=f32), self.E(B * Nk, dtype=f32)) if save else (None, None)
+            ops.layernorm_fwd(sr, self.P(p + ".attn.norm.weight"), self.P(p + ".attn.norm.bias"), 1e-5, srn, c.ms, c.rs)
+            kv_in = srn
+            c.pat, c.sr, c.Hk, c.Wk = pat, sr, Hk, Wk
+        else:
+            Nk = N
+            kv_in = xn1
+        kv = self.E(B * Nk, 2 * C)
+        ops.mm(kv_in, self.W(p + ".attn.kv.weight"), kv, bias=self.P(p + ".attn.kv.bias"))
+        # S = scale * Q K^T  (fp32, transient), P = softmax(S), O = P V
+        S = self.E(B * heads * N, Nk, dtype=f32)
+        ops.gemm_raw(q, kv, S, N, Nk, d, C, 2 * C, Nk, batch=(B, heads), sA=(N * C, d), sB=(Nk * 2 * C, d),
+                     sC=(heads * N * Nk, N * Nk), alpha=scale)
+        Pm = self.E(B * heads * N, Nk)
+        ops.softmax_rows_fwd(S, Pm)
+        del S
+        O = self.E(M, C)
+        ops.gemm_raw(Pm, kv, O, N, d, Nk, Nk, 2 * C, C, b_off=C, trans_b=True, batch=(B, heads),
+                     sA=(heads * N * Nk, N * Nk), sB=(Nk * 2 * C, d), sC=(N * C, d))
+        x1 = self.E(M, C, dtype=f32)
+        ops.mm(O, self.W(p + ".attn.proj.weight"), x1, bias=self.P(p + ".attn.proj.bias"), residual=x,
+               row_scale=None if dp is None else dp[0], rows_per_sample=N)
+        xn2 = self.E(M, C)
+        c.m2, c.r2 = st(), st()
+        ops.layernorm_fwd(x1, self.P(p + ".norm2.weight"), self.P(p + ".norm2.bias"), 1e-6, xn2, c.m2, c.r2)
+        h = self.E(M, 4 * C)
+        ops.mm(xn2, self.W(p + ".mlp.fc1.weight"), h, bias=self.P(p + ".mlp.fc1.bias"))
+        g = self.E(M, 4 * C)
+        ops.dwconv3x3_fwd(h, self.P(p + ".mlp.dwconv.dwconv.weight"), self.P(p + ".mlp.dwconv.dwconv.bias"), ACT_GELU, g, B, H, W)
+        x2 = self.E(M, C, dtype=f32)
+        ops.mm(g, self.W(p + ".mlp.fc2.weight"), x2, bias=self.P(p + ".mlp.fc2.bias"), residual=x1,
+               row_scale=None if dp is None else dp[1], rows_per_sample=N)
+        if save:
+            c.xn1, c.q, c.kv, c.kv_in, c.Pm, c.O, c.x1, c.xn2, c.h, c.g, c.Nk = xn1, q, kv, kv_in, Pm, O, x1, xn2, h, g, Nk
+        return x2, c
+
+    def block_bwd(self, c, dx2, dx2_bf, B, prev_scale, need_bf):
+        """dx2: fp32 grad of the block output; dx2_bf: bf16 copy already multiplied by this block's MLP
+        DropPath scale.  Returns (dx fp32, dx_bf bf16 scaled by `prev_scale` or None)."""
+        p, s, H, W = c.p, c.s, c.H, c.W
+        C, heads, R = self.dims[s], self.heads[s], self.srs[s]
+        d = C // heads
+        N = H * W
+        M = B * N
+        Nk = c.Nk
+        scale = d ** -0.5
+        # ---- Mix-FFN
+        self.linear_wgrad(dx2_bf, c.g, p + ".mlp.fc2.weight", p + ".mlp.fc2.bias")
+        dg = self.E(M, 4 * C)
+        ops.mm(dx2_bf, self.W(p + ".mlp.fc2.weight"), dg, tb=True)
+        du = self.E(M, 4 * C)
+        ops.dwconv3x3_bwd_pre(c.h, self.P(p + ".mlp.dwconv.dwconv.weight"), self.P(p + ".mlp.dwconv.dwconv.bias"), ACT_GELU,
+                              dg, du, self.G(p + ".mlp.dwconv.dwconv.weight").view(4 * C, 9), self.G(p + ".mlp.dwconv.dwconv.bias"),
+                              B, H, W)
+        dh = dg
+        ops.dwconv3x3_fwd(du, self.P(p + ".mlp.dwconv.dwconv.weight"), None, ACT_NONE, dh, B, H, W, flip=True)
+        del du
+        self.linear_wgrad(dh, c.xn2, p + ".mlp.fc1.weight", p + ".mlp.fc1.bias")
+        dxn2 = self.E(M, C)
+        ops.mm(dh, self.W(p + ".mlp.fc1.weight"), dxn2, tb=True)
+        del dh, dg
+        dx1 = self.E(M, C, dtype=f32)
+        dx1_bf = self.E(M, C)
+        ops.layernorm_bwd(dxn2, c.x1, c.m2, c.r2, self.P(p + ".norm2.weight"), dres=dx2, dx=dx1, dx_bf=dx1_bf,
+                          scale=None if c.dp is None else c.dp[0], rows_per_sample=N,
+                          dgamma=self.G(p + ".norm2.weight"), dbeta=self.G(p + ".norm2.bias"))
+        # ---- attention
+        self.linear_wgrad(dx1_bf, c.O, p + ".attn.proj.weight", p + ".attn.proj.bias")
+        dO = self.E(M, C)
+        ops.mm(dx1_bf, self.W(p + ".attn.proj.weight"), dO, tb=True)
+        dkv = self.E(B * Nk, 2 * C)
+        bs = (B, heads)
+        sP = (heads * N * Nk, N * Nk)
+        # dV = P^T dO
+        ops.gemm_raw(c.Pm, dO, dkv, Nk, d, N, Nk, C, 2 * C, c_off=C, trans_a=True, trans_b=True, batch=bs, sA=sP,
+                     sB=(N * C, d), sC=(Nk * 2 * C, d))
+        # dP = dO V^T
+        dP = self.E(B * heads * N, Nk, dtype=f32)
+        ops.gemm_raw(dO, c.kv, dP, N, Nk, d, C, 2 * C, Nk, b_off=C, batch=bs, sA=(N * C, d), sB=(Nk * 2 * C, d), sC=sP)
+        dS = self.E(B * heads * N, Nk)
+        ops.softmax_rows_bwd(c.Pm, dP, scale, dS)
+        del dP
+        # dQ = dS K ; dK = dS^T Q
+        dq = self.E(M, C)
+        ops.gemm_raw(dS, c.kv, dq, N, d, Nk, Nk, 2 * C, C, trans_b=True, batch=bs, sA=sP, sB=(Nk * 2 * C, d), sC=(N * C, d))
+        ops.gemm_raw(dS, c.q, dkv, Nk, d, N, Nk, C, 2 * C, trans_a=True, trans_b=True, batch=bs, sA=sP, sB=(N * C, d),
+                     sC=(Nk * 2 * C, d))
+        del dS
+        self.linear_wgrad(dkv, c.kv_in, p + ".attn.kv.weight", p + ".attn.kv.bias")
+        dkvin = self.E(B * Nk, C)
+        ops.mm(dkv, self.W(p + ".attn.kv.weight"), dkvin, tb=True)
+        if R > 1:
+            dsr = self.E(B * Nk, C)
+            ops.layernorm_bwd(dkvin, c.sr, c.ms, c.rs, self.P(p + ".attn.norm.weight"), dx=dsr,
+                              dgamma=self.G(p + ".attn.norm.weight"), dbeta=self.G(p + ".attn.norm.bias"))
+            wsr = self.packed[p + ".attn.sr.weight"]
+            gp = self.Z(C, wsr.shape[1])
+            ops.mm(dsr, c.pat, gp, ta=True, tb=True, accumulate=True)
+            ops.convw_unpack_grad(gp, self.G(p + ".attn.sr.weight"))
+            ops.colsum(dsr, self.G(p + ".attn.sr.bias"))
+            dpat = self.E(B * Nk, wsr.shape[1])
+            ops.mm(dsr, wsr, dpat, tb=True)
+            dxn_b = self.E(M, C)
+            ops.col2im_nhwc(dpat, dxn_b, B, H, W, R, R, 0, c.Hk, c.Wk)
+        else:
+            dxn_b = dkvin
+        self.linear_wgrad(dq, c.xn1, p + ".attn.q.weight", p + ".attn.q.bias")
+        dxn_a = self.E(M, C)
+        ops.mm(dq, self.W(p + ".attn.q.weight"), dxn_a, tb=True)
+        dx = self.E(M, C, dtype=f32)
+        dx_bf = self.E(M, C) if need_bf else None
+        ops.layernorm_bwd(dxn_a, c.x, c.m1, c.r1, self.P(p + ".norm1.weight"), dy2=dxn_b, dres=dx1, dx=dx, dx_bf=dx_bf,
+                          scale=prev_scale, rows_per_sample=N,
+                          dgamma=self.G(p + ".norm1.weight"), dbeta=self.G(p + ".norm1.bias"))
+        return dx, dx_bf
+
+    # ------------------------------------------------------------------------------------------
+    # FRM
+    # ------------------------------------------------------------------------------------------
+    def frm_fwd(self, s, cat12, B, HW, save):
+        p = f"backbone.FRMs.{s}"
+        C = self.dims[s]
+        M = B * HW
+        c = _NS()
+        y = self.E(B, 4 * C, dtype=f32)
+        am = self.E(B, 2 * C, dtype=torch.int32)
+        ops.pool_avgmax_fwd(cat12, y, am, B, HW)
+        hid = self.E(B, 4 * C, dtype=f32)
+        ops.smallm_linear_fwd(y, self.P(p + ".channel_weights.mlp.0.weight"), self.P(p + ".channel_weights.mlp.0.bias"), ACT_RELU, hid)
+        cw = self.E(B, 2 * C, dtype=f32)
+        ops.smallm_linear_fwd(hid, self.P(p + ".channel_weights.mlp.2.weight"), self.P(p + ".channel_weights.mlp.2.bias"), ACT_SIGMOID, cw)
+        t = self.E(M, C)
+        ops.mm(cat12, self.W(p + ".spatial_weights.mlp.0.weight"), t, bias=self.P(p + ".spatial_weights.mlp.0.bias"), act=ACT_RELU)
+        sw = self.E(M, 2, dtype=f32)
+        r1, r2 = self.E(M, C), self.E(M, C)
+        ops.frm_rectify_fwd(cat12, t, self.P(p + ".spatial_weights.mlp.2.weight").view(2, C), self.P(p + ".spatial_weights.mlp.2.bias"),
+                            cw, sw, r1, r2, B, HW)
+        c.p, c.s, c.cat12, c.y, c.am, c.hid, c.cw, c.t, c.sw = p, s, cat12, y, am, hid, cw, t, sw
+        return r1, r2, c
+
+    def frm_bwd(self, c, dr1, dr2, B, HW):
+        """dr1/dr2 fp32 [M,C] -> dcat fp32 [M,2C] (grad of the two stage-norm outputs)"""
+        p, s = c.p, c.s
+        C = self.dims[s]
+        M = B * HW
+        dcat = self.E(M, 2 * C, dtype=f32)
+        dt = self.E(M, C)
+        dcw = self.Z(B, 2 * C)
+        ops.frm_rectify_bwd(dr1, dr2, c.cat12, c.t, self.P(p + ".spatial_weights.mlp.2.weight").view(2, C), c.cw, c.sw, dcat, dt, dcw,
+                            self.G(p + ".spatial_weights.mlp.2.weight").view(2, C), self.G(p + ".spatial_weights.mlp.2.bias"), B, HW)
+        self.linear_wgrad(dt, c.cat12, p + ".spatial_weights.mlp.0.weight", p + ".spatial_weights.mlp.0.bias")
+        ops.mm(dt, self.W(p + ".spatial_weights.mlp.0.weight"), dcat, tb=True, residual=dcat)
+        dhid = self.E(B, 4 * C, dtype=f32)
+        ws = self.E(B, 4 * C, dtype=f32)
+        ops.smallm_linear_bwd(dcw, c.cw, ACT_SIGMOID, c.hid, self.P(p + ".channel_weights.mlp.2.weight"), dhid,
+                              self.G(p + ".channel_weights.mlp.2.weight"), self.G(p + ".channel_weights.mlp.2.bias"), ws)
+        dy = self.E(B, 4 * C, dtype=f32)
+        ops.smallm_linear_bwd(dhid, c.hid, ACT_RELU, c.y, self.P(p + ".channel_weights.mlp.0.weight"), dy,
+                              self.G(p + ".channel_weights.mlp.0.weight"), self.G(p + ".channel_weights.mlp.0.bias"), ws)
+        ops.pool_avgmax_bwd(dy, c.am, dcat, B, HW)
+        return dcat
+
+    # ------------------------------------------------------------------------------------------
+    # BatchNorm helper (train: batch statistics + running update; eval: running statistics)
+    # ------------------------------------------------------------------------------------------
+    def bn_stats(self, prefix, module, x, training):
+        C = x.shape[1]
+        mean, invstd = self.E(C, dtype=f32), self.E(C, dtype=f32)
+        rm, rv = self.buffers[prefix + ".running_mean"], self.buffers[prefix + ".running_var"]
+        if training:
+            ws = self.Z(2 * C, dtype=torch.float64)
+            ops.colstats(x, ws[:C], ws[C:])
+            mom = module.momentum if module.momentum is not None else 0.1
+            ops.bn_finalize(ws[:C], ws[C:], x.shape[0], module.eps, mom, rm, rv,
+                            self.buffers[prefix + ".num_batches_tracked"], mean, invstd)
+        else:
+            ops.bn_eval_stats(rm, rv, module.eps, mean, invstd)
+        return mean, invstd
+
+    # ------------------------------------------------------------------------------------------
+    # FFM
+    # ------------------------------------------------------------------------------------------
+    def ffm_fwd(self, s, r, B, H, W, training, save):
+        p = f"backbone.FFMs.{s}"
+        C, heads = self.dims[s], self.heads[s]
+        d = C // heads
+        N = H * W
+        M = B * N
+        scale = d ** -0.5
+        mod = self.model.backbone.FFMs[s]
+        c = _NS()
+        c.p, c.s, c.H, c.W, c.r = p, s, H, W, r
+        c.yv, c.u, c.kv, c.p32, c.p16 = [], [], [], [], []
+        for i in (0, 1):
+            wcp = self.W(p + f".cross.channel_proj{i + 1}.weight")
+            bcp = self.P(p + f".cross.channel_proj{i + 1}.bias")
+            yv = self.E(M, 2 * C)
+            ops.mm(r[i], wcp[:C], yv[:, :C], bias=bcp[:C], act=ACT_RELU)
+            u = self.E(M, C)
+            ops.mm(r[i], wcp[C:], u, bias=bcp[C:], act=ACT_RELU)
+            kv = self.E(M, 2 * C)
+            ops.mm(u, self.W(p + f".cross.cross_attn.kv{i + 1}.weight"), kv)
+            ctx = self.Z(B * heads, d, d)
+            ops.gemm_raw(kv, kv, ctx, d, d, N, 2 * C, 2 * C, d, b_off=C, trans_a=True, trans_b=True, batch=(B, heads),
+                         sA=(N * 2 * C, d), sB=(N * 2 * C, d), sC=(heads * d * d, d * d), accumulate=True,
+                         split_k=max(1, min(16, N // 2048)))
+            p32, p16 = self.E(B * heads, d, d, dtype=f32), self.E(B * heads, d, d)
+            ops.softmax_dim2_fwd(ctx, scale, p32, p16)
+            c.yv.append(yv); c.u.append(u); c.kv.append(kv); c.p32.append(p32); c.p16.append(p16)
+        merge = self.E(M, 2 * C)
+        c.e, c.me, c.re = [], [], []
+        for i in (0, 1):
+            # v_i = q_i ctx_{other}
+            ops.gemm_raw(c.u[i], c.p16[1 - i], c.yv[i], N, d, d, C, d, 2 * C, c_off=C, trans_b=True, batch=(B, heads),
+                         sA=(N * C, d), sB=(heads * d * d, d * d), sC=(N * 2 * C, d))
+            e = self.E(M, C, dtype=f32)
+            ops.mm(c.yv[i], self.W(p + f".cross.end_proj{i + 1}.weight"), e, bias=self.P(p + f".cross.end_proj{i + 1}.bias"),
+                   residual=r[i])
+            me, re = (self.E(M, dtype=f32), self.E(M, dtype=f32)) if save else (None, None)
+            ops.layernorm_fwd(e, self.P(p + f".cross.norm{i + 1}.weight"), self.P(p + f".cross.norm{i + 1}.bias"), 1e-5,
+                              merge[:, i * C:(i + 1) * C], me, re)
+            c.e.append(e); c.me.append(me); c.re.append(re)
+        q = p + ".channel_emb"
+        res = self.E(M, C, dtype=f32)
+        ops.mm(merge, self.W(q + ".residual.weight"), res)
+        c0 = self.E(M, C)
+        ops.mm(merge, self.W(q + ".channel_embed.0.weight"), c0, bias=self.P(q + ".channel_embed.0.bias"))
+        c1 = self.E(M, C)
+        ops.dwconv3x3_fwd(c0, self.P(q + ".channel_embed.1.weight"), self.P(q + ".channel_embed.1.bias"), ACT_RELU, c1, B, H, W)
+        c3 = self.E(M, C, dtype=f32)
+        ops.mm(c1, self.W(q + ".channel_embed.3.weight"), c3, bias=self.P(q + ".channel_embed.3.bias"))
+        bn1, bn2 = mod.channel_emb.channel_embed[4], mod.channel_emb.norm
+        c.mean1, c.inv1 = self.bn_stats(q + ".channel_embed.4", bn1, c3, training)
+        z = self.E(M, C, dtype=f32)
+        ops.bn_apply(c3, c.mean1, c.inv1, self.P(q + ".channel_embed.4.weight"), self.P(q + ".channel_embed.4.bias"), z, residual=res)
+        c.mean2, c.inv2 = self.bn_stats(q + ".norm", bn2, z, training)
+        out = self.E(M, C)
+        ops.bn_apply(z, c.mean2, c.inv2, self.P(q + ".norm.weight"), self.P(q + ".norm.bias"), out)
+        c.merge, c.c0, c.c1, c.c3, c.z = merge, c0, c1, c3, z
+        return out, c
+
+    def ffm_bwd(self, c, dout, B):
+        """dout bf16 [M,C] (grad of the fused feature) -> [dr1, dr2] fp32 (grad of the rectified inputs)"""
+        p, s, H, W = c.p, c.s, c.H, c.W
+        C, heads = self.dims[s], self.heads[s]
+        d = C // heads
+        N = H * W
+        M = B * N
+        scale = d ** -0.5
+        q = p + ".channel_emb"
+        ws = self.Z(2 * C, dtype=torch.float64)
+        dz = self.E(M, C, dtype=f32)
+        ops.bn_bwd(dout, c.z, c.mean2, c.inv2, self.P(q + ".norm.weight"), self.P(q + ".norm.bias"), dz,
+                   self.G(q + ".norm.weight"), self.G(q + ".norm.bias"), ws)
+        ws2 = self.Z(2 * C, dtype=torch.float64)
+        dc3, dz_bf = self.E(M, C), self.E(M, C)
+        ops.bn_bwd(dz, c.c3, c.mean1, c.inv1, self.P(q + ".channel_embed.4.weight"), self.P(q + ".channel_embed.4.bias"), dc3,
+                   self.G(q + ".channel_embed.4.weight"), self.G(q + ".channel_embed.4.bias"), ws2, dres=dz_bf)
+        del dz
+        self.linear_wgrad(dc3, c.c1, q + ".channel_embed.3.weight", q + ".channel_embed.3.bias")
+        dc1 = self.E(M, C)
+        ops.mm(dc3, self.W(q + ".channel_embed.3.weight"), dc1, tb=True)
+        du = self.E(M, C)
+        ops.dwconv3x3_bwd_pre(c.c0, self.P(q + ".channel_embed.1.weight"), self.P(q + ".channel_embed.1.bias"), ACT_RELU, dc1, du,
+                              self.G(q + ".channel_embed.1.weight").view(C, 9), self.G(q + ".channel_embed.1.bias"), B, H, W)
+        dc0 = dc1
+        ops.dwconv3x3_fwd(du, self.P(q + ".channel_embed.1.weight"), None, ACT_NONE, dc0, B, H, W, flip=True)
+        self.linear_wgrad(dc0, c.merge, q + ".channel_embed.0.weight", q + ".channel_embed.0.bias")
+        self.linear_wgrad(dz_bf, c.merge, q + ".residual.weight")
+        dmerge = self.E(M, 2 * C)
+        ops.mm(dc0, self.W(q + ".channel_embed.0.weight"), dmerge, tb=True)
+        ops.mm(dz_bf, self.W(q + ".residual.weight"), dmerge, tb=True, residual=dmerge)
+        de, dyv = [], []
+        for i in (0, 1):
+            de_i, de_bf = self.E(M, C, dtype=f32), self.E(M, C)
+            ops.layernorm_bwd(dmerge[:, i * C:(i + 1) * C], c.e[i], c.me[i], c.re[i], self.P(p + f".cross.norm{i + 1}.weight"),
+                              dx=de_i, dx_bf=de_bf, dgamma=self.G(p + f".cross.norm{i + 1}.weight"),
+                              dbeta=self.G(p + f".cross.norm{i + 1}.bias"))
+            self.linear_wgrad(de_bf, c.yv[i], p + f".cross.end_proj{i + 1}.weight", p + f".cross.end_proj{i + 1}.bias")
+            dyv_i = self.E(M, 2 * C)
+            ops.mm(de_bf, self.W(p + f".cross.end_proj{i + 1}.weight"), dyv_i, tb=True)
+            de.append(de_i); dyv.append(dyv_i)
+        bs = (B, heads)
+        sctx = (heads * d * d, d * d)
+        split = max(1, min(16, N // 2048))
+        dPc = [None, None]
+        du = [None, None]
+        for i in (0, 1):
+            o = 1 - i
+            # v_i = q_i ctx_o  =>  dctx_o = q_i^T dv_i ;  du_i = dv_i ctx_o^T
+            dp_ = self.Z(B * heads, d, d)
+            ops.gemm_raw(c.u[i], dyv[i], dp_, d, d, N, C, 2 * C, d, b_off=C, trans_a=True, trans_b=True, batch=bs,
+                         sA=(N * C, d), sB=(N * 2 * C, d), sC=sctx, accumulate=True, split_k=split)
+            dPc[o] = dp_
+            du_i = self.E(M, C)
+            ops.gemm_raw(dyv[i], c.p16[o], du_i, N, d, d, 2 * C, d, C, a_off=C, batch=bs, sA=(N * 2 * C, d), sB=sctx, sC=(N * C, d))
+            du[i] = du_i
+        dr = []
+        for i in (0, 1):
+            dC = self.E(B * heads, d, d)
+            ops.softmax_dim2_bwd(c.p32[i], dPc[i], scale, dC)
+            dkv = self.E(M, 2 * C)
+            # ctx = K^T V : dK = V dC^T ; dV = K dC
+            ops.gemm_raw(c.kv[i], dC, dkv, N, d, d, 2 * C, d, 2 * C, a_off=C, batch=bs, sA=(N * 2 * C, d), sB=sctx, sC=(N * 2 * C, d))
+            ops.gemm_raw(c.kv[i], dC, dkv, N, d, d, 2 * C, d, 2 * C, c_off=C, trans_b=True, batch=bs, sA=(N * 2 * C, d), sB=sctx,
+                         sC=(N * 2 * C, d))
+            self.linear_wgrad(dkv, c.u[i], p + f".cross.cross_attn.kv{i + 1}.weight")
+            ops.mm(dkv, self.W(p + f".cross.cross_attn.kv{i + 1}.weight"), du[i], tb=True, residual=du[i])
+            ops.relu_bwd_(du[i], c.u[i])
+            dy_i = dyv[i][:, :C]
+            ops.relu_bwd_(dy_i, c.yv[i][:, :C])
+            wname, bname = p + f".cross.channel_proj{i + 1}.weight", p + f".cross.channel_proj{i + 1}.bias"
+            gw, gb = self.G2(wname), self.G(bname)
+            ops.mm(dy_i, c.r[i], gw[:C], ta=True, tb=True, accumulate=True)
+            ops.mm(du[i], c.r[i], gw[C:], ta=True, tb=True, accumulate=True)
+            ops.colsum(dy_i, gb[:C])
+            ops.colsum(du[i], gb[C:])
+            wcp = self.W(wname)
+            dr_i = self.E(M, C, dtype=f32)
+            ops.mm(dy_i, wcp[:C], dr_i, tb=True, residual=de[i])
+            ops.mm(du[i], wcp[C:], dr_i, tb=True, residual=dr_i)
+            dr.append(dr_i)
+        return dr
+
+    # ------------------------------------------------------------------------------------------
+    # decoder + loss
+    # ------------------------------------------------------------------------------------------
+    def decoder_fwd(self, feats, sizes, B, training, dropmask, save):
+        E_ = self.embed
+        hd = self.model.decode_head
+        p = "decode_head"
+        wf = self.W(p + ".linear_fuse.0.weight")  # [E, 4E]; concat order c4, c3, c2, c1 (MLPDecoder.py:77)
+        c = _NS()
+        c.e, c.zs = [], []
+        for s in range(4):
+            Ms = feats[s].shape[0]
+            e = self.E(Ms, E_)
+            ops.mm(feats[s], self.W(p + f".linear_c{s + 1}.proj.weight"), e, bias=self.P(p + f".linear_c{s + 1}.proj.bias"))
+            z = self.E(Ms, E_)
+            ops.mm(e, wf[:, (3 - s) * E_:(4 - s) * E_], z)
+            c.e.append(e); c.zs.append(z)
+        M0 = feats[0].shape[0]
+        fuse = self.E(M0, E_, dtype=f32)
+        ops.upsample_sum_fwd(c.zs, sizes, self.P(p + ".linear_fuse.0.bias"), fuse, B, E_)
+        bn = hd.linear_fuse[1]
+        c.mean, c.inv = self.bn_stats(p + ".linear_fuse.1", bn, fuse, training)
+        yb = self.E(M0, E_)
+        N0 = sizes[0][0] * sizes[0][1]
+        ops.bn_apply(fuse, c.mean, c.inv, self.P(p + ".linear_fuse.1.weight"), self.P(p + ".linear_fuse.1.bias"), yb, relu=True,
+                     mask=dropmask, rows_per_sample=N0)
+        logits = self.E(M0, self.ncls, dtype=f32)
+        ops.mm(yb, self.W(p + ".linear_pred.weight"), logits, bias=self.P(p + ".linear_pred.bias"))
+        c.feats, c.sizes, c.fuse, c.yb, c.dropmask, c.N0 = feats, sizes, fuse, yb, dropmask, N0
+        self.tr("decode_head.logits", logits)
+        return logits, c
+
+    def decoder_bwd(self, c, dlog, B):
+        """dlog bf16 [M0, ncls] -> list of df_s bf16 [M_s, C_s]"""
+        E_ = self.embed
+        p = "decode_head"
+        M0 = c.fuse.shape[0]
+        self.linear_wgrad(dlog, c.yb, p + ".linear_pred.weight", p + ".linear_pred.bias")
+        dyb = self.E(M0, E_)
+        ops.mm(dlog, self.W(p + ".linear_pred.weight"), dyb, tb=True)
+        ws = self.Z(2 * E_, dtype=torch.float64)
+        dfuse = self.E(M0, E_)
+        ops.bn_bwd(dyb, c.fuse, c.mean, c.inv, self.P(p + ".linear_fuse.1.weight"), self.P(p + ".linear_fuse.1.bias"), dfuse,
+                   self.G(p + ".linear_fuse.1.weight"), self.G(p + ".linear_fuse.1.bias"), ws, relu=True, mask=c.dropmask,
+                   rows_per_sample=c.N0)
+        del dyb
+        ops.colsum(dfuse, self.G(p + ".linear_fuse.0.bias"))
+        wf = self.W(p + ".linear_fuse.0.weight")
+        gf = self.G2(p + ".linear_fuse.0.weight")
+        H0, W0 = c.sizes[0]
+        dfs = []
+        for s in range(4):
+            Ms = c.feats[s].shape[0]
+            if s == 0:
+                dz = dfuse
+            else:
+                dz = self.E(Ms, E_)
+                ops.upsample_bwd(dfuse, H0, W0, dz, c.sizes[s][0], c.sizes[s][1], B, E_)
+            sl = slice((3 - s) * E_, (4 - s) * E_)
+            ops.mm(dz, c.e[s], gf[:, sl], ta=True, tb=True, accumulate=True)
+            de = self.E(Ms, E_)
+            ops.mm(dz, wf[:, sl], de, tb=True)
+            self.linear_wgrad(de, c.feats[s], p + f".linear_c{s + 1}.proj.weight", p + f".linear_c{s + 1}.proj.bias")
+            df = self.E(Ms, c.feats[s].shape[1])
+            ops.mm(de, self.W(p + f".linear_c{s + 1}.proj.weight"), df, tb=True)
+            dfs.append(df)
+        return dfs
+
+    # ------------------------------------------------------------------------------------------
+    # whole network
+    # ------------------------------------------------------------------------------------------
+    def _encode(self, rgb, x, training, save, dp):
+        B, _, H, W = rgb.shape
+        bbm = self.model.backbone
+        inp = [rgb, x]
+        ctx = _NS()
+        ctx.stages = []
+        feats, sizes = [], []
+        Hc, Wc = H, W
+        for s in range(4):
+            C = self.dims[s]
+            st = _NS()
+            st.blocks = [[], []]
+            st.pe = []
+            xs = []
+            for br, (pe_name, blk_name) in enumerate((("patch_embed", "block"), ("extra_patch_embed", "extra_block"))):
+                x0, Ho, Wo, cpe = self.pe_fwd(f"backbone.{pe_name}{s + 1}", inp[br], s, B, Hc, Wc, save)
+                st.pe.append(cpe)
+                self.tr(f"backbone.{pe_name}{s + 1}", x0)
+                xcur = x0
+                for i in range(self.depths[s]):
+                    bp = f"backbone.{blk_name}{s + 1}.{i}"
+                    xcur, cb = self.block_fwd(bp, xcur, B, Ho, Wo, s, dp.get(bp), save)
+                    self.tr(bp, xcur)
+                    if save:
+                        st.blocks[br].append(cb)
+                xs.append(xcur)
+            N = Ho * Wo
+            M = B * N
+            cat12 = self.E(M, 2 * C)
+            st.mn, st.rn = [], []
+            for br, nname in enumerate(("norm", "extra_norm")):
+                mn, rn = (self.E(M, dtype=f32), self.E(M, dtype=f32)) if save else (None, None)
+                ops.layernorm_fwd(xs[br], self.P(f"backbone.{nname}{s + 1}.weight"), self.P(f"backbone.{nname}{s + 1}.bias"), 1e-6,
+                                  cat12[:, br * C:(br + 1) * C], mn, rn)
+                st.mn.append(mn); st.rn.append(rn)
+            st.xs = xs
+            self.tr(f"backbone.norm{s + 1}", cat12[:, :C])
+            self.tr(f"backbone.extra_norm{s + 1}", cat12[:, C:])
+            r1, r2, st.frm = self.frm_fwd(s, cat12, B, N, save)
+            self.tr(f"backbone.FRMs.{s}.out1", r1)
+            self.tr(f"backbone.FRMs.{s}.out2", r2)
+            fused, st.ffm = self.ffm_fwd(s, [r1, r2], B, Ho, Wo, training, save)
+            self.tr(f"backbone.FFMs.{s}", fused)
+            feats.append(fused)
+            sizes.append((Ho, Wo))
+            st.H, st.W = Ho, Wo
+            ctx.stages.append(st)
+            inp = [r1, r2]
+            Hc, Wc = Ho, Wo
+        return feats, sizes, ctx
+
+    def forward_logits(self, rgb, x):
+        """eval / inference path: full-resolution NCHW fp32 logits (builder.py:212-238)"""
+        self._begin(rgb, x)
+        training = self.model.training
+        B, _, H, W = rgb.shape
+        dp, dm = self._make_dp(B, training)
+        feats, sizes, _ = self._encode(rgb, x, training, False, dp)
+        logits, _ = self.decoder_fwd(feats, sizes, B, training, dm, False)
+        out = self.E(B, self.ncls, H, W, dtype=f32)
+        ops.logits_upsample_nchw(logits, out, B, sizes[0][0], sizes[0][1], H, W, self.ncls)
+        return out
+
+    def forward_loss(self, rgb, x, label, ignore_index, with_grad):
+        """loss (0-d fp32).  with_grad: also runs the complete backward pass, leaving d loss / d theta in flat_g."""
+        self._begin(rgb, x)
+        training = self.model.training
+        B, _, H, W = rgb.shape
+        assert B <= 16, "per-GPU batch > 16 is not supported by the FRM small-M kernels"
+        label = label.to(torch.int64).contiguous()
+        dp, dm = self._make_dp(B, training)
+        feats, sizes, ctx = self._encode(rgb, x, training, with_grad, dp)
+        logits, cdec = self.decoder_fwd(feats, sizes, B, training, dm, with_grad)
+        h0, w0 = sizes[0]
+        acc = self.Z(2, dtype=torch.float64)
+        loss = self.E((), dtype=f32)
+        if not with_grad:
+            ops.ce_upsampled(logits, label, ignore_index, acc, None, B, h0, w0, H, W, self.ncls)
+            ops.ce_finalize(acc, loss)
+            return loss
+        self.flat_g.zero_()
+        dl = self.Z(B * h0 * w0, self.ncls)
+        ops.ce_upsampled(logits, label, ignore_index, acc, dl, B, h0, w0, H, W, self.ncls)
+        dlog = self.E(B * h0 * w0, self.ncls)
+        ops.ce_finalize(acc, loss, dl, None, dlog)
+        dfs = self.decoder_bwd(cdec, dlog, B)
+        del cdec
+        pending = None  # (dcol_rgb, dcol_x) of the next stage's patch embeds, to be scattered into this stage's dr
+        for s in (3, 2, 1, 0):
+            st = ctx.stages[s]
+            C = self.dims[s]
+            N = st.H * st.W
+            dr = self.ffm_bwd(st.ffm, dfs[s], B)
+            if pending is not None:
+                nst = ctx.stages[s + 1]
+                for br in (0, 1):
+                    ops.col2im_nhwc(pending[br], dr[br], B, st.H, st.W, 3, 2, 1, nst.H, nst.W, add=dr[br])
+            dcat = self.frm_bwd(st.frm, dr[0], dr[1], B, N)
+            pending = []
+            for br, (nname, blk_name) in enumerate((("norm", "block"), ("extra_norm", "extra_block"))):
+                blocks = st.blocks[br]
+                last = blocks[-1]
+                dx = self.E(B * N, C, dtype=f32)
+                dx_bf = self.E(B * N, C)
+                ops.layernorm_bwd(dcat[:, br * C:(br + 1) * C], st.xs[br], st.mn[br], st.rn[br],
+                                  self.P(f"backbone.{nname}{s + 1}.weight"), dx=dx, dx_bf=dx_bf,
+                                  scale=None if last.dp is None else last.dp[1], rows_per_sample=N,
+                                  dgamma=self.G(f"backbone.{nname}{s + 1}.weight"), dbeta=self.G(f"backbone.{nname}{s + 1}.bias"))
+                for i in range(len(blocks) - 1, -1, -1):
+                    prev = blocks[i - 1] if i > 0 else None
+                    prev_scale = None if (prev is None or prev.dp is None) else prev.dp[1]
+                    dx, dx_bf = self.block_bwd(blocks[i], dx, dx_bf, B, prev_scale, need_bf=(i > 0))
+                    blocks[i] = None
+                pending.append(self.pe_bwd(st.pe[br], dx, B))
+            if s == 0:
+                pending = None
+            ctx.stages[s] = None
+        return loss
+
+    def _begin(self, rgb, x):
+        if not rgb.is_cuda:
+            raise RuntimeError("cmx_b200: inputs must be CUDA tensors — the hot path has no CPU fallback")
+        assert rgb.shape == x.shape and rgb.dim() == 4 and rgb.shape[1] == 3, "expected two [B,3,H,W] inputs"
+        self.dev = rgb.device
+        self._ensure_flat(rgb.device)
+        self.refresh_weights()

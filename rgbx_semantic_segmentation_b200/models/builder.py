@@ -1,0 +1,181 @@
+"""Drop-in replacement for the reference `models/builder.py::EncoderDecoder` (builder.py:14-253) on the
+CMX MiT + MLPDecoder hot path.  Same constructor, attributes, state_dict keys and forward contract:
+
+    model = EncoderDecoder(cfg=config, criterion=nn.CrossEntropyLoss(reduction='mean', ignore_index=255),
+                           norm_layer=nn.BatchNorm2d)
+    loss   = model(rgb, modal_x, label)      # train.py:186
+    logits = model(rgb, modal_x)             # engine/evaluator.py:385  -> [B, classes, H, W] fp32
+
+The arithmetic runs on hand-written sm_100a kernels (bf16 operands, fp32 accumulate / residual stream /
+statistics / loss) — there is no PyTorch or CPU fallback: CPU inputs raise RuntimeError.
+"""
+import os
+
+import torch
+import torch.nn as nn
+
+from ..engine import Engine
+from .decoders.MLPDecoder import DecoderHead
+from .encoders import dual_segformer
+
+_MIT = {"mit_b0": (dual_segformer.mit_b0, [32, 64, 160, 256]), "mit_b1": (dual_segformer.mit_b1, [64, 128, 320, 512]),
+        "mit_b2": (dual_segformer.mit_b2, [64, 128, 320, 512]), "mit_b3": (dual_segformer.mit_b3, [64, 128, 320, 512]),
+        "mit_b4": (dual_segformer.mit_b4, [64, 128, 320, 512]), "mit_b5": (dual_segformer.mit_b5, [64, 128, 320, 512])}
+
+
+def _cfg_get(cfg, key, default):
+    if cfg is None:
+        return default
+    if isinstance(cfg, dict):
+        return cfg.get(key, default)
+    return getattr(cfg, key, default)
+
+
+class _CMXStep(torch.autograd.Function):
+    """Autograd boundary: forward runs the fused forward+backward step on the engine (optionally as one CUDA
+    graph replay); backward only hands the finished gradients (times grad_output) to the parameters, so DDP's
+    bucket hooks and torch optimizers see ordinary fp32 .grad tensors."""
+
+    @staticmethod
+    def forward(ctx, model, rgb, modal_x, label, *params):
+        ctx.model = model
+        return model._run_step(rgb, modal_x, label)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        eng = ctx.model._engine
+        flat = eng.flat_g * grad_out  # one elementwise pass over the flat gradient buffer (fresh tensor each step)
+        grads = tuple(flat[eng.off[n]:eng.off[n] + eng._numel(n)].view(eng.shape[n]) for n in eng.names)
+        return (None, None, None, None) + grads
+
+
+class EncoderDecoder(nn.Module):
+    def __init__(self, cfg=None, criterion=nn.CrossEntropyLoss(reduction='mean', ignore_index=255), norm_layer=nn.BatchNorm2d):
+        super().__init__()
+        self.norm_layer = norm_layer
+        self.cfg = cfg
+        backbone = _cfg_get(cfg, "backbone", "mit_b2")
+        if backbone not in _MIT:
+            # builder.py:146-150 falls back to mit_b2 for unknown names; other families are out of scope here
+            if any(backbone.startswith(p) for p in ("swin", "segnext", "resnet")) or backbone.endswith("aspp"):
+                raise NotImplementedError("cmx_b200 accelerates the dual MiT (mit_b0..b5) path only; got backbone=%r" % backbone)
+            backbone = "mit_b2"
+        for key, want in (("feature_rectify_module", "FRM"), ("feature_fusion_module", "FFM")):
+            got = _cfg_get(cfg, key, want)
+            if got != want:
+                raise NotImplementedError("cmx_b200 implements the default %s only (cfg.%s=%r)" % (want, key, got))
+        ctor, channels = _MIT[backbone]
+        # NOTE: the reference sets channels=[96,192,384,768] for mit_b4/b5 (builder.py:66-75) which crashes in
+        # DecoderHead; the channels the backbone really emits are used instead.
+        self.channels = list(channels)
+        self.backbone = ctor(norm_fuse=norm_layer)
+        self.aux_head = None
+        decoder = _cfg_get(cfg, "decoder", "MLPDecoder")
+        if decoder != "MLPDecoder":
+            raise NotImplementedError("cmx_b200 implements cfg.decoder='MLPDecoder' only (got %r)" % decoder)
+        self.decode_head = DecoderHead(in_channels=self.channels, num_classes=_cfg_get(cfg, "num_classes", 40),
+                                       norm_layer=norm_layer, embed_dim=_cfg_get(cfg, "decoder_embed_dim", 512))
+        self.criterion = criterion
+        if self.criterion:
+            self.init_weights(cfg, pretrained=_cfg_get(cfg, "pretrained_model", None))
+        self._engine = None
+        self._graphs = {}
+        self.use_cuda_graph = os.environ.get("CMX_CUDA_GRAPH", "1") != "0"
+
+    # ---- reference API ---------------------------------------------------------------------------
+    def init_weights(self, cfg, pretrained=None):
+        """builder.py:199-210 + utils/init_func.py:10-19: kaiming_normal_(fan_in, relu) on decoder convs and
+        eps/momentum override on decoder norm layers."""
+        if pretrained:
+            self.backbone.init_weights(pretrained=pretrained)
+        bn_eps, bn_momentum = _cfg_get(cfg, "bn_eps", 1e-3), _cfg_get(cfg, "bn_momentum", 0.1)
+        for _, m in self.decode_head.named_modules():
+            if isinstance(m, (nn.Conv1d, nn.Conv2d, nn.Conv3d)):
+                nn.init.kaiming_normal_(m.weight, mode='fan_in', nonlinearity='relu')
+            elif isinstance(m, self.norm_layer):
+                m.eps = bn_eps
+                m.momentum = bn_momentum
+                nn.init.constant_(m.weight, 1)
+                nn.init.constant_(m.bias, 0)
+
+    def encode_decode(self, rgb, modal_x):
+        return self._eng().forward_logits(rgb.float().contiguous(), modal_x.float().contiguous())
+
+    def forward(self, rgb, modal_x, label=None):
+        if label is None:
+            with torch.no_grad():
+                return self._forward_eval(rgb, modal_x)
+        crit = self.criterion
+        if not isinstance(crit, nn.CrossEntropyLoss) or crit.reduction != 'mean' or crit.weight is not None \
+                or getattr(crit, "label_smoothing", 0.0) != 0.0:
+            raise NotImplementedError("cmx_b200 fuses nn.CrossEntropyLoss(reduction='mean', ignore_index=k) only (train.py:72-73)")
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            params = tuple(self._eng_params())
+            return _CMXStep.apply(self, rgb, modal_x, label, *params)
+        with torch.no_grad():
+            return self._eng().forward_loss(rgb.float().contiguous(), modal_x.float().contiguous(), label,
+                                            crit.ignore_index, with_grad=False)
+
+    # ---- engine plumbing ---------------------------------------------------------------------------
+    def _eng(self):
+        if self._engine is None:
+            self._engine = Engine(self)
+        return self._engine
+
+    def _eng_params(self):
+        eng = self._eng()
+        d = dict(self.named_parameters())
+        return [d[n] for n in eng.names]
+
+    def _forward_eval(self, rgb, modal_x):
+        rgb, modal_x = rgb.float().contiguous(), modal_x.float().contiguous()
+        key = ("eval", tuple(rgb.shape), self.training, rgb.device.index)
+        if not self.use_cuda_graph or self.training:
+            return self._eng().forward_logits(rgb, modal_x)
+        g = self._graphs.get(key)
+        if g is None:
+            self._graphs[key] = {"warm": 1}
+            return self._eng().forward_logits(rgb, modal_x)
+        if "graph" not in g:
+            g["rgb"], g["x"] = rgb.clone(), modal_x.clone()
+            graph = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize()
+            with torch.cuda.graph(graph):
+                g["out"] = self._eng().forward_logits(g["rgb"], g["x"])
+            g["graph"] = graph
+        g["rgb"].copy_(rgb)
+        g["x"].copy_(modal_x)
+        g["graph"].replay()
+        return g["out"].clone()
+
+    def _run_step(self, rgb, modal_x, label):
+        rgb, modal_x = rgb.float().contiguous(), modal_x.float().contiguous()
+        ign = self.criterion.ignore_index
+        eng = self._eng()
+        key = ("train", tuple(rgb.shape), self.training, rgb.device.index)
+        if not self.use_cuda_graph or eng.forced_dp is not None or eng.forced_dropout is not None:
+            return eng.forward_loss(rgb, modal_x, label, ign, with_grad=True)
+        g = self._graphs.get(key)
+        if g is None:
+            self._graphs[key] = {"warm": 1}
+            return eng.forward_loss(rgb, modal_x, label, ign, with_grad=True)
+        if "graph" not in g:
+            g["rgb"], g["x"], g["label"] = rgb.clone(), modal_x.clone(), label.to(torch.int64).clone()
+            graph = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize()
+            with torch.cuda.graph(graph):
+                g["loss"] = eng.forward_loss(g["rgb"], g["x"], g["label"], ign, with_grad=True)
+            g["graph"] = graph
+        g["rgb"].copy_(rgb)
+        g["x"].copy_(modal_x)
+        g["label"].copy_(label)
+        g["graph"].replay()
+        return g["loss"].clone()
+
+    def __getstate__(self):
+        # the evaluator pickles the model into spawned children (engine/evaluator.py:131-137):
+        # drop per-process device state (engine buffers, CUDA graphs); it is rebuilt lazily.
+        st = self.__dict__.copy()
+        st["_engine"] = None
+        st["_graphs"] = {}
+        return st
