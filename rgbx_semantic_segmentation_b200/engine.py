@@ -739,9 +739,9 @@ class Engine:
             N = st.H * st.W
             dr = self.ffm_bwd(st.ffm, dfs[s], B)
             if pending is not None:
-                nst = ctx.stages[s + 1]
+                nH, nW = sizes[s + 1]
                 for br in (0, 1):
-                    ops.col2im_nhwc(pending[br], dr[br], B, st.H, st.W, 3, 2, 1, nst.H, nst.W, add=dr[br])
+                    ops.col2im_nhwc(pending[br], dr[br], B, st.H, st.W, 3, 2, 1, nH, nW, add=dr[br])
             dcat = self.frm_bwd(st.frm, dr[0], dr[1], B, N)
             pending = []
             for br, (nname, blk_name) in enumerate((("norm", "block"), ("extra_norm", "extra_block"))):

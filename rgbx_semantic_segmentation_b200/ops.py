@@ -44,6 +44,29 @@ def launch_count():
     return int(_lib.load().cmx_launch_count())
 
 
+# Optional per-launch profiling (bench.py / debugging): when PROFILE is a list every C-ABI call is bracketed
+# by CUDA events on the launching stream and (name, start, stop, flops, bytes) is appended.
+PROFILE = None
+
+
+def _call(name, *args, tag=None, flops=0, nbytes=0):
+    fn = getattr(_lib.load(), name)
+    if PROFILE is None:
+        rc = fn(*args)
+    else:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = fn(*args)
+        e1.record()
+        PROFILE.append((tag or name, e0, e1, flops, nbytes))
+    if rc != 0:
+        raise RuntimeError("cmx_b200.%s failed (rc=%d): %s" % (name, rc, _lib.last_error()))
+
+
+def _nb(*ts):
+    return sum(t.numel() * t.element_size() for t in ts if t is not None)
+
+
 # ------------------------------------------------------------------------------------------------
 # GEMM
 # ------------------------------------------------------------------------------------------------
@@ -83,7 +106,12 @@ def gemm_raw(A, B, C, M, N, K, lda, ldb, ldc, *, a_off=0, b_off=0, c_off=0, tran
     g.split_k = split_k
     g.rows_per_sample = rows_per_sample
     g.impl = impl
-    _lib.check(_lib.load().cmx_gemm(ctypes.byref(g), _stream()), "gemm")
+    nb = batch[0] * batch[1]
+    which = "tc" if int(_lib.load().cmx_gemm_which(ctypes.byref(g))) == 2 else ("fb_batched" if nb > 1 else "fb")
+    kind = "wgrad" if trans_a else ("dgrad" if trans_b and nb == 1 else "fwd")
+    cbytes = C.element_size() * (2 if (accumulate or split_k > 1) else 1)
+    _call("cmx_gemm", ctypes.byref(g), _stream(), tag="gemm_%s_%s" % (which, kind), flops=2 * M * N * K * nb,
+          nbytes=nb * (2 * (M * K + N * K) + cbytes * M * N + (residual.element_size() * M * N if residual is not None else 0)))
     return C
 
 
@@ -123,44 +151,44 @@ def gemm_which(M, N, K, lda, ldb, ldc, trans_a=False, trans_b=False, c_dtype=BF1
 def layernorm_fwd(x, gamma, beta, eps, y, mean=None, rstd=None):
     M, C = x.shape
     _cuda(x, y)
-    _lib.check(_lib.load().cmx_layernorm_fwd(x.data_ptr(), _dt(x), _ld(x), gamma.data_ptr(), beta.data_ptr(), eps,
-                                             y.data_ptr(), _dt(y), _ld(y), _p(mean), _p(rstd), M, C, _stream()), "layernorm_fwd")
+    _call("cmx_layernorm_fwd", x.data_ptr(), _dt(x), _ld(x), gamma.data_ptr(), beta.data_ptr(), eps,
+                                             y.data_ptr(), _dt(y), _ld(y), _p(mean), _p(rstd), M, C, _stream(), nbytes=_nb(x, y))
     return y
 
 
 def layernorm_bwd(dy, x, mean, rstd, gamma, *, dy2=None, dres=None, dx=None, dx_bf=None, scale=None, rows_per_sample=0,
                   dgamma=None, dbeta=None):
     M, C = x.shape
-    _lib.check(_lib.load().cmx_layernorm_bwd(
+    _call("cmx_layernorm_bwd", 
         dy.data_ptr(), _dt(dy), _ld(dy), _p(dy2), _ld(dy2) if dy2 is not None else 0, x.data_ptr(), _dt(x), _ld(x),
         mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(), _p(dres), _ld(dres) if dres is not None else 0,
         _p(dx), _dt(dx) if dx is not None else F32, _ld(dx) if dx is not None else 0,
         _p(dx_bf), _ld(dx_bf) if dx_bf is not None else 0, _p(scale), rows_per_sample,
-        _p(dgamma), _p(dbeta), M, C, _stream()), "layernorm_bwd")
+        _p(dgamma), _p(dbeta), M, C, _stream(), nbytes=_nb(dy, dy2, x, dres, dx, dx_bf))
 
 
 def colstats(x, sum_, sumsq):
     M, C = x.shape
-    _lib.check(_lib.load().cmx_colstats(x.data_ptr(), _dt(x), _ld(x), sum_.data_ptr(), sumsq.data_ptr(), M, C, _stream()), "colstats")
+    _call("cmx_colstats", x.data_ptr(), _dt(x), _ld(x), sum_.data_ptr(), sumsq.data_ptr(), M, C, _stream(), nbytes=_nb(x))
 
 
 def bn_finalize(sum_, sumsq, count, eps, momentum, running_mean, running_var, nbt, mean, invstd):
     C = mean.numel()
-    _lib.check(_lib.load().cmx_bn_finalize(sum_.data_ptr(), sumsq.data_ptr(), count, eps, momentum, _p(running_mean),
-                                           _p(running_var), _p(nbt), mean.data_ptr(), invstd.data_ptr(), C, _stream()), "bn_finalize")
+    _call("cmx_bn_finalize", sum_.data_ptr(), sumsq.data_ptr(), count, eps, momentum, _p(running_mean),
+                                           _p(running_var), _p(nbt), mean.data_ptr(), invstd.data_ptr(), C, _stream())
 
 
 def bn_eval_stats(running_mean, running_var, eps, mean, invstd):
-    _lib.check(_lib.load().cmx_bn_eval_stats(running_mean.data_ptr(), running_var.data_ptr(), eps, mean.data_ptr(),
-                                             invstd.data_ptr(), mean.numel(), _stream()), "bn_eval_stats")
+    _call("cmx_bn_eval_stats", running_mean.data_ptr(), running_var.data_ptr(), eps, mean.data_ptr(),
+                                             invstd.data_ptr(), mean.numel(), _stream())
 
 
 def bn_apply(x, mean, invstd, gamma, beta, y, *, residual=None, relu=False, mask=None, rows_per_sample=0):
     M, C = x.shape
-    _lib.check(_lib.load().cmx_bn_apply(x.data_ptr(), _dt(x), _ld(x), mean.data_ptr(), invstd.data_ptr(), gamma.data_ptr(),
+    _call("cmx_bn_apply", x.data_ptr(), _dt(x), _ld(x), mean.data_ptr(), invstd.data_ptr(), gamma.data_ptr(),
                                         beta.data_ptr(), _p(residual), _dt(residual) if residual is not None else F32,
                                         _ld(residual) if residual is not None else 0, int(relu), _p(mask), rows_per_sample,
-                                        y.data_ptr(), _dt(y), _ld(y), M, C, _stream()), "bn_apply")
+                                        y.data_ptr(), _dt(y), _ld(y), M, C, _stream(), nbytes=_nb(x, residual, y))
     return y
 
 
@@ -172,11 +200,10 @@ def bn_bwd(dy, x, mean, invstd, gamma, beta, dx, dgamma, dbeta, ws, *, residual=
     common = (dy.data_ptr(), _dt(dy), _ld(dy), x.data_ptr(), _dt(x), _ld(x), mean.data_ptr(), invstd.data_ptr(),
               gamma.data_ptr(), beta.data_ptr(), _p(residual), _dt(residual) if residual is not None else F32,
               _ld(residual) if residual is not None else 0, int(relu), _p(mask), rows_per_sample)
-    lib = _lib.load()
-    _lib.check(lib.cmx_bn_bwd_reduce(*common, s1.data_ptr(), s2.data_ptr(), M, C, _stream()), "bn_bwd_reduce")
-    _lib.check(lib.cmx_bn_bwd_apply(*common, s1.data_ptr(), s2.data_ptr(), dx.data_ptr(), _dt(dx), _ld(dx), _p(dres),
-                                    _dt(dres) if dres is not None else _dt(dx), _ld(dres) if dres is not None else 0,
-                                    _p(dgamma), _p(dbeta), M, C, _stream()), "bn_bwd_apply")
+    _call("cmx_bn_bwd_reduce", *common, s1.data_ptr(), s2.data_ptr(), M, C, _stream(), nbytes=_nb(dy, x))
+    _call("cmx_bn_bwd_apply", *common, s1.data_ptr(), s2.data_ptr(), dx.data_ptr(), _dt(dx), _ld(dx), _p(dres),
+          _dt(dres) if dres is not None else _dt(dx), _ld(dres) if dres is not None else 0,
+          _p(dgamma), _p(dbeta), M, C, _stream(), nbytes=_nb(dy, x, dx, dres))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -184,16 +211,15 @@ def bn_bwd(dy, x, mean, invstd, gamma, beta, dx, dgamma, dbeta, ws, *, residual=
 # ------------------------------------------------------------------------------------------------
 def dwconv3x3_fwd(x, w, bias, act, y, B, H, W, flip=False):
     C = x.shape[1]
-    _lib.check(_lib.load().cmx_dwconv3x3_fwd(x.data_ptr(), _ld(x), w.data_ptr(), _p(bias), act, int(flip), y.data_ptr(), _ld(y),
-                                             B, H, W, C, _stream()), "dwconv3x3_fwd")
+    _call("cmx_dwconv3x3_fwd", x.data_ptr(), _ld(x), w.data_ptr(), _p(bias), act, int(flip), y.data_ptr(), _ld(y),
+                                             B, H, W, C, _stream(), tag="cmx_dwconv3x3_%s" % ("dgrad" if flip else "fwd"), nbytes=_nb(x, y))
     return y
 
 
 def dwconv3x3_bwd_pre(x, w, bias, act, dy, du, dw, db, B, H, W):
     C = x.shape[1]
-    _lib.check(_lib.load().cmx_dwconv3x3_bwd_pre(x.data_ptr(), _ld(x), w.data_ptr(), _p(bias), act, dy.data_ptr(), _ld(dy),
-                                                 du.data_ptr(), _ld(du), dw.data_ptr(), _p(db), B, H, W, C, _stream()),
-               "dwconv3x3_bwd_pre")
+    _call("cmx_dwconv3x3_bwd_pre", x.data_ptr(), _ld(x), w.data_ptr(), _p(bias), act, dy.data_ptr(), _ld(dy),
+                                                 du.data_ptr(), _ld(du), dw.data_ptr(), _p(db), B, H, W, C, _stream(), nbytes=_nb(x, dy, du))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -202,59 +228,58 @@ def dwconv3x3_bwd_pre(x, w, bias, act, dy, du, dw, db, B, H, W):
 def im2col_nchw(x, col, k, s, p, Ho, Wo):
     B, Cin, H, W = x.shape
     assert x.is_contiguous() and x.dtype == torch.float32
-    _lib.check(_lib.load().cmx_im2col_nchw(x.data_ptr(), col.data_ptr(), B, Cin, H, W, k, s, p, Ho, Wo, col.shape[1], _stream()),
-               "im2col_nchw")
+    _call("cmx_im2col_nchw", x.data_ptr(), col.data_ptr(), B, Cin, H, W, k, s, p, Ho, Wo, col.shape[1], _stream(), nbytes=_nb(x, col))
     return col
 
 
 def im2col_nhwc(x, col, B, H, W, k, s, p, Ho, Wo):
     C = x.shape[1]
-    _lib.check(_lib.load().cmx_im2col_nhwc(x.data_ptr(), _ld(x), col.data_ptr(), B, H, W, C, k, s, p, Ho, Wo, _stream()), "im2col_nhwc")
+    _call("cmx_im2col_nhwc", x.data_ptr(), _ld(x), col.data_ptr(), B, H, W, C, k, s, p, Ho, Wo, _stream(), nbytes=_nb(x, col))
     return col
 
 
 def col2im_nhwc(dcol, dx, B, H, W, k, s, p, Ho, Wo, add=None):
     C = dx.shape[1]
-    _lib.check(_lib.load().cmx_col2im_nhwc(dcol.data_ptr(), _p(add), _dt(add) if add is not None else F32,
+    _call("cmx_col2im_nhwc", dcol.data_ptr(), _p(add), _dt(add) if add is not None else F32,
                                            _ld(add) if add is not None else 0, dx.data_ptr(), _dt(dx), _ld(dx), B, H, W, C, k, s, p,
-                                           Ho, Wo, _stream()), "col2im_nhwc")
+                                           Ho, Wo, _stream(), nbytes=_nb(dcol, add, dx))
     return dx
 
 
 def convw_pack(w, wp):
     Co, Ci, kh, kw = w.shape
-    _lib.check(_lib.load().cmx_convw_pack(w.data_ptr(), wp.data_ptr(), Co, Ci, kh, kw, wp.shape[1], _stream()), "convw_pack")
+    _call("cmx_convw_pack", w.data_ptr(), wp.data_ptr(), Co, Ci, kh, kw, wp.shape[1], _stream())
     return wp
 
 
 def convw_unpack_grad(gp, gw):
     Co, Ci, kh, kw = gw.shape
-    _lib.check(_lib.load().cmx_convw_unpack_grad(gp.data_ptr(), gw.data_ptr(), Co, Ci, kh, kw, gp.shape[1], _stream()), "convw_unpack_grad")
+    _call("cmx_convw_unpack_grad", gp.data_ptr(), gw.data_ptr(), Co, Ci, kh, kw, gp.shape[1], _stream())
 
 
 def cast_f32_bf16(x, y):
-    _lib.check(_lib.load().cmx_cast_f32_bf16(x.data_ptr(), y.data_ptr(), x.numel(), _stream()), "cast_f32_bf16")
+    _call("cmx_cast_f32_bf16", x.data_ptr(), y.data_ptr(), x.numel(), _stream(), nbytes=_nb(x, y))
     return y
 
 
 def cast_bf16_f32(x, y):
-    _lib.check(_lib.load().cmx_cast_bf16_f32(x.data_ptr(), y.data_ptr(), x.numel(), _stream()), "cast_bf16_f32")
+    _call("cmx_cast_bf16_f32", x.data_ptr(), y.data_ptr(), x.numel(), _stream())
     return y
 
 
 def colsum(x, out):
     M, N = x.shape
-    _lib.check(_lib.load().cmx_colsum(x.data_ptr(), _dt(x), _ld(x), out.data_ptr(), M, N, _stream()), "colsum")
+    _call("cmx_colsum", x.data_ptr(), _dt(x), _ld(x), out.data_ptr(), M, N, _stream(), nbytes=_nb(x))
 
 
 def relu_bwd_(dy, y):
     M, N = dy.shape
-    _lib.check(_lib.load().cmx_relu_bwd(dy.data_ptr(), _ld(dy), y.data_ptr(), _ld(y), M, N, _stream()), "relu_bwd")
+    _call("cmx_relu_bwd", dy.data_ptr(), _ld(dy), y.data_ptr(), _ld(y), M, N, _stream(), nbytes=2 * _nb(dy) + _nb(y))
     return dy
 
 
 def axpby(a, x, b, y, out):
-    _lib.check(_lib.load().cmx_axpby_f32(a, x.data_ptr(), b, _p(y), out.data_ptr(), x.numel(), _stream()), "axpby")
+    _call("cmx_axpby_f32", a, x.data_ptr(), b, _p(y), out.data_ptr(), x.numel(), _stream())
     return out
 
 
@@ -263,25 +288,25 @@ def axpby(a, x, b, y, out):
 # ------------------------------------------------------------------------------------------------
 def softmax_rows_fwd(s, p):
     rows, n = s.shape
-    _lib.check(_lib.load().cmx_softmax_rows_fwd(s.data_ptr(), _ld(s), p.data_ptr(), _ld(p), rows, n, _stream()), "softmax_rows_fwd")
+    _call("cmx_softmax_rows_fwd", s.data_ptr(), _ld(s), p.data_ptr(), _ld(p), rows, n, _stream(), nbytes=_nb(s, p))
     return p
 
 
 def softmax_rows_bwd(p, dp, scale, ds):
     rows, n = p.shape
-    _lib.check(_lib.load().cmx_softmax_rows_bwd(p.data_ptr(), _ld(p), dp.data_ptr(), _ld(dp), scale, ds.data_ptr(), _ld(ds), rows, n,
-                                                _stream()), "softmax_rows_bwd")
+    _call("cmx_softmax_rows_bwd", p.data_ptr(), _ld(p), dp.data_ptr(), _ld(dp), scale, ds.data_ptr(), _ld(ds), rows, n,
+                                                _stream(), nbytes=_nb(p, dp, ds))
     return ds
 
 
 def softmax_dim2_fwd(c, scale, p32, p16):
     nb, d, _ = c.shape
-    _lib.check(_lib.load().cmx_softmax_dim2_fwd(c.data_ptr(), scale, p32.data_ptr(), p16.data_ptr(), nb, d, _stream()), "softmax_dim2_fwd")
+    _call("cmx_softmax_dim2_fwd", c.data_ptr(), scale, p32.data_ptr(), p16.data_ptr(), nb, d, _stream())
 
 
 def softmax_dim2_bwd(p32, dp, scale, dc16):
     nb, d, _ = p32.shape
-    _lib.check(_lib.load().cmx_softmax_dim2_bwd(p32.data_ptr(), dp.data_ptr(), scale, dc16.data_ptr(), nb, d, _stream()), "softmax_dim2_bwd")
+    _call("cmx_softmax_dim2_bwd", p32.data_ptr(), dp.data_ptr(), scale, dc16.data_ptr(), nb, d, _stream())
 
 
 # ------------------------------------------------------------------------------------------------
@@ -289,41 +314,40 @@ def softmax_dim2_bwd(p32, dp, scale, dc16):
 # ------------------------------------------------------------------------------------------------
 def pool_avgmax_fwd(x, y, argmax, B, HW):
     C2 = x.shape[1]
-    _lib.check(_lib.load().cmx_pool_avgmax_fwd(x.data_ptr(), _ld(x), y.data_ptr(), argmax.data_ptr(), B, HW, C2, _stream()), "pool_avgmax_fwd")
+    _call("cmx_pool_avgmax_fwd", x.data_ptr(), _ld(x), y.data_ptr(), argmax.data_ptr(), B, HW, C2, _stream(), nbytes=_nb(x))
 
 
 def pool_avgmax_bwd(dy, argmax, dx, B, HW):
     C2 = dx.shape[1]
-    _lib.check(_lib.load().cmx_pool_avgmax_bwd(dy.data_ptr(), argmax.data_ptr(), dx.data_ptr(), _ld(dx), B, HW, C2, _stream()), "pool_avgmax_bwd")
+    _call("cmx_pool_avgmax_bwd", dy.data_ptr(), argmax.data_ptr(), dx.data_ptr(), _ld(dx), B, HW, C2, _stream(), nbytes=2 * _nb(dx))
 
 
 def smallm_linear_fwd(x, w, b, act, y):
     Mb, K = x.shape
     N = w.shape[0]
-    _lib.check(_lib.load().cmx_smallm_linear_fwd(x.data_ptr(), w.data_ptr(), _p(b), act, y.data_ptr(), Mb, N, K, _stream()), "smallm_linear_fwd")
+    _call("cmx_smallm_linear_fwd", x.data_ptr(), w.data_ptr(), _p(b), act, y.data_ptr(), Mb, N, K, _stream())
     return y
 
 
 def smallm_linear_bwd(dy, y, act, x, w, dx, dw, db, ws):
     Mb, K = x.shape
     N = w.shape[0]
-    _lib.check(_lib.load().cmx_smallm_linear_bwd(dy.data_ptr(), y.data_ptr(), act, x.data_ptr(), w.data_ptr(), _p(dx), _p(dw), _p(db),
-                                                 ws.data_ptr(), Mb, N, K, _stream()), "smallm_linear_bwd")
+    _call("cmx_smallm_linear_bwd", dy.data_ptr(), y.data_ptr(), act, x.data_ptr(), w.data_ptr(), _p(dx), _p(dw), _p(db),
+                                                 ws.data_ptr(), Mb, N, K, _stream())
 
 
 def frm_rectify_fwd(a, t, w2, b2, cw, sw, r1, r2, B, HW):
     C = t.shape[1]
-    _lib.check(_lib.load().cmx_frm_rectify_fwd(a.data_ptr(), _ld(a), t.data_ptr(), _ld(t), w2.data_ptr(), b2.data_ptr(), cw.data_ptr(),
-                                               sw.data_ptr(), r1.data_ptr(), _ld(r1), r2.data_ptr(), _ld(r2), B, HW, C, _stream()),
-               "frm_rectify_fwd")
+    _call("cmx_frm_rectify_fwd", a.data_ptr(), _ld(a), t.data_ptr(), _ld(t), w2.data_ptr(), b2.data_ptr(), cw.data_ptr(),
+                                               sw.data_ptr(), r1.data_ptr(), _ld(r1), r2.data_ptr(), _ld(r2), B, HW, C, _stream(), nbytes=_nb(a, t, r1, r2))
 
 
 def frm_rectify_bwd(dr1, dr2, a, t, w2, cw, sw, da, dt, dcw, dw2, db2, B, HW):
     C = t.shape[1]
-    _lib.check(_lib.load().cmx_frm_rectify_bwd(dr1.data_ptr(), _ld(dr1), dr2.data_ptr(), _ld(dr2), a.data_ptr(), _ld(a), t.data_ptr(),
+    _call("cmx_frm_rectify_bwd", dr1.data_ptr(), _ld(dr1), dr2.data_ptr(), _ld(dr2), a.data_ptr(), _ld(a), t.data_ptr(),
                                                _ld(t), w2.data_ptr(), cw.data_ptr(), sw.data_ptr(), da.data_ptr(), _ld(da),
                                                dt.data_ptr(), _ld(dt), dcw.data_ptr(), dw2.data_ptr(), db2.data_ptr(), B, HW, C,
-                                               _stream()), "frm_rectify_bwd")
+                                               _stream(), nbytes=_nb(dr1, dr2, a, t, da, dt))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -333,31 +357,30 @@ def upsample_sum_fwd(zs, sizes, bias, out, B, C):
     """zs: [z0, z1, z2, z3] bf16 (z0 at output resolution; later entries may be None); sizes: [(H,W)]*4"""
     z = list(zs) + [None] * (4 - len(zs))
     sz = list(sizes) + [(1, 1)] * (4 - len(sizes))
-    _lib.check(_lib.load().cmx_upsample_sum_fwd(_p(z[0]), _p(z[1]), _p(z[2]), _p(z[3]), sz[0][0], sz[0][1], sz[1][0], sz[1][1],
-                                                sz[2][0], sz[2][1], sz[3][0], sz[3][1], _p(bias), out.data_ptr(), B, C, _stream()),
-               "upsample_sum_fwd")
+    _call("cmx_upsample_sum_fwd", _p(z[0]), _p(z[1]), _p(z[2]), _p(z[3]), sz[0][0], sz[0][1], sz[1][0], sz[1][1],
+                                                sz[2][0], sz[2][1], sz[3][0], sz[3][1], _p(bias), out.data_ptr(), B, C, _stream(), nbytes=_nb(*zs) + _nb(out))
     return out
 
 
 def upsample_bwd(dout, Ho, Wo, dz, Hi, Wi, B, C):
-    _lib.check(_lib.load().cmx_upsample_bwd(dout.data_ptr(), Ho, Wo, dz.data_ptr(), Hi, Wi, B, C, _stream()), "upsample_bwd")
+    _call("cmx_upsample_bwd", dout.data_ptr(), Ho, Wo, dz.data_ptr(), Hi, Wi, B, C, _stream(), nbytes=_nb(dout, dz))
     return dz
 
 
 def ce_upsampled(logits, label, ignore_index, acc, dlogits, B, h, w, H, W, ncls):
     assert label.dtype == torch.int64 and label.is_contiguous()
-    _lib.check(_lib.load().cmx_ce_upsampled_fwd_bwd(logits.data_ptr(), label.data_ptr(), ignore_index, acc.data_ptr(), _p(dlogits),
-                                                    B, h, w, H, W, ncls, _stream()), "ce_upsampled_fwd_bwd")
+    _call("cmx_ce_upsampled_fwd_bwd", logits.data_ptr(), label.data_ptr(), ignore_index, acc.data_ptr(), _p(dlogits),
+                                                    B, h, w, H, W, ncls, _stream())
 
 
 def ce_finalize(acc, loss, dlogits=None, gscale=None, out=None):
     n = dlogits.numel() if dlogits is not None else 0
-    _lib.check(_lib.load().cmx_ce_finalize(acc.data_ptr(), _p(loss), _p(dlogits), _p(gscale), _p(out),
-                                           _dt(out) if out is not None else F32, n, _stream()), "ce_finalize")
+    _call("cmx_ce_finalize", acc.data_ptr(), _p(loss), _p(dlogits), _p(gscale), _p(out),
+                                           _dt(out) if out is not None else F32, n, _stream())
 
 
 def logits_upsample_nchw(logits, out, B, h, w, H, W, ncls):
-    _lib.check(_lib.load().cmx_logits_upsample_nchw(logits.data_ptr(), out.data_ptr(), B, h, w, H, W, ncls, _stream()), "logits_upsample_nchw")
+    _call("cmx_logits_upsample_nchw", logits.data_ptr(), out.data_ptr(), B, h, w, H, W, ncls, _stream())
     return out
 
 
@@ -367,8 +390,8 @@ _INT_TAG = {torch.uint8: 0, torch.int32: 1, torch.int64: 2}
 def confusion(pred, gt, n_cl, hist, stats):
     _cuda(pred, gt, hist, stats)
     assert pred.is_contiguous() and gt.is_contiguous() and pred.numel() == gt.numel()
-    _lib.check(_lib.load().cmx_confusion(pred.data_ptr(), _INT_TAG[pred.dtype], gt.data_ptr(), _INT_TAG[gt.dtype], pred.numel(), n_cl,
-                                         hist.data_ptr(), stats.data_ptr(), _stream()), "confusion")
+    _call("cmx_confusion", pred.data_ptr(), _INT_TAG[pred.dtype], gt.data_ptr(), _INT_TAG[gt.dtype], pred.numel(), n_cl,
+                                         hist.data_ptr(), stats.data_ptr(), _stream())
 
 
 def argmax_confusion(scores, gt, n_cl, hist, stats, pred_out=None):
@@ -376,5 +399,5 @@ def argmax_confusion(scores, gt, n_cl, hist, stats, pred_out=None):
     _cuda(scores)
     assert scores.is_contiguous() and scores.dtype == torch.float32 and scores.shape[0] == n_cl
     npix = scores[0].numel()
-    _lib.check(_lib.load().cmx_argmax_confusion(scores.data_ptr(), _p(gt), _INT_TAG[gt.dtype] if gt is not None else 0, npix, n_cl,
-                                                _p(pred_out), _p(hist), _p(stats), _stream()), "argmax_confusion")
+    _call("cmx_argmax_confusion", scores.data_ptr(), _p(gt), _INT_TAG[gt.dtype] if gt is not None else 0, npix, n_cl,
+                                                _p(pred_out), _p(hist), _p(stats), _stream())

@@ -1,0 +1,146 @@
+"""CPU tests of the host side: C-ABI library exports, module tree / state_dict contract of the EncoderDecoder
+drop-in, loud failure without a GPU, pickling, and the N>1 gradient hand-off under DDP (gloo)."""
+import ctypes
+import os
+import pickle
+import subprocess
+import sys
+
+import pytest
+import torch
+import torch.nn as nn
+
+from oracle import cmx_ref
+from rgbx_semantic_segmentation_b200 import _lib
+from rgbx_semantic_segmentation_b200.models.builder import EncoderDecoder
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class Cfg:
+    backbone = "mit_b2"
+    decoder = "MLPDecoder"
+    decoder_embed_dim = 512
+    num_classes = 9
+    pretrained_model = None
+    bn_eps = 1e-3
+    bn_momentum = 0.1
+
+
+class CfgB0(Cfg):
+    backbone = "mit_b0"
+    decoder_embed_dim = 64
+
+
+def test_library_exports_every_declared_symbol():
+    if not _lib.lib_available():
+        import __graft_entry__
+        __graft_entry__.build()
+    protos = _lib.parse_header()
+    assert len(protos) >= 40
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in protos:
+        assert hasattr(lib, name), name
+    lib.cmx_version.restype = ctypes.c_int
+    assert lib.cmx_version() == 100                      # no compute call without a GPU
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = {l.split()[-1] for l in out.splitlines() if " T " in l and "cmx_" in l}
+    assert exported == set(protos), exported ^ set(protos)
+
+
+def test_state_dict_schema_and_param_groups():
+    m = EncoderDecoder(Cfg, nn.CrossEntropyLoss(reduction="mean", ignore_index=255), nn.BatchNorm2d)
+    sd = m.state_dict()
+    sch = cmx_ref.state_dict_schema(cmx_ref.MIT_SPECS["mit_b2"], 9)
+    assert list(sd.keys()) == list(sch.keys()) and len(sd) == 837
+    assert all(tuple(sd[k].shape) == sch[k][0] for k in sch)
+    assert sum(p.numel() for p in m.parameters()) == 66565521
+    # utils/init_func.py:33-57 group_weight: 288 decay + 522 no-decay tensors
+    decay, no_decay = [], []
+    for mod in m.modules():
+        if isinstance(mod, (nn.Linear, nn.Conv2d)):
+            decay.append(mod.weight)
+            if mod.bias is not None:
+                no_decay.append(mod.bias)
+        elif isinstance(mod, (nn.BatchNorm2d, nn.LayerNorm)):
+            no_decay += [mod.weight, mod.bias]
+    assert (len(decay), len(no_decay)) == (288, 522)
+    # train-built => decoder BN eps/momentum overridden (App. A-4); FFM BNs stay at 1e-5
+    assert m.decode_head.linear_fuse[1].eps == 1e-3 and m.backbone.FFMs[0].channel_emb.norm.eps == 1e-5
+    e = EncoderDecoder(Cfg, None, nn.BatchNorm2d)
+    assert e.decode_head.linear_fuse[1].eps == 1e-5
+    assert m.aux_head is None and m.channels == [64, 128, 320, 512] and m.cfg is Cfg
+    # drop-path schedule incl. the stage-2 quirk (App. A-6)
+    rgb_p, ext_p = cmx_ref.drop_path_probs(cmx_ref.MIT_SPECS["mit_b2"])
+    for s in range(4):
+        for i, blk in enumerate(getattr(m.backbone, f"block{s + 1}")):
+            assert abs(getattr(blk.drop_path, "drop_prob", 0.0) - rgb_p[s][i]) < 1e-12
+        for i, blk in enumerate(getattr(m.backbone, f"extra_block{s + 1}")):
+            assert abs(getattr(blk.drop_path, "drop_prob", 0.0) - ext_p[s][i]) < 1e-12
+
+
+def test_b4_channels_fixed_and_unsupported_configs_raise():
+    c = type("C", (Cfg,), {"backbone": "mit_b4", "num_classes": 5})
+    m = EncoderDecoder(c, None, nn.BatchNorm2d)
+    assert m.decode_head.linear_c4.proj.in_features == 512        # reference bug App. A-1 not reproduced
+    assert sum(p.numel() for p in m.parameters()) == 139856269
+    for bad in ({"backbone": "swin_s"}, {"decoder": "UPernet"}, {"feature_rectify_module": "IFRM"}):
+        with pytest.raises(NotImplementedError):
+            EncoderDecoder(type("C", (Cfg,), bad), None, nn.BatchNorm2d)
+
+
+def test_cpu_inputs_fail_loudly_and_model_pickles():
+    c = CfgB0
+    m = EncoderDecoder(c, nn.CrossEntropyLoss(ignore_index=255), nn.BatchNorm2d)
+    z = torch.zeros(1, 3, 32, 32)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(z, z)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(z, z, torch.zeros(1, 32, 32, dtype=torch.long))
+    with pytest.raises(NotImplementedError):
+        EncoderDecoder(c, nn.MSELoss(), nn.BatchNorm2d)(z, z, torch.zeros(1, 32, 32, dtype=torch.long))
+    m2 = pickle.loads(pickle.dumps(m))                              # engine/evaluator.py:131 pickles the model
+    assert list(m2.state_dict().keys()) == list(m.state_dict().keys())
+
+
+DDP_WORKER = r'''
+import os, sys, torch, torch.nn as nn, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from rgbx_semantic_segmentation_b200.models.builder import EncoderDecoder
+from rgbx_semantic_segmentation_b200.engine import Engine
+class Cfg:
+    backbone = "mit_b0"; decoder = "MLPDecoder"; decoder_embed_dim = 64; num_classes = 5
+    pretrained_model = None; bn_eps = 1e-3; bn_momentum = 0.1
+rank = int(os.environ["RANK"])
+dist.init_process_group("gloo")
+torch.manual_seed(0)
+m = EncoderDecoder(Cfg, nn.CrossEntropyLoss(ignore_index=255), nn.BatchNorm2d)
+eng = m._eng()
+eng._flatten(torch.device("cpu"))
+def fake_step(rgb, x, label):            # stands in for the CUDA step: rank-dependent gradient, rank-dependent loss
+    eng.flat_g.fill_(float(rank + 1))
+    return torch.tensor(float(rank))
+m._run_step = fake_step
+ddp = torch.nn.parallel.DistributedDataParallel(m)
+z = torch.zeros(1, 3, 32, 32)
+loss = ddp(z, z, torch.zeros(1, 32, 32, dtype=torch.long))
+loss.backward()
+ok = all(torch.allclose(p.grad, torch.full_like(p.grad, 1.5)) for p in m.parameters())   # mean of 1 and 2
+lt = loss.detach().clone(); dist.all_reduce(lt); lt /= dist.get_world_size()             # utils/pyt_utils.py:119-124
+print("RESULT", rank, ok, float(lt), len(list(m.parameters())))
+dist.destroy_process_group()
+'''
+
+
+def test_ddp_gradient_handoff_world2_gloo(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(DDP_WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29533", WORLD_SIZE="2")
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT], env=dict(env, RANK=str(r), LOCAL_RANK=str(r)),
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    for r, o in enumerate(outs):
+        line = [l for l in o.splitlines() if l.startswith("RESULT")]
+        assert line, o[-2000:]
+        _, rk, ok, lt, n = line[0].split()
+        assert ok == "True" and abs(float(lt) - 0.5) < 1e-6, line
