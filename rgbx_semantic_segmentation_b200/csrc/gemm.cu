@@ -126,6 +126,12 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm,
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -166,10 +172,16 @@ constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;
 constexpr int TC_THREADS = 192;
 
-template <int BN, bool A_MN, bool B_MN>
+struct TcBatch {
+  int batch2, splits;
+  long sC1, sC2;  // element strides of C per batch index
+};
+
+template <int BN, bool A_MN, bool B_MN, bool BATCHED>
 __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                             const __grid_constant__ CUtensorMap tmB, Epi epi,
-                                                            int k_blocks_total, int k_blocks_per_split, int stages) {
+                                                            int k_blocks_total, int k_blocks_per_split, int stages,
+                                                            TcBatch tb) {
   extern __shared__ uint8_t smem_raw[];
   constexpr uint32_t A_BYTES = TC_BM * TC_BK * 2;
   constexpr uint32_t B_BYTES = BN * TC_BK * 2;
@@ -187,7 +199,17 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
   const int lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * BN;
   const int m0 = blockIdx.y * TC_BM;
-  const int kb_begin = blockIdx.z * k_blocks_per_split;
+  int zz = blockIdx.z;
+  const int split_idx = zz % tb.splits;
+  zz /= tb.splits;
+  const int b2 = BATCHED ? zz % tb.batch2 : 0;
+  const int b1 = BATCHED ? zz / tb.batch2 : 0;
+  if (BATCHED) {
+    const long off = (long)b1 * tb.sC1 + (long)b2 * tb.sC2;
+    if (epi.c_dtype == CMX_F32) epi.C = reinterpret_cast<float*>(epi.C) + off;
+    else epi.C = reinterpret_cast<bf16*>(epi.C) + off;
+  }
+  const int kb_begin = split_idx * k_blocks_per_split;
   int kb_end = kb_begin + k_blocks_per_split;
   if (kb_end > k_blocks_total) kb_end = k_blocks_total;
   const int nkb = kb_end - kb_begin;  // >= 1 by construction on the host
@@ -224,17 +246,32 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
         const uint32_t sa = smem_base + s * STAGE_BYTES;
         const uint32_t sb = sa + A_BYTES;
         const int k = (kb_begin + i) * TC_BK;
-        if (!A_MN) {
-          tma_load_2d(sa, &tmA, full_bar(s), k, m0);
-        } else {
+        if (!BATCHED) {
+          if (!A_MN) {
+            tma_load_2d(sa, &tmA, full_bar(s), k, m0);
+          } else {
 #pragma unroll
-          for (int c = 0; c < TC_BM / 64; c++) tma_load_2d(sa + c * 8192, &tmA, full_bar(s), m0 + c * 64, k);
-        }
-        if (!B_MN) {
-          tma_load_2d(sb, &tmB, full_bar(s), k, n0);
-        } else {
+            for (int c = 0; c < TC_BM / 64; c++) tma_load_2d(sa + c * 8192, &tmA, full_bar(s), m0 + c * 64, k);
+          }
+          if (!B_MN) {
+            tma_load_2d(sb, &tmB, full_bar(s), k, n0);
+          } else {
 #pragma unroll
-          for (int c = 0; c < BN / 64; c++) tma_load_2d(sb + c * 8192, &tmB, full_bar(s), n0 + c * 64, k);
+            for (int c = 0; c < BN / 64; c++) tma_load_2d(sb + c * 8192, &tmB, full_bar(s), n0 + c * 64, k);
+          }
+        } else {
+          if (!A_MN) {
+            tma_load_4d(sa, &tmA, full_bar(s), k, m0, b2, b1);
+          } else {
+#pragma unroll
+            for (int c = 0; c < TC_BM / 64; c++) tma_load_4d(sa + c * 8192, &tmA, full_bar(s), m0 + c * 64, k, b2, b1);
+          }
+          if (!B_MN) {
+            tma_load_4d(sb, &tmB, full_bar(s), k, n0, b2, b1);
+          } else {
+#pragma unroll
+            for (int c = 0; c < BN / 64; c++) tma_load_4d(sb + c * 8192, &tmB, full_bar(s), n0 + c * 64, k, b2, b1);
+          }
         }
       }
     }
@@ -277,11 +314,15 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
 #pragma unroll
         for (int g = 0; g < 4; g++) {
           const long col = (long)n0 + c * 32 + g * 8;
-          if (col < epi.N) {
+          if (col + 8 <= epi.N) {
             float v[8];
 #pragma unroll
             for (int j = 0; j < 8; j++) v[j] = __uint_as_float(r[g * 8 + j]);
             epi_store_vec8(epi, row, col, v);
+          } else if (col < epi.N) {  // ragged tail (e.g. Nkv = 300)
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+              if (col + j < epi.N) epi_store_scalar(epi, row, col + j, __uint_as_float(r[g * 8 + j]));
           }
         }
       }
@@ -420,34 +461,65 @@ static int make_map(CUtensorMap* tm, const void* ptr, uint64_t dim0, uint64_t di
   return 0;
 }
 
+// 4-D bf16 tensor map for batched operands: (dim0 contiguous, dim1 rows with stride ld, batch2, batch1)
+static int make_map4(CUtensorMap* tm, const void* ptr, uint64_t dim0, uint64_t dim1, uint64_t ld, uint64_t nb2, uint64_t s2,
+                     uint64_t nb1, uint64_t s1, uint32_t box0, uint32_t box1) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) CMX_FAIL(-2, "cuTensorMapEncodeTiled unavailable");
+  cuuint64_t dims[4] = {dim0, dim1, nb2, nb1};
+  // a batch dimension of extent 1 may carry stride 0 from the caller; TMA wants a positive 16-byte multiple
+  cuuint64_t strides[3] = {ld * 2, (nb2 > 1 ? s2 : ld) * 2, (nb1 > 1 ? s1 : ld) * 2};
+  cuuint32_t box[4] = {box0, box1, 1, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    CMX_FAIL(-3, "cuTensorMapEncodeTiled(4d) failed (%d): dims %llu x %llu x %llu x %llu strides %llu %llu %llu", (int)r,
+             (unsigned long long)dim0, (unsigned long long)dim1, (unsigned long long)nb2, (unsigned long long)nb1,
+             (unsigned long long)strides[0], (unsigned long long)strides[1], (unsigned long long)strides[2]);
+  return 0;
+}
+
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 static bool tc_eligible(const CmxGemm* g) {
-  if (g->batch1 != 1 || g->batch2 != 1) return false;
-  if (g->M < 1 || g->N < 8 || g->K < 8) return false;
-  if ((g->N % 8) || (g->lda % 8) || (g->ldb % 8) || (g->ldc % 8)) return false;
+  const bool batched = g->batch1 != 1 || g->batch2 != 1;
+  if (g->M < 1 || g->N < 1 || g->K < 1) return false;
+  if ((g->lda % 8) || (g->ldb % 8) || (g->ldc % 8)) return false;  // 16-byte row strides (TMA) / vector epilogue
   if (!aligned16(g->A) || !aligned16(g->B) || !aligned16(g->C)) return false;
   if (g->residual && ((g->ldr % 8) || !aligned16(g->residual))) return false;
   if (g->bias && !aligned16(g->bias)) return false;
-  if (g->trans_a && !g->trans_b) return false;                       // (MN, K) combination not instantiated
-  if (!g->trans_a && (g->K % 8)) return false;                       // K-major rows: 16 B multiple
-  if (g->trans_a && (g->M % 8)) return false;
-  if (g->trans_b && (g->N % 8)) return false;
-  if (!g->trans_b && (g->K % 8)) return false;
+  if (g->trans_a && !g->trans_b) return false;  // (MN, K) combination not instantiated
   if ((g->split_k > 1 || g->accumulate) && g->c_dtype != CMX_F32) return false;
+  if (batched) {
+    if (g->residual || g->bias || g->row_scale) return false;
+    if ((g->sA1 % 8) || (g->sA2 % 8) || (g->sB1 % 8) || (g->sB2 % 8) || (g->sC1 % 8) || (g->sC2 % 8)) return false;
+    if ((g->batch1 > 1 && (g->sA1 <= 0 || g->sB1 <= 0)) || (g->batch2 > 1 && (g->sA2 <= 0 || g->sB2 <= 0))) return false;
+    if ((long)g->batch1 * g->batch2 * (g->split_k > 1 ? g->split_k : 1) > 65535) return false;
+  }
   return true;
 }
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, bool BATCHED>
 static int launch_tc(const CmxGemm* g, const Epi& epi, cudaStream_t st) {
   CUtensorMap tmA, tmB;
   int rc;
-  if (!A_MN) rc = make_map(&tmA, g->A, g->K, g->M, g->lda, TC_BK, TC_BM);
-  else rc = make_map(&tmA, g->A, g->M, g->K, g->lda, 64, TC_BK);
-  if (rc) return rc;
-  if (!B_MN) rc = make_map(&tmB, g->B, g->K, g->N, g->ldb, TC_BK, BN);
-  else rc = make_map(&tmB, g->B, g->N, g->K, g->ldb, 64, TC_BK);
-  if (rc) return rc;
+  if (!BATCHED) {
+    if (!A_MN) rc = make_map(&tmA, g->A, g->K, g->M, g->lda, TC_BK, TC_BM);
+    else rc = make_map(&tmA, g->A, g->M, g->K, g->lda, 64, TC_BK);
+    if (rc) return rc;
+    if (!B_MN) rc = make_map(&tmB, g->B, g->K, g->N, g->ldb, TC_BK, BN);
+    else rc = make_map(&tmB, g->B, g->N, g->K, g->ldb, 64, TC_BK);
+    if (rc) return rc;
+  } else {
+    if (!A_MN) rc = make_map4(&tmA, g->A, g->K, g->M, g->lda, g->batch2, g->sA2, g->batch1, g->sA1, TC_BK, TC_BM);
+    else rc = make_map4(&tmA, g->A, g->M, g->K, g->lda, g->batch2, g->sA2, g->batch1, g->sA1, 64, TC_BK);
+    if (rc) return rc;
+    if (!B_MN) rc = make_map4(&tmB, g->B, g->K, g->N, g->ldb, g->batch2, g->sB2, g->batch1, g->sB1, TC_BK, BN);
+    else rc = make_map4(&tmB, g->B, g->N, g->K, g->ldb, g->batch2, g->sB2, g->batch1, g->sB1, 64, TC_BK);
+    if (rc) return rc;
+  }
   const int kb_total = cdiv(g->K, TC_BK);
   int split = g->split_k > 1 ? g->split_k : 1;
   if (split > kb_total) split = kb_total;
@@ -460,7 +532,7 @@ static int launch_tc(const CmxGemm* g, const Epi& epi, cudaStream_t st) {
   if (stages < 1) stages = 1;
   const size_t smem = (size_t)stages * STAGE_BYTES + 1024 + 16 * stages + 64;
   static bool attr_done = false;
-  auto kern = gemm_tc_kernel<BN, A_MN, B_MN>;
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, BATCHED>;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) CMX_FAIL((int)e, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
@@ -468,41 +540,55 @@ static int launch_tc(const CmxGemm* g, const Epi& epi, cudaStream_t st) {
   }
   Epi e2 = epi;
   e2.atomic = (split > 1 || g->accumulate) ? 1 : 0;
-  dim3 grid(cdiv(g->N, BN), cdiv(g->M, TC_BM), split);
-  kern<<<grid, TC_THREADS, smem, st>>>(tmA, tmB, e2, kb_total, kb_per, stages);
+  TcBatch tb;
+  tb.batch2 = g->batch2;
+  tb.splits = split;
+  tb.sC1 = g->sC1;
+  tb.sC2 = g->sC2;
+  dim3 grid(cdiv(g->N, BN), cdiv(g->M, TC_BM), (unsigned)(split * g->batch1 * g->batch2));
+  kern<<<grid, TC_THREADS, smem, st>>>(tmA, tmB, e2, kb_total, kb_per, stages, tb);
   g_cmx_launches++;
   CMX_CHECK_LAUNCH("gemm_tc_kernel");
   return 0;
 }
 
+// tile width: least padded columns, ties to the wider tile.  MN-major B tiles are built from 64-wide chunks.
 static int pick_bn(const CmxGemm* g) {
   const long N = g->N;
-  if (g->trans_b) {  // MN-major B tiles are built from 64-wide chunks
-    if (N <= 64) return 64;
-    if (N <= 128) return 128;
-    if (N % 256 == 0 || N > 512) return 256;
-    return 128;
+  const int cands_k[4] = {256, 160, 128, 64};
+  const int cands_mn[3] = {256, 128, 64};
+  const int* c = g->trans_b ? cands_mn : cands_k;
+  const int nc = g->trans_b ? 3 : 4;
+  int best = c[0];
+  long best_cost = -1;
+  for (int i = 0; i < nc; i++) {
+    const long cost = (N + c[i] - 1) / c[i] * c[i];
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = c[i]; }
   }
-  if (N <= 64) return 64;
-  if (N <= 128) return 128;
-  if (N % 160 == 0 && N % 256 != 0) return 160;
-  return 256;
+  return best;
 }
 
 static int dispatch_tc(const CmxGemm* g, const Epi& epi, cudaStream_t st) {
   const int bn = pick_bn(g);
   const bool a = g->trans_a != 0, b = g->trans_b != 0;
-#define TC_CASE(BNv)                                                     \
-  if (bn == BNv) {                                                       \
-    if (!a && !b) return launch_tc<BNv, false, false>(g, epi, st);       \
-    if (!a && b) return launch_tc<BNv, false, true>(g, epi, st);         \
-    return launch_tc<BNv, true, true>(g, epi, st);                       \
+  const bool batched = g->batch1 != 1 || g->batch2 != 1;
+#define TC_CASE(BNv)                                                                                   \
+  if (bn == BNv) {                                                                                     \
+    if (!batched) {                                                                                    \
+      if (!a && !b) return launch_tc<BNv, false, false, false>(g, epi, st);                            \
+      if (!a && b) return launch_tc<BNv, false, true, false>(g, epi, st);                              \
+      return launch_tc<BNv, true, true, false>(g, epi, st);                                            \
+    } else {                                                                                           \
+      if (!a && !b) return launch_tc<BNv, false, false, true>(g, epi, st);                             \
+      if (!a && b) return launch_tc<BNv, false, true, true>(g, epi, st);                               \
+      return launch_tc<BNv, true, true, true>(g, epi, st);                                             \
+    }                                                                                                  \
   }
   TC_CASE(64)
   TC_CASE(128)
   TC_CASE(256)
 #undef TC_CASE
-  if (bn == 160) return launch_tc<160, false, false>(g, epi, st);
+  if (bn == 160) return batched ? launch_tc<160, false, false, true>(g, epi, st) : launch_tc<160, false, false, false>(g, epi, st);
   CMX_FAIL(-4, "no tcgen05 instantiation for BN=%d", bn);
 }
 

@@ -260,15 +260,16 @@ class Engine:
         kv = self.E(B * Nk, 2 * C)
         ops.mm(kv_in, self.W(p + ".attn.kv.weight"), kv, bias=self.P(p + ".attn.kv.bias"))
         # S = scale * Q K^T  (fp32, transient), P = softmax(S), O = P V
-        S = self.E(B * heads * N, Nk, dtype=f32)
-        ops.gemm_raw(q, kv, S, N, Nk, d, C, 2 * C, Nk, batch=(B, heads), sA=(N * C, d), sB=(Nk * 2 * C, d),
-                     sC=(heads * N * Nk, N * Nk), alpha=scale)
-        Pm = self.E(B * heads * N, Nk)
+        Np = (Nk + 7) // 8 * 8   # leading dimension of the score / probability rows (16-byte rows for TMA)
+        S = self.E(B * heads * N, Np, dtype=f32)[:, :Nk]
+        ops.gemm_raw(q, kv, S, N, Nk, d, C, 2 * C, Np, batch=(B, heads), sA=(N * C, d), sB=(Nk * 2 * C, d),
+                     sC=(heads * N * Np, N * Np), alpha=scale)
+        Pm = self.E(B * heads * N, Np)[:, :Nk]
         ops.softmax_rows_fwd(S, Pm)
         del S
         O = self.E(M, C)
-        ops.gemm_raw(Pm, kv, O, N, d, Nk, Nk, 2 * C, C, b_off=C, trans_b=True, batch=(B, heads),
-                     sA=(heads * N * Nk, N * Nk), sB=(Nk * 2 * C, d), sC=(N * C, d))
+        ops.gemm_raw(Pm, kv, O, N, d, Nk, Np, 2 * C, C, b_off=C, trans_b=True, batch=(B, heads),
+                     sA=(heads * N * Np, N * Np), sB=(Nk * 2 * C, d), sC=(N * C, d))
         x1 = self.E(M, C, dtype=f32)
         ops.mm(O, self.W(p + ".attn.proj.weight"), x1, bias=self.P(p + ".attn.proj.bias"), residual=x,
                row_scale=None if dp is None else dp[0], rows_per_sample=N)
@@ -320,24 +321,32 @@ class Engine:
         self.linear_wgrad(dx1_bf, c.O, p + ".attn.proj.weight", p + ".attn.proj.bias")
         dO = self.E(M, C)
         ops.mm(dx1_bf, self.W(p + ".attn.proj.weight"), dO, tb=True)
-        dkv = self.E(B * Nk, 2 * C)
+        # dK / dV contract over all N tokens into a tiny [Nk, 64] tile per (sample, head): split-K with fp32
+        # atomics for parallelism, then one small cast to the bf16 GEMM operand
+        dkv32 = self.Z(B * Nk, 2 * C)
         bs = (B, heads)
-        sP = (heads * N * Nk, N * Nk)
+        Np = (Nk + 7) // 8 * 8
+        sP = (heads * N * Np, N * Np)
+        tiles = B * heads * ((Nk + 127) // 128)
+        split = max(1, min(N // 512, (2 * ops.NUM_SMS + tiles - 1) // tiles))
         # dV = P^T dO
-        ops.gemm_raw(c.Pm, dO, dkv, Nk, d, N, Nk, C, 2 * C, c_off=C, trans_a=True, trans_b=True, batch=bs, sA=sP,
-                     sB=(N * C, d), sC=(Nk * 2 * C, d))
+        ops.gemm_raw(c.Pm, dO, dkv32, Nk, d, N, Np, C, 2 * C, c_off=C, trans_a=True, trans_b=True, batch=bs, sA=sP,
+                     sB=(N * C, d), sC=(Nk * 2 * C, d), accumulate=True, split_k=split)
         # dP = dO V^T
-        dP = self.E(B * heads * N, Nk, dtype=f32)
-        ops.gemm_raw(dO, c.kv, dP, N, Nk, d, C, 2 * C, Nk, b_off=C, batch=bs, sA=(N * C, d), sB=(Nk * 2 * C, d), sC=sP)
-        dS = self.E(B * heads * N, Nk)
+        dP = self.E(B * heads * N, Np, dtype=f32)[:, :Nk]
+        ops.gemm_raw(dO, c.kv, dP, N, Nk, d, C, 2 * C, Np, b_off=C, batch=bs, sA=(N * C, d), sB=(Nk * 2 * C, d), sC=sP)
+        dS = self.E(B * heads * N, Np)[:, :Nk]
         ops.softmax_rows_bwd(c.Pm, dP, scale, dS)
         del dP
         # dQ = dS K ; dK = dS^T Q
         dq = self.E(M, C)
-        ops.gemm_raw(dS, c.kv, dq, N, d, Nk, Nk, 2 * C, C, trans_b=True, batch=bs, sA=sP, sB=(Nk * 2 * C, d), sC=(N * C, d))
-        ops.gemm_raw(dS, c.q, dkv, Nk, d, N, Nk, C, 2 * C, trans_a=True, trans_b=True, batch=bs, sA=sP, sB=(N * C, d),
-                     sC=(Nk * 2 * C, d))
+        ops.gemm_raw(dS, c.kv, dq, N, d, Nk, Np, 2 * C, C, trans_b=True, batch=bs, sA=sP, sB=(Nk * 2 * C, d), sC=(N * C, d))
+        ops.gemm_raw(dS, c.q, dkv32, Nk, d, N, Np, C, 2 * C, trans_a=True, trans_b=True, batch=bs, sA=sP, sB=(N * C, d),
+                     sC=(Nk * 2 * C, d), accumulate=True, split_k=split)
         del dS
+        dkv = self.E(B * Nk, 2 * C)
+        ops.cast_f32_bf16(dkv32, dkv)
+        del dkv32
         self.linear_wgrad(dkv, c.kv_in, p + ".attn.kv.weight", p + ".attn.kv.bias")
         dkvin = self.E(B * Nk, C)
         ops.mm(dkv, self.W(p + ".attn.kv.weight"), dkvin, tb=True)

@@ -39,6 +39,20 @@ def test_tc_forward_plain(M, N, K):
     _check(out, _ref(a, b, False, False), K, "tc fwd %dx%dx%d" % (M, N, K))
 
 
+@pytest.mark.parametrize("M,N,K", [(200, 300, 64), (130, 64, 300), (257, 300, 300)])
+def test_tc_forward_ragged(M, N, K):
+    """N and K that are not multiples of 8 (Nkv = 300): padded leading dimensions, TMA zero fill, scalar tail stores"""
+    torch.manual_seed(6)
+    Kp, Np = (K + 7) // 8 * 8, (N + 7) // 8 * 8
+    a = torch.randn(M, Kp, device=DEV).to(bf)[:, :K]
+    b = torch.randn(N, Kp, device=DEV).to(bf)[:, :K]
+    out = torch.full((M, Np), 3.0, device=DEV)[:, :N]
+    ops.mm(a, b, out, impl=2)
+    _check(out, a.float() @ b.float().t(), K, "ragged")
+    if Np > N:
+        assert float((out.as_strided((M, Np - N), (Np, 1), N) - 3.0).abs().max()) == 0.0   # pad columns untouched
+
+
 @pytest.mark.parametrize("M,N,K", [(300, 64, 64), (520, 320, 320), (1000, 256, 128)])
 def test_tc_forward_epilogue(M, N, K):
     torch.manual_seed(1)
@@ -88,6 +102,71 @@ def test_tc_wgrad_mn_major_splitk(M, N, K):
     out = torch.ones(M, N, device=DEV, dtype=torch.float32)
     ops.mm(a, b, out, ta=True, tb=True, accumulate=True, impl=2)
     _check(out, 1 + _ref(a, b, True, True), K, "tc wgrad")
+
+
+@pytest.mark.parametrize("N,Nk,heads", [(1200, 300, 5), (400, 300, 2), (333, 77, 1)])
+def test_tc_batched_attention_shapes(N, Nk, heads):
+    """the six batched GEMMs of (spatial-reduction) self-attention forward + backward on strided head views,
+    Nkv = 300 (ragged: not a multiple of 8 -> padded leading dimension, TMA zero fill)"""
+    torch.manual_seed(4)
+    B, d = 2, 64
+    C = heads * d
+    Np = (Nk + 7) // 8 * 8
+    q = torch.randn(B * N, C, device=DEV).to(bf)
+    kv = torch.randn(B * Nk, 2 * C, device=DEV).to(bf)
+    dO = torch.randn(B * N, C, device=DEV).to(bf)
+    qf = q.float().view(B, N, heads, d).permute(0, 2, 1, 3)
+    kf = kv.float().view(B, Nk, 2, heads, d)[:, :, 0].permute(0, 2, 1, 3)
+    vf = kv.float().view(B, Nk, 2, heads, d)[:, :, 1].permute(0, 2, 1, 3)
+    dOf = dO.float().view(B, N, heads, d).permute(0, 2, 1, 3)
+    bs = (B, heads)
+    sP = (heads * N * Np, N * Np)
+    S = torch.full((B * heads * N, Np), 7.0, device=DEV)[:, :Nk]
+    ops.gemm_raw(q, kv, S, N, Nk, d, C, 2 * C, Np, batch=bs, sA=(N * C, d), sB=(Nk * 2 * C, d), sC=sP, alpha=0.125, impl=2)
+    _check(S.reshape(B, heads, N, Nk), 0.125 * qf @ kf.transpose(-1, -2), d, "S = QK^T")
+    P = torch.softmax(S.float(), -1)
+    Pb = torch.zeros(B * heads * N, Np, device=DEV, dtype=bf)[:, :Nk]
+    Pb.copy_(P)
+    Pf = Pb.float().reshape(B, heads, N, Nk)
+    O = torch.empty(B * N, C, device=DEV, dtype=bf)
+    ops.gemm_raw(Pb, kv, O, N, d, Nk, Np, 2 * C, C, b_off=C, trans_b=True, batch=bs, sA=sP, sB=(Nk * 2 * C, d), sC=(N * C, d), impl=2)
+    _check(O.view(B, N, heads, d).permute(0, 2, 1, 3), Pf @ vf, Nk, "O = PV")
+    dkv = torch.zeros(B * Nk, 2 * C, device=DEV)
+    ops.gemm_raw(Pb, dO, dkv, Nk, d, N, Np, C, 2 * C, c_off=C, trans_a=True, trans_b=True, batch=bs, sA=sP, sB=(N * C, d),
+                 sC=(Nk * 2 * C, d), accumulate=True, split_k=3, impl=2)
+    ops.gemm_raw(Pb, q, dkv, Nk, d, N, Np, C, 2 * C, trans_a=True, trans_b=True, batch=bs, sA=sP, sB=(N * C, d),
+                 sC=(Nk * 2 * C, d), accumulate=True, split_k=2, impl=2)
+    got = dkv.view(B, Nk, 2, heads, d)
+    _check(got[:, :, 1].permute(0, 2, 1, 3), Pf.transpose(-1, -2) @ dOf, N, "dV = P^T dO")
+    _check(got[:, :, 0].permute(0, 2, 1, 3), Pf.transpose(-1, -2) @ qf, N, "dK-like = P^T Q")
+    dP = torch.empty(B * heads * N, Np, device=DEV)[:, :Nk]
+    ops.gemm_raw(dO, kv, dP, N, Nk, d, C, 2 * C, Np, b_off=C, batch=bs, sA=(N * C, d), sB=(Nk * 2 * C, d), sC=sP, impl=2)
+    _check(dP.reshape(B, heads, N, Nk), dOf @ vf.transpose(-1, -2), d, "dP = dO V^T")
+    dq = torch.empty(B * N, C, device=DEV, dtype=bf)
+    ops.gemm_raw(Pb, kv, dq, N, d, Nk, Np, 2 * C, C, trans_b=True, batch=bs, sA=sP, sB=(Nk * 2 * C, d), sC=(N * C, d), impl=2)
+    _check(dq.view(B, N, heads, d).permute(0, 2, 1, 3), Pf @ kf, Nk, "dQ-like = P K")
+
+
+def test_tc_batched_ffm_context():
+    """FFM cross-attention context: ctx[b,h] = K^T V over all tokens (64x64 output, split-K), then q @ ctx"""
+    torch.manual_seed(5)
+    B, N, heads, d = 2, 2500, 2, 64
+    C = heads * d
+    kv = torch.randn(B * N, 2 * C, device=DEV).to(bf)
+    ctx = torch.zeros(B * heads, d, d, device=DEV)
+    ops.gemm_raw(kv, kv, ctx, d, d, N, 2 * C, 2 * C, d, b_off=C, trans_a=True, trans_b=True, batch=(B, heads),
+                 sA=(N * 2 * C, d), sB=(N * 2 * C, d), sC=(heads * d * d, d * d), accumulate=True, split_k=4, impl=2)
+    k = kv.float().view(B, N, 2, heads, d)[:, :, 0].permute(0, 2, 1, 3)
+    v = kv.float().view(B, N, 2, heads, d)[:, :, 1].permute(0, 2, 1, 3)
+    _check(ctx.view(B, heads, d, d), k.transpose(-1, -2) @ v, N, "ctx = K^T V")
+    p16 = torch.softmax(ctx * 0.125, dim=-2).to(bf)
+    u = torch.randn(B * N, C, device=DEV).to(bf)
+    yv = torch.zeros(B * N, 2 * C, device=DEV, dtype=bf)
+    ops.gemm_raw(u, p16, yv, N, d, d, C, d, 2 * C, c_off=C, trans_b=True, batch=(B, heads), sA=(N * C, d),
+                 sB=(heads * d * d, d * d), sC=(N * 2 * C, d), impl=2)
+    ref = u.float().view(B, N, heads, d).permute(0, 2, 1, 3) @ p16.float().view(B, heads, d, d)
+    _check(yv[:, C:].reshape(B, N, heads, d).permute(0, 2, 1, 3), ref, d, "v = q ctx")
+    assert float(yv[:, :C].abs().max()) == 0.0
 
 
 def test_auto_dispatch_prefers_tc():
