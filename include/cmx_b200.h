@@ -25,7 +25,7 @@ int cmx_version(void);
 long long cmx_launch_count(void);
 
 /* ---------------------------------------------------------------------------------------------
- * GEMM  C[M,N] = residual + row_scale[row/rows_per_sample] * act(alpha * A.B + bias)
+ * GEMM  C[M,N] = residual + row_scale[row/rows_per_sample] * act(alpha * A.B + bias),  act in {none, ReLU}
  * Replaces every nn.Linear / 1x1 conv / patchified conv / bmm of the path:
  *   dual_segformer.py:68,72 (fc1, fc2) :119-135 (q, sr, kv, q@k^T, attn@v, proj) :219 (patch embed proj)
  *   net_utils.py:79-83, 206-212, 274-279, 325-328 ; MLPDecoder.py:18, 76, 79 ; and their autograd
@@ -59,6 +59,8 @@ typedef struct CmxGemm {
   int32_t impl;
 } CmxGemm;
 int cmx_gemm(const CmxGemm* g, void* stream);
+/* debug aid: device buffer (3*64*4 int64) receiving clock64 stamps of CTA 0's producer / MMA / epilogue roles, or NULL */
+int cmx_debug_set_gemm_trace(void* buf);
 /* which implementation cmx_gemm would pick: 2 = tcgen05, 1 = fallback */
 int cmx_gemm_which(const CmxGemm* g);
 

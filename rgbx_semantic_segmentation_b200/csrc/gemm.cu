@@ -38,8 +38,7 @@ __device__ __forceinline__ float epi_scalar(const Epi& e, long row, long col, fl
   float v = acc * e.alpha;
   if (e.bias) v += e.bias[col];
   if (e.act == CMX_ACT_RELU) v = fmaxf(v, 0.f);
-  else if (e.act == CMX_ACT_GELU) v = gelu_f(v);
-  if (e.row_scale) v *= e.row_scale[row / e.rows_per_sample];
+  if (e.row_scale) v *= e.row_scale[(int)row / e.rows_per_sample];
   if (e.res) {
     if (e.r_dtype == CMX_F32) v += reinterpret_cast<const float*>(e.res)[row * e.ldr + col];
     else v += __bfloat162float(reinterpret_cast<const bf16*>(e.res)[row * e.ldr + col]);
@@ -55,19 +54,40 @@ __device__ __forceinline__ void epi_store_scalar(const Epi& e, long row, long co
     reinterpret_cast<bf16*>(e.C)[row * e.ldc + col] = __float2bfloat16(v);
   }
 }
+// epilogue math for 8 consecutive columns kept in registers (used by the TMA-store path); sbias = shared-memory
+// copy of the bias slice of this tile (or nullptr).  Out-of-range columns/rows only skip the residual load.
+__device__ __forceinline__ void epi_math8(const Epi& e, long row, long col, const float (&sbias)[8], bool row_ok, float rs,
+                                          float (&v)[8]) {
+  const float lo = e.act == CMX_ACT_RELU ? 0.f : -INFINITY;   // ReLU as a clamp: no branch in the unrolled loop
+#pragma unroll
+  for (int i = 0; i < 8; i++) v[i] = fmaxf(fmaf(v[i], e.alpha, sbias[i]), lo) * rs;
+  if (e.res && row_ok) {
+    if (col + 8 <= e.N) {
+      float r[8];
+      if (e.r_dtype == CMX_F32) load8(reinterpret_cast<const float*>(e.res) + row * e.ldr + col, r);
+      else load8(reinterpret_cast<const bf16*>(e.res) + row * e.ldr + col, r);
+#pragma unroll
+      for (int i = 0; i < 8; i++) v[i] += r[i];
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; i++)
+        if (col + i < e.N)
+          v[i] += e.r_dtype == CMX_F32 ? reinterpret_cast<const float*>(e.res)[row * e.ldr + col + i]
+                                       : __bfloat162float(reinterpret_cast<const bf16*>(e.res)[row * e.ldr + col + i]);
+    }
+  }
+}
+
 // 8 consecutive columns, all in range, 16B-aligned addresses (checked on the host)
 __device__ __forceinline__ void epi_store_vec8(const Epi& e, long row, long col, float* v) {
-  float rs = e.row_scale ? e.row_scale[row / e.rows_per_sample] : 1.f;
+  const float rs = e.row_scale ? e.row_scale[(int)row / e.rows_per_sample] : 1.f;
+  const float lo = e.act == CMX_ACT_RELU ? 0.f : -INFINITY;
   float b[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) b[i] = 0.f;
   if (e.bias) load8(e.bias + col, b);
 #pragma unroll
-  for (int i = 0; i < 8; i++) {
-    float t = v[i] * e.alpha;
-    if (e.bias) t += b[i];
-    if (e.act == CMX_ACT_RELU) t = fmaxf(t, 0.f);
-    else if (e.act == CMX_ACT_GELU) t = gelu_f(t);
-    v[i] = t * rs;
-  }
+  for (int i = 0; i < 8; i++) v[i] = fmaxf(fmaf(v[i], e.alpha, b[i]), lo) * rs;
   if (e.res) {
     float r[8];
     if (e.r_dtype == CMX_F32) load8(reinterpret_cast<const float*>(e.res) + row * e.ldr + col, r);
@@ -132,6 +152,22 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm,
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -157,6 +193,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
       : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// wait that also threads the 32 destination registers through the asm statement, so that no consumer of r[] can be
+// scheduled above the wait when other work is placed between the tcgen05.ld and its wait (software pipelining)
+__device__ __forceinline__ void tmem_wait_ld_dep(uint32_t* r) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
+                 "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),
+                 "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
+}
 
 // UMMA shared-memory descriptor, SWIZZLE_128B, sm_100 version field = 1
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -165,63 +212,78 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
 }
 
 // ------------------------------------------------------------------------------------------------
-// tcgen05 GEMM kernel.  One 128 x BN output tile per CTA (grid.x = N tiles, grid.y = M tiles,
-// grid.z = split-K slices).  BK = 64 bf16 = one 128-byte swizzle atom.
+// tcgen05 GEMM kernel — persistent, warp-specialised.
+//   grid  = min(#tiles, #SMs) CTAs, each walking tiles t = blockIdx.x, +gridDim.x, ... (N-tile fastest so the
+//           weight tile stays L2/smem-hot); a tile is 128 x BN of one (batch, split-K slice).
+//   warp 0 = TMA producer: the shared-memory ring (BK = 64 bf16 = one 128-byte swizzle atom per row) keeps
+//            running ACROSS tile boundaries, so the loads of tile i+1 overlap the MMAs/epilogue of tile i.
+//   warp 1 = MMA issuer (one elected lane) + TMEM allocator; accumulators are double-buffered in TMEM
+//            (2 x BN fp32 columns) so the MMAs of tile i+1 overlap the epilogue of tile i.
+//   warps 2-9 = epilogue (two warps per TMEM lane quarter, interleaved 32-column chunks):
+//            tcgen05.ld -> bias/act/DropPath-scale/residual -> 16-byte stores or fp32 red.add (split-K).
 // ------------------------------------------------------------------------------------------------
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;
-constexpr int TC_THREADS = 192;
+constexpr int TC_EPI_WARPS = 8;
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 
-struct TcBatch {
-  int batch2, splits;
+struct TcSched {
+  int tiles_n, tiles_m, batch2, nbatch, splits;
+  int kb_total, kb_per, stages;
+  long total_tiles;
   long sC1, sC2;  // element strides of C per batch index
+  int tma_store;  // 0 = per-thread global stores (atomics / odd layouts), 1 = smem-staged TMA bulk store
+  long long* trace;  // debug: CTA 0 writes clock64 stamps [role][tile][4] (role 0 producer, 1 mma, 2 epilogue)
 };
+#define TC_TRACE(role, tile, slot)                                                              \
+  do {                                                                                          \
+    if (sc.trace && blockIdx.x == 0 && (tile) < 64) sc.trace[((role) * 64 + (tile)) * 4 + (slot)] = clock64(); \
+  } while (0)
+
+constexpr uint32_t TC_CSTAGE_BYTES = TC_EPI_WARPS * 2 * 4096;  // per epilogue warp: 2 x (32 rows x 128 B)
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 
 template <int BN, bool A_MN, bool B_MN, bool BATCHED>
-__global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                            const __grid_constant__ CUtensorMap tmB, Epi epi,
-                                                            int k_blocks_total, int k_blocks_per_split, int stages,
-                                                            TcBatch tb) {
+__global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                               const __grid_constant__ CUtensorMap tmB,
+                                                               const __grid_constant__ CUtensorMap tmC, Epi epi0,
+                                                               TcSched sc) {
   extern __shared__ uint8_t smem_raw[];
   constexpr uint32_t A_BYTES = TC_BM * TC_BK * 2;
   constexpr uint32_t B_BYTES = BN * TC_BK * 2;
   constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
-  constexpr uint32_t TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+  constexpr uint32_t ACC_STRIDE = BN <= 64 ? 64 : BN <= 128 ? 128 : 256;  // TMEM columns per accumulator buffer
+  constexpr uint32_t TMEM_COLS = 2 * ACC_STRIDE;
+  const int stages = sc.stages;
 
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + stages * STAGE_BYTES;  // full[stages], empty[stages], tmem_full, tmem_ptr
+  const uint32_t cstage_base = smem_base + stages * STAGE_BYTES;                   // 1024-aligned (stage sizes are)
+  const uint32_t bias_base = cstage_base + (sc.tma_store ? TC_CSTAGE_BYTES : 0u);  // float[2][256]
+  const uint32_t bar_base = bias_base + 2048u;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (stages + s); };
-  const uint32_t tmem_full_bar = bar_base + 16u * stages;
-  const uint32_t tmem_ptr_addr = tmem_full_bar + 8u;
+  const uint32_t tfull_bar = bar_base + 16u * stages;       // [2]
+  const uint32_t tempty_bar = tfull_bar + 16u;              // [2]
+  const uint32_t tmem_ptr_addr = tempty_bar + 16u;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * BN;
-  const int m0 = blockIdx.y * TC_BM;
-  int zz = blockIdx.z;
-  const int split_idx = zz % tb.splits;
-  zz /= tb.splits;
-  const int b2 = BATCHED ? zz % tb.batch2 : 0;
-  const int b1 = BATCHED ? zz / tb.batch2 : 0;
-  if (BATCHED) {
-    const long off = (long)b1 * tb.sC1 + (long)b2 * tb.sC2;
-    if (epi.c_dtype == CMX_F32) epi.C = reinterpret_cast<float*>(epi.C) + off;
-    else epi.C = reinterpret_cast<bf16*>(epi.C) + off;
-  }
-  const int kb_begin = split_idx * k_blocks_per_split;
-  int kb_end = kb_begin + k_blocks_per_split;
-  if (kb_end > k_blocks_total) kb_end = k_blocks_total;
-  const int nkb = kb_end - kb_begin;  // >= 1 by construction on the host
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+    if (sc.tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmC)) : "memory");
     for (int s = 0; s < stages; s++) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int a = 0; a < 2; a++) {
+      mbar_init(tfull_bar + 8u * a, 1);
+      mbar_init(tempty_bar + 8u * a, TC_EPI_WARPS);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -235,42 +297,67 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr));
 
+  // tile -> (n tile, m tile, batch, split) ; identical arithmetic in all three roles
+  auto decode = [&](long tl, int& n0, int& m0, int& b1, int& b2, int& kb_begin, int& nkb, int& split_idx) {
+    unsigned t = (unsigned)tl;  // the host guarantees total_tiles < 2^31
+    const int tn = (int)(t % (unsigned)sc.tiles_n);
+    t /= (unsigned)sc.tiles_n;
+    const int tm = (int)(t % (unsigned)sc.tiles_m);
+    t /= (unsigned)sc.tiles_m;
+    const int bb = (int)(t % (unsigned)sc.nbatch);
+    split_idx = (int)(t / (unsigned)sc.nbatch);
+    n0 = tn * BN;
+    m0 = tm * TC_BM;
+    b2 = bb % sc.batch2;
+    b1 = bb / sc.batch2;
+    kb_begin = split_idx * sc.kb_per;
+    int kb_end = kb_begin + sc.kb_per;
+    if (kb_end > sc.kb_total) kb_end = sc.kb_total;
+    nkb = kb_end - kb_begin;
+  };
+
   if (warp == 0) {
     // ================= TMA producer =================
     if (lane == 0) {
-      for (int i = 0; i < nkb; i++) {
-        const int s = i % stages;
-        const uint32_t ph = (uint32_t)(i / stages) & 1u;
-        mbar_wait(empty_bar(s), ph ^ 1u);
-        mbar_expect_tx(full_bar(s), STAGE_BYTES);
-        const uint32_t sa = smem_base + s * STAGE_BYTES;
-        const uint32_t sb = sa + A_BYTES;
-        const int k = (kb_begin + i) * TC_BK;
-        if (!BATCHED) {
-          if (!A_MN) {
-            tma_load_2d(sa, &tmA, full_bar(s), k, m0);
-          } else {
+      uint32_t it = 0;
+      for (long t = blockIdx.x; t < sc.total_tiles; t += gridDim.x) {
+        int n0, m0, b1, b2, kb_begin, nkb, sp;
+        decode(t, n0, m0, b1, b2, kb_begin, nkb, sp);
+        for (int i = 0; i < nkb; i++, it++) {
+          const int s = it % stages;
+          const uint32_t ph = (it / stages) & 1u;
+          mbar_wait(empty_bar(s), ph ^ 1u);
+          if (i == 0) TC_TRACE(0, it, 0);
+          mbar_expect_tx(full_bar(s), STAGE_BYTES);
+          const uint32_t sa = smem_base + s * STAGE_BYTES;
+          const uint32_t sb = sa + A_BYTES;
+          const int k = (kb_begin + i) * TC_BK;
+          if (!BATCHED) {
+            if (!A_MN) {
+              tma_load_2d(sa, &tmA, full_bar(s), k, m0);
+            } else {
 #pragma unroll
-            for (int c = 0; c < TC_BM / 64; c++) tma_load_2d(sa + c * 8192, &tmA, full_bar(s), m0 + c * 64, k);
-          }
-          if (!B_MN) {
-            tma_load_2d(sb, &tmB, full_bar(s), k, n0);
-          } else {
+              for (int c = 0; c < TC_BM / 64; c++) tma_load_2d(sa + c * 8192, &tmA, full_bar(s), m0 + c * 64, k);
+            }
+            if (!B_MN) {
+              tma_load_2d(sb, &tmB, full_bar(s), k, n0);
+            } else {
 #pragma unroll
-            for (int c = 0; c < BN / 64; c++) tma_load_2d(sb + c * 8192, &tmB, full_bar(s), n0 + c * 64, k);
-          }
-        } else {
-          if (!A_MN) {
-            tma_load_4d(sa, &tmA, full_bar(s), k, m0, b2, b1);
+              for (int c = 0; c < BN / 64; c++) tma_load_2d(sb + c * 8192, &tmB, full_bar(s), n0 + c * 64, k);
+            }
           } else {
+            if (!A_MN) {
+              tma_load_4d(sa, &tmA, full_bar(s), k, m0, b2, b1);
+            } else {
 #pragma unroll
-            for (int c = 0; c < TC_BM / 64; c++) tma_load_4d(sa + c * 8192, &tmA, full_bar(s), m0 + c * 64, k, b2, b1);
-          }
-          if (!B_MN) {
-            tma_load_4d(sb, &tmB, full_bar(s), k, n0, b2, b1);
-          } else {
+              for (int c = 0; c < TC_BM / 64; c++) tma_load_4d(sa + c * 8192, &tmA, full_bar(s), m0 + c * 64, k, b2, b1);
+            }
+            if (!B_MN) {
+              tma_load_4d(sb, &tmB, full_bar(s), k, n0, b2, b1);
+            } else {
 #pragma unroll
-            for (int c = 0; c < BN / 64; c++) tma_load_4d(sb + c * 8192, &tmB, full_bar(s), n0 + c * 64, k, b2, b1);
+              for (int c = 0; c < BN / 64; c++) tma_load_4d(sb + c * 8192, &tmB, full_bar(s), n0 + c * 64, k, b2, b1);
+            }
           }
         }
       }
@@ -280,53 +367,212 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
     if (lane == 0) {
       constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
                                  ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-      for (int i = 0; i < nkb; i++) {
-        const int s = i % stages;
-        const uint32_t ph = (uint32_t)(i / stages) & 1u;
-        mbar_wait(full_bar(s), ph);
+      uint32_t it = 0, lt = 0;
+      for (long t = blockIdx.x; t < sc.total_tiles; t += gridDim.x, lt++) {
+        int n0, m0, b1, b2, kb_begin, nkb, sp;
+        decode(t, n0, m0, b1, b2, kb_begin, nkb, sp);
+        const uint32_t acc = lt & 1u, aph = (lt >> 1) & 1u;
+        TC_TRACE(1, lt, 0);
+        mbar_wait(tempty_bar + 8u * acc, aph ^ 1u);  // epilogue has drained this accumulator buffer
+        TC_TRACE(1, lt, 1);
         tc_fence_after();
-        const uint32_t sa = smem_base + s * STAGE_BYTES;
-        const uint32_t sb = sa + A_BYTES;
+        const uint32_t d_tmem = tmem_base + acc * ACC_STRIDE;
+        for (int i = 0; i < nkb; i++, it++) {
+          const int s = it % stages;
+          const uint32_t ph = (it / stages) & 1u;
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          const uint32_t sa = smem_base + s * STAGE_BYTES;
+          const uint32_t sb = sa + A_BYTES;
 #pragma unroll
-        for (int k = 0; k < TC_BK / 16; k++) {
-          // K-major: 16 bf16 = 32 B inside the 128 B swizzle row; MN-major: 16 K-rows of 128 B = 2048 B
-          const uint64_t da = A_MN ? umma_desc(sa + k * 2048, 8192, 1024) : umma_desc(sa + k * 32, 16, 1024);
-          const uint64_t db = B_MN ? umma_desc(sb + k * 2048, 8192, 1024) : umma_desc(sb + k * 32, 16, 1024);
-          tc_mma_bf16(tmem_base, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < TC_BK / 16; k++) {
+            // K-major: 16 bf16 = 32 B inside the 128 B swizzle row; MN-major: 16 K-rows of 128 B = 2048 B
+            const uint64_t da = A_MN ? umma_desc(sa + k * 2048, 8192, 1024) : umma_desc(sa + k * 32, 16, 1024);
+            const uint64_t db = B_MN ? umma_desc(sb + k * 2048, 8192, 1024) : umma_desc(sb + k * 32, 16, 1024);
+            tc_mma_bf16(d_tmem, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
+          }
+          if (i == 0) TC_TRACE(1, lt, 2);
+          tc_commit(empty_bar(s));  // frees the smem slot once the MMAs that read it retire
         }
-        tc_commit(empty_bar(s));  // frees the smem slot once the MMAs that read it retire
+        tc_commit(tfull_bar + 8u * acc);
+        TC_TRACE(1, lt, 3);
       }
-      tc_commit(tmem_full_bar);
     }
   } else {
-    // ================= epilogue: warps 2..5, TMEM lane quarter = warp % 4 =================
+    // ================= epilogue: warps 2..9; TMEM lane quarter = warp % 4, two warps per quarter =================
     const int q = warp & 3;
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-    const long row = (long)m0 + q * 32 + lane;
-    const bool row_ok = row < epi.M;
-#pragma unroll 1
-    for (int c = 0; c < BN / 32; c++) {
-      uint32_t r[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
-      tmem_wait_ld();
-      if (row_ok) {
+    const int half = (warp - 2) >> 2;
+    const int etid = threadIdx.x - 64;  // 0..255
+    const uint32_t my_stage = cstage_base + (uint32_t)(warp - 2) * 8192u;
+    uint32_t lt = 0, nstore = 0;
+    for (long t = blockIdx.x; t < sc.total_tiles; t += gridDim.x, lt++) {
+      int n0, m0, b1, b2, kb_begin, nkb, sp;
+      decode(t, n0, m0, b1, b2, kb_begin, nkb, sp);
+      Epi epi = epi0;
+      if (BATCHED) {
+        const long off = (long)b1 * sc.sC1 + (long)b2 * sc.sC2;
+        if (epi.c_dtype == CMX_F32) epi.C = reinterpret_cast<float*>(epi.C) + off;
+        else epi.C = reinterpret_cast<bf16*>(epi.C) + off;
+      }
+      if (sp != 0) {  // split-K: bias / residual are contributed once, by slice 0
+        epi.bias = nullptr;
+        epi.res = nullptr;
+      }
+      // bias slice of this tile -> shared memory (double-buffered by tile parity; one named barrier per tile)
+      const uint32_t sb_addr = bias_base + (lt & 1u) * 1024u;
+      if (epi.bias && etid < BN) {
+        const float bv = (n0 + etid < epi.N) ? epi.bias[n0 + etid] : 0.f;
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(sb_addr + 4u * etid), "f"(bv) : "memory");
+      }
+      if (warp == 4 && lane == 0) TC_TRACE(2, lt, 0);
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const uint32_t acc = lt & 1u, aph = (lt >> 1) & 1u;
+      if (warp == 4 && lane == 0) TC_TRACE(2, lt, 1);
+      mbar_wait(tfull_bar + 8u * acc, aph);
+      if (warp == 4 && lane == 0) TC_TRACE(2, lt, 2);
+      tc_fence_after();
+      const long row = (long)m0 + q * 32 + lane;
+      const bool row_ok = row < epi.M;
+      const float rs = (epi.row_scale && row_ok) ? epi.row_scale[(int)row / epi.rows_per_sample] : 1.f;
+      const uint32_t t_addr = tmem_base + acc * ACC_STRIDE + ((uint32_t)(q * 32) << 16);
+      if (sc.tma_store) {
+        // ---- smem-staged TMA store: warp-private [32 rows x 128 B] boxes, SWIZZLE_128B, double buffered.
+        // The tcgen05.ld of chunk k+1 is issued before the math / st.shared of chunk k (two register sets).
+        const int UC = epi.c_dtype == CMX_F32 ? 1 : 2;   // chunks per store unit: 32 fp32 or 64 bf16 columns = 128 B
+        // k-th chunk of this warp (units half, half+2, ...), -1 when exhausted; a trailing partial unit
+        // (BN = 160 with bf16) is excluded here and handled by the per-thread store path below
+        auto chunk_of = [&](int k) -> int {
+          const int u = half + 2 * (k / UC);
+          const int c = u * UC + (k % UC);
+          if ((u + 1) * UC * 32 > BN || n0 + c * 32 >= epi.N) return -1;
+          return c;
+        };
+        auto process = [&](uint32_t* r, int c) {
+          const int cc = c % UC;
+          const uint32_t buf = my_stage + (nstore & 1u) * 4096u;
+          if (cc == 0) {
+            if (lane == 0) tma_store_wait_read<1>();  // the store that used this buffer two units ago has read it
+            __syncwarp();
+          }
 #pragma unroll
-        for (int g = 0; g < 4; g++) {
-          const long col = (long)n0 + c * 32 + g * 8;
-          if (col + 8 <= epi.N) {
+          for (int g = 0; g < 4; g++) {
             float v[8];
 #pragma unroll
             for (int j = 0; j < 8; j++) v[j] = __uint_as_float(r[g * 8 + j]);
-            epi_store_vec8(epi, row, col, v);
-          } else if (col < epi.N) {  // ragged tail (e.g. Nkv = 300)
+            float sbv[8];
 #pragma unroll
-            for (int j = 0; j < 8; j++)
-              if (col + j < epi.N) epi_store_scalar(epi, row, col + j, __uint_as_float(r[g * 8 + j]));
+            for (int j = 0; j < 8; j++) sbv[j] = 0.f;
+            if (epi.bias) {
+              const uint32_t ba = sb_addr + 4u * (c * 32 + g * 8);
+              asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(sbv[0]), "=f"(sbv[1]), "=f"(sbv[2]), "=f"(sbv[3]) : "r"(ba));
+              asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(sbv[4]), "=f"(sbv[5]), "=f"(sbv[6]), "=f"(sbv[7]) : "r"(ba + 16u));
+            }
+            epi_math8(epi, row, (long)n0 + c * 32 + g * 8, sbv, row_ok, rs, v);
+            const uint32_t sw = (uint32_t)(lane & 7);
+            if (epi.c_dtype == CMX_F32) {
+              const uint32_t j0 = (uint32_t)(g * 2);
+              st_shared_v4(buf + lane * 128u + ((j0 ^ sw) << 4), __float_as_uint(v[0]), __float_as_uint(v[1]),
+                           __float_as_uint(v[2]), __float_as_uint(v[3]));
+              st_shared_v4(buf + lane * 128u + (((j0 + 1) ^ sw) << 4), __float_as_uint(v[4]), __float_as_uint(v[5]),
+                           __float_as_uint(v[6]), __float_as_uint(v[7]));
+            } else {
+              uint32_t pk[4];
+#pragma unroll
+              for (int j = 0; j < 4; j++) {
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+                pk[j] = *reinterpret_cast<uint32_t*>(&h2);
+              }
+              const uint32_t j0 = (uint32_t)(cc * 4 + g);
+              st_shared_v4(buf + lane * 128u + ((j0 ^ sw) << 4), pk[0], pk[1], pk[2], pk[3]);
+            }
+          }
+          // last chunk of the unit (or the unit is cut short by N): publish the box
+          const bool unit_done = (cc == UC - 1) || (n0 + (c + 1) * 32 >= epi.N);
+          if (unit_done) {
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              const int ucol0 = n0 + (c - cc) * 32;
+              if (BATCHED) tma_store_4d(&tmC, buf, ucol0, m0 + q * 32, b2, b1);
+              else tma_store_2d(&tmC, buf, ucol0, m0 + q * 32);
+              tma_store_commit();
+            }
+            nstore++;
+          }
+        };
+        uint32_t ra[32], rb[32];
+        int cA = chunk_of(0);
+        if (cA >= 0) tmem_ld32(t_addr + (uint32_t)(cA * 32), ra);
+#pragma unroll 1
+        for (int k = 0; cA >= 0; k += 2) {
+          tmem_wait_ld_dep(ra);
+          const int cB = chunk_of(k + 1);
+          if (cB >= 0) tmem_ld32(t_addr + (uint32_t)(cB * 32), rb);
+          process(ra, cA);
+          if (cB < 0) break;
+          tmem_wait_ld_dep(rb);
+          cA = chunk_of(k + 2);
+          if (cA >= 0) tmem_ld32(t_addr + (uint32_t)(cA * 32), ra);
+          process(rb, cB);
+        }
+        if ((BN / 32) % UC != 0) {
+          // BN = 160 with 64-column bf16 boxes leaves a 32-column remainder: a full box would spill into the
+          // neighbouring tile, so that chunk takes the per-thread store path (done by the warp owning that unit)
+          const int c = BN / 32 - 1;
+          const int u = c / UC;
+          if ((u & 1) == half && n0 + c * 32 < epi.N) {
+            uint32_t r[32];
+            tmem_ld32(t_addr + (uint32_t)(c * 32), r);
+            tmem_wait_ld();
+            if (row_ok) {
+#pragma unroll
+              for (int g = 0; g < 4; g++) {
+                const long col = (long)n0 + c * 32 + g * 8;
+                if (col + 8 <= epi.N) {
+                  float v[8];
+#pragma unroll
+                  for (int j = 0; j < 8; j++) v[j] = __uint_as_float(r[g * 8 + j]);
+                  epi_store_vec8(epi, row, col, v);
+                } else if (col < epi.N) {
+#pragma unroll
+                  for (int j = 0; j < 8; j++)
+                    if (col + j < epi.N) epi_store_scalar(epi, row, col + j, __uint_as_float(r[g * 8 + j]));
+                }
+              }
+            }
+          }
+        }
+      } else {
+#pragma unroll 1
+        for (int c = half; c < BN / 32; c += 2) {
+          if (n0 + c * 32 >= epi.N) break;
+          uint32_t r[32];
+          tmem_ld32(t_addr + (uint32_t)(c * 32), r);
+          tmem_wait_ld();
+          if (row_ok) {
+#pragma unroll
+            for (int g = 0; g < 4; g++) {
+              const long col = (long)n0 + c * 32 + g * 8;
+              if (col + 8 <= epi.N) {
+                float v[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) v[j] = __uint_as_float(r[g * 8 + j]);
+                epi_store_vec8(epi, row, col, v);
+              } else if (col < epi.N) {  // ragged tail (e.g. Nkv = 300)
+#pragma unroll
+                for (int j = 0; j < 8; j++)
+                  if (col + j < epi.N) epi_store_scalar(epi, row, col + j, __uint_as_float(r[g * 8 + j]));
+              }
+            }
           }
         }
       }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar + 8u * acc);
+      if (warp == 4 && lane == 0) TC_TRACE(2, lt, 3);
     }
+    if (sc.tma_store && lane == 0) tma_store_wait_all();  // global writes complete before the CTA retires
   }
   tc_fence_before();
   __syncthreads();
@@ -481,6 +727,41 @@ static int make_map4(CUtensorMap* tm, const void* ptr, uint64_t dim0, uint64_t d
   return 0;
 }
 
+// C tensor map for the TMA-store epilogue: box = 128 bytes x 32 rows, SWIZZLE_128B; rank 2 or 4 (batched)
+static int make_map_c(CUtensorMap* tm, const CmxGemm* g, bool batched) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) CMX_FAIL(-2, "cuTensorMapEncodeTiled unavailable");
+  const bool f32 = g->c_dtype == CMX_F32;
+  const uint64_t es_ = f32 ? 4 : 2;
+  cuuint64_t dims[4] = {(cuuint64_t)g->N, (cuuint64_t)g->M, (cuuint64_t)g->batch2, (cuuint64_t)g->batch1};
+  cuuint64_t strides[3] = {(cuuint64_t)g->ldc * es_, (cuuint64_t)(g->batch2 > 1 ? g->sC2 : g->ldc) * es_,
+                           (cuuint64_t)(g->batch1 > 1 ? g->sC1 : g->ldc) * es_};
+  cuuint32_t box[4] = {f32 ? 32u : 64u, 32u, 1u, 1u};
+  cuuint32_t est[4] = {1, 1, 1, 1};
+  CUresult r = enc(tm, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, batched ? 4 : 2, g->C, dims,
+                   strides, box, est, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) CMX_FAIL(-3, "cuTensorMapEncodeTiled(C) failed (%d)", (int)r);
+  return 0;
+}
+
+static long long* g_tc_trace = nullptr;
+CMX_API int cmx_debug_set_gemm_trace(void* buf) {  // debug only: device buffer of 3*64*4 int64, or NULL
+  g_tc_trace = reinterpret_cast<long long*>(buf);
+  return 0;
+}
+
+static int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 static bool tc_eligible(const CmxGemm* g) {
@@ -492,11 +773,11 @@ static bool tc_eligible(const CmxGemm* g) {
   if (g->bias && !aligned16(g->bias)) return false;
   if (g->trans_a && !g->trans_b) return false;  // (MN, K) combination not instantiated
   if ((g->split_k > 1 || g->accumulate) && g->c_dtype != CMX_F32) return false;
+  if (g->split_k > 1 && g->act != CMX_ACT_NONE) return false;  // non-linear epilogue needs the full sum
   if (batched) {
     if (g->residual || g->bias || g->row_scale) return false;
     if ((g->sA1 % 8) || (g->sA2 % 8) || (g->sB1 % 8) || (g->sB2 % 8) || (g->sC1 % 8) || (g->sC2 % 8)) return false;
     if ((g->batch1 > 1 && (g->sA1 <= 0 || g->sB1 <= 0)) || (g->batch2 > 1 && (g->sA2 <= 0 || g->sB2 <= 0))) return false;
-    if ((long)g->batch1 * g->batch2 * (g->split_k > 1 ? g->split_k : 1) > 65535) return false;
   }
   return true;
 }
@@ -520,17 +801,35 @@ static int launch_tc(const CmxGemm* g, const Epi& epi, cudaStream_t st) {
     else rc = make_map4(&tmB, g->B, g->N, g->K, g->ldb, g->batch2, g->sB2, g->batch1, g->sB1, 64, TC_BK);
     if (rc) return rc;
   }
-  const int kb_total = cdiv(g->K, TC_BK);
+  TcSched sc;
+  sc.kb_total = cdiv(g->K, TC_BK);
   int split = g->split_k > 1 ? g->split_k : 1;
-  if (split > kb_total) split = kb_total;
-  int kb_per = cdiv(kb_total, split);
-  split = cdiv(kb_total, kb_per);  // no empty slices
+  if (split > sc.kb_total) split = sc.kb_total;
+  sc.kb_per = cdiv(sc.kb_total, split);
+  split = cdiv(sc.kb_total, sc.kb_per);  // no empty slices
+  sc.splits = split;
+  sc.tiles_n = cdiv(g->N, BN);
+  sc.tiles_m = cdiv(g->M, TC_BM);
+  sc.batch2 = g->batch2;
+  sc.nbatch = g->batch1 * g->batch2;
+  sc.total_tiles = (long)sc.tiles_n * sc.tiles_m * sc.nbatch * split;
+  sc.sC1 = g->sC1;
+  sc.sC2 = g->sC2;
+  const bool atomic = (split > 1 || g->accumulate);
+  sc.tma_store = (!atomic && getenv("CMX_GEMM_NO_TMA_STORE") == nullptr) ? 1 : 0;
+  sc.trace = g_tc_trace;
+  CUtensorMap tmC;
+  memset(&tmC, 0, sizeof(tmC));
+  if (sc.tma_store) {
+    rc = make_map_c(&tmC, g, BATCHED);
+    if (rc) return rc;
+  }
   constexpr int STAGE_BYTES = (TC_BM + BN) * TC_BK * 2;
-  int max_stages = (200 * 1024) / STAGE_BYTES;
-  if (max_stages > 6) max_stages = 6;
-  int stages = kb_per < max_stages ? kb_per : max_stages;
-  if (stages < 1) stages = 1;
-  const size_t smem = (size_t)stages * STAGE_BYTES + 1024 + 16 * stages + 64;
+  int stages = (int)((200 * 1024 - (sc.tma_store ? TC_CSTAGE_BYTES : 0)) / STAGE_BYTES);
+  if (stages > 8) stages = 8;
+  if (stages < 2) stages = 2;
+  sc.stages = stages;
+  const size_t smem = (size_t)stages * STAGE_BYTES + (sc.tma_store ? TC_CSTAGE_BYTES : 0) + 2048 + 1024 + 16 * stages + 128;
   static bool attr_done = false;
   auto kern = gemm_tc_kernel<BN, A_MN, B_MN, BATCHED>;
   if (!attr_done) {
@@ -539,14 +838,9 @@ static int launch_tc(const CmxGemm* g, const Epi& epi, cudaStream_t st) {
     attr_done = true;
   }
   Epi e2 = epi;
-  e2.atomic = (split > 1 || g->accumulate) ? 1 : 0;
-  TcBatch tb;
-  tb.batch2 = g->batch2;
-  tb.splits = split;
-  tb.sC1 = g->sC1;
-  tb.sC2 = g->sC2;
-  dim3 grid(cdiv(g->N, BN), cdiv(g->M, TC_BM), (unsigned)(split * g->batch1 * g->batch2));
-  kern<<<grid, TC_THREADS, smem, st>>>(tmA, tmB, e2, kb_total, kb_per, stages, tb);
+  e2.atomic = atomic ? 1 : 0;
+  const long grid = sc.total_tiles < num_sms() ? sc.total_tiles : num_sms();
+  kern<<<(unsigned)grid, TC_THREADS, smem, st>>>(tmA, tmB, tmC, e2, sc);
   g_cmx_launches++;
   CMX_CHECK_LAUNCH("gemm_tc_kernel");
   return 0;
@@ -616,6 +910,8 @@ CMX_API int cmx_gemm(const CmxGemm* g, void* stream) {
   CMX_REQUIRE(g->batch1 >= 1 && g->batch2 >= 1, "cmx_gemm: bad batch");
   CMX_REQUIRE(!((g->split_k > 1 || g->accumulate) && g->c_dtype != CMX_F32), "cmx_gemm: split-K/accumulate needs fp32 C");
   CMX_REQUIRE(!(g->row_scale && g->rows_per_sample <= 0), "cmx_gemm: row_scale needs rows_per_sample");
+  CMX_REQUIRE(g->act == CMX_ACT_NONE || g->act == CMX_ACT_RELU, "cmx_gemm: epilogue activation must be none (0) or ReLU (1)");
+  CMX_REQUIRE(g->M < (1ll << 31) && g->N < (1ll << 31), "cmx_gemm: M, N must fit in 31 bits");
   Epi epi;
   epi.C = g->C; epi.ldc = g->ldc; epi.bias = g->bias; epi.res = g->residual; epi.ldr = g->ldr;
   epi.row_scale = g->row_scale; epi.rows_per_sample = g->rows_per_sample > 0 ? g->rows_per_sample : 1;

@@ -51,6 +51,7 @@ class Engine:
         self.forced_dropout = None   # test hook: tensor[B, E]
         self.stochastic = True       # DropPath / Dropout2d active in training mode
         self.trace = None            # debug hook: dict filled with fp32 copies of intermediate activations
+        self.poison = None           # debug hook: list of (tensor, allocation site) when NaN-poisoning is on
 
     # ------------------------------------------------------------------------------------------
     # flat parameter / gradient storage
@@ -140,6 +141,17 @@ class Engine:
     # small helpers
     # ------------------------------------------------------------------------------------------
     def E(self, *shape, dtype=bf16):
+        if self.poison is not None:
+            # debug aid (scripts/gpu_poison.py): NaN-fill every fresh buffer and remember where it was allocated,
+            # so that buffers that are read before being (fully) written can be found without compute-sanitizer
+            import sys
+            if len(shape) == 1 and isinstance(shape[0], (tuple, list)):
+                shape = tuple(shape[0])
+            t = torch.full(shape, float("nan"), device=self.dev, dtype=dtype) if dtype.is_floating_point \
+                else torch.full(shape, -1, device=self.dev, dtype=dtype)
+            f = sys._getframe(1)
+            self.poison.append((t, "%s:%d" % (f.f_code.co_name, f.f_lineno)))
+            return t
         return torch.empty(*shape, device=self.dev, dtype=dtype)
 
     def Z(self, *shape, dtype=f32):
@@ -247,8 +259,9 @@ class Engine:
             wsr = self.packed[p + ".attn.sr.weight"]
             pat = self.E(B * Nk, wsr.shape[1])
             ops.im2col_nhwc(xn1, pat, B, H, W, R, R, 0, Hk, Wk)
-            sr = self.E(B * Nk, C, dtype=f32)
-            ops.mm(pat, wsr, sr, bias=self.P(p + ".attn.sr.bias"))
+            # few output tiles (B*Nk x C) but K = R*R*C up to 4096: split-K with fp32 atomics (bias added by slice 0)
+            sr = self.Z(B * Nk, C)
+            ops.mm(pat, wsr, sr, bias=self.P(p + ".attn.sr.bias"), accumulate=True)
             srn = self.E(B * Nk, C)
             c.ms, c.rs = (self.E(B * Nk, dtype=f32), self.E(B * Nk, dtype=f32)) if save else (None, None)
             ops.layernorm_fwd(sr, self.P(p + ".attn.norm.weight"), self.P(p + ".attn.norm.bias"), 1e-5, srn, c.ms, c.rs)

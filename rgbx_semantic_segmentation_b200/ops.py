@@ -47,6 +47,7 @@ def launch_count():
 # Optional per-launch profiling (bench.py / debugging): when PROFILE is a list every C-ABI call is bracketed
 # by CUDA events on the launching stream and (name, start, stop, flops, bytes) is appended.
 PROFILE = None
+PROFILE_SHAPES = bool(int(__import__('os').environ.get('CMX_PROFILE_SHAPES', '0')))
 
 
 def _call(name, *args, tag=None, flops=0, nbytes=0):
@@ -110,7 +111,10 @@ def gemm_raw(A, B, C, M, N, K, lda, ldb, ldc, *, a_off=0, b_off=0, c_off=0, tran
     which = "tc" if int(_lib.load().cmx_gemm_which(ctypes.byref(g))) == 2 else ("fb_batched" if nb > 1 else "fb")
     kind = "wgrad" if trans_a else ("dgrad" if trans_b and nb == 1 else "fwd")
     cbytes = C.element_size() * (2 if (accumulate or split_k > 1) else 1)
-    _call("cmx_gemm", ctypes.byref(g), _stream(), tag="gemm_%s_%s" % (which, kind), flops=2 * M * N * K * nb,
+    tag = "gemm_%s_%s" % (which, kind)
+    if PROFILE_SHAPES:
+        tag += "_%dx%dx%d" % (M, N, K) + ("_b%d" % nb if nb > 1 else "") + ("_s%d" % split_k if split_k > 1 else "")
+    _call("cmx_gemm", ctypes.byref(g), _stream(), tag=tag, flops=2 * M * N * K * nb,
           nbytes=nb * (2 * (M * K + N * K) + cbytes * M * N + (residual.element_size() * M * N if residual is not None else 0)))
     return C
 

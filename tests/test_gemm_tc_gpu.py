@@ -70,8 +70,8 @@ def test_tc_forward_epilogue(M, N, K):
     outb = torch.empty(M, N, device=DEV, dtype=bf)
     ops.mm(a, b, outb, bias=bias, act=ops.ACT_RELU, impl=2)
     _check(outb, torch.relu(base + bias), K, "relu bf16 out")
-    ops.mm(a, b, outb, bias=bias, act=ops.ACT_GELU, residual=res.to(bf), impl=2)
-    _check(outb, torch.nn.functional.gelu(base + bias) + res.to(bf).float(), K, "gelu + bf16 residual")
+    ops.mm(a, b, outb, bias=bias, act=ops.ACT_RELU, residual=res.to(bf), impl=2)
+    _check(outb, torch.relu(base + bias) + res.to(bf).float(), K, "relu + bf16 residual")
     # strided output / strided A (views into wider buffers)
     wide = torch.zeros(M, 2 * N, device=DEV, dtype=bf)
     ops.mm(a, b, wide[:, N:], impl=2)
