@@ -6,6 +6,7 @@
 #include "common.cuh"
 #include "../../include/cmx_b200.h"
 #include <atomic>
+#include <stdlib.h>
 extern std::atomic<long long> g_cmx_launches;
 
 template <int ACT>
@@ -110,10 +111,172 @@ __global__ void __launch_bounds__(DW_CG* DW_PY) dwconv_fwd_kernel(const bf16* __
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Shared-memory tiled variant (the production path).  CTA = 8 rows x 32 pixels x 64 channels:
+//   * the (8+2) x (32+2) halo tile of x is staged once in shared memory with 16-byte loads ([pixel][64 ch] bf16,
+//     128 B per pixel => a warp reading one pixel's channel pairs is one conflict-free 128 B wavefront);
+//   * thread (row r = tid/32, channel pair cp = tid%32) walks its row with a 3x3 register window (3 LDS.32 per
+//     pixel), so per-channel weights, bias and - in the backward mode - the dW[9]/db accumulators are plain
+//     registers (20 floats) instead of per-pixel arrays;
+//   * global traffic per warp access is one full 128-byte line (64 channels x bf16), for dy reads and y/du writes.
+// MODE 0: y = act(conv(x)+b)   MODE 1: du = dy * act'(conv(x)+b), dW/db reduced   MODE 2: dx = conv_flipped(du)
+// ------------------------------------------------------------------------------------------------
+constexpr int DT_TH = 8, DT_TW = 32, DT_CH = 64;
+
+template <int ACT, int MODE>
+__global__ void __launch_bounds__(256) dwconv_tiled_kernel(const bf16* __restrict__ x, long ldx, const float* __restrict__ w,
+                                                           const float* __restrict__ bias, const bf16* __restrict__ dy, long lddy,
+                                                           bf16* __restrict__ out, long ldo, float* __restrict__ dw,
+                                                           float* __restrict__ db, int B, int H, int W, int C, int tiles_x,
+                                                           int tiles_y, long ntiles) {
+  __shared__ __align__(16) bf16 tile[(DT_TH + 2) * (DT_TW + 2) * DT_CH];  // 43.5 KB
+  __shared__ float sred[20][DT_CH];
+  const int tid = threadIdx.x;
+  const int r = tid >> 5, cp = tid & 31;
+  const int cbase = blockIdx.x * DT_CH;
+  const int c = cbase + cp * 2;
+  const bool c_ok = c < C;  // C is even
+  float wt[2][9], bs[2] = {0.f, 0.f};
+#pragma unroll
+  for (int t = 0; t < 9; t++) {
+    const int tt = MODE == 2 ? 8 - t : t;
+    wt[0][t] = c_ok ? w[(long)c * 9 + tt] : 0.f;
+    wt[1][t] = c_ok ? w[(long)(c + 1) * 9 + tt] : 0.f;
+  }
+  if (MODE != 2 && bias && c_ok) { bs[0] = bias[c]; bs[1] = bias[c + 1]; }
+  float gw[2][9], gb[2] = {0.f, 0.f};
+#pragma unroll
+  for (int t = 0; t < 9; t++) { gw[0][t] = 0.f; gw[1][t] = 0.f; }
+
+  for (long tl = blockIdx.y; tl < ntiles; tl += gridDim.y) {
+    const int tx = (int)(tl % tiles_x);
+    const int ty = (int)((tl / tiles_x) % tiles_y);
+    const int b = (int)(tl / ((long)tiles_x * tiles_y));
+    const int x0 = tx * DT_TW, y0 = ty * DT_TH;
+    __syncthreads();  // previous tile fully consumed
+    // ---- stage the halo tile: (TH+2)*(TW+2) pixels x 8 chunks of 8 channels
+    for (int i = tid; i < (DT_TH + 2) * (DT_TW + 2) * (DT_CH / 8); i += 256) {
+      const int ch8 = i & 7;
+      const int pix = i >> 3;
+      const int px = pix % (DT_TW + 2), py = pix / (DT_TW + 2);
+      const int gy = y0 + py - 1, gx = x0 + px - 1;
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (gy >= 0 && gy < H && gx >= 0 && gx < W && cbase + ch8 * 8 < C)
+        v = *reinterpret_cast<const uint4*>(x + ((long)(b * H + gy) * W + gx) * ldx + cbase + ch8 * 8);
+      *reinterpret_cast<uint4*>(&tile[(long)pix * DT_CH + ch8 * 8]) = v;
+    }
+    __syncthreads();
+    const int gy = y0 + r;
+    if (gy < H && c_ok) {
+      // 3x3 window: win[row][col] for the 2 channels; columns slide
+      float2 win[3][3];
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+          const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&tile[((r + i) * (DT_TW + 2) + j) * DT_CH + cp * 2]);
+          win[i][j + 1] = __bfloat1622float2(h2);
+        }
+      }
+      const long rowbase = (long)(b * H + gy) * W;
+#pragma unroll 4
+      for (int px = 0; px < DT_TW; px++) {
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+          win[i][0] = win[i][1];
+          win[i][1] = win[i][2];
+          const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&tile[((r + i) * (DT_TW + 2) + px + 2) * DT_CH + cp * 2]);
+          win[i][2] = __bfloat1622float2(h2);
+        }
+        const int gx = x0 + px;
+        if (gx >= W) break;
+        float a0 = bs[0], a1 = bs[1];
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+          for (int j = 0; j < 3; j++) {
+            a0 = fmaf(wt[0][i * 3 + j], win[i][j].x, a0);
+            a1 = fmaf(wt[1][i * 3 + j], win[i][j].y, a1);
+          }
+        if (MODE == 1) {
+          const __nv_bfloat162 g2 = *reinterpret_cast<const __nv_bfloat162*>(dy + (rowbase + gx) * lddy + c);
+          float2 g = __bfloat1622float2(g2);
+          g.x *= act_grad_f<ACT>(a0);
+          g.y *= act_grad_f<ACT>(a1);
+          gb[0] += g.x;
+          gb[1] += g.y;
+#pragma unroll
+          for (int i = 0; i < 3; i++)
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+              gw[0][i * 3 + j] = fmaf(g.x, win[i][j].x, gw[0][i * 3 + j]);
+              gw[1][i * 3 + j] = fmaf(g.y, win[i][j].y, gw[1][i * 3 + j]);
+            }
+          *reinterpret_cast<__nv_bfloat162*>(out + (rowbase + gx) * ldo + c) = __floats2bfloat162_rn(g.x, g.y);
+        } else {
+          *reinterpret_cast<__nv_bfloat162*>(out + (rowbase + gx) * ldo + c) =
+              __floats2bfloat162_rn(act_f<ACT>(a0), act_f<ACT>(a1));
+        }
+      }
+    }
+  }
+  if (MODE == 1) {
+    // reduce the 8 row-threads of every channel pair, then one atomicAdd per (channel, tap) per CTA
+    __syncthreads();
+    for (int i = tid; i < 20 * DT_CH; i += 256) (&sred[0][0])[i] = 0.f;
+    __syncthreads();
+    if (c_ok) {
+#pragma unroll
+      for (int t = 0; t < 9; t++) {
+        atomicAdd(&sred[t][cp * 2], gw[0][t]);
+        atomicAdd(&sred[t][cp * 2 + 1], gw[1][t]);
+      }
+      atomicAdd(&sred[9][cp * 2], gb[0]);
+      atomicAdd(&sred[9][cp * 2 + 1], gb[1]);
+    }
+    __syncthreads();
+    for (int i = tid; i < 10 * DT_CH; i += 256) {
+      const int t = i / DT_CH, l = i % DT_CH;
+      const int cc = cbase + l;
+      if (cc < C) {
+        if (t < 9) atomicAdd(dw + (long)cc * 9 + t, sred[t][l]);
+        else if (db) atomicAdd(db + cc, sred[9][l]);
+      }
+    }
+  }
+}
+
+template <int ACT, int MODE>
+static void dwconv_tiled_launch(const void* x, long ldx, const float* w, const float* bias, const void* dy, long lddy, void* out,
+                                long ldo, float* dw, float* db, int B, int H, int W, int C, cudaStream_t st) {
+  const int tiles_x = (W + DT_TW - 1) / DT_TW, tiles_y = (H + DT_TH - 1) / DT_TH;
+  const long ntiles = (long)B * tiles_x * tiles_y;
+  const int gx = (C + DT_CH - 1) / DT_CH;
+  long gy = ntiles;
+  const long cap = MODE == 1 ? (148L * 5 + gx - 1) / gx : (148L * 20 + gx - 1) / gx;  // backward: few CTAs => few atomics
+  if (gy > cap) gy = cap;
+  dim3 grid(gx, (unsigned)gy);
+  dwconv_tiled_kernel<ACT, MODE><<<grid, 256, 0, st>>>((const bf16*)x, ldx, w, bias, (const bf16*)dy, lddy, (bf16*)out, ldo, dw, db, B,
+                                                       H, W, C, tiles_x, tiles_y, ntiles);
+}
+
 CMX_API int cmx_dwconv3x3_fwd(const void* x, int64_t ldx, const float* w, const float* bias, int act, int flip, void* y,
                               int64_t ldy, int B, int H, int W, int C, void* stream) {
   CMX_REQUIRE(C % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0, "dwconv3x3: C and ld must be multiples of 8 (C=%d)", C);
   cudaStream_t st = (cudaStream_t)stream;
+  if ((long)B * H * W == 0) return 0;
+  if (getenv("CMX_DWCONV_LEGACY") == nullptr) {
+    if (flip) {
+      CMX_REQUIRE(act == CMX_ACT_NONE, "dwconv3x3: flip is for the data gradient (no activation)");
+      dwconv_tiled_launch<CMX_ACT_NONE, 2>(x, ldx, w, nullptr, nullptr, 0, y, ldy, nullptr, nullptr, B, H, W, C, st);
+    } else if (act == CMX_ACT_GELU) dwconv_tiled_launch<CMX_ACT_GELU, 0>(x, ldx, w, bias, nullptr, 0, y, ldy, nullptr, nullptr, B, H, W, C, st);
+    else if (act == CMX_ACT_RELU) dwconv_tiled_launch<CMX_ACT_RELU, 0>(x, ldx, w, bias, nullptr, 0, y, ldy, nullptr, nullptr, B, H, W, C, st);
+    else dwconv_tiled_launch<CMX_ACT_NONE, 0>(x, ldx, w, bias, nullptr, 0, y, ldy, nullptr, nullptr, B, H, W, C, st);
+    g_cmx_launches++;
+    CMX_CHECK_LAUNCH("dwconv3x3_tiled");
+    return 0;
+  }
   constexpr int TW = 4;
   const long nstrips = (long)B * H * ((W + TW - 1) / TW);
   if (nstrips == 0) return 0;
@@ -250,6 +413,15 @@ CMX_API int cmx_dwconv3x3_bwd_pre(const void* x, int64_t ldx, const float* w, co
                                   void* stream) {
   CMX_REQUIRE(C % 4 == 0 && ldx % 4 == 0 && lddy % 4 == 0 && lddu % 4 == 0, "dwconv3x3_bwd_pre: C/ld %% 4");
   cudaStream_t st = (cudaStream_t)stream;
+  if ((long)B * H * W == 0) return 0;
+  if (getenv("CMX_DWCONV_LEGACY") == nullptr && C % 8 == 0 && ldx % 8 == 0) {
+    if (act == CMX_ACT_GELU) dwconv_tiled_launch<CMX_ACT_GELU, 1>(x, ldx, w, bias, dy, lddy, du, lddu, dw, db, B, H, W, C, st);
+    else if (act == CMX_ACT_RELU) dwconv_tiled_launch<CMX_ACT_RELU, 1>(x, ldx, w, bias, dy, lddy, du, lddu, dw, db, B, H, W, C, st);
+    else dwconv_tiled_launch<CMX_ACT_NONE, 1>(x, ldx, w, bias, dy, lddy, du, lddu, dw, db, B, H, W, C, st);
+    g_cmx_launches++;
+    CMX_CHECK_LAUNCH("dwconv3x3_bwd_pre_tiled");
+    return 0;
+  }
   const long nstrips = (long)B * H * ((W + 1) / 2);
   if (nstrips == 0) return 0;
   const int gx = cdiv(C, DW_CG * 4);

@@ -225,8 +225,67 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, lo
     atomicAdd(out + c, t);
   }
 }
+// 8 columns (one 16-byte load) per thread; block = NG column groups x (256/NG) row lanes
+__global__ void __launch_bounds__(256) colsum_vec8_kernel(const bf16* __restrict__ x, long ldx, float* __restrict__ out, long M, int N,
+                                                          int ng, int rows_per_cta) {
+  __shared__ float sacc[256][9];
+  const int tid = threadIdx.x;
+  const int cg = tid % ng, rl = tid / ng, nrl = 256 / ng;
+  const int c = (blockIdx.x * ng + cg) * 8;
+  const long r0 = (long)blockIdx.y * rows_per_cta;
+  long r1 = r0 + rows_per_cta;
+  if (r1 > M) r1 = M;
+  float a[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) a[i] = 0.f;
+  if (c < N && rl < nrl) {
+    long r = r0 + rl;
+    for (; r + 3 * nrl < r1; r += 4 * nrl) {  // 4 independent 16-byte loads in flight
+      float v0[8], v1[8], v2[8], v3[8];
+      load8(x + r * ldx + c, v0);
+      load8(x + (r + nrl) * ldx + c, v1);
+      load8(x + (r + 2 * nrl) * ldx + c, v2);
+      load8(x + (r + 3 * nrl) * ldx + c, v3);
+#pragma unroll
+      for (int i = 0; i < 8; i++) a[i] += (v0[i] + v1[i]) + (v2[i] + v3[i]);
+    }
+    for (; r < r1; r += nrl) {
+      float v[8];
+      load8(x + r * ldx + c, v);
+#pragma unroll
+      for (int i = 0; i < 8; i++) a[i] += v[i];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; i++) sacc[tid][i] = a[i];
+  __syncthreads();
+  if (tid < ng * 8) {
+    const int g = tid >> 3, i = tid & 7;
+    const int cc = (blockIdx.x * ng + g) * 8 + i;
+    if (cc < N) {
+      float t = 0.f;
+      for (int l = 0; l < nrl; l++) t += sacc[l * ng + g][i];
+      atomicAdd(out + cc, t);
+    }
+  }
+}
+
 CMX_API int cmx_colsum(const void* x, int x_dtype, int64_t ldx, float* out, int64_t M, int N, void* stream) {
   if (M == 0 || N == 0) return 0;
+  if (x_dtype == CMX_BF16 && N % 8 == 0 && ldx % 8 == 0 && (((uintptr_t)x) & 15) == 0) {
+    int ng = N / 8;
+    if (ng > 32) ng = 32;
+    while (256 % ng) ng--;  // ng must divide 256 (N/8 in {4,8,16,20->16,32,...})
+    const int nrl = 256 / ng;
+    long want_ctas = 148L * 4;
+    const int gx = cdiv(N / 8, ng);
+    long rows_per_cta = (M * gx + want_ctas - 1) / want_ctas;
+    rows_per_cta = (rows_per_cta + nrl - 1) / nrl * nrl;
+    if (rows_per_cta < 4L * nrl) rows_per_cta = 4L * nrl;
+    dim3 grid(gx, cdiv(M, rows_per_cta));
+    colsum_vec8_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, ldx, out, M, N, ng, (int)rows_per_cta);
+    LAUNCH_DONE("colsum_vec8");
+  }
   const int rows_per_cta = 512;
   dim3 grid(cdiv(N, 32), cdiv(M, rows_per_cta));
   CMX_REQUIRE(grid.y <= 65535, "colsum: M too large");

@@ -62,12 +62,223 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const TX* __restrict__ x, l
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm v2 (production path for C % 8 == 0): G lanes cooperate on one row, 32/G rows per warp, every lane
+// owns J vectors of 8 consecutive channels (16-byte bf16 / 32-byte fp32 accesses).  C = 64 -> 4 rows per warp,
+// C = 128 -> 2, C >= 160 -> 1; reductions are xor-shuffles inside the G-lane group.
+// ------------------------------------------------------------------------------------------------
+template <int G>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <typename TX, typename TY, int G, int J>
+__global__ void __launch_bounds__(256) ln_fwd_v2_kernel(const TX* __restrict__ x, long ldx, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, float eps, TY* __restrict__ y, long ldy,
+                                                        float* __restrict__ mean, float* __restrict__ rstd, long M, int C) {
+  constexpr int RPW = 32 / G;
+  const int lane = threadIdx.x & 31;
+  const int lg = lane % G;
+  const long row = ((long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW + lane / G;
+  const bool ok = row < M;
+  float v[J][8];
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < J; j++) {
+    const int c = 8 * (lg + G * j);
+#pragma unroll
+    for (int i = 0; i < 8; i++) v[j][i] = 0.f;
+    if (ok && c < C) {
+      load8(x + row * ldx + c, v[j]);
+#pragma unroll
+      for (int i = 0; i < 8; i++) s += v[j][i];
+    }
+  }
+  const float mu = group_sum<G>(s) / (float)C;
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < J; j++) {
+    const int c = 8 * (lg + G * j);
+    if (c < C) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        const float d = v[j][i] - mu;
+        q += d * d;
+      }
+    }
+  }
+  const float rs = rsqrtf(group_sum<G>(q) / (float)C + eps);
+  if (!ok) return;
+  if (lg == 0) {
+    if (mean) mean[row] = mu;
+    if (rstd) rstd[row] = rs;
+  }
+#pragma unroll
+  for (int j = 0; j < J; j++) {
+    const int c = 8 * (lg + G * j);
+    if (c < C) {
+      float g[8], b[8], o[8];
+      load8(gamma + c, g);
+      load8(beta + c, b);
+#pragma unroll
+      for (int i = 0; i < 8; i++) o[i] = (v[j][i] - mu) * rs * g[i] + b[i];
+      store8(y + row * ldy + c, o);
+    }
+  }
+}
+
+template <typename TDY, typename TX, typename TDX, int G, int J>
+__global__ void __launch_bounds__(256) ln_bwd_v2_kernel(const TDY* __restrict__ dy, long lddy, const bf16* __restrict__ dy2, long lddy2,
+                                                        const TX* __restrict__ x, long ldx, const float* __restrict__ mean,
+                                                        const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                                        const float* __restrict__ dres, long lddres, TDX* __restrict__ dx, long lddx,
+                                                        bf16* __restrict__ dxbf, long lddxbf, const float* __restrict__ scale,
+                                                        int rows_per_sample, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                        long M, int C) {
+  constexpr int RPW = 32 / G;
+  __shared__ float sh_g[512];
+  __shared__ float sh_b[512];
+  const int lane = threadIdx.x & 31;
+  const int lg = lane % G;
+  const int warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  for (int i = threadIdx.x; i < C; i += blockDim.x) { sh_g[i] = 0.f; sh_b[i] = 0.f; }
+  __syncthreads();
+  float ag[J][8], ab[J][8], gm[J][8];
+#pragma unroll
+  for (int j = 0; j < J; j++) {
+    const int c = 8 * (lg + G * j);
+#pragma unroll
+    for (int i = 0; i < 8; i++) { ag[j][i] = 0.f; ab[j][i] = 0.f; gm[j][i] = 0.f; }
+    if (c < C) load8(gamma + c, gm[j]);
+  }
+  const long nslots = (M + RPW - 1) / RPW;  // warp-iterations
+  for (long slot = (long)blockIdx.x * nwarp + warp; slot < nslots; slot += (long)gridDim.x * nwarp) {
+    const long row = slot * RPW + lane / G;
+    const bool ok = row < M;
+    const float mu = ok ? mean[row] : 0.f, rs = ok ? rstd[row] : 0.f;
+    float g[J][8], xh[J][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < J; j++) {
+      const int c = 8 * (lg + G * j);
+#pragma unroll
+      for (int i = 0; i < 8; i++) { g[j][i] = 0.f; xh[j][i] = 0.f; }
+      if (ok && c < C) {
+        float d[8], xv[8];
+        load8(dy + row * lddy + c, d);
+        if (dy2) {
+          float d2[8];
+          load8(dy2 + row * lddy2 + c, d2);
+#pragma unroll
+          for (int i = 0; i < 8; i++) d[i] += d2[i];
+        }
+        load8(x + row * ldx + c, xv);
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          xh[j][i] = (xv[i] - mu) * rs;
+          ag[j][i] += d[i] * xh[j][i];
+          ab[j][i] += d[i];
+          g[j][i] = d[i] * gm[j][i];
+          s1 += g[j][i];
+          s2 += g[j][i] * xh[j][i];
+        }
+      }
+    }
+    s1 = group_sum<G>(s1) / (float)C;
+    s2 = group_sum<G>(s2) / (float)C;
+    if (!ok) continue;
+    const float sc = (scale && dxbf) ? scale[(int)(row / rows_per_sample)] : 1.f;
+#pragma unroll
+    for (int j = 0; j < J; j++) {
+      const int c = 8 * (lg + G * j);
+      if (c < C) {
+        float o[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) o[i] = rs * (g[j][i] - s1 - xh[j][i] * s2);
+        if (dres) {
+          float r[8];
+          load8(dres + row * lddres + c, r);
+#pragma unroll
+          for (int i = 0; i < 8; i++) o[i] += r[i];
+        }
+        if (dx) store8(dx + row * lddx + c, o);
+        if (dxbf) {
+#pragma unroll
+          for (int i = 0; i < 8; i++) o[i] *= sc;
+          store8(dxbf + row * lddxbf + c, o);
+        }
+      }
+    }
+  }
+  if (dgamma) {
+#pragma unroll
+    for (int j = 0; j < J; j++) {
+      const int c = 8 * (lg + G * j);
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        float a = ag[j][i], b = ab[j][i];
+#pragma unroll
+        for (int o = G; o < 32; o <<= 1) {  // fold the 32/G row groups of this warp
+          a += __shfl_xor_sync(0xffffffffu, a, o);
+          b += __shfl_xor_sync(0xffffffffu, b, o);
+        }
+        if (lane < G && c < C) {
+          atomicAdd(&sh_g[c + i], a);
+          atomicAdd(&sh_b[c + i], b);
+        }
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < C; i += blockDim.x) {
+      atomicAdd(dgamma + i, sh_g[i]);
+      atomicAdd(dbeta + i, sh_b[i]);
+    }
+  }
+}
+
+static inline void ln_gj(int C, int& G, int& J) {
+  const int nvec = C / 8;
+  G = nvec <= 4 ? 4 : nvec <= 8 ? 8 : nvec <= 16 ? 16 : 32;
+  J = (nvec + G - 1) / G;
+}
+#define LN_GJ_DISPATCH(MACRO)                     \
+  do {                                            \
+    if (G == 4) MACRO(4, 1);                      \
+    else if (G == 8) MACRO(8, 1);                 \
+    else if (G == 16) MACRO(16, 1);               \
+    else if (J == 1) MACRO(32, 1);                \
+    else MACRO(32, 2);                            \
+  } while (0)
+
 CMX_API int cmx_layernorm_fwd(const void* x, int x_dtype, int64_t ldx, const float* gamma, const float* beta, float eps,
                               void* y, int y_dtype, int64_t ldy, float* mean, float* rstd, int64_t M, int C, void* stream) {
   CMX_REQUIRE(C % 4 == 0 && C <= 4 * 32 * LN_MAXJ && C > 0, "layernorm: C=%d unsupported", C);
   CMX_REQUIRE(ldx % 4 == 0 && ldy % 4 == 0, "layernorm: ld must be a multiple of 4");
   if (M == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
+  if (C % 8 == 0 && C <= 512 && ldx % 8 == 0 && ldy % 8 == 0) {
+    int G, J;
+    ln_gj(C, G, J);
+    const int rpb = 8 * (32 / G);
+    dim3 grid2(cdiv(M, rpb));
+#define LN_F2T(TX, TY, Gv, Jv) ln_fwd_v2_kernel<TX, TY, Gv, Jv><<<grid2, 256, 0, st>>>((const TX*)x, ldx, gamma, beta, eps, (TY*)y, ldy, mean, rstd, M, C)
+#define LN_F2(Gv, Jv)                                                                 \
+  do {                                                                                \
+    if (x_dtype == CMX_F32 && y_dtype == CMX_BF16) LN_F2T(float, bf16, Gv, Jv);       \
+    else if (x_dtype == CMX_F32 && y_dtype == CMX_F32) LN_F2T(float, float, Gv, Jv);  \
+    else if (x_dtype == CMX_BF16 && y_dtype == CMX_BF16) LN_F2T(bf16, bf16, Gv, Jv);  \
+    else LN_F2T(bf16, float, Gv, Jv);                                                 \
+  } while (0)
+    LN_GJ_DISPATCH(LN_F2);
+#undef LN_F2
+#undef LN_F2T
+    g_cmx_launches++;
+    CMX_CHECK_LAUNCH("ln_fwd_v2");
+    return 0;
+  }
   const int wpb = 8;
   dim3 grid(cdiv(M, wpb));
 #define LN_F(TX, TY) ln_fwd_kernel<TX, TY><<<grid, wpb * 32, 0, st>>>((const TX*)x, ldx, gamma, beta, eps, (TY*)y, ldy, mean, rstd, M, C)
@@ -191,9 +402,39 @@ CMX_API int cmx_layernorm_bwd(const void* dy, int dy_dtype, int64_t lddy, const 
   CMX_REQUIRE((dgamma == nullptr) == (dbeta == nullptr), "layernorm_bwd: dgamma/dbeta must come together");
   if (M == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
+  if (rows_per_sample <= 0) rows_per_sample = 1;
+  if (C % 8 == 0 && C <= 512 && lddy % 8 == 0 && ldx % 8 == 0 && (!dy2 || lddy2 % 8 == 0) && (!dres || lddres % 8 == 0) &&
+      (!dx || lddx % 8 == 0) && (!dx_bf || lddxbf % 8 == 0)) {
+    int G, J;
+    ln_gj(C, G, J);
+    int grid2 = cdiv(M, 8 * (32 / G));
+    if (grid2 > 148 * 6) grid2 = 148 * 6;
+#define LN_B2T(TDY, TX, TDX, Gv, Jv)                                                                                            \
+  ln_bwd_v2_kernel<TDY, TX, TDX, Gv, Jv><<<grid2, 256, 0, st>>>((const TDY*)dy, lddy, (const bf16*)dy2, lddy2, (const TX*)x, ldx, \
+                                                                mean, rstd, gamma, dres, lddres, (TDX*)dx, lddx, (bf16*)dx_bf,    \
+                                                                lddxbf, scale, rows_per_sample, dgamma, dbeta, M, C)
+#define LN_B2(Gv, Jv)                                                            \
+  do {                                                                           \
+    switch (dy_dtype * 4 + x_dtype * 2 + dx_dtype) {                             \
+      case 0: LN_B2T(bf16, bf16, bf16, Gv, Jv); break;                           \
+      case 1: LN_B2T(bf16, bf16, float, Gv, Jv); break;                          \
+      case 2: LN_B2T(bf16, float, bf16, Gv, Jv); break;                          \
+      case 3: LN_B2T(bf16, float, float, Gv, Jv); break;                         \
+      case 4: LN_B2T(float, bf16, bf16, Gv, Jv); break;                          \
+      case 5: LN_B2T(float, bf16, float, Gv, Jv); break;                         \
+      case 6: LN_B2T(float, float, bf16, Gv, Jv); break;                         \
+      default: LN_B2T(float, float, float, Gv, Jv); break;                       \
+    }                                                                            \
+  } while (0)
+    LN_GJ_DISPATCH(LN_B2);
+#undef LN_B2
+#undef LN_B2T
+    g_cmx_launches++;
+    CMX_CHECK_LAUNCH("ln_bwd_v2");
+    return 0;
+  }
   int grid = cdiv(M, 8);
   if (grid > 148 * 8) grid = 148 * 8;
-  if (rows_per_sample <= 0) rows_per_sample = 1;
 #define LN_B(TDY, TX, TDX)                                                                                              \
   ln_bwd_kernel<TDY, TX, TDX><<<grid, 256, 0, st>>>((const TDY*)dy, lddy, (const bf16*)dy2, lddy2, (const TX*)x, ldx, mean, \
                                                     rstd, gamma, dres, lddres, (TDX*)dx, lddx, (bf16*)dx_bf, lddxbf, scale, \
