@@ -181,7 +181,11 @@ def main_ours(args):
     model = EncoderDecoder(Cfg, nn.CrossEntropyLoss(reduction="mean", ignore_index=255), nn.BatchNorm2d).to(dev).train()
     net = model
     if world > 1:
-        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=False)
+        if os.environ.get("CMX_BENCH_TORCH_DDP", "0") == "1":   # the reference's wrapper also works (slower: per-param copies)
+            net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local])
+        else:
+            from rgbx_semantic_segmentation_b200.parallel import FlatDataParallel
+            net = FlatDataParallel(model)
     opt = torch.optim.AdamW(group_weight(model, 6e-5), lr=6e-5, betas=(0.9, 0.999), weight_decay=0.01, fused=True)
     B = PER_GPU_BATCH
     rgb, x, gt = synth_batch(B, 1 + rank, device=dev)
@@ -290,6 +294,8 @@ def main_ours(args):
                 "config": {"workload": "CMX MiT-B2 RGB-T MFNet shape (480x640, 9 classes) bf16 training, batch 8 per GPU "
                                        "(BASELINE.json configs[1]; configs[2] for N>1)",
                            "global_batch": gb, "per_gpu_batch": B, "parallelism": "dp%d" % world, "optimizer": "AdamW(fused)",
+                           "grad_allreduce": None if world == 1 else ("torch DDP buckets" if os.environ.get("CMX_BENCH_TORCH_DDP", "0") == "1"
+                                                                      else "one NCCL all-reduce over the flat fp32 gradient buffer"),
                            "cuda_graph": bool(model.use_cuda_graph),
                            "l2": "per-step working set (>5 GB of activations at batch 8) exceeds the 126 MB L2; no explicit flush"},
                 "e2e": {"value": gb * args.steps / (ms2 * 1e-3), "unit": UNIT, "ms_per_step": ms2 / args.steps,

@@ -44,7 +44,10 @@ class _CMXStep(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_out):
         eng = ctx.model._engine
-        flat = eng.flat_g * grad_out  # one elementwise pass over the flat gradient buffer (fresh tensor each step)
+        from ..parallel import allreduce_flat_grads_
+        world = allreduce_flat_grads_(ctx.model, eng.flat_g)   # no-op unless wrapped in FlatDataParallel
+        # one elementwise pass over the flat gradient buffer (fresh tensor each step)
+        flat = eng.flat_g * (grad_out / world if world > 1 else grad_out)
         grads = tuple(flat[eng.off[n]:eng.off[n] + eng._numel(n)].view(eng.shape[n]) for n in eng.names)
         return (None, None, None, None) + grads
 
@@ -80,6 +83,7 @@ class EncoderDecoder(nn.Module):
             self.init_weights(cfg, pretrained=_cfg_get(cfg, "pretrained_model", None))
         self._engine = None
         self._graphs = {}
+        self._flat_dp = None
         self.use_cuda_graph = os.environ.get("CMX_CUDA_GRAPH", "1") != "0"
 
     # ---- reference API ---------------------------------------------------------------------------
@@ -178,4 +182,5 @@ class EncoderDecoder(nn.Module):
         st = self.__dict__.copy()
         st["_engine"] = None
         st["_graphs"] = {}
+        st["_flat_dp"] = None
         return st

@@ -121,7 +121,19 @@ def fake_step(rgb, x, label):            # stands in for the CUDA step: rank-dep
     eng.flat_g.fill_(float(rank + 1))
     return torch.tensor(float(rank))
 m._run_step = fake_step
-ddp = torch.nn.parallel.DistributedDataParallel(m)
+mode = sys.argv[2]
+if mode == "ddp":
+    ddp = torch.nn.parallel.DistributedDataParallel(m)
+else:
+    from rgbx_semantic_segmentation_b200.parallel import FlatDataParallel
+    with torch.no_grad():
+        for p in m.parameters():
+            p.add_(float(rank))                      # desynchronise: the wrapper must broadcast rank 0's values
+    ddp = FlatDataParallel(m)
+    ref = [p.detach().clone() for p in m.parameters()]
+    for p in ref:
+        dist.broadcast(p, src=0)
+    assert all(torch.equal(a, b) for a, b in zip(ref, m.parameters())), "parameters not broadcast from rank 0"
 z = torch.zeros(1, 3, 32, 32)
 loss = ddp(z, z, torch.zeros(1, 32, 32, dtype=torch.long))
 loss.backward()
@@ -132,11 +144,12 @@ dist.destroy_process_group()
 '''
 
 
-def test_ddp_gradient_handoff_world2_gloo(tmp_path):
+@pytest.mark.parametrize("mode,port", [("ddp", "29533"), ("flat", "29534")])
+def test_ddp_gradient_handoff_world2_gloo(tmp_path, mode, port):
     script = tmp_path / "w.py"
     script.write_text(DDP_WORKER)
-    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29533", WORLD_SIZE="2")
-    procs = [subprocess.Popen([sys.executable, str(script), ROOT], env=dict(env, RANK=str(r), LOCAL_RANK=str(r)),
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=port, WORLD_SIZE="2")
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, mode], env=dict(env, RANK=str(r), LOCAL_RANK=str(r)),
                               stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(2)]
     outs = [p.communicate(timeout=240)[0] for p in procs]
     for r, o in enumerate(outs):
