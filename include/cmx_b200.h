@@ -138,6 +138,14 @@ int cmx_relu_bwd(void* dy, int64_t lddy, const void* y, int64_t ldy, int64_t M, 
 /* out = a*x + b*y elementwise on fp32 flat buffers (grad scaling) */
 int cmx_axpby_f32(float a, const float* x, float b, const float* y, float* out, int64_t n, void* stream);
 
+/* ---- fused spatial-reduction self-attention forward (dual_segformer.py:127-134), head_dim 64, Nkv <= 320 ----------
+ * O[b,n,h,:] = softmax_k(scale * q[b,n,h,:].k[b,k,h,:]) v[b,k,h,:]   — flash style (scores only in tensor memory).
+ * q [B*N, ldq] (head h at columns h*64..), kv [B*Nk, ldkv] (K at h*64, V at heads*64 + h*64), o [B*N, ldo], all bf16.
+ * p_out (optional, bf16 [B*heads*N, ldp]): the normalised probabilities, written by TMA for the backward pass.
+ * lse (optional, fp32 [B*heads*N]): natural-log row normaliser. */
+int cmx_attn_fwd(const void* q, int64_t ldq, const void* kv, int64_t ldkv, void* o, int64_t ldo, void* p_out, int64_t ldp,
+                 float* lse, int B, int N, int Nk, int heads, float scale, void* stream);
+
 /* ---- softmax ---------------------------------------------------------------------------------- */
 /* row softmax of fp32 S [rows, n] (ld) -> bf16 P  (dual_segformer.py:131) and its backward
  * dS = scale * P .* (dP - rowsum(P.*dP)) -> bf16 */

@@ -1,0 +1,323 @@
+// Fused spatial-reduction self-attention forward (dual_segformer.py:127-134): O = softmax(scale * Q K^T) V per
+// (sample, head), head_dim = 64, Nkv <= 320 (Nkv = 300 at every MiT stage for 480x640 inputs), flash style:
+// the N x Nkv score matrix lives only in tensor memory / registers.
+//
+//   * persistent CTAs walk contiguous ranges of 128-row Q tiles ordered by (sample, head): the K and V tiles of a
+//     (sample, head) are TMA-loaded once ([320 x 64] bf16 each, SWIZZLE_128B, rows >= Nkv zero-filled) and stay in
+//     shared memory; Q tiles stream through a 2-deep TMA ring.
+//   * warp 1 issues tcgen05.mma: S[128 x 320] = Q K^T (two N=160 UMMAs x 4 k-steps, fp32 in TMEM columns 0..319) and
+//     O[128 x 64] = P V (A = P from shared memory, B = V viewed MN-major - the same bytes as the K-major tile -
+//     TMEM columns 320..383).  The QK^T of tile i+1 is issued before the epilogue of tile i finishes.
+//   * warps 2-9 (two threads per row, 160 columns each): pass 1 row max from TMEM, pass 2 exp2 + row sum, P (bf16) to
+//     shared memory in the K-major SWIZZLE_128B layout, normalised in place, which then feeds BOTH the P V MMA and -
+//     for training - a TMA bulk store of the probabilities the backward pass consumes.
+#include "tc_common.cuh"
+#include "../../include/cmx_b200.h"
+#include <atomic>
+#include <string.h>
+extern std::atomic<long long> g_cmx_launches;
+
+constexpr int AT_BM = 128;      // query rows per tile
+constexpr int AT_D = 64;        // head dim
+constexpr int AT_NK = 320;      // padded key count (5 k-blocks of 64)
+constexpr int AT_THREADS = 64 + 256;
+constexpr uint32_t AT_K_OFF = 0, AT_V_OFF = 40960, AT_Q_OFF = 81920, AT_P_OFF = 114688, AT_RED_OFF = 196608;
+constexpr uint32_t AT_BAR_OFF = AT_RED_OFF + 2048;
+constexpr uint32_t AT_SMEM = AT_BAR_OFF + 256 + 1024;  // + alignment slack
+constexpr uint32_t AT_O_COL = 320;
+
+struct AttnArgs {
+  bf16* o;
+  long ldo;
+  float* lse;
+  int B, N, Nk, heads;
+  int tiles_per_bh;
+  long total_tiles;
+  float scale_log2e;
+  int store_p;
+};
+
+__global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ,
+                                                                 const __grid_constant__ CUtensorMap tmKV,
+                                                                 const __grid_constant__ CUtensorMap tmP, AttnArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sb = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sK = sb + AT_K_OFF, sV = sb + AT_V_OFF, sQ = sb + AT_Q_OFF, sP = sb + AT_P_OFF, sRed = sb + AT_RED_OFF;
+  const uint32_t bar = sb + AT_BAR_OFF;
+  const uint32_t kv_full = bar, kv_empty = bar + 8, q_full = bar + 16 /*[2]*/, q_empty = bar + 32 /*[2]*/, s_full = bar + 48,
+                 p_full = bar + 56, o_full = bar + 64, o_empty = bar + 72, tmem_slot = bar + 80;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // contiguous tile range of this CTA
+  const long per = (a.total_tiles + gridDim.x - 1) / gridDim.x;
+  const long t_begin = (long)blockIdx.x * per;
+  long t_end = t_begin + per;
+  if (t_end > a.total_tiles) t_end = a.total_tiles;
+  const int ntiles = t_end > t_begin ? (int)(t_end - t_begin) : 0;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmQ)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmKV)) : "memory");
+    mbar_init(kv_full, 1);
+    mbar_init(kv_empty, 1);
+    for (int i = 0; i < 2; i++) { mbar_init(q_full + 8 * i, 1); mbar_init(q_empty + 8 * i, 1); }
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 1);
+    mbar_init(o_full, 1);
+    mbar_init(o_empty, 8);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    // ============================ TMA producer ============================
+    if (lane == 0) {
+      int group = -1;
+      long cur_bh = -1;
+      for (int i = 0; i < ntiles; i++) {
+        const long t = t_begin + i;
+        const long bh = t / a.tiles_per_bh;
+        const int q0 = (int)(t % a.tiles_per_bh) * AT_BM;
+        const int b = (int)(bh / a.heads), h = (int)(bh % a.heads);
+        if (bh != cur_bh) {
+          cur_bh = bh;
+          group++;
+          if (group > 0) mbar_wait(kv_empty, (uint32_t)(group - 1) & 1u);  // all MMAs that read the old K/V retired
+          mbar_expect_tx(kv_full, 2 * AT_NK * 128);
+          const int C = a.heads * AT_D;
+          tma_load_3d(sK, &tmKV, kv_full, h * AT_D, 0, b);
+          tma_load_3d(sK + 160 * 128, &tmKV, kv_full, h * AT_D, 160, b);
+          tma_load_3d(sV, &tmKV, kv_full, C + h * AT_D, 0, b);
+          tma_load_3d(sV + 160 * 128, &tmKV, kv_full, C + h * AT_D, 160, b);
+        }
+        const int s = i & 1;
+        mbar_wait(q_empty + 8 * s, (((uint32_t)i >> 1) & 1u) ^ 1u);
+        mbar_expect_tx(q_full + 8 * s, AT_BM * 128);
+        tma_load_3d(sQ + s * 16384, &tmQ, q_full + 8 * s, h * AT_D, q0, b);
+      }
+    }
+  } else if (warp == 1) {
+    // ============================ MMA issuer ============================
+    if (lane == 0 && ntiles > 0) {
+      constexpr uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(160 >> 3) << 17) | ((uint32_t)(AT_BM >> 4) << 24);
+      constexpr uint32_t idesc_o = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(AT_D >> 3) << 17) |
+                                   ((uint32_t)(AT_BM >> 4) << 24);
+      auto issue_qk = [&](int i) {  // S = Q_i K^T
+        const uint32_t q = sQ + (i & 1) * 16384;
+#pragma unroll
+        for (int hf = 0; hf < 2; hf++)
+#pragma unroll
+          for (int ks = 0; ks < 4; ks++)
+            tc_mma_bf16(tmem + hf * 160, umma_desc(q + ks * 32, 16, 1024), umma_desc(sK + hf * 160 * 128 + ks * 32, 16, 1024),
+                        idesc_s, ks > 0 ? 1u : 0u);
+        tc_commit(s_full);
+        tc_commit(q_empty + 8 * (i & 1));
+      };
+      int group = 0;
+      mbar_wait(kv_full, 0);
+      mbar_wait(q_full, 0);
+      tc_fence_after();
+      issue_qk(0);
+      for (int i = 0; i < ntiles; i++) {
+        const long bh = (t_begin + i) / a.tiles_per_bh;
+        const bool last_of_group = (i + 1 == ntiles) || ((t_begin + i + 1) / a.tiles_per_bh != bh);
+        mbar_wait(p_full, (uint32_t)i & 1u);                        // P_i is in shared memory, S is free again
+        if (i > 0) mbar_wait(o_empty, (uint32_t)(i - 1) & 1u);      // epilogue of tile i-1 has drained O
+        tc_fence_after();
+#pragma unroll
+        for (int kb = 0; kb < AT_NK / 64; kb++)
+#pragma unroll
+          for (int ks = 0; ks < 4; ks++)
+            tc_mma_bf16(tmem + AT_O_COL, umma_desc(sP + kb * 16384 + ks * 32, 16, 1024),
+                        umma_desc(sV + kb * 8192 + ks * 2048, 8192, 1024), idesc_o, (kb > 0 || ks > 0) ? 1u : 0u);
+        tc_commit(o_full);
+        if (last_of_group) tc_commit(kv_empty);
+        if (i + 1 < ntiles) {
+          if (last_of_group) {
+            group++;
+            mbar_wait(kv_full, (uint32_t)group & 1u);
+          }
+          mbar_wait(q_full + 8 * ((i + 1) & 1), ((uint32_t)(i + 1) >> 1) & 1u);
+          tc_fence_after();
+          issue_qk(i + 1);
+        }
+      }
+    }
+  } else {
+    // ============================ softmax + epilogue (warps 2..9) ============================
+    const int q = warp & 3;               // TMEM lane quarter
+    const int half = (warp - 2) >> 2;     // column half: [0,160) or [160,320)
+    const int r = q * 32 + lane;          // row inside the tile
+    const uint32_t t_row = tmem + ((uint32_t)(q * 32) << 16);
+    const float sl2 = a.scale_log2e;
+    for (int i = 0; i < ntiles; i++) {
+      const long t = t_begin + i;
+      const long bh = t / a.tiles_per_bh;
+      const int q0 = (int)(t % a.tiles_per_bh) * AT_BM;
+      const int b = (int)(bh / a.heads), h = (int)(bh % a.heads);
+      // the TMA store of the previous tile's P must have finished READING shared memory before P is overwritten
+      if (a.store_p && threadIdx.x == 64) tma_store_wait_read<0>();
+      mbar_wait(s_full, (uint32_t)i & 1u);
+      tc_fence_after();
+      // ---- pass 1: row maximum over this thread's 160 columns
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < 5; c++) {
+        uint32_t v[32];
+        tmem_ld32(t_row + (uint32_t)(half * 160 + c * 32), v);
+        tmem_wait_ld();
+        const int col0 = half * 160 + c * 32;
+#pragma unroll
+        for (int j = 0; j < 32; j++)
+          if (col0 + j < a.Nk) mx = fmaxf(mx, __uint_as_float(v[j]));
+      }
+      asm volatile("st.shared.f32 [%0], %1;" ::"r"(sRed + 4u * (half * 128 + r)), "f"(mx) : "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");   // also orders thread 64's wait_group.read before any P write
+      float m0, m1;
+      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(m0) : "r"(sRed + 4u * r));
+      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(m1) : "r"(sRed + 4u * (128 + r)));
+      const float m = fmaxf(m0, m1);
+      const float moff = m * sl2;
+      // ---- pass 2: p = 2^(s*scale*log2e - m*scale*log2e), row sum, bf16 P -> shared memory (K-major, SWIZZLE_128B)
+      float sum = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < 5; c++) {
+        uint32_t v[32];
+        tmem_ld32(t_row + (uint32_t)(half * 160 + c * 32), v);
+        tmem_wait_ld();
+        const int col0 = half * 160 + c * 32;
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            const int cc = col0 + g * 8 + 2 * j;
+            float p0 = cc < a.Nk ? exp2f(fmaf(__uint_as_float(v[g * 8 + 2 * j]), sl2, -moff)) : 0.f;
+            float p1 = cc + 1 < a.Nk ? exp2f(fmaf(__uint_as_float(v[g * 8 + 2 * j + 1]), sl2, -moff)) : 0.f;
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(p0, p1);
+            const float2 back = __bfloat1622float2(h2);
+            sum += back.x + back.y;   // the sum of what the P V MMA will actually see
+            pk[j] = *reinterpret_cast<uint32_t*>(&h2);
+          }
+          const int col = col0 + g * 8;
+          const uint32_t kb = (uint32_t)col >> 6, ch = ((uint32_t)col & 63u) >> 3;
+          st_shared_v4(sP + kb * 16384 + (uint32_t)r * 128 + ((ch ^ ((uint32_t)r & 7u)) << 4), pk[0], pk[1], pk[2], pk[3]);
+        }
+      }
+      asm volatile("st.shared.f32 [%0], %1;" ::"r"(sRed + 1024u + 4u * (half * 128 + r)), "f"(sum) : "memory");
+      asm volatile("bar.sync 2, 256;" ::: "memory");
+      float l0, l1;
+      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(l0) : "r"(sRed + 1024u + 4u * r));
+      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(l1) : "r"(sRed + 1024u + 4u * (128 + r)));
+      const float inv = 1.f / (l0 + l1);
+      // ---- normalise this thread's 160 probabilities in place (so that the stored P and the P V product agree)
+#pragma unroll 1
+      for (int cg = 0; cg < 20; cg++) {
+        const int col = half * 160 + cg * 8;
+        const uint32_t kb = (uint32_t)col >> 6, ch = ((uint32_t)col & 63u) >> 3;
+        const uint32_t ad = sP + kb * 16384 + (uint32_t)r * 128 + ((ch ^ ((uint32_t)r & 7u)) << 4);
+        uint32_t w[4];
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(ad));
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          float2 f = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&w[j]));
+          __nv_bfloat162 h2 = __floats2bfloat162_rn(f.x * inv, f.y * inv);
+          w[j] = *reinterpret_cast<uint32_t*>(&h2);
+        }
+        st_shared_v4(ad, w[0], w[1], w[2], w[3]);
+      }
+      if (a.lse && half == 0 && q0 + r < a.N)
+        a.lse[bh * a.N + q0 + r] = m * (sl2 * 0.69314718055994531f) + logf(l0 + l1);
+      tc_fence_before();
+      fence_async_smem();
+      asm volatile("bar.sync 3, 256;" ::: "memory");      // P complete (generic-proxy writes fenced for the async proxy)
+      if (threadIdx.x == 64) {
+        mbar_arrive(p_full);
+        if (a.store_p) {
+#pragma unroll
+          for (int kb = 0; kb < AT_NK / 64; kb++)
+            if (kb * 64 < a.Nk)
+              asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                           ::"l"(reinterpret_cast<uint64_t>(&tmP)), "r"(sP + kb * 16384), "r"(kb * 64), "r"(q0), "r"((int)bh)
+                           : "memory");
+          tma_store_commit();
+        }
+      }
+      // ---- epilogue: O (already normalised) TMEM -> bf16 -> global; each thread of the pair takes 32 of the 64 columns
+      mbar_wait(o_full, (uint32_t)i & 1u);
+      tc_fence_after();
+      {
+        uint32_t v[32];
+        tmem_ld32(t_row + AT_O_COL + (uint32_t)(half * 32), v);
+        tmem_wait_ld();
+        if (q0 + r < a.N) {
+          bf16* dst = a.o + ((long)b * a.N + q0 + r) * a.ldo + h * AT_D + half * 32;
+#pragma unroll
+          for (int g = 0; g < 4; g++) {
+            float f[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) f[j] = __uint_as_float(v[g * 8 + j]);
+            store8(dst + g * 8, f);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(o_empty);
+    }
+    if (a.store_p && threadIdx.x == 64) tma_store_wait_all();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+}
+
+CMX_API int cmx_attn_fwd(const void* q, int64_t ldq, const void* kv, int64_t ldkv, void* o, int64_t ldo, void* p_out, int64_t ldp,
+                         float* lse, int B, int N, int Nk, int heads, float scale, void* stream) {
+  CMX_REQUIRE(q && kv && o, "attn_fwd: null operand");
+  CMX_REQUIRE(Nk >= 1 && Nk <= AT_NK, "attn_fwd: Nkv=%d unsupported (max %d) - use the unfused path", Nk, AT_NK);
+  CMX_REQUIRE(ldq % 8 == 0 && ldkv % 8 == 0 && ldo % 8 == 0 && (!p_out || ldp % 8 == 0), "attn_fwd: leading dims must be multiples of 8");
+  CMX_REQUIRE(ldq >= heads * AT_D && ldkv >= 2 * heads * AT_D, "attn_fwd: head_dim must be 64");
+  CMX_REQUIRE(((uintptr_t)q & 15) == 0 && ((uintptr_t)kv & 15) == 0 && ((uintptr_t)o & 15) == 0 && ((uintptr_t)p_out & 15) == 0,
+              "attn_fwd: pointers must be 16-byte aligned");
+  if (B == 0 || N == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  CUtensorMap tmQ, tmKV, tmP;
+  memset(&tmP, 0, sizeof(tmP));
+  int rc = cmx_make_map3(&tmQ, q, (uint64_t)heads * AT_D, (uint64_t)N, (uint64_t)B, (uint64_t)ldq, (uint64_t)N * ldq, AT_D, AT_BM);
+  if (rc) return rc;
+  rc = cmx_make_map3(&tmKV, kv, (uint64_t)2 * heads * AT_D, (uint64_t)Nk, (uint64_t)B, (uint64_t)ldkv, (uint64_t)Nk * ldkv, AT_D, 160);
+  if (rc) return rc;
+  if (p_out) {
+    rc = cmx_make_map3(&tmP, p_out, (uint64_t)Nk, (uint64_t)N, (uint64_t)B * heads, (uint64_t)ldp, (uint64_t)N * ldp, 64, AT_BM);
+    if (rc) return rc;
+  }
+  AttnArgs a;
+  a.o = (bf16*)o; a.ldo = ldo; a.lse = lse; a.B = B; a.N = N; a.Nk = Nk; a.heads = heads;
+  a.tiles_per_bh = cdiv(N, AT_BM);
+  a.total_tiles = (long)a.tiles_per_bh * B * heads;
+  a.scale_log2e = scale * 1.4426950408889634f;
+  a.store_p = p_out ? 1 : 0;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AT_SMEM);
+    if (e != cudaSuccess) CMX_FAIL((int)e, "cudaFuncSetAttribute(attn): %s", cudaGetErrorString(e));
+    attr_done = true;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const long grid = a.total_tiles < sms ? a.total_tiles : sms;
+  attn_fwd_kernel<<<(unsigned)grid, AT_THREADS, AT_SMEM, st>>>(tmQ, tmKV, tmP, a);
+  g_cmx_launches++;
+  CMX_CHECK_LAUNCH("attn_fwd_kernel");
+  return 0;
+}

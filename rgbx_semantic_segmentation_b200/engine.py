@@ -18,6 +18,8 @@ Design notes
   * linear_fuse (1x1 conv over the 2048-channel concat) is applied per stage at native resolution —
     bilinear interpolation commutes with a per-pixel linear map — so the concat tensor never exists.
 """
+import os
+
 import torch
 
 from . import ops
@@ -51,6 +53,7 @@ class Engine:
         self.forced_dropout = None   # test hook: tensor[B, E]
         self.stochastic = True       # DropPath / Dropout2d active in training mode
         self.trace = None            # debug hook: dict filled with fp32 copies of intermediate activations
+        self.fused_attention = os.environ.get("CMX_FUSED_ATTENTION", "1") != "0"
         self.poison = None           # debug hook: list of (tensor, allocation site) when NaN-poisoning is on
 
     # ------------------------------------------------------------------------------------------
@@ -272,17 +275,22 @@ class Engine:
             kv_in = xn1
         kv = self.E(B * Nk, 2 * C)
         ops.mm(kv_in, self.W(p + ".attn.kv.weight"), kv, bias=self.P(p + ".attn.kv.bias"))
-        # S = scale * Q K^T  (fp32, transient), P = softmax(S), O = P V
         Np = (Nk + 7) // 8 * 8   # leading dimension of the score / probability rows (16-byte rows for TMA)
-        S = self.E(B * heads * N, Np, dtype=f32)[:, :Nk]
-        ops.gemm_raw(q, kv, S, N, Nk, d, C, 2 * C, Np, batch=(B, heads), sA=(N * C, d), sB=(Nk * 2 * C, d),
-                     sC=(heads * N * Np, N * Np), alpha=scale)
-        Pm = self.E(B * heads * N, Np)[:, :Nk]
-        ops.softmax_rows_fwd(S, Pm)
-        del S
         O = self.E(M, C)
-        ops.gemm_raw(Pm, kv, O, N, d, Nk, Np, 2 * C, C, b_off=C, trans_b=True, batch=(B, heads),
-                     sA=(heads * N * Np, N * Np), sB=(Nk * 2 * C, d), sC=(N * C, d))
+        if d == 64 and Nk <= ops.ATTN_MAX_NK and self.fused_attention:
+            # flash-style fused kernel: scores stay in tensor memory; P is only written (by TMA) when backward needs it
+            Pm = self.E(B * heads * N, Np)[:, :Nk] if save else None
+            ops.attn_fwd(q, kv, O, B, N, Nk, heads, scale, p_out=Pm)
+        else:
+            # unfused path (head_dim != 64 or Nkv > 320): S = scale * Q K^T (fp32, transient), P = softmax(S), O = P V
+            S = self.E(B * heads * N, Np, dtype=f32)[:, :Nk]
+            ops.gemm_raw(q, kv, S, N, Nk, d, C, 2 * C, Np, batch=(B, heads), sA=(N * C, d), sB=(Nk * 2 * C, d),
+                         sC=(heads * N * Np, N * Np), alpha=scale)
+            Pm = self.E(B * heads * N, Np)[:, :Nk]
+            ops.softmax_rows_fwd(S, Pm)
+            del S
+            ops.gemm_raw(Pm, kv, O, N, d, Nk, Np, 2 * C, C, b_off=C, trans_b=True, batch=(B, heads),
+                         sA=(heads * N * Np, N * Np), sB=(Nk * 2 * C, d), sC=(N * C, d))
         x1 = self.E(M, C, dtype=f32)
         ops.mm(O, self.W(p + ".attn.proj.weight"), x1, bias=self.P(p + ".attn.proj.bias"), residual=x,
                row_scale=None if dp is None else dp[0], rows_per_sample=N)

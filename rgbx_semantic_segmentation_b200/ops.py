@@ -288,6 +288,21 @@ def axpby(a, x, b, y, out):
 
 
 # ------------------------------------------------------------------------------------------------
+# fused attention forward
+# ------------------------------------------------------------------------------------------------
+ATTN_MAX_NK = 320
+
+
+def attn_fwd(q, kv, o, B, N, Nk, heads, scale, p_out=None, lse=None):
+    """q [B*N, C], kv [B*Nk, 2C], o [B*N, C] (bf16, head_dim 64); p_out: bf16 view [B*heads*N, Nk] with padded ld"""
+    _cuda(q, kv, o)
+    _call("cmx_attn_fwd", q.data_ptr(), _ld(q), kv.data_ptr(), _ld(kv), o.data_ptr(), _ld(o), _p(p_out),
+          _ld(p_out) if p_out is not None else 0, _p(lse), B, N, Nk, heads, scale, _stream(),
+          flops=4 * B * heads * N * Nk * 64, nbytes=_nb(q, kv, o) + (B * heads * N * Nk * 2 if p_out is not None else 0))
+    return o
+
+
+# ------------------------------------------------------------------------------------------------
 # softmax
 # ------------------------------------------------------------------------------------------------
 def softmax_rows_fwd(s, p):

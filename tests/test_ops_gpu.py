@@ -400,3 +400,36 @@ def test_confusion_bit_exact():
         h_ref, lab, cor = metric_ref.hist_info(n_cl, p_ref, gt)
         assert np.array_equal(pred8.cpu().numpy(), p_ref)
         assert np.array_equal(hist.cpu().numpy(), h_ref) and stats.tolist() == [lab, cor]
+
+
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,N,Nk,heads", [(2, 1200, 300, 5), (1, 333, 77, 1), (2, 4800, 300, 2), (1, 19200, 300, 1), (3, 300, 300, 8),
+                                          (1, 130, 4, 2)])
+def test_fused_attention_forward(B, N, Nk, heads):
+    torch.manual_seed(11)
+    d = 64
+    C = heads * d
+    q = rnd(B * N, C, dtype=bf)
+    kv = rnd(B * Nk, 2 * C, dtype=bf)
+    o = torch.full((B * N, C), 7.0, device=DEV, dtype=bf)
+    Np = (Nk + 7) // 8 * 8
+    pbuf = torch.full((B * heads * N, Np), 3.0, device=DEV, dtype=bf)
+    lse = torch.empty(B * heads * N, device=DEV)
+    scale = d ** -0.5
+    ops.attn_fwd(q, kv, o, B, N, Nk, heads, scale, p_out=pbuf[:, :Nk], lse=lse)
+    qf = q.float().view(B, N, heads, d).permute(0, 2, 1, 3)
+    kf = kv.float().view(B, Nk, 2, heads, d)[:, :, 0].permute(0, 2, 1, 3)
+    vf = kv.float().view(B, Nk, 2, heads, d)[:, :, 1].permute(0, 2, 1, 3)
+    s = (qf @ kf.transpose(-1, -2)) * scale
+    pr = torch.softmax(s, -1)
+    ref = (pr @ vf).permute(0, 2, 1, 3).reshape(B * N, C)
+    close(pbuf[:, :Nk].reshape(B, heads, N, Nk), pr, 2e-2, 2e-3, "attention probabilities")
+    if Np > Nk:   # pad columns are either untouched or zero (TMA bulk stores clip the inner dimension at 16-byte granularity)
+        pad = pbuf[:, Nk:].float()
+        assert bool(((pad == 3.0) | (pad == 0.0)).all())
+    close(o, ref, 2e-2, 2e-2, "attention output")
+    close(lse.view(B, heads, N), torch.logsumexp(s, -1), 1e-3, 1e-3, "lse")
+    # inference mode (no P, no LSE) gives the same output
+    o2 = torch.empty_like(o)
+    ops.attn_fwd(q, kv, o2, B, N, Nk, heads, scale)
+    assert torch.equal(o, o2)
