@@ -146,6 +146,12 @@ int cmx_axpby_f32(float a, const float* x, float b, const float* y, float* out, 
 int cmx_attn_fwd(const void* q, int64_t ldq, const void* kv, int64_t ldkv, void* o, int64_t ldo, void* p_out, int64_t ldp,
                  float* lse, int B, int N, int Nk, int heads, float scale, void* stream);
 
+/* fused attention backward core: dP = dO V^T (tensor memory only), dS = scale * P .* (dP - rowsum(P .* dP)) -> ds_out
+ * (bf16, same layout as p; consumed by the split-K dK = dS^T Q GEMM), dQ = dS K -> dq [B*N, lddq].  dV = P^T dO and
+ * dK stay ordinary batched split-K cmx_gemm calls (they contract over all query tokens). */
+int cmx_attn_bwd(const void* d_o, int64_t lddo, const void* kv, int64_t ldkv, const void* p, int64_t ldp, void* ds_out,
+                 int64_t ldds, void* dq, int64_t lddq, int B, int N, int Nk, int heads, float scale, void* stream);
+
 /* ---- softmax ---------------------------------------------------------------------------------- */
 /* row softmax of fp32 S [rows, n] (ld) -> bf16 P  (dual_segformer.py:131) and its backward
  * dS = scale * P .* (dP - rowsum(P.*dP)) -> bf16 */

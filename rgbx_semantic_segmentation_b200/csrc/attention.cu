@@ -34,18 +34,24 @@ struct AttnArgs {
   int tiles_per_bh;
   long total_tiles;
   float scale_log2e;
+  float scale;
   int store_p;
 };
 
-__global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ,
-                                                                 const __grid_constant__ CUtensorMap tmKV,
-                                                                 const __grid_constant__ CUtensorMap tmP, AttnArgs a) {
+// MODE 0: forward.  MODE 1: backward core - the same pipeline with  A1 = dO, B1 = V  (dP = dO V^T in TMEM),
+// P TMA-loaded into the staging tile, dS = scale * P .* (dP - rowsum(P .* dP)) computed in place and TMA-stored
+// (it feeds the split-K dK = dS^T Q GEMM), and the second MMA  dQ = dS K  (B2 = K viewed MN-major).
+template <int MODE>
+__global__ void __launch_bounds__(AT_THREADS, 1) attn_kernel(const __grid_constant__ CUtensorMap tmQ,
+                                                             const __grid_constant__ CUtensorMap tmKV,
+                                                             const __grid_constant__ CUtensorMap tmP,
+                                                             const __grid_constant__ CUtensorMap tmDS, AttnArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sb = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sK = sb + AT_K_OFF, sV = sb + AT_V_OFF, sQ = sb + AT_Q_OFF, sP = sb + AT_P_OFF, sRed = sb + AT_RED_OFF;
   const uint32_t bar = sb + AT_BAR_OFF;
   const uint32_t kv_full = bar, kv_empty = bar + 8, q_full = bar + 16 /*[2]*/, q_empty = bar + 32 /*[2]*/, s_full = bar + 48,
-                 p_full = bar + 56, o_full = bar + 64, o_empty = bar + 72, tmem_slot = bar + 80;
+                 p_full = bar + 56, o_full = bar + 64, o_empty = bar + 72, p_in = bar + 80, tmem_slot = bar + 88;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   // contiguous tile range of this CTA
@@ -65,6 +71,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_kernel(const __grid_co
     mbar_init(p_full, 1);
     mbar_init(o_full, 1);
     mbar_init(o_empty, 8);
+    mbar_init(p_in, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -93,10 +100,14 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_kernel(const __grid_co
           if (group > 0) mbar_wait(kv_empty, (uint32_t)(group - 1) & 1u);  // all MMAs that read the old K/V retired
           mbar_expect_tx(kv_full, 2 * AT_NK * 128);
           const int C = a.heads * AT_D;
-          tma_load_3d(sK, &tmKV, kv_full, h * AT_D, 0, b);
-          tma_load_3d(sK + 160 * 128, &tmKV, kv_full, h * AT_D, 160, b);
-          tma_load_3d(sV, &tmKV, kv_full, C + h * AT_D, 0, b);
-          tma_load_3d(sV + 160 * 128, &tmKV, kv_full, C + h * AT_D, 160, b);
+          // first-MMA operand (K-major view) goes to slot sK, second-MMA operand (MN-major view) to slot sV:
+          // forward (K, V); backward (V, K)
+          const int c1 = MODE == 0 ? h * AT_D : C + h * AT_D;
+          const int c2 = MODE == 0 ? C + h * AT_D : h * AT_D;
+          tma_load_3d(sK, &tmKV, kv_full, c1, 0, b);
+          tma_load_3d(sK + 160 * 128, &tmKV, kv_full, c1, 160, b);
+          tma_load_3d(sV, &tmKV, kv_full, c2, 0, b);
+          tma_load_3d(sV + 160 * 128, &tmKV, kv_full, c2, 160, b);
         }
         const int s = i & 1;
         mbar_wait(q_empty + 8 * s, (((uint32_t)i >> 1) & 1u) ^ 1u);
@@ -132,8 +143,9 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_kernel(const __grid_co
         mbar_wait(p_full, (uint32_t)i & 1u);                        // P_i is in shared memory, S is free again
         if (i > 0) mbar_wait(o_empty, (uint32_t)(i - 1) & 1u);      // epilogue of tile i-1 has drained O
         tc_fence_after();
-#pragma unroll
-        for (int kb = 0; kb < AT_NK / 64; kb++)
+        const int nkb_mma = MODE == 0 ? AT_NK / 64 : (a.Nk + 63) / 64;  // backward: only the k-blocks that were loaded
+#pragma unroll 1
+        for (int kb = 0; kb < nkb_mma; kb++)
 #pragma unroll
           for (int ks = 0; ks < 4; ks++)
             tc_mma_bf16(tmem + AT_O_COL, umma_desc(sP + kb * 16384 + ks * 32, 16, 1024),
@@ -163,92 +175,171 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_kernel(const __grid_co
       const long bh = t / a.tiles_per_bh;
       const int q0 = (int)(t % a.tiles_per_bh) * AT_BM;
       const int b = (int)(bh / a.heads), h = (int)(bh % a.heads);
-      // the TMA store of the previous tile's P must have finished READING shared memory before P is overwritten
-      if (a.store_p && threadIdx.x == 64) tma_store_wait_read<0>();
-      mbar_wait(s_full, (uint32_t)i & 1u);
-      tc_fence_after();
-      // ---- pass 1: row maximum over this thread's 160 columns
-      float mx = -INFINITY;
+      if (MODE == 1) {
+        const int nkb = (a.Nk + 63) / 64;
+        if (threadIdx.x == 64) {
+          tma_store_wait_read<0>();                       // dS store of the previous tile has read the staging tile
+          mbar_expect_tx(p_in, (uint32_t)nkb * 16384u);
+          for (int kb = 0; kb < nkb; kb++) tma_load_3d(sP + kb * 16384, &tmP, p_in, kb * 64, q0, (int)bh);
+        }
+        mbar_wait(s_full, (uint32_t)i & 1u);               // dP = dO V^T is in tensor memory
+        tc_fence_after();
+        mbar_wait(p_in, (uint32_t)i & 1u);                 // P tile landed
+        const int ncg = ((a.Nk + 7) >> 3);                 // 8-column groups that can hold non-zero probabilities
+        // ---- pass 1: D = rowsum(P .* dP) over this thread's 160 columns
+        float dot = 0.f;
 #pragma unroll 1
-      for (int c = 0; c < 5; c++) {
-        uint32_t v[32];
-        tmem_ld32(t_row + (uint32_t)(half * 160 + c * 32), v);
-        tmem_wait_ld();
-        const int col0 = half * 160 + c * 32;
+        for (int c = 0; c < 5; c++) {
+          const int col0 = half * 160 + c * 32;
+          if ((col0 >> 3) >= ncg) break;
+          uint32_t v[32];
+          tmem_ld32(t_row + (uint32_t)col0, v);
+          tmem_wait_ld();
 #pragma unroll
-        for (int j = 0; j < 32; j++)
-          if (col0 + j < a.Nk) mx = fmaxf(mx, __uint_as_float(v[j]));
-      }
-      asm volatile("st.shared.f32 [%0], %1;" ::"r"(sRed + 4u * (half * 128 + r)), "f"(mx) : "memory");
-      asm volatile("bar.sync 1, 256;" ::: "memory");   // also orders thread 64's wait_group.read before any P write
-      float m0, m1;
-      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(m0) : "r"(sRed + 4u * r));
-      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(m1) : "r"(sRed + 4u * (128 + r)));
-      const float m = fmaxf(m0, m1);
-      const float moff = m * sl2;
-      // ---- pass 2: p = 2^(s*scale*log2e - m*scale*log2e), row sum, bf16 P -> shared memory (K-major, SWIZZLE_128B)
-      float sum = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < 5; c++) {
-        uint32_t v[32];
-        tmem_ld32(t_row + (uint32_t)(half * 160 + c * 32), v);
-        tmem_wait_ld();
-        const int col0 = half * 160 + c * 32;
+          for (int g = 0; g < 4; g++) {
+            const int col = col0 + g * 8;
+            const uint32_t kb = (uint32_t)col >> 6, ch = ((uint32_t)col & 63u) >> 3;
+            uint32_t w[4];
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3])
+                         : "r"(sP + kb * 16384 + (uint32_t)r * 128 + ((ch ^ ((uint32_t)r & 7u)) << 4)));
 #pragma unroll
-        for (int g = 0; g < 4; g++) {
-          uint32_t pk[4];
-#pragma unroll
-          for (int j = 0; j < 4; j++) {
-            const int cc = col0 + g * 8 + 2 * j;
-            float p0 = cc < a.Nk ? exp2f(fmaf(__uint_as_float(v[g * 8 + 2 * j]), sl2, -moff)) : 0.f;
-            float p1 = cc + 1 < a.Nk ? exp2f(fmaf(__uint_as_float(v[g * 8 + 2 * j + 1]), sl2, -moff)) : 0.f;
-            __nv_bfloat162 h2 = __floats2bfloat162_rn(p0, p1);
-            const float2 back = __bfloat1622float2(h2);
-            sum += back.x + back.y;   // the sum of what the P V MMA will actually see
-            pk[j] = *reinterpret_cast<uint32_t*>(&h2);
+            for (int j = 0; j < 4; j++) {
+              const float2 pf = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&w[j]));
+              dot = fmaf(pf.x, __uint_as_float(v[g * 8 + 2 * j]), dot);
+              dot = fmaf(pf.y, __uint_as_float(v[g * 8 + 2 * j + 1]), dot);
+            }
           }
-          const int col = col0 + g * 8;
-          const uint32_t kb = (uint32_t)col >> 6, ch = ((uint32_t)col & 63u) >> 3;
-          st_shared_v4(sP + kb * 16384 + (uint32_t)r * 128 + ((ch ^ ((uint32_t)r & 7u)) << 4), pk[0], pk[1], pk[2], pk[3]);
         }
-      }
-      asm volatile("st.shared.f32 [%0], %1;" ::"r"(sRed + 1024u + 4u * (half * 128 + r)), "f"(sum) : "memory");
-      asm volatile("bar.sync 2, 256;" ::: "memory");
-      float l0, l1;
-      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(l0) : "r"(sRed + 1024u + 4u * r));
-      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(l1) : "r"(sRed + 1024u + 4u * (128 + r)));
-      const float inv = 1.f / (l0 + l1);
-      // ---- normalise this thread's 160 probabilities in place (so that the stored P and the P V product agree)
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(sRed + 4u * (half * 128 + r)), "f"(dot) : "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        float d0, d1;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(d0) : "r"(sRed + 4u * r));
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(d1) : "r"(sRed + 4u * (128 + r)));
+        const float D = d0 + d1;
+        // ---- pass 2: dS = scale * P .* (dP - D), written in place of P
 #pragma unroll 1
-      for (int cg = 0; cg < 20; cg++) {
-        const int col = half * 160 + cg * 8;
-        const uint32_t kb = (uint32_t)col >> 6, ch = ((uint32_t)col & 63u) >> 3;
-        const uint32_t ad = sP + kb * 16384 + (uint32_t)r * 128 + ((ch ^ ((uint32_t)r & 7u)) << 4);
-        uint32_t w[4];
-        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(ad));
+        for (int c = 0; c < 5; c++) {
+          const int col0 = half * 160 + c * 32;
+          if ((col0 >> 3) >= ncg) break;
+          uint32_t v[32];
+          tmem_ld32(t_row + (uint32_t)col0, v);
+          tmem_wait_ld();
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-          float2 f = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&w[j]));
-          __nv_bfloat162 h2 = __floats2bfloat162_rn(f.x * inv, f.y * inv);
-          w[j] = *reinterpret_cast<uint32_t*>(&h2);
+          for (int g = 0; g < 4; g++) {
+            const int col = col0 + g * 8;
+            const uint32_t kb = (uint32_t)col >> 6, ch = ((uint32_t)col & 63u) >> 3;
+            const uint32_t ad = sP + kb * 16384 + (uint32_t)r * 128 + ((ch ^ ((uint32_t)r & 7u)) << 4);
+            uint32_t w[4];
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(ad));
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+              const float2 pf = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&w[j]));
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(a.scale * pf.x * (__uint_as_float(v[g * 8 + 2 * j]) - D),
+                                                        a.scale * pf.y * (__uint_as_float(v[g * 8 + 2 * j + 1]) - D));
+              w[j] = *reinterpret_cast<uint32_t*>(&h2);
+            }
+            st_shared_v4(ad, w[0], w[1], w[2], w[3]);
+          }
         }
-        st_shared_v4(ad, w[0], w[1], w[2], w[3]);
-      }
-      if (a.lse && half == 0 && q0 + r < a.N)
-        a.lse[bh * a.N + q0 + r] = m * (sl2 * 0.69314718055994531f) + logf(l0 + l1);
-      tc_fence_before();
-      fence_async_smem();
-      asm volatile("bar.sync 3, 256;" ::: "memory");      // P complete (generic-proxy writes fenced for the async proxy)
-      if (threadIdx.x == 64) {
-        mbar_arrive(p_full);
-        if (a.store_p) {
-#pragma unroll
-          for (int kb = 0; kb < AT_NK / 64; kb++)
-            if (kb * 64 < a.Nk)
-              asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
-                           ::"l"(reinterpret_cast<uint64_t>(&tmP)), "r"(sP + kb * 16384), "r"(kb * 64), "r"(q0), "r"((int)bh)
-                           : "memory");
+        tc_fence_before();
+        fence_async_smem();
+        asm volatile("bar.sync 3, 256;" ::: "memory");
+        if (threadIdx.x == 64) {
+          mbar_arrive(p_full);
+          for (int kb = 0; kb < nkb; kb++)
+            asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                         ::"l"(reinterpret_cast<uint64_t>(&tmDS)), "r"(sP + kb * 16384), "r"(kb * 64), "r"(q0), "r"((int)bh)
+                         : "memory");
           tma_store_commit();
+        }
+      } else {
+        // the TMA store of the previous tile's P must have finished READING shared memory before P is overwritten
+        if (a.store_p && threadIdx.x == 64) tma_store_wait_read<0>();
+        mbar_wait(s_full, (uint32_t)i & 1u);
+        tc_fence_after();
+        // ---- pass 1: row maximum over this thread's 160 columns
+        float mx = -INFINITY;
+  #pragma unroll 1
+        for (int c = 0; c < 5; c++) {
+          uint32_t v[32];
+          tmem_ld32(t_row + (uint32_t)(half * 160 + c * 32), v);
+          tmem_wait_ld();
+          const int col0 = half * 160 + c * 32;
+  #pragma unroll
+          for (int j = 0; j < 32; j++)
+            if (col0 + j < a.Nk) mx = fmaxf(mx, __uint_as_float(v[j]));
+        }
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(sRed + 4u * (half * 128 + r)), "f"(mx) : "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");   // also orders thread 64's wait_group.read before any P write
+        float m0, m1;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(m0) : "r"(sRed + 4u * r));
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(m1) : "r"(sRed + 4u * (128 + r)));
+        const float m = fmaxf(m0, m1);
+        const float moff = m * sl2;
+        // ---- pass 2: p = 2^(s*scale*log2e - m*scale*log2e), row sum, bf16 P -> shared memory (K-major, SWIZZLE_128B)
+        float sum = 0.f;
+  #pragma unroll 1
+        for (int c = 0; c < 5; c++) {
+          uint32_t v[32];
+          tmem_ld32(t_row + (uint32_t)(half * 160 + c * 32), v);
+          tmem_wait_ld();
+          const int col0 = half * 160 + c * 32;
+  #pragma unroll
+          for (int g = 0; g < 4; g++) {
+            uint32_t pk[4];
+  #pragma unroll
+            for (int j = 0; j < 4; j++) {
+              const int cc = col0 + g * 8 + 2 * j;
+              float p0 = cc < a.Nk ? exp2f(fmaf(__uint_as_float(v[g * 8 + 2 * j]), sl2, -moff)) : 0.f;
+              float p1 = cc + 1 < a.Nk ? exp2f(fmaf(__uint_as_float(v[g * 8 + 2 * j + 1]), sl2, -moff)) : 0.f;
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(p0, p1);
+              const float2 back = __bfloat1622float2(h2);
+              sum += back.x + back.y;   // the sum of what the P V MMA will actually see
+              pk[j] = *reinterpret_cast<uint32_t*>(&h2);
+            }
+            const int col = col0 + g * 8;
+            const uint32_t kb = (uint32_t)col >> 6, ch = ((uint32_t)col & 63u) >> 3;
+            st_shared_v4(sP + kb * 16384 + (uint32_t)r * 128 + ((ch ^ ((uint32_t)r & 7u)) << 4), pk[0], pk[1], pk[2], pk[3]);
+          }
+        }
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(sRed + 1024u + 4u * (half * 128 + r)), "f"(sum) : "memory");
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        float l0, l1;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(l0) : "r"(sRed + 1024u + 4u * r));
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(l1) : "r"(sRed + 1024u + 4u * (128 + r)));
+        const float inv = 1.f / (l0 + l1);
+        // ---- normalise this thread's 160 probabilities in place (so that the stored P and the P V product agree)
+  #pragma unroll 1
+        for (int cg = 0; cg < 20; cg++) {
+          const int col = half * 160 + cg * 8;
+          const uint32_t kb = (uint32_t)col >> 6, ch = ((uint32_t)col & 63u) >> 3;
+          const uint32_t ad = sP + kb * 16384 + (uint32_t)r * 128 + ((ch ^ ((uint32_t)r & 7u)) << 4);
+          uint32_t w[4];
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(ad));
+  #pragma unroll
+          for (int j = 0; j < 4; j++) {
+            float2 f = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&w[j]));
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(f.x * inv, f.y * inv);
+            w[j] = *reinterpret_cast<uint32_t*>(&h2);
+          }
+          st_shared_v4(ad, w[0], w[1], w[2], w[3]);
+        }
+        if (a.lse && half == 0 && q0 + r < a.N)
+          a.lse[bh * a.N + q0 + r] = m * (sl2 * 0.69314718055994531f) + logf(l0 + l1);
+        tc_fence_before();
+        fence_async_smem();
+        asm volatile("bar.sync 3, 256;" ::: "memory");      // P complete (generic-proxy writes fenced for the async proxy)
+        if (threadIdx.x == 64) {
+          mbar_arrive(p_full);
+          if (a.store_p) {
+  #pragma unroll
+            for (int kb = 0; kb < AT_NK / 64; kb++)
+              if (kb * 64 < a.Nk)
+                asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                             ::"l"(reinterpret_cast<uint64_t>(&tmP)), "r"(sP + kb * 16384), "r"(kb * 64), "r"(q0), "r"((int)bh)
+                             : "memory");
+            tma_store_commit();
+          }
         }
       }
       // ---- epilogue: O (already normalised) TMEM -> bf16 -> global; each thread of the pair takes 32 of the 64 columns
@@ -273,7 +364,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_fwd_kernel(const __grid_co
       __syncwarp();
       if (lane == 0) mbar_arrive(o_empty);
     }
-    if (a.store_p && threadIdx.x == 64) tma_store_wait_all();
+    if ((a.store_p || MODE == 1) && threadIdx.x == 64) tma_store_wait_all();
   }
   tc_fence_before();
   __syncthreads();
@@ -305,10 +396,11 @@ CMX_API int cmx_attn_fwd(const void* q, int64_t ldq, const void* kv, int64_t ldk
   a.tiles_per_bh = cdiv(N, AT_BM);
   a.total_tiles = (long)a.tiles_per_bh * B * heads;
   a.scale_log2e = scale * 1.4426950408889634f;
+  a.scale = scale;
   a.store_p = p_out ? 1 : 0;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AT_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(attn_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AT_SMEM);
     if (e != cudaSuccess) CMX_FAIL((int)e, "cudaFuncSetAttribute(attn): %s", cudaGetErrorString(e));
     attr_done = true;
   }
@@ -316,8 +408,49 @@ CMX_API int cmx_attn_fwd(const void* q, int64_t ldq, const void* kv, int64_t ldk
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const long grid = a.total_tiles < sms ? a.total_tiles : sms;
-  attn_fwd_kernel<<<(unsigned)grid, AT_THREADS, AT_SMEM, st>>>(tmQ, tmKV, tmP, a);
+  attn_kernel<0><<<(unsigned)grid, AT_THREADS, AT_SMEM, st>>>(tmQ, tmKV, tmP, tmP, a);
   g_cmx_launches++;
   CMX_CHECK_LAUNCH("attn_fwd_kernel");
+  return 0;
+}
+
+CMX_API int cmx_attn_bwd(const void* d_o, int64_t lddo, const void* kv, int64_t ldkv, const void* p, int64_t ldp, void* ds_out,
+                         int64_t ldds, void* dq, int64_t lddq, int B, int N, int Nk, int heads, float scale, void* stream) {
+  CMX_REQUIRE(d_o && kv && p && ds_out && dq, "attn_bwd: null operand");
+  CMX_REQUIRE(Nk >= 1 && Nk <= AT_NK, "attn_bwd: Nkv=%d unsupported (max %d) - use the unfused path", Nk, AT_NK);
+  CMX_REQUIRE(lddo % 8 == 0 && ldkv % 8 == 0 && ldp % 8 == 0 && ldds % 8 == 0 && lddq % 8 == 0, "attn_bwd: leading dims %% 8");
+  CMX_REQUIRE(((uintptr_t)d_o & 15) == 0 && ((uintptr_t)kv & 15) == 0 && ((uintptr_t)p & 15) == 0 && ((uintptr_t)ds_out & 15) == 0 &&
+                  ((uintptr_t)dq & 15) == 0, "attn_bwd: pointers must be 16-byte aligned");
+  if (B == 0 || N == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  CUtensorMap tmQ, tmKV, tmP, tmDS;
+  int rc = cmx_make_map3(&tmQ, d_o, (uint64_t)heads * AT_D, (uint64_t)N, (uint64_t)B, (uint64_t)lddo, (uint64_t)N * lddo, AT_D, AT_BM);
+  if (rc) return rc;
+  rc = cmx_make_map3(&tmKV, kv, (uint64_t)2 * heads * AT_D, (uint64_t)Nk, (uint64_t)B, (uint64_t)ldkv, (uint64_t)Nk * ldkv, AT_D, 160);
+  if (rc) return rc;
+  rc = cmx_make_map3(&tmP, p, (uint64_t)Nk, (uint64_t)N, (uint64_t)B * heads, (uint64_t)ldp, (uint64_t)N * ldp, 64, AT_BM);
+  if (rc) return rc;
+  rc = cmx_make_map3(&tmDS, ds_out, (uint64_t)Nk, (uint64_t)N, (uint64_t)B * heads, (uint64_t)ldds, (uint64_t)N * ldds, 64, AT_BM);
+  if (rc) return rc;
+  AttnArgs a;
+  a.o = (bf16*)dq; a.ldo = lddq; a.lse = nullptr; a.B = B; a.N = N; a.Nk = Nk; a.heads = heads;
+  a.tiles_per_bh = cdiv(N, AT_BM);
+  a.total_tiles = (long)a.tiles_per_bh * B * heads;
+  a.scale_log2e = scale * 1.4426950408889634f;
+  a.scale = scale;
+  a.store_p = 0;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(attn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AT_SMEM);
+    if (e != cudaSuccess) CMX_FAIL((int)e, "cudaFuncSetAttribute(attn bwd): %s", cudaGetErrorString(e));
+    attr_done = true;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const long grid = a.total_tiles < sms ? a.total_tiles : sms;
+  attn_kernel<1><<<(unsigned)grid, AT_THREADS, AT_SMEM, st>>>(tmQ, tmKV, tmP, tmDS, a);
+  g_cmx_launches++;
+  CMX_CHECK_LAUNCH("attn_bwd_kernel");
   return 0;
 }

@@ -353,15 +353,20 @@ class Engine:
         # dV = P^T dO
         ops.gemm_raw(c.Pm, dO, dkv32, Nk, d, N, Np, C, 2 * C, c_off=C, trans_a=True, trans_b=True, batch=bs, sA=sP,
                      sB=(N * C, d), sC=(Nk * 2 * C, d), accumulate=True, split_k=split)
-        # dP = dO V^T
-        dP = self.E(B * heads * N, Np, dtype=f32)[:, :Nk]
-        ops.gemm_raw(dO, c.kv, dP, N, Nk, d, C, 2 * C, Np, b_off=C, batch=bs, sA=(N * C, d), sB=(Nk * 2 * C, d), sC=sP)
-        dS = self.E(B * heads * N, Np)[:, :Nk]
-        ops.softmax_rows_bwd(c.Pm, dP, scale, dS)
-        del dP
-        # dQ = dS K ; dK = dS^T Q
         dq = self.E(M, C)
-        ops.gemm_raw(dS, c.kv, dq, N, d, Nk, Np, 2 * C, C, trans_b=True, batch=bs, sA=sP, sB=(Nk * 2 * C, d), sC=(N * C, d))
+        dS = self.E(B * heads * N, Np)[:, :Nk]
+        if d == 64 and Nk <= ops.ATTN_MAX_NK and self.fused_attention:
+            # fused: dP = dO V^T stays in tensor memory, dS in place of the TMA-loaded P tile, dQ = dS K
+            ops.attn_bwd(dO, c.kv, c.Pm, dS, dq, B, N, Nk, heads, scale)
+        else:
+            # dP = dO V^T
+            dP = self.E(B * heads * N, Np, dtype=f32)[:, :Nk]
+            ops.gemm_raw(dO, c.kv, dP, N, Nk, d, C, 2 * C, Np, b_off=C, batch=bs, sA=(N * C, d), sB=(Nk * 2 * C, d), sC=sP)
+            ops.softmax_rows_bwd(c.Pm, dP, scale, dS)
+            del dP
+            # dQ = dS K
+            ops.gemm_raw(dS, c.kv, dq, N, d, Nk, Np, 2 * C, C, trans_b=True, batch=bs, sA=sP, sB=(Nk * 2 * C, d), sC=(N * C, d))
+        # dK = dS^T Q
         ops.gemm_raw(dS, c.q, dkv32, Nk, d, N, Np, C, 2 * C, trans_a=True, trans_b=True, batch=bs, sA=sP, sB=(N * C, d),
                      sC=(Nk * 2 * C, d), accumulate=True, split_k=split)
         del dS

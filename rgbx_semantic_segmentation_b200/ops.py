@@ -302,6 +302,15 @@ def attn_fwd(q, kv, o, B, N, Nk, heads, scale, p_out=None, lse=None):
     return o
 
 
+def attn_bwd(d_o, kv, p, ds, dq, B, N, Nk, heads, scale):
+    """d_o [B*N, C], kv [B*Nk, 2C], p / ds: bf16 views [B*heads*N, Nk] (padded ld), dq [B*N, C]"""
+    _cuda(d_o, kv, p, ds, dq)
+    _call("cmx_attn_bwd", d_o.data_ptr(), _ld(d_o), kv.data_ptr(), _ld(kv), p.data_ptr(), _ld(p), ds.data_ptr(), _ld(ds),
+          dq.data_ptr(), _ld(dq), B, N, Nk, heads, scale, _stream(),
+          flops=4 * B * heads * N * Nk * 64, nbytes=_nb(d_o, kv, dq) + 2 * (B * heads * N * Nk * 2))
+    return dq
+
+
 # ------------------------------------------------------------------------------------------------
 # softmax
 # ------------------------------------------------------------------------------------------------

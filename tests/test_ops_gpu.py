@@ -433,3 +433,15 @@ def test_fused_attention_forward(B, N, Nk, heads):
     o2 = torch.empty_like(o)
     ops.attn_fwd(q, kv, o2, B, N, Nk, heads, scale)
     assert torch.equal(o, o2)
+    # fused backward core: dS and dQ from (dO, K, V, P)
+    dO = rnd(B * N, C, dtype=bf)
+    dsb = torch.full((B * heads * N, Np), 5.0, device=DEV, dtype=bf)
+    dq = torch.full((B * N, C), 9.0, device=DEV, dtype=bf)
+    ops.attn_bwd(dO, kv, pbuf[:, :Nk], dsb[:, :Nk], dq, B, N, Nk, heads, scale)
+    Pf = pbuf[:, :Nk].float().reshape(B, heads, N, Nk)
+    dOf = dO.float().view(B, N, heads, d).permute(0, 2, 1, 3)
+    dP = dOf @ vf.transpose(-1, -2)
+    dS = scale * Pf * (dP - (Pf * dP).sum(-1, keepdim=True))
+    close(dsb[:, :Nk].reshape(B, heads, N, Nk), dS, 2e-2, 2e-3 * float(dS.abs().max()) + 1e-6, "dS")
+    dq_ref = (dsb[:, :Nk].float().reshape(B, heads, N, Nk) @ kf).permute(0, 2, 1, 3).reshape(B * N, C)
+    close(dq, dq_ref, 2e-2, 2e-2 * float(dq_ref.abs().max()) + 1e-6, "dQ")
