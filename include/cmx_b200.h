@@ -68,13 +68,15 @@ int cmx_gemm_which(const CmxGemm* g);
 int cmx_layernorm_fwd(const void* x, int x_dtype, int64_t ldx, const float* gamma, const float* beta, float eps,
                       void* y, int y_dtype, int64_t ldy, float* mean, float* rstd, int64_t M, int C, void* stream);
 /* dx = dres + LN'(dy + dy2);  dx_bf = bf16(dx * scale[row / rows_per_sample]) (optional);
- * dgamma/dbeta (fp32[C]) are ACCUMULATED (atomic). dy_dtype applies to dy; dy2 is bf16; dres fp32. */
+ * dgamma/dbeta (fp32[C]) are ACCUMULATED (atomic). dy_dtype applies to dy; dy2 is bf16; dres fp32.
+ * dbias (optional, fp32[C], accumulated): column sums of the bf16 output (dx_bf if given, else dx) = bias gradient of
+ * the Linear/conv layer whose output this LayerNorm normalised. */
 int cmx_layernorm_bwd(const void* dy, int dy_dtype, int64_t lddy, const void* dy2, int64_t lddy2,
                       const void* x, int x_dtype, int64_t ldx, const float* mean, const float* rstd,
                       const float* gamma, const float* dres, int64_t lddres,
                       void* dx, int dx_dtype, int64_t lddx, void* dx_bf, int64_t lddxbf,
                       const float* scale, int rows_per_sample,
-                      float* dgamma, float* dbeta, int64_t M, int C, void* stream);
+                      float* dgamma, float* dbeta, float* dbias, int64_t M, int C, void* stream);
 
 /* ---- BatchNorm2d over token-major [M,C] (net_utils.py:318,321; MLPDecoder.py:52-53) ----------- */
 int cmx_colstats(const void* x, int x_dtype, int64_t ldx, double* sum, double* sumsq, int64_t M, int C, void* stream);
@@ -107,7 +109,9 @@ int cmx_bn_bwd_apply(const void* dy, int dy_dtype, int64_t lddy, const void* x, 
  *      net_utils.py:314-315).  w: fp32 [C,9] (== Conv2d weight [C,1,3,3]).  flip: correlate with the
  *      180-degree rotated kernel (data-gradient).  */
 int cmx_dwconv3x3_fwd(const void* x, int64_t ldx, const float* w, const float* bias, int act, int flip,
-                      void* y, int64_t ldy, int B, int H, int W, int C, void* stream);
+                      void* y, int64_t ldy, float* ysum, int B, int H, int W, int C, void* stream);
+/* ysum (optional, fp32[C], accumulated): per-channel sums of the output (bias gradient of the producer layer when
+ * this call computes a data gradient) */
 /* du = dy * act'(conv(x)+b) -> bf16; dW[C,9], db[C] accumulated (fp32 atomics). */
 int cmx_dwconv3x3_bwd_pre(const void* x, int64_t ldx, const float* w, const float* bias, int act,
                           const void* dy, int64_t lddy, void* du, int64_t lddu, float* dw, float* db,
@@ -166,7 +170,8 @@ int cmx_softmax_dim2_bwd(const float* p32, const float* dp, float scale, void* d
 /* ---- FRM (net_utils.py:22-30, 79-83, 147-152) ------------------------------------------------- */
 /* global avg + max pool per (b,c) of x1|x2 packed as one [B*HW, C2] matrix (C2 = 2C). y[b] = [avg(C2) | max(C2)],
  * argmax (row index within the sample) saved for backward. */
-int cmx_pool_avgmax_fwd(const void* x, int64_t ldx, float* y, int32_t* argmax, int B, int HW, int C2, void* stream);
+int64_t cmx_pool_avgmax_ws_bytes(int B, int C2);   /* size of the partial-result workspace `ws` */
+int cmx_pool_avgmax_fwd(const void* x, int64_t ldx, float* y, int32_t* argmax, void* ws, int B, int HW, int C2, void* stream);
 /* dx[row,c] += dy_avg[b,c]/HW + (row==argmax[b,c]) * dy_max[b,c]   (dx fp32, in place) */
 int cmx_pool_avgmax_bwd(const float* dy, const int32_t* argmax, float* dx, int64_t lddx, int B, int HW, int C2, void* stream);
 /* small-M fp32 linear: y = act(x W^T + b), x [Mb,K], W [N,K]; act: 0 none, 1 relu, 3 sigmoid */

@@ -43,7 +43,7 @@ def parse_header(path=HEADER):
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     src = re.sub(r"//[^\n]*", "", src)
     protos = {}
-    for m in re.finditer(r"(const char\*|long long|int)\s+(cmx_\w+)\s*\(([^;{}]*?)\)\s*;", src, flags=re.S):
+    for m in re.finditer(r"(const char\*|long long|int64_t|int)\s+(cmx_\w+)\s*\(([^;{}]*?)\)\s*;", src, flags=re.S):
         ret, name, args = m.group(1), m.group(2), m.group(3)
         argtypes = []
         args = " ".join(args.split())
@@ -55,7 +55,7 @@ def parse_header(path=HEADER):
                 else:
                     ty = a.replace("const ", "").rsplit(" ", 1)[0].strip()
                     argtypes.append(_CTYPE[ty])
-        restype = {"const char*": ctypes.c_char_p, "long long": ctypes.c_longlong, "int": ctypes.c_int}[ret]
+        restype = {"const char*": ctypes.c_char_p, "long long": ctypes.c_longlong, "int64_t": ctypes.c_int64, "int": ctypes.c_int}[ret]
         protos[name] = (restype, argtypes)
     return protos
 

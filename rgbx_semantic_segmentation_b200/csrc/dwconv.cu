@@ -215,11 +215,28 @@ __global__ void __launch_bounds__(256) dwconv_tiled_kernel(const bf16* __restric
             }
           *reinterpret_cast<__nv_bfloat162*>(out + (rowbase + gx) * ldo + c) = __floats2bfloat162_rn(g.x, g.y);
         } else {
-          *reinterpret_cast<__nv_bfloat162*>(out + (rowbase + gx) * ldo + c) =
-              __floats2bfloat162_rn(act_f<ACT>(a0), act_f<ACT>(a1));
+          const __nv_bfloat162 o2 = __floats2bfloat162_rn(act_f<ACT>(a0), act_f<ACT>(a1));
+          *reinterpret_cast<__nv_bfloat162*>(out + (rowbase + gx) * ldo + c) = o2;
+          if (db) {  // per-channel sum of what was written (bias gradient of the layer that produced x's gradient)
+            const float2 of = __bfloat1622float2(o2);
+            gb[0] += of.x;
+            gb[1] += of.y;
+          }
         }
       }
     }
+  }
+  if (MODE != 1 && db) {
+    __syncthreads();
+    for (int i = tid; i < DT_CH; i += 256) sred[9][i] = 0.f;
+    __syncthreads();
+    if (c_ok) {
+      atomicAdd(&sred[9][cp * 2], gb[0]);
+      atomicAdd(&sred[9][cp * 2 + 1], gb[1]);
+    }
+    __syncthreads();
+    for (int i = tid; i < DT_CH; i += 256)
+      if (cbase + i < C) atomicAdd(db + cbase + i, sred[9][i]);
   }
   if (MODE == 1) {
     // reduce the 8 row-threads of every channel pair, then one atomicAdd per (channel, tap) per CTA
@@ -254,7 +271,7 @@ static void dwconv_tiled_launch(const void* x, long ldx, const float* w, const f
   const long ntiles = (long)B * tiles_x * tiles_y;
   const int gx = (C + DT_CH - 1) / DT_CH;
   long gy = ntiles;
-  const long cap = MODE == 1 ? (148L * 5 + gx - 1) / gx : (148L * 20 + gx - 1) / gx;  // backward: few CTAs => few atomics
+  const long cap = (MODE == 1 || db) ? (148L * 5 + gx - 1) / gx : (148L * 20 + gx - 1) / gx;  // reductions: few CTAs => few atomics
   if (gy > cap) gy = cap;
   dim3 grid(gx, (unsigned)gy);
   dwconv_tiled_kernel<ACT, MODE><<<grid, 256, 0, st>>>((const bf16*)x, ldx, w, bias, (const bf16*)dy, lddy, (bf16*)out, ldo, dw, db, B,
@@ -262,21 +279,22 @@ static void dwconv_tiled_launch(const void* x, long ldx, const float* w, const f
 }
 
 CMX_API int cmx_dwconv3x3_fwd(const void* x, int64_t ldx, const float* w, const float* bias, int act, int flip, void* y,
-                              int64_t ldy, int B, int H, int W, int C, void* stream) {
+                              int64_t ldy, float* ysum, int B, int H, int W, int C, void* stream) {
   CMX_REQUIRE(C % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0, "dwconv3x3: C and ld must be multiples of 8 (C=%d)", C);
   cudaStream_t st = (cudaStream_t)stream;
   if ((long)B * H * W == 0) return 0;
   if (getenv("CMX_DWCONV_LEGACY") == nullptr) {
     if (flip) {
       CMX_REQUIRE(act == CMX_ACT_NONE, "dwconv3x3: flip is for the data gradient (no activation)");
-      dwconv_tiled_launch<CMX_ACT_NONE, 2>(x, ldx, w, nullptr, nullptr, 0, y, ldy, nullptr, nullptr, B, H, W, C, st);
-    } else if (act == CMX_ACT_GELU) dwconv_tiled_launch<CMX_ACT_GELU, 0>(x, ldx, w, bias, nullptr, 0, y, ldy, nullptr, nullptr, B, H, W, C, st);
-    else if (act == CMX_ACT_RELU) dwconv_tiled_launch<CMX_ACT_RELU, 0>(x, ldx, w, bias, nullptr, 0, y, ldy, nullptr, nullptr, B, H, W, C, st);
-    else dwconv_tiled_launch<CMX_ACT_NONE, 0>(x, ldx, w, bias, nullptr, 0, y, ldy, nullptr, nullptr, B, H, W, C, st);
+      dwconv_tiled_launch<CMX_ACT_NONE, 2>(x, ldx, w, nullptr, nullptr, 0, y, ldy, nullptr, ysum, B, H, W, C, st);
+    } else if (act == CMX_ACT_GELU) dwconv_tiled_launch<CMX_ACT_GELU, 0>(x, ldx, w, bias, nullptr, 0, y, ldy, nullptr, ysum, B, H, W, C, st);
+    else if (act == CMX_ACT_RELU) dwconv_tiled_launch<CMX_ACT_RELU, 0>(x, ldx, w, bias, nullptr, 0, y, ldy, nullptr, ysum, B, H, W, C, st);
+    else dwconv_tiled_launch<CMX_ACT_NONE, 0>(x, ldx, w, bias, nullptr, 0, y, ldy, nullptr, ysum, B, H, W, C, st);
     g_cmx_launches++;
     CMX_CHECK_LAUNCH("dwconv3x3_tiled");
     return 0;
   }
+  CMX_REQUIRE(!ysum, "dwconv3x3: ysum is only available on the tiled path");
   constexpr int TW = 4;
   const long nstrips = (long)B * H * ((W + TW - 1) / TW);
   if (nstrips == 0) return 0;

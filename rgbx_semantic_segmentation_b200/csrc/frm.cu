@@ -13,46 +13,96 @@ extern std::atomic<long long> g_cmx_launches;
     return 0;                  \
   } while (0)
 
-// ---- avg + max pool over the HW rows of each sample ---------------------------------------------------
-// grid (ceil(C2/32), B); block 32 x 8.  First-max index kept (PyTorch adaptive_max_pool2d semantics).
-__global__ void __launch_bounds__(256) pool_avgmax_kernel(const bf16* __restrict__ x, long ldx, float* __restrict__ y,
-                                                          int32_t* __restrict__ argmax, int HW, int C2) {
-  __shared__ float ssum[8][33];
-  __shared__ float smax[8][33];
-  __shared__ int sidx[8][33];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + tx;
-  const int b = blockIdx.y;
-  float s = 0.f, m = -INFINITY;
-  int mi = 0;
-  if (c < C2)
-    for (int r = ty; r < HW; r += 8) {
-      const float v = __bfloat162float(x[((long)b * HW + r) * ldx + c]);
-      s += v;
-      if (v > m) { m = v; mi = r; }
+// ---- avg + max pool over the HW rows of each sample -------------------------------------------------------
+// Stage 1: grid (column blocks, B, row chunks); thread = 8 channels (one 16-byte load) x row lane; per-chunk partial
+// (sum, max, first-argmax) go to the caller's workspace.  Stage 2 folds the chunks in row order, so the FIRST maximum
+// wins on ties (PyTorch adaptive_max_pool2d semantics).
+constexpr int POOL_MAXCH = 64;
+__global__ void __launch_bounds__(256) pool_partial_kernel(const bf16* __restrict__ x, long ldx, float* __restrict__ wsum,
+                                                           float* __restrict__ wmax, int* __restrict__ widx, int HW, int C2,
+                                                           int ng, int rows_per_chunk, int nchunk) {
+  __shared__ float ssum[256][8];
+  __shared__ float smax[256][8];
+  __shared__ int sidx[256][8];
+  const int tid = threadIdx.x;
+  const int cg = tid % ng, rl = tid / ng, nrl = 256 / ng;
+  const int c = (blockIdx.x * ng + cg) * 8;
+  const int b = blockIdx.y, ch = blockIdx.z;
+  const int r0 = ch * rows_per_chunk;
+  int r1 = r0 + rows_per_chunk;
+  if (r1 > HW) r1 = HW;
+  float s[8], m[8];
+  int mi[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) { s[i] = 0.f; m[i] = -INFINITY; mi[i] = r0; }
+  if (c < C2 && rl < nrl)
+    for (int r = r0 + rl; r < r1; r += nrl) {
+      float v[8];
+      load8(x + ((long)b * HW + r) * ldx + c, v);
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        s[i] += v[i];
+        if (v[i] > m[i]) { m[i] = v[i]; mi[i] = r; }
+      }
     }
-  ssum[ty][tx] = s;
-  smax[ty][tx] = m;
-  sidx[ty][tx] = mi;
+#pragma unroll
+  for (int i = 0; i < 8; i++) { ssum[tid][i] = s[i]; smax[tid][i] = m[i]; sidx[tid][i] = mi[i]; }
   __syncthreads();
-  if (ty == 0 && c < C2) {
-    float ts = 0.f, tm = -INFINITY;
-    int ti = 0;
-    for (int i = 0; i < 8; i++) {
-      ts += ssum[i][tx];
-      const float v = smax[i][tx];
-      const int id = sidx[i][tx];
-      if (v > tm || (v == tm && id < ti)) { tm = v; ti = id; }
+  if (tid < ng * 8) {
+    const int g = tid >> 3, i = tid & 7;
+    const int cc = (blockIdx.x * ng + g) * 8 + i;
+    if (cc < C2) {
+      float ts = 0.f, tm = -INFINITY;
+      int ti = r0;
+      for (int l = 0; l < nrl; l++) {
+        const int t = l * ng + g;
+        ts += ssum[t][i];
+        const float v = smax[t][i];
+        const int id = sidx[t][i];
+        if (v > tm || (v == tm && id < ti)) { tm = v; ti = id; }
+      }
+      const long o = ((long)b * nchunk + ch) * C2 + cc;
+      wsum[o] = ts; wmax[o] = tm; widx[o] = ti;
     }
-    y[(long)b * 2 * C2 + c] = ts / (float)HW;
-    y[(long)b * 2 * C2 + C2 + c] = tm;
-    argmax[(long)b * C2 + c] = ti;
   }
 }
-CMX_API int cmx_pool_avgmax_fwd(const void* x, int64_t ldx, float* y, int32_t* argmax, int B, int HW, int C2, void* stream) {
+__global__ void pool_finalize_kernel(const float* __restrict__ wsum, const float* __restrict__ wmax, const int* __restrict__ widx,
+                                     float* __restrict__ y, int32_t* __restrict__ argmax, int B, int HW, int C2, int nchunk) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * C2) return;
+  const int c = idx % C2, b = idx / C2;
+  float ts = 0.f, tm = -INFINITY;
+  int ti = 0;
+  for (int ch = 0; ch < nchunk; ch++) {
+    const long o = ((long)b * nchunk + ch) * C2 + c;
+    ts += wsum[o];
+    if (wmax[o] > tm) { tm = wmax[o]; ti = widx[o]; }
+  }
+  y[(long)b * 2 * C2 + c] = ts / (float)HW;
+  y[(long)b * 2 * C2 + C2 + c] = tm;
+  argmax[(long)b * C2 + c] = ti;
+}
+CMX_API int64_t cmx_pool_avgmax_ws_bytes(int B, int C2) { return (int64_t)B * POOL_MAXCH * C2 * 12; }
+CMX_API int cmx_pool_avgmax_fwd(const void* x, int64_t ldx, float* y, int32_t* argmax, void* ws, int B, int HW, int C2, void* stream) {
   if (B == 0) return 0;
-  dim3 grid(cdiv(C2, 32), B);
-  pool_avgmax_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, ldx, y, argmax, HW, C2);
+  CMX_REQUIRE(C2 % 8 == 0 && ldx % 8 == 0 && ws, "pool_avgmax: C2 %% 8 and a workspace are required");
+  cudaStream_t st = (cudaStream_t)stream;
+  int ng = C2 / 8;
+  if (ng > 32) ng = 32;
+  while (256 % ng) ng--;
+  const int nrl = 256 / ng;
+  int nchunk = cdiv(HW, 4 * nrl);
+  if (nchunk > POOL_MAXCH) nchunk = POOL_MAXCH;
+  if (nchunk < 1) nchunk = 1;
+  const int rows_per_chunk = cdiv(HW, nchunk);
+  nchunk = cdiv(HW, rows_per_chunk);
+  float* wsum = (float*)ws;
+  float* wmax = wsum + (size_t)B * POOL_MAXCH * C2;
+  int* widx = (int*)(wmax + (size_t)B * POOL_MAXCH * C2);
+  dim3 grid(cdiv(C2 / 8, ng), B, nchunk);
+  pool_partial_kernel<<<grid, 256, 0, st>>>((const bf16*)x, ldx, wsum, wmax, widx, HW, C2, ng, rows_per_chunk, nchunk);
+  g_cmx_launches++;
+  pool_finalize_kernel<<<cdiv(B * C2, 128), 128, 0, st>>>(wsum, wmax, widx, y, argmax, B, HW, C2, nchunk);
   LAUNCH_DONE("pool_avgmax_fwd");
 }
 __global__ void __launch_bounds__(256) pool_avgmax_bwd_kernel(const float* __restrict__ dy, const int32_t* __restrict__ argmax,
@@ -136,15 +186,31 @@ __global__ void __launch_bounds__(256) smallm_dw_kernel(const float* __restrict_
   for (int m = 0; m < Mb; m++) s = fmaf(dpre[(long)m * N + n], x[(long)m * K + k], s);
   dw[idx] += s;
 }
+// dx[m,k] = sum_n dpre[m,n] W[n,k]: thread = column k (coalesced W reads), blockIdx.y = chunk of 64 rows of W,
+// all Mb <= 16 samples at once; partial sums are atomically added into the zeroed dx
 __global__ void __launch_bounds__(256) smallm_dx_kernel(const float* __restrict__ dpre, const float* __restrict__ w, float* __restrict__ dx,
                                                         int Mb, int N, int K) {
-  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (long)Mb * K) return;
-  const int k = (int)(idx % K);
-  const int m = (int)(idx / K);
-  float s = 0.f;
-  for (int n = 0; n < N; n++) s = fmaf(dpre[(long)m * N + n], w[(long)n * K + k], s);
-  dx[idx] = s;
+  __shared__ float sd[SMALLM_MAX][64];
+  const int n0 = blockIdx.y * 64;
+  for (int i = threadIdx.x; i < SMALLM_MAX * 64; i += 256) {
+    const int m = i >> 6, n = n0 + (i & 63);
+    sd[m][i & 63] = (m < Mb && n < N) ? dpre[(long)m * N + n] : 0.f;
+  }
+  __syncthreads();
+  const int k = blockIdx.x * 256 + threadIdx.x;
+  if (k >= K) return;
+  float acc[SMALLM_MAX];
+#pragma unroll
+  for (int m = 0; m < SMALLM_MAX; m++) acc[m] = 0.f;
+  const int nn = min(64, N - n0);
+  for (int n = 0; n < nn; n++) {
+    const float wv = w[(long)(n0 + n) * K + k];
+#pragma unroll
+    for (int m = 0; m < SMALLM_MAX; m++) acc[m] = fmaf(sd[m][n], wv, acc[m]);
+  }
+#pragma unroll
+  for (int m = 0; m < SMALLM_MAX; m++)
+    if (m < Mb) atomicAdd(dx + (long)m * K + k, acc[m]);
 }
 CMX_API int cmx_smallm_linear_bwd(const float* dy, const float* y, int act, const float* x, const float* w, float* dx, float* dw,
                                   float* db, float* dpre_ws, int Mb, int N, int K, void* stream) {
@@ -156,7 +222,9 @@ CMX_API int cmx_smallm_linear_bwd(const float* dy, const float* y, int act, cons
     g_cmx_launches++;
   }
   if (dx) {
-    smallm_dx_kernel<<<cdiv((long)Mb * K, 256), 256, 0, st>>>(dpre_ws, w, dx, Mb, N, K);
+    cudaMemsetAsync(dx, 0, sizeof(float) * (size_t)Mb * K, st);
+    dim3 grid(cdiv(K, 256), cdiv(N, 64));
+    smallm_dx_kernel<<<grid, 256, 0, st>>>(dpre_ws, w, dx, Mb, N, K);
     g_cmx_launches++;
   }
   CMX_CHECK_LAUNCH("smallm_linear_bwd");

@@ -16,27 +16,34 @@ extern std::atomic<long long> g_cmx_launches;
 // ---- stage-1 im2col from the NCHW fp32 image ------------------------------------------------------
 __global__ void __launch_bounds__(256) im2col_nchw_kernel(const float* __restrict__ x, bf16* __restrict__ col, int B, int Cin, int H,
                                                           int W, int k, int s, int p, int Ho, int Wo, int kpad) {
+  // one thread = 8 consecutive im2col columns of one output pixel (one 16-byte store)
+  const int g8 = kpad >> 3;
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long total = (long)B * Ho * Wo * kpad;
+  const long total = (long)B * Ho * Wo * g8;
   if (idx >= total) return;
-  const int j = (int)(idx % kpad);
-  const long row = idx / kpad;
-  float v = 0.f;
-  if (j < k * k * Cin) {
-    const int ci = j % Cin, tap = j / Cin;
-    const int kh = tap / k, kw = tap % k;
-    const int ox = (int)(row % Wo);
-    const int oy = (int)((row / Wo) % Ho);
-    const int b = (int)(row / ((long)Wo * Ho));
-    const int iy = oy * s - p + kh, ix = ox * s - p + kw;
-    if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = x[(((long)b * Cin + ci) * H + iy) * W + ix];
+  const int j0 = (int)(idx % g8) * 8;
+  const long row = idx / g8;
+  const int ox = (int)(row % Wo);
+  const int oy = (int)((row / Wo) % Ho);
+  const int b = (int)(row / ((long)Wo * Ho));
+  float v[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const int j = j0 + i;
+    v[i] = 0.f;
+    if (j < k * k * Cin) {
+      const int ci = j % Cin, tap = j / Cin;
+      const int kh = tap / k, kw = tap % k;
+      const int iy = oy * s - p + kh, ix = ox * s - p + kw;
+      if (iy >= 0 && iy < H && ix >= 0 && ix < W) v[i] = x[(((long)b * Cin + ci) * H + iy) * W + ix];
+    }
   }
-  col[idx] = __float2bfloat16(v);
+  store8(col + row * kpad + j0, v);
 }
 CMX_API int cmx_im2col_nchw(const float* x, void* col, int B, int Cin, int H, int W, int k, int s, int p, int Ho, int Wo,
                             int kpad, void* stream) {
-  CMX_REQUIRE(kpad >= k * k * Cin, "im2col_nchw: kpad too small");
-  const long total = (long)B * Ho * Wo * kpad;
+  CMX_REQUIRE(kpad >= k * k * Cin && kpad % 8 == 0, "im2col_nchw: kpad must be a multiple of 8 and >= k*k*Cin");
+  const long total = (long)B * Ho * Wo * (kpad >> 3);
   if (total == 0) return 0;
   im2col_nchw_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(x, (bf16*)col, B, Cin, H, W, k, s, p, Ho, Wo, kpad);
   LAUNCH_DONE("im2col_nchw");

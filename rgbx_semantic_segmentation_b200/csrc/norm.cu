@@ -137,21 +137,22 @@ __global__ void __launch_bounds__(256) ln_bwd_v2_kernel(const TDY* __restrict__ 
                                                         const float* __restrict__ dres, long lddres, TDX* __restrict__ dx, long lddx,
                                                         bf16* __restrict__ dxbf, long lddxbf, const float* __restrict__ scale,
                                                         int rows_per_sample, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                                        long M, int C) {
+                                                        float* __restrict__ dbias, long M, int C) {
   constexpr int RPW = 32 / G;
   __shared__ float sh_g[512];
   __shared__ float sh_b[512];
+  __shared__ float sh_s[512];
   const int lane = threadIdx.x & 31;
   const int lg = lane % G;
   const int warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-  for (int i = threadIdx.x; i < C; i += blockDim.x) { sh_g[i] = 0.f; sh_b[i] = 0.f; }
+  for (int i = threadIdx.x; i < C; i += blockDim.x) { sh_g[i] = 0.f; sh_b[i] = 0.f; sh_s[i] = 0.f; }
   __syncthreads();
-  float ag[J][8], ab[J][8], gm[J][8];
+  float ag[J][8], ab[J][8], gm[J][8], as[J][8];
 #pragma unroll
   for (int j = 0; j < J; j++) {
     const int c = 8 * (lg + G * j);
 #pragma unroll
-    for (int i = 0; i < 8; i++) { ag[j][i] = 0.f; ab[j][i] = 0.f; gm[j][i] = 0.f; }
+    for (int i = 0; i < 8; i++) { ag[j][i] = 0.f; ab[j][i] = 0.f; gm[j][i] = 0.f; as[j][i] = 0.f; }
     if (c < C) load8(gamma + c, gm[j]);
   }
   const long nslots = (M + RPW - 1) / RPW;  // warp-iterations
@@ -210,6 +211,23 @@ __global__ void __launch_bounds__(256) ln_bwd_v2_kernel(const TDY* __restrict__ 
           for (int i = 0; i < 8; i++) o[i] *= sc;
           store8(dxbf + row * lddxbf + c, o);
         }
+        if (dbias) {
+#pragma unroll
+          for (int i = 0; i < 8; i++) as[j][i] += o[i];
+        }
+      }
+    }
+  }
+  if (dbias) {
+#pragma unroll
+    for (int j = 0; j < J; j++) {
+      const int c = 8 * (lg + G * j);
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        float a = as[j][i];
+#pragma unroll
+        for (int o = G; o < 32; o <<= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if (lane < G && c < C) atomicAdd(&sh_s[c + i], a);
       }
     }
   }
@@ -236,6 +254,10 @@ __global__ void __launch_bounds__(256) ln_bwd_v2_kernel(const TDY* __restrict__ 
       atomicAdd(dgamma + i, sh_g[i]);
       atomicAdd(dbeta + i, sh_b[i]);
     }
+  }
+  if (dbias) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(dbias + i, sh_s[i]);
   }
 }
 
@@ -396,8 +418,8 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const TDY* __restrict__ dy,
 CMX_API int cmx_layernorm_bwd(const void* dy, int dy_dtype, int64_t lddy, const void* dy2, int64_t lddy2, const void* x,
                               int x_dtype, int64_t ldx, const float* mean, const float* rstd, const float* gamma,
                               const float* dres, int64_t lddres, void* dx, int dx_dtype, int64_t lddx, void* dx_bf,
-                              int64_t lddxbf, const float* scale, int rows_per_sample, float* dgamma, float* dbeta, int64_t M,
-                              int C, void* stream) {
+                              int64_t lddxbf, const float* scale, int rows_per_sample, float* dgamma, float* dbeta,
+                              float* dbias, int64_t M, int C, void* stream) {
   CMX_REQUIRE(C % 4 == 0 && C <= 4 * 32 * LN_MAXJ && C > 0, "layernorm_bwd: C=%d unsupported", C);
   CMX_REQUIRE((dgamma == nullptr) == (dbeta == nullptr), "layernorm_bwd: dgamma/dbeta must come together");
   if (M == 0) return 0;
@@ -412,7 +434,7 @@ CMX_API int cmx_layernorm_bwd(const void* dy, int dy_dtype, int64_t lddy, const 
 #define LN_B2T(TDY, TX, TDX, Gv, Jv)                                                                                            \
   ln_bwd_v2_kernel<TDY, TX, TDX, Gv, Jv><<<grid2, 256, 0, st>>>((const TDY*)dy, lddy, (const bf16*)dy2, lddy2, (const TX*)x, ldx, \
                                                                 mean, rstd, gamma, dres, lddres, (TDX*)dx, lddx, (bf16*)dx_bf,    \
-                                                                lddxbf, scale, rows_per_sample, dgamma, dbeta, M, C)
+                                                                lddxbf, scale, rows_per_sample, dgamma, dbeta, dbias, M, C)
 #define LN_B2(Gv, Jv)                                                            \
   do {                                                                           \
     switch (dy_dtype * 4 + x_dtype * 2 + dx_dtype) {                             \
@@ -433,6 +455,7 @@ CMX_API int cmx_layernorm_bwd(const void* dy, int dy_dtype, int64_t lddy, const 
     CMX_CHECK_LAUNCH("ln_bwd_v2");
     return 0;
   }
+  CMX_REQUIRE(!dbias, "layernorm_bwd: dbias needs the vectorised path (C %% 8 == 0, leading dims %% 8 == 0)");
   int grid = cdiv(M, 8);
   if (grid > 148 * 8) grid = 148 * 8;
 #define LN_B(TDY, TX, TDX)                                                                                              \

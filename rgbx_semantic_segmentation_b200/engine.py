@@ -228,11 +228,11 @@ class Engine:
         M, C = c.y.shape
         dy = self.E(M, C)
         ops.layernorm_bwd(dx0, c.y, c.mean, c.rstd, self.P(name + ".norm.weight"), dx=dy,
-                          dgamma=self.G(name + ".norm.weight"), dbeta=self.G(name + ".norm.bias"))
+                          dgamma=self.G(name + ".norm.weight"), dbeta=self.G(name + ".norm.bias"),
+                          dbias=self.G(name + ".proj.bias"))   # conv bias gradient = column sums of dy, folded in
         gp = self.Z(C, c.wp.shape[1])
         ops.mm(dy, c.col, gp, ta=True, tb=True, accumulate=True)
         ops.convw_unpack_grad(gp, self.G(name + ".proj.weight"))
-        ops.colsum(dy, self.G(name + ".proj.bias"))
         if c.s == 0:
             return None
         dcol = self.E(M, c.wp.shape[1])
@@ -308,9 +308,11 @@ class Engine:
             c.xn1, c.q, c.kv, c.kv_in, c.Pm, c.O, c.x1, c.xn2, c.h, c.g, c.Nk = xn1, q, kv, kv_in, Pm, O, x1, xn2, h, g, Nk
         return x2, c
 
-    def block_bwd(self, c, dx2, dx2_bf, B, prev_scale, need_bf):
+    def block_bwd(self, c, dx2, dx2_bf, B, prev_scale, need_bf, prev_fc2_bias=None):
         """dx2: fp32 grad of the block output; dx2_bf: bf16 copy already multiplied by this block's MLP
-        DropPath scale.  Returns (dx fp32, dx_bf bf16 scaled by `prev_scale` or None)."""
+        DropPath scale (its column sums = this block's fc2 bias gradient were accumulated by whoever produced it).
+        Returns (dx fp32, dx_bf bf16 scaled by `prev_scale` or None); `prev_fc2_bias` names the fc2 bias of the
+        PREVIOUS block, whose gradient is the column sum of dx_bf and is folded into the norm1 backward kernel."""
         p, s, H, W = c.p, c.s, c.H, c.W
         C, heads, R = self.dims[s], self.heads[s], self.srs[s]
         d = C // heads
@@ -319,7 +321,7 @@ class Engine:
         Nk = c.Nk
         scale = d ** -0.5
         # ---- Mix-FFN
-        self.linear_wgrad(dx2_bf, c.g, p + ".mlp.fc2.weight", p + ".mlp.fc2.bias")
+        self.linear_wgrad(dx2_bf, c.g, p + ".mlp.fc2.weight")
         dg = self.E(M, 4 * C)
         ops.mm(dx2_bf, self.W(p + ".mlp.fc2.weight"), dg, tb=True)
         du = self.E(M, 4 * C)
@@ -327,9 +329,10 @@ class Engine:
                               dg, du, self.G(p + ".mlp.dwconv.dwconv.weight").view(4 * C, 9), self.G(p + ".mlp.dwconv.dwconv.bias"),
                               B, H, W)
         dh = dg
-        ops.dwconv3x3_fwd(du, self.P(p + ".mlp.dwconv.dwconv.weight"), None, ACT_NONE, dh, B, H, W, flip=True)
+        ops.dwconv3x3_fwd(du, self.P(p + ".mlp.dwconv.dwconv.weight"), None, ACT_NONE, dh, B, H, W, flip=True,
+                          ysum=self.G(p + ".mlp.fc1.bias"))   # fc1 bias gradient = per-channel sums of dh
         del du
-        self.linear_wgrad(dh, c.xn2, p + ".mlp.fc1.weight", p + ".mlp.fc1.bias")
+        self.linear_wgrad(dh, c.xn2, p + ".mlp.fc1.weight")
         dxn2 = self.E(M, C)
         ops.mm(dh, self.W(p + ".mlp.fc1.weight"), dxn2, tb=True)
         del dh, dg
@@ -337,9 +340,10 @@ class Engine:
         dx1_bf = self.E(M, C)
         ops.layernorm_bwd(dxn2, c.x1, c.m2, c.r2, self.P(p + ".norm2.weight"), dres=dx2, dx=dx1, dx_bf=dx1_bf,
                           scale=None if c.dp is None else c.dp[0], rows_per_sample=N,
-                          dgamma=self.G(p + ".norm2.weight"), dbeta=self.G(p + ".norm2.bias"))
+                          dgamma=self.G(p + ".norm2.weight"), dbeta=self.G(p + ".norm2.bias"),
+                          dbias=self.G(p + ".attn.proj.bias"))
         # ---- attention
-        self.linear_wgrad(dx1_bf, c.O, p + ".attn.proj.weight", p + ".attn.proj.bias")
+        self.linear_wgrad(dx1_bf, c.O, p + ".attn.proj.weight")
         dO = self.E(M, C)
         ops.mm(dx1_bf, self.W(p + ".attn.proj.weight"), dO, tb=True)
         # dK / dV contract over all N tokens into a tiny [Nk, 64] tile per (sample, head): split-K with fp32
@@ -379,12 +383,12 @@ class Engine:
         if R > 1:
             dsr = self.E(B * Nk, C)
             ops.layernorm_bwd(dkvin, c.sr, c.ms, c.rs, self.P(p + ".attn.norm.weight"), dx=dsr,
-                              dgamma=self.G(p + ".attn.norm.weight"), dbeta=self.G(p + ".attn.norm.bias"))
+                              dgamma=self.G(p + ".attn.norm.weight"), dbeta=self.G(p + ".attn.norm.bias"),
+                              dbias=self.G(p + ".attn.sr.bias"))
             wsr = self.packed[p + ".attn.sr.weight"]
             gp = self.Z(C, wsr.shape[1])
             ops.mm(dsr, c.pat, gp, ta=True, tb=True, accumulate=True)
             ops.convw_unpack_grad(gp, self.G(p + ".attn.sr.weight"))
-            ops.colsum(dsr, self.G(p + ".attn.sr.bias"))
             dpat = self.E(B * Nk, wsr.shape[1])
             ops.mm(dsr, wsr, dpat, tb=True)
             dxn_b = self.E(M, C)
@@ -398,7 +402,8 @@ class Engine:
         dx_bf = self.E(M, C) if need_bf else None
         ops.layernorm_bwd(dxn_a, c.x, c.m1, c.r1, self.P(p + ".norm1.weight"), dy2=dxn_b, dres=dx1, dx=dx, dx_bf=dx_bf,
                           scale=prev_scale, rows_per_sample=N,
-                          dgamma=self.G(p + ".norm1.weight"), dbeta=self.G(p + ".norm1.bias"))
+                          dgamma=self.G(p + ".norm1.weight"), dbeta=self.G(p + ".norm1.bias"),
+                          dbias=None if prev_fc2_bias is None else self.G(prev_fc2_bias))
         return dx, dx_bf
 
     # ------------------------------------------------------------------------------------------
@@ -411,7 +416,7 @@ class Engine:
         c = _NS()
         y = self.E(B, 4 * C, dtype=f32)
         am = self.E(B, 2 * C, dtype=torch.int32)
-        ops.pool_avgmax_fwd(cat12, y, am, B, HW)
+        ops.pool_avgmax_fwd(cat12, y, am, B, HW)   # (two-stage reduction; the wrapper allocates the partials workspace)
         hid = self.E(B, 4 * C, dtype=f32)
         ops.smallm_linear_fwd(y, self.P(p + ".channel_weights.mlp.0.weight"), self.P(p + ".channel_weights.mlp.0.bias"), ACT_RELU, hid)
         cw = self.E(B, 2 * C, dtype=f32)
@@ -551,8 +556,9 @@ class Engine:
         ops.dwconv3x3_bwd_pre(c.c0, self.P(q + ".channel_embed.1.weight"), self.P(q + ".channel_embed.1.bias"), ACT_RELU, dc1, du,
                               self.G(q + ".channel_embed.1.weight").view(C, 9), self.G(q + ".channel_embed.1.bias"), B, H, W)
         dc0 = dc1
-        ops.dwconv3x3_fwd(du, self.P(q + ".channel_embed.1.weight"), None, ACT_NONE, dc0, B, H, W, flip=True)
-        self.linear_wgrad(dc0, c.merge, q + ".channel_embed.0.weight", q + ".channel_embed.0.bias")
+        ops.dwconv3x3_fwd(du, self.P(q + ".channel_embed.1.weight"), None, ACT_NONE, dc0, B, H, W, flip=True,
+                          ysum=self.G(q + ".channel_embed.0.bias"))
+        self.linear_wgrad(dc0, c.merge, q + ".channel_embed.0.weight")
         self.linear_wgrad(dz_bf, c.merge, q + ".residual.weight")
         dmerge = self.E(M, 2 * C)
         ops.mm(dc0, self.W(q + ".channel_embed.0.weight"), dmerge, tb=True)
@@ -562,8 +568,8 @@ class Engine:
             de_i, de_bf = self.E(M, C, dtype=f32), self.E(M, C)
             ops.layernorm_bwd(dmerge[:, i * C:(i + 1) * C], c.e[i], c.me[i], c.re[i], self.P(p + f".cross.norm{i + 1}.weight"),
                               dx=de_i, dx_bf=de_bf, dgamma=self.G(p + f".cross.norm{i + 1}.weight"),
-                              dbeta=self.G(p + f".cross.norm{i + 1}.bias"))
-            self.linear_wgrad(de_bf, c.yv[i], p + f".cross.end_proj{i + 1}.weight", p + f".cross.end_proj{i + 1}.bias")
+                              dbeta=self.G(p + f".cross.norm{i + 1}.bias"), dbias=self.G(p + f".cross.end_proj{i + 1}.bias"))
+            self.linear_wgrad(de_bf, c.yv[i], p + f".cross.end_proj{i + 1}.weight")
             dyv_i = self.E(M, 2 * C)
             ops.mm(de_bf, self.W(p + f".cross.end_proj{i + 1}.weight"), dyv_i, tb=True)
             de.append(de_i); dyv.append(dyv_i)
@@ -787,11 +793,13 @@ class Engine:
                 ops.layernorm_bwd(dcat[:, br * C:(br + 1) * C], st.xs[br], st.mn[br], st.rn[br],
                                   self.P(f"backbone.{nname}{s + 1}.weight"), dx=dx, dx_bf=dx_bf,
                                   scale=None if last.dp is None else last.dp[1], rows_per_sample=N,
-                                  dgamma=self.G(f"backbone.{nname}{s + 1}.weight"), dbeta=self.G(f"backbone.{nname}{s + 1}.bias"))
+                                  dgamma=self.G(f"backbone.{nname}{s + 1}.weight"), dbeta=self.G(f"backbone.{nname}{s + 1}.bias"),
+                                  dbias=self.G(last.p + ".mlp.fc2.bias"))
                 for i in range(len(blocks) - 1, -1, -1):
                     prev = blocks[i - 1] if i > 0 else None
                     prev_scale = None if (prev is None or prev.dp is None) else prev.dp[1]
-                    dx, dx_bf = self.block_bwd(blocks[i], dx, dx_bf, B, prev_scale, need_bf=(i > 0))
+                    dx, dx_bf = self.block_bwd(blocks[i], dx, dx_bf, B, prev_scale, need_bf=(i > 0),
+                                               prev_fc2_bias=None if prev is None else prev.p + ".mlp.fc2.bias")
                     blocks[i] = None
                 pending.append(self.pe_bwd(st.pe[br], dx, B))
             if s == 0:

@@ -161,14 +161,14 @@ def layernorm_fwd(x, gamma, beta, eps, y, mean=None, rstd=None):
 
 
 def layernorm_bwd(dy, x, mean, rstd, gamma, *, dy2=None, dres=None, dx=None, dx_bf=None, scale=None, rows_per_sample=0,
-                  dgamma=None, dbeta=None):
+                  dgamma=None, dbeta=None, dbias=None):
     M, C = x.shape
     _call("cmx_layernorm_bwd", 
         dy.data_ptr(), _dt(dy), _ld(dy), _p(dy2), _ld(dy2) if dy2 is not None else 0, x.data_ptr(), _dt(x), _ld(x),
         mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(), _p(dres), _ld(dres) if dres is not None else 0,
         _p(dx), _dt(dx) if dx is not None else F32, _ld(dx) if dx is not None else 0,
         _p(dx_bf), _ld(dx_bf) if dx_bf is not None else 0, _p(scale), rows_per_sample,
-        _p(dgamma), _p(dbeta), M, C, _stream(), nbytes=_nb(dy, dy2, x, dres, dx, dx_bf))
+        _p(dgamma), _p(dbeta), _p(dbias), M, C, _stream(), nbytes=_nb(dy, dy2, x, dres, dx, dx_bf))
 
 
 def colstats(x, sum_, sumsq):
@@ -213,9 +213,9 @@ def bn_bwd(dy, x, mean, invstd, gamma, beta, dx, dgamma, dbeta, ws, *, residual=
 # ------------------------------------------------------------------------------------------------
 # depthwise conv
 # ------------------------------------------------------------------------------------------------
-def dwconv3x3_fwd(x, w, bias, act, y, B, H, W, flip=False):
+def dwconv3x3_fwd(x, w, bias, act, y, B, H, W, flip=False, ysum=None):
     C = x.shape[1]
-    _call("cmx_dwconv3x3_fwd", x.data_ptr(), _ld(x), w.data_ptr(), _p(bias), act, int(flip), y.data_ptr(), _ld(y),
+    _call("cmx_dwconv3x3_fwd", x.data_ptr(), _ld(x), w.data_ptr(), _p(bias), act, int(flip), y.data_ptr(), _ld(y), _p(ysum),
                                              B, H, W, C, _stream(), tag="cmx_dwconv3x3_%s" % ("dgrad" if flip else "fwd"), nbytes=_nb(x, y))
     return y
 
@@ -340,9 +340,12 @@ def softmax_dim2_bwd(p32, dp, scale, dc16):
 # ------------------------------------------------------------------------------------------------
 # FRM
 # ------------------------------------------------------------------------------------------------
-def pool_avgmax_fwd(x, y, argmax, B, HW):
+def pool_avgmax_fwd(x, y, argmax, B, HW, ws=None):
     C2 = x.shape[1]
-    _call("cmx_pool_avgmax_fwd", x.data_ptr(), _ld(x), y.data_ptr(), argmax.data_ptr(), B, HW, C2, _stream(), nbytes=_nb(x))
+    if ws is None:
+        ws = torch.empty(int(_lib.load().cmx_pool_avgmax_ws_bytes(B, C2)), dtype=torch.uint8, device=x.device)
+    _call("cmx_pool_avgmax_fwd", x.data_ptr(), _ld(x), y.data_ptr(), argmax.data_ptr(), ws.data_ptr(), B, HW, C2, _stream(),
+          nbytes=_nb(x))
 
 
 def pool_avgmax_bwd(dy, argmax, dx, B, HW):

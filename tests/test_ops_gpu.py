@@ -87,8 +87,10 @@ def test_layernorm_fwd_bwd(C, xdt, ydt):
     dxbf = torch.empty(M, C, device=DEV, dtype=bf)
     dg = torch.zeros(C, device=DEV)
     db = torch.zeros(C, device=DEV)
+    dbias = torch.zeros(C, device=DEV)
     ops.layernorm_bwd(dy, x, mean, rstd, g, dy2=dy2, dres=dres, dx=dx, dx_bf=dxbf, scale=scale, rows_per_sample=rows_per_sample,
-                      dgamma=dg, dbeta=db)
+                      dgamma=dg, dbeta=db, dbias=dbias)
+    close(dbias, dxbf.float().sum(0), 1e-2, 5e-2 * M ** 0.5, "ln fused bias-gradient column sum")
     up = dy.float() + dy2.float()
     ref.backward(up)
     close(dx, xr.grad + dres, 1e-3, 2e-3, "ln dx")
@@ -158,7 +160,9 @@ def test_dwconv(act, B, H, W, C):
     dw, db = torch.zeros(C, 9, device=DEV), torch.zeros(C, device=DEV)
     ops.dwconv3x3_bwd_pre(x, w, bias, act, dy, du, dw, db, B, H, W)
     dx = torch.empty_like(x)
-    ops.dwconv3x3_fwd(du, w, None, 0, dx, B, H, W, flip=True)
+    ysum = torch.zeros(C, device=DEV)
+    ops.dwconv3x3_fwd(du, w, None, 0, dx, B, H, W, flip=True, ysum=ysum)
+    close(ysum, dx.float().sum(0), 1e-3, 1e-2, "dwconv dgrad fused column sum")
     close(dx, xr.grad.permute(0, 2, 3, 1).reshape(-1, C), 2e-2, 2e-2, "dwconv dx")
     n = (B * H * W) ** 0.5
     close(dw.reshape(C, 1, 3, 3), wr.grad, 1e-2, 2e-2 * n, "dwconv dw")
