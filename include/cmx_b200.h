@@ -59,7 +59,7 @@ typedef struct CmxGemm {
   int32_t impl;
 } CmxGemm;
 int cmx_gemm(const CmxGemm* g, void* stream);
-/* debug aid: device buffer (3*64*4 int64) receiving clock64 stamps of CTA 0's producer / MMA / epilogue roles, or NULL */
+/* debug aid: device buffer (5*64*4 int64) receiving clock64 stamps of CTA 0's producer / MMA / epilogue roles, or NULL */
 int cmx_debug_set_gemm_trace(void* buf);
 /* which implementation cmx_gemm would pick: 2 = tcgen05, 1 = fallback */
 int cmx_gemm_which(const CmxGemm* g);

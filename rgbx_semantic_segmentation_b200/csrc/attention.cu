@@ -46,6 +46,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_kernel(const __grid_consta
                                                              const __grid_constant__ CUtensorMap tmKV,
                                                              const __grid_constant__ CUtensorMap tmP,
                                                              const __grid_constant__ CUtensorMap tmDS, AttnArgs a) {
+  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sb = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sK = sb + AT_K_OFF, sV = sb + AT_V_OFF, sQ = sb + AT_Q_OFF, sP = sb + AT_P_OFF, sRed = sb + AT_RED_OFF;
@@ -83,6 +84,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_kernel(const __grid_consta
   tc_fence_after();
   uint32_t tmem;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot));
+  pdl_wait();  // PDL: the prologue above overlapped the previous kernel's tail
 
   if (warp == 0) {
     // ============================ TMA producer ============================
@@ -408,7 +410,19 @@ CMX_API int cmx_attn_fwd(const void* q, int64_t ldq, const void* kv, int64_t ldk
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const long grid = a.total_tiles < sms ? a.total_tiles : sms;
-  attn_kernel<0><<<(unsigned)grid, AT_THREADS, AT_SMEM, st>>>(tmQ, tmKV, tmP, tmP, a);
+  {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(AT_THREADS);
+    cfg.dynamicSmemBytes = AT_SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = cmx_use_pdl() ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, attn_kernel<0>, tmQ, tmKV, tmP, tmP, a);
+  }
   g_cmx_launches++;
   CMX_CHECK_LAUNCH("attn_fwd_kernel");
   return 0;
@@ -449,7 +463,19 @@ CMX_API int cmx_attn_bwd(const void* d_o, int64_t lddo, const void* kv, int64_t 
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const long grid = a.total_tiles < sms ? a.total_tiles : sms;
-  attn_kernel<1><<<(unsigned)grid, AT_THREADS, AT_SMEM, st>>>(tmQ, tmKV, tmP, tmDS, a);
+  {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(AT_THREADS);
+    cfg.dynamicSmemBytes = AT_SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = cmx_use_pdl() ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, attn_kernel<1>, tmQ, tmKV, tmP, tmDS, a);
+  }
   g_cmx_launches++;
   CMX_CHECK_LAUNCH("attn_bwd_kernel");
   return 0;

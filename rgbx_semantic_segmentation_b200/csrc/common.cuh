@@ -34,6 +34,14 @@ static inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
 enum { CMX_BF16 = 0, CMX_F32 = 1 };
 enum { CMX_ACT_NONE = 0, CMX_ACT_RELU = 1, CMX_ACT_GELU = 2 };
 
+// ---- programmatic dependent launch (PDL) -------------------------------------------------------------
+// Every kernel signals "dependents may be scheduled" as its first instruction; only kernels launched with the
+// programmatic-stream-serialization attribute (the tcgen05 GEMM and attention kernels) react to it: they run their
+// prologue (barrier init, TMEM allocation, tensor-map prefetch) while the previous kernel drains and then block in
+// pdl_wait() until that kernel has fully completed and flushed its writes.  For ordinary launches both are no-ops.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---- device helpers ------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -42,6 +42,7 @@ template <int ACT, bool FLIP, int TW>
 __global__ void __launch_bounds__(DW_CG* DW_PY) dwconv_fwd_kernel(const bf16* __restrict__ x, long ldx, const float* __restrict__ w,
                                                                   const float* __restrict__ bias, bf16* __restrict__ y, long ldy,
                                                                   int B, int H, int W, int C) {
+  pdl_trigger();
   constexpr int VEC = 8;
   __shared__ __align__(16) float sw[9][DW_CG * VEC];
   __shared__ __align__(16) float sb[DW_CG * VEC];
@@ -130,6 +131,7 @@ __global__ void __launch_bounds__(256) dwconv_tiled_kernel(const bf16* __restric
                                                            bf16* __restrict__ out, long ldo, float* __restrict__ dw,
                                                            float* __restrict__ db, int B, int H, int W, int C, int tiles_x,
                                                            int tiles_y, long ntiles) {
+  pdl_trigger();
   __shared__ __align__(16) bf16 tile[(DT_TH + 2) * (DT_TW + 2) * DT_CH];  // 43.5 KB
   __shared__ float sred[20][DT_CH];
   const int tid = threadIdx.x;
@@ -325,6 +327,7 @@ __global__ void __launch_bounds__(DW_CG* DW_PY) dwconv_bwd_pre_kernel(const bf16
                                                                       long lddy, bf16* __restrict__ du, long lddu,
                                                                       float* __restrict__ dw, float* __restrict__ db, int B, int H,
                                                                       int W, int C) {
+  pdl_trigger();
   constexpr int VEC = 4, TW = 2;
   __shared__ __align__(16) float sw[9][DW_CG * VEC];
   __shared__ __align__(16) float sb[DW_CG * VEC];

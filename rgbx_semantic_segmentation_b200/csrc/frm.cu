@@ -21,6 +21,7 @@ constexpr int POOL_MAXCH = 64;
 __global__ void __launch_bounds__(256) pool_partial_kernel(const bf16* __restrict__ x, long ldx, float* __restrict__ wsum,
                                                            float* __restrict__ wmax, int* __restrict__ widx, int HW, int C2,
                                                            int ng, int rows_per_chunk, int nchunk) {
+  pdl_trigger();
   __shared__ float ssum[256][8];
   __shared__ float smax[256][8];
   __shared__ int sidx[256][8];
@@ -68,6 +69,7 @@ __global__ void __launch_bounds__(256) pool_partial_kernel(const bf16* __restric
 }
 __global__ void pool_finalize_kernel(const float* __restrict__ wsum, const float* __restrict__ wmax, const int* __restrict__ widx,
                                      float* __restrict__ y, int32_t* __restrict__ argmax, int B, int HW, int C2, int nchunk) {
+  pdl_trigger();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * C2) return;
   const int c = idx % C2, b = idx / C2;
@@ -107,6 +109,7 @@ CMX_API int cmx_pool_avgmax_fwd(const void* x, int64_t ldx, float* y, int32_t* a
 }
 __global__ void __launch_bounds__(256) pool_avgmax_bwd_kernel(const float* __restrict__ dy, const int32_t* __restrict__ argmax,
                                                               float* __restrict__ dx, long lddx, int HW, int C2, long total) {
+  pdl_trigger();
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const int c = (int)(idx % C2);
@@ -129,6 +132,7 @@ constexpr int SMALLM_MAX = 16;
 __global__ void __launch_bounds__(256) smallm_linear_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                                 const float* __restrict__ b, int act, float* __restrict__ y, int Mb,
                                                                 int N, int K) {
+  pdl_trigger();
   const int lane = threadIdx.x & 31;
   const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (n >= N) return;
@@ -162,6 +166,7 @@ CMX_API int cmx_smallm_linear_fwd(const float* x, const float* w, const float* b
 // dpre = dy * act'(y)
 __global__ void smallm_dpre_kernel(const float* __restrict__ dy, const float* __restrict__ y, int act, float* __restrict__ dpre,
                                    float* __restrict__ db, int Mb, int N) {
+  pdl_trigger();
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
   float s = 0.f;
@@ -178,6 +183,7 @@ __global__ void smallm_dpre_kernel(const float* __restrict__ dy, const float* __
 // dW[n,k] += sum_m dpre[m,n] x[m,k];   dx[m,k] = sum_n dpre[m,n] W[n,k]
 __global__ void __launch_bounds__(256) smallm_dw_kernel(const float* __restrict__ dpre, const float* __restrict__ x, float* __restrict__ dw,
                                                         int Mb, int N, int K) {
+  pdl_trigger();
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long)N * K) return;
   const int k = (int)(idx % K);
@@ -190,6 +196,7 @@ __global__ void __launch_bounds__(256) smallm_dw_kernel(const float* __restrict_
 // all Mb <= 16 samples at once; partial sums are atomically added into the zeroed dx
 __global__ void __launch_bounds__(256) smallm_dx_kernel(const float* __restrict__ dpre, const float* __restrict__ w, float* __restrict__ dx,
                                                         int Mb, int N, int K) {
+  pdl_trigger();
   __shared__ float sd[SMALLM_MAX][64];
   const int n0 = blockIdx.y * 64;
   for (int i = threadIdx.x; i < SMALLM_MAX * 64; i += 256) {
@@ -239,6 +246,7 @@ __global__ void __launch_bounds__(256) frm_rectify_fwd_kernel(const bf16* __rest
                                                               const float* __restrict__ cw, float* __restrict__ sw,
                                                               bf16* __restrict__ r1, long ldr1, bf16* __restrict__ r2, long ldr2,
                                                               long M, int HW, int C) {
+  pdl_trigger();
   const int lane = threadIdx.x & 31;
   const long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= M) return;
@@ -298,6 +306,7 @@ __global__ void __launch_bounds__(256) frm_rectify_bwd_kernel(const float* __res
                                                               float* __restrict__ da, long ldda, bf16* __restrict__ dt, long lddt,
                                                               float* __restrict__ dcw, float* __restrict__ dw2, float* __restrict__ db2,
                                                               int HW, int C) {
+  pdl_trigger();
   __shared__ float s_dcw[2][512];
   __shared__ float s_dw2[2][512];
   __shared__ float s_db2[2];

@@ -131,7 +131,7 @@ struct TcSched {
   long total_tiles;
   long sC1, sC2;  // element strides of C per batch index
   int tma_store;  // 0 = per-thread global stores (atomics / odd layouts), 1 = smem-staged TMA bulk store
-  long long* trace;  // debug: CTA 0 writes clock64 stamps [role][tile][4] (role 0 producer, 1 mma, 2 epilogue)
+  long long* trace;  // debug: CTA 0 writes clock64 stamps [role][tile][4] (role 0 producer, 1 mma, 2 epilogue, 3/4 epilogue detail)
 };
 #define TC_TRACE(role, tile, slot)                                                              \
   do {                                                                                          \
@@ -145,6 +145,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
                                                                const __grid_constant__ CUtensorMap tmB,
                                                                const __grid_constant__ CUtensorMap tmC, Epi epi0,
                                                                TcSched sc) {
+  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   constexpr uint32_t A_BYTES = TC_BM * TC_BK * 2;
   constexpr uint32_t B_BYTES = BN * TC_BK * 2;
@@ -190,6 +191,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr));
+  pdl_wait();  // PDL: everything above overlapped the previous kernel's tail; its results are visible from here on
 
   // tile -> (n tile, m tile, batch, split) ; identical arithmetic in all three roles
   auto decode = [&](long tl, int& n0, int& m0, int& b1, int& b2, int& kb_begin, int& nkb, int& split_idx) {
@@ -344,9 +346,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
         auto process = [&](uint32_t* r, int c) {
           const int cc = c % UC;
           const uint32_t buf = my_stage + (nstore & 1u) * 4096u;
+          const bool trc = (warp == 4 && lane == 0);
           if (cc == 0) {
+            if (trc) TC_TRACE(3, lt, 0);
             if (lane == 0) tma_store_wait_read<1>();  // the store that used this buffer two units ago has read it
             __syncwarp();
+            if (trc) TC_TRACE(3, lt, 1);
           }
 #pragma unroll
           for (int g = 0; g < 4; g++) {
@@ -382,15 +387,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
           }
           // last chunk of the unit (or the unit is cut short by N): publish the box
           const bool unit_done = (cc == UC - 1) || (n0 + (c + 1) * 32 >= epi.N);
+          if (trc) TC_TRACE(3, lt, 2 + (cc ? 1 : 0));
           if (unit_done) {
             fence_async_smem();
             __syncwarp();
+            if (trc) TC_TRACE(4, lt, 0);
             if (lane == 0) {
               const int ucol0 = n0 + (c - cc) * 32;
               if (BATCHED) tma_store_4d(&tmC, buf, ucol0, m0 + q * 32, b2, b1);
               else tma_store_2d(&tmC, buf, ucol0, m0 + q * 32);
               tma_store_commit();
             }
+            if (trc) TC_TRACE(4, lt, 1);
             nstore++;
           }
         };
@@ -491,6 +499,7 @@ struct GenArgs {
 constexpr int GB = 64, GK = 32;
 
 __global__ void __launch_bounds__(128) gemm_wmma_kernel(GenArgs g, Epi epi) {
+  pdl_trigger();
   using namespace nvcuda;
   __shared__ __align__(32) bf16 As[GB][GK + 8];
   __shared__ __align__(32) bf16 Bs[GK][GB + 8];
@@ -734,7 +743,17 @@ static int launch_tc(const CmxGemm* g, const Epi& epi, cudaStream_t st) {
   Epi e2 = epi;
   e2.atomic = atomic ? 1 : 0;
   const long grid = sc.total_tiles < num_sms() ? sc.total_tiles : num_sms();
-  kern<<<(unsigned)grid, TC_THREADS, smem, st>>>(tmA, tmB, tmC, e2, sc);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = cmx_use_pdl() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, e2, sc);
   g_cmx_launches++;
   CMX_CHECK_LAUNCH("gemm_tc_kernel");
   return 0;

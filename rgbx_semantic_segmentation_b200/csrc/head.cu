@@ -24,6 +24,7 @@ struct UpSrc {
 __global__ void __launch_bounds__(256) upsample_sum_kernel(const bf16* __restrict__ z0, UpSrc s1, UpSrc s2, UpSrc s3,
                                                            const float* __restrict__ bias, float* __restrict__ out, int B, int H0,
                                                            int W0, int C) {
+  pdl_trigger();
   const int c8 = C >> 3;
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const long total = (long)B * H0 * W0 * c8;
@@ -81,6 +82,7 @@ CMX_API int cmx_upsample_sum_fwd(const void* z0, const void* z1, const void* z2,
 // ---- adjoint of one bilinear source (gather over the output pixels whose stencil touches (yi,xi)) -------
 __global__ void __launch_bounds__(256) upsample_bwd_kernel(const bf16* __restrict__ dout, int Ho, int Wo, bf16* __restrict__ dz, int Hi,
                                                            int Wi, int B, int C, float sh, float sw) {
+  pdl_trigger();
   const int c8 = C >> 3;
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const long total = (long)B * Hi * Wi * c8;
@@ -140,6 +142,7 @@ constexpr int CE_TW = 32, CE_TH = 8;
 __global__ void __launch_bounds__(256) ce_upsampled_kernel(const float* __restrict__ logits, const int64_t* __restrict__ label,
                                                            int ignore_index, double* __restrict__ acc, float* __restrict__ dlogits,
                                                            int h, int w, int H, int W, int ncls, float sh, float sw, int cap) {
+  pdl_trigger();
   extern __shared__ float s_dyn[];  // [cap] low-res logits window, [cap] gradient accumulator
   float* s_l = s_dyn;
   float* s_g = s_dyn + cap;
@@ -256,6 +259,7 @@ template <typename TO>
 __global__ void __launch_bounds__(256) ce_finalize_kernel(const double* __restrict__ acc, float* __restrict__ loss,
                                                           const float* __restrict__ dlogits, const float* __restrict__ gscale,
                                                           TO* __restrict__ out, long n) {
+  pdl_trigger();
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i == 0 && loss) *loss = (float)(acc[0] / acc[1]);  // all-ignored batch -> 0/0 = NaN, like torch
   if (i < n && out) {
@@ -274,6 +278,7 @@ CMX_API int cmx_ce_finalize(const double* acc, float* loss, const float* dlogits
 // ---- eval: low-res channels-last logits -> full-res NCHW ------------------------------------------------
 __global__ void __launch_bounds__(256) logits_upsample_nchw_kernel(const float* __restrict__ logits, float* __restrict__ out, int B, int h,
                                                                    int w, int H, int W, int ncls, float sh, float sw) {
+  pdl_trigger();
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const long total = (long)B * H * W;
   if (idx >= total) return;
@@ -305,6 +310,7 @@ constexpr int CF_MAXCL = 64;  // n_cl^2 <= 4096 shared-memory bins
 template <typename TP, typename TG>
 __global__ void __launch_bounds__(256) confusion_kernel(const TP* __restrict__ pred, const TG* __restrict__ gt, long n, int n_cl,
                                                         unsigned long long* __restrict__ hist, unsigned long long* __restrict__ stats) {
+  pdl_trigger();
   __shared__ unsigned int sh[CF_MAXCL * CF_MAXCL];
   __shared__ unsigned int s_lab, s_cor;
   for (int i = threadIdx.x; i < n_cl * n_cl; i += blockDim.x) sh[i] = 0;
@@ -357,6 +363,7 @@ template <typename TG>
 __global__ void __launch_bounds__(256) argmax_confusion_kernel(const float* __restrict__ scores, const TG* __restrict__ gt, long npix,
                                                                int n_cl, uint8_t* __restrict__ pred_out,
                                                                unsigned long long* __restrict__ hist, unsigned long long* __restrict__ stats) {
+  pdl_trigger();
   __shared__ unsigned int sh[CF_MAXCL * CF_MAXCL];
   __shared__ unsigned int s_lab, s_cor;
   for (int i = threadIdx.x; i < n_cl * n_cl; i += blockDim.x) sh[i] = 0;

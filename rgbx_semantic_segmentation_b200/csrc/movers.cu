@@ -16,6 +16,7 @@ extern std::atomic<long long> g_cmx_launches;
 // ---- stage-1 im2col from the NCHW fp32 image ------------------------------------------------------
 __global__ void __launch_bounds__(256) im2col_nchw_kernel(const float* __restrict__ x, bf16* __restrict__ col, int B, int Cin, int H,
                                                           int W, int k, int s, int p, int Ho, int Wo, int kpad) {
+  pdl_trigger();
   // one thread = 8 consecutive im2col columns of one output pixel (one 16-byte store)
   const int g8 = kpad >> 3;
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -52,6 +53,7 @@ CMX_API int cmx_im2col_nchw(const float* x, void* col, int B, int Cin, int H, in
 // ---- NHWC bf16 im2col (8 channels per thread) ------------------------------------------------------
 __global__ void __launch_bounds__(256) im2col_nhwc_kernel(const bf16* __restrict__ x, long ldx, bf16* __restrict__ col, int B, int H,
                                                           int W, int C, int k, int s, int p, int Ho, int Wo) {
+  pdl_trigger();
   const int c8 = C >> 3;
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const long total = (long)B * Ho * Wo * k * k * c8;
@@ -83,6 +85,7 @@ template <typename TA, typename TO>
 __global__ void __launch_bounds__(256) col2im_nhwc_kernel(const bf16* __restrict__ dcol, const TA* __restrict__ add, long ldadd,
                                                           TO* __restrict__ dx, long lddx, int B, int H, int W, int C, int k, int s,
                                                           int p, int Ho, int Wo) {
+  pdl_trigger();
   const int c8 = C >> 3;
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const long total = (long)B * H * W * c8;
@@ -132,6 +135,7 @@ CMX_API int cmx_col2im_nhwc(const void* dcol, const void* add, int add_dtype, in
 
 // ---- conv weight pack / grad unpack ------------------------------------------------------------------
 __global__ void convw_pack_kernel(const float* __restrict__ w, bf16* __restrict__ wp, int Co, int Ci, int kh, int kw, int kpad) {
+  pdl_trigger();
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long)Co * kpad) return;
   const int j = (int)(idx % kpad);
@@ -149,6 +153,7 @@ CMX_API int cmx_convw_pack(const float* w, void* wp, int Co, int Ci, int kh, int
   LAUNCH_DONE("convw_pack");
 }
 __global__ void convw_unpack_grad_kernel(const float* __restrict__ gp, float* __restrict__ gw, int Co, int Ci, int kh, int kw, int kpad) {
+  pdl_trigger();
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const int K = kh * kw * Ci;
   if (idx >= (long)Co * K) return;
@@ -165,6 +170,7 @@ CMX_API int cmx_convw_unpack_grad(const float* gp, float* gw, int Co, int Ci, in
 
 // ---- casts / axpby -----------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ y, long n) {
+  pdl_trigger();
   const long i = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
   if (i + 8 <= n) {
     float f[8];
@@ -181,6 +187,7 @@ CMX_API int cmx_cast_f32_bf16(const float* x, void* y, int64_t n, void* stream) 
   LAUNCH_DONE("cast_f32_bf16");
 }
 __global__ void __launch_bounds__(256) cast_bf16_f32_kernel(const bf16* __restrict__ x, float* __restrict__ y, long n) {
+  pdl_trigger();
   const long i = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
   if (i + 8 <= n) {
     float f[8];
@@ -198,6 +205,7 @@ CMX_API int cmx_cast_bf16_f32(const void* x, float* y, int64_t n, void* stream) 
 }
 __global__ void __launch_bounds__(256) axpby_kernel(float a, const float* __restrict__ x, float b, const float* __restrict__ y,
                                                     float* __restrict__ out, long n) {
+  pdl_trigger();
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float v = a * x[i];
@@ -214,6 +222,7 @@ CMX_API int cmx_axpby_f32(float a, const float* x, float b, const float* y, floa
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, long ldx, float* __restrict__ out, long M, int N,
                                                      int rows_per_cta) {
+  pdl_trigger();
   __shared__ float s1[8][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + tx;
@@ -235,6 +244,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, lo
 // 8 columns (one 16-byte load) per thread; block = NG column groups x (256/NG) row lanes
 __global__ void __launch_bounds__(256) colsum_vec8_kernel(const bf16* __restrict__ x, long ldx, float* __restrict__ out, long M, int N,
                                                           int ng, int rows_per_cta) {
+  pdl_trigger();
   __shared__ float sacc[256][9];
   const int tid = threadIdx.x;
   const int cg = tid % ng, rl = tid / ng, nrl = 256 / ng;
@@ -304,6 +314,7 @@ CMX_API int cmx_colsum(const void* x, int x_dtype, int64_t ldx, float* out, int6
 // ---- ReLU backward in place ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) relu_bwd_kernel(bf16* __restrict__ dy, long lddy, const bf16* __restrict__ y, long ldy, long M,
                                                        int N) {
+  pdl_trigger();
   const int n8 = N >> 3;
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= M * n8) return;
@@ -327,6 +338,7 @@ CMX_API int cmx_relu_bwd(void* dy, int64_t lddy, const void* y, int64_t ldy, int
 constexpr int SM_MAXJ = 32;
 __global__ void __launch_bounds__(256) softmax_rows_fwd_kernel(const float* __restrict__ s, long lds, bf16* __restrict__ p, long ldp,
                                                                long rows, int n) {
+  pdl_trigger();
   const int lane = threadIdx.x & 31;
   const long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -364,6 +376,7 @@ CMX_API int cmx_softmax_rows_fwd(const float* s, int64_t lds, void* p, int64_t l
 __global__ void __launch_bounds__(256) softmax_rows_bwd_kernel(const bf16* __restrict__ p, long ldp, const float* __restrict__ dp,
                                                                long lddp, float scale, bf16* __restrict__ ds, long ldds, long rows,
                                                                int n) {
+  pdl_trigger();
   const int lane = threadIdx.x & 31;
   const long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -393,6 +406,7 @@ CMX_API int cmx_softmax_rows_bwd(const void* p, int64_t ldp, const float* dp, in
 
 // ---- softmax over dim -2 of [nb, d, d] (FFM context, d = 64): thread per column ------------------------
 __global__ void softmax_dim2_fwd_kernel(const float* __restrict__ c, float scale, float* __restrict__ p32, bf16* __restrict__ p16, int d) {
+  pdl_trigger();
   const int col = threadIdx.x;
   const long base = (long)blockIdx.x * d * d;
   if (col >= d) return;
@@ -414,6 +428,7 @@ CMX_API int cmx_softmax_dim2_fwd(const float* c, float scale, float* p32, void* 
   LAUNCH_DONE("softmax_dim2_fwd");
 }
 __global__ void softmax_dim2_bwd_kernel(const float* __restrict__ p32, const float* __restrict__ dp, float scale, bf16* __restrict__ dc16, int d) {
+  pdl_trigger();
   const int col = threadIdx.x;
   const long base = (long)blockIdx.x * d * d;
   if (col >= d) return;

@@ -15,6 +15,7 @@ template <typename TX, typename TY>
 __global__ void __launch_bounds__(256) ln_fwd_kernel(const TX* __restrict__ x, long ldx, const float* __restrict__ gamma,
                                                      const float* __restrict__ beta, float eps, TY* __restrict__ y, long ldy,
                                                      float* __restrict__ mean, float* __restrict__ rstd, long M, int C) {
+  pdl_trigger();
   const int lane = threadIdx.x & 31;
   const long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= M) return;
@@ -79,6 +80,7 @@ template <typename TX, typename TY, int G, int J>
 __global__ void __launch_bounds__(256) ln_fwd_v2_kernel(const TX* __restrict__ x, long ldx, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, float eps, TY* __restrict__ y, long ldy,
                                                         float* __restrict__ mean, float* __restrict__ rstd, long M, int C) {
+  pdl_trigger();
   constexpr int RPW = 32 / G;
   const int lane = threadIdx.x & 31;
   const int lg = lane % G;
@@ -138,6 +140,7 @@ __global__ void __launch_bounds__(256) ln_bwd_v2_kernel(const TDY* __restrict__ 
                                                         bf16* __restrict__ dxbf, long lddxbf, const float* __restrict__ scale,
                                                         int rows_per_sample, float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                         float* __restrict__ dbias, long M, int C) {
+  pdl_trigger();
   constexpr int RPW = 32 / G;
   __shared__ float sh_g[512];
   __shared__ float sh_b[512];
@@ -327,6 +330,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const TDY* __restrict__ dy,
                                                      bf16* __restrict__ dxbf, long lddxbf, const float* __restrict__ scale,
                                                      int rows_per_sample, float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                      long M, int C) {
+  pdl_trigger();
   __shared__ float sh_g[1024];
   __shared__ float sh_b[1024];
   const int lane = threadIdx.x & 31;
@@ -485,6 +489,7 @@ CMX_API int cmx_layernorm_bwd(const void* dy, int dy_dtype, int64_t lddy, const 
 template <typename T>
 __global__ void __launch_bounds__(256) colstats_kernel(const T* __restrict__ x, long ldx, double* __restrict__ sum,
                                                        double* __restrict__ sumsq, long M, int C, int rows_per_cta) {
+  pdl_trigger();
   __shared__ float s1[8][33], s2[8][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + tx;
@@ -525,6 +530,7 @@ CMX_API int cmx_colstats(const void* x, int x_dtype, int64_t ldx, double* sum, d
 
 __global__ void bn_finalize_kernel(const double* sum, const double* sumsq, long count, float eps, float momentum,
                                    float* running_mean, float* running_var, int64_t* nbt, float* mean, float* invstd, int C) {
+  pdl_trigger();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c == 0 && nbt) *nbt += 1;
   if (c >= C) return;
@@ -551,6 +557,7 @@ CMX_API int cmx_bn_finalize(const double* sum, const double* sumsq, int64_t coun
 }
 
 __global__ void bn_eval_stats_kernel(const float* rm, const float* rv, float eps, float* mean, float* invstd, int C) {
+  pdl_trigger();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   mean[c] = rm[c];
@@ -573,6 +580,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const TX* __restrict__ x,
                                                        const float* __restrict__ beta, const TR* __restrict__ res, long ldr,
                                                        int relu, const float* __restrict__ mask, int rows_per_sample,
                                                        TY* __restrict__ y, long ldy, long M, int C) {
+  pdl_trigger();
   const int c4 = C >> 2;
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= M * c4) return;
@@ -663,6 +671,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const TDY* __restric
                                                             const TR* __restrict__ res, long ldr, int relu,
                                                             const float* __restrict__ mask, int rps, double* __restrict__ sum_dy,
                                                             double* __restrict__ sum_dy_xhat, long M, int C, int rows_per_cta) {
+  pdl_trigger();
   __shared__ float s1[8][33], s2[8][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + tx;
@@ -700,6 +709,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const TDY* __restrict
                                                            const double* __restrict__ sum_dy, const double* __restrict__ sum_dy_xhat,
                                                            TDX* __restrict__ dx, long lddx, TDX* __restrict__ dres, long lddres,
                                                            float* __restrict__ dgamma, float* __restrict__ dbeta, long M, int C) {
+  pdl_trigger();
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx < C && blockIdx.y == 0 && dgamma) {
     // fold the parameter gradients into the first C threads of the grid

@@ -3,6 +3,7 @@
 #pragma once
 #include "common.cuh"
 #include <cuda.h>
+#include <stdlib.h>
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -106,6 +107,16 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+// host: PDL launches can be disabled with CMX_PDL=0 (debugging)
+static inline bool cmx_use_pdl() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("CMX_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
 }
 
 // host: driver entry point for tensor-map encoding (no libcuda link dependency)

@@ -54,6 +54,10 @@ class Engine:
         self.stochastic = True       # DropPath / Dropout2d active in training mode
         self.trace = None            # debug hook: dict filled with fp32 copies of intermediate activations
         self.fused_attention = os.environ.get("CMX_FUSED_ATTENTION", "1") != "0"
+        # the RGB and X branch chains of a stage are independent until the FRM: run them on two streams (fork/join is
+        # captured into the CUDA graph as two parallel branches) so the small stage-3/4 kernels overlap
+        self.dual_stream = os.environ.get("CMX_DUAL_STREAM", "1") != "0"
+        self._side = None
         self.poison = None           # debug hook: list of (tensor, allocation site) when NaN-poisoning is on
 
     # ------------------------------------------------------------------------------------------
@@ -698,20 +702,33 @@ class Engine:
             C = self.dims[s]
             st = _NS()
             st.blocks = [[], []]
-            st.pe = []
-            xs = []
-            for br, (pe_name, blk_name) in enumerate((("patch_embed", "block"), ("extra_patch_embed", "extra_block"))):
-                x0, Ho, Wo, cpe = self.pe_fwd(f"backbone.{pe_name}{s + 1}", inp[br], s, B, Hc, Wc, save)
-                st.pe.append(cpe)
+            xs = [None, None]
+            st.pe = [None, None]
+            hw = [None, None]
+
+            def run_branch(br):
+                pe_name, blk_name = (("patch_embed", "block"), ("extra_patch_embed", "extra_block"))[br]
+                x0, Ho_, Wo_, cpe = self.pe_fwd(f"backbone.{pe_name}{s + 1}", inp[br], s, B, Hc, Wc, save)
+                st.pe[br] = cpe
                 self.tr(f"backbone.{pe_name}{s + 1}", x0)
                 xcur = x0
                 for i in range(self.depths[s]):
                     bp = f"backbone.{blk_name}{s + 1}.{i}"
-                    xcur, cb = self.block_fwd(bp, xcur, B, Ho, Wo, s, dp.get(bp), save)
+                    xcur, cb = self.block_fwd(bp, xcur, B, Ho_, Wo_, s, dp.get(bp), save)
                     self.tr(bp, xcur)
                     if save:
                         st.blocks[br].append(cb)
-                xs.append(xcur)
+                xs[br] = xcur
+                hw[br] = (Ho_, Wo_)
+
+            with self._fork_join() as side:
+                if side is not None:
+                    with torch.cuda.stream(side):
+                        run_branch(1)
+                else:
+                    run_branch(1)
+                run_branch(0)
+            Ho, Wo = hw[0]
             N = Ho * Wo
             M = B * N
             cat12 = self.E(M, 2 * C)
@@ -736,6 +753,29 @@ class Engine:
             inp = [r1, r2]
             Hc, Wc = Ho, Wo
         return feats, sizes, ctx
+
+    def _fork_join(self):
+        """context manager: yields a side stream that has waited for the current stream (or None when disabled);
+        on exit the current stream waits for the side stream.  Works eagerly and under CUDA-graph capture."""
+        eng = self
+
+        class _FJ:
+            def __enter__(self_):
+                if not eng.dual_stream:
+                    self_.side = None
+                    return None
+                if eng._side is None or eng._side.device != eng.dev:
+                    eng._side = torch.cuda.Stream(device=eng.dev)
+                self_.main = torch.cuda.current_stream(eng.dev)
+                self_.side = eng._side
+                self_.side.wait_stream(self_.main)
+                return self_.side
+
+            def __exit__(self_, *exc):
+                if self_.side is not None:
+                    self_.main.wait_stream(self_.side)
+                return False
+        return _FJ()
 
     def forward_logits(self, rgb, x):
         """eval / inference path: full-resolution NCHW fp32 logits (builder.py:212-238)"""
@@ -784,8 +824,10 @@ class Engine:
                 for br in (0, 1):
                     ops.col2im_nhwc(pending[br], dr[br], B, st.H, st.W, 3, 2, 1, nH, nW, add=dr[br])
             dcat = self.frm_bwd(st.frm, dr[0], dr[1], B, N)
-            pending = []
-            for br, (nname, blk_name) in enumerate((("norm", "block"), ("extra_norm", "extra_block"))):
+            pending = [None, None]
+
+            def bwd_branch(br):
+                nname = ("norm", "extra_norm")[br]
                 blocks = st.blocks[br]
                 last = blocks[-1]
                 dx = self.E(B * N, C, dtype=f32)
@@ -801,7 +843,15 @@ class Engine:
                     dx, dx_bf = self.block_bwd(blocks[i], dx, dx_bf, B, prev_scale, need_bf=(i > 0),
                                                prev_fc2_bias=None if prev is None else prev.p + ".mlp.fc2.bias")
                     blocks[i] = None
-                pending.append(self.pe_bwd(st.pe[br], dx, B))
+                pending[br] = self.pe_bwd(st.pe[br], dx, B)
+
+            with self._fork_join() as side:      # dcat (allocated on the main stream) stays referenced until the join
+                if side is not None:
+                    with torch.cuda.stream(side):
+                        bwd_branch(1)
+                else:
+                    bwd_branch(1)
+                bwd_branch(0)
             if s == 0:
                 pending = None
             ctx.stages[s] = None
