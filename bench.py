@@ -141,7 +141,11 @@ def cpu_reference_rate(steps, warmup, threads=None):
         if i >= warmup:
             times.append(time.perf_counter() - t0)
     total = sum(times)
-    return {"value": len(times) / total, "unit": UNIT, "cores": threads, "kind": "port",
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        cmx_ref.forward(sd, spec, rgb, x, training=False)
+        t_inf = time.perf_counter() - t0
+    return {"value": len(times) / total, "unit": UNIT, "cores": threads, "kind": "port", "inference_img_s": 1.0 / t_inf,
             "sample": "%d steps of batch 1 (fwd+bwd+AdamW, fp32 oracle port of the reference, %d threads) after %d warm-up"
                       % (len(times), threads, warmup), "ms_per_step": 1e3 * total / len(times)}
 
@@ -282,10 +286,31 @@ def main_ours(args):
                 for k, (t, n, fl, nb) in top:
                     f.write("%s,%d,%.3f,%.4f,%.1f,%.1f,%.2f\n" % (k, n, t, t / total, 1e3 * t / n, nb / (t * 1e-3) / 1e9 if t else 0,
                                                                  fl / (t * 1e-3) / 1e12 if t else 0))
+    # ---------------- inference (eval mode, no_grad): batch-8 throughput and batch-1 latency (evaluator.py:381-391 call shape)
+    infer = None
+    if rank == 0:
+        model.eval()
+        infer = {}
+        with torch.no_grad():
+            for bs in (PER_GPU_BATCH, 1):
+                a_, b_ = rgb[:bs].contiguous(), x[:bs].contiguous()
+                for _ in range(4):
+                    model(a_, b_)
+                torch.cuda.synchronize()
+                i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                n_it = 20
+                i0.record()
+                for _ in range(n_it):
+                    out = model(a_, b_)
+                i1.record()
+                torch.cuda.synchronize()
+                t_ms = i0.elapsed_time(i1) / n_it
+                infer["batch%d" % bs] = {"img_s": bs / (t_ms * 1e-3), "ms_per_forward": t_ms}
+        model.train()
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_reference_rate(3, 1)
-        cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample", "inference_img_s")}
     if rank == 0:
         gb = B * world
         line = {"metric": METRIC, "value": gb * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -302,6 +327,7 @@ def main_ours(args):
                         "h2d_bytes_per_step": int(hr.numel() * 4 + hx.numel() * 4 + hg.numel() * 8), "d2h_bytes_per_step": 4},
                 "gpu_launches": int(launches_per_step * args.steps) if launches_per_step else 0,
                 "gpu_launches_per_step": launches_per_step, "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
+                "inference": infer,
                 "last_loss": last,
                 "top_kernels": [{"kernel": k, "launches": v[1], "ms": round(v[0], 3)} for k, v in top[:8]]}
         print(json.dumps(line), flush=True)

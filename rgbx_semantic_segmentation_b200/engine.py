@@ -58,6 +58,11 @@ class Engine:
         # captured into the CUDA graph as two parallel branches) so the small stage-3/4 kernels overlap
         self.dual_stream = os.environ.get("CMX_DUAL_STREAM", "1") != "0"
         self._side = None
+        # weight-gradient GEMMs never feed the backward chain: they run on a companion stream of whichever stream
+        # computes the data gradients and are joined at the end of each module's backward
+        self.wgrad_stream = os.environ.get("CMX_WGRAD_STREAM", "1") != "0"
+        self._wstreams = {}
+        self._wkeep = {}
         self.poison = None           # debug hook: list of (tensor, allocation site) when NaN-poisoning is on
 
     # ------------------------------------------------------------------------------------------
@@ -168,11 +173,49 @@ class Engine:
         if self.trace is not None:
             self.trace[key] = t.detach().float().clone()
 
+    # ---- companion weight-gradient stream ---------------------------------------------------------
+    def _wgrad_ctx(self, *keep):
+        """context manager: work issued inside runs on the companion stream of the current stream after everything
+        already enqueued on the current stream; `keep` tensors stay referenced until the matching _wgrad_join()."""
+        eng = self
+
+        class _W:
+            def __enter__(self_):
+                self_.ctx = None
+                if not eng.wgrad_stream:
+                    return
+                cur = torch.cuda.current_stream(eng.dev)
+                key = cur.cuda_stream
+                ws = eng._wstreams.get(key)
+                if ws is None:
+                    ws = eng._wstreams[key] = torch.cuda.Stream(device=eng.dev)
+                eng._wkeep.setdefault(key, []).extend(keep)
+                ws.wait_stream(cur)
+                self_.ctx = torch.cuda.stream(ws)
+                self_.ctx.__enter__()
+
+            def __exit__(self_, *exc):
+                if self_.ctx is not None:
+                    self_.ctx.__exit__(*exc)
+                return False
+        return _W()
+
+    def _wgrad_join(self):
+        """the current stream waits for its companion weight-gradient stream; operand keep-alives are released"""
+        if not self.wgrad_stream:
+            return
+        cur = torch.cuda.current_stream(self.dev)
+        ws = self._wstreams.get(cur.cuda_stream)
+        if ws is not None:
+            cur.wait_stream(ws)
+        self._wkeep.pop(cur.cuda_stream, None)
+
     def linear_wgrad(self, dy, x, wname, bname=None):
-        """dW[out,in] += dy[tok,out]^T x[tok,in];  db += colsum(dy)"""
-        ops.mm(dy, x, self.G2(wname), ta=True, tb=True, accumulate=True)
-        if bname is not None:
-            ops.colsum(dy, self.G(bname))
+        """dW[out,in] += dy[tok,out]^T x[tok,in];  db += colsum(dy)   (on the companion stream)"""
+        with self._wgrad_ctx(dy, x):
+            ops.mm(dy, x, self.G2(wname), ta=True, tb=True, accumulate=True)
+            if bname is not None:
+                ops.colsum(dy, self.G(bname))
 
     # ------------------------------------------------------------------------------------------
     # stochastic-depth / dropout multipliers
@@ -234,13 +277,16 @@ class Engine:
         ops.layernorm_bwd(dx0, c.y, c.mean, c.rstd, self.P(name + ".norm.weight"), dx=dy,
                           dgamma=self.G(name + ".norm.weight"), dbeta=self.G(name + ".norm.bias"),
                           dbias=self.G(name + ".proj.bias"))   # conv bias gradient = column sums of dy, folded in
-        gp = self.Z(C, c.wp.shape[1])
-        ops.mm(dy, c.col, gp, ta=True, tb=True, accumulate=True)
-        ops.convw_unpack_grad(gp, self.G(name + ".proj.weight"))
-        if c.s == 0:
-            return None
-        dcol = self.E(M, c.wp.shape[1])
-        ops.mm(dy, c.wp, dcol, tb=True)
+        with self._wgrad_ctx(dy, c.col):
+            gp = self.Z(C, c.wp.shape[1])
+            ops.mm(dy, c.col, gp, ta=True, tb=True, accumulate=True)
+            ops.convw_unpack_grad(gp, self.G(name + ".proj.weight"))
+            del gp
+        dcol = None
+        if c.s != 0:
+            dcol = self.E(M, c.wp.shape[1])
+            ops.mm(dy, c.wp, dcol, tb=True)
+        self._wgrad_join()
         return dcol
 
     # ------------------------------------------------------------------------------------------
@@ -390,9 +436,11 @@ class Engine:
                               dgamma=self.G(p + ".attn.norm.weight"), dbeta=self.G(p + ".attn.norm.bias"),
                               dbias=self.G(p + ".attn.sr.bias"))
             wsr = self.packed[p + ".attn.sr.weight"]
-            gp = self.Z(C, wsr.shape[1])
-            ops.mm(dsr, c.pat, gp, ta=True, tb=True, accumulate=True)
-            ops.convw_unpack_grad(gp, self.G(p + ".attn.sr.weight"))
+            with self._wgrad_ctx(dsr, c.pat):
+                gp = self.Z(C, wsr.shape[1])
+                ops.mm(dsr, c.pat, gp, ta=True, tb=True, accumulate=True)
+                ops.convw_unpack_grad(gp, self.G(p + ".attn.sr.weight"))
+                del gp
             dpat = self.E(B * Nk, wsr.shape[1])
             ops.mm(dsr, wsr, dpat, tb=True)
             dxn_b = self.E(M, C)
@@ -408,6 +456,7 @@ class Engine:
                           scale=prev_scale, rows_per_sample=N,
                           dgamma=self.G(p + ".norm1.weight"), dbeta=self.G(p + ".norm1.bias"),
                           dbias=None if prev_fc2_bias is None else self.G(prev_fc2_bias))
+        self._wgrad_join()
         return dx, dx_bf
 
     # ------------------------------------------------------------------------------------------
@@ -454,6 +503,7 @@ class Engine:
         ops.smallm_linear_bwd(dhid, c.hid, ACT_RELU, c.y, self.P(p + ".channel_weights.mlp.0.weight"), dy,
                               self.G(p + ".channel_weights.mlp.0.weight"), self.G(p + ".channel_weights.mlp.0.bias"), ws)
         ops.pool_avgmax_bwd(dy, c.am, dcat, B, HW)
+        self._wgrad_join()
         return dcat
 
     # ------------------------------------------------------------------------------------------
@@ -608,15 +658,17 @@ class Engine:
             ops.relu_bwd_(dy_i, c.yv[i][:, :C])
             wname, bname = p + f".cross.channel_proj{i + 1}.weight", p + f".cross.channel_proj{i + 1}.bias"
             gw, gb = self.G2(wname), self.G(bname)
-            ops.mm(dy_i, c.r[i], gw[:C], ta=True, tb=True, accumulate=True)
-            ops.mm(du[i], c.r[i], gw[C:], ta=True, tb=True, accumulate=True)
-            ops.colsum(dy_i, gb[:C])
-            ops.colsum(du[i], gb[C:])
+            with self._wgrad_ctx(dyv[i], du[i], c.r[i]):
+                ops.mm(dy_i, c.r[i], gw[:C], ta=True, tb=True, accumulate=True)
+                ops.mm(du[i], c.r[i], gw[C:], ta=True, tb=True, accumulate=True)
+                ops.colsum(dy_i, gb[:C])
+                ops.colsum(du[i], gb[C:])
             wcp = self.W(wname)
             dr_i = self.E(M, C, dtype=f32)
             ops.mm(dy_i, wcp[:C], dr_i, tb=True, residual=de[i])
             ops.mm(du[i], wcp[C:], dr_i, tb=True, residual=dr_i)
             dr.append(dr_i)
+        self._wgrad_join()
         return dr
 
     # ------------------------------------------------------------------------------------------
@@ -678,13 +730,15 @@ class Engine:
                 dz = self.E(Ms, E_)
                 ops.upsample_bwd(dfuse, H0, W0, dz, c.sizes[s][0], c.sizes[s][1], B, E_)
             sl = slice((3 - s) * E_, (4 - s) * E_)
-            ops.mm(dz, c.e[s], gf[:, sl], ta=True, tb=True, accumulate=True)
+            with self._wgrad_ctx(dz, c.e[s]):
+                ops.mm(dz, c.e[s], gf[:, sl], ta=True, tb=True, accumulate=True)
             de = self.E(Ms, E_)
             ops.mm(dz, wf[:, sl], de, tb=True)
             self.linear_wgrad(de, c.feats[s], p + f".linear_c{s + 1}.proj.weight", p + f".linear_c{s + 1}.proj.bias")
             df = self.E(Ms, c.feats[s].shape[1])
             ops.mm(de, self.W(p + f".linear_c{s + 1}.proj.weight"), df, tb=True)
             dfs.append(df)
+        self._wgrad_join()
         return dfs
 
     # ------------------------------------------------------------------------------------------
