@@ -162,7 +162,7 @@ def main_reference(args):
             "config": {"workload": "CMX MiT-B2 RGB-T MFNet shape (480x640, 9 classes) training step on the host CPU, batch 1 per step"},
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -330,12 +330,31 @@ def main_ours(args):
                 "inference": infer,
                 "last_loss": last,
                 "top_kernels": [{"kernel": k, "launches": v[1], "ms": round(v[0], 3)} for k, v in top[:8]]}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def _protect_stdout():
+    """Libraries (NCCL's version banner, torchrun warnings) print to fd 1; the contract is ONE JSON line on stdout.
+    Route fd 1 to stderr for the duration of the run and keep a private handle for the final line."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 if __name__ == "__main__":
+    _protect_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

@@ -227,3 +227,35 @@ def test_metric_dropin_bit_exact(golden_dir):
         assert np.array_equal(np.asarray(sc[1:], dtype=np.float64), z[f"c{i}_scores"], equal_nan=True)
         i += 1
     assert i == 4
+
+
+def test_full_size_training_step_vs_oracle():
+    """BASELINE.json configs[1] shape (MiT-B2, 480x640, 9 classes) at batch 2: loss and gradients vs the fp32 oracle."""
+    spec = cmx_ref.MIT_SPECS["mit_b2"]
+    sd = synth_state_dict(spec, 9, seed=0)
+    rgb, x, gt = synth_inputs(2, 480, 640, 9, seed=1)
+    m = make("mit_b2", 9, True, sd).train()
+    m._eng().stochastic = False
+    loss = m(rgb.cuda(), x.cuda(), gt.cuda())
+    loss.backward()
+    torch.set_num_threads(os.cpu_count() or 1)
+    params = {k: v.clone().requires_grad_(v.is_floating_point() and not k.endswith(("running_mean", "running_var")))
+              for k, v in sd.items()}
+    ref = cmx_ref.forward(params, spec, rgb, x, gt, training=True, decoder_bn_eps=1e-3)
+    ref.backward()
+    assert abs(loss.item() - ref.item()) <= 5e-3 * abs(ref.item()), (loss.item(), ref.item())
+    grads_vs(m, {n: params[n].grad for n, _ in m.named_parameters()}, "b2 480x640 batch 2")
+
+
+def test_mit_b4_pst900_shape_eval_vs_oracle():
+    """BASELINE.json configs[3] shape: MiT-B4, 720x1280, 5 classes (Nkv = 880/920 > 320 -> unfused attention path,
+    non-integer 23x40 -> 180x320 bilinear ratio in the decoder)."""
+    spec = cmx_ref.MIT_SPECS["mit_b4"]
+    sd = synth_state_dict(spec, 5, seed=0)
+    rgb, x, _ = synth_inputs(1, 720, 1280, 5, seed=1)
+    m = make("mit_b4", 5, False, sd).eval()
+    out = m(rgb.cuda(), x.cuda()).cpu()
+    torch.set_num_threads(os.cpu_count() or 1)
+    with torch.no_grad():
+        ref = cmx_ref.forward(sd, spec, rgb, x, training=False, decoder_bn_eps=1e-5)
+    check_logits(out[:, :, ::4, ::4], ref[:, :, ::4, ::4], "b4 720x1280")
