@@ -200,16 +200,18 @@ int cmx_upsample_sum_fwd(const void* z0, const void* z1, const void* z2, const v
 int cmx_upsample_bwd(const void* dout, int Ho, int Wo, void* dz, int Hi, int Wi, int B, int C, void* stream);
 
 /* ---- loss / logits / metric (builder.py:233,249; evaluator.py:393; utils/metric.py:8-15) ------- */
-/* low-res logits [B,h,w,ncls] fp32 (channels-last) -> bilinear x to [H,W] -> CE(ignore) .
+/* low-res logits [B,h,w,ncls] fp32 (channels-last, pixel stride ld >= ncls elements: the engine pads the class axis to a
+ * multiple of 8 so the prediction layer runs on the tcgen05 path) -> bilinear x to [H,W] -> CE(ignore).
  * acc[0] += sum of -log p (double), acc[1] += valid count (double). If dlogits != NULL also accumulates the
- * UNNORMALISED gradient sum_{pixels} w * (softmax - onehot) into dlogits [B,h,w,ncls] fp32. */
-int cmx_ce_upsampled_fwd_bwd(const float* logits, const int64_t* label, int ignore_index, double* acc,
+ * UNNORMALISED gradient sum_{pixels} w * (softmax - onehot) into dlogits (fp32, same layout and stride as logits). */
+int cmx_ce_upsampled_fwd_bwd(const float* logits, int64_t ld, const int64_t* label, int ignore_index, double* acc,
                              float* dlogits, int B, int h, int w, int H, int W, int ncls, void* stream);
 /* loss = acc[0]/acc[1];  dlogits_out(bf16/f32) = dlogits * gscale/acc[1] */
 int cmx_ce_finalize(const double* acc, float* loss, const float* dlogits, const float* gscale,
                     void* dlogits_out, int out_dtype, int64_t n, void* stream);
 /* low-res channels-last logits -> full-res NCHW fp32 logits (eval output of EncoderDecoder.forward) */
-int cmx_logits_upsample_nchw(const float* logits, float* out, int B, int h, int w, int H, int W, int ncls, void* stream);
+int cmx_logits_upsample_nchw(const float* logits, int64_t ld, float* out, int B, int h, int w, int H, int W, int ncls,
+                             void* stream);
 /* confusion matrix: hist[n_cl*gt+pred] += 1 for 0<=gt<n_cl (int64), stats[0]=labeled, stats[1]=correct.
  * pred_dtype/gt_dtype: 0 = uint8, 1 = int32, 2 = int64.  */
 int cmx_confusion(const void* pred, int pred_dtype, const void* gt, int gt_dtype, int64_t n, int n_cl,

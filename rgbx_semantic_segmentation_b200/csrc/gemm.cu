@@ -117,13 +117,22 @@ __device__ __forceinline__ void epi_store_vec8(const Epi& e, long row, long col,
 //            running ACROSS tile boundaries, so the loads of tile i+1 overlap the MMAs/epilogue of tile i.
 //   warp 1 = MMA issuer (one elected lane) + TMEM allocator; accumulators are double-buffered in TMEM
 //            (2 x BN fp32 columns) so the MMAs of tile i+1 overlap the epilogue of tile i.
-//   warps 2-9 = epilogue (two warps per TMEM lane quarter, interleaved 32-column chunks):
+//   warps 2.. = epilogue (4 or 8 warps, see tc_epi_warps; with 8, two warps per TMEM lane quarter take interleaved
+//            32-column chunks):
 //            tcgen05.ld -> bias/act/DropPath-scale/residual -> 16-byte stores or fp32 red.add (split-K).
 // ------------------------------------------------------------------------------------------------
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;
-constexpr int TC_EPI_WARPS = 8;
-constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
+// Two CTA shapes.  BN <= 128: 4 epilogue warps (one per TMEM lane quarter), <= 110 KB of shared memory, 2 x BN (<= 256)
+// TMEM columns and <= 168 registers x 192 threads, so TWO CTAs are resident per SM: the epilogue of one overlaps the
+// loads/MMAs/epilogue of the other, and kernels of the other streams (the second modality branch, the weight-gradient
+// companion streams) or the PDL-launched successor can share the SM.  BN > 128: 8 epilogue warps (two per lane quarter,
+// interleaved 32-column chunks), the whole SM.
+__host__ __device__ constexpr int tc_epi_warps(int bn) { return bn <= 128 ? 4 : 8; }
+__host__ __device__ constexpr int tc_threads(int bn) { return 64 + 32 * tc_epi_warps(bn); }
+__host__ __device__ constexpr int tc_ctas_per_sm(int bn) { return bn <= 128 ? 2 : 1; }
+__host__ __device__ constexpr uint32_t tc_cstage_bytes(int bn) { return tc_epi_warps(bn) * 2 * 4096; }  // per epilogue warp: 2 x (32 rows x 128 B)
+__host__ __device__ constexpr int tc_smem_budget(int bn) { return bn <= 128 ? 110 * 1024 : 200 * 1024; }
 
 struct TcSched {
   int tiles_n, tiles_m, batch2, nbatch, splits;
@@ -138,10 +147,9 @@ struct TcSched {
     if (sc.trace && blockIdx.x == 0 && (tile) < 64) sc.trace[((role) * 64 + (tile)) * 4 + (slot)] = clock64(); \
   } while (0)
 
-constexpr uint32_t TC_CSTAGE_BYTES = TC_EPI_WARPS * 2 * 4096;  // per epilogue warp: 2 x (32 rows x 128 B)
 
 template <int BN, bool A_MN, bool B_MN, bool BATCHED>
-__global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+__global__ void __launch_bounds__(tc_threads(BN), tc_ctas_per_sm(BN)) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                const __grid_constant__ CUtensorMap tmB,
                                                                const __grid_constant__ CUtensorMap tmC, Epi epi0,
                                                                TcSched sc) {
@@ -152,6 +160,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
   constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr uint32_t ACC_STRIDE = BN <= 64 ? 64 : BN <= 128 ? 128 : 256;  // TMEM columns per accumulator buffer
   constexpr uint32_t TMEM_COLS = 2 * ACC_STRIDE;
+  constexpr int TC_EPI_WARPS = tc_epi_warps(BN);
+  constexpr int NH = TC_EPI_WARPS / 4;  // warps per TMEM lane quarter = column interleave factor
+  constexpr uint32_t TC_CSTAGE_BYTES = tc_cstage_bytes(BN);
   const int stages = sc.stages;
 
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -295,10 +306,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
       }
     }
   } else {
-    // ================= epilogue: warps 2..9; TMEM lane quarter = warp % 4, two warps per quarter =================
+    // ================= epilogue: warps 2..; TMEM lane quarter = warp % 4, NH warps per quarter =================
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
-    const int etid = threadIdx.x - 64;  // 0..255
+    const int etid = threadIdx.x - 64;  // 0 .. 32 * TC_EPI_WARPS - 1
     const uint32_t my_stage = cstage_base + (uint32_t)(warp - 2) * 8192u;
     uint32_t lt = 0, nstore = 0;
     for (long t = blockIdx.x; t < sc.total_tiles; t += gridDim.x, lt++) {
@@ -316,12 +327,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
       }
       // bias slice of this tile -> shared memory (double-buffered by tile parity; one named barrier per tile)
       const uint32_t sb_addr = bias_base + (lt & 1u) * 1024u;
-      if (epi.bias && etid < BN) {
-        const float bv = (n0 + etid < epi.N) ? epi.bias[n0 + etid] : 0.f;
-        asm volatile("st.shared.f32 [%0], %1;" ::"r"(sb_addr + 4u * etid), "f"(bv) : "memory");
+      if (epi.bias) {
+        for (int i = etid; i < BN; i += 32 * TC_EPI_WARPS) {
+          const float bv = (n0 + i < epi.N) ? epi.bias[n0 + i] : 0.f;
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(sb_addr + 4u * i), "f"(bv) : "memory");
+        }
       }
       if (warp == 4 && lane == 0) TC_TRACE(2, lt, 0);
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
       const uint32_t acc = lt & 1u, aph = (lt >> 1) & 1u;
       if (warp == 4 && lane == 0) TC_TRACE(2, lt, 1);
       mbar_wait(tfull_bar + 8u * acc, aph);
@@ -335,10 +348,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
         // ---- smem-staged TMA store: warp-private [32 rows x 128 B] boxes, SWIZZLE_128B, double buffered.
         // The tcgen05.ld of chunk k+1 is issued before the math / st.shared of chunk k (two register sets).
         const int UC = epi.c_dtype == CMX_F32 ? 1 : 2;   // chunks per store unit: 32 fp32 or 64 bf16 columns = 128 B
-        // k-th chunk of this warp (units half, half+2, ...), -1 when exhausted; a trailing partial unit
+        // k-th chunk of this warp (units half, half+NH, ...), -1 when exhausted; a trailing partial unit
         // (BN = 160 with bf16) is excluded here and handled by the per-thread store path below
         auto chunk_of = [&](int k) -> int {
-          const int u = half + 2 * (k / UC);
+          const int u = half + NH * (k / UC);
           const int c = u * UC + (k % UC);
           if ((u + 1) * UC * 32 > BN || n0 + c * 32 >= epi.N) return -1;
           return c;
@@ -422,7 +435,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
           // neighbouring tile, so that chunk takes the per-thread store path (done by the warp owning that unit)
           const int c = BN / 32 - 1;
           const int u = c / UC;
-          if ((u & 1) == half && n0 + c * 32 < epi.N) {
+          if ((u % NH) == half && n0 + c * 32 < epi.N) {
             uint32_t r[32];
             tmem_ld32(t_addr + (uint32_t)(c * 32), r);
             tmem_wait_ld();
@@ -446,7 +459,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
         }
       } else {
 #pragma unroll 1
-        for (int c = half; c < BN / 32; c += 2) {
+        for (int c = half; c < BN / 32; c += NH) {
           if (n0 + c * 32 >= epi.N) break;
           uint32_t r[32];
           tmem_ld32(t_addr + (uint32_t)(c * 32), r);
@@ -728,7 +741,8 @@ static int launch_tc(const CmxGemm* g, const Epi& epi, cudaStream_t st) {
     if (rc) return rc;
   }
   constexpr int STAGE_BYTES = (TC_BM + BN) * TC_BK * 2;
-  int stages = (int)((200 * 1024 - (sc.tma_store ? TC_CSTAGE_BYTES : 0)) / STAGE_BYTES);
+  constexpr uint32_t TC_CSTAGE_BYTES = tc_cstage_bytes(BN);
+  int stages = (int)((tc_smem_budget(BN) - 4096 - (sc.tma_store ? TC_CSTAGE_BYTES : 0)) / STAGE_BYTES);
   if (stages > 8) stages = 8;
   if (stages < 2) stages = 2;
   sc.stages = stages;
@@ -738,14 +752,16 @@ static int launch_tc(const CmxGemm* g, const Epi& epi, cudaStream_t st) {
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) CMX_FAIL((int)e, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     attr_done = true;
   }
   Epi e2 = epi;
   e2.atomic = atomic ? 1 : 0;
-  const long grid = sc.total_tiles < num_sms() ? sc.total_tiles : num_sms();
+  const long slots = (long)num_sms() * tc_ctas_per_sm(BN);
+  const long grid = sc.total_tiles < slots ? sc.total_tiles : slots;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
-  cfg.blockDim = dim3(TC_THREADS);
+  cfg.blockDim = dim3(tc_threads(BN));
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];

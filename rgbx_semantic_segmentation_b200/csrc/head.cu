@@ -139,7 +139,7 @@ CMX_API int cmx_upsample_bwd(const void* dout, int Ho, int Wo, void* dz, int Hi,
 constexpr int CE_MAXC = 16;
 constexpr int CE_TW = 32, CE_TH = 8;
 
-__global__ void __launch_bounds__(256) ce_upsampled_kernel(const float* __restrict__ logits, const int64_t* __restrict__ label,
+__global__ void __launch_bounds__(256) ce_upsampled_kernel(const float* __restrict__ logits, long ld, const int64_t* __restrict__ label,
                                                            int ignore_index, double* __restrict__ acc, float* __restrict__ dlogits,
                                                            int h, int w, int H, int W, int ncls, float sh, float sw, int cap) {
   pdl_trigger();
@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(256) ce_upsampled_kernel(const float* __restri
     const int k = i % ncls;
     const int xx = (i / ncls) % nw;
     const int yy = i / (ncls * nw);
-    s_l[i] = logits[(((long)b * h + ly0 + yy) * w + lx0 + xx) * ncls + k];
+    s_l[i] = logits[(((long)b * h + ly0 + yy) * w + lx0 + xx) * ld + k];
     s_g[i] = 0.f;
   }
   __syncthreads();
@@ -237,13 +237,14 @@ __global__ void __launch_bounds__(256) ce_upsampled_kernel(const float* __restri
       const int xx = (i / ncls) % nw;
       const int yy = i / (ncls * nw);
       const float g = s_g[i];
-      if (g != 0.f) atomicAdd(dlogits + (((long)b * h + ly0 + yy) * w + lx0 + xx) * ncls + k, g);
+      if (g != 0.f) atomicAdd(dlogits + (((long)b * h + ly0 + yy) * w + lx0 + xx) * ld + k, g);
     }
   }
 }
-CMX_API int cmx_ce_upsampled_fwd_bwd(const float* logits, const int64_t* label, int ignore_index, double* acc, float* dlogits, int B,
-                                     int h, int w, int H, int W, int ncls, void* stream) {
+CMX_API int cmx_ce_upsampled_fwd_bwd(const float* logits, int64_t ld, const int64_t* label, int ignore_index, double* acc,
+                                     float* dlogits, int B, int h, int w, int H, int W, int ncls, void* stream) {
   CMX_REQUIRE(ncls >= 1 && ncls <= CE_MAXC, "ce: ncls=%d > %d unsupported", ncls, CE_MAXC);
+  CMX_REQUIRE(ld >= ncls, "ce: row stride %ld < ncls %d", (long)ld, ncls);
   CMX_REQUIRE(H >= h && W >= w, "ce: only upsampling supported");
   if (B == 0) return 0;
   const float sh = (float)h / (float)H, sw = (float)w / (float)W;
@@ -252,7 +253,7 @@ CMX_API int cmx_ce_upsampled_fwd_bwd(const float* logits, const int64_t* label, 
   const size_t smem = (size_t)cap * 2 * sizeof(float);
   CMX_REQUIRE(smem <= 48 * 1024, "ce: low-res window too large for shared memory");
   dim3 grid(cdiv(W, CE_TW), cdiv(H, CE_TH), B), block(32, 8);
-  ce_upsampled_kernel<<<grid, block, smem, (cudaStream_t)stream>>>(logits, label, ignore_index, acc, dlogits, h, w, H, W, ncls, sh, sw, cap);
+  ce_upsampled_kernel<<<grid, block, smem, (cudaStream_t)stream>>>(logits, (long)ld, label, ignore_index, acc, dlogits, h, w, H, W, ncls, sh, sw, cap);
   LAUNCH_DONE("ce_upsampled_fwd_bwd");
 }
 template <typename TO>
@@ -276,7 +277,7 @@ CMX_API int cmx_ce_finalize(const double* acc, float* loss, const float* dlogits
 }
 
 // ---- eval: low-res channels-last logits -> full-res NCHW ------------------------------------------------
-__global__ void __launch_bounds__(256) logits_upsample_nchw_kernel(const float* __restrict__ logits, float* __restrict__ out, int B, int h,
+__global__ void __launch_bounds__(256) logits_upsample_nchw_kernel(const float* __restrict__ logits, long ld, float* __restrict__ out, int B, int h,
                                                                    int w, int H, int W, int ncls, float sh, float sw) {
   pdl_trigger();
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -290,17 +291,19 @@ __global__ void __launch_bounds__(256) logits_upsample_nchw_kernel(const float* 
   bilin_src(y, sh, h, y0, y1, ly);
   bilin_src(x, sw, w, x0, x1, lx);
   const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
-  const float* p00 = logits + (((long)b * h + y0) * w + x0) * ncls;
-  const float* p01 = logits + (((long)b * h + y0) * w + x1) * ncls;
-  const float* p10 = logits + (((long)b * h + y1) * w + x0) * ncls;
-  const float* p11 = logits + (((long)b * h + y1) * w + x1) * ncls;
+  const float* p00 = logits + (((long)b * h + y0) * w + x0) * ld;
+  const float* p01 = logits + (((long)b * h + y0) * w + x1) * ld;
+  const float* p10 = logits + (((long)b * h + y1) * w + x0) * ld;
+  const float* p11 = logits + (((long)b * h + y1) * w + x1) * ld;
   for (int k = 0; k < ncls; k++)
     out[(((long)b * ncls + k) * H + y) * W + x] = w00 * p00[k] + w01 * p01[k] + w10 * p10[k] + w11 * p11[k];
 }
-CMX_API int cmx_logits_upsample_nchw(const float* logits, float* out, int B, int h, int w, int H, int W, int ncls, void* stream) {
+CMX_API int cmx_logits_upsample_nchw(const float* logits, int64_t ld, float* out, int B, int h, int w, int H, int W, int ncls,
+                                     void* stream) {
+  CMX_REQUIRE(ld >= ncls, "logits_upsample: row stride %ld < ncls %d", (long)ld, ncls);
   const long total = (long)B * H * W;
   if (total == 0) return 0;
-  logits_upsample_nchw_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(logits, out, B, h, w, H, W, ncls,
+  logits_upsample_nchw_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(logits, (long)ld, out, B, h, w, H, W, ncls,
                                                                                  (float)h / (float)H, (float)w / (float)W);
   LAUNCH_DONE("logits_upsample_nchw");
 }

@@ -47,6 +47,7 @@ class Engine:
         self.dims, self.heads, self.depths, self.srs = bb.embed_dims, bb.num_heads, bb.depths, bb.sr_ratios
         self.embed = model.decode_head.linear_pred.in_channels
         self.ncls = model.decode_head.num_classes
+        self.ncls_ld = (self.ncls + 7) // 8 * 8
         self.names = [n for n, _ in model.named_parameters()]
         self.flat_p = None
         self.forced_dp = None        # test hook: {block prefix: tensor[2,B]}
@@ -697,7 +698,9 @@ class Engine:
         N0 = sizes[0][0] * sizes[0][1]
         ops.bn_apply(fuse, c.mean, c.inv, self.P(p + ".linear_fuse.1.weight"), self.P(p + ".linear_fuse.1.bias"), yb, relu=True,
                      mask=dropmask, rows_per_sample=N0)
-        logits = self.E(M0, self.ncls, dtype=f32)
+        # class axis padded to a multiple of 8 (row stride only: the pad columns are never read) so that the prediction
+        # layer and its dgrad/wgrad satisfy the 16-byte row-stride rule of the tcgen05 path
+        logits = self.E(M0, self.ncls_ld, dtype=f32)[:, :self.ncls]
         ops.mm(yb, self.W(p + ".linear_pred.weight"), logits, bias=self.P(p + ".linear_pred.bias"))
         c.feats, c.sizes, c.fuse, c.yb, c.dropmask, c.N0 = feats, sizes, fuse, yb, dropmask, N0
         self.tr("decode_head.logits", logits)
@@ -861,11 +864,11 @@ class Engine:
             ops.ce_finalize(acc, loss)
             return loss
         self.flat_g.zero_()
-        dl = self.Z(B * h0 * w0, self.ncls)
-        ops.ce_upsampled(logits, label, ignore_index, acc, dl, B, h0, w0, H, W, self.ncls)
-        dlog = self.E(B * h0 * w0, self.ncls)
-        ops.ce_finalize(acc, loss, dl, None, dlog)
-        dfs = self.decoder_bwd(cdec, dlog, B)
+        dl = self.Z(B * h0 * w0, self.ncls_ld)
+        ops.ce_upsampled(logits, label, ignore_index, acc, dl[:, :self.ncls], B, h0, w0, H, W, self.ncls)
+        dlog = self.E(B * h0 * w0, self.ncls_ld)
+        ops.ce_finalize(acc, loss, dl, None, dlog)   # element-wise over the padded buffer (pad columns stay 0)
+        dfs = self.decoder_bwd(cdec, dlog[:, :self.ncls], B)
         del cdec
         pending = None  # (dcol_rgb, dcol_x) of the next stage's patch embeds, to be scattered into this stage's dr
         for s in (3, 2, 1, 0):

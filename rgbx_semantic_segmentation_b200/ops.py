@@ -399,8 +399,12 @@ def upsample_bwd(dout, Ho, Wo, dz, Hi, Wi, B, C):
 
 
 def ce_upsampled(logits, label, ignore_index, acc, dlogits, B, h, w, H, W, ncls):
+    """logits / dlogits: [B*h*w, ncls] row-major views (row stride >= ncls, identical for both)"""
     assert label.dtype == torch.int64 and label.is_contiguous()
-    _call("cmx_ce_upsampled_fwd_bwd", logits.data_ptr(), label.data_ptr(), ignore_index, acc.data_ptr(), _p(dlogits),
+    assert logits.dtype == torch.float32 and tuple(logits.shape) == (B * h * w, ncls)
+    if dlogits is not None:
+        assert dlogits.dtype == torch.float32 and dlogits.shape == logits.shape and _ld(dlogits) == _ld(logits)
+    _call("cmx_ce_upsampled_fwd_bwd", logits.data_ptr(), _ld(logits), label.data_ptr(), ignore_index, acc.data_ptr(), _p(dlogits),
                                                     B, h, w, H, W, ncls, _stream())
 
 
@@ -411,7 +415,8 @@ def ce_finalize(acc, loss, dlogits=None, gscale=None, out=None):
 
 
 def logits_upsample_nchw(logits, out, B, h, w, H, W, ncls):
-    _call("cmx_logits_upsample_nchw", logits.data_ptr(), out.data_ptr(), B, h, w, H, W, ncls, _stream())
+    assert logits.dtype == torch.float32 and tuple(logits.shape) == (B * h * w, ncls)
+    _call("cmx_logits_upsample_nchw", logits.data_ptr(), _ld(logits), out.data_ptr(), B, h, w, H, W, ncls, _stream())
     return out
 
 

@@ -51,3 +51,27 @@ for idx, (M, N, K, odt, hb, hr, tb) in enumerate(SHAPES):
     t = sorted(ts)[len(ts) // 2]
     print("%d: M=%d N=%d K=%d out=%s bias=%d res=%d tb=%d : %.1f us  %.0f GB/s  %.1f TFLOP/s" % (
         idx, M, N, K, str(odt)[6:], hb, hr, tb, t, nbytes / t / 1e3, 2.0 * M * N * K / t / 1e6), flush=True)
+
+# weight-gradient shapes: dW[N_out, N_in] += dY[tok, N_out]^T X[tok, N_in]  (MN-major operands, split-K fp32 atomics)
+WGRAD = [(64, 64, 153600), (256, 64, 153600), (128, 128, 38400), (512, 128, 38400), (320, 320, 9600), (1280, 320, 9600),
+         (512, 512, 2400), (512, 512, 153600)]
+for idx, (M, N, K) in enumerate(WGRAD):
+    if only is not None and ("w%d" % idx) not in only.split(","):
+        continue
+    dy = torch.randn(K, M, device=dev).to(bf)
+    x = torch.randn(K, N, device=dev).to(bf)
+    out = torch.zeros(M, N, device=dev)
+    ts = []
+    for i in range(iters + 2):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ops.mm(dy, x, out, ta=True, tb=True, accumulate=True)
+        e1.record()
+        torch.cuda.synchronize()
+        if i >= 2:
+            ts.append(e0.elapsed_time(e1) * 1e3)
+    nbytes = dy.numel() * 2 + x.numel() * 2 + out.numel() * 8
+    t = sorted(ts)[len(ts) // 2]
+    print("w%d: dW[%d,%d] over %d tokens : %.1f us  %.0f GB/s  %.1f TFLOP/s" % (idx, M, N, K, t, nbytes / t / 1e3,
+                                                                             2.0 * M * N * K / t / 1e6), flush=True)

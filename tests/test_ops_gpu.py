@@ -356,28 +356,33 @@ def test_upsample_sum_and_adjoint(sizes):
         close(dz, zr[i].grad.permute(0, 2, 3, 1).reshape(-1, C), 1e-2, 2e-2, "upsample adjoint %d" % i)
 
 
-@pytest.mark.parametrize("h,w,H,W,ncls", [(12, 16, 48, 64, 9), (23, 40, 90, 160, 5), (5, 7, 19, 27, 9)])
-def test_ce_upsampled(h, w, H, W, ncls):
+@pytest.mark.parametrize("h,w,H,W,ncls,ld", [(12, 16, 48, 64, 9, 16), (23, 40, 90, 160, 5, 8), (5, 7, 19, 27, 9, 9)])
+def test_ce_upsampled(h, w, H, W, ncls, ld):
+    """ld > ncls: the engine's padded class axis (pad columns hold garbage and must be neither read nor written)"""
     torch.manual_seed(10)
     B = 2
-    logits = rnd(B, h, w, ncls, scale=2.0)
+    base = torch.full((B * h * w, ld), float("nan"), device=DEV)
+    logits = base[:, :ncls]
+    logits.copy_(rnd(B * h * w, ncls, scale=2.0))
     label = torch.randint(0, ncls, (B, H, W), device=DEV)
     label[torch.rand(B, H, W, device=DEV) < 0.1] = 255
     label[:, :3] = 255
     acc = torch.zeros(2, dtype=torch.float64, device=DEV)
-    dl = torch.zeros_like(logits)
+    dl_full = torch.zeros(B * h * w, ld, device=DEV)
+    dl = dl_full[:, :ncls]
     ops.ce_upsampled(logits, label, 255, acc, dl, B, h, w, H, W, ncls)
+    assert float(dl_full[:, ncls:].abs().sum()) == 0.0
     loss = torch.empty((), device=DEV)
     gs = torch.tensor(2.0, device=DEV)
-    dout = torch.empty_like(logits)
-    ops.ce_finalize(acc, loss, dl, gs, dout)
-    lr = logits.permute(0, 3, 1, 2).clone().requires_grad_(True)
+    dout = torch.empty_like(dl_full)
+    ops.ce_finalize(acc, loss, dl_full, gs, dout)
+    lr = logits.reshape(B, h, w, ncls).permute(0, 3, 1, 2).clone().requires_grad_(True)
     up = F.interpolate(lr, size=(H, W), mode="bilinear", align_corners=False)
     ref = F.cross_entropy(up, label, ignore_index=255)
     (2.0 * ref).backward()
     assert abs(float(loss) - float(ref)) < 1e-5 * max(1, abs(float(ref)))
     assert float(acc[1]) == float((label != 255).sum())
-    close(dout, lr.grad.permute(0, 2, 3, 1), 1e-3, 1e-6, "ce dlogits")
+    close(dout[:, :ncls], lr.grad.permute(0, 2, 3, 1).reshape(-1, ncls), 1e-3, 1e-6, "ce dlogits")
     full = torch.empty(B, ncls, H, W, device=DEV)
     ops.logits_upsample_nchw(logits, full, B, h, w, H, W, ncls)
     close(full, up, 1e-5, 1e-5, "logits upsample")
