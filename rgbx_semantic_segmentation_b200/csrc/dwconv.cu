@@ -139,17 +139,17 @@ __global__ void __launch_bounds__(256) dwconv_tiled_kernel(const bf16* __restric
   const int cbase = blockIdx.x * DT_CH;
   const int c = cbase + cp * 2;
   const bool c_ok = c < C;  // C is even
-  float wt[2][9], bs[2] = {0.f, 0.f};
+  float2 wt[9], bs = make_float2(0.f, 0.f);  // .x = channel c, .y = channel c + 1: every FMA below is one packed FFMA2
 #pragma unroll
   for (int t = 0; t < 9; t++) {
     const int tt = MODE == 2 ? 8 - t : t;
-    wt[0][t] = c_ok ? w[(long)c * 9 + tt] : 0.f;
-    wt[1][t] = c_ok ? w[(long)(c + 1) * 9 + tt] : 0.f;
+    wt[t].x = c_ok ? w[(long)c * 9 + tt] : 0.f;
+    wt[t].y = c_ok ? w[(long)(c + 1) * 9 + tt] : 0.f;
   }
-  if (MODE != 2 && bias && c_ok) { bs[0] = bias[c]; bs[1] = bias[c + 1]; }
-  float gw[2][9], gb[2] = {0.f, 0.f};
+  if (MODE != 2 && bias && c_ok) { bs.x = bias[c]; bs.y = bias[c + 1]; }
+  float2 gw[9], gb = make_float2(0.f, 0.f);
 #pragma unroll
-  for (int t = 0; t < 9; t++) { gw[0][t] = 0.f; gw[1][t] = 0.f; }
+  for (int t = 0; t < 9; t++) gw[t] = make_float2(0.f, 0.f);
 
   for (long tl = blockIdx.y; tl < ntiles; tl += gridDim.y) {
     const int tx = (int)(tl % tiles_x);
@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(256) dwconv_tiled_kernel(const bf16* __restric
         }
       }
       const long rowbase = (long)(b * H + gy) * W;
-#pragma unroll 4
+#pragma unroll 6  // a multiple of 3: the sliding-window register rotation disappears in the unrolled body
       for (int px = 0; px < DT_TW; px++) {
 #pragma unroll
         for (int i = 0; i < 3; i++) {
@@ -193,36 +193,30 @@ __global__ void __launch_bounds__(256) dwconv_tiled_kernel(const bf16* __restric
         }
         const int gx = x0 + px;
         if (gx >= W) break;
-        float a0 = bs[0], a1 = bs[1];
+        float2 a = bs;
 #pragma unroll
         for (int i = 0; i < 3; i++)
 #pragma unroll
-          for (int j = 0; j < 3; j++) {
-            a0 = fmaf(wt[0][i * 3 + j], win[i][j].x, a0);
-            a1 = fmaf(wt[1][i * 3 + j], win[i][j].y, a1);
-          }
+          for (int j = 0; j < 3; j++) ffma2(a, wt[i * 3 + j], win[i][j]);
         if (MODE == 1) {
           const __nv_bfloat162 g2 = *reinterpret_cast<const __nv_bfloat162*>(dy + (rowbase + gx) * lddy + c);
           float2 g = __bfloat1622float2(g2);
-          g.x *= act_grad_f<ACT>(a0);
-          g.y *= act_grad_f<ACT>(a1);
-          gb[0] += g.x;
-          gb[1] += g.y;
+          g.x *= act_grad_f<ACT>(a.x);
+          g.y *= act_grad_f<ACT>(a.y);
+          gb.x += g.x;
+          gb.y += g.y;
 #pragma unroll
           for (int i = 0; i < 3; i++)
 #pragma unroll
-            for (int j = 0; j < 3; j++) {
-              gw[0][i * 3 + j] = fmaf(g.x, win[i][j].x, gw[0][i * 3 + j]);
-              gw[1][i * 3 + j] = fmaf(g.y, win[i][j].y, gw[1][i * 3 + j]);
-            }
+            for (int j = 0; j < 3; j++) ffma2(gw[i * 3 + j], g, win[i][j]);
           *reinterpret_cast<__nv_bfloat162*>(out + (rowbase + gx) * ldo + c) = __floats2bfloat162_rn(g.x, g.y);
         } else {
-          const __nv_bfloat162 o2 = __floats2bfloat162_rn(act_f<ACT>(a0), act_f<ACT>(a1));
+          const __nv_bfloat162 o2 = __floats2bfloat162_rn(act_f<ACT>(a.x), act_f<ACT>(a.y));
           *reinterpret_cast<__nv_bfloat162*>(out + (rowbase + gx) * ldo + c) = o2;
           if (db) {  // per-channel sum of what was written (bias gradient of the layer that produced x's gradient)
             const float2 of = __bfloat1622float2(o2);
-            gb[0] += of.x;
-            gb[1] += of.y;
+            gb.x += of.x;
+            gb.y += of.y;
           }
         }
       }
@@ -233,8 +227,8 @@ __global__ void __launch_bounds__(256) dwconv_tiled_kernel(const bf16* __restric
     for (int i = tid; i < DT_CH; i += 256) sred[9][i] = 0.f;
     __syncthreads();
     if (c_ok) {
-      atomicAdd(&sred[9][cp * 2], gb[0]);
-      atomicAdd(&sred[9][cp * 2 + 1], gb[1]);
+      atomicAdd(&sred[9][cp * 2], gb.x);
+      atomicAdd(&sred[9][cp * 2 + 1], gb.y);
     }
     __syncthreads();
     for (int i = tid; i < DT_CH; i += 256)
@@ -248,11 +242,11 @@ __global__ void __launch_bounds__(256) dwconv_tiled_kernel(const bf16* __restric
     if (c_ok) {
 #pragma unroll
       for (int t = 0; t < 9; t++) {
-        atomicAdd(&sred[t][cp * 2], gw[0][t]);
-        atomicAdd(&sred[t][cp * 2 + 1], gw[1][t]);
+        atomicAdd(&sred[t][cp * 2], gw[t].x);
+        atomicAdd(&sred[t][cp * 2 + 1], gw[t].y);
       }
-      atomicAdd(&sred[9][cp * 2], gb[0]);
-      atomicAdd(&sred[9][cp * 2 + 1], gb[1]);
+      atomicAdd(&sred[9][cp * 2], gb.x);
+      atomicAdd(&sred[9][cp * 2 + 1], gb.y);
     }
     __syncthreads();
     for (int i = tid; i < 10 * DT_CH; i += 256) {

@@ -782,9 +782,16 @@ static int pick_bn(const CmxGemm* g) {
   const int cands_mn[3] = {256, 128, 64};
   const int* c = g->trans_b ? cands_mn : cands_k;
   const int nc = g->trans_b ? 3 : 4;
-  int best = c[0];
+  static int bn_max = -1;  // debug/tuning knob: CMX_GEMM_BN_MAX=128 forces the two-CTA-per-SM tile shapes
+  if (bn_max < 0) {
+    const char* e = getenv("CMX_GEMM_BN_MAX");
+    bn_max = e ? atoi(e) : 256;
+    if (bn_max < 64) bn_max = 64;
+  }
+  int best = c[nc - 1];
   long best_cost = -1;
   for (int i = 0; i < nc; i++) {
+    if (c[i] > bn_max) continue;
     const long cost = (N + c[i] - 1) / c[i] * c[i];
     if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = c[i]; }
   }

@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(256) ln_fwd_v2_kernel(const TX* __restrict__ x
 }
 
 template <typename TDY, typename TX, typename TDX, int G, int J>
-__global__ void __launch_bounds__(256) ln_bwd_v2_kernel(const TDY* __restrict__ dy, long lddy, const bf16* __restrict__ dy2, long lddy2,
+__global__ void __launch_bounds__(256, (J == 1 ? 3 : 2)) ln_bwd_v2_kernel(const TDY* __restrict__ dy, long lddy, const bf16* __restrict__ dy2, long lddy2,
                                                         const TX* __restrict__ x, long ldx, const float* __restrict__ mean,
                                                         const float* __restrict__ rstd, const float* __restrict__ gamma,
                                                         const float* __restrict__ dres, long lddres, TDX* __restrict__ dx, long lddx,
@@ -163,16 +163,17 @@ __global__ void __launch_bounds__(256) ln_bwd_v2_kernel(const TDY* __restrict__ 
     const long row = slot * RPW + lane / G;
     const bool ok = row < M;
     const float mu = ok ? mean[row] : 0.f, rs = ok ? rstd[row] : 0.f;
-    float g[J][8], xh[J][8];
+    float g[J][8], xh[J][8], rr[J][8];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int j = 0; j < J; j++) {
       const int c = 8 * (lg + G * j);
 #pragma unroll
-      for (int i = 0; i < 8; i++) { g[j][i] = 0.f; xh[j][i] = 0.f; }
+      for (int i = 0; i < 8; i++) { g[j][i] = 0.f; xh[j][i] = 0.f; rr[j][i] = 0.f; }
       if (ok && c < C) {
         float d[8], xv[8];
         load8(dy + row * lddy + c, d);
+        if (dres) load8(dres + row * lddres + c, rr[j]);  // issued with the other loads: one memory round trip per row
         if (dy2) {
           float d2[8];
           load8(dy2 + row * lddy2 + c, d2);
@@ -202,12 +203,8 @@ __global__ void __launch_bounds__(256) ln_bwd_v2_kernel(const TDY* __restrict__ 
         float o[8];
 #pragma unroll
         for (int i = 0; i < 8; i++) o[i] = rs * (g[j][i] - s1 - xh[j][i] * s2);
-        if (dres) {
-          float r[8];
-          load8(dres + row * lddres + c, r);
 #pragma unroll
-          for (int i = 0; i < 8; i++) o[i] += r[i];
-        }
+        for (int i = 0; i < 8; i++) o[i] += rr[j][i];
         if (dx) store8(dx + row * lddx + c, o);
         if (dxbf) {
 #pragma unroll
@@ -434,7 +431,8 @@ CMX_API int cmx_layernorm_bwd(const void* dy, int dy_dtype, int64_t lddy, const 
     int G, J;
     ln_gj(C, G, J);
     int grid2 = cdiv(M, 8 * (32 / G));
-    if (grid2 > 148 * 6) grid2 = 148 * 6;
+    const int resident = 148 * (J == 1 ? 3 : 2);  // one full wave of CTAs (see __launch_bounds__), grid-stride beyond
+    if (grid2 > resident) grid2 = resident;
 #define LN_B2T(TDY, TX, TDX, Gv, Jv)                                                                                            \
   ln_bwd_v2_kernel<TDY, TX, TDX, Gv, Jv><<<grid2, 256, 0, st>>>((const TDY*)dy, lddy, (const bf16*)dy2, lddy2, (const TX*)x, ldx, \
                                                                 mean, rstd, gamma, dres, lddres, (TDX*)dx, lddx, (bf16*)dx_bf,    \
