@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(DW_CG* DW_PY) dwconv_fwd_kernel(const bf16* __
 constexpr int DT_TH = 8, DT_TW = 32, DT_CH = 64;
 
 template <int ACT, int MODE>
-__global__ void __launch_bounds__(256) dwconv_tiled_kernel(const bf16* __restrict__ x, long ldx, const float* __restrict__ w,
+__global__ void __launch_bounds__(256, 2) dwconv_tiled_kernel(const bf16* __restrict__ x, long ldx, const float* __restrict__ w,
                                                            const float* __restrict__ bias, const bf16* __restrict__ dy, long lddy,
                                                            bf16* __restrict__ out, long ldo, float* __restrict__ dw,
                                                            float* __restrict__ db, int B, int H, int W, int C, int tiles_x,
@@ -157,19 +157,40 @@ __global__ void __launch_bounds__(256) dwconv_tiled_kernel(const bf16* __restric
     const int b = (int)(tl / ((long)tiles_x * tiles_y));
     const int x0 = tx * DT_TW, y0 = ty * DT_TH;
     __syncthreads();  // previous tile fully consumed
-    // ---- stage the halo tile: (TH+2)*(TW+2) pixels x 8 chunks of 8 channels
-    for (int i = tid; i < (DT_TH + 2) * (DT_TW + 2) * (DT_CH / 8); i += 256) {
-      const int ch8 = i & 7;
-      const int pix = i >> 3;
-      const int px = pix % (DT_TW + 2), py = pix / (DT_TW + 2);
-      const int gy = y0 + py - 1, gx = x0 + px - 1;
-      uint4 v = make_uint4(0, 0, 0, 0);
-      if (gy >= 0 && gy < H && gx >= 0 && gx < W && cbase + ch8 * 8 < C)
-        v = *reinterpret_cast<const uint4*>(x + ((long)(b * H + gy) * W + gx) * ldx + cbase + ch8 * 8);
-      *reinterpret_cast<uint4*>(&tile[(long)pix * DT_CH + ch8 * 8]) = v;
+    // ---- stage the halo tile: (TH+2)*(TW+2) pixels x 8 chunks of 8 channels, as asynchronous 16-byte copies
+    // (cp.async with zero fill outside the image): all ~11 copies of a thread are in flight together
+    {
+      constexpr int NCH = (DT_TH + 2) * (DT_TW + 2) * (DT_CH / 8);
+      const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(tile);
+#pragma unroll
+      for (int k = 0; k < (NCH + 255) / 256; k++) {
+        const int i = tid + k * 256;
+        if (i < NCH) {
+          const int ch8 = i & 7;
+          const int pix = i >> 3;
+          const int px = pix % (DT_TW + 2), py = pix / (DT_TW + 2);
+          const int gy = y0 + py - 1, gx = x0 + px - 1;
+          const bool inb = gy >= 0 && gy < H && gx >= 0 && gx < W && cbase + ch8 * 8 < C;
+          const bf16* src = inb ? x + ((long)(b * H + gy) * W + gx) * ldx + cbase + ch8 * 8 : x;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(tile_s + (uint32_t)(pix * DT_CH + ch8 * 8) * 2u), "l"(src),
+                       "r"(inb ? 16 : 0)
+                       : "memory");
+        }
+      }
     }
-    __syncthreads();
     const int gy = y0 + r;
+    // MODE 1: this thread's 32 dy values of the row are requested before waiting for the tile (independent loads)
+    uint32_t gq[DT_TW];
+    if (MODE == 1) {
+#pragma unroll
+      for (int px = 0; px < DT_TW; px++) {
+        const int gx = x0 + px;
+        gq[px] = 0u;
+        if (gy < H && c_ok && gx < W) gq[px] = __ldg(reinterpret_cast<const unsigned int*>(dy + ((long)(b * H + gy) * W + gx) * lddy + c));
+      }
+    }
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
     if (gy < H && c_ok) {
       // 3x3 window: win[row][col] for the 2 channels; columns slide
       float2 win[3][3];
@@ -182,7 +203,7 @@ __global__ void __launch_bounds__(256) dwconv_tiled_kernel(const bf16* __restric
         }
       }
       const long rowbase = (long)(b * H + gy) * W;
-#pragma unroll 6  // a multiple of 3: the sliding-window register rotation disappears in the unrolled body
+#pragma unroll  // fully unrolled: the sliding-window register rotation disappears and gq[] stays in registers
       for (int px = 0; px < DT_TW; px++) {
 #pragma unroll
         for (int i = 0; i < 3; i++) {
@@ -199,8 +220,7 @@ __global__ void __launch_bounds__(256) dwconv_tiled_kernel(const bf16* __restric
 #pragma unroll
           for (int j = 0; j < 3; j++) ffma2(a, wt[i * 3 + j], win[i][j]);
         if (MODE == 1) {
-          const __nv_bfloat162 g2 = *reinterpret_cast<const __nv_bfloat162*>(dy + (rowbase + gx) * lddy + c);
-          float2 g = __bfloat1622float2(g2);
+          float2 g = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&gq[px]));
           g.x *= act_grad_f<ACT>(a.x);
           g.y *= act_grad_f<ACT>(a.y);
           gb.x += g.x;
