@@ -775,27 +775,38 @@ static int launch_tc(const CmxGemm* g, const Epi& epi, cudaStream_t st) {
   return 0;
 }
 
-// tile width: least padded columns, ties to the wider tile.  MN-major B tiles are built from 64-wide chunks.
+// Tile width.  Default policy "auto" (measured on B200 over the MiT-B2 shapes, graph-replayed launches,
+// scripts/gemm_shapes_bench.py): the two-CTA-per-SM shapes only - BN = 128, or BN = 64 when N <= 64 or when 128-wide
+// tiles would leave SMs empty (< 148 tiles: the small-token stages, where more and narrower tiles are 15-25 % faster).
+// BN = 256 / 160 (whole-SM CTAs) are within +-3 % of BN = 128 standalone except for a few huge weight gradients and
+// cost the co-residency with the other streams' kernels; they stay reachable for experiments and tests through
+// CMX_GEMM_TILE_POLICY=pad (least padded columns, ties to the wider tile) and CMX_GEMM_BN_MAX.
 static int pick_bn(const CmxGemm* g) {
   const long N = g->N;
-  const int cands_k[4] = {256, 160, 128, 64};
-  const int cands_mn[3] = {256, 128, 64};
-  const int* c = g->trans_b ? cands_mn : cands_k;
-  const int nc = g->trans_b ? 3 : 4;
-  static int bn_max = -1;  // debug/tuning knob: CMX_GEMM_BN_MAX=128 forces the two-CTA-per-SM tile shapes
-  if (bn_max < 0) {
-    const char* e = getenv("CMX_GEMM_BN_MAX");
-    bn_max = e ? atoi(e) : 256;
-    if (bn_max < 64) bn_max = 64;
+  const char* pol = getenv("CMX_GEMM_TILE_POLICY");
+  const char* emax = getenv("CMX_GEMM_BN_MAX");
+  int bn_max = emax ? atoi(emax) : 256;
+  if (bn_max < 64) bn_max = 64;
+  if (pol && pol[0] == 'p') {
+    const int cands_k[4] = {256, 160, 128, 64};
+    const int cands_mn[3] = {256, 128, 64};   // MN-major B tiles are built from 64-wide chunks
+    const int* c = g->trans_b ? cands_mn : cands_k;
+    const int nc = g->trans_b ? 3 : 4;
+    int best = c[nc - 1];
+    long best_cost = -1;
+    for (int i = 0; i < nc; i++) {
+      if (c[i] > bn_max) continue;
+      const long cost = (N + c[i] - 1) / c[i] * c[i];
+      if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = c[i]; }
+    }
+    return best;
   }
-  int best = c[nc - 1];
-  long best_cost = -1;
-  for (int i = 0; i < nc; i++) {
-    if (c[i] > bn_max) continue;
-    const long cost = (N + c[i] - 1) / c[i] * c[i];
-    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = c[i]; }
-  }
-  return best;
+  if (N <= 64 || bn_max < 128) return 64;
+  const long kb_total = (g->K + TC_BK - 1) / TC_BK;
+  long split = g->split_k > 1 ? g->split_k : 1;
+  if (split > kb_total) split = kb_total;
+  const long tiles128 = ((g->M + TC_BM - 1) / TC_BM) * ((N + 127) / 128) * g->batch1 * g->batch2 * split;
+  return tiles128 < num_sms() ? 64 : 128;
 }
 
 static int dispatch_tc(const CmxGemm* g, const Epi& epi, cudaStream_t st) {

@@ -13,6 +13,14 @@ DEV = "cuda"
 bf = torch.bfloat16
 
 
+@pytest.fixture(autouse=True, params=["auto", "pad"])
+def tile_policy(request, monkeypatch):
+    """every case runs under both tile-width policies: "auto" (the two-CTA-per-SM BN = 64 / 128 shapes the engine uses)
+    and "pad" (least padding: also exercises the whole-SM BN = 160 / 256 instantiations)"""
+    monkeypatch.setenv("CMX_GEMM_TILE_POLICY", request.param)
+    yield request.param
+
+
 def _ref(a, b, ta, tb):
     A = a.float().t() if ta else a.float()
     Bm = b.float() if tb else b.float().t()
