@@ -14,6 +14,7 @@
 #include <cuda.h>
 #include <mma.h>
 #include <atomic>
+#include <type_traits>
 #include <stdlib.h>
 #include <string.h>
 
@@ -56,12 +57,29 @@ __device__ __forceinline__ void epi_store_scalar(const Epi& e, long row, long co
   }
 }
 // epilogue math for 8 consecutive columns kept in registers (used by the TMA-store path); sbias = shared-memory
-// copy of the bias slice of this tile (or nullptr).  Out-of-range columns/rows only skip the residual load.
+// copy of the bias slice of this tile (zeros without bias).  MODE 0 (alpha = 1, no bias / activation / row scale: every
+// dgrad and attention-style product) compiles to nothing; MODE 1 (alpha and/or bias: the forward linears) is four
+// packed FFMA2; MODE 2 adds the ReLU clamp and the DropPath row scale.  The single
+// epilogue warp per SM sub-partition is issue-latency bound, so instructions per element are what the epilogue costs.
+// Out-of-range columns/rows only skip the residual load.
+template <int MODE>  // 0 plain, 1 alpha/bias only, 2 also ReLU and/or row scale
 __device__ __forceinline__ void epi_math8(const Epi& e, long row, long col, const float (&sbias)[8], bool row_ok, float rs,
                                           float (&v)[8]) {
-  const float lo = e.act == CMX_ACT_RELU ? 0.f : -INFINITY;   // ReLU as a clamp: no branch in the unrolled loop
+  if (MODE != 0) {
+    const float2 a2 = make_float2(e.alpha, e.alpha);
 #pragma unroll
-  for (int i = 0; i < 8; i++) v[i] = fmaxf(fmaf(v[i], e.alpha, sbias[i]), lo) * rs;
+    for (int i = 0; i < 4; i++) {
+      float2 t = make_float2(sbias[2 * i], sbias[2 * i + 1]);
+      ffma2(t, make_float2(v[2 * i], v[2 * i + 1]), a2);
+      v[2 * i] = t.x;
+      v[2 * i + 1] = t.y;
+    }
+    if (MODE == 2) {
+      const float lo = e.act == CMX_ACT_RELU ? 0.f : -INFINITY;   // ReLU as a clamp: no branch in the unrolled loop
+#pragma unroll
+      for (int i = 0; i < 8; i++) v[i] = fmaxf(v[i], lo) * rs;
+    }
+  }
   if (e.res && row_ok) {
     if (col + 8 <= e.N) {
       float r[8];
@@ -79,16 +97,20 @@ __device__ __forceinline__ void epi_math8(const Epi& e, long row, long col, cons
   }
 }
 
-// 8 consecutive columns, all in range, 16B-aligned addresses (checked on the host)
+// 8 consecutive columns, all in range, 16B-aligned addresses (checked on the host).  PLAIN: alpha = 1 and no bias /
+// activation / row scale (every split-K weight gradient) - the accumulator goes straight to the store / red.add.
+template <bool PLAIN = false>
 __device__ __forceinline__ void epi_store_vec8(const Epi& e, long row, long col, float* v) {
-  const float rs = e.row_scale ? e.row_scale[(int)row / e.rows_per_sample] : 1.f;
-  const float lo = e.act == CMX_ACT_RELU ? 0.f : -INFINITY;
-  float b[8];
+  if (!PLAIN) {
+    const float rs = e.row_scale ? e.row_scale[(int)row / e.rows_per_sample] : 1.f;
+    const float lo = e.act == CMX_ACT_RELU ? 0.f : -INFINITY;
+    float b[8];
 #pragma unroll
-  for (int i = 0; i < 8; i++) b[i] = 0.f;
-  if (e.bias) load8(e.bias + col, b);
+    for (int i = 0; i < 8; i++) b[i] = 0.f;
+    if (e.bias) load8(e.bias + col, b);
 #pragma unroll
-  for (int i = 0; i < 8; i++) v[i] = fmaxf(fmaf(v[i], e.alpha, b[i]), lo) * rs;
+    for (int i = 0; i < 8; i++) v[i] = fmaxf(fmaf(v[i], e.alpha, b[i]), lo) * rs;
+  }
   if (e.res) {
     float r[8];
     if (e.r_dtype == CMX_F32) load8(reinterpret_cast<const float*>(e.res) + row * e.ldr + col, r);
@@ -356,7 +378,8 @@ __global__ void __launch_bounds__(tc_threads(BN), tc_ctas_per_sm(BN)) gemm_tc_ke
           if ((u + 1) * UC * 32 > BN || n0 + c * 32 >= epi.N) return -1;
           return c;
         };
-        auto process = [&](uint32_t* r, int c) {
+        auto process = [&](auto mode_tag, uint32_t* r, int c) {
+          constexpr int EMODE = decltype(mode_tag)::value;
           const int cc = c % UC;
           const uint32_t buf = my_stage + (nstore & 1u) * 4096u;
           const bool trc = (warp == 4 && lane == 0);
@@ -374,12 +397,12 @@ __global__ void __launch_bounds__(tc_threads(BN), tc_ctas_per_sm(BN)) gemm_tc_ke
             float sbv[8];
 #pragma unroll
             for (int j = 0; j < 8; j++) sbv[j] = 0.f;
-            if (epi.bias) {
+            if (EMODE != 0 && epi.bias) {
               const uint32_t ba = sb_addr + 4u * (c * 32 + g * 8);
               asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(sbv[0]), "=f"(sbv[1]), "=f"(sbv[2]), "=f"(sbv[3]) : "r"(ba));
               asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(sbv[4]), "=f"(sbv[5]), "=f"(sbv[6]), "=f"(sbv[7]) : "r"(ba + 16u));
             }
-            epi_math8(epi, row, (long)n0 + c * 32 + g * 8, sbv, row_ok, rs, v);
+            epi_math8<EMODE>(epi, row, (long)n0 + c * 32 + g * 8, sbv, row_ok, rs, v);
             const uint32_t sw = (uint32_t)(lane & 7);
             if (epi.c_dtype == CMX_F32) {
               const uint32_t j0 = (uint32_t)(g * 2);
@@ -415,20 +438,45 @@ __global__ void __launch_bounds__(tc_threads(BN), tc_ctas_per_sm(BN)) gemm_tc_ke
             nstore++;
           }
         };
-        uint32_t ra[32], rb[32];
-        int cA = chunk_of(0);
-        if (cA >= 0) tmem_ld32(t_addr + (uint32_t)(cA * 32), ra);
+        auto run_chunks = [&](auto mode_tag) {
+          if constexpr (NH == 1) {
+            // two resident CTAs per SM hide the tcgen05.ld latency of each other: one register set, no spills
+            uint32_t ra[32];
 #pragma unroll 1
-        for (int k = 0; cA >= 0; k += 2) {
-          tmem_wait_ld_dep(ra);
-          const int cB = chunk_of(k + 1);
-          if (cB >= 0) tmem_ld32(t_addr + (uint32_t)(cB * 32), rb);
-          process(ra, cA);
-          if (cB < 0) break;
-          tmem_wait_ld_dep(rb);
-          cA = chunk_of(k + 2);
+            for (int k = 0;; k++) {
+              const int c = chunk_of(k);
+              if (c < 0) break;
+              tmem_ld32(t_addr + (uint32_t)(c * 32), ra);
+              tmem_wait_ld_dep(ra);
+              process(mode_tag, ra, c);
+            }
+            return;
+          }
+          uint32_t ra[32], rb[32];
+          int cA = chunk_of(0);
           if (cA >= 0) tmem_ld32(t_addr + (uint32_t)(cA * 32), ra);
-          process(rb, cB);
+#pragma unroll 1
+          for (int k = 0; cA >= 0; k += 2) {
+            tmem_wait_ld_dep(ra);
+            const int cB = chunk_of(k + 1);
+            if (cB >= 0) tmem_ld32(t_addr + (uint32_t)(cB * 32), rb);
+            process(mode_tag, ra, cA);
+            if (cB < 0) break;
+            tmem_wait_ld_dep(rb);
+            cA = chunk_of(k + 2);
+            if (cA >= 0) tmem_ld32(t_addr + (uint32_t)(cA * 32), ra);
+            process(mode_tag, rb, cB);
+          }
+        };
+        // warp-uniform choice between two separately compiled epilogue bodies (a real branch, not predication)
+        const bool m2 = epi.act != CMX_ACT_NONE || epi.row_scale, m1 = epi.alpha != 1.f || epi.bias;
+        if constexpr (NH == 1) {
+          if (m2) run_chunks(std::integral_constant<int, 2>{});
+          else if (m1) run_chunks(std::integral_constant<int, 1>{});
+          else run_chunks(std::integral_constant<int, 0>{});
+        } else {  // whole-SM shapes (off the default policy): two bodies keep the double register set spill-free
+          if (m2 || m1) run_chunks(std::integral_constant<int, 2>{});
+          else run_chunks(std::integral_constant<int, 0>{});
         }
         if ((BN / 32) % UC != 0) {
           // BN = 160 with 64-column bf16 boxes leaves a 32-column remainder: a full box would spill into the
@@ -458,29 +506,34 @@ __global__ void __launch_bounds__(tc_threads(BN), tc_ctas_per_sm(BN)) gemm_tc_ke
           }
         }
       } else {
+        auto run_direct = [&](auto plain_tag) {
+          constexpr bool PLAIN = decltype(plain_tag)::value;
 #pragma unroll 1
-        for (int c = half; c < BN / 32; c += NH) {
-          if (n0 + c * 32 >= epi.N) break;
-          uint32_t r[32];
-          tmem_ld32(t_addr + (uint32_t)(c * 32), r);
-          tmem_wait_ld();
-          if (row_ok) {
+          for (int c = half; c < BN / 32; c += NH) {
+            if (n0 + c * 32 >= epi.N) break;
+            uint32_t r[32];
+            tmem_ld32(t_addr + (uint32_t)(c * 32), r);
+            tmem_wait_ld();
+            if (row_ok) {
 #pragma unroll
-            for (int g = 0; g < 4; g++) {
-              const long col = (long)n0 + c * 32 + g * 8;
-              if (col + 8 <= epi.N) {
-                float v[8];
+              for (int g = 0; g < 4; g++) {
+                const long col = (long)n0 + c * 32 + g * 8;
+                if (col + 8 <= epi.N) {
+                  float v[8];
 #pragma unroll
-                for (int j = 0; j < 8; j++) v[j] = __uint_as_float(r[g * 8 + j]);
-                epi_store_vec8(epi, row, col, v);
-              } else if (col < epi.N) {  // ragged tail (e.g. Nkv = 300)
+                  for (int j = 0; j < 8; j++) v[j] = __uint_as_float(r[g * 8 + j]);
+                  epi_store_vec8<PLAIN>(epi, row, col, v);
+                } else if (col < epi.N) {  // ragged tail (e.g. Nkv = 300)
 #pragma unroll
-                for (int j = 0; j < 8; j++)
-                  if (col + j < epi.N) epi_store_scalar(epi, row, col + j, __uint_as_float(r[g * 8 + j]));
+                  for (int j = 0; j < 8; j++)
+                    if (col + j < epi.N) epi_store_scalar(epi, row, col + j, __uint_as_float(r[g * 8 + j]));
+                }
               }
             }
           }
-        }
+        };
+        if (epi.alpha == 1.f && !epi.bias && epi.act == CMX_ACT_NONE && !epi.row_scale) run_direct(std::true_type{});
+        else run_direct(std::false_type{});
       }
       tc_fence_before();
       __syncwarp();
