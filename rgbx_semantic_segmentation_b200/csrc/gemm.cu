@@ -334,6 +334,9 @@ __global__ void __launch_bounds__(tc_threads(BN), tc_ctas_per_sm(BN)) gemm_tc_ke
     const int etid = threadIdx.x - 64;  // 0 .. 32 * TC_EPI_WARPS - 1
     const uint32_t my_stage = cstage_base + (uint32_t)(warp - 2) * 8192u;
     uint32_t lt = 0, nstore = 0;
+    float bias_pf[BN / 32];  // next tile's bias values (lane-strided), NH == 1 only
+#pragma unroll
+    for (int i = 0; i < BN / 32; i++) bias_pf[i] = 0.f;
     for (long t = blockIdx.x; t < sc.total_tiles; t += gridDim.x, lt++) {
       int n0, m0, b1, b2, kb_begin, nkb, sp;
       decode(t, n0, m0, b1, b2, kb_begin, nkb, sp);
@@ -347,16 +350,43 @@ __global__ void __launch_bounds__(tc_threads(BN), tc_ctas_per_sm(BN)) gemm_tc_ke
         epi.bias = nullptr;
         epi.res = nullptr;
       }
-      // bias slice of this tile -> shared memory (double-buffered by tile parity; one named barrier per tile)
-      const uint32_t sb_addr = bias_base + (lt & 1u) * 1024u;
-      if (epi.bias) {
-        for (int i = etid; i < BN; i += 32 * TC_EPI_WARPS) {
-          const float bv = (n0 + i < epi.N) ? epi.bias[n0 + i] : 0.f;
-          asm volatile("st.shared.f32 [%0], %1;" ::"r"(sb_addr + 4u * i), "f"(bv) : "memory");
+      uint32_t sb_addr;
+      if constexpr (NH == 1) {
+        // bias slice of this tile -> a WARP-PRIVATE shared-memory copy (no CTA barrier); the values were fetched into
+        // registers one tile ahead, so the global-load latency hides behind the previous tile's epilogue
+        sb_addr = bias_base + (uint32_t)(warp - 2) * (BN * 4u);
+        if (lt == 0 && epi0.bias) {
+#pragma unroll
+          for (int i = 0; i < BN / 32; i++) bias_pf[i] = (n0 + lane + 32 * i < epi0.N) ? epi0.bias[n0 + lane + 32 * i] : 0.f;
         }
+        if (epi.bias) {
+          __syncwarp();   // every lane has finished reading the previous tile's copy
+#pragma unroll
+          for (int i = 0; i < BN / 32; i++)
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(sb_addr + 4u * (lane + 32 * i)), "f"(bias_pf[i]) : "memory");
+          __syncwarp();
+        }
+        const long tn = t + gridDim.x;
+        if (epi0.bias && tn < sc.total_tiles) {
+          int n1, m1, c1, c2, kb1, nk1, sp1;
+          decode(tn, n1, m1, c1, c2, kb1, nk1, sp1);
+#pragma unroll
+          for (int i = 0; i < BN / 32; i++) bias_pf[i] = (n1 + lane + 32 * i < epi0.N) ? epi0.bias[n1 + lane + 32 * i] : 0.f;
+        }
+        if (warp == 4 && lane == 0) { TC_TRACE(2, lt, 0); TC_TRACE(2, lt, 1); }
+      } else {
+        // bias slice of this tile -> shared memory (double-buffered by tile parity; one named barrier per tile)
+        sb_addr = bias_base + (lt & 1u) * 1024u;
+        if (epi.bias) {
+          for (int i = etid; i < BN; i += 32 * TC_EPI_WARPS) {
+            const float bv = (n0 + i < epi.N) ? epi.bias[n0 + i] : 0.f;
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(sb_addr + 4u * i), "f"(bv) : "memory");
+          }
+        }
+        if (warp == 4 && lane == 0) TC_TRACE(2, lt, 0);
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
+        if (warp == 4 && lane == 0) TC_TRACE(2, lt, 1);
       }
-      if (warp == 4 && lane == 0) TC_TRACE(2, lt, 0);
-      asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
       const uint32_t acc = lt & 1u, aph = (lt >> 1) & 1u;
       if (warp == 4 && lane == 0) TC_TRACE(2, lt, 1);
       mbar_wait(tfull_bar + 8u * acc, aph);
