@@ -190,7 +190,11 @@ def main_ours(args):
         else:
             from rgbx_semantic_segmentation_b200.parallel import FlatDataParallel
             net = FlatDataParallel(model)
-    opt = torch.optim.AdamW(group_weight(model, 6e-5), lr=6e-5, betas=(0.9, 0.999), weight_decay=0.01, fused=True)
+    if args.optimizer == "flat":
+        from rgbx_semantic_segmentation_b200.optim import FlatAdamW   # same update as torch.optim.AdamW, one launch
+        opt = FlatAdamW(group_weight(model, 6e-5), lr=6e-5, betas=(0.9, 0.999), weight_decay=0.01)
+    else:
+        opt = torch.optim.AdamW(group_weight(model, 6e-5), lr=6e-5, betas=(0.9, 0.999), weight_decay=0.01, fused=True)
     B = PER_GPU_BATCH
     rgb, x, gt = synth_batch(B, 1 + rank, device=dev)
 
@@ -325,7 +329,7 @@ def main_ours(args):
                 "dtype": "bf16", "data": "synthetic",
                 "config": {"workload": "CMX MiT-B2 RGB-T MFNet shape (480x640, 9 classes) bf16 training, batch 8 per GPU "
                                        "(BASELINE.json configs[1]; configs[2] for N>1)",
-                           "global_batch": gb, "per_gpu_batch": B, "parallelism": "dp%d" % world, "optimizer": "AdamW(fused)",
+                           "global_batch": gb, "per_gpu_batch": B, "parallelism": "dp%d" % world, "optimizer": "FlatAdamW (AdamW, one launch)" if args.optimizer == "flat" else "torch.optim.AdamW(fused)",
                            "grad_allreduce": None if world == 1 else ("torch DDP buckets" if os.environ.get("CMX_BENCH_TORCH_DDP", "0") == "1"
                                                                       else "one NCCL all-reduce over the flat fp32 gradient buffer"),
                            "cuda_graph": bool(model.use_cuda_graph),
@@ -369,6 +373,8 @@ if __name__ == "__main__":
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--profile-out", default=None, help="write the per-kernel CUDA-event breakdown of one step (csv)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--optimizer", default="flat", choices=["flat", "torch"],
+                    help="flat: optim.FlatAdamW (one launch over the flat parameter buffer); torch: torch.optim.AdamW(fused=True)")
     a = ap.parse_args()
     if a.impl == "reference":
         main_reference(a)

@@ -141,6 +141,14 @@ int cmx_colsum(const void* x, int x_dtype, int64_t ldx, float* out, int64_t M, i
 int cmx_relu_bwd(void* dy, int64_t lddy, const void* y, int64_t ldy, int64_t M, int N, void* stream);
 /* out = a*x + b*y elementwise on fp32 flat buffers (grad scaling) */
 int cmx_axpby_f32(float a, const float* x, float b, const float* y, float* out, int64_t n, void* stream);
+/* AdamW (torch.optim.AdamW semantics: decoupled decay, bias correction, no amsgrad) over the engine's flat fp32
+ * parameter storage in ONE launch - the optimizer step of train.py:95-100,176-178.  p/g/m/v: n fp32 elements (n a
+ * multiple of 64); block_group[n/64] (DEVICE, uint8): parameter group of each 64-element block, 255 = leave untouched;
+ * lr/wd: HOST arrays of ngroups (<= 8) values; step counts from 1; grads are multiplied by grad_scale first;
+ * w_bf16 (optional, device): receives the bf16 copy of the updated parameters. */
+int cmx_adamw_flat(float* p, const float* g, float* m, float* v, void* w_bf16, const uint8_t* block_group, int64_t n,
+                   const float* lr, const float* wd, int ngroups, float beta1, float beta2, float eps, float grad_scale,
+                   int64_t step, void* stream);
 
 /* ---- fused spatial-reduction self-attention forward (dual_segformer.py:127-134), head_dim 64, Nkv <= 320 ----------
  * O[b,n,h,:] = softmax_k(scale * q[b,n,h,:].k[b,k,h,:]) v[b,k,h,:]   — flash style (scores only in tensor memory).

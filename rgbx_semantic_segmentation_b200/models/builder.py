@@ -126,6 +126,13 @@ class EncoderDecoder(nn.Module):
             self._engine = Engine(self)
         return self._engine
 
+    def flatten_parameters(self):
+        """move the parameters into the engine's flat fp32 buffer now (otherwise done by the first forward); call after
+        model.cuda() when an optimizer that needs the flat layout (optim.FlatAdamW) is stepped before any forward"""
+        dev = next(self.parameters()).device
+        self._eng()._ensure_flat(dev)
+        return self
+
     def _eng_params(self):
         eng = self._eng()
         d = dict(self.named_parameters())

@@ -259,3 +259,49 @@ def test_mit_b4_pst900_shape_eval_vs_oracle():
     with torch.no_grad():
         ref = cmx_ref.forward(sd, spec, rgb, x, training=False, decoder_bn_eps=1e-5)
     check_logits(out[:, :, ::4, ::4], ref[:, :, ::4, ::4], "b4 720x1280")
+
+
+def test_flat_adamw_matches_torch_adamw():
+    """optim.FlatAdamW (one launch over the flat parameter buffer) vs torch.optim.AdamW on identical gradients:
+    two parameter groups with different lr / weight decay (utils/init_func.py:33-57 grouping), 3 steps, then a
+    state_dict round trip into a fresh optimizer and one more step."""
+    from rgbx_semantic_segmentation_b200.optim import FlatAdamW
+    spec = cmx_ref.MIT_SPECS["mit_b0"]
+    sd = synth_state_dict(spec, 9, seed=0)
+    rgb, x, gt = synth_inputs(2, 64, 96, 9, seed=1)
+    m = make("mit_b0", 9, True, sd).train()
+    m._eng().stochastic = False
+    m(rgb.cuda(), x.cuda(), gt.cuda()).backward()
+    decay = [p for n, p in m.named_parameters() if p.dim() > 1]
+    no_decay = [p for n, p in m.named_parameters() if p.dim() <= 1]
+    groups = lambda a, b: [dict(params=a, lr=3e-3, weight_decay=0.05), dict(params=b, lr=1e-3, weight_decay=0.0)]  # noqa: E731
+    # reference copies (independent tensors, same gradients)
+    ref_p = {p: p.detach().clone().requires_grad_(True) for p in decay + no_decay}
+    for p, q in ref_p.items():
+        q.grad = p.grad.detach().clone()
+    ref = torch.optim.AdamW(groups([ref_p[p] for p in decay], [ref_p[p] for p in no_decay]), betas=(0.9, 0.99), eps=1e-8)
+    opt = FlatAdamW(groups(decay, no_decay), betas=(0.9, 0.99), eps=1e-8)
+
+    def check(tag):
+        worst = max(((p.detach() - q.detach()).abs().max() / (q.detach().abs().max() + 1e-12)).item() for p, q in ref_p.items())
+        assert worst < 2e-6, "%s: max relative parameter deviation %.3g" % (tag, worst)
+
+    for i in range(3):
+        ref.step()
+        opt.step()
+        check("step %d" % (i + 1))
+    ssd = opt.state_dict()
+    assert set(ssd["state"][0].keys()) == {"step", "exp_avg", "exp_avg_sq"} and float(ssd["state"][0]["step"]) == 3.0
+    opt2 = FlatAdamW(groups(decay, no_decay), betas=(0.9, 0.99), eps=1e-8)
+    opt2.load_state_dict(ssd)
+    opt2.param_groups[0]["lr"] = ref.param_groups[0]["lr"] = 1e-3   # LR schedulers rewrite param_groups (train.py:160-163)
+    ref.step()
+    opt2.step()
+    check("after state_dict round trip")
+    # the engine sees the update: parameters are views of its flat buffer
+    n0 = next(iter(dict(m.named_parameters())))
+    assert torch.equal(m._eng().P(n0), dict(m.named_parameters())[n0].detach())
+    # misuse fails loudly
+    dict(m.named_parameters())[n0].grad = torch.zeros_like(dict(m.named_parameters())[n0])
+    with pytest.raises(RuntimeError):
+        opt2.step()
