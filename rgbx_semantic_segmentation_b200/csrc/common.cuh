@@ -81,7 +81,64 @@ __device__ __forceinline__ float gelu_grad_f(float x) {
   gelu_parts(x, cdf, e);
   return fmaf(x * 0.39894228040143267794f, e, cdf);
 }
-// packed fp32x2 FMA (Blackwell FFMA2): d = a * b + d on both halves with ONE issue slot
+// packed fp32x2 helpers (Blackwell FFMA2 / FMUL2 / FADD2: both halves in ONE issue slot)
+__device__ __forceinline__ float2 fmul2(const float2 a, const float2 b) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmul.rn.f32x2 rd, ra, rb;\n\t"
+      "mov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+__device__ __forceinline__ float2 fadd2(const float2 a, const float2 b) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tadd.rn.f32x2 rd, ra, rb;\n\t"
+      "mov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+__device__ __forceinline__ float2 ffma2r(const float2 a, const float2 b, const float2 c) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
+}
+// GELU / GELU' of a channel pair with the packed ops (same A&S 7.1.26 erf as gelu_parts): ~19 / ~21 issue slots per
+// PAIR instead of 2 x 16 / 2 x 18
+__device__ __forceinline__ void gelu_parts2(const float2 x, float2& cdf, float2& e) {
+  const float2 x2 = fmul2(x, x);
+  const float2 arg = fmul2(x2, make_float2(-0.72134752044448170368f, -0.72134752044448170368f));  // -0.5 * log2(e) * x^2
+  e.x = exp2f(arg.x);  // ex2.approx
+  e.y = exp2f(arg.y);
+  float2 t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.x) : "f"(fmaf(0.3275911f * 0.70710678118654752440f, fabsf(x.x), 1.f)));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.y) : "f"(fmaf(0.3275911f * 0.70710678118654752440f, fabsf(x.y), 1.f)));
+  // 0.5 * (a1 t + ... + a5 t^5) = ((((h5 t + h4) t + h3) t + h2) t + h1) t with h_i = a_i / 2
+  float2 p = ffma2r(make_float2(0.5307027145f, 0.5307027145f), t, make_float2(-0.7265760135f, -0.7265760135f));
+  p = ffma2r(p, t, make_float2(0.7107068705f, 0.7107068705f));
+  p = ffma2r(p, t, make_float2(-0.142248368f, -0.142248368f));
+  p = ffma2r(p, t, make_float2(0.127414796f, 0.127414796f));
+  const float2 h = fmul2(fmul2(p, t), e);  // 0.5 * erfc(|x| / sqrt 2)
+  // cdf = 0.5 + copysign(0.5 - h, x)
+  float2 s = fadd2(make_float2(0.5f, 0.5f), make_float2(-h.x, -h.y));
+  s.x = copysignf(s.x, x.x);
+  s.y = copysignf(s.y, x.y);
+  cdf = fadd2(make_float2(0.5f, 0.5f), s);
+}
+__device__ __forceinline__ float2 gelu2(const float2 x) {
+  float2 cdf, e;
+  gelu_parts2(x, cdf, e);
+  return fmul2(x, cdf);
+}
+__device__ __forceinline__ float2 gelu_grad2(const float2 x) {
+  float2 cdf, e;
+  gelu_parts2(x, cdf, e);
+  return ffma2r(fmul2(x, make_float2(0.39894228040143267794f, 0.39894228040143267794f)), e, cdf);
+}
+// packed fp32x2 FMA: d = a * b + d
 __device__ __forceinline__ void ffma2(float2& d, const float2 a, const float2 b) {
   asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rd, {%0, %1};\n\t"
       "fma.rn.f32x2 rd, ra, rb, rd;\n\tmov.b64 {%0, %1}, rd;\n\t}"

@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(DW_CG* DW_PY) dwconv_fwd_kernel(const bf16* __
 constexpr int DT_TH = 8, DT_TW = 32, DT_CH = 64;
 
 template <int ACT, int MODE>
-__global__ void __launch_bounds__(256, 2) dwconv_tiled_kernel(const bf16* __restrict__ x, long ldx, const float* __restrict__ w,
+__global__ void __launch_bounds__(256, (MODE == 1 ? 2 : 3)) dwconv_tiled_kernel(const bf16* __restrict__ x, long ldx, const float* __restrict__ w,
                                                            const float* __restrict__ bias, const bf16* __restrict__ dy, long lddy,
                                                            bf16* __restrict__ out, long ldo, float* __restrict__ dw,
                                                            float* __restrict__ db, int B, int H, int W, int C, int tiles_x,
@@ -221,8 +221,12 @@ __global__ void __launch_bounds__(256, 2) dwconv_tiled_kernel(const bf16* __rest
           for (int j = 0; j < 3; j++) ffma2(a, wt[i * 3 + j], win[i][j]);
         if (MODE == 1) {
           float2 g = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&gq[px]));
-          g.x *= act_grad_f<ACT>(a.x);
-          g.y *= act_grad_f<ACT>(a.y);
+          if (ACT == CMX_ACT_GELU) {
+            g = fmul2(g, gelu_grad2(a));
+          } else {
+            g.x *= act_grad_f<ACT>(a.x);
+            g.y *= act_grad_f<ACT>(a.y);
+          }
           gb.x += g.x;
           gb.y += g.y;
 #pragma unroll
@@ -231,7 +235,9 @@ __global__ void __launch_bounds__(256, 2) dwconv_tiled_kernel(const bf16* __rest
             for (int j = 0; j < 3; j++) ffma2(gw[i * 3 + j], g, win[i][j]);
           *reinterpret_cast<__nv_bfloat162*>(out + (rowbase + gx) * ldo + c) = __floats2bfloat162_rn(g.x, g.y);
         } else {
-          const __nv_bfloat162 o2 = __floats2bfloat162_rn(act_f<ACT>(a.x), act_f<ACT>(a.y));
+          if (ACT == CMX_ACT_GELU) a = gelu2(a);
+          else { a.x = act_f<ACT>(a.x); a.y = act_f<ACT>(a.y); }
+          const __nv_bfloat162 o2 = __floats2bfloat162_rn(a.x, a.y);
           *reinterpret_cast<__nv_bfloat162*>(out + (rowbase + gx) * ldo + c) = o2;
           if (db) {  // per-channel sum of what was written (bias gradient of the layer that produced x's gradient)
             const float2 of = __bfloat1622float2(o2);

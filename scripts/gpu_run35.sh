@@ -1,0 +1,5 @@
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_ops_gpu.py -x -q -k "dwconv" 2>&1 | tail -3
+timeout 600 python bench.py --no-cpu-baseline --profile-out gpurun_out/kernels_35.csv > gpurun_out/bench_35.json 2> gpurun_out/bench_35.err; tail -3 gpurun_out/bench_35.err; python -c "
+import json; d=json.load(open('gpurun_out/bench_35.json')); print({k:d[k] for k in ('value','ms_per_step','gpu_launches_per_step','inference')}); print(d['e2e'])"
+grep dwconv gpurun_out/kernels_35.csv
