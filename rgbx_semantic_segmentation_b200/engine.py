@@ -676,22 +676,31 @@ class Engine:
     # decoder + loss
     # ------------------------------------------------------------------------------------------
     def decoder_fwd(self, feats, sizes, B, training, dropmask, save):
+        """MLPDecoder.py:59-81.  linear_c{s} (a Linear) and its 512-column slice of the 1x1 linear_fuse conv are two
+        linear maps with nothing in between (reshape, bilinear upsample and concat are linear and commute), so they
+        are folded per step into one [E, C_s] matrix  Wcomb_s = Wf[:, slice_s] @ Wc_s  and one bias
+        btot = bf + Wf @ concat(bc4, bc3, bc2, bc1):  z_s = x_s Wcomb_s^T replaces the [M_s, E] x [E, E] GEMM per
+        stage (40.3 of the decoder's 42.9 GFLOP/img) and the e_s intermediates; the parameter gradients are recovered
+        from dWcomb_s by two tiny GEMMs in decoder_bwd.  The 2048-channel concat is never materialised."""
         E_ = self.embed
         hd = self.model.decode_head
         p = "decode_head"
         wf = self.W(p + ".linear_fuse.0.weight")  # [E, 4E]; concat order c4, c3, c2, c1 (MLPDecoder.py:77)
         c = _NS()
-        c.e, c.zs = [], []
+        c.zs, c.wcomb = [], []
         for s in range(4):
-            Ms = feats[s].shape[0]
-            e = self.E(Ms, E_)
-            ops.mm(feats[s], self.W(p + f".linear_c{s + 1}.proj.weight"), e, bias=self.P(p + f".linear_c{s + 1}.proj.bias"))
+            Ms, Cs = feats[s].shape
+            wcomb = self.E(E_, Cs)
+            ops.mm(wf[:, (3 - s) * E_:(4 - s) * E_], self.W(p + f".linear_c{s + 1}.proj.weight"), wcomb, tb=True)
             z = self.E(Ms, E_)
-            ops.mm(e, wf[:, (3 - s) * E_:(4 - s) * E_], z)
-            c.e.append(e); c.zs.append(z)
+            ops.mm(feats[s], wcomb, z)
+            c.zs.append(z); c.wcomb.append(wcomb)
+        c.bcat = torch.cat([self.P(p + f".linear_c{s + 1}.proj.bias") for s in (3, 2, 1, 0)]).view(1, 4 * E_)
+        btot = self.E(1, E_, dtype=f32)
+        ops.smallm_linear_fwd(c.bcat, self.P(p + ".linear_fuse.0.weight").view(E_, 4 * E_), self.P(p + ".linear_fuse.0.bias"), 0, btot)
         M0 = feats[0].shape[0]
         fuse = self.E(M0, E_, dtype=f32)
-        ops.upsample_sum_fwd(c.zs, sizes, self.P(p + ".linear_fuse.0.bias"), fuse, B, E_)
+        ops.upsample_sum_fwd(c.zs, sizes, btot.view(E_), fuse, B, E_)
         bn = hd.linear_fuse[1]
         c.mean, c.inv = self.bn_stats(p + ".linear_fuse.1", bn, fuse, training)
         yb = self.E(M0, E_)
@@ -703,6 +712,8 @@ class Engine:
         logits = self.E(M0, self.ncls_ld, dtype=f32)[:, :self.ncls]
         ops.mm(yb, self.W(p + ".linear_pred.weight"), logits, bias=self.P(p + ".linear_pred.bias"))
         c.feats, c.sizes, c.fuse, c.yb, c.dropmask, c.N0 = feats, sizes, fuse, yb, dropmask, N0
+        if not save:
+            c.zs = None
         self.tr("decode_head.logits", logits)
         return logits, c
 
@@ -720,26 +731,39 @@ class Engine:
                    self.G(p + ".linear_fuse.1.weight"), self.G(p + ".linear_fuse.1.bias"), ws, relu=True, mask=c.dropmask,
                    rows_per_sample=c.N0)
         del dyb
-        ops.colsum(dfuse, self.G(p + ".linear_fuse.0.bias"))
+        c.zs = None
+        # bias path: d btot = colsum(dfuse);  d bf = d btot;  d Wf += d btot (x) bcat;  d bcat = Wf^T d btot
+        dbt = self.Z(1, E_)
+        ops.colsum(dfuse, dbt.view(E_))
+        dbcat = self.E(1, 4 * E_, dtype=f32)
+        ops.smallm_linear_bwd(dbt, dbt, 0, c.bcat, self.P(p + ".linear_fuse.0.weight").view(E_, 4 * E_), dbcat,
+                              self.G(p + ".linear_fuse.0.weight").view(E_, 4 * E_), self.G(p + ".linear_fuse.0.bias"),
+                              self.E(1, E_, dtype=f32))
+        for j, s in enumerate((3, 2, 1, 0)):
+            self.G(p + f".linear_c{s + 1}.proj.bias").add_(dbcat[0, j * E_:(j + 1) * E_])
         wf = self.W(p + ".linear_fuse.0.weight")
         gf = self.G2(p + ".linear_fuse.0.weight")
         H0, W0 = c.sizes[0]
         dfs = []
         for s in range(4):
-            Ms = c.feats[s].shape[0]
+            Ms, Cs = c.feats[s].shape
             if s == 0:
                 dz = dfuse
             else:
                 dz = self.E(Ms, E_)
                 ops.upsample_bwd(dfuse, H0, W0, dz, c.sizes[s][0], c.sizes[s][1], B, E_)
             sl = slice((3 - s) * E_, (4 - s) * E_)
-            with self._wgrad_ctx(dz, c.e[s]):
-                ops.mm(dz, c.e[s], gf[:, sl], ta=True, tb=True, accumulate=True)
-            de = self.E(Ms, E_)
-            ops.mm(dz, wf[:, sl], de, tb=True)
-            self.linear_wgrad(de, c.feats[s], p + f".linear_c{s + 1}.proj.weight", p + f".linear_c{s + 1}.proj.bias")
-            df = self.E(Ms, c.feats[s].shape[1])
-            ops.mm(de, self.W(p + f".linear_c{s + 1}.proj.weight"), df, tb=True)
+            wc = self.W(p + f".linear_c{s + 1}.proj.weight")
+            with self._wgrad_ctx(dz, c.feats[s]):
+                gcomb = self.Z(E_, Cs)
+                ops.mm(dz, c.feats[s], gcomb, ta=True, tb=True, accumulate=True)      # dWcomb_s = dz^T x_s
+                gcomb_bf = self.E(E_, Cs)
+                ops.cast_f32_bf16(gcomb, gcomb_bf)
+                ops.mm(gcomb_bf, wc, gf[:, sl], accumulate=True)                        # dWf[:, slice] += dWcomb Wc^T
+                ops.mm(wf[:, sl], gcomb_bf, self.G2(p + f".linear_c{s + 1}.proj.weight"), ta=True, tb=True,
+                       accumulate=True)                                                # dWc += Wf[:, slice]^T dWcomb
+            df = self.E(Ms, Cs)
+            ops.mm(dz, c.wcomb[s], df, tb=True)
             dfs.append(df)
         self._wgrad_join()
         return dfs

@@ -98,7 +98,7 @@ def grads_vs(m, ref_grads, what):
     cosv = sorted(r[0] for r in rows)
     assert cosv[0] >= 0.90, "%s: worst grad cosine %s" % (what, sorted(rows)[:3])
     assert cosv[len(cosv) // 2] >= 0.99, "%s: median grad cosine %.4f" % (what, cosv[len(cosv) // 2])
-    bad = [r for r in rows if abs(r[1] - 1) > 0.25]
+    bad = [r for r in rows if abs(r[1] - 1) > 0.25 and abs(r[1] - 1) * ref_grads[r[2]].double().norm().item() > 5e-4 * gmax]
     assert not bad, "%s: grad norm ratio off: %s" % (what, bad[:3])
 
 
@@ -129,7 +129,12 @@ def test_train_loss_and_grads_vs_reference(golden_dir, name):
     for n in names:
         if norms[n] > 1e-4 * gmax:
             r = pd[n].grad.double().norm().item() / norms[n]
-            assert abs(r - 1) < 0.25, (n, r)
+            # 25 % on the norm, or - for tensors that are themselves ~1e-3 of the largest gradient - an absolute slack of
+            # 5e-4 of the largest gradient norm.  The case that needs it: the 2-element FRM spatial-gate biases, whose
+            # gradient is a sum over pixels of terms that cancel 13-24x (sum |ds| = 2e-2 vs |sum ds| = 1.5e-3 at stage 2,
+            # scripts/gpu_debug_gate.py); the kernel reproduces an fp64 evaluation on the same saved tensors exactly, the
+            # ~1.5 % (of sum |ds|) deviation comes from the bf16 gradients that reach the gate
+            assert abs(r - 1) < 0.25 or abs(r - 1) * norms[n] < 5e-4 * gmax, (n, r)
     for k in z.files:
         if k.startswith("grad::"):
             gr = torch.from_numpy(z[k]).double().flatten()
