@@ -317,6 +317,33 @@ def main_ours(args):
                 torch.cuda.synchronize()
                 t_ms = i0.elapsed_time(i1) / n_it
                 infer["batch%d" % bs] = {"img_s": bs / (t_ms * 1e-3), "ms_per_forward": t_ms}
+        # BASELINE.json configs[4]: sliding-window multi-scale evaluation of one 480x640 image (scales 0.75/1/1.25, crop
+        # 480x640, stride 2/3, no flip = 6 crops) from HOST uint8 arrays to the host prediction map + confusion matrix:
+        # the reference's per-crop loop (6 batch-1 forwards) vs the batched driver (one batch-6 forward), same model
+        try:
+            import numpy as np
+            from rgbx_semantic_segmentation_b200.utils.metric import hist_info
+            from rgbx_semantic_segmentation_b200.utils.sliding_eval import SlidingEvalContext, sliding_eval_rgbX_batched
+            rng = np.random.default_rng(2)
+            im = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+            mx = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+            gtm = rng.integers(0, NCLS, (H, W)).astype(np.uint8)
+            ctx = SlidingEvalContext(model, NCLS, [0.75, 1.0, 1.25], False)
+            for tag, mb in (("per_crop", 1), ("batched", 8)):
+                for _ in range(2):
+                    pred = sliding_eval_rgbX_batched(ctx, im, mx, (H, W), 2 / 3, dev, max_batch=mb)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                n_img = 5
+                for _ in range(n_img):
+                    pred = sliding_eval_rgbX_batched(ctx, im, mx, (H, W), 2 / 3, dev, max_batch=mb)
+                    hist_info(NCLS, pred, gtm)
+                torch.cuda.synchronize()
+                dt = (time.perf_counter() - t0) / n_img
+                infer["sliding_eval_" + tag] = {"img_s": 1.0 / dt, "ms_per_image": dt * 1e3, "crops_per_image": 6,
+                                                 "note": "host wall clock incl. cv2 resizes, H2D, D2H, argmax, confusion matrix"}
+        except ImportError as ex:   # cv2 missing
+            infer["sliding_eval"] = {"unavailable": str(ex)}
         model.train()
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -310,3 +310,24 @@ def test_flat_adamw_matches_torch_adamw():
     dict(m.named_parameters())[n0].grad = torch.zeros_like(dict(m.named_parameters())[n0])
     with pytest.raises(RuntimeError):
         opt2.step()
+
+
+def test_sliding_window_driver_batched_equals_per_crop():
+    """utils/sliding_eval.py on the real model: one batched forward over all crops of all scales gives the same
+    prediction map as the reference's per-crop schedule (max_batch=1) wherever the per-crop scores are separated."""
+    pytest.importorskip("cv2")
+    from rgbx_semantic_segmentation_b200.utils.sliding_eval import SlidingEvalContext, sliding_eval_rgbX_batched
+    spec = cmx_ref.MIT_SPECS["mit_b0"]
+    sd = synth_state_dict(spec, 5, seed=0)
+    m = make("mit_b0", 5, False, sd).eval()
+    rng = np.random.default_rng(7)
+    img = rng.integers(0, 256, (96, 128, 3), dtype=np.uint8)
+    mx = rng.integers(0, 256, (96, 128), dtype=np.uint8)          # grey X: replicated to 3 channels like RGBXDataset.py:57-59
+    class Net:                                                       # noqa: E306
+        def eval(self): return self
+        def __call__(self, a, b): return m(a, b.expand(-1, 3, -1, -1).contiguous())
+    ctx = SlidingEvalContext(Net(), 5, [0.75, 1.0, 1.5], True)
+    p1 = sliding_eval_rgbX_batched(ctx, img, mx, (64, 64), 2 / 3, "cuda", max_batch=1)
+    p8 = sliding_eval_rgbX_batched(ctx, img, mx, (64, 64), 2 / 3, "cuda", max_batch=8)
+    assert p1.shape == (96, 128) and p1.dtype == np.int64
+    assert (p1 != p8).mean() < 0.02, "batched and per-crop predictions differ on %.2f %% of the pixels" % (100 * (p1 != p8).mean())
