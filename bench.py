@@ -329,19 +329,26 @@ def main_ours(args):
             mx = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
             gtm = rng.integers(0, NCLS, (H, W)).astype(np.uint8)
             ctx = SlidingEvalContext(model, NCLS, [0.75, 1.0, 1.25], False)
-            for tag, mb in (("per_crop", 1), ("batched", 8)):
+            from rgbx_semantic_segmentation_b200.utils.sliding_eval import sliding_eval_rgbX_gpu
+            runs = (("per_crop", lambda: sliding_eval_rgbX_batched(ctx, im, mx, (H, W), 2 / 3, dev, max_batch=1),
+                     "reference schedule: host float64 normalisation per crop, 6 batch-1 forwards, host score resize/argmax"),
+                    ("batched", lambda: sliding_eval_rgbX_batched(ctx, im, mx, (H, W), 2 / 3, dev, max_batch=8),
+                     "same host pre/post-processing, one batch-6 forward"),
+                    ("device", lambda: sliding_eval_rgbX_gpu(ctx, im, mx, (H, W), 2 / 3, dev, max_batch=8),
+                     "device-resident: uint8 upload, normalise/pad/tile, one batch-6 forward, exp, resize, sum, argmax on the GPU"))
+            for tag, fn, note in runs:
                 for _ in range(2):
-                    pred = sliding_eval_rgbX_batched(ctx, im, mx, (H, W), 2 / 3, dev, max_batch=mb)
+                    pred = fn()
                 torch.cuda.synchronize()
                 t0 = time.perf_counter()
                 n_img = 5
                 for _ in range(n_img):
-                    pred = sliding_eval_rgbX_batched(ctx, im, mx, (H, W), 2 / 3, dev, max_batch=mb)
+                    pred = fn()
                     hist_info(NCLS, pred, gtm)
                 torch.cuda.synchronize()
                 dt = (time.perf_counter() - t0) / n_img
                 infer["sliding_eval_" + tag] = {"img_s": 1.0 / dt, "ms_per_image": dt * 1e3, "crops_per_image": 6,
-                                                 "note": "host wall clock incl. cv2 resizes, H2D, D2H, argmax, confusion matrix"}
+                                                 "note": note + "; host wall clock from uint8 arrays to prediction map + confusion matrix"}
         except ImportError as ex:   # cv2 missing
             infer["sliding_eval"] = {"unavailable": str(ex)}
         model.train()

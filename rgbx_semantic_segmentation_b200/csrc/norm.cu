@@ -142,14 +142,10 @@ __global__ void __launch_bounds__(256, (J == 1 ? 3 : 2)) ln_bwd_v2_kernel(const 
                                                         float* __restrict__ dbias, long M, int C) {
   pdl_trigger();
   constexpr int RPW = 32 / G;
-  __shared__ float sh_g[512];
-  __shared__ float sh_b[512];
-  __shared__ float sh_s[512];
+  __shared__ __align__(16) float sh_red[8][512];   // per-warp column partial sums (blockDim.x == 256)
   const int lane = threadIdx.x & 31;
   const int lg = lane % G;
   const int warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-  for (int i = threadIdx.x; i < C; i += blockDim.x) { sh_g[i] = 0.f; sh_b[i] = 0.f; sh_s[i] = 0.f; }
-  __syncthreads();
   float ag[J][8], ab[J][8], gm[J][8], as[J][8];
 #pragma unroll
   for (int j = 0; j < J; j++) {
@@ -218,46 +214,35 @@ __global__ void __launch_bounds__(256, (J == 1 ? 3 : 2)) ln_bwd_v2_kernel(const 
       }
     }
   }
-  if (dbias) {
+  // column reductions: fold the 32/G row groups of each warp with shuffles, park the per-warp sums in a shared slab
+  // (plain 16-byte stores, no shared-memory atomics), add the 8 warps per column, one global atomic per column per CTA
+  auto reduce_cols = [&](float (&acc)[J][8], float* __restrict__ gout) {
 #pragma unroll
     for (int j = 0; j < J; j++) {
       const int c = 8 * (lg + G * j);
+      float r[8];
 #pragma unroll
       for (int i = 0; i < 8; i++) {
-        float a = as[j][i];
+        float a = acc[j][i];
 #pragma unroll
         for (int o = G; o < 32; o <<= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-        if (lane < G && c < C) atomicAdd(&sh_s[c + i], a);
+        r[i] = a;
       }
-    }
-  }
-  if (dgamma) {
-#pragma unroll
-    for (int j = 0; j < J; j++) {
-      const int c = 8 * (lg + G * j);
-#pragma unroll
-      for (int i = 0; i < 8; i++) {
-        float a = ag[j][i], b = ab[j][i];
-#pragma unroll
-        for (int o = G; o < 32; o <<= 1) {  // fold the 32/G row groups of this warp
-          a += __shfl_xor_sync(0xffffffffu, a, o);
-          b += __shfl_xor_sync(0xffffffffu, b, o);
-        }
-        if (lane < G && c < C) {
-          atomicAdd(&sh_g[c + i], a);
-          atomicAdd(&sh_b[c + i], b);
-        }
-      }
+      if (lane < G && c < C) store8(&sh_red[warp][c], r);
     }
     __syncthreads();
     for (int i = threadIdx.x; i < C; i += blockDim.x) {
-      atomicAdd(dgamma + i, sh_g[i]);
-      atomicAdd(dbeta + i, sh_b[i]);
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; w++) t += sh_red[w][i];
+      atomicAdd(gout + i, t);
     }
-  }
-  if (dbias) {
     __syncthreads();
-    for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(dbias + i, sh_s[i]);
+  };
+  if (dbias) reduce_cols(as, dbias);
+  if (dgamma) {
+    reduce_cols(ag, dgamma);
+    reduce_cols(ab, dbeta);
   }
 }
 

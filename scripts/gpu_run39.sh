@@ -1,0 +1,6 @@
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_ops_gpu.py -x -q -k "layernorm or ln" 2>&1 | tail -3
+timeout 900 python -m pytest tests/test_model_gpu.py -x -q 2>&1 | tail -3
+timeout 600 python bench.py --no-cpu-baseline --profile-out gpurun_out/kernels_39.csv > gpurun_out/bench_39.json 2> gpurun_out/bench_39.err; tail -3 gpurun_out/bench_39.err; python -c "
+import json; d=json.load(open('gpurun_out/bench_39.json')); print({k:d[k] for k in ('value','ms_per_step','gpu_launches_per_step','inference')}); print(d['e2e'])"
+grep layernorm gpurun_out/kernels_39.csv

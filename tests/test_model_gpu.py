@@ -331,3 +331,7 @@ def test_sliding_window_driver_batched_equals_per_crop():
     p8 = sliding_eval_rgbX_batched(ctx, img, mx, (64, 64), 2 / 3, "cuda", max_batch=8)
     assert p1.shape == (96, 128) and p1.dtype == np.int64
     assert (p1 != p8).mean() < 0.02, "batched and per-crop predictions differ on %.2f %% of the pixels" % (100 * (p1 != p8).mean())
+    from rgbx_semantic_segmentation_b200.utils.sliding_eval import sliding_eval_rgbX_gpu
+    pg = sliding_eval_rgbX_gpu(ctx, img, mx, (64, 64), 2 / 3, "cuda", max_batch=8)
+    assert pg.shape == (96, 128) and pg.dtype == np.int64
+    assert (pg != p8).mean() < 0.02, "device-resident and host-preprocessed predictions differ on %.2f %% of the pixels" % (100 * (pg != p8).mean())
