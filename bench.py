@@ -305,11 +305,11 @@ def main_ours(args):
         with torch.no_grad():
             for bs in (PER_GPU_BATCH, 1):
                 a_, b_ = rgb[:bs].contiguous(), x[:bs].contiguous()
-                for _ in range(4):
+                for _ in range(10):
                     model(a_, b_)
                 torch.cuda.synchronize()
                 i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                n_it = 20
+                n_it = 30
                 i0.record()
                 for _ in range(n_it):
                     out = model(a_, b_)

@@ -203,7 +203,7 @@ int cmx_frm_rectify_bwd(const float* dr1, int64_t lddr1, const float* dr2, int64
 /* out[b,y,x,:] (fp32) = bias + z0[b,y,x,:] + sum_i bilinear(z_i)[b,y,x,:]  (align_corners=False) */
 int cmx_upsample_sum_fwd(const void* z0, const void* z1, const void* z2, const void* z3,
                          int H0, int W0, int H1, int W1, int H2, int W2, int H3, int W3,
-                         const float* bias, float* out, int B, int C, void* stream);
+                         const float* bias, void* out, int out_dtype, int B, int C, void* stream);
 /* adjoint for ONE source: dz[b,yi,xi,:] = sum_{y,x} w(y,x;yi,xi) * dout[b,y,x,:]  (bf16 in, bf16 out) */
 int cmx_upsample_bwd(const void* dout, int Ho, int Wo, void* dz, int Hi, int Wi, int B, int C, void* stream);
 

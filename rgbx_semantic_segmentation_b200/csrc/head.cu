@@ -21,8 +21,9 @@ struct UpSrc {
   int H, W;
   float sh, sw;  // in/out scale (fp32, as PyTorch computes it)
 };
+template <typename TO>
 __global__ void __launch_bounds__(256) upsample_sum_kernel(const bf16* __restrict__ z0, UpSrc s1, UpSrc s2, UpSrc s3,
-                                                           const float* __restrict__ bias, float* __restrict__ out, int B, int H0,
+                                                           const float* __restrict__ bias, TO* __restrict__ out, int B, int H0,
                                                            int W0, int C) {
   pdl_trigger();
   const int c8 = C >> 3;
@@ -68,14 +69,18 @@ __global__ void __launch_bounds__(256) upsample_sum_kernel(const bf16* __restric
   store8(out + pix * C + c, acc);
 }
 CMX_API int cmx_upsample_sum_fwd(const void* z0, const void* z1, const void* z2, const void* z3, int H0, int W0, int H1, int W1,
-                                 int H2, int W2, int H3, int W3, const float* bias, float* out, int B, int C, void* stream) {
+                                 int H2, int W2, int H3, int W3, const float* bias, void* out, int out_dtype, int B, int C,
+                                 void* stream) {
   CMX_REQUIRE(C % 8 == 0, "upsample_sum: C %% 8");
   const long total = (long)B * H0 * W0 * (C >> 3);
   if (total == 0) return 0;
   UpSrc s1{(const bf16*)z1, H1, W1, (float)H1 / (float)H0, (float)W1 / (float)W0};
   UpSrc s2{(const bf16*)z2, H2, W2, (float)H2 / (float)H0, (float)W2 / (float)W0};
   UpSrc s3{(const bf16*)z3, H3, W3, (float)H3 / (float)H0, (float)W3 / (float)W0};
-  upsample_sum_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)z0, s1, s2, s3, bias, out, B, H0, W0, C);
+  if (out_dtype == CMX_F32)
+    upsample_sum_kernel<float><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)z0, s1, s2, s3, bias, (float*)out, B, H0, W0, C);
+  else
+    upsample_sum_kernel<bf16><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)z0, s1, s2, s3, bias, (bf16*)out, B, H0, W0, C);
   LAUNCH_DONE("upsample_sum_fwd");
 }
 

@@ -48,6 +48,9 @@ class Engine:
         self.embed = model.decode_head.linear_pred.in_channels
         self.ncls = model.decode_head.num_classes
         self.ncls_ld = (self.ncls + 7) // 8 * 8
+        # decoder BatchNorm input: fp32 by default; bf16 (CMX_DECODER_FUSE_BF16=1) saves 4 x 157 MB of traffic per step at
+        # batch 8 but measured no step-time difference (A/B on one box: 23.63-23.71 vs 23.63-23.65 ms)
+        self.fuse_dtype = bf16 if os.environ.get("CMX_DECODER_FUSE_BF16", "0") == "1" else f32
         self.names = [n for n, _ in model.named_parameters()]
         self.flat_p = None
         self.forced_dp = None        # test hook: {block prefix: tensor[2,B]}
@@ -64,6 +67,7 @@ class Engine:
         self.wgrad_stream = os.environ.get("CMX_WGRAD_STREAM", "1") != "0"
         self._wstreams = {}
         self._wkeep = {}
+        self._dec_prep = None
         self.poison = None           # debug hook: list of (tensor, allocation site) when NaN-poisoning is on
 
     # ------------------------------------------------------------------------------------------
@@ -685,21 +689,17 @@ class Engine:
         E_ = self.embed
         hd = self.model.decode_head
         p = "decode_head"
-        wf = self.W(p + ".linear_fuse.0.weight")  # [E, 4E]; concat order c4, c3, c2, c1 (MLPDecoder.py:77)
         c = _NS()
-        c.zs, c.wcomb = [], []
+        c.wcomb, c.bcat, btot = self._dec_prep
+        self._dec_prep = None
+        self._wgrad_join()      # the folded weights were computed on the companion stream while the encoder ran
+        c.zs = []
         for s in range(4):
-            Ms, Cs = feats[s].shape
-            wcomb = self.E(E_, Cs)
-            ops.mm(wf[:, (3 - s) * E_:(4 - s) * E_], self.W(p + f".linear_c{s + 1}.proj.weight"), wcomb, tb=True)
-            z = self.E(Ms, E_)
-            ops.mm(feats[s], wcomb, z)
-            c.zs.append(z); c.wcomb.append(wcomb)
-        c.bcat = torch.cat([self.P(p + f".linear_c{s + 1}.proj.bias") for s in (3, 2, 1, 0)]).view(1, 4 * E_)
-        btot = self.E(1, E_, dtype=f32)
-        ops.smallm_linear_fwd(c.bcat, self.P(p + ".linear_fuse.0.weight").view(E_, 4 * E_), self.P(p + ".linear_fuse.0.bias"), 0, btot)
+            z = self.E(feats[s].shape[0], E_)
+            ops.mm(feats[s], c.wcomb[s], z)
+            c.zs.append(z)
         M0 = feats[0].shape[0]
-        fuse = self.E(M0, E_, dtype=f32)
+        fuse = self.E(M0, E_, dtype=self.fuse_dtype)
         ops.upsample_sum_fwd(c.zs, sizes, btot.view(E_), fuse, B, E_)
         bn = hd.linear_fuse[1]
         c.mean, c.inv = self.bn_stats(p + ".linear_fuse.1", bn, fuse, training)
@@ -717,6 +717,22 @@ class Engine:
         self.tr("decode_head.logits", logits)
         return logits, c
 
+    def decoder_prep(self):
+        """weights-only part of decoder_fwd (the folded matrices and bias): issued at the start of the step on the
+        companion stream, so it overlaps the encoder instead of sitting on the decoder's critical path"""
+        E_ = self.embed
+        p = "decode_head"
+        wf = self.W(p + ".linear_fuse.0.weight")  # [E, 4E]; concat order c4, c3, c2, c1 (MLPDecoder.py:77)
+        wcombs = [self.E(E_, self.W(p + f".linear_c{s + 1}.proj.weight").shape[1]) for s in range(4)]
+        btot = self.E(1, E_, dtype=f32)
+        bcat = self.E(1, 4 * E_, dtype=f32)
+        with self._wgrad_ctx(wcombs, btot, bcat):
+            for s in range(4):
+                ops.mm(wf[:, (3 - s) * E_:(4 - s) * E_], self.W(p + f".linear_c{s + 1}.proj.weight"), wcombs[s], tb=True)
+            torch.cat([self.P(p + f".linear_c{s + 1}.proj.bias") for s in (3, 2, 1, 0)], out=bcat.view(4 * E_))
+            ops.smallm_linear_fwd(bcat, self.P(p + ".linear_fuse.0.weight").view(E_, 4 * E_), self.P(p + ".linear_fuse.0.bias"), 0, btot)
+        self._dec_prep = (wcombs, bcat, btot)
+
     def decoder_bwd(self, c, dlog, B):
         """dlog bf16 [M0, ncls] -> list of df_s bf16 [M_s, C_s]"""
         E_ = self.embed
@@ -732,15 +748,17 @@ class Engine:
                    rows_per_sample=c.N0)
         del dyb
         c.zs = None
-        # bias path: d btot = colsum(dfuse);  d bf = d btot;  d Wf += d btot (x) bcat;  d bcat = Wf^T d btot
-        dbt = self.Z(1, E_)
-        ops.colsum(dfuse, dbt.view(E_))
-        dbcat = self.E(1, 4 * E_, dtype=f32)
-        ops.smallm_linear_bwd(dbt, dbt, 0, c.bcat, self.P(p + ".linear_fuse.0.weight").view(E_, 4 * E_), dbcat,
-                              self.G(p + ".linear_fuse.0.weight").view(E_, 4 * E_), self.G(p + ".linear_fuse.0.bias"),
-                              self.E(1, E_, dtype=f32))
-        for j, s in enumerate((3, 2, 1, 0)):
-            self.G(p + f".linear_c{s + 1}.proj.bias").add_(dbcat[0, j * E_:(j + 1) * E_])
+        # bias path (parameter gradients only -> companion stream): d btot = colsum(dfuse);  d bf = d btot;
+        # d Wf += d btot (x) bcat;  d bcat = Wf^T d btot
+        with self._wgrad_ctx(dfuse, c.bcat):
+            dbt = self.Z(1, E_)
+            ops.colsum(dfuse, dbt.view(E_))
+            dbcat = self.E(1, 4 * E_, dtype=f32)
+            ops.smallm_linear_bwd(dbt, dbt, 0, c.bcat, self.P(p + ".linear_fuse.0.weight").view(E_, 4 * E_), dbcat,
+                                  self.G(p + ".linear_fuse.0.weight").view(E_, 4 * E_), self.G(p + ".linear_fuse.0.bias"),
+                                  self.E(1, E_, dtype=f32))
+            for j, s in enumerate((3, 2, 1, 0)):
+                self.G(p + f".linear_c{s + 1}.proj.bias").add_(dbcat[0, j * E_:(j + 1) * E_])
         wf = self.W(p + ".linear_fuse.0.weight")
         gf = self.G2(p + ".linear_fuse.0.weight")
         H0, W0 = c.sizes[0]
@@ -861,6 +879,7 @@ class Engine:
     def forward_logits(self, rgb, x):
         """eval / inference path: full-resolution NCHW fp32 logits (builder.py:212-238)"""
         self._begin(rgb, x)
+        self.decoder_prep()
         training = self.model.training
         B, _, H, W = rgb.shape
         dp, dm = self._make_dp(B, training)
@@ -873,6 +892,7 @@ class Engine:
     def forward_loss(self, rgb, x, label, ignore_index, with_grad):
         """loss (0-d fp32).  with_grad: also runs the complete backward pass, leaving d loss / d theta in flat_g."""
         self._begin(rgb, x)
+        self.decoder_prep()
         training = self.model.training
         B, _, H, W = rgb.shape
         assert B <= 16, "per-GPU batch > 16 is not supported by the FRM small-M kernels"

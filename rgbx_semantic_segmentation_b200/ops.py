@@ -389,7 +389,7 @@ def upsample_sum_fwd(zs, sizes, bias, out, B, C):
     z = list(zs) + [None] * (4 - len(zs))
     sz = list(sizes) + [(1, 1)] * (4 - len(sizes))
     _call("cmx_upsample_sum_fwd", _p(z[0]), _p(z[1]), _p(z[2]), _p(z[3]), sz[0][0], sz[0][1], sz[1][0], sz[1][1],
-                                                sz[2][0], sz[2][1], sz[3][0], sz[3][1], _p(bias), out.data_ptr(), B, C, _stream(), nbytes=_nb(*zs) + _nb(out))
+                                                sz[2][0], sz[2][1], sz[3][0], sz[3][1], _p(bias), out.data_ptr(), _dt(out), B, C, _stream(), nbytes=_nb(*zs) + _nb(out))
     return out
 
 

@@ -347,6 +347,9 @@ def test_upsample_sum_and_adjoint(sizes):
     for z in zr[1:]:
         ref = ref + F.interpolate(z, size=(H0, W0), mode="bilinear", align_corners=False)
     close(out, ref.permute(0, 2, 3, 1).reshape(-1, C), 1e-5, 1e-5, "upsample sum")
+    out_bf = torch.empty(B * H0 * W0, C, device=DEV, dtype=bf)     # the engine's bf16 BatchNorm-input variant
+    ops.upsample_sum_fwd(zs, sizes, bias, out_bf, B, C)
+    assert torch.equal(out_bf, out.to(bf)), "bf16 output must be the rounded fp32 result"
     dout = rnd(B * H0 * W0, C, dtype=bf)
     ref.backward(dout.float().reshape(B, H0, W0, C).permute(0, 3, 1, 2))
     for i in (1, 2, 3):
