@@ -335,3 +335,41 @@ def test_sliding_window_driver_batched_equals_per_crop():
     pg = sliding_eval_rgbX_gpu(ctx, img, mx, (64, 64), 2 / 3, "cuda", max_batch=8)
     assert pg.shape == (96, 128) and pg.dtype == np.int64
     assert (pg != p8).mean() < 0.02, "device-resident and host-preprocessed predictions differ on %.2f %% of the pixels" % (100 * (pg != p8).mean())
+
+
+def test_ragged_input_size_train_and_eval_vs_oracle():
+    """input not a multiple of 32 (72x104 -> stages 18x26, 9x13, 5x7, 3x4: odd feature maps, non-integer bilinear ratios,
+    SR convolutions that drop the last rows/columns like nn.Conv2d(k=s=R) does), batch 1, plus an all-ignored label row
+    block; loss, all gradients and eval logits against the fp32 oracle."""
+    spec = cmx_ref.MIT_SPECS["mit_b0"]
+    sd = synth_state_dict(spec, 9, seed=0)
+    rgb, x, gt = synth_inputs(1, 72, 104, 9, seed=3)
+    gt[:, :7] = 255
+    m = make("mit_b0", 9, True, sd).train()
+    m._eng().stochastic = False
+    loss = m(rgb.cuda(), x.cuda(), gt.cuda())
+    loss.backward()
+    params = {k: v.clone().requires_grad_(v.is_floating_point() and not k.endswith(("running_mean", "running_var")))
+              for k, v in sd.items()}
+    ref = cmx_ref.forward(params, spec, rgb, x, gt, training=True, decoder_bn_eps=1e-3)
+    ref.backward()
+    assert abs(loss.item() - ref.item()) <= 5e-3 * abs(ref.item()), (loss.item(), ref.item())
+    grads_vs(m, {n: params[n].grad for n, _ in m.named_parameters()}, "b0 72x104")
+    me = make("mit_b0", 9, False, sd).eval()
+    out = me(rgb.cuda(), x.cuda()).cpu()
+    with torch.no_grad():
+        refl = cmx_ref.forward(sd, spec, rgb, x, training=False, decoder_bn_eps=1e-5)
+    assert out.shape == refl.shape == (1, 9, 72, 104)
+    check_logits(out, refl, "b0 72x104 eval")
+
+
+def test_all_pixels_ignored_gives_nan_loss_like_torch():
+    """nn.CrossEntropyLoss(mean, ignore_index) over zero valid pixels is 0/0 = NaN in the reference (train.py:72-73)"""
+    spec = cmx_ref.MIT_SPECS["mit_b0"]
+    sd = synth_state_dict(spec, 5, seed=0)
+    rgb, x, gt = synth_inputs(1, 64, 64, 5, seed=2)
+    gt[:] = 255
+    m = make("mit_b0", 5, True, sd).train()
+    with torch.no_grad():
+        loss = m(rgb.cuda(), x.cuda(), gt.cuda())
+    assert torch.isnan(loss).item()
