@@ -132,6 +132,17 @@ int cmx_col2im_nhwc(const void* dcol, const void* add, int add_dtype, int64_t ld
  * (fp32 [Co,kpad] grad -> ACCUMULATED into [Co,Ci,kh,kw]) */
 int cmx_convw_pack(const float* w, void* wp, int Co, int Ci, int kh, int kw, int kpad, void* stream);
 int cmx_convw_unpack_grad(const float* gp, float* gw, int Co, int Ci, int kh, int kw, int kpad, void* stream);
+/* the same two operations for ALL real convolutions of the model in one launch each (start of the step / end of the
+ * backward pass).  descs: DEVICE array of n descriptors; gp/gw are only read by the unpack, w/wp only by the pack. */
+typedef struct CmxConvDesc {
+  const float* w;   /* [Co, Ci, kh, kw] fp32 master weight */
+  void* wp;         /* [Co, kpad] bf16 packed (kh, kw, ci)-major operand */
+  const float* gp;  /* [Co, kpad] fp32 packed gradient (accumulated by the wgrad GEMM) */
+  float* gw;        /* [Co, Ci, kh, kw] fp32 gradient, += */
+  int32_t Co, Ci, kh, kw, kpad, reserved;
+} CmxConvDesc;
+int cmx_convw_pack_multi(const CmxConvDesc* descs, int n, void* stream);
+int cmx_convw_unpack_grad_multi(const CmxConvDesc* descs, int n, void* stream);
 /* fp32 -> bf16 cast (weights), optionally many at once is done by the caller on a flat buffer */
 int cmx_cast_f32_bf16(const float* x, void* y, int64_t n, void* stream);
 int cmx_cast_bf16_f32(const void* x, float* y, int64_t n, void* stream);

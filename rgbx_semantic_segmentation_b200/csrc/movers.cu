@@ -168,6 +168,45 @@ CMX_API int cmx_convw_unpack_grad(const float* gp, float* gw, int Co, int Ci, in
   LAUNCH_DONE("convw_unpack_grad");
 }
 
+// all real convolutions of the model in ONE launch each way (34 for MiT-B2): blockIdx.y = convolution, grid-stride in x
+__global__ void __launch_bounds__(256) convw_pack_multi_kernel(const CmxConvDesc* __restrict__ d) {
+  pdl_trigger();
+  const CmxConvDesc c = d[blockIdx.y];
+  const int K = c.kh * c.kw * c.Ci;
+  bf16* wp = reinterpret_cast<bf16*>(c.wp);
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < (long)c.Co * c.kpad; idx += (long)gridDim.x * blockDim.x) {
+    const int j = (int)(idx % c.kpad);
+    const int co = (int)(idx / c.kpad);
+    float v = 0.f;
+    if (j < K) {
+      const int ci = j % c.Ci, tap = j / c.Ci;
+      v = c.w[((long)co * c.Ci + ci) * (c.kh * c.kw) + tap];
+    }
+    wp[idx] = __float2bfloat16(v);
+  }
+}
+__global__ void __launch_bounds__(256) convw_unpack_multi_kernel(const CmxConvDesc* __restrict__ d) {
+  pdl_trigger();
+  const CmxConvDesc c = d[blockIdx.y];
+  const int K = c.kh * c.kw * c.Ci;
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < (long)c.Co * K; idx += (long)gridDim.x * blockDim.x) {
+    const int j = (int)(idx % K);
+    const int co = (int)(idx / K);
+    const int ci = j % c.Ci, tap = j / c.Ci;
+    c.gw[((long)co * c.Ci + ci) * (c.kh * c.kw) + tap] += c.gp[(long)co * c.kpad + j];
+  }
+}
+CMX_API int cmx_convw_pack_multi(const CmxConvDesc* descs, int n, void* stream) {
+  if (n <= 0) return 0;
+  convw_pack_multi_kernel<<<dim3(64, n), 256, 0, (cudaStream_t)stream>>>(descs);
+  LAUNCH_DONE("convw_pack_multi");
+}
+CMX_API int cmx_convw_unpack_grad_multi(const CmxConvDesc* descs, int n, void* stream) {
+  if (n <= 0) return 0;
+  convw_unpack_multi_kernel<<<dim3(64, n), 256, 0, (cudaStream_t)stream>>>(descs);
+  LAUNCH_DONE("convw_unpack_grad_multi");
+}
+
 // ---- casts / axpby -----------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ y, long n) {
   pdl_trigger();

@@ -91,7 +91,27 @@ class Engine:
         self.flat_g = torch.zeros(total, device=device, dtype=f32)
         self.flat_w = torch.zeros(total, device=device, dtype=bf16)
         self.params = params
-        self.packed = {}
+        # real (non-depthwise, non-1x1) convolutions - patch embeds and SR convs: (kh,kw,ci)-packed bf16 operands and packed
+        # fp32 gradient accumulators live in two flat buffers, described once by a device table, so that packing (start
+        # of the step) and gradient unpacking (end of the backward pass) are ONE launch each instead of one per conv
+        import struct
+        convs, tot = [], 0
+        for n in self.names:
+            s4 = tuple(params[n].shape)
+            if len(s4) == 4 and s4[2] > 1 and s4[1] > 1:
+                kpad = (s4[1] * s4[2] * s4[3] + 7) // 8 * 8
+                convs.append((n, s4, kpad, tot))
+                tot += (s4[0] * kpad + 63) // 64 * 64
+        self.pk_w = torch.zeros(max(tot, 1), device=device, dtype=bf16)
+        self.pk_g = torch.zeros(max(tot, 1), device=device, dtype=f32)
+        self.packed, self.packed_g, blob = {}, {}, b""
+        for n, s4, kpad, o in convs:
+            self.packed[n] = self.pk_w[o:o + s4[0] * kpad].view(s4[0], kpad)
+            self.packed_g[n] = self.pk_g[o:o + s4[0] * kpad].view(s4[0], kpad)
+            blob += struct.pack("<QQQQiiiiii", flat.data_ptr() + 4 * off[n], self.packed[n].data_ptr(), self.packed_g[n].data_ptr(),
+                                self.flat_g.data_ptr() + 4 * off[n], s4[0], s4[1], s4[2], s4[3], kpad, 0)
+        self.n_convs = len(convs)
+        self.conv_table = torch.frombuffer(bytearray(blob), dtype=torch.uint8).to(device) if convs else None
         self.buffers = dict(self.model.named_buffers())
         # DropPath table (block prefix, probability) — device tensor built once (graph capture forbids H2D)
         self._dp_keys, probs = [], []
@@ -145,14 +165,8 @@ class Engine:
     def refresh_weights(self):
         """fp32 master -> bf16 operand copies (one flat cast) + (kh,kw,ci)-packed conv weights"""
         ops.cast_f32_bf16(self.flat_p, self.flat_w)
-        for n in self.names:
-            s = self.shape[n]
-            if len(s) == 4 and s[2] > 1 and s[1] > 1:  # real (non-depthwise, non-1x1) convs: patch embeds, SR
-                k = s[1] * s[2] * s[3]
-                kpad = (k + 7) // 8 * 8
-                if n not in self.packed:
-                    self.packed[n] = torch.empty(s[0], kpad, device=self.flat_p.device, dtype=bf16)
-                ops.convw_pack(self.P(n), self.packed[n])
+        if self.n_convs:
+            ops.convw_pack_multi(self.conv_table, self.n_convs)
 
     # ------------------------------------------------------------------------------------------
     # small helpers
@@ -282,11 +296,8 @@ class Engine:
         ops.layernorm_bwd(dx0, c.y, c.mean, c.rstd, self.P(name + ".norm.weight"), dx=dy,
                           dgamma=self.G(name + ".norm.weight"), dbeta=self.G(name + ".norm.bias"),
                           dbias=self.G(name + ".proj.bias"))   # conv bias gradient = column sums of dy, folded in
-        with self._wgrad_ctx(dy, c.col):
-            gp = self.Z(C, c.wp.shape[1])
-            ops.mm(dy, c.col, gp, ta=True, tb=True, accumulate=True)
-            ops.convw_unpack_grad(gp, self.G(name + ".proj.weight"))
-            del gp
+        with self._wgrad_ctx(dy, c.col):   # packed gradient; unpacked for all convs at the end of the backward pass
+            ops.mm(dy, c.col, self.packed_g[name + ".proj.weight"], ta=True, tb=True, accumulate=True)
         dcol = None
         if c.s != 0:
             dcol = self.E(M, c.wp.shape[1])
@@ -442,10 +453,7 @@ class Engine:
                               dbias=self.G(p + ".attn.sr.bias"))
             wsr = self.packed[p + ".attn.sr.weight"]
             with self._wgrad_ctx(dsr, c.pat):
-                gp = self.Z(C, wsr.shape[1])
-                ops.mm(dsr, c.pat, gp, ta=True, tb=True, accumulate=True)
-                ops.convw_unpack_grad(gp, self.G(p + ".attn.sr.weight"))
-                del gp
+                ops.mm(dsr, c.pat, self.packed_g[p + ".attn.sr.weight"], ta=True, tb=True, accumulate=True)
             dpat = self.E(B * Nk, wsr.shape[1])
             ops.mm(dsr, wsr, dpat, tb=True)
             dxn_b = self.E(M, C)
@@ -908,6 +916,7 @@ class Engine:
             ops.ce_finalize(acc, loss)
             return loss
         self.flat_g.zero_()
+        self.pk_g.zero_()
         dl = self.Z(B * h0 * w0, self.ncls_ld)
         ops.ce_upsampled(logits, label, ignore_index, acc, dl[:, :self.ncls], B, h0, w0, H, W, self.ncls)
         dlog = self.E(B * h0 * w0, self.ncls_ld)
@@ -956,6 +965,8 @@ class Engine:
             if s == 0:
                 pending = None
             ctx.stages[s] = None
+        if self.n_convs:   # every weight-gradient stream has been joined: add all packed conv gradients into flat_g
+            ops.convw_unpack_grad_multi(self.conv_table, self.n_convs)
         return loss
 
     def _begin(self, rgb, x):

@@ -256,6 +256,15 @@ def convw_pack(w, wp):
     return wp
 
 
+def convw_pack_multi(table, n):
+    """table: device uint8 tensor holding n CmxConvDesc records (include/cmx_b200.h)"""
+    _call("cmx_convw_pack_multi", table.data_ptr(), n, _stream())
+
+
+def convw_unpack_grad_multi(table, n):
+    _call("cmx_convw_unpack_grad_multi", table.data_ptr(), n, _stream())
+
+
 def convw_unpack_grad(gp, gw):
     Co, Ci, kh, kw = gw.shape
     _call("cmx_convw_unpack_grad", gp.data_ptr(), gw.data_ptr(), Co, Ci, kh, kw, gp.shape[1], _stream())

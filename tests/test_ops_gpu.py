@@ -212,6 +212,26 @@ def test_im2col_paths():
     ops.convw_unpack_grad(gp, gw)
     ref = 1 + gp[:, :147].reshape(64, 7, 7, 3).permute(0, 3, 1, 2)
     close(gw, ref, 0, 1e-6, "unpack grad")
+    # the one-launch variants over a device descriptor table (what the engine uses) == the per-conv calls
+    import struct
+    shapes = [(64, 3, 7, 7), (128, 64, 3, 3), (64, 64, 8, 8), (40, 24, 2, 2)]
+    ws = [rnd(*sh, scale=0.1) for sh in shapes]
+    kp = [(sh[1] * sh[2] * sh[3] + 7) // 8 * 8 for sh in shapes]
+    wps = [torch.full((sh[0], k), 7.0, device=DEV, dtype=bf) for sh, k in zip(shapes, kp)]
+    gps = [rnd(sh[0], k) for sh, k in zip(shapes, kp)]
+    gws = [rnd(*sh) for sh in shapes]
+    gws0 = [g.clone() for g in gws]
+    blob = b"".join(struct.pack("<QQQQiiiiii", w.data_ptr(), wp.data_ptr(), gp.data_ptr(), gw.data_ptr(), *sh, k, 0)
+                    for w, wp, gp, gw, sh, k in zip(ws, wps, gps, gws, shapes, kp))
+    table = torch.frombuffer(bytearray(blob), dtype=torch.uint8).to(DEV)
+    ops.convw_pack_multi(table, len(shapes))
+    ops.convw_unpack_grad_multi(table, len(shapes))
+    for w, wp, gp, gw, gw0, sh, k in zip(ws, wps, gps, gws, gws0, shapes, kp):
+        one = torch.empty_like(wp)
+        ops.convw_pack(w, one)
+        assert torch.equal(wp, one)
+        ops.convw_unpack_grad(gp, gw0)
+        assert torch.equal(gw, gw0)
 
 
 def test_casts_colsum_relu():
