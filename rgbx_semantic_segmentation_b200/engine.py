@@ -19,6 +19,7 @@ Design notes
     bilinear interpolation commutes with a per-pixel linear map — so the concat tensor never exists.
 """
 import os
+import re
 
 import torch
 
@@ -51,7 +52,14 @@ class Engine:
         # decoder BatchNorm input: fp32 by default; bf16 (CMX_DECODER_FUSE_BF16=1) saves 4 x 157 MB of traffic per step at
         # batch 8 but measured no step-time difference (A/B on one box: 23.63-23.71 vs 23.63-23.65 ms)
         self.fuse_dtype = bf16 if os.environ.get("CMX_DECODER_FUSE_BF16", "0") == "1" else f32
-        self.names = [n for n, _ in model.named_parameters()]
+        # Flat-buffer order = [decoder, stage 4, stage 3 | stage 2, stage 1]: the backward pass finishes the parameter
+        # gradients of the first group (91 % of the bytes for MiT-B2) before it starts stage 2, so data-parallel training
+        # can all-reduce that contiguous slice while the two high-resolution stages are still running (parallel.py)
+        names = [n for n, _ in model.named_parameters()]
+        early = [n for n in names if self._stage_of(n) >= 2]
+        late = [n for n in names if self._stage_of(n) < 2]
+        self.names = early + late
+        self.n_early = len(early)
         self.flat_p = None
         self.forced_dp = None        # test hook: {block prefix: tensor[2,B]}
         self.forced_dropout = None   # test hook: tensor[B, E]
@@ -69,6 +77,17 @@ class Engine:
         self._wkeep = {}
         self._dec_prep = None
         self.poison = None           # debug hook: list of (tensor, allocation site) when NaN-poisoning is on
+
+    @staticmethod
+    def _stage_of(name):
+        """0..3 for backbone parameters of that stage, 4 for the decoder"""
+        m = re.match(r"backbone\.(?:extra_)?(?:patch_embed|block|norm)(\d)", name)
+        if m:
+            return int(m.group(1)) - 1
+        m = re.match(r"backbone\.(?:FRMs|FFMs)\.(\d)", name)
+        if m:
+            return int(m.group(1))
+        return 4
 
     # ------------------------------------------------------------------------------------------
     # flat parameter / gradient storage
@@ -111,6 +130,8 @@ class Engine:
             blob += struct.pack("<QQQQiiiiii", flat.data_ptr() + 4 * off[n], self.packed[n].data_ptr(), self.packed_g[n].data_ptr(),
                                 self.flat_g.data_ptr() + 4 * off[n], s4[0], s4[1], s4[2], s4[3], kpad, 0)
         self.n_convs = len(convs)
+        self.n_convs_early = sum(1 for n, _, _, _ in convs if self._stage_of(n) >= 2)
+        self.split_off = off[self.names[self.n_early]] if self.n_early < len(self.names) else total   # first late element
         self.conv_table = torch.frombuffer(bytearray(blob), dtype=torch.uint8).to(device) if convs else None
         self.buffers = dict(self.model.named_buffers())
         # DropPath table (block prefix, probability) — device tensor built once (graph capture forbids H2D)
@@ -899,6 +920,17 @@ class Engine:
 
     def forward_loss(self, rgb, x, label, ignore_index, with_grad):
         """loss (0-d fp32).  with_grad: also runs the complete backward pass, leaving d loss / d theta in flat_g."""
+        gen = self.forward_loss_steps(rgb, x, label, ignore_index, with_grad)
+        try:
+            while True:
+                next(gen)
+        except StopIteration as done:
+            return done.value
+
+    def forward_loss_steps(self, rgb, x, label, ignore_index, with_grad):
+        """generator form of forward_loss: yields ONCE (with_grad only), after the backward pass has completed every
+        gradient of flat_g[:split_off] (decoder, stages 4 and 3) and all side streams are joined - the point where a
+        data-parallel caller starts the all-reduce of that slice (and may switch CUDA graphs); returns the loss."""
         self._begin(rgb, x)
         self.decoder_prep()
         training = self.model.training
@@ -965,8 +997,13 @@ class Engine:
             if s == 0:
                 pending = None
             ctx.stages[s] = None
-        if self.n_convs:   # every weight-gradient stream has been joined: add all packed conv gradients into flat_g
-            ops.convw_unpack_grad_multi(self.conv_table, self.n_convs)
+            if s == 2:
+                # every weight-gradient stream has been joined: add the packed conv gradients of stages 3-4 into flat_g
+                if self.n_convs_early:
+                    ops.convw_unpack_grad_multi(self.conv_table, self.n_convs_early)
+                yield "early_gradients_ready"
+        if self.n_convs > self.n_convs_early:
+            ops.convw_unpack_grad_multi(self.conv_table[56 * self.n_convs_early:], self.n_convs - self.n_convs_early)
         return loss
 
     def _begin(self, rgb, x):

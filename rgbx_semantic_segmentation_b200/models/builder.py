@@ -160,27 +160,62 @@ class EncoderDecoder(nn.Module):
         return g["out"].clone()
 
     def _run_step(self, rgb, modal_x, label):
+        """One fused forward+backward step.  The engine yields once, when the gradients of flat_g[:split_off] are final:
+        under FlatDataParallel their all-reduce starts there and overlaps the rest of the backward pass; with CUDA graphs
+        the step is therefore captured as TWO graphs sharing one memory pool (NCCL itself is never captured)."""
+        from ..parallel import allreduce_slice_async
         rgb, modal_x = rgb.float().contiguous(), modal_x.float().contiguous()
         ign = self.criterion.ignore_index
         eng = self._eng()
         key = ("train", tuple(rgb.shape), self.training, rgb.device.index)
+
+        def finish(gen):
+            try:
+                next(gen)
+            except StopIteration as done:
+                return done.value
+            raise RuntimeError("cmx_b200: the engine yielded more than once")
+
+        def eager(a, b, c):
+            gen = eng.forward_loss_steps(a, b, c, ign, with_grad=True)
+            next(gen)
+            allreduce_slice_async(self, eng.flat_g[:eng.split_off])
+            loss = finish(gen)
+            allreduce_slice_async(self, eng.flat_g[eng.split_off:])
+            return loss
+
         if not self.use_cuda_graph or eng.forced_dp is not None or eng.forced_dropout is not None:
-            return eng.forward_loss(rgb, modal_x, label, ign, with_grad=True)
+            return eager(rgb, modal_x, label)
         g = self._graphs.get(key)
         if g is None:
             self._graphs[key] = {"warm": 1}
-            return eng.forward_loss(rgb, modal_x, label, ign, with_grad=True)
+            return eager(rgb, modal_x, label)
         if "graph" not in g:
             g["rgb"], g["x"], g["label"] = rgb.clone(), modal_x.clone(), label.to(torch.int64).clone()
-            graph = torch.cuda.CUDAGraph()
+            split = self._flat_dp is not None
             torch.cuda.synchronize()
-            with torch.cuda.graph(graph):
-                g["loss"] = eng.forward_loss(g["rgb"], g["x"], g["label"], ign, with_grad=True)
-            g["graph"] = graph
+            if not split:
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    g["loss"] = eng.forward_loss(g["rgb"], g["x"], g["label"], ign, with_grad=True)
+                g["graph"], g["graph2"] = graph, None
+            else:
+                pool = torch.cuda.graph_pool_handle()
+                ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+                with torch.cuda.graph(ga, pool=pool):
+                    gen = eng.forward_loss_steps(g["rgb"], g["x"], g["label"], ign, with_grad=True)
+                    next(gen)
+                with torch.cuda.graph(gb, pool=pool):
+                    g["loss"] = finish(gen)
+                g["graph"], g["graph2"] = ga, gb
         g["rgb"].copy_(rgb)
         g["x"].copy_(modal_x)
         g["label"].copy_(label)
         g["graph"].replay()
+        if g["graph2"] is not None:
+            allreduce_slice_async(self, eng.flat_g[:eng.split_off])
+            g["graph2"].replay()
+            allreduce_slice_async(self, eng.flat_g[eng.split_off:])
         return g["loss"].clone()
 
     def __getstate__(self):
@@ -190,4 +225,5 @@ class EncoderDecoder(nn.Module):
         st["_engine"] = None
         st["_graphs"] = {}
         st["_flat_dp"] = None
+        st.pop("_flat_pending", None)
         return st

@@ -4,8 +4,10 @@ NCCL process group from engine/engine.py:56).
 `torch.nn.parallel.DistributedDataParallel(model)` works unchanged (gradients reach it through autograd), but because
 the fused step delivers all 810 gradients at once, DDP's per-parameter bucket copies (~1600 tiny copy kernels) are
 fully exposed.  `FlatDataParallel` keeps the same semantics — parameters/buffers broadcast from rank 0 at construction,
-gradients averaged over ranks every step — with ONE NCCL all-reduce over the engine's flat fp32 gradient buffer
-(266 MB for MiT-B2: ~0.7 ms at 8 ranks over NVLink/NVSwitch), issued right after the backward kernels."""
+gradients averaged over ranks every step — with TWO NCCL all-reduces over contiguous slices of the engine's flat fp32
+gradient buffer (266 MB for MiT-B2): the slice holding the decoder and stages 4-3 (91 % of the bytes) is reduced as soon
+as the backward pass has finished it, concurrently with the backward of the two high-resolution stages; the rest right
+after the last backward kernel (train.py:145-146 relies on DDP's bucketed overlap for the same purpose)."""
 import torch
 import torch.distributed as dist
 import torch.nn as nn
@@ -28,11 +30,48 @@ class FlatDataParallel(nn.Module):
         return self.module(*args, **kwargs)
 
 
+class _Pending:
+    """asynchronous all-reduces of slices of the flat gradient buffer issued during the step; wait() makes the current
+    stream wait for them (no host block) and returns the divisor"""
+
+    def __init__(self, world):
+        self.world, self.works = world, []
+
+    def add(self, work):
+        self.works.append(work)
+
+    def wait(self):
+        for w in self.works:
+            w.wait()
+        self.works = []
+        return self.world
+
+
+def allreduce_slice_async(model, flat_slice):
+    """SUM all-reduce of one contiguous slice of the flat gradient buffer, ordered after the work already enqueued on the
+    current stream and running on the process group's own stream, i.e. concurrently with whatever the caller enqueues
+    next (the rest of the backward pass).  No-op (returns None) unless the model is wrapped in FlatDataParallel."""
+    dp = getattr(model, "_flat_dp", None)
+    if dp is None:
+        return None
+    group, world = dp
+    pend = getattr(model, "_flat_pending", None)
+    if pend is None:
+        pend = model._flat_pending = _Pending(world)
+    if flat_slice.numel():
+        pend.add(dist.all_reduce(flat_slice, op=dist.ReduceOp.SUM, group=group, async_op=True))
+    return pend
+
+
 def allreduce_flat_grads_(model, flat):
-    """in-place SUM all-reduce of the flat gradient buffer; returns the divisor (world size) or 1"""
+    """finish the gradient reduction: waits for the slices already in flight (issued by the step itself, overlapped with the
+    backward pass), or - if none were issued - all-reduces the whole flat buffer now; returns the divisor (world size) or 1"""
     dp = getattr(model, "_flat_dp", None)
     if dp is None:
         return 1
     group, world = dp
+    pend = getattr(model, "_flat_pending", None)
+    if pend is not None and pend.works:
+        return pend.wait()
     dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
     return world

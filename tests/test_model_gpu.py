@@ -373,3 +373,49 @@ def test_all_pixels_ignored_gives_nan_loss_like_torch():
     with torch.no_grad():
         loss = m(rgb.cuda(), x.cuda(), gt.cuda())
     assert torch.isnan(loss).item()
+
+
+def test_flat_data_parallel_two_graph_step_single_process_group():
+    """FlatDataParallel path on one GPU (single-rank NCCL group): the step is captured as TWO CUDA graphs around the
+    point where the first gradient slice is final, the slice all-reduces are issued asynchronously and awaited in
+    backward(); loss and gradients must match the plain single-graph model, and the overlap plumbing must not leak
+    pending work between steps."""
+    import torch.distributed as dist
+    from rgbx_semantic_segmentation_b200.parallel import FlatDataParallel
+    spec = cmx_ref.MIT_SPECS["mit_b0"]
+    sd = synth_state_dict(spec, 9, seed=0)
+    rgb, x, gt = synth_inputs(2, 64, 96, 9, seed=1)
+    created = not dist.is_initialized()
+    if created:
+        dist.init_process_group("nccl", init_method="tcp://127.0.0.1:29531", rank=0, world_size=1)
+    try:
+        plain = make("mit_b0", 9, True, sd).train()
+        plain._eng().stochastic = False
+        m = make("mit_b0", 9, True, sd).train()
+        m._eng().stochastic = False
+        net = FlatDataParallel(m)
+        eng = m._eng()
+        ref_loss = plain(rgb.cuda(), x.cuda(), gt.cuda())
+        ref_loss.backward()
+        losses = []
+        for it in range(4):     # eager, eager->capture, replay, replay
+            for p in m.parameters():
+                p.grad = None
+            loss = net(rgb.cuda(), x.cuda(), gt.cuda())
+            loss.backward()
+            losses.append(loss.item())
+            assert not m._flat_pending.works, "all-reduce handles must be consumed by backward()"
+        key = [k for k in m._graphs if k[0] == "train"][0]
+        assert m._graphs[key]["graph2"] is not None, "FlatDataParallel must capture the step as two graphs"
+        assert 0 < eng.split_off < eng.total and eng.n_early > 0
+        assert all(abs(v - ref_loss.item()) < 2e-3 * abs(ref_loss.item()) for v in losses), (losses, ref_loss.item())
+        pg = dict(plain.named_parameters())
+        worst = 1.0
+        for n, p in m.named_parameters():
+            a, b = p.grad.double().flatten(), pg[n].grad.double().flatten()
+            if b.norm() > 1e-4:
+                worst = min(worst, (a @ b / (a.norm() * b.norm())).item())
+        assert worst > 0.98, worst
+    finally:
+        if created:
+            dist.destroy_process_group()
