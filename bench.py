@@ -299,6 +299,12 @@ def main_ours(args):
             ach = nb / (t * 1e-3) / 1e9
             roof = {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
                     "traffic": None}
+        # whole-step roofline: every launch at max(bytes / HBM peak, flops / sustained bf16 peak), against the measured step
+        t_roof = sum(max(nb_ / (pk["hbm_gbs"] * 1e9), fl_ / (pk["bf16_tflops_sustained"] * 1e12)) for _, _, _, fl_, nb_ in prof) * 1e3
+        roof["step"] = {"algorithmic_gbytes": sum(p_[4] for p_ in prof) / 1e9, "algorithmic_tflop": sum(p_[3] for p_ in prof) / 1e12,
+                        "t_roofline_ms": t_roof, "t_measured_ms": ms / args.steps, "frac": t_roof / (ms / args.steps),
+                        "note": "sum over the launches of one step (launches without a byte count contribute 0); "
+                                "measured = graph-replayed training step incl. optimizer"}
         roof.update(kernel=name, launches_per_step=n, avg_us=1e3 * t / n, share_of_step=t / total, peak_src=pk["src"],
                     timing="CUDA events around every launch of one eager step run on a single stream with the host pre-enqueued "
                            "(isolated kernel durations; their sum is %.1f ms, the graph-replayed multi-stream step overlaps them)" % total,
