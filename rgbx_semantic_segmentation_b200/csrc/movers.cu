@@ -168,42 +168,53 @@ CMX_API int cmx_convw_unpack_grad(const float* gp, float* gw, int Co, int Ci, in
   LAUNCH_DONE("convw_unpack_grad");
 }
 
-// all real convolutions of the model in ONE launch each way (34 for MiT-B2): blockIdx.y = convolution, grid-stride in x
+// all real convolutions of the model in ONE launch each way (34 for MiT-B2): blockIdx.y = convolution, blockIdx.x walks
+// the output channels; one [Ci, kh*kw] <-> [(kh*kw), Ci] row transpose per CTA through shared memory, so both the
+// global read and the global write of a row are contiguous
+constexpr int CONVW_MAXK = 4608;  // 512 x 3 x 3 (the largest patch embed); SR convs: C * R * R <= 4096
 __global__ void __launch_bounds__(256) convw_pack_multi_kernel(const CmxConvDesc* __restrict__ d) {
   pdl_trigger();
+  __shared__ float row[CONVW_MAXK];
   const CmxConvDesc c = d[blockIdx.y];
-  const int K = c.kh * c.kw * c.Ci;
+  const int taps = c.kh * c.kw, K = taps * c.Ci;
   bf16* wp = reinterpret_cast<bf16*>(c.wp);
-  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < (long)c.Co * c.kpad; idx += (long)gridDim.x * blockDim.x) {
-    const int j = (int)(idx % c.kpad);
-    const int co = (int)(idx / c.kpad);
-    float v = 0.f;
-    if (j < K) {
-      const int ci = j % c.Ci, tap = j / c.Ci;
-      v = c.w[((long)co * c.Ci + ci) * (c.kh * c.kw) + tap];
+  for (int co = blockIdx.x; co < c.Co; co += gridDim.x) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < K; i += blockDim.x) row[i] = c.w[(long)co * K + i];   // [ci][tap], contiguous
+    __syncthreads();
+    for (int j = threadIdx.x; j < c.kpad; j += blockDim.x) {
+      float v = 0.f;
+      if (j < K) v = row[(j % c.Ci) * taps + j / c.Ci];
+      wp[(long)co * c.kpad + j] = __float2bfloat16(v);
     }
-    wp[idx] = __float2bfloat16(v);
   }
 }
 __global__ void __launch_bounds__(256) convw_unpack_multi_kernel(const CmxConvDesc* __restrict__ d) {
   pdl_trigger();
+  __shared__ float row[CONVW_MAXK];
   const CmxConvDesc c = d[blockIdx.y];
-  const int K = c.kh * c.kw * c.Ci;
-  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < (long)c.Co * K; idx += (long)gridDim.x * blockDim.x) {
-    const int j = (int)(idx % K);
-    const int co = (int)(idx / K);
-    const int ci = j % c.Ci, tap = j / c.Ci;
-    c.gw[((long)co * c.Ci + ci) * (c.kh * c.kw) + tap] += c.gp[(long)co * c.kpad + j];
+  const int taps = c.kh * c.kw, K = taps * c.Ci;
+  for (int co = blockIdx.x; co < c.Co; co += gridDim.x) {
+    __syncthreads();
+    for (int j = threadIdx.x; j < K; j += blockDim.x) row[j] = c.gp[(long)co * c.kpad + j];   // [tap][ci], contiguous
+    __syncthreads();
+    for (int i = threadIdx.x; i < K; i += blockDim.x) c.gw[(long)co * K + i] += row[(i % taps) * c.Ci + i / taps];
   }
+}
+static int convw_check(const CmxConvDesc*, int n) {
+  CMX_REQUIRE(n <= 65535, "convw_*_multi: too many convolutions");
+  return 0;
 }
 CMX_API int cmx_convw_pack_multi(const CmxConvDesc* descs, int n, void* stream) {
   if (n <= 0) return 0;
-  convw_pack_multi_kernel<<<dim3(64, n), 256, 0, (cudaStream_t)stream>>>(descs);
+  if (int rc = convw_check(descs, n)) return rc;
+  convw_pack_multi_kernel<<<dim3(128, n), 256, 0, (cudaStream_t)stream>>>(descs);
   LAUNCH_DONE("convw_pack_multi");
 }
 CMX_API int cmx_convw_unpack_grad_multi(const CmxConvDesc* descs, int n, void* stream) {
   if (n <= 0) return 0;
-  convw_unpack_multi_kernel<<<dim3(64, n), 256, 0, (cudaStream_t)stream>>>(descs);
+  if (int rc = convw_check(descs, n)) return rc;
+  convw_unpack_multi_kernel<<<dim3(128, n), 256, 0, (cudaStream_t)stream>>>(descs);
   LAUNCH_DONE("convw_unpack_grad_multi");
 }
 

@@ -119,6 +119,7 @@ class Engine:
             s4 = tuple(params[n].shape)
             if len(s4) == 4 and s4[2] > 1 and s4[1] > 1:
                 kpad = (s4[1] * s4[2] * s4[3] + 7) // 8 * 8
+                assert s4[1] * s4[2] * s4[3] <= 4608, "conv %s: Ci*kh*kw exceeds the pack kernel's shared-memory row" % n
                 convs.append((n, s4, kpad, tot))
                 tot += (s4[0] * kpad + 63) // 64 * 64
         self.pk_w = torch.zeros(max(tot, 1), device=device, dtype=bf16)
