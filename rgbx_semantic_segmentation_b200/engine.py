@@ -436,15 +436,21 @@ class Engine:
         ops.mm(dx1_bf, self.W(p + ".attn.proj.weight"), dO, tb=True)
         # dK / dV contract over all N tokens into a tiny [Nk, 64] tile per (sample, head): split-K with fp32
         # atomics for parallelism, then one small cast to the bf16 GEMM operand
-        dkv32 = self.Z(B * Nk, 2 * C)
         bs = (B, heads)
         Np = (Nk + 7) // 8 * 8
         sP = (heads * N * Np, N * Np)
         tiles = B * heads * ((Nk + 127) // 128)
         split = max(1, min(N // 512, (2 * ops.NUM_SMS + tiles - 1) // tiles))
+        if tiles >= 96:
+            split = 1   # the low-resolution stages have enough (sample, head) tiles: bf16 results straight from the
+            #             epilogue - no fp32 scratch, memset or cast on the backward chain
+        direct = split == 1
+        dkv = self.E(B * Nk, 2 * C) if direct else None
+        dkv32 = None if direct else self.Z(B * Nk, 2 * C)
+        dkv_out = dkv if direct else dkv32
         # dV = P^T dO
-        ops.gemm_raw(c.Pm, dO, dkv32, Nk, d, N, Np, C, 2 * C, c_off=C, trans_a=True, trans_b=True, batch=bs, sA=sP,
-                     sB=(N * C, d), sC=(Nk * 2 * C, d), accumulate=True, split_k=split)
+        ops.gemm_raw(c.Pm, dO, dkv_out, Nk, d, N, Np, C, 2 * C, c_off=C, trans_a=True, trans_b=True, batch=bs, sA=sP,
+                     sB=(N * C, d), sC=(Nk * 2 * C, d), accumulate=not direct, split_k=split)
         dq = self.E(M, C)
         dS = self.E(B * heads * N, Np)[:, :Nk]
         if d == 64 and Nk <= ops.ATTN_MAX_NK and self.fused_attention:
@@ -459,12 +465,13 @@ class Engine:
             # dQ = dS K
             ops.gemm_raw(dS, c.kv, dq, N, d, Nk, Np, 2 * C, C, trans_b=True, batch=bs, sA=sP, sB=(Nk * 2 * C, d), sC=(N * C, d))
         # dK = dS^T Q
-        ops.gemm_raw(dS, c.q, dkv32, Nk, d, N, Np, C, 2 * C, trans_a=True, trans_b=True, batch=bs, sA=sP, sB=(N * C, d),
-                     sC=(Nk * 2 * C, d), accumulate=True, split_k=split)
+        ops.gemm_raw(dS, c.q, dkv_out, Nk, d, N, Np, C, 2 * C, trans_a=True, trans_b=True, batch=bs, sA=sP, sB=(N * C, d),
+                     sC=(Nk * 2 * C, d), accumulate=not direct, split_k=split)
         del dS
-        dkv = self.E(B * Nk, 2 * C)
-        ops.cast_f32_bf16(dkv32, dkv)
-        del dkv32
+        if not direct:
+            dkv = self.E(B * Nk, 2 * C)
+            ops.cast_f32_bf16(dkv32, dkv)
+            del dkv32
         self.linear_wgrad(dkv, c.kv_in, p + ".attn.kv.weight", p + ".attn.kv.bias")
         dkvin = self.E(B * Nk, C)
         ops.mm(dkv, self.W(p + ".attn.kv.weight"), dkvin, tb=True)

@@ -147,6 +147,15 @@ def test_tc_batched_attention_shapes(N, Nk, heads):
     got = dkv.view(B, Nk, 2, heads, d)
     _check(got[:, :, 1].permute(0, 2, 1, 3), Pf.transpose(-1, -2) @ dOf, N, "dV = P^T dO")
     _check(got[:, :, 0].permute(0, 2, 1, 3), Pf.transpose(-1, -2) @ qf, N, "dK-like = P^T Q")
+    # the low-resolution stages skip split-K: bf16 results straight from the epilogue (TMA store clipped at Nk rows)
+    dkvb = torch.full((B * Nk, 2 * C), 3.0, device=DEV, dtype=bf)
+    ops.gemm_raw(Pb, dO, dkvb, Nk, d, N, Np, C, 2 * C, c_off=C, trans_a=True, trans_b=True, batch=bs, sA=sP, sB=(N * C, d),
+                 sC=(Nk * 2 * C, d), impl=2)
+    ops.gemm_raw(Pb, q, dkvb, Nk, d, N, Np, C, 2 * C, trans_a=True, trans_b=True, batch=bs, sA=sP, sB=(N * C, d),
+                 sC=(Nk * 2 * C, d), impl=2)
+    gb = dkvb.view(B, Nk, 2, heads, d)
+    _check(gb[:, :, 1].permute(0, 2, 1, 3), Pf.transpose(-1, -2) @ dOf, N, "dV = P^T dO (bf16, no split)")
+    _check(gb[:, :, 0].permute(0, 2, 1, 3), Pf.transpose(-1, -2) @ qf, N, "dK-like = P^T Q (bf16, no split)")
     dP = torch.empty(B * heads * N, Np, device=DEV)[:, :Nk]
     ops.gemm_raw(dO, kv, dP, N, Nk, d, C, 2 * C, Np, b_off=C, batch=bs, sA=(N * C, d), sB=(Nk * 2 * C, d), sC=sP, impl=2)
     _check(dP.reshape(B, heads, N, Nk), dOf @ vf.transpose(-1, -2), d, "dP = dO V^T")
