@@ -225,6 +225,12 @@ int cmx_upsample_bwd(const void* dout, int Ho, int Wo, void* dz, int Hi, int Wi,
  * UNNORMALISED gradient sum_{pixels} w * (softmax - onehot) into dlogits (fp32, same layout and stride as logits). */
 int cmx_ce_upsampled_fwd_bwd(const float* logits, int64_t ld, const int64_t* label, int ignore_index, double* acc,
                              float* dlogits, int B, int h, int w, int H, int W, int ncls, void* stream);
+/* same pass for the reference's alternate criteria (train.py:70-93): w_ce * CE + w_focal * FocalLoss(gamma, alpha) with the
+ * all-classes focal form of utils/loss_opr.py:157-196 ('FocalLoss': w_ce 0, w_focal 1; 'CE_Focal': 1 and 0.2, builder.py:246-247);
+ * acc[0] += weighted loss sum, acc[1] += valid count, dlogits accumulates the weighted unnormalised gradient. */
+int cmx_ce_focal_upsampled_fwd_bwd(const float* logits, int64_t ld, const int64_t* label, int ignore_index, double* acc,
+                                   float* dlogits, int B, int h, int w, int H, int W, int ncls, float w_ce, float w_focal,
+                                   float gamma, float alpha, void* stream);
 /* loss = acc[0]/acc[1];  dlogits_out(bf16/f32) = dlogits * gscale/acc[1] */
 int cmx_ce_finalize(const double* acc, float* loss, const float* dlogits, const float* gscale,
                     void* dlogits_out, int out_dtype, int64_t n, void* stream);

@@ -144,9 +144,15 @@ CMX_API int cmx_upsample_bwd(const void* dout, int Ho, int Wo, void* dz, int Hi,
 constexpr int CE_MAXC = 16;
 constexpr int CE_TW = 32, CE_TH = 8;
 
+// FOCAL: loss = w_ce * CE + w_focal * FocalLoss, where FocalLoss is the reference's all-classes form (utils/loss_opr.py:
+// 157-196: pt_k = p_k for the target class and 1 - p_k otherwise, -alpha_k (1 - pt_k)^gamma log(pt_k + 1e-8) summed over the
+// classes; alpha_k = alpha / 1 - alpha), both averaged over the valid pixels (train.py:70-93: 'FocalLoss', 'CE_Focal').
+struct FocalArgs { float w_ce, w_focal, gamma, alpha; };
+template <bool FOCAL>
 __global__ void __launch_bounds__(256) ce_upsampled_kernel(const float* __restrict__ logits, long ld, const int64_t* __restrict__ label,
                                                            int ignore_index, double* __restrict__ acc, float* __restrict__ dlogits,
-                                                           int h, int w, int H, int W, int ncls, float sh, float sw, int cap) {
+                                                           int h, int w, int H, int W, int ncls, float sh, float sw, int cap,
+                                                           FocalArgs fa) {
   pdl_trigger();
   extern __shared__ float s_dyn[];  // [cap] low-res logits window, [cap] gradient accumulator
   float* s_l = s_dyn;
@@ -210,12 +216,39 @@ __global__ void __launch_bounds__(256) ce_upsampled_kernel(const float* __restri
       }
       loss = logf(sum) + mx - picked;
       valid = 1;
+      const float inv = 1.f / sum;
+      float hk[CE_MAXC], hs = 0.f;   // FOCAL: d focal / d p_k and sum_k h_k p_k
+      if (FOCAL) {
+        // out-of-range labels are clamped like the reference (loss_opr.py:171) - CE has no such case (it would raise)
+        const int t = lab < 0 ? 0 : (lab >= ncls ? ncls - 1 : (int)lab);
+        float fl = 0.f;
+#pragma unroll
+        for (int k = 0; k < CE_MAXC; k++) {
+          hk[k] = 0.f;
+          if (k < ncls) {
+            const float p = v[k] * inv;
+            if (k == t) {
+              const float om = fmaxf(1.f - p, 0.f), lg = logf(p + 1e-8f);
+              const float pw1 = om > 0.f ? __powf(om, fa.gamma - 1.f) : (fa.gamma == 1.f ? 1.f : 0.f);
+              fl -= fa.alpha * pw1 * om * lg;
+              hk[k] = fa.alpha * (fa.gamma * pw1 * lg - pw1 * om / (p + 1e-8f));
+            } else {
+              const float q = fmaxf(1.f - p, 0.f), lg = logf(q + 1e-8f);
+              const float pw1 = p > 0.f ? __powf(p, fa.gamma - 1.f) : (fa.gamma == 1.f ? 1.f : 0.f);
+              fl -= (1.f - fa.alpha) * pw1 * p * lg;
+              hk[k] = (1.f - fa.alpha) * (-fa.gamma * pw1 * lg + pw1 * p / (q + 1e-8f));
+            }
+            hs += hk[k] * p;
+          }
+        }
+        loss = fa.w_ce * loss + fa.w_focal * fl;
+      }
       if (dlogits) {
-        const float inv = 1.f / sum;
 #pragma unroll
         for (int k = 0; k < CE_MAXC; k++) {
           if (k < ncls) {
-            const float g = v[k] * inv - (k == (int)lab ? 1.f : 0.f);
+            float g = v[k] * inv - (k == (int)lab ? 1.f : 0.f);
+            if (FOCAL) g = fa.w_ce * g + fa.w_focal * (v[k] * inv) * (hk[k] - hs);
             atomicAdd(&s_g[o00 + k], w00 * g);
             atomicAdd(&s_g[o01 + k], w01 * g);
             atomicAdd(&s_g[o10 + k], w10 * g);
@@ -246,8 +279,8 @@ __global__ void __launch_bounds__(256) ce_upsampled_kernel(const float* __restri
     }
   }
 }
-CMX_API int cmx_ce_upsampled_fwd_bwd(const float* logits, int64_t ld, const int64_t* label, int ignore_index, double* acc,
-                                     float* dlogits, int B, int h, int w, int H, int W, int ncls, void* stream) {
+static int ce_launch(const float* logits, int64_t ld, const int64_t* label, int ignore_index, double* acc, float* dlogits, int B,
+                     int h, int w, int H, int W, int ncls, const FocalArgs* focal, void* stream) {
   CMX_REQUIRE(ncls >= 1 && ncls <= CE_MAXC, "ce: ncls=%d > %d unsupported", ncls, CE_MAXC);
   CMX_REQUIRE(ld >= ncls, "ce: row stride %ld < ncls %d", (long)ld, ncls);
   CMX_REQUIRE(H >= h && W >= w, "ce: only upsampling supported");
@@ -258,8 +291,24 @@ CMX_API int cmx_ce_upsampled_fwd_bwd(const float* logits, int64_t ld, const int6
   const size_t smem = (size_t)cap * 2 * sizeof(float);
   CMX_REQUIRE(smem <= 48 * 1024, "ce: low-res window too large for shared memory");
   dim3 grid(cdiv(W, CE_TW), cdiv(H, CE_TH), B), block(32, 8);
-  ce_upsampled_kernel<<<grid, block, smem, (cudaStream_t)stream>>>(logits, (long)ld, label, ignore_index, acc, dlogits, h, w, H, W, ncls, sh, sw, cap);
+  if (focal)
+    ce_upsampled_kernel<true><<<grid, block, smem, (cudaStream_t)stream>>>(logits, (long)ld, label, ignore_index, acc, dlogits, h, w, H, W,
+                                                                          ncls, sh, sw, cap, *focal);
+  else
+    ce_upsampled_kernel<false><<<grid, block, smem, (cudaStream_t)stream>>>(logits, (long)ld, label, ignore_index, acc, dlogits, h, w, H, W,
+                                                                           ncls, sh, sw, cap, FocalArgs{1.f, 0.f, 0.f, 0.f});
   LAUNCH_DONE("ce_upsampled_fwd_bwd");
+}
+CMX_API int cmx_ce_upsampled_fwd_bwd(const float* logits, int64_t ld, const int64_t* label, int ignore_index, double* acc,
+                                     float* dlogits, int B, int h, int w, int H, int W, int ncls, void* stream) {
+  return ce_launch(logits, ld, label, ignore_index, acc, dlogits, B, h, w, H, W, ncls, nullptr, stream);
+}
+CMX_API int cmx_ce_focal_upsampled_fwd_bwd(const float* logits, int64_t ld, const int64_t* label, int ignore_index, double* acc,
+                                           float* dlogits, int B, int h, int w, int H, int W, int ncls, float w_ce, float w_focal,
+                                           float gamma, float alpha, void* stream) {
+  CMX_REQUIRE(gamma >= 0.f && alpha >= 0.f && alpha <= 1.f, "ce_focal: gamma=%g alpha=%g out of range", gamma, alpha);
+  const FocalArgs fa{w_ce, w_focal, gamma, alpha};
+  return ce_launch(logits, ld, label, ignore_index, acc, dlogits, B, h, w, H, W, ncls, &fa, stream);
 }
 template <typename TO>
 __global__ void __launch_bounds__(256) ce_finalize_kernel(const double* __restrict__ acc, float* __restrict__ loss,

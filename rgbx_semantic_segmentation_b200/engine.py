@@ -926,16 +926,17 @@ class Engine:
         ops.logits_upsample_nchw(logits, out, B, sizes[0][0], sizes[0][1], H, W, self.ncls)
         return out
 
-    def forward_loss(self, rgb, x, label, ignore_index, with_grad):
-        """loss (0-d fp32).  with_grad: also runs the complete backward pass, leaving d loss / d theta in flat_g."""
-        gen = self.forward_loss_steps(rgb, x, label, ignore_index, with_grad)
+    def forward_loss(self, rgb, x, label, ignore_index, with_grad, focal=None):
+        """loss (0-d fp32).  with_grad: also runs the complete backward pass, leaving d loss / d theta in flat_g.
+        focal = (w_ce, w_focal, gamma, alpha) selects w_ce * CE + w_focal * FocalLoss instead of plain cross entropy."""
+        gen = self.forward_loss_steps(rgb, x, label, ignore_index, with_grad, focal)
         try:
             while True:
                 next(gen)
         except StopIteration as done:
             return done.value
 
-    def forward_loss_steps(self, rgb, x, label, ignore_index, with_grad):
+    def forward_loss_steps(self, rgb, x, label, ignore_index, with_grad, focal=None):
         """generator form of forward_loss: yields ONCE (with_grad only), after the backward pass has completed every
         gradient of flat_g[:split_off] (decoder, stages 4 and 3) and all side streams are joined - the point where a
         data-parallel caller starts the all-reduce of that slice (and may switch CUDA graphs); returns the loss."""
@@ -952,13 +953,19 @@ class Engine:
         acc = self.Z(2, dtype=torch.float64)
         loss = self.E((), dtype=f32)
         if not with_grad:
-            ops.ce_upsampled(logits, label, ignore_index, acc, None, B, h0, w0, H, W, self.ncls)
+            if focal is None:
+                ops.ce_upsampled(logits, label, ignore_index, acc, None, B, h0, w0, H, W, self.ncls)
+            else:
+                ops.ce_focal_upsampled(logits, label, ignore_index, acc, None, B, h0, w0, H, W, self.ncls, *focal)
             ops.ce_finalize(acc, loss)
             return loss
         self.flat_g.zero_()
         self.pk_g.zero_()
         dl = self.Z(B * h0 * w0, self.ncls_ld)
-        ops.ce_upsampled(logits, label, ignore_index, acc, dl[:, :self.ncls], B, h0, w0, H, W, self.ncls)
+        if focal is None:
+            ops.ce_upsampled(logits, label, ignore_index, acc, dl[:, :self.ncls], B, h0, w0, H, W, self.ncls)
+        else:
+            ops.ce_focal_upsampled(logits, label, ignore_index, acc, dl[:, :self.ncls], B, h0, w0, H, W, self.ncls, *focal)
         dlog = self.E(B * h0 * w0, self.ncls_ld)
         ops.ce_finalize(acc, loss, dl, None, dlog)   # element-wise over the padded buffer (pad columns stay 0)
         dfs = self.decoder_bwd(cdec, dlog[:, :self.ncls], B)

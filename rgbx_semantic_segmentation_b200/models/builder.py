@@ -109,16 +109,35 @@ class EncoderDecoder(nn.Module):
         if label is None:
             with torch.no_grad():
                 return self._forward_eval(rgb, modal_x)
-        crit = self.criterion
-        if not isinstance(crit, nn.CrossEntropyLoss) or crit.reduction != 'mean' or crit.weight is not None \
-                or getattr(crit, "label_smoothing", 0.0) != 0.0:
-            raise NotImplementedError("cmx_b200 fuses nn.CrossEntropyLoss(reduction='mean', ignore_index=k) only (train.py:72-73)")
+        ign, focal = self._criterion_spec()
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             params = tuple(self._eng_params())
             return _CMXStep.apply(self, rgb, modal_x, label, *params)
         with torch.no_grad():
-            return self._eng().forward_loss(rgb.float().contiguous(), modal_x.float().contiguous(), label,
-                                            crit.ignore_index, with_grad=False)
+            return self._eng().forward_loss(rgb.float().contiguous(), modal_x.float().contiguous(), label, ign,
+                                            with_grad=False, focal=focal)
+
+    def _criterion_spec(self):
+        """-> (ignore_index, None | (w_ce, w_focal, gamma, alpha)) for the criteria fused into the loss kernel (train.py:70-93):
+        nn.CrossEntropyLoss(mean, ignore_index) · FocalLoss(ignore_label, gamma, alpha, 'mean') (utils/loss_opr.py:157-196, or
+        this package's utils.loss_opr.FocalLoss) · the 'CE_Focal' tuple, combined as c0 + 0.2 * c1 (builder.py:246-247)."""
+        def is_ce(c):
+            return isinstance(c, nn.CrossEntropyLoss) and c.reduction == 'mean' and c.weight is None \
+                and getattr(c, "label_smoothing", 0.0) == 0.0
+
+        def is_focal(c):
+            return type(c).__name__ == "FocalLoss" and all(hasattr(c, a) for a in ("ignore_label", "gamma", "alpha")) \
+                and getattr(c, "reduction", "mean") == 'mean'
+        crit = self.criterion
+        if is_ce(crit):
+            return crit.ignore_index, None
+        if is_focal(crit):
+            return int(crit.ignore_label), (0.0, 1.0, float(crit.gamma), float(crit.alpha))
+        if isinstance(crit, tuple) and len(crit) == 2 and is_ce(crit[0]) and is_focal(crit[1]) \
+                and crit[0].ignore_index == int(crit[1].ignore_label):
+            return crit[0].ignore_index, (1.0, 0.2, float(crit[1].gamma), float(crit[1].alpha))
+        raise NotImplementedError("cmx_b200 fuses nn.CrossEntropyLoss(reduction='mean', ignore_index=k), FocalLoss(mean) and the "
+                                  "(CrossEntropyLoss, FocalLoss) tuple only (train.py:70-93)")
 
     # ---- engine plumbing ---------------------------------------------------------------------------
     def _eng(self):
@@ -165,9 +184,9 @@ class EncoderDecoder(nn.Module):
         the step is therefore captured as TWO graphs sharing one memory pool (NCCL itself is never captured)."""
         from ..parallel import allreduce_slice_async
         rgb, modal_x = rgb.float().contiguous(), modal_x.float().contiguous()
-        ign = self.criterion.ignore_index
+        ign, focal = self._criterion_spec()
         eng = self._eng()
-        key = ("train", tuple(rgb.shape), self.training, rgb.device.index)
+        key = ("train", tuple(rgb.shape), self.training, rgb.device.index, focal)
 
         def finish(gen):
             try:
@@ -177,7 +196,7 @@ class EncoderDecoder(nn.Module):
             raise RuntimeError("cmx_b200: the engine yielded more than once")
 
         def eager(a, b, c):
-            gen = eng.forward_loss_steps(a, b, c, ign, with_grad=True)
+            gen = eng.forward_loss_steps(a, b, c, ign, with_grad=True, focal=focal)
             next(gen)
             allreduce_slice_async(self, eng.flat_g[:eng.split_off])
             loss = finish(gen)
@@ -197,13 +216,13 @@ class EncoderDecoder(nn.Module):
             if not split:
                 graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(graph):
-                    g["loss"] = eng.forward_loss(g["rgb"], g["x"], g["label"], ign, with_grad=True)
+                    g["loss"] = eng.forward_loss(g["rgb"], g["x"], g["label"], ign, with_grad=True, focal=focal)
                 g["graph"], g["graph2"] = graph, None
             else:
                 pool = torch.cuda.graph_pool_handle()
                 ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
                 with torch.cuda.graph(ga, pool=pool):
-                    gen = eng.forward_loss_steps(g["rgb"], g["x"], g["label"], ign, with_grad=True)
+                    gen = eng.forward_loss_steps(g["rgb"], g["x"], g["label"], ign, with_grad=True, focal=focal)
                     next(gen)
                 with torch.cuda.graph(gb, pool=pool):
                     g["loss"] = finish(gen)

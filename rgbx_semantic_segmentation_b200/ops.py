@@ -417,6 +417,16 @@ def ce_upsampled(logits, label, ignore_index, acc, dlogits, B, h, w, H, W, ncls)
                                                     B, h, w, H, W, ncls, _stream())
 
 
+def ce_focal_upsampled(logits, label, ignore_index, acc, dlogits, B, h, w, H, W, ncls, w_ce, w_focal, gamma, alpha):
+    """w_ce * CE + w_focal * FocalLoss(gamma, alpha) (utils/loss_opr.py:157-196) in the same single pass as ce_upsampled"""
+    assert label.dtype == torch.int64 and label.is_contiguous()
+    assert logits.dtype == torch.float32 and tuple(logits.shape) == (B * h * w, ncls)
+    if dlogits is not None:
+        assert dlogits.dtype == torch.float32 and dlogits.shape == logits.shape and _ld(dlogits) == _ld(logits)
+    _call("cmx_ce_focal_upsampled_fwd_bwd", logits.data_ptr(), _ld(logits), label.data_ptr(), ignore_index, acc.data_ptr(), _p(dlogits),
+          B, h, w, H, W, ncls, float(w_ce), float(w_focal), float(gamma), float(alpha), _stream())
+
+
 def ce_finalize(acc, loss, dlogits=None, gscale=None, out=None):
     n = dlogits.numel() if dlogits is not None else 0
     _call("cmx_ce_finalize", acc.data_ptr(), _p(loss), _p(dlogits), _p(gscale), _p(out),

@@ -1,0 +1,4 @@
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_ops_gpu.py -x -q -k "focal or ce_ups" 2>&1 | tail -3
+timeout 900 python -m pytest tests/test_model_gpu.py -x -q 2>&1 | tail -3
+timeout 600 python bench.py --no-cpu-baseline 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('N1', d['ms_per_step'], d['e2e']['ms_per_step'], d['gpu_launches_per_step'])"

@@ -419,3 +419,33 @@ def test_flat_data_parallel_two_graph_step_single_process_group():
     finally:
         if created:
             dist.destroy_process_group()
+
+
+def test_focal_and_ce_focal_criteria_train_step_vs_oracle():
+    """criterion = FocalLoss / (CrossEntropyLoss, FocalLoss) (train.py:70-93, builder.py:246-247): loss and gradients of the whole
+    model against the fp32 oracle with the same criterion applied to its logits"""
+    from rgbx_semantic_segmentation_b200.models.builder import EncoderDecoder
+    from rgbx_semantic_segmentation_b200.utils.loss_opr import FocalLoss
+    spec = cmx_ref.MIT_SPECS["mit_b0"]
+    sd = synth_state_dict(spec, 9, seed=0)
+    rgb, x, gt = synth_inputs(2, 64, 96, 9, seed=1)
+    ce = nn.CrossEntropyLoss(reduction="mean", ignore_index=255)
+    for crit in (FocalLoss(ignore_label=255, gamma=4.0, alpha=0.25), (ce, FocalLoss(ignore_label=255, gamma=2.0, alpha=0.25))):
+        cfg = Cfg()
+        cfg.backbone, cfg.num_classes = "mit_b0", 9
+        m = EncoderDecoder(cfg, crit, nn.BatchNorm2d)
+        m.load_state_dict(sd, strict=True)
+        m = m.cuda().train()
+        m._eng().stochastic = False
+        loss = m(rgb.cuda(), x.cuda(), gt.cuda())
+        loss.backward()
+        params = {k: v.clone().requires_grad_(v.is_floating_point() and not k.endswith(("running_mean", "running_var")))
+                  for k, v in sd.items()}
+        logits = cmx_ref.forward(params, spec, rgb, x, None, training=True, decoder_bn_eps=1e-3)
+        ref = crit(logits, gt) if not isinstance(crit, tuple) else crit[0](logits, gt) + 0.2 * crit[1](logits, gt)
+        ref.backward()
+        assert abs(loss.item() - ref.item()) <= 5e-3 * abs(ref.item()), (loss.item(), ref.item())
+        grads_vs(m, {n: params[n].grad for n, _ in m.named_parameters()}, "focal criterion")
+    with pytest.raises(NotImplementedError):
+        bad = EncoderDecoder(cfg, nn.MSELoss(), nn.BatchNorm2d).cuda().train()
+        bad(rgb.cuda(), x.cuda(), gt.cuda())

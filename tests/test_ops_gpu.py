@@ -411,6 +411,34 @@ def test_ce_upsampled(h, w, H, W, ncls, ld):
     close(full, up, 1e-5, 1e-5, "logits upsample")
 
 
+@pytest.mark.parametrize("name,mode", [("g2", "focal"), ("g4", "focal"), ("g1", "focal"), ("g2", "cefocal"), ("g4", "cefocal")])
+def test_focal_loss_kernel_vs_reference_golden(golden_dir, name, mode):
+    """fused FocalLoss / CE_Focal (train.py:70-93) against values produced by the reference's FocalLoss class; identity
+    'upsample' (H = h) so the golden logits are the kernel's logits"""
+    import os
+    z = np.load(os.path.join(golden_dir, "focal.npz"))
+    ncls, gamma, alpha, _ = z[name + "_meta"]
+    ncls = int(ncls)
+    lg = torch.from_numpy(z[name + "_logits"]).to(DEV)                     # [B, C, h, w]
+    B, _, h, w = lg.shape
+    ld = (ncls + 7) // 8 * 8
+    base = torch.full((B * h * w, ld), float("nan"), device=DEV)
+    logits = base[:, :ncls]
+    logits.copy_(lg.permute(0, 2, 3, 1).reshape(-1, ncls))
+    label = torch.from_numpy(z[name + "_target"]).to(DEV)
+    acc = torch.zeros(2, dtype=torch.float64, device=DEV)
+    dl_full = torch.zeros(B * h * w, ld, device=DEV)
+    w_ce, w_f = (0.0, 1.0) if mode == "focal" else (1.0, 0.2)
+    ops.ce_focal_upsampled(logits, label, 255, acc, dl_full[:, :ncls], B, h, w, h, w, ncls, w_ce, w_f, float(gamma), float(alpha))
+    loss = torch.empty((), device=DEV)
+    dout = torch.empty_like(dl_full)
+    ops.ce_finalize(acc, loss, dl_full, None, dout)
+    ref_loss = float(z[name + "_" + mode])
+    assert abs(float(loss) - ref_loss) < 2e-5 * max(1.0, abs(ref_loss)), (float(loss), ref_loss)
+    ref_grad = torch.from_numpy(z[name + "_" + mode + "_grad"]).to(DEV).permute(0, 2, 3, 1).reshape(-1, ncls)
+    close(dout[:, :ncls], ref_grad, 2e-3, 1e-7, "focal dlogits")
+
+
 def test_confusion_bit_exact():
     from oracle import metric_ref
     rng = np.random.default_rng(0)
