@@ -783,6 +783,9 @@ class Engine:
         ops.bn_bwd(dyb, c.fuse, c.mean, c.inv, self.P(p + ".linear_fuse.1.weight"), self.P(p + ".linear_fuse.1.bias"), dfuse,
                    self.G(p + ".linear_fuse.1.weight"), self.G(p + ".linear_fuse.1.bias"), ws, relu=True, mask=c.dropmask,
                    rows_per_sample=c.N0)
+        self.tr("grad.decode_head.logits", dlog)
+        self.tr("grad.decode_head.post_bn", dyb)
+        self.tr("grad.decode_head.fuse", dfuse)
         del dyb
         c.zs = None
         # bias path (parameter gradients only -> companion stream): d btot = colsum(dfuse);  d bf = d btot;
