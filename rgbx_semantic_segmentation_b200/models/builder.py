@@ -110,9 +110,10 @@ class EncoderDecoder(nn.Module):
             with torch.no_grad():
                 return self._forward_eval(rgb, modal_x)
         ign, focal = self._criterion_spec()
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            params = tuple(self._eng_params())
-            return _CMXStep.apply(self, rgb, modal_x, label, *params)
+        if torch.is_grad_enabled():
+            params = self._eng_params()
+            if any(p.requires_grad for p in params):
+                return _CMXStep.apply(self, rgb, modal_x, label, *params)
         with torch.no_grad():
             return self._eng().forward_loss(rgb.float().contiguous(), modal_x.float().contiguous(), label, ign,
                                             with_grad=False, focal=focal)
@@ -153,9 +154,15 @@ class EncoderDecoder(nn.Module):
         return self
 
     def _eng_params(self):
+        """parameters in the engine's flat order; cached (walking named_parameters() costs ~1 ms of host time per call,
+        which sits between two steps whenever the caller synchronises on the loss)"""
         eng = self._eng()
-        d = dict(self.named_parameters())
-        return [d[n] for n in eng.names]
+        cache = self.__dict__.get("_params_cache")
+        if cache is None or cache[0] is not eng.names:
+            d = dict(self.named_parameters())
+            cache = (eng.names, tuple(d[n] for n in eng.names))
+            self.__dict__["_params_cache"] = cache
+        return cache[1]
 
     def _forward_eval(self, rgb, modal_x):
         rgb, modal_x = rgb.float().contiguous(), modal_x.float().contiguous()
@@ -245,4 +252,5 @@ class EncoderDecoder(nn.Module):
         st["_graphs"] = {}
         st["_flat_dp"] = None
         st.pop("_flat_pending", None)
+        st.pop("_params_cache", None)
         return st
