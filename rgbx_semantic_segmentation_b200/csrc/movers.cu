@@ -99,14 +99,16 @@ __global__ void __launch_bounds__(256) col2im_nhwc_kernel(const bf16* __restrict
 #pragma unroll
   for (int i = 0; i < 8; i++) acc[i] = 0.f;
   if (add) load8(add + pix * ldadd + cg * 8, acc);
-  for (int kh = 0; kh < k; kh++) {
+  // only taps with (iy + p - kh) divisible by the stride contribute: kh = (iy + p) mod s, + s, ... (one tap for the
+  // non-overlapping SR convolutions k = s = R instead of a scan over all R*R)
+  for (int kh = (iy + p) % s; kh < k; kh += s) {
     const int ty = iy + p - kh;
-    if (ty < 0 || ty % s) continue;
+    if (ty < 0) break;
     const int oy = ty / s;
     if (oy >= Ho) continue;
-    for (int kw = 0; kw < k; kw++) {
+    for (int kw = (ix + p) % s; kw < k; kw += s) {
       const int tx = ix + p - kw;
-      if (tx < 0 || tx % s) continue;
+      if (tx < 0) break;
       const int ox = tx / s;
       if (ox >= Wo) continue;
       float v[8];
