@@ -67,22 +67,43 @@ __global__ void __launch_bounds__(256) pool_partial_kernel(const bf16* __restric
     }
   }
 }
-__global__ void pool_finalize_kernel(const float* __restrict__ wsum, const float* __restrict__ wmax, const int* __restrict__ widx,
-                                     float* __restrict__ y, int32_t* __restrict__ argmax, int B, int HW, int C2, int nchunk) {
+// block = 32 channels x 8 chunk lanes: the (up to 64) chunk partials of a channel are read by 8 lanes in parallel (this
+// kernel is pure load latency) and folded in shared memory; ties go to the smaller row index (= first maximum)
+__global__ void __launch_bounds__(256) pool_finalize_kernel(const float* __restrict__ wsum, const float* __restrict__ wmax,
+                                                            const int* __restrict__ widx, float* __restrict__ y,
+                                                            int32_t* __restrict__ argmax, int B, int HW, int C2, int nchunk) {
   pdl_trigger();
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= B * C2) return;
-  const int c = idx % C2, b = idx / C2;
+  __shared__ float ssum[8][33], smax[8][33];
+  __shared__ int sidx[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int idx = blockIdx.x * 32 + tx;
+  const bool ok = idx < B * C2;
+  const int c = ok ? idx % C2 : 0, b = ok ? idx / C2 : 0;
   float ts = 0.f, tm = -INFINITY;
-  int ti = 0;
-  for (int ch = 0; ch < nchunk; ch++) {
-    const long o = ((long)b * nchunk + ch) * C2 + c;
-    ts += wsum[o];
-    if (wmax[o] > tm) { tm = wmax[o]; ti = widx[o]; }
+  int ti = 0x7fffffff;
+  if (ok) {
+#pragma unroll 8
+    for (int ch = ty; ch < nchunk; ch += 8) {
+      const long o = ((long)b * nchunk + ch) * C2 + c;
+      const float v = wmax[o];
+      ts += wsum[o];
+      if (v > tm) { tm = v; ti = widx[o]; }
+    }
   }
-  y[(long)b * 2 * C2 + c] = ts / (float)HW;
-  y[(long)b * 2 * C2 + C2 + c] = tm;
-  argmax[(long)b * C2 + c] = ti;
+  ssum[ty][tx] = ts; smax[ty][tx] = tm; sidx[ty][tx] = ti;
+  __syncthreads();
+  if (ty == 0 && ok) {
+#pragma unroll
+    for (int l = 1; l < 8; l++) {
+      ts += ssum[l][tx];
+      const float v = smax[l][tx];
+      const int id = sidx[l][tx];
+      if (v > tm || (v == tm && id < ti)) { tm = v; ti = id; }
+    }
+    y[(long)b * 2 * C2 + c] = ts / (float)HW;
+    y[(long)b * 2 * C2 + C2 + c] = tm;
+    argmax[(long)b * C2 + c] = ti == 0x7fffffff ? 0 : ti;
+  }
 }
 CMX_API int64_t cmx_pool_avgmax_ws_bytes(int B, int C2) { return (int64_t)B * POOL_MAXCH * C2 * 12; }
 CMX_API int cmx_pool_avgmax_fwd(const void* x, int64_t ldx, float* y, int32_t* argmax, void* ws, int B, int HW, int C2, void* stream) {
@@ -104,7 +125,7 @@ CMX_API int cmx_pool_avgmax_fwd(const void* x, int64_t ldx, float* y, int32_t* a
   dim3 grid(cdiv(C2 / 8, ng), B, nchunk);
   pool_partial_kernel<<<grid, 256, 0, st>>>((const bf16*)x, ldx, wsum, wmax, widx, HW, C2, ng, rows_per_chunk, nchunk);
   g_cmx_launches++;
-  pool_finalize_kernel<<<cdiv(B * C2, 128), 128, 0, st>>>(wsum, wmax, widx, y, argmax, B, HW, C2, nchunk);
+  pool_finalize_kernel<<<cdiv(B * C2, 32), 256, 0, st>>>(wsum, wmax, widx, y, argmax, B, HW, C2, nchunk);
   LAUNCH_DONE("pool_avgmax_fwd");
 }
 __global__ void __launch_bounds__(256) pool_avgmax_bwd_kernel(const float* __restrict__ dy, const int32_t* __restrict__ argmax,
@@ -120,9 +141,36 @@ __global__ void __launch_bounds__(256) pool_avgmax_bwd_kernel(const float* __res
   if (argmax[(long)b * C2 + c] == r) g += dy[(long)b * 2 * C2 + C2 + c];
   dx[row * lddx + c] += g;
 }
+// thread = 4 consecutive channels of one row (16-byte read-modify-write)
+__global__ void __launch_bounds__(256) pool_avgmax_bwd_v4_kernel(const float* __restrict__ dy, const int32_t* __restrict__ argmax,
+                                                                 float* __restrict__ dx, long lddx, int HW, int C2, long total4) {
+  pdl_trigger();
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total4) return;
+  const int c4 = C2 >> 2;
+  const int c = (int)(idx % c4) * 4;
+  const long row = idx / c4;
+  const int b = (int)(row / HW);
+  const int r = (int)(row - (long)b * HW);
+  const float4 ga = __ldg(reinterpret_cast<const float4*>(dy + (long)b * 2 * C2 + c));
+  const float4 gm = __ldg(reinterpret_cast<const float4*>(dy + (long)b * 2 * C2 + C2 + c));
+  const int4 am = __ldg(reinterpret_cast<const int4*>(argmax + (long)b * C2 + c));
+  float4* p = reinterpret_cast<float4*>(dx + row * lddx + c);
+  float4 v = *p;
+  const float inv = 1.f / (float)HW;
+  v.x += ga.x * inv + (am.x == r ? gm.x : 0.f);
+  v.y += ga.y * inv + (am.y == r ? gm.y : 0.f);
+  v.z += ga.z * inv + (am.z == r ? gm.z : 0.f);
+  v.w += ga.w * inv + (am.w == r ? gm.w : 0.f);
+  *p = v;
+}
 CMX_API int cmx_pool_avgmax_bwd(const float* dy, const int32_t* argmax, float* dx, int64_t lddx, int B, int HW, int C2, void* stream) {
   const long total = (long)B * HW * C2;
   if (total == 0) return 0;
+  if (C2 % 4 == 0 && lddx % 4 == 0 && ((((uintptr_t)dy) | ((uintptr_t)argmax) | ((uintptr_t)dx)) & 15) == 0) {
+    pool_avgmax_bwd_v4_kernel<<<cdiv(total / 4, 256), 256, 0, (cudaStream_t)stream>>>(dy, argmax, dx, lddx, HW, C2, total / 4);
+    LAUNCH_DONE("pool_avgmax_bwd");
+  }
   pool_avgmax_bwd_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(dy, argmax, dx, lddx, HW, C2, total);
   LAUNCH_DONE("pool_avgmax_bwd");
 }
@@ -158,9 +206,62 @@ __global__ void __launch_bounds__(256) smallm_linear_fwd_kernel(const float* __r
     }
   }
 }
+// K % 4 == 0: 16-byte loads and four independent weight loads in flight per lane (the scalar loop above serialises
+// K/32 DRAM round trips per warp: 71 us for the 2048 x 2048 stage-4 matrix)
+__global__ void __launch_bounds__(256) smallm_linear_fwd_v4_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                                   const float* __restrict__ b, int act, float* __restrict__ y,
+                                                                   int Mb, int N, int K) {
+  pdl_trigger();
+  const int lane = threadIdx.x & 31;
+  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (n >= N) return;
+  float acc[SMALLM_MAX];
+#pragma unroll
+  for (int m = 0; m < SMALLM_MAX; m++) acc[m] = 0.f;
+  const float* wr = w + (long)n * K;
+  int k = lane * 4;
+  for (; k + 3 * 128 < K; k += 4 * 128) {
+    float4 wv[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) wv[u] = __ldg(reinterpret_cast<const float4*>(wr + k + u * 128));
+#pragma unroll
+    for (int m = 0; m < SMALLM_MAX; m++)
+      if (m < Mb) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const float4 xv = __ldg(reinterpret_cast<const float4*>(x + (long)m * K + k + u * 128));
+          acc[m] = fmaf(wv[u].x, xv.x, fmaf(wv[u].y, xv.y, fmaf(wv[u].z, xv.z, fmaf(wv[u].w, xv.w, acc[m]))));
+        }
+      }
+  }
+  for (; k < K; k += 128) {
+    const float4 wv = __ldg(reinterpret_cast<const float4*>(wr + k));
+#pragma unroll
+    for (int m = 0; m < SMALLM_MAX; m++)
+      if (m < Mb) {
+        const float4 xv = __ldg(reinterpret_cast<const float4*>(x + (long)m * K + k));
+        acc[m] = fmaf(wv.x, xv.x, fmaf(wv.y, xv.y, fmaf(wv.z, xv.z, fmaf(wv.w, xv.w, acc[m]))));
+      }
+  }
+#pragma unroll
+  for (int m = 0; m < SMALLM_MAX; m++) {
+    if (m < Mb) {
+      float v = warp_sum(acc[m]);
+      if (lane == 0) {
+        if (b) v += b[n];
+        if (act == 1) v = fmaxf(v, 0.f);
+        else if (act == 3) v = sigmoid_f(v);
+        y[(long)m * N + n] = v;
+      }
+    }
+  }
+}
 CMX_API int cmx_smallm_linear_fwd(const float* x, const float* w, const float* b, int act, float* y, int Mb, int N, int K, void* stream) {
   CMX_REQUIRE(Mb >= 1 && Mb <= SMALLM_MAX, "smallm_linear: Mb=%d must be in [1,%d]", Mb, SMALLM_MAX);
-  smallm_linear_fwd_kernel<<<cdiv(N, 8), 256, 0, (cudaStream_t)stream>>>(x, w, b, act, y, Mb, N, K);
+  if (K % 4 == 0 && ((((uintptr_t)x) | ((uintptr_t)w)) & 15) == 0)
+    smallm_linear_fwd_v4_kernel<<<cdiv(N, 8), 256, 0, (cudaStream_t)stream>>>(x, w, b, act, y, Mb, N, K);
+  else
+    smallm_linear_fwd_kernel<<<cdiv(N, 8), 256, 0, (cudaStream_t)stream>>>(x, w, b, act, y, Mb, N, K);
   LAUNCH_DONE("smallm_linear_fwd");
 }
 // dpre = dy * act'(y)
@@ -209,11 +310,16 @@ __global__ void __launch_bounds__(256) smallm_dx_kernel(const float* __restrict_
   float acc[SMALLM_MAX];
 #pragma unroll
   for (int m = 0; m < SMALLM_MAX; m++) acc[m] = 0.f;
-  const int nn = min(64, N - n0);
-  for (int n = 0; n < nn; n++) {
-    const float wv = w[(long)(n0 + n) * K + k];
+  // 8 independent weight loads in flight (rows beyond N are zero in sd, their weights are read as 0)
+  for (int n = 0; n < 64; n += 8) {
+    if (n0 + n >= N) break;
+    float wv[8];
 #pragma unroll
-    for (int m = 0; m < SMALLM_MAX; m++) acc[m] = fmaf(sd[m][n], wv, acc[m]);
+    for (int u = 0; u < 8; u++) wv[u] = n0 + n + u < N ? __ldg(w + (long)(n0 + n + u) * K + k) : 0.f;
+#pragma unroll
+    for (int u = 0; u < 8; u++)
+#pragma unroll
+      for (int m = 0; m < SMALLM_MAX; m++) acc[m] = fmaf(sd[m][n + u], wv[u], acc[m]);
   }
 #pragma unroll
   for (int m = 0; m < SMALLM_MAX; m++)
@@ -241,35 +347,49 @@ CMX_API int cmx_smallm_linear_bwd(const float* dy, const float* y, int act, cons
 // ---- fused spatial gate + rectification ------------------------------------------------------------------
 // One warp per token row; lane owns channels {4*(lane+32j)}, C <= 512, C % 4 == 0.
 constexpr int FR_MAXJ = 4;
+// sum over the G (power of two <= 32) consecutive lanes that share a row
+__device__ __forceinline__ float group_sum(float v, int G) {
+  for (int o = G >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// G lanes per row: 32, or C/4 when that is a smaller power of two (C = 64: two rows per warp, no idle lanes)
+static inline int frm_lanes_per_row(int C) {
+  const int g = C / 4;
+  return (g < 32 && (g & (g - 1)) == 0) ? g : 32;
+}
 __global__ void __launch_bounds__(256) frm_rectify_fwd_kernel(const bf16* __restrict__ a, long lda, const bf16* __restrict__ t, long ldt,
                                                               const float* __restrict__ w2, const float* __restrict__ b2,
                                                               const float* __restrict__ cw, float* __restrict__ sw,
                                                               bf16* __restrict__ r1, long ldr1, bf16* __restrict__ r2, long ldr2,
-                                                              long M, int HW, int C) {
+                                                              long M, int HW, int C, int G) {
   pdl_trigger();
   const int lane = threadIdx.x & 31;
-  const long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= M) return;
-  const int b = (int)(row / HW);
+  const int sl = lane % G, rpw = 32 / G;
+  const long row = ((long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * rpw + lane / G;
+  const bool valid = row < M;
+  const int b = valid ? (int)(row / HW) : 0;
   float d0 = 0.f, d1 = 0.f;
+  if (valid) {
 #pragma unroll
-  for (int j = 0; j < FR_MAXJ; j++) {
-    const int c = 4 * (lane + 32 * j);
-    if (c < C) {
-      float tv[4], wa[4], wb[4];
-      load4(t + row * ldt + c, tv);
-      load4(w2 + c, wa);
-      load4(w2 + C + c, wb);
+    for (int j = 0; j < FR_MAXJ; j++) {
+      const int c = 4 * (sl + 32 * j);
+      if (c < C) {
+        float tv[4], wa[4], wb[4];
+        load4(t + row * ldt + c, tv);
+        load4(w2 + c, wa);
+        load4(w2 + C + c, wb);
 #pragma unroll
-      for (int i = 0; i < 4; i++) { d0 = fmaf(tv[i], wa[i], d0); d1 = fmaf(tv[i], wb[i], d1); }
+        for (int i = 0; i < 4; i++) { d0 = fmaf(tv[i], wa[i], d0); d1 = fmaf(tv[i], wb[i], d1); }
+      }
     }
   }
-  const float s0 = sigmoid_f(warp_sum(d0) + b2[0]);
-  const float s1 = sigmoid_f(warp_sum(d1) + b2[1]);
-  if (lane == 0) { sw[row * 2] = s0; sw[row * 2 + 1] = s1; }
+  const float s0 = sigmoid_f(group_sum(d0, G) + b2[0]);
+  const float s1 = sigmoid_f(group_sum(d1, G) + b2[1]);
+  if (!valid) return;
+  if (sl == 0) { sw[row * 2] = s0; sw[row * 2 + 1] = s1; }
 #pragma unroll
   for (int j = 0; j < FR_MAXJ; j++) {
-    const int c = 4 * (lane + 32 * j);
+    const int c = 4 * (sl + 32 * j);
     if (c < C) {
       float a1[4], a2[4], c0[4], c1[4], o1[4], o2[4];
       load4(a + row * lda + c, a1);
@@ -292,8 +412,9 @@ CMX_API int cmx_frm_rectify_fwd(const void* a, int64_t lda, const void* t, int64
   CMX_REQUIRE(C % 4 == 0 && C <= 128 * FR_MAXJ, "frm_rectify: C=%d unsupported", C);
   const long M = (long)B * HW;
   if (M == 0) return 0;
-  frm_rectify_fwd_kernel<<<cdiv(M, 8), 256, 0, (cudaStream_t)stream>>>((const bf16*)a, lda, (const bf16*)t, ldt, w2, b2, cw, sw,
-                                                                       (bf16*)r1, ldr1, (bf16*)r2, ldr2, M, HW, C);
+  const int G = frm_lanes_per_row(C);
+  frm_rectify_fwd_kernel<<<cdiv(M, 8 * (32 / G)), 256, 0, (cudaStream_t)stream>>>((const bf16*)a, lda, (const bf16*)t, ldt, w2, b2, cw,
+                                                                                  sw, (bf16*)r1, ldr1, (bf16*)r2, ldr2, M, HW, C, G);
   LAUNCH_DONE("frm_rectify_fwd");
 }
 
@@ -305,7 +426,7 @@ __global__ void __launch_bounds__(256) frm_rectify_bwd_kernel(const float* __res
                                                               const float* __restrict__ cw, const float* __restrict__ sw,
                                                               float* __restrict__ da, long ldda, bf16* __restrict__ dt, long lddt,
                                                               float* __restrict__ dcw, float* __restrict__ dw2, float* __restrict__ db2,
-                                                              int HW, int C) {
+                                                              int HW, int C, int G) {
   pdl_trigger();
   __shared__ float s_dcw[2][512];
   __shared__ float s_dw2[2][512];
@@ -321,15 +442,18 @@ __global__ void __launch_bounds__(256) frm_rectify_bwd_kernel(const float* __res
 #pragma unroll
     for (int i = 0; i < 4; i++) { acw0[j][i] = 0.f; acw1[j][i] = 0.f; aw0[j][i] = 0.f; aw1[j][i] = 0.f; }
   float ab0 = 0.f, ab1 = 0.f;
-  for (int r = blockIdx.x * nwarp + warp; r < HW; r += gridDim.x * nwarp) {
-    const long row = (long)b * HW + r;
+  const int sl = lane % G, rpw = 32 / G, sub = lane / G;
+  for (int rb = (blockIdx.x * nwarp + warp) * rpw; rb < HW; rb += gridDim.x * nwarp * rpw) {
+    const int r = rb + sub;
+    const bool valid = r < HW;
+    const long row = (long)b * HW + (valid ? r : rb);  // invalid sub-rows shadow a valid one, contribute nothing, store nothing
     const float s0 = sw[row * 2], s1 = sw[row * 2 + 1];
     float g1[FR_MAXJ][4], g2[FR_MAXJ][4], a1[FR_MAXJ][4], a2[FR_MAXJ][4];
     float ds0 = 0.f, ds1 = 0.f;
 #pragma unroll
     for (int j = 0; j < FR_MAXJ; j++) {
-      const int c = 4 * (lane + 32 * j);
-      if (c < C) {
+      const int c = 4 * (sl + 32 * j);
+      if (c < C && valid) {
         load4(dr1 + row * lddr1 + c, g1[j]);
         load4(dr2 + row * lddr2 + c, g2[j]);
         load4(a + row * lda + c, a1[j]);
@@ -351,13 +475,13 @@ __global__ void __launch_bounds__(256) frm_rectify_bwd_kernel(const float* __res
         store4(da + row * ldda + C + c, o2);
       }
     }
-    ds0 = 0.5f * warp_sum(ds0) * s0 * (1.f - s0);  // through the sigmoid
-    ds1 = 0.5f * warp_sum(ds1) * s1 * (1.f - s1);
-    ab0 += ds0; ab1 += ds1;
+    ds0 = 0.5f * group_sum(ds0, G) * s0 * (1.f - s0);  // through the sigmoid
+    ds1 = 0.5f * group_sum(ds1, G) * s1 * (1.f - s1);
+    if (sl == 0) { ab0 += ds0; ab1 += ds1; }
 #pragma unroll
     for (int j = 0; j < FR_MAXJ; j++) {
-      const int c = 4 * (lane + 32 * j);
-      if (c < C) {
+      const int c = 4 * (sl + 32 * j);
+      if (c < C && valid) {
         float tv[4], wa[4], wb[4], o[4];
         load4(t + row * ldt + c, tv);
         load4(w2 + c, wa);
@@ -374,7 +498,7 @@ __global__ void __launch_bounds__(256) frm_rectify_bwd_kernel(const float* __res
   }
 #pragma unroll
   for (int j = 0; j < FR_MAXJ; j++) {
-    const int c = 4 * (lane + 32 * j);
+    const int c = 4 * (sl + 32 * j);
     if (c < C) {
 #pragma unroll
       for (int i = 0; i < 4; i++) {
@@ -385,7 +509,7 @@ __global__ void __launch_bounds__(256) frm_rectify_bwd_kernel(const float* __res
       }
     }
   }
-  if (lane == 0) { atomicAdd(&s_db2[0], ab0); atomicAdd(&s_db2[1], ab1); }
+  if (sl == 0) { atomicAdd(&s_db2[0], ab0); atomicAdd(&s_db2[1], ab1); }
   __syncthreads();
   for (int i = threadIdx.x; i < C; i += blockDim.x) {
     atomicAdd(dcw + (long)b * 2 * C + i, s_dcw[0][i]);
@@ -401,11 +525,12 @@ CMX_API int cmx_frm_rectify_bwd(const float* dr1, int64_t lddr1, const float* dr
                                 void* stream) {
   CMX_REQUIRE(C % 4 == 0 && C <= 128 * FR_MAXJ, "frm_rectify_bwd: C=%d unsupported", C);
   if (B == 0 || HW == 0) return 0;
-  int gx = cdiv(HW, 8 * 8);  // >= 8 rows per warp before the reduction flush
+  const int G = frm_lanes_per_row(C);
+  int gx = cdiv(HW, 8 * 8 * (32 / G));  // >= 8 row groups per warp before the reduction flush
   if (gx < 1) gx = 1;
   if (gx > 296) gx = 296;
   dim3 grid(gx, B);
   frm_rectify_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dr1, lddr1, dr2, lddr2, (const bf16*)a, lda, (const bf16*)t, ldt, w2,
-                                                                 cw, sw, da, ldda, (bf16*)dt, lddt, dcw, dw2, db2, HW, C);
+                                                                 cw, sw, da, ldda, (bf16*)dt, lddt, dcw, dw2, db2, HW, C, G);
   LAUNCH_DONE("frm_rectify_bwd");
 }

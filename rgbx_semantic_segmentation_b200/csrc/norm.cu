@@ -4,6 +4,7 @@
 #include "common.cuh"
 #include "../../include/cmx_b200.h"
 #include <atomic>
+#include <initializer_list>
 extern std::atomic<long long> g_cmx_launches;
 
 // ------------------------------------------------------------------------------------------------
@@ -710,6 +711,188 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const TDY* __restrict
   if (dres) st1(dres + row * lddres + c, d);
 }
 
+// Vectorised variants (C % 8 == 0, C <= 2048, 16-byte aligned rows): thread = 8 consecutive channels (one or two
+// 16-byte loads per tensor) of every NRL-th row, channel constants in registers, two rows in flight per thread.
+template <typename TDY, typename TX, typename TR>
+__device__ __forceinline__ void bn_eff_grad8(const TDY* dy, long lddy, const TX* x, long ldx, const TR* res, long ldr, long row,
+                                             int c, const float* mu, const float* is, const float* g, const float* be, int relu,
+                                             const float* mask, int rps, int C, float* d, float* xh) {
+  float xv[8];
+  load8(x + row * ldx + c, xv);
+  load8(dy + row * lddy + c, d);
+#pragma unroll
+  for (int i = 0; i < 8; i++) xh[i] = (xv[i] - mu[i]) * is[i];
+  if (mask) {
+    float mk[8];
+    load8(mask + (row / rps) * C + c, mk);
+#pragma unroll
+    for (int i = 0; i < 8; i++) d[i] *= mk[i];
+  }
+  if (relu) {
+    float o[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) o[i] = xh[i] * g[i] + be[i];
+    if (res) {
+      float r[8];
+      load8(res + row * ldr + c, r);
+#pragma unroll
+      for (int i = 0; i < 8; i++) o[i] += r[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+      if (o[i] <= 0.f) d[i] = 0.f;
+  }
+}
+
+template <typename TDY, typename TX, typename TR>
+__global__ void __launch_bounds__(256) bn_bwd_reduce_v8_kernel(const TDY* __restrict__ dy, long lddy, const TX* __restrict__ x,
+                                                               long ldx, const float* __restrict__ mean,
+                                                               const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                                               const float* __restrict__ beta, const TR* __restrict__ res,
+                                                               long ldr, int relu, const float* __restrict__ mask, int rps,
+                                                               double* __restrict__ sum_dy, double* __restrict__ sum_dy_xhat,
+                                                               long M, int C, int ng, int rows_per_cta) {
+  pdl_trigger();
+  __shared__ float sa[256][9], sb[256][9];
+  const int tid = threadIdx.x;
+  const int cg = tid % ng, rl = tid / ng, nrl = 256 / ng;
+  const int c = (blockIdx.x * ng + cg) * 8;
+  const long r0 = (long)blockIdx.y * rows_per_cta;
+  long r1 = r0 + rows_per_cta;
+  if (r1 > M) r1 = M;
+  float a[8], b[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) a[i] = b[i] = 0.f;
+  if (c < C && rl < nrl) {
+    float mu[8], is[8], g[8], be[8];
+    load8(mean + c, mu);
+    load8(invstd + c, is);
+    load8(gamma + c, g);
+    load8(beta + c, be);
+    long r = r0 + rl;
+    for (; r + nrl < r1; r += 2 * nrl) {
+      float d0[8], h0[8], d1[8], h1[8];
+      bn_eff_grad8(dy, lddy, x, ldx, res, ldr, r, c, mu, is, g, be, relu, mask, rps, C, d0, h0);
+      bn_eff_grad8(dy, lddy, x, ldx, res, ldr, r + nrl, c, mu, is, g, be, relu, mask, rps, C, d1, h1);
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        a[i] += d0[i] + d1[i];
+        b[i] += d0[i] * h0[i] + d1[i] * h1[i];
+      }
+    }
+    if (r < r1) {
+      float d0[8], h0[8];
+      bn_eff_grad8(dy, lddy, x, ldx, res, ldr, r, c, mu, is, g, be, relu, mask, rps, C, d0, h0);
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        a[i] += d0[i];
+        b[i] += d0[i] * h0[i];
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    sa[tid][i] = a[i];
+    sb[tid][i] = b[i];
+  }
+  __syncthreads();
+  if (tid < ng * 8) {
+    const int gi = tid >> 3, i = tid & 7;
+    const int cc = (blockIdx.x * ng + gi) * 8 + i;
+    if (cc < C) {
+      double da = 0., db = 0.;
+      for (int l = 0; l < nrl; l++) {
+        da += (double)sa[l * ng + gi][i];
+        db += (double)sb[l * ng + gi][i];
+      }
+      atomicAdd(sum_dy + cc, da);
+      atomicAdd(sum_dy_xhat + cc, db);
+    }
+  }
+}
+
+template <typename TDY, typename TX, typename TR, typename TDX>
+__global__ void __launch_bounds__(256) bn_bwd_apply_v8_kernel(const TDY* __restrict__ dy, long lddy, const TX* __restrict__ x,
+                                                              long ldx, const float* __restrict__ mean,
+                                                              const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                                              const float* __restrict__ beta, const TR* __restrict__ res,
+                                                              long ldr, int relu, const float* __restrict__ mask, int rps,
+                                                              const double* __restrict__ sum_dy,
+                                                              const double* __restrict__ sum_dy_xhat, TDX* __restrict__ dx,
+                                                              long lddx, TDX* __restrict__ dres, long lddres,
+                                                              float* __restrict__ dgamma, float* __restrict__ dbeta, long M, int C,
+                                                              int ng, int rows_per_cta) {
+  pdl_trigger();
+  const int tid = threadIdx.x;
+  const int cg = tid % ng, rl = tid / ng, nrl = 256 / ng;
+  const int c = (blockIdx.x * ng + cg) * 8;
+  if (c >= C || rl >= nrl) return;
+  const long r0 = (long)blockIdx.y * rows_per_cta;
+  long r1 = r0 + rows_per_cta;
+  if (r1 > M) r1 = M;
+  float mu[8], is[8], g[8], be[8], m1[8], m2[8], gi[8];
+  load8(mean + c, mu);
+  load8(invstd + c, is);
+  load8(gamma + c, g);
+  load8(beta + c, be);
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const double s1 = sum_dy[c + i], s2 = sum_dy_xhat[c + i];
+    m1[i] = (float)(s1 / (double)M);
+    m2[i] = (float)(s2 / (double)M);
+    gi[i] = g[i] * is[i];
+    if (dgamma && blockIdx.y == 0 && rl == 0) {  // parameter gradients: once per channel
+      atomicAdd(dgamma + c + i, (float)s2);
+      atomicAdd(dbeta + c + i, (float)s1);
+    }
+  }
+  long r = r0 + rl;
+  for (; r + nrl < r1; r += 2 * nrl) {
+    float d0[8], h0[8], d1[8], h1[8], o0[8], o1[8];
+    bn_eff_grad8(dy, lddy, x, ldx, res, ldr, r, c, mu, is, g, be, relu, mask, rps, C, d0, h0);
+    bn_eff_grad8(dy, lddy, x, ldx, res, ldr, r + nrl, c, mu, is, g, be, relu, mask, rps, C, d1, h1);
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      o0[i] = gi[i] * (d0[i] - m1[i] - h0[i] * m2[i]);
+      o1[i] = gi[i] * (d1[i] - m1[i] - h1[i] * m2[i]);
+    }
+    store8(dx + r * lddx + c, o0);
+    store8(dx + (r + nrl) * lddx + c, o1);
+    if (dres) {
+      store8(dres + r * lddres + c, d0);
+      store8(dres + (r + nrl) * lddres + c, d1);
+    }
+  }
+  if (r < r1) {
+    float d0[8], h0[8], o0[8];
+    bn_eff_grad8(dy, lddy, x, ldx, res, ldr, r, c, mu, is, g, be, relu, mask, rps, C, d0, h0);
+#pragma unroll
+    for (int i = 0; i < 8; i++) o0[i] = gi[i] * (d0[i] - m1[i] - h0[i] * m2[i]);
+    store8(dx + r * lddx + c, o0);
+    if (dres) store8(dres + r * lddres + c, d0);
+  }
+}
+
+// column-group / row-lane split of a 256-thread block and the row chunk that gives ~want_ctas CTAs
+static inline void bn_v8_shape(long M, int C, long want_ctas, int& ng, int& gx, int& rows_per_cta) {
+  ng = 32;  // largest power of two <= 32 that divides the number of 8-channel groups
+  while ((C / 8) % ng) ng >>= 1;
+  const int nrl = 256 / ng;
+  gx = (C / 8) / ng;
+  long rpc = (M * gx + want_ctas - 1) / want_ctas;
+  rpc = (rpc + 2 * nrl - 1) / (2 * nrl) * (2 * nrl);
+  if (rpc < 4L * nrl) rpc = 4L * nrl;
+  rows_per_cta = (int)rpc;
+}
+static inline bool bn_v8_ok(int C, std::initializer_list<const void*> ptrs, std::initializer_list<long> lds) {
+  if (C % 32) return false;  // at least four 16-byte groups per row segment (coalescing); otherwise the scalar kernels
+  for (const void* p : ptrs)
+    if (((uintptr_t)p) & 15) return false;
+  for (long l : lds)
+    if (l % 8) return false;
+  return true;
+}
+
 #define BN_DISPATCH3(MACRO)                                                          \
   do {                                                                               \
     const int key = dy_dtype * 4 + x_dtype * 2 + r_dtype;                            \
@@ -732,6 +915,20 @@ CMX_API int cmx_bn_bwd_reduce(const void* dy, int dy_dtype, int64_t lddy, const 
   if (M == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   if (rows_per_sample <= 0) rows_per_sample = 1;
+  if (bn_v8_ok(C, {dy, x, residual, mask, mean, invstd, gamma, beta}, {(long)lddy, (long)ldx, (long)ldr})) {
+    int ng, gx, rpc;
+    bn_v8_shape(M, C, 148L * 6, ng, gx, rpc);
+    dim3 grid(gx, cdiv(M, rpc));
+#define BN_R8(TDY, TX, TR)                                                                                                     \
+  bn_bwd_reduce_v8_kernel<TDY, TX, TR><<<grid, 256, 0, st>>>((const TDY*)dy, lddy, (const TX*)x, ldx, mean, invstd, gamma, beta, \
+                                                             (const TR*)residual, ldr, relu, mask, rows_per_sample, sum_dy,     \
+                                                             sum_dy_xhat, M, C, ng, rpc)
+    BN_DISPATCH3(BN_R8);
+#undef BN_R8
+    g_cmx_launches++;
+    CMX_CHECK_LAUNCH("bn_bwd_reduce_v8");
+    return 0;
+  }
   const int rows_per_cta = 256;
   dim3 grid(cdiv(C, 32), cdiv(M, rows_per_cta));
   CMX_REQUIRE(grid.y <= 65535, "bn_bwd_reduce: M too large");
@@ -755,6 +952,28 @@ CMX_API int cmx_bn_bwd_apply(const void* dy, int dy_dtype, int64_t lddy, const v
   CMX_REQUIRE(!dres || dres_dtype == dx_dtype, "bn_bwd_apply: dres dtype must equal dx dtype");
   cudaStream_t st = (cudaStream_t)stream;
   if (rows_per_sample <= 0) rows_per_sample = 1;
+  if (bn_v8_ok(C, {dy, x, residual, mask, mean, invstd, gamma, beta, dx, dres},
+               {(long)lddy, (long)ldx, (long)ldr, (long)lddx, (long)lddres})) {
+    int ng, gx, rpc;
+    bn_v8_shape(M, C, 148L * 8, ng, gx, rpc);
+    dim3 grid8(gx, cdiv(M, rpc));
+#define BN_A8(TDY, TX, TR)                                                                                                       \
+  do {                                                                                                                           \
+    if (dx_dtype == CMX_F32)                                                                                                     \
+      bn_bwd_apply_v8_kernel<TDY, TX, TR, float><<<grid8, 256, 0, st>>>(                                                         \
+          (const TDY*)dy, lddy, (const TX*)x, ldx, mean, invstd, gamma, beta, (const TR*)residual, ldr, relu, mask,              \
+          rows_per_sample, sum_dy, sum_dy_xhat, (float*)dx, lddx, (float*)dres, lddres, dgamma, dbeta, M, C, ng, rpc);           \
+    else                                                                                                                         \
+      bn_bwd_apply_v8_kernel<TDY, TX, TR, bf16><<<grid8, 256, 0, st>>>(                                                          \
+          (const TDY*)dy, lddy, (const TX*)x, ldx, mean, invstd, gamma, beta, (const TR*)residual, ldr, relu, mask,              \
+          rows_per_sample, sum_dy, sum_dy_xhat, (bf16*)dx, lddx, (bf16*)dres, lddres, dgamma, dbeta, M, C, ng, rpc);             \
+  } while (0)
+    BN_DISPATCH3(BN_A8);
+#undef BN_A8
+    g_cmx_launches++;
+    CMX_CHECK_LAUNCH("bn_bwd_apply_v8");
+    return 0;
+  }
   dim3 grid(cdiv(M * C, 256));
 #define BN_A(TDY, TX, TR)                                                                                                       \
   do {                                                                                                                          \

@@ -101,12 +101,14 @@ def test_layernorm_fwd_bwd(C, xdt, ydt):
 
 
 # ---------------------------------------------------------------------------------------------
-def test_batchnorm_train_fwd_bwd():
+@pytest.mark.parametrize("B,HW,C,xdt,use_res", [(3, 50, 64, torch.float32, True), (2, 1201, 320, bf, False),
+                                                 (8, 300, 512, torch.float32, True), (3, 77, 24, torch.float32, True),
+                                                 (1, 5, 128, bf, True)])
+def test_batchnorm_train_fwd_bwd(B, HW, C, xdt, use_res):
     torch.manual_seed(3)
-    B, HW, C = 3, 50, 64
     M = B * HW
-    x = rnd(M, C, scale=1.5) + 0.3
-    res = rnd(M, C, dtype=bf)
+    x = (rnd(M, C, scale=1.5) + 0.3).to(xdt)
+    res = rnd(M, C, dtype=bf) if use_res else None
     g = 1 + 0.1 * rnd(C)
     b = 0.1 * rnd(C)
     mask = ((torch.rand(B, C, device=DEV) > 0.2).float() / 0.8)
@@ -118,11 +120,12 @@ def test_batchnorm_train_fwd_bwd():
     ops.bn_finalize(ws[:C], ws[C:], M, 1e-3, 0.1, rm, rv, nbt, mean, invstd)
     y = torch.empty(M, C, device=DEV, dtype=bf)
     ops.bn_apply(x, mean, invstd, g, b, y, residual=res, relu=True, mask=mask, rows_per_sample=HW)
-    xr = x.clone().requires_grad_(True)
+    xr = x.float().clone().requires_grad_(True)
     gr, br = g.clone().requires_grad_(True), b.clone().requires_grad_(True)
     rm2, rv2 = torch.zeros(C, device=DEV), torch.ones(C, device=DEV)
     xb = F.batch_norm(xr.t().reshape(1, C, M), rm2, rv2, gr, br, True, 0.1, 1e-3).reshape(C, M).t()
-    ref = torch.relu(xb + res.float()) * mask.repeat_interleave(HW, 0)
+    pre = xb + (res.float() if use_res else 0.)
+    ref = torch.relu(pre) * mask.repeat_interleave(HW, 0)
     close(y, ref, 1e-2, 1e-2, "bn apply")
     close(rm, rm2, 1e-5, 1e-6, "running mean")
     close(rv, rv2, 1e-5, 1e-6, "running var")
@@ -135,6 +138,7 @@ def test_batchnorm_train_fwd_bwd():
     ws.zero_()
     ops.bn_bwd(dy, x, mean, invstd, g, b, dx, dg, db, ws, residual=res, relu=True, mask=mask, rows_per_sample=HW, dres=dres)
     close(dx, xr.grad, 1e-3, 1e-3, "bn dx")
+    close(dres, dy.float() * mask.repeat_interleave(HW, 0) * (pre > 0), 1e-6, 1e-6, "bn effective upstream gradient")
     close(dg, gr.grad, 1e-3, 1e-2, "bn dgamma")
     close(db, br.grad, 1e-3, 1e-2, "bn dbeta")
 
@@ -281,9 +285,9 @@ def test_softmax_kernels():
 
 
 # ---------------------------------------------------------------------------------------------
-def test_frm_kernels():
+@pytest.mark.parametrize("B,HW,C", [(3, 77, 64), (2, 301, 32), (2, 1200, 320), (8, 300, 512), (1, 53, 48)])
+def test_frm_kernels(B, HW, C):
     torch.manual_seed(8)
-    B, HW, C = 3, 77, 64
     M = B * HW
     a = rnd(M, 2 * C, dtype=bf)
     y = torch.empty(B, 4 * C, device=DEV)
