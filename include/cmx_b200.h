@@ -217,6 +217,10 @@ int cmx_upsample_sum_fwd(const void* z0, const void* z1, const void* z2, const v
                          const float* bias, void* out, int out_dtype, int B, int C, void* stream);
 /* adjoint for ONE source: dz[b,yi,xi,:] = sum_{y,x} w(y,x;yi,xi) * dout[b,y,x,:]  (bf16 in, bf16 out) */
 int cmx_upsample_bwd(const void* dout, int Ho, int Wo, void* dz, int Hi, int Wi, int B, int C, void* stream);
+/* the same adjoint for up to three sources (dz2 / dz3 may be NULL) in one pass over dout; C % 64 == 0
+ * (MLPDecoder.py:66-77 backward: the upsampled c2..c4 branches share the gradient of the fused map) */
+int cmx_upsample_bwd_multi(const void* dout, int Ho, int Wo, void* dz1, int H1, int W1, void* dz2, int H2, int W2,
+                           void* dz3, int H3, int W3, int B, int C, void* stream);
 
 /* ---- loss / logits / metric (builder.py:233,249; evaluator.py:393; utils/metric.py:8-15) ------- */
 /* low-res logits [B,h,w,ncls] fp32 (channels-last, pixel stride ld >= ncls elements: the engine pads the class axis to a

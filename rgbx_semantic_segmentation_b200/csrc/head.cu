@@ -21,20 +21,20 @@ struct UpSrc {
   int H, W;
   float sh, sw;  // in/out scale (fp32, as PyTorch computes it)
 };
-template <typename TO>
+template <typename TO, typename I>
 __global__ void __launch_bounds__(256) upsample_sum_kernel(const bf16* __restrict__ z0, UpSrc s1, UpSrc s2, UpSrc s3,
                                                            const float* __restrict__ bias, TO* __restrict__ out, int B, int H0,
                                                            int W0, int C) {
   pdl_trigger();
   const int c8 = C >> 3;
-  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long total = (long)B * H0 * W0 * c8;
+  const I idx = (I)blockIdx.x * blockDim.x + threadIdx.x;  // I: unsigned when the element count allows (cheap divisions)
+  const I total = (I)B * H0 * W0 * c8;
   if (idx >= total) return;
-  const int c = (int)(idx % c8) * 8;
-  const long pix = idx / c8;
-  const int x = (int)(pix % W0);
-  const int y = (int)((pix / W0) % H0);
-  const int b = (int)(pix / ((long)W0 * H0));
+  const int c = (int)(idx % (I)c8) * 8;
+  const I pix = idx / (I)c8;
+  const int x = (int)(pix % (I)W0);
+  const int y = (int)((pix / (I)W0) % (I)H0);
+  const int b = (int)(pix / ((I)W0 * H0));
   float acc[8];
   if (bias) load8(bias + c, acc);
   else {
@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(256) upsample_sum_kernel(const bf16* __restric
   }
   {
     float v[8];
-    load8(z0 + pix * C + c, v);
+    load8(z0 + (long)pix * C + c, v);
 #pragma unroll
     for (int i = 0; i < 8; i++) acc[i] += v[i];
   }
@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(256) upsample_sum_kernel(const bf16* __restric
 #pragma unroll
     for (int i = 0; i < 8; i++) acc[i] += w00 * v00[i] + w01 * v01[i] + w10 * v10[i] + w11 * v11[i];
   }
-  store8(out + pix * C + c, acc);
+  store8(out + (long)pix * C + c, acc);
 }
 CMX_API int cmx_upsample_sum_fwd(const void* z0, const void* z1, const void* z2, const void* z3, int H0, int W0, int H1, int W1,
                                  int H2, int W2, int H3, int W3, const float* bias, void* out, int out_dtype, int B, int C,
@@ -77,10 +77,16 @@ CMX_API int cmx_upsample_sum_fwd(const void* z0, const void* z1, const void* z2,
   UpSrc s1{(const bf16*)z1, H1, W1, (float)H1 / (float)H0, (float)W1 / (float)W0};
   UpSrc s2{(const bf16*)z2, H2, W2, (float)H2 / (float)H0, (float)W2 / (float)W0};
   UpSrc s3{(const bf16*)z3, H3, W3, (float)H3 / (float)H0, (float)W3 / (float)W0};
-  if (out_dtype == CMX_F32)
-    upsample_sum_kernel<float><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)z0, s1, s2, s3, bias, (float*)out, B, H0, W0, C);
-  else
-    upsample_sum_kernel<bf16><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)z0, s1, s2, s3, bias, (bf16*)out, B, H0, W0, C);
+#define UPS(TO, I) upsample_sum_kernel<TO, I><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)z0, s1, s2, s3, bias, (TO*)out, B, H0, W0, C)
+  const bool small = total < (1L << 31);
+  if (out_dtype == CMX_F32) {
+    if (small) UPS(float, unsigned);
+    else UPS(float, long);
+  } else {
+    if (small) UPS(bf16, unsigned);
+    else UPS(bf16, long);
+  }
+#undef UPS
   LAUNCH_DONE("upsample_sum_fwd");
 }
 
@@ -138,11 +144,153 @@ CMX_API int cmx_upsample_bwd(const void* dout, int Ho, int Wo, void* dz, int Hi,
   LAUNCH_DONE("upsample_bwd");
 }
 
+// ---- adjoint of up to three bilinear sources in ONE pass over dout (row-separable form) -----------------------
+// CTA = (destination k, low-res row yi, sample b, 64-channel chunk).  Phase 1 folds the <= 2*ceil(Ho/Hi)+2 output rows
+// whose vertical stencil touches yi into a [Wo][64] fp32 row in shared memory (coalesced 16-byte loads, all threads,
+// the row list is CTA-uniform so there is no divergence); phase 2 folds that row horizontally into the Wi low-res
+// pixels.  blockIdx.x enumerates the rows of ALL destinations that belong to one band of the coarsest destination, so
+// CTAs that read the same dout rows are adjacent in launch order and dout comes from DRAM about once instead of 3 x 4.
+struct UpDst {
+  bf16* dz;
+  int H, W;
+  float sh, sw;
+  int rows_per_band;
+};
+constexpr int UPB_CC = 64;     // channels per CTA
+constexpr int UPB_MAXROWS = 64;
+__global__ void __launch_bounds__(256) upsample_bwd_multi_kernel(const bf16* __restrict__ dout, int Ho, int Wo, int C, UpDst d0,
+                                                                 UpDst d1, UpDst d2, int nchunk) {
+  pdl_trigger();
+  extern __shared__ float s_t[];  // [Wo][UPB_CC]
+  __shared__ int s_y[UPB_MAXROWS];
+  __shared__ float s_w[UPB_MAXROWS];
+  __shared__ int s_n;
+  int job = blockIdx.x;
+  UpDst d = d0;
+  if (job >= d.rows_per_band) {
+    job -= d.rows_per_band;
+    d = d1;
+    if (job >= d.rows_per_band) {
+      job -= d.rows_per_band;
+      d = d2;
+    }
+  }
+  const int yi = blockIdx.y * d.rows_per_band + job;
+  if (yi >= d.H) return;
+  const int b = blockIdx.z / nchunk;
+  const int c0 = (blockIdx.z % nchunk) * UPB_CC;
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    const float rh = 1.f / d.sh;
+    int ylo = (int)floorf((yi - 0.5f) * rh - 0.5f) - 1, yhi = (int)ceilf((yi + 1.5f) * rh - 0.5f) + 1;
+    if (ylo < 0) ylo = 0;
+    if (yhi > Ho - 1) yhi = Ho - 1;
+    int n = 0;
+    for (int y = ylo; y <= yhi; y++) {
+      int y0, y1;
+      float ly;
+      bilin_src(y, d.sh, d.H, y0, y1, ly);
+      const float wy = (y0 == yi ? 1.f - ly : 0.f) + (y1 == yi ? ly : 0.f);
+      if (wy != 0.f && n < UPB_MAXROWS) { s_y[n] = y; s_w[n] = wy; n++; }
+    }
+    s_n = n;
+  }
+  __syncthreads();
+  const int n = s_n;
+  // phase 1: t[x][c] = sum_rows wy * dout[b, y, x, c0 + c]
+  const bf16* base = dout + (long)b * Ho * Wo * C + c0;
+  for (int item = tid; item < Wo * (UPB_CC / 8); item += 256) {
+    const int g = item & (UPB_CC / 8 - 1), x = item / (UPB_CC / 8);
+    const bf16* px = base + (long)x * C + g * 8;
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) acc[i] = 0.f;
+    int r = 0;
+    for (; r + 3 < n; r += 4) {  // four independent 16-byte loads in flight
+      float v0[8], v1[8], v2[8], v3[8];
+      load8(px + (long)s_y[r] * Wo * C, v0);
+      load8(px + (long)s_y[r + 1] * Wo * C, v1);
+      load8(px + (long)s_y[r + 2] * Wo * C, v2);
+      load8(px + (long)s_y[r + 3] * Wo * C, v3);
+      const float w0 = s_w[r], w1 = s_w[r + 1], w2 = s_w[r + 2], w3 = s_w[r + 3];
+#pragma unroll
+      for (int i = 0; i < 8; i++) acc[i] += (w0 * v0[i] + w1 * v1[i]) + (w2 * v2[i] + w3 * v3[i]);
+    }
+    for (; r < n; r++) {
+      float v0[8];
+      load8(px + (long)s_y[r] * Wo * C, v0);
+      const float w0 = s_w[r];
+#pragma unroll
+      for (int i = 0; i < 8; i++) acc[i] = fmaf(w0, v0[i], acc[i]);
+    }
+    float4* o = reinterpret_cast<float4*>(s_t + x * UPB_CC + g * 8);
+    o[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    o[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+  }
+  __syncthreads();
+  // phase 2: dz[b, yi, xi, c0 + c] = sum_x wx * t[x][c]   (thread = channel pair of one low-res pixel)
+  const float rw = 1.f / d.sw;
+  bf16* orow = d.dz + ((long)b * d.H + yi) * d.W * C + c0;
+  for (int item = tid; item < d.W * (UPB_CC / 2); item += 256) {
+    const int cp = item & (UPB_CC / 2 - 1), xi = item / (UPB_CC / 2);
+    int xlo = (int)floorf((xi - 0.5f) * rw - 0.5f) - 1, xhi = (int)ceilf((xi + 1.5f) * rw - 0.5f) + 1;
+    if (xlo < 0) xlo = 0;
+    if (xhi > Wo - 1) xhi = Wo - 1;
+    float a0 = 0.f, a1 = 0.f;
+    for (int x = xlo; x <= xhi; x++) {
+      int x0, x1;
+      float lx;
+      bilin_src(x, d.sw, d.W, x0, x1, lx);
+      const float wx = (x0 == xi ? 1.f - lx : 0.f) + (x1 == xi ? lx : 0.f);
+      const float2 tv = *reinterpret_cast<const float2*>(s_t + x * UPB_CC + cp * 2);
+      a0 = fmaf(wx, tv.x, a0);
+      a1 = fmaf(wx, tv.y, a1);
+    }
+    *reinterpret_cast<__nv_bfloat162*>(orow + (long)xi * C + cp * 2) = __floats2bfloat162_rn(a0, a1);
+  }
+}
+CMX_API int cmx_upsample_bwd_multi(const void* dout, int Ho, int Wo, void* dz1, int H1, int W1, void* dz2, int H2, int W2,
+                                   void* dz3, int H3, int W3, int B, int C, void* stream) {
+  CMX_REQUIRE(C % UPB_CC == 0, "upsample_bwd_multi: C %% 64");
+  CMX_REQUIRE(dz1 && H1 > 0 && W1 > 0, "upsample_bwd_multi: at least one destination");
+  if (B == 0) return 0;
+  void* dz[3] = {dz1, dz2, dz3};
+  int Hs[3] = {H1, H2, H3}, Ws[3] = {W1, W2, W3};
+  int nd = 0, bands = 1 << 30;
+  for (int k = 0; k < 3; k++)
+    if (dz[k]) {
+      CMX_REQUIRE(nd == k, "upsample_bwd_multi: destinations must be packed from the first slot");
+      CMX_REQUIRE(Hs[k] > 0 && Ws[k] > 0 && Hs[k] <= Ho && Ws[k] <= Wo, "upsample_bwd_multi: destination %d larger than the source", k);
+      CMX_REQUIRE(2 * cdiv(Ho, Hs[k]) + 4 <= UPB_MAXROWS, "upsample_bwd_multi: scale factor too large");
+      nd++;
+      if (Hs[k] < bands) bands = Hs[k];
+    }
+  UpDst d[3];
+  int jobs = 0;
+  for (int k = 0; k < 3; k++) {
+    if (k < nd) {
+      d[k] = UpDst{(bf16*)dz[k], Hs[k], Ws[k], (float)Hs[k] / (float)Ho, (float)Ws[k] / (float)Wo, cdiv(Hs[k], bands)};
+      jobs += d[k].rows_per_band;
+    } else {
+      d[k] = UpDst{nullptr, 0, 0, 1.f, 1.f, 1 << 30};
+    }
+  }
+  const int nchunk = C / UPB_CC;
+  const size_t smem = (size_t)Wo * UPB_CC * sizeof(float);
+  CMX_REQUIRE(smem <= 200 * 1024, "upsample_bwd_multi: Wo=%d too wide", Wo);
+  CMX_REQUIRE((long)B * nchunk <= 65535 && bands <= 65535, "upsample_bwd_multi: grid too large");
+  if (smem > 48 * 1024) cudaFuncSetAttribute(upsample_bwd_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  dim3 grid(jobs, bands, B * nchunk);
+  upsample_bwd_multi_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>((const bf16*)dout, Ho, Wo, C, d[0], d[1], d[2], nchunk);
+  LAUNCH_DONE("upsample_bwd_multi");
+}
+
 // ---- fused bilinear upsample + cross entropy (+ gradient scatter) ----------------------------------------
 // CTA = 32 x 8 threads covering a 32 x 8 full-resolution tile.  The low-res window the tile touches is
 // staged in shared memory (logits in, gradient accumulator out); MAXC classes.
 constexpr int CE_MAXC = 16;
 constexpr int CE_TW = 32, CE_TH = 8;
+constexpr float CE_FIX = 2097152.f;  // 2^21: fixed-point scale of the per-CTA gradient partials (plain CE)
 
 // FOCAL: loss = w_ce * CE + w_focal * FocalLoss, where FocalLoss is the reference's all-classes form (utils/loss_opr.py:
 // 157-196: pt_k = p_k for the target class and 1 - p_k otherwise, -alpha_k (1 - pt_k)^gamma log(pt_k + 1e-8) summed over the
@@ -249,10 +397,21 @@ __global__ void __launch_bounds__(256) ce_upsampled_kernel(const float* __restri
           if (k < ncls) {
             float g = v[k] * inv - (k == (int)lab ? 1.f : 0.f);
             if (FOCAL) g = fa.w_ce * g + fa.w_focal * (v[k] * inv) * (hk[k] - hs);
-            atomicAdd(&s_g[o00 + k], w00 * g);
-            atomicAdd(&s_g[o01 + k], w01 * g);
-            atomicAdd(&s_g[o10 + k], w10 * g);
-            atomicAdd(&s_g[o11 + k], w11 * g);
+            if (FOCAL) {
+              atomicAdd(&s_g[o00 + k], w00 * g);
+              atomicAdd(&s_g[o01 + k], w01 * g);
+              atomicAdd(&s_g[o10 + k], w10 * g);
+              atomicAdd(&s_g[o11 + k], w11 * g);
+            } else {
+              // plain CE: |w * g| <= 1 and a CTA has 256 pixels, so the per-CTA partial sums fit a 2^-21 fixed-point
+              // int32: native shared-memory integer atomics (ATOMS.ADD) instead of 36 compare-and-swap loops per pixel
+              // on addresses that 16 neighbouring pixels share, and an order-independent (deterministic) CTA partial
+              int* s_gi = reinterpret_cast<int*>(s_g);
+              atomicAdd(&s_gi[o00 + k], __float2int_rn(w00 * g * CE_FIX));
+              atomicAdd(&s_gi[o01 + k], __float2int_rn(w01 * g * CE_FIX));
+              atomicAdd(&s_gi[o10 + k], __float2int_rn(w10 * g * CE_FIX));
+              atomicAdd(&s_gi[o11 + k], __float2int_rn(w11 * g * CE_FIX));
+            }
           }
         }
       }
@@ -274,7 +433,7 @@ __global__ void __launch_bounds__(256) ce_upsampled_kernel(const float* __restri
       const int k = i % ncls;
       const int xx = (i / ncls) % nw;
       const int yy = i / (ncls * nw);
-      const float g = s_g[i];
+      const float g = FOCAL ? s_g[i] : (float)reinterpret_cast<const int*>(s_g)[i] * (1.f / CE_FIX);
       if (g != 0.f) atomicAdd(dlogits + (((long)b * h + ly0 + yy) * w + lx0 + xx) * ld + k, g);
     }
   }

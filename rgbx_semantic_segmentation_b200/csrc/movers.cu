@@ -14,19 +14,22 @@ extern std::atomic<long long> g_cmx_launches;
   } while (0)
 
 // ---- stage-1 im2col from the NCHW fp32 image ------------------------------------------------------
+// I = index type of the thread -> (row, column group) decomposition: unsigned 32-bit whenever the element count allows
+// (64-bit divisions cost ~100 instructions each and these kernels move 16-32 bytes per thread)
+template <typename I>
 __global__ void __launch_bounds__(256) im2col_nchw_kernel(const float* __restrict__ x, bf16* __restrict__ col, int B, int Cin, int H,
                                                           int W, int k, int s, int p, int Ho, int Wo, int kpad) {
   pdl_trigger();
   // one thread = 8 consecutive im2col columns of one output pixel (one 16-byte store)
   const int g8 = kpad >> 3;
-  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long total = (long)B * Ho * Wo * g8;
+  const I idx = (I)blockIdx.x * blockDim.x + threadIdx.x;
+  const I total = (I)B * Ho * Wo * g8;
   if (idx >= total) return;
-  const int j0 = (int)(idx % g8) * 8;
-  const long row = idx / g8;
-  const int ox = (int)(row % Wo);
-  const int oy = (int)((row / Wo) % Ho);
-  const int b = (int)(row / ((long)Wo * Ho));
+  const int j0 = (int)(idx % (I)g8) * 8;
+  const I row = idx / (I)g8;
+  const int ox = (int)(row % (I)Wo);
+  const int oy = (int)((row / (I)Wo) % (I)Ho);
+  const int b = (int)(row / ((I)Wo * Ho));
   float v[8];
 #pragma unroll
   for (int i = 0; i < 8; i++) {
@@ -39,66 +42,73 @@ __global__ void __launch_bounds__(256) im2col_nchw_kernel(const float* __restric
       if (iy >= 0 && iy < H && ix >= 0 && ix < W) v[i] = x[(((long)b * Cin + ci) * H + iy) * W + ix];
     }
   }
-  store8(col + row * kpad + j0, v);
+  store8(col + (long)row * kpad + j0, v);
 }
 CMX_API int cmx_im2col_nchw(const float* x, void* col, int B, int Cin, int H, int W, int k, int s, int p, int Ho, int Wo,
                             int kpad, void* stream) {
   CMX_REQUIRE(kpad >= k * k * Cin && kpad % 8 == 0, "im2col_nchw: kpad must be a multiple of 8 and >= k*k*Cin");
   const long total = (long)B * Ho * Wo * (kpad >> 3);
   if (total == 0) return 0;
-  im2col_nchw_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(x, (bf16*)col, B, Cin, H, W, k, s, p, Ho, Wo, kpad);
+  if (total < (1L << 31))
+    im2col_nchw_kernel<unsigned><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(x, (bf16*)col, B, Cin, H, W, k, s, p, Ho, Wo, kpad);
+  else
+    im2col_nchw_kernel<long><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(x, (bf16*)col, B, Cin, H, W, k, s, p, Ho, Wo, kpad);
   LAUNCH_DONE("im2col_nchw");
 }
 
 // ---- NHWC bf16 im2col (8 channels per thread) ------------------------------------------------------
+template <typename I>
 __global__ void __launch_bounds__(256) im2col_nhwc_kernel(const bf16* __restrict__ x, long ldx, bf16* __restrict__ col, int B, int H,
                                                           int W, int C, int k, int s, int p, int Ho, int Wo) {
   pdl_trigger();
   const int c8 = C >> 3;
-  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long total = (long)B * Ho * Wo * k * k * c8;
+  const I idx = (I)blockIdx.x * blockDim.x + threadIdx.x;
+  const I total = (I)B * Ho * Wo * k * k * c8;
   if (idx >= total) return;
-  const int cg = (int)(idx % c8);
-  long t = idx / c8;
-  const int tap = (int)(t % (k * k));
-  const long row = t / (k * k);
+  const int cg = (int)(idx % (I)c8);
+  const I t = idx / (I)c8;
+  const int tap = (int)(t % (I)(k * k));
+  const I row = t / (I)(k * k);
   const int kh = tap / k, kw = tap % k;
-  const int ox = (int)(row % Wo);
-  const int oy = (int)((row / Wo) % Ho);
-  const int b = (int)(row / ((long)Wo * Ho));
+  const int ox = (int)(row % (I)Wo);
+  const int oy = (int)((row / (I)Wo) % (I)Ho);
+  const int b = (int)(row / ((I)Wo * Ho));
   const int iy = oy * s - p + kh, ix = ox * s - p + kw;
   uint4 v = make_uint4(0, 0, 0, 0);
   if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = *reinterpret_cast<const uint4*>(x + ((long)(b * H + iy) * W + ix) * ldx + cg * 8);
-  *reinterpret_cast<uint4*>(col + (row * (k * k) + tap) * C + cg * 8) = v;
+  *reinterpret_cast<uint4*>(col + ((long)row * (k * k) + tap) * C + cg * 8) = v;
 }
 CMX_API int cmx_im2col_nhwc(const void* x, int64_t ldx, void* col, int B, int H, int W, int C, int k, int s, int p, int Ho,
                             int Wo, void* stream) {
   CMX_REQUIRE(C % 8 == 0 && ldx % 8 == 0, "im2col_nhwc: C %% 8");
   const long total = (long)B * Ho * Wo * k * k * (C >> 3);
   if (total == 0) return 0;
-  im2col_nhwc_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, ldx, (bf16*)col, B, H, W, C, k, s, p, Ho, Wo);
+  if (total < (1L << 31))
+    im2col_nhwc_kernel<unsigned><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, ldx, (bf16*)col, B, H, W, C, k, s, p, Ho, Wo);
+  else
+    im2col_nhwc_kernel<long><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, ldx, (bf16*)col, B, H, W, C, k, s, p, Ho, Wo);
   LAUNCH_DONE("im2col_nhwc");
 }
 
 // ---- col2im (adjoint of im2col_nhwc), gather form -------------------------------------------------
-template <typename TA, typename TO>
+template <typename TA, typename TO, typename I>
 __global__ void __launch_bounds__(256) col2im_nhwc_kernel(const bf16* __restrict__ dcol, const TA* __restrict__ add, long ldadd,
                                                           TO* __restrict__ dx, long lddx, int B, int H, int W, int C, int k, int s,
                                                           int p, int Ho, int Wo) {
   pdl_trigger();
   const int c8 = C >> 3;
-  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long total = (long)B * H * W * c8;
+  const I idx = (I)blockIdx.x * blockDim.x + threadIdx.x;
+  const I total = (I)B * H * W * c8;
   if (idx >= total) return;
-  const int cg = (int)(idx % c8);
-  const long pix = idx / c8;
-  const int ix = (int)(pix % W);
-  const int iy = (int)((pix / W) % H);
-  const int b = (int)(pix / ((long)W * H));
+  const int cg = (int)(idx % (I)c8);
+  const I pix = idx / (I)c8;
+  const int ix = (int)(pix % (I)W);
+  const int iy = (int)((pix / (I)W) % (I)H);
+  const int b = (int)(pix / ((I)W * H));
   float acc[8];
 #pragma unroll
   for (int i = 0; i < 8; i++) acc[i] = 0.f;
-  if (add) load8(add + pix * ldadd + cg * 8, acc);
+  if (add) load8(add + (long)pix * ldadd + cg * 8, acc);
   // only taps with (iy + p - kh) divisible by the stride contribute: kh = (iy + p) mod s, + s, ... (one tap for the
   // non-overlapping SR convolutions k = s = R instead of a scan over all R*R)
   for (int kh = (iy + p) % s; kh < k; kh += s) {
@@ -117,7 +127,7 @@ __global__ void __launch_bounds__(256) col2im_nhwc_kernel(const bf16* __restrict
       for (int i = 0; i < 8; i++) acc[i] += v[i];
     }
   }
-  store8(dx + pix * lddx + cg * 8, acc);
+  store8(dx + (long)pix * lddx + cg * 8, acc);
 }
 CMX_API int cmx_col2im_nhwc(const void* dcol, const void* add, int add_dtype, int64_t ldadd, void* dx, int dx_dtype, int64_t lddx,
                             int B, int H, int W, int C, int k, int s, int p, int Ho, int Wo, void* stream) {
@@ -126,7 +136,15 @@ CMX_API int cmx_col2im_nhwc(const void* dcol, const void* add, int add_dtype, in
   if (total == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   dim3 grid(cdiv(total, 256));
-#define C2I(TA, TO) col2im_nhwc_kernel<TA, TO><<<grid, 256, 0, st>>>((const bf16*)dcol, (const TA*)add, ldadd, (TO*)dx, lddx, B, H, W, C, k, s, p, Ho, Wo)
+#define C2I(TA, TO)                                                                                                            \
+  do {                                                                                                                         \
+    if (total < (1L << 31))                                                                                                    \
+      col2im_nhwc_kernel<TA, TO, unsigned><<<grid, 256, 0, st>>>((const bf16*)dcol, (const TA*)add, ldadd, (TO*)dx, lddx, B, H, \
+                                                                 W, C, k, s, p, Ho, Wo);                                        \
+    else                                                                                                                       \
+      col2im_nhwc_kernel<TA, TO, long><<<grid, 256, 0, st>>>((const bf16*)dcol, (const TA*)add, ldadd, (TO*)dx, lddx, B, H, W,  \
+                                                             C, k, s, p, Ho, Wo);                                               \
+  } while (0)
   if (add_dtype == CMX_F32 && dx_dtype == CMX_F32) C2I(float, float);
   else if (add_dtype == CMX_F32) C2I(float, bf16);
   else if (dx_dtype == CMX_F32) C2I(bf16, float);

@@ -803,13 +803,16 @@ class Engine:
         gf = self.G2(p + ".linear_fuse.0.weight")
         H0, W0 = c.sizes[0]
         dfs = []
+        # adjoint of the three upsampled branches in one pass over dfuse (coarsest destination first = band index)
+        dzs = [dfuse] + [self.E(c.feats[s].shape[0], E_) for s in (1, 2, 3)]
+        if E_ % 64 == 0:
+            ops.upsample_bwd_multi(dfuse, H0, W0, dzs[:0:-1], [c.sizes[s] for s in (3, 2, 1)], B, E_)
+        else:
+            for s in (1, 2, 3):
+                ops.upsample_bwd(dfuse, H0, W0, dzs[s], c.sizes[s][0], c.sizes[s][1], B, E_)
         for s in range(4):
             Ms, Cs = c.feats[s].shape
-            if s == 0:
-                dz = dfuse
-            else:
-                dz = self.E(Ms, E_)
-                ops.upsample_bwd(dfuse, H0, W0, dz, c.sizes[s][0], c.sizes[s][1], B, E_)
+            dz = dzs[s]
             sl = slice((3 - s) * E_, (4 - s) * E_)
             wc = self.W(p + f".linear_c{s + 1}.proj.weight")
             with self._wgrad_ctx(dz, c.feats[s]):

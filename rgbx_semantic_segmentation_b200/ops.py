@@ -407,6 +407,19 @@ def upsample_bwd(dout, Ho, Wo, dz, Hi, Wi, B, C):
     return dz
 
 
+def upsample_bwd_multi(dout, Ho, Wo, dzs, sizes, B, C):
+    """adjoint of 1..3 bilinear sources in one pass over dout: dzs[i] bf16 [B*h_i*w_i, C], sizes[i] = (h_i, w_i)"""
+    assert 1 <= len(dzs) <= 3 and len(dzs) == len(sizes)
+    args = []
+    for i in range(3):
+        if i < len(dzs):
+            args += [dzs[i].data_ptr(), sizes[i][0], sizes[i][1]]
+        else:
+            args += [None, 0, 0]
+    _call("cmx_upsample_bwd_multi", dout.data_ptr(), Ho, Wo, *args, B, C, _stream(), nbytes=_nb(dout, *dzs))
+    return dzs
+
+
 def ce_upsampled(logits, label, ignore_index, acc, dlogits, B, h, w, H, W, ncls):
     """logits / dlogits: [B*h*w, ncls] row-major views (row stride >= ncls, identical for both)"""
     assert label.dtype == torch.int64 and label.is_contiguous()

@@ -381,6 +381,12 @@ def test_upsample_sum_and_adjoint(sizes):
         dz = torch.empty(B * h * w, C, device=DEV, dtype=bf)
         ops.upsample_bwd(dout, H0, W0, dz, h, w, B, C)
         close(dz, zr[i].grad.permute(0, 2, 3, 1).reshape(-1, C), 1e-2, 2e-2, "upsample adjoint %d" % i)
+    # the three adjoints in one pass over dout (any order / subset of destinations)
+    for order in ((3, 2, 1), (1, 2, 3), (2,), (3, 1)):
+        dzs = [torch.full((B * sizes[i][0] * sizes[i][1], C), float("nan"), device=DEV, dtype=bf) for i in order]
+        ops.upsample_bwd_multi(dout, H0, W0, dzs, [sizes[i] for i in order], B, C)
+        for dz, i in zip(dzs, order):
+            close(dz, zr[i].grad.permute(0, 2, 3, 1).reshape(-1, C), 1e-2, 2e-2, "fused upsample adjoint %d" % i)
 
 
 @pytest.mark.parametrize("h,w,H,W,ncls,ld", [(12, 16, 48, 64, 9, 16), (23, 40, 90, 160, 5, 8), (5, 7, 19, 27, 9, 9)])
