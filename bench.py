@@ -305,6 +305,29 @@ def main_ours(args):
                         "t_roofline_ms": t_roof, "t_measured_ms": ms / args.steps, "frac": t_roof / (ms / args.steps),
                         "note": "sum over the launches of one step (launches without a byte count contribute 0); "
                                 "measured = graph-replayed training step incl. optimizer"}
+        # DRAM bytes actually moved per launch (dram__bytes_read + write) from the committed ncu capture of this step
+        # (scripts/ncu_launch_summary.py -> profiles/ncu_traffic_by_class.json); None when no capture is committed
+        traffic, traffic_src = {}, None
+        tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_traffic_by_class.json")
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                tj = json.load(f)
+            traffic = {k: v.get("dram_bytes_per_launch") for k, v in tj.get("by_class", {}).items()}
+            traffic_src = tj.get("source")
+        roof["traffic"] = traffic.get(name)
+        roof["traffic_src"] = traffic_src
+        # the other classes that matter, same definitions (achieved = algorithmic bytes or flops / isolated duration)
+        klist = []
+        for kname, (kt, kn, kfl, knb) in top[:12]:
+            if not knb:
+                continue
+            tb = kfl / max(knb, 1) > RIDGE_FLOP_PER_BYTE
+            kach = kfl / (kt * 1e-3) / 1e12 if tb else knb / (kt * 1e-3) / 1e9
+            kpk = pk["bf16_tflops_sustained"] if tb else pk["hbm_gbs"]
+            klist.append({"kernel": kname, "launches": kn, "share": round(kt / total, 4), "bound": "tensor" if tb else "hbm",
+                          "achieved": round(kach, 1), "unit": "TFLOP/s" if tb else "GB/s", "frac": round(kach / kpk, 3),
+                          "algorithmic_bytes_per_launch": knb / kn, "traffic": traffic.get(kname)})
+        roof["kernels"] = klist
         roof.update(kernel=name, launches_per_step=n, avg_us=1e3 * t / n, share_of_step=t / total, peak_src=pk["src"],
                     timing="CUDA events around every launch of one eager step run on a single stream with the host pre-enqueued "
                            "(isolated kernel durations; their sum is %.1f ms, the graph-replayed multi-stream step overlaps them)" % total,

@@ -155,13 +155,14 @@ struct UpDst {
   int H, W;
   float sh, sw;
   int rows_per_band;
+  int maxc;  // upper bound of the horizontal stencil support in output pixels (2 * ceil(Wo / W) + 4)
 };
 constexpr int UPB_CC = 64;     // channels per CTA
 constexpr int UPB_MAXROWS = 64;
 __global__ void __launch_bounds__(256) upsample_bwd_multi_kernel(const bf16* __restrict__ dout, int Ho, int Wo, int C, UpDst d0,
                                                                  UpDst d1, UpDst d2, int nchunk) {
   pdl_trigger();
-  extern __shared__ float s_t[];  // [Wo][UPB_CC]
+  extern __shared__ float s_t[];  // [Wo][UPB_CC] row accumulator, then the horizontal weight table
   __shared__ int s_y[UPB_MAXROWS];
   __shared__ float s_w[UPB_MAXROWS];
   __shared__ int s_n;
@@ -194,6 +195,28 @@ __global__ void __launch_bounds__(256) upsample_bwd_multi_kernel(const bf16* __r
       if (wy != 0.f && n < UPB_MAXROWS) { s_y[n] = y; s_w[n] = wy; n++; }
     }
     s_n = n;
+  }
+  // horizontal weights, once per CTA instead of once per (pixel, channel pair): s_wx[xi][j] = weight of output column
+  // s_x0[xi] + j in low-res column xi
+  float* s_wx = s_t + Wo * UPB_CC;
+  int* s_x0 = reinterpret_cast<int*>(s_wx + d.W * d.maxc);
+  {
+    const float rw = 1.f / d.sw;
+    for (int i = tid; i < d.W * d.maxc; i += 256) {
+      const int xi = i / d.maxc, j = i - xi * d.maxc;
+      int xlo = (int)floorf((xi - 0.5f) * rw - 0.5f) - 1;
+      if (xlo < 0) xlo = 0;
+      const int x = xlo + j;
+      float wx = 0.f;
+      if (x < Wo) {
+        int x0, x1;
+        float lx;
+        bilin_src(x, d.sw, d.W, x0, x1, lx);
+        wx = (x0 == xi ? 1.f - lx : 0.f) + (x1 == xi ? lx : 0.f);
+      }
+      s_wx[i] = wx;
+      if (j == 0) s_x0[xi] = xlo;
+    }
   }
   __syncthreads();
   const int n = s_n;
@@ -228,21 +251,21 @@ __global__ void __launch_bounds__(256) upsample_bwd_multi_kernel(const bf16* __r
     o[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
   }
   __syncthreads();
-  // phase 2: dz[b, yi, xi, c0 + c] = sum_x wx * t[x][c]   (thread = channel pair of one low-res pixel)
-  const float rw = 1.f / d.sw;
+  // phase 2: dz[b, yi, xi, c0 + c] = sum_x wx * t[x][c]   (thread = channel pair of one low-res pixel; a warp shares xi,
+  // so the weight reads are shared-memory broadcasts)
   bf16* orow = d.dz + ((long)b * d.H + yi) * d.W * C + c0;
   for (int item = tid; item < d.W * (UPB_CC / 2); item += 256) {
     const int cp = item & (UPB_CC / 2 - 1), xi = item / (UPB_CC / 2);
-    int xlo = (int)floorf((xi - 0.5f) * rw - 0.5f) - 1, xhi = (int)ceilf((xi + 1.5f) * rw - 0.5f) + 1;
-    if (xlo < 0) xlo = 0;
-    if (xhi > Wo - 1) xhi = Wo - 1;
+    const int xlo = s_x0[xi];
+    int cnt = Wo - xlo;
+    if (cnt > d.maxc) cnt = d.maxc;
+    const float* wrow = s_wx + xi * d.maxc;
+    const float* trow = s_t + xlo * UPB_CC + cp * 2;
     float a0 = 0.f, a1 = 0.f;
-    for (int x = xlo; x <= xhi; x++) {
-      int x0, x1;
-      float lx;
-      bilin_src(x, d.sw, d.W, x0, x1, lx);
-      const float wx = (x0 == xi ? 1.f - lx : 0.f) + (x1 == xi ? lx : 0.f);
-      const float2 tv = *reinterpret_cast<const float2*>(s_t + x * UPB_CC + cp * 2);
+#pragma unroll 4
+    for (int j = 0; j < cnt; j++) {
+      const float wx = wrow[j];
+      const float2 tv = *reinterpret_cast<const float2*>(trow + j * UPB_CC);
       a0 = fmaf(wx, tv.x, a0);
       a1 = fmaf(wx, tv.y, a1);
     }
@@ -267,16 +290,20 @@ CMX_API int cmx_upsample_bwd_multi(const void* dout, int Ho, int Wo, void* dz1, 
     }
   UpDst d[3];
   int jobs = 0;
+  size_t tab_bytes = 0;
   for (int k = 0; k < 3; k++) {
     if (k < nd) {
-      d[k] = UpDst{(bf16*)dz[k], Hs[k], Ws[k], (float)Hs[k] / (float)Ho, (float)Ws[k] / (float)Wo, cdiv(Hs[k], bands)};
+      d[k] = UpDst{(bf16*)dz[k], Hs[k], Ws[k], (float)Hs[k] / (float)Ho, (float)Ws[k] / (float)Wo, cdiv(Hs[k], bands),
+                   2 * cdiv(Wo, Ws[k]) + 4};
       jobs += d[k].rows_per_band;
+      const size_t tab = (size_t)Ws[k] * (d[k].maxc + 1) * sizeof(float);
+      if (tab > tab_bytes) tab_bytes = tab;
     } else {
-      d[k] = UpDst{nullptr, 0, 0, 1.f, 1.f, 1 << 30};
+      d[k] = UpDst{nullptr, 0, 0, 1.f, 1.f, 1 << 30, 0};
     }
   }
   const int nchunk = C / UPB_CC;
-  const size_t smem = (size_t)Wo * UPB_CC * sizeof(float);
+  const size_t smem = (size_t)Wo * UPB_CC * sizeof(float) + tab_bytes;
   CMX_REQUIRE(smem <= 200 * 1024, "upsample_bwd_multi: Wo=%d too wide", Wo);
   CMX_REQUIRE((long)B * nchunk <= 65535 && bands <= 65535, "upsample_bwd_multi: grid too large");
   if (smem > 48 * 1024) cudaFuncSetAttribute(upsample_bwd_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -1,0 +1,7 @@
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_ops_gpu.py -x -q -k "upsample" 2>&1 | tail -2
+for i in 1 2; do timeout 600 python bench.py --no-cpu-baseline --profile-out gpurun_out/kernels_58.csv 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('NEW', d['ms_per_step'], d['e2e']['ms_per_step'])"; done
+grep "upsample\|colstats\|bn_" gpurun_out/kernels_58.csv
+CMX_DECODER_FUSE_BF16=1 timeout 900 python -m pytest tests/test_model_gpu.py -x -q 2>&1 | tail -2
+for i in 1 2; do CMX_DECODER_FUSE_BF16=1 timeout 600 python bench.py --no-cpu-baseline --profile-out gpurun_out/kernels_58b.csv 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('FUSE_BF16', d['ms_per_step'], d['e2e']['ms_per_step'], d['last_loss'])"; done
+grep "upsample\|colstats\|bn_" gpurun_out/kernels_58b.csv
