@@ -73,6 +73,8 @@ class Engine:
         # weight-gradient GEMMs never feed the backward chain: they run on a companion stream of whichever stream
         # computes the data gradients and are joined at the end of each module's backward
         self.wgrad_stream = os.environ.get("CMX_WGRAD_STREAM", "1") != "0"
+        self.hp_streams = os.environ.get("CMX_HP_STREAMS", "0") == "1"
+        self._hp = None
         self._wstreams = {}
         self._wkeep = {}
         self._dec_prep = None
@@ -896,6 +898,32 @@ class Engine:
             Hc, Wc = Ho, Wo
         return feats, sizes, ctx
 
+    def hp_main(self):
+        """context manager (CMX_HP_STREAMS=1): run the enclosed step on an engine-owned HIGH-priority stream (forked from and
+        joined back into the current stream; the X-branch side stream is high priority too) so that the kernels of the
+        dependent forward/backward chains are scheduled ahead of the weight-gradient kernels of the companion streams,
+        which keep the default (lowest) priority.  Kernel-node priorities survive CUDA-graph capture."""
+        eng = self
+
+        class _HP:
+            def __enter__(self_):
+                self_.ctx = None
+                if not eng.hp_streams:
+                    return
+                if eng._hp is None or eng._hp.device != eng.dev:
+                    eng._hp = torch.cuda.Stream(device=eng.dev, priority=-1)
+                self_.cur = torch.cuda.current_stream(eng.dev)
+                eng._hp.wait_stream(self_.cur)
+                self_.ctx = torch.cuda.stream(eng._hp)
+                self_.ctx.__enter__()
+
+            def __exit__(self_, *exc):
+                if self_.ctx is not None:
+                    self_.ctx.__exit__(*exc)
+                    self_.cur.wait_stream(eng._hp)
+                return False
+        return _HP()
+
     def _fork_join(self):
         """context manager: yields a side stream that has waited for the current stream (or None when disabled);
         on exit the current stream waits for the side stream.  Works eagerly and under CUDA-graph capture."""
@@ -907,7 +935,7 @@ class Engine:
                     self_.side = None
                     return None
                 if eng._side is None or eng._side.device != eng.dev:
-                    eng._side = torch.cuda.Stream(device=eng.dev)
+                    eng._side = torch.cuda.Stream(device=eng.dev, priority=-1 if eng.hp_streams else 0)
                 self_.main = torch.cuda.current_stream(eng.dev)
                 self_.side = eng._side
                 self_.side.wait_stream(self_.main)

@@ -177,7 +177,7 @@ class EncoderDecoder(nn.Module):
             g["rgb"], g["x"] = rgb.clone(), modal_x.clone()
             graph = torch.cuda.CUDAGraph()
             torch.cuda.synchronize()
-            with torch.cuda.graph(graph):
+            with torch.cuda.graph(graph), self._eng().hp_main():
                 g["out"] = self._eng().forward_logits(g["rgb"], g["x"])
             g["graph"] = graph
         g["rgb"].copy_(rgb)
@@ -222,7 +222,7 @@ class EncoderDecoder(nn.Module):
             torch.cuda.synchronize()
             if not split:
                 graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(graph):
+                with torch.cuda.graph(graph), eng.hp_main():
                     g["loss"] = eng.forward_loss(g["rgb"], g["x"], g["label"], ign, with_grad=True, focal=focal)
                 g["graph"], g["graph2"] = graph, None
             else:

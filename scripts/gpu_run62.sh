@@ -1,0 +1,4 @@
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_ops_gpu.py tests/test_model_gpu.py -x -q 2>&1 | tail -2
+for i in 1 2; do timeout 600 python bench.py --no-cpu-baseline 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('PDL_ALL', d['ms_per_step'], d['e2e']['ms_per_step'], d['last_loss'], d['inference']['batch8']['ms_per_forward'], d['inference']['batch1']['ms_per_forward'])"; done
+for i in 1 2; do CMX_PDL_ALL=0 timeout 600 python bench.py --no-cpu-baseline 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('PDL_TC_ONLY', d['ms_per_step'], d['e2e']['ms_per_step'], d['last_loss'], d['inference']['batch8']['ms_per_forward'], d['inference']['batch1']['ms_per_forward'])"; done
