@@ -26,6 +26,8 @@ sys.path.insert(0, ROOT)
 
 H, W, NCLS, PER_GPU_BATCH = 480, 640, 9, 8
 METRIC, UNIT = "train img/s, CMX MiT-B2 RGB-T 480x640 (fwd+bwd+AdamW)", "img/s"
+WORKLOAD = ("CMX MiT-B2 RGB-T MFNet shape (480x640, 9 classes) bf16 training, batch 8 per GPU "
+            "(BASELINE.json configs[1]; configs[2] for N>1)")
 RIDGE_FLOP_PER_BYTE = 213.0  # 1396.8 TF / 6.554 TB/s (MEASURED_PEAKS.json)
 
 
@@ -159,7 +161,9 @@ def main_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
             "warmup": max(1, args.warmup), "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "CMX MiT-B2 RGB-T MFNet shape (480x640, 9 classes) training step on the host CPU, batch 1 per step"},
+            "config": {"workload": WORKLOAD,
+                       "sample": "the same training step (fwd+bwd+AdamW) on one image of the batch per step: the reference's fp32 "
+                                 "algorithm on the host CPU, all host threads (img/s does not depend on the batch size there)"},
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
@@ -402,8 +406,7 @@ def main_ours(args):
         line = {"metric": METRIC, "value": gb * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": warm, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "bf16", "data": "synthetic",
-                "config": {"workload": "CMX MiT-B2 RGB-T MFNet shape (480x640, 9 classes) bf16 training, batch 8 per GPU "
-                                       "(BASELINE.json configs[1]; configs[2] for N>1)",
+                "config": {"workload": WORKLOAD,
                            "global_batch": gb, "per_gpu_batch": B, "parallelism": "dp%d" % world, "optimizer": "FlatAdamW (AdamW, one launch)" if args.optimizer == "flat" else "torch.optim.AdamW(fused)",
                            "grad_allreduce": None if world == 1 else ("torch DDP buckets" if os.environ.get("CMX_BENCH_TORCH_DDP", "0") == "1"
                                                                       else "one NCCL all-reduce over the flat fp32 gradient buffer"),
