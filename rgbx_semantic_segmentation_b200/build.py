@@ -10,7 +10,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "build")
 LIB = os.path.join(CSRC, "libcmx_b200.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-Xcompiler", "-fPIC,-fvisibility=hidden", "--use_fast_math" if False else "-DCMX_NO_FAST_MATH"]
+              "-Xcompiler", "-fPIC,-fvisibility=hidden", "-DCMX_NO_FAST_MATH"]  # no --use_fast_math: erf/exp parity
 
 
 def _nvcc():
@@ -23,7 +23,8 @@ def _sources():
 
 def _stamp():
     h = hashlib.sha256()
-    for p in _sources() + [os.path.join(CSRC, "common.cuh"), os.path.join(HERE, "..", "include", "cmx_b200.h")]:
+    headers = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh"))
+    for p in _sources() + headers + [os.path.join(HERE, "..", "include", "cmx_b200.h")]:
         with open(p, "rb") as f:
             h.update(f.read())
     h.update(" ".join(NVCC_FLAGS).encode())

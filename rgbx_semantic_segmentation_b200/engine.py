@@ -903,7 +903,7 @@ class Engine:
         joined back into the current stream; the X-branch side stream is high priority too) so that the kernels of the
         dependent forward/backward chains are scheduled ahead of the weight-gradient kernels of the companion streams,
         which keep the default (lowest) priority.  Kernel-node priorities survive CUDA-graph capture.
-        Measured on one B200 (scripts/gpu_run63.sh): 22.75 ms/step against 21.77 with equal priorities - delaying the
+        Measured on one B200 (scripts/gpu_runs/gpu_run63.sh): 22.75 ms/step against 21.77 with equal priorities - delaying the
         weight-gradient GEMMs pushes them into the tail of each stage where nothing is left to overlap them with - so it
         stays off by default."""
         eng = self
