@@ -157,3 +157,27 @@ def test_ddp_gradient_handoff_world2_gloo(tmp_path, mode, port):
         assert line, o[-2000:]
         _, rk, ok, lt, n = line[0].split()
         assert ok == "True" and abs(float(lt) - 0.5) < 1e-6, line
+
+
+def test_sass_holds_tcgen05_and_tma_and_no_legacy_mma_outside_the_fallback():
+    """static proof (no GPU): the GEMM / attention kernels in the built library issue tcgen05.mma (UTC*MMA), read their
+    accumulators from tensor memory (LDTM) and move tiles with TMA (UTMALDG / UTMASTG); legacy mma.sync (HMMA) exists only
+    in the generic strided fallback GEMM.  Same parser as scripts/sass_summary.py -> profiles/r1_sass_resource_summary.txt."""
+    import csv
+    import shutil
+    import subprocess
+    import sys
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "scripts", "sass_summary.py")], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    rows = list(csv.DictReader(l for l in out.stdout.splitlines() if not l.startswith("#")))
+    by = {}
+    for r in rows:
+        by.setdefault(r["kernel"].split("<")[0], []).append(r)
+    for fam in ("gemm_tc_kernel", "attn_kernel"):
+        assert by[fam], fam
+        for r in by[fam]:
+            assert int(r["UTCMMA"]) > 0 and int(r["LDTM"]) > 0 and int(r["UTMALDG"]) > 0 and int(r["HMMA"]) == 0, r
+    assert [k for k, v in by.items() if any(int(r["HMMA"]) for r in v)] == ["gemm_wmma_kernel"]
