@@ -175,6 +175,17 @@ int cmx_attn_fwd(const void* q, int64_t ldq, const void* kv, int64_t ldkv, void*
 int cmx_attn_bwd(const void* d_o, int64_t lddo, const void* kv, int64_t ldkv, const void* p, int64_t ldp, void* ds_out,
                  int64_t ldds, void* dq, int64_t lddq, int B, int N, int Nk, int heads, float scale, void* stream);
 
+/* EXPERIMENTAL (round-2 work item; the engine calls it only under CMX_ATTN_DKV_RECOMPUTE=1, parity not yet run on a GPU):
+ * key-major dK / dV of the same attention with the probabilities recomputed from q, k and the forward's lse instead of
+ * read back from HBM.  delta [B*heads*N] = rowsum(dO .* O) from cmx_attn_delta; dkv_acc: zero-initialised fp32
+ * [B*Nk, lddkv] (dK at columns h*64.., dV at heads*64 + h*64.., the layout of the kv projection output), added to
+ * with fp32 RED.  Replaces the two batched split-K cmx_gemm calls dV = P^T dO and dK = dS^T Q. */
+int cmx_attn_delta(const void* d_o, int64_t lddo, const void* o, int64_t ldo, float* delta, int B, int N, int heads,
+                   void* stream);
+int cmx_attn_dkv(const void* q, int64_t ldq, const void* d_o, int64_t lddo, const void* kv, int64_t ldkv, const float* lse,
+                 const float* delta, float* dkv_acc, int64_t lddkv, int B, int N, int Nk, int heads, float scale,
+                 void* stream);
+
 /* ---- softmax ---------------------------------------------------------------------------------- */
 /* row softmax of fp32 S [rows, n] (ld) -> bf16 P  (dual_segformer.py:131) and its backward
  * dS = scale * P .* (dP - rowsum(P.*dP)) -> bf16 */

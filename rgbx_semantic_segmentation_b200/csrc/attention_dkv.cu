@@ -1,0 +1,324 @@
+// EXPERIMENTAL (round-2 work item, not on the default path; the engine only calls it under CMX_ATTN_DKV_RECOMPUTE=1):
+// key-major attention backward for dK / dV with the probabilities RECOMPUTED from Q, K and the forward's row
+// normaliser instead of being read back from HBM (dual_segformer.py:127-134, backward of softmax(scale Q K^T) V).
+//
+//   per CTA: one (sample, head), one block of 128 keys, one contiguous range of 128-query tiles
+//     S^T [128 keys x 128 queries] = K_blk Q_i^T          tcgen05.mma, TMEM columns   0..127
+//     dP^T[128 keys x 128 queries] = V_blk dO_i^T         tcgen05.mma, TMEM columns 128..255
+//     P^T  = exp2(scale*log2e * S^T - log2e * lse[q])     (rows >= Nkv and queries >= N give 0)
+//     dS^T = scale * P^T .* (dP^T - delta[q])             delta[q] = rowsum(dO .* O)  (cmx_attn_delta)
+//     dV  += P^T  dO_i   (A = P^T  from shared memory, B = the dO tile viewed MN-major)   TMEM columns 256..319
+//     dK  += dS^T Q_i    (A = dS^T from shared memory, B = the Q  tile viewed MN-major)   TMEM columns 320..383
+//   the [128 x 64] dV / dK accumulators stay in tensor memory over all query tiles of the CTA and are added to the
+//   fp32 [B*Nkv, 2C] gradient of the kv projection output at the end (fp32 RED: the query range of one (sample, head,
+//   key block) is split over several CTAs so that the high-resolution stages fill the GPU).
+//
+// It replaces the two batched split-K GEMMs dV = P^T dO and dK = dS^T Q (which re-read the stored P and dS,
+// 2 x 1.35 GB per training step at MiT-B2 480x640 batch 8).  Warp roles as in attention.cu: warp 0 TMA producer,
+// warp 1 MMA issuer, warps 2-9 (two threads per key row, 64 query columns each) exp2 / dS / bf16 staging.
+#include "tc_common.cuh"
+#include "../../include/cmx_b200.h"
+#include <atomic>
+#include <string.h>
+extern std::atomic<long long> g_cmx_launches;
+
+constexpr int DK_BK = 128;   // keys per CTA
+constexpr int DK_BQ = 128;   // queries per tile
+constexpr int DK_D = 64;     // head dim
+constexpr int DK_THREADS = 64 + 256;
+constexpr uint32_t DK_K_OFF = 0, DK_V_OFF = 16384, DK_Q_OFF = 32768, DK_DO_OFF = 65536, DK_P_OFF = 98304, DK_DS_OFF = 131072,
+                   DK_LD_OFF = 163840, DK_BAR_OFF = DK_LD_OFF + 2048;
+constexpr uint32_t DK_SMEM = DK_BAR_OFF + 256 + 1024;  // + alignment slack
+constexpr uint32_t DK_COL_S = 0, DK_COL_DP = 128, DK_COL_DV = 256, DK_COL_DK = 320;
+
+struct DkvArgs {
+  const float* lse;    // [B*heads, N] natural-log row normaliser of the forward
+  const float* delta;  // [B*heads, N] rowsum(dO .* O)
+  float* dkv;          // [B*Nk, lddkv] fp32, dK at columns h*64.., dV at heads*64 + h*64..
+  long lddkv;
+  int B, N, Nk, heads;
+  int nkb;             // key blocks per (sample, head)
+  int qsplit;          // CTAs per (sample, head, key block)
+  int tiles_per_split; // query tiles per CTA
+  int tiles;           // query tiles per (sample, head)
+  float scale_log2e, scale;
+};
+
+__global__ void __launch_bounds__(DK_THREADS, 1) attn_dkv_kernel(const __grid_constant__ CUtensorMap tmQ,
+                                                                 const __grid_constant__ CUtensorMap tmDO,
+                                                                 const __grid_constant__ CUtensorMap tmKV, DkvArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sb = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sK = sb + DK_K_OFF, sV = sb + DK_V_OFF, sQ = sb + DK_Q_OFF, sDO = sb + DK_DO_OFF, sP = sb + DK_P_OFF,
+                 sDS = sb + DK_DS_OFF, sLD = sb + DK_LD_OFF;
+  const uint32_t bar = sb + DK_BAR_OFF;
+  const uint32_t kv_full = bar, qd_full = bar + 8 /*[2]*/, qd_empty = bar + 24 /*[2]*/, s_full = bar + 40, p_full = bar + 48,
+                 pds_empty = bar + 56, acc_full = bar + 64, tmem_slot = bar + 72;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // (sample, head), key block and query-tile range of this CTA
+  const int split = (int)(blockIdx.x % (unsigned)a.qsplit);
+  const int unit = (int)(blockIdx.x / (unsigned)a.qsplit);
+  const int jb = unit % a.nkb;
+  const int bh = unit / a.nkb;
+  const int b = bh / a.heads, h = bh % a.heads;
+  const int t_begin = split * a.tiles_per_split;
+  int t_end = t_begin + a.tiles_per_split;
+  if (t_end > a.tiles) t_end = a.tiles;
+  const int ntiles = t_end > t_begin ? t_end - t_begin : 0;
+  const int C = a.heads * DK_D;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmQ)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmDO)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmKV)) : "memory");
+    mbar_init(kv_full, 1);
+    for (int i = 0; i < 2; i++) { mbar_init(qd_full + 8 * i, 1); mbar_init(qd_empty + 8 * i, 1); }
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 1);
+    mbar_init(pds_empty, 1);
+    mbar_init(acc_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    // ============================ TMA producer ============================
+    if (lane == 0 && ntiles > 0) {
+      mbar_expect_tx(kv_full, 2 * DK_BK * 128);
+      tma_load_3d(sK, &tmKV, kv_full, h * DK_D, jb * DK_BK, b);        // rows >= Nkv are zero-filled
+      tma_load_3d(sV, &tmKV, kv_full, C + h * DK_D, jb * DK_BK, b);
+      for (int i = 0; i < ntiles; i++) {
+        const int s = i & 1;
+        const int q0 = (t_begin + i) * DK_BQ;
+        mbar_wait(qd_empty + 8 * s, (((uint32_t)i >> 1) & 1u) ^ 1u);
+        mbar_expect_tx(qd_full + 8 * s, 2 * DK_BQ * 128);
+        tma_load_3d(sQ + s * 16384, &tmQ, qd_full + 8 * s, h * DK_D, q0, b);
+        tma_load_3d(sDO + s * 16384, &tmDO, qd_full + 8 * s, h * DK_D, q0, b);
+      }
+    }
+  } else if (warp == 1) {
+    // ============================ MMA issuer ============================
+    if (lane == 0 && ntiles > 0) {
+      // D fp32, A/B bf16, K-major A; B K-major for the score products, MN-major (bit 16) for the gradient products
+      constexpr uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(DK_BQ >> 3) << 17) | ((uint32_t)(DK_BK >> 4) << 24);
+      constexpr uint32_t idesc_g = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(DK_D >> 3) << 17) |
+                                   ((uint32_t)(DK_BK >> 4) << 24);
+      auto issue_scores = [&](int i) {  // S^T = K Q_i^T, dP^T = V dO_i^T
+        const uint32_t q = sQ + (i & 1) * 16384, g = sDO + (i & 1) * 16384;
+#pragma unroll
+        for (int ks = 0; ks < 4; ks++)
+          tc_mma_bf16(tmem + DK_COL_S, umma_desc(sK + ks * 32, 16, 1024), umma_desc(q + ks * 32, 16, 1024), idesc_s, ks > 0 ? 1u : 0u);
+#pragma unroll
+        for (int ks = 0; ks < 4; ks++)
+          tc_mma_bf16(tmem + DK_COL_DP, umma_desc(sV + ks * 32, 16, 1024), umma_desc(g + ks * 32, 16, 1024), idesc_s, ks > 0 ? 1u : 0u);
+        tc_commit(s_full);
+      };
+      auto issue_grads = [&](int i) {   // dV += P^T dO_i, dK += dS^T Q_i (contraction over the 128 queries of tile i)
+        const uint32_t q = sQ + (i & 1) * 16384, g = sDO + (i & 1) * 16384;
+#pragma unroll
+        for (int kb = 0; kb < 2; kb++)
+#pragma unroll
+          for (int ks = 0; ks < 4; ks++)
+            tc_mma_bf16(tmem + DK_COL_DV, umma_desc(sP + kb * 16384 + ks * 32, 16, 1024),
+                        umma_desc(g + kb * 8192 + ks * 2048, 8192, 1024), idesc_g, (i > 0 || kb > 0 || ks > 0) ? 1u : 0u);
+#pragma unroll
+        for (int kb = 0; kb < 2; kb++)
+#pragma unroll
+          for (int ks = 0; ks < 4; ks++)
+            tc_mma_bf16(tmem + DK_COL_DK, umma_desc(sDS + kb * 16384 + ks * 32, 16, 1024),
+                        umma_desc(q + kb * 8192 + ks * 2048, 8192, 1024), idesc_g, (i > 0 || kb > 0 || ks > 0) ? 1u : 0u);
+      };
+      mbar_wait(kv_full, 0);
+      for (int i = 0; i < ntiles; i++) {
+        mbar_wait(qd_full + 8 * (i & 1), ((uint32_t)i >> 1) & 1u);
+        if (i > 0) mbar_wait(p_full, (uint32_t)(i - 1) & 1u);   // S / dP of tile i-1 consumed, P^T / dS^T of tile i-1 staged
+        tc_fence_after();
+        issue_scores(i);                                        // first, so that the exp2 warps restart as early as possible
+        if (i > 0) {
+          issue_grads(i - 1);
+          tc_commit(pds_empty);                                 // P^T / dS^T staging tiles free again
+          tc_commit(qd_empty + 8 * ((i - 1) & 1));              // Q / dO ring slot free again
+        }
+      }
+      mbar_wait(p_full, (uint32_t)(ntiles - 1) & 1u);
+      tc_fence_after();
+      issue_grads(ntiles - 1);
+      tc_commit(acc_full);
+    }
+  } else if (ntiles > 0) {
+    // ============================ exp2 / dS warps (2..9) ============================
+    const int qd = warp & 3;               // TMEM lane quarter
+    const int half = (warp - 2) >> 2;      // query-column half: [0,64) or [64,128)
+    const int r = qd * 32 + lane;          // key row inside the block
+    const int ct = threadIdx.x - 64;       // 0..255
+    const uint32_t t_row = tmem + ((uint32_t)(qd * 32) << 16);
+    const bool key_ok = jb * DK_BK + r < a.Nk;
+    const float sl2 = a.scale_log2e, sc = a.scale;
+    const float* lse = a.lse + (long)bh * a.N;
+    const float* dlt = a.delta + (long)bh * a.N;
+    for (int i = 0; i < ntiles; i++) {
+      const int q0 = (t_begin + i) * DK_BQ;
+      const uint32_t buf = sLD + (uint32_t)(i & 1) * 1024u;   // double-buffered [128 x lse*log2e][128 x delta] (2 x 512 B)
+      // stage the per-query constants of this tile: +inf normaliser for queries >= N makes their probability exactly 0
+      {
+        const int qi = q0 + (ct & 127);
+        float val;
+        if (ct < 128) val = qi < a.N ? lse[qi] * 1.4426950408889634f : INFINITY;
+        else val = qi < a.N ? dlt[qi] : 0.f;
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(buf + (ct < 128 ? 0u : 512u) + 4u * (uint32_t)(ct & 127)), "f"(val) : "memory");
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      mbar_wait(s_full, (uint32_t)i & 1u);                     // S^T and dP^T of tile i are in tensor memory
+      if (i > 0) mbar_wait(pds_empty, (uint32_t)(i - 1) & 1u); // the gradient MMAs of tile i-1 have read the staging tiles
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < 2; c++) {
+        const int col0 = half * 64 + c * 32;
+        uint32_t sv[32], dv[32];
+        tmem_ld32(t_row + DK_COL_S + (uint32_t)col0, sv);
+        tmem_ld32(t_row + DK_COL_DP + (uint32_t)col0, dv);
+        tmem_wait_ld();
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
+          float l2[8], dl[8];
+#pragma unroll
+          for (int v4 = 0; v4 < 2; v4++) {
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(l2[4 * v4]), "=f"(l2[4 * v4 + 1]), "=f"(l2[4 * v4 + 2]),
+                         "=f"(l2[4 * v4 + 3]) : "r"(buf + 4u * (uint32_t)(col0 + g * 8 + 4 * v4)));
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(dl[4 * v4]), "=f"(dl[4 * v4 + 1]), "=f"(dl[4 * v4 + 2]),
+                         "=f"(dl[4 * v4 + 3]) : "r"(buf + 512u + 4u * (uint32_t)(col0 + g * 8 + 4 * v4)));
+          }
+          uint32_t pk[4], dk[4];
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            const int e = g * 8 + 2 * j;
+            const float p0 = key_ok ? exp2f(fmaf(__uint_as_float(sv[e]), sl2, -l2[2 * j])) : 0.f;
+            const float p1 = key_ok ? exp2f(fmaf(__uint_as_float(sv[e + 1]), sl2, -l2[2 * j + 1])) : 0.f;
+            const float s0 = sc * p0 * (__uint_as_float(dv[e]) - dl[2 * j]);
+            const float s1 = sc * p1 * (__uint_as_float(dv[e + 1]) - dl[2 * j + 1]);
+            __nv_bfloat162 hp = __floats2bfloat162_rn(p0, p1), hs = __floats2bfloat162_rn(s0, s1);
+            pk[j] = *reinterpret_cast<uint32_t*>(&hp);
+            dk[j] = *reinterpret_cast<uint32_t*>(&hs);
+          }
+          // K-major SWIZZLE_128B staging: 64 queries (128 B) per row and k-block, 16-byte chunk index XOR (row & 7)
+          const uint32_t ch = (uint32_t)(c * 4 + g);
+          const uint32_t off = (uint32_t)half * 16384u + (uint32_t)r * 128u + ((ch ^ ((uint32_t)r & 7u)) << 4);
+          st_shared_v4(sP + off, pk[0], pk[1], pk[2], pk[3]);
+          st_shared_v4(sDS + off, dk[0], dk[1], dk[2], dk[3]);
+        }
+      }
+      tc_fence_before();
+      fence_async_smem();
+      asm volatile("bar.sync 2, 256;" ::: "memory");   // staging tiles complete and fenced for the async proxy; TMEM reads done
+      if (ct == 0) mbar_arrive(p_full);
+    }
+    // ---- epilogue: dV / dK accumulators (TMEM) -> fp32 adds into the kv-projection gradient
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    const int key = jb * DK_BK + r;
+    float* row = a.dkv + ((long)b * a.Nk + key) * a.lddkv + h * DK_D + half * 32;
+#pragma unroll 1
+    for (int w = 0; w < 2; w++) {   // w = 0: dV (columns C + ...), w = 1: dK
+      uint32_t v[32];
+      tmem_ld32(t_row + (w == 0 ? DK_COL_DV : DK_COL_DK) + (uint32_t)(half * 32), v);
+      tmem_wait_ld();
+      if (key_ok) {
+        float* dst = row + (w == 0 ? C : 0);
+#pragma unroll
+        for (int j = 0; j < 32; j++) atomicAdd(dst + j, __uint_as_float(v[j]));
+      }
+    }
+    tc_fence_before();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+}
+
+// delta[(b*heads + h)*N + n] = sum_j dO[b,n,h*64+j] * O[b,n,h*64+j]   (one warp per token, two elements per lane and head)
+__global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* __restrict__ d_o, long lddo, const bf16* __restrict__ o, long ldo,
+                                                         float* __restrict__ delta, long rows, int N, int heads) {
+  const long row = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const long b = row / N, n = row % N;
+  const __nv_bfloat162* a = reinterpret_cast<const __nv_bfloat162*>(d_o + row * lddo);
+  const __nv_bfloat162* c = reinterpret_cast<const __nv_bfloat162*>(o + row * ldo);
+  for (int h = 0; h < heads; h++) {
+    const float2 x = __bfloat1622float2(a[h * 32 + lane]), y = __bfloat1622float2(c[h * 32 + lane]);
+    float s = fmaf(x.x, y.x, x.y * y.y);
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
+    if (lane == 0) delta[(b * heads + h) * N + n] = s;
+  }
+}
+
+CMX_API int cmx_attn_delta(const void* d_o, int64_t lddo, const void* o, int64_t ldo, float* delta, int B, int N, int heads,
+                           void* stream) {
+  CMX_REQUIRE(d_o && o && delta, "attn_delta: null operand");
+  CMX_REQUIRE(lddo % 2 == 0 && ldo % 2 == 0 && lddo >= heads * DK_D && ldo >= heads * DK_D, "attn_delta: head_dim must be 64");
+  CMX_REQUIRE(((uintptr_t)d_o & 3) == 0 && ((uintptr_t)o & 3) == 0, "attn_delta: pointers must be 4-byte aligned");
+  const long rows = (long)B * N;
+  if (rows == 0) return 0;
+  attn_delta_kernel<<<(unsigned)cdiv(rows, 8), 256, 0, (cudaStream_t)stream>>>((const bf16*)d_o, lddo, (const bf16*)o, ldo, delta, rows, N,
+                                                                               heads);
+  g_cmx_launches++;
+  CMX_CHECK_LAUNCH("attn_delta_kernel");
+  return 0;
+}
+
+CMX_API int cmx_attn_dkv(const void* q, int64_t ldq, const void* d_o, int64_t lddo, const void* kv, int64_t ldkv, const float* lse,
+                         const float* delta, float* dkv_acc, int64_t lddkv, int B, int N, int Nk, int heads, float scale,
+                         void* stream) {
+  CMX_REQUIRE(q && d_o && kv && lse && delta && dkv_acc, "attn_dkv: null operand");
+  CMX_REQUIRE(Nk >= 1, "attn_dkv: Nkv=%d", Nk);
+  CMX_REQUIRE(ldq % 8 == 0 && lddo % 8 == 0 && ldkv % 8 == 0, "attn_dkv: leading dims must be multiples of 8");
+  CMX_REQUIRE(ldq >= heads * DK_D && lddo >= heads * DK_D && ldkv >= 2 * heads * DK_D && lddkv >= 2 * heads * DK_D,
+              "attn_dkv: head_dim must be 64");
+  CMX_REQUIRE(((uintptr_t)q & 15) == 0 && ((uintptr_t)d_o & 15) == 0 && ((uintptr_t)kv & 15) == 0, "attn_dkv: pointers must be 16-byte aligned");
+  if (B == 0 || N == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  CUtensorMap tmQ, tmDO, tmKV;
+  int rc = cmx_make_map3(&tmQ, q, (uint64_t)heads * DK_D, (uint64_t)N, (uint64_t)B, (uint64_t)ldq, (uint64_t)N * ldq, DK_D, DK_BQ);
+  if (rc) return rc;
+  rc = cmx_make_map3(&tmDO, d_o, (uint64_t)heads * DK_D, (uint64_t)N, (uint64_t)B, (uint64_t)lddo, (uint64_t)N * lddo, DK_D, DK_BQ);
+  if (rc) return rc;
+  rc = cmx_make_map3(&tmKV, kv, (uint64_t)2 * heads * DK_D, (uint64_t)Nk, (uint64_t)B, (uint64_t)ldkv, (uint64_t)Nk * ldkv, DK_D, DK_BK);
+  if (rc) return rc;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  DkvArgs a;
+  a.lse = lse; a.delta = delta; a.dkv = dkv_acc; a.lddkv = lddkv;
+  a.B = B; a.N = N; a.Nk = Nk; a.heads = heads;
+  a.nkb = (int)cdiv(Nk, DK_BK);
+  a.tiles = (int)cdiv(N, DK_BQ);
+  const long units = (long)B * heads * a.nkb;
+  long qs = units >= sms ? 1 : sms / units;        // fill the GPU once; every split keeps >= 1 query tile
+  if (qs > a.tiles) qs = a.tiles;
+  a.tiles_per_split = (int)cdiv(a.tiles, qs);
+  a.qsplit = (int)cdiv(a.tiles, a.tiles_per_split);
+  a.scale_log2e = scale * 1.4426950408889634f;
+  a.scale = scale;
+  const long grid = units * a.qsplit;
+  CMX_REQUIRE(grid < (1l << 31), "attn_dkv: grid too large");
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(attn_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DK_SMEM);
+    if (e != cudaSuccess) CMX_FAIL((int)e, "cudaFuncSetAttribute(attn_dkv): %s", cudaGetErrorString(e));
+    attr_done = true;
+  }
+  attn_dkv_kernel<<<(unsigned)grid, DK_THREADS, DK_SMEM, st>>>(tmQ, tmDO, tmKV, a);
+  g_cmx_launches++;
+  CMX_CHECK_LAUNCH("attn_dkv_kernel");
+  return 0;
+}

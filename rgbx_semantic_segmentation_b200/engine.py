@@ -66,6 +66,9 @@ class Engine:
         self.stochastic = True       # DropPath / Dropout2d active in training mode
         self.trace = None            # debug hook: dict filled with fp32 copies of intermediate activations
         self.fused_attention = os.environ.get("CMX_FUSED_ATTENTION", "1") != "0"
+        # EXPERIMENTAL, off by default (round-2 work item, not yet validated on a GPU): dK / dV from the key-major kernel that
+        # recomputes the probabilities (csrc/attention_dkv.cu) instead of the two batched GEMMs over the stored P / dS
+        self.attn_dkv_recompute = os.environ.get("CMX_ATTN_DKV_RECOMPUTE", "0") == "1"
         # the RGB and X branch chains of a stage are independent until the FRM: run them on two streams (fork/join is
         # captured into the CUDA graph as two parallel branches) so the small stage-3/4 kernels overlap
         self.dual_stream = os.environ.get("CMX_DUAL_STREAM", "1") != "0"
@@ -370,7 +373,8 @@ class Engine:
         if d == 64 and Nk <= ops.ATTN_MAX_NK and self.fused_attention:
             # flash-style fused kernel: scores stay in tensor memory; P is only written (by TMA) when backward needs it
             Pm = self.E(B * heads * N, Np)[:, :Nk] if save else None
-            ops.attn_fwd(q, kv, O, B, N, Nk, heads, scale, p_out=Pm)
+            c.lse = self.E(B * heads * N, dtype=f32) if save and self.attn_dkv_recompute else None
+            ops.attn_fwd(q, kv, O, B, N, Nk, heads, scale, p_out=Pm, lse=c.lse)
         else:
             # unfused path (head_dim != 64 or Nkv > 320): S = scale * Q K^T (fp32, transient), P = softmax(S), O = P V
             S = self.E(B * heads * N, Np, dtype=f32)[:, :Nk]
@@ -447,12 +451,21 @@ class Engine:
             split = 1   # the low-resolution stages have enough (sample, head) tiles: bf16 results straight from the
             #             epilogue - no fp32 scratch, memset or cast on the backward chain
         direct = split == 1
+        recompute = getattr(c, "lse", None) is not None
+        if recompute:
+            direct = False
         dkv = self.E(B * Nk, 2 * C) if direct else None
         dkv32 = None if direct else self.Z(B * Nk, 2 * C)
         dkv_out = dkv if direct else dkv32
-        # dV = P^T dO
-        ops.gemm_raw(c.Pm, dO, dkv_out, Nk, d, N, Np, C, 2 * C, c_off=C, trans_a=True, trans_b=True, batch=bs, sA=sP,
-                     sB=(N * C, d), sC=(Nk * 2 * C, d), accumulate=not direct, split_k=split)
+        if recompute:
+            # EXPERIMENTAL: dK and dV in one key-major kernel, P recomputed from q, k and the forward's lse
+            delta = self.E(B * heads * N, dtype=f32)
+            ops.attn_delta(dO, c.O, delta, B, N, heads)
+            ops.attn_dkv(c.q, dO, c.kv, c.lse, delta, dkv32, B, N, Nk, heads, scale)
+        else:
+            # dV = P^T dO
+            ops.gemm_raw(c.Pm, dO, dkv_out, Nk, d, N, Np, C, 2 * C, c_off=C, trans_a=True, trans_b=True, batch=bs, sA=sP,
+                         sB=(N * C, d), sC=(Nk * 2 * C, d), accumulate=not direct, split_k=split)
         dq = self.E(M, C)
         dS = self.E(B * heads * N, Np)[:, :Nk]
         if d == 64 and Nk <= ops.ATTN_MAX_NK and self.fused_attention:
@@ -466,9 +479,10 @@ class Engine:
             del dP
             # dQ = dS K
             ops.gemm_raw(dS, c.kv, dq, N, d, Nk, Np, 2 * C, C, trans_b=True, batch=bs, sA=sP, sB=(Nk * 2 * C, d), sC=(N * C, d))
-        # dK = dS^T Q
-        ops.gemm_raw(dS, c.q, dkv_out, Nk, d, N, Np, C, 2 * C, trans_a=True, trans_b=True, batch=bs, sA=sP, sB=(N * C, d),
-                     sC=(Nk * 2 * C, d), accumulate=not direct, split_k=split)
+        if not recompute:
+            # dK = dS^T Q
+            ops.gemm_raw(dS, c.q, dkv_out, Nk, d, N, Np, C, 2 * C, trans_a=True, trans_b=True, batch=bs, sA=sP, sB=(N * C, d),
+                         sC=(Nk * 2 * C, d), accumulate=not direct, split_k=split)
         del dS
         if not direct:
             dkv = self.E(B * Nk, 2 * C)

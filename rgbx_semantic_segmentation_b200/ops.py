@@ -320,6 +320,27 @@ def attn_bwd(d_o, kv, p, ds, dq, B, N, Nk, heads, scale):
     return dq
 
 
+def attn_delta(d_o, o, delta, B, N, heads):
+    """EXPERIMENTAL: delta [B*heads*N] fp32 = rowsum over each head's 64 channels of dO .* O (d_o, o: bf16 [B*N, C])"""
+    _cuda(d_o, o, delta)
+    _call("cmx_attn_delta", d_o.data_ptr(), _ld(d_o), o.data_ptr(), _ld(o), delta.data_ptr(), B, N, heads, _stream(),
+          nbytes=_nb(d_o, o, delta))
+    return delta
+
+
+def attn_dkv(q, d_o, kv, lse, delta, dkv32, B, N, Nk, heads, scale):
+    """EXPERIMENTAL: key-major dK / dV with recomputed probabilities, added into the zero-initialised fp32 dkv32 [B*Nk, 2C]
+    (q, d_o: bf16 [B*N, C]; kv: bf16 [B*Nk, 2C]; lse, delta: fp32 [B*heads*N])"""
+    _cuda(q, d_o, kv, lse, delta, dkv32)
+    if dkv32.dtype != torch.float32 or lse.dtype != torch.float32 or delta.dtype != torch.float32:
+        raise TypeError("attn_dkv: lse, delta and dkv32 must be fp32")
+    nkb = (Nk + 127) // 128
+    _call("cmx_attn_dkv", q.data_ptr(), _ld(q), d_o.data_ptr(), _ld(d_o), kv.data_ptr(), _ld(kv), lse.data_ptr(), delta.data_ptr(),
+          dkv32.data_ptr(), _ld(dkv32), B, N, Nk, heads, scale, _stream(),
+          flops=8 * B * heads * N * nkb * 128 * 64, nbytes=nkb * _nb(q, d_o) + _nb(kv, dkv32, lse, delta))
+    return dkv32
+
+
 # ------------------------------------------------------------------------------------------------
 # softmax
 # ------------------------------------------------------------------------------------------------

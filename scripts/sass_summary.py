@@ -1,7 +1,7 @@
 """Static evidence, no GPU needed: for every kernel in csrc/libcmx_b200.so list registers / shared memory / spills
 (`cuobjdump -res-usage`) and how many Blackwell-native SASS instructions it holds (`cuobjdump -sass`):
 UTC*MMA = tcgen05.mma, LDTM/STTM = tcgen05.ld/st, UTMALDG/UTMASTG/UBLKCP = TMA, HMMA = legacy mma.sync (must be 0),
-LDGSTS = cp.async, ATOMS/RED/ATOMG = shared / global atomics, FFMA2 = packed fp32 FMA.
+LDGSTS = cp.async, ATOMS / REDG+ATOMG = shared / global atomics, FFMA2 = packed fp32 FMA.
 Usage: python scripts/sass_summary.py > profiles/r1_sass_resource_summary.txt"""
 import collections
 import os
@@ -11,7 +11,7 @@ import sys
 
 LIB = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "rgbx_semantic_segmentation_b200", "csrc", "libcmx_b200.so")
 PATS = [("UTCMMA", r"\bUTC[A-Z]*MMA"), ("LDTM", r"\bLDTM"), ("STTM", r"\bSTTM"), ("UTMALDG", r"\bUTMALDG"), ("UTMASTG", r"\bUTMASTG"),
-        ("UBLKCP", r"\bUBLKCP"), ("HMMA", r"\bHMMA"), ("LDGSTS", r"\bLDGSTS"), ("ATOMS", r"\bATOMS"), ("REDG", r"\b(RED|ATOMG)\b"),
+        ("UBLKCP", r"\bUBLKCP"), ("HMMA", r"\bHMMA"), ("LDGSTS", r"\bLDGSTS"), ("ATOMS", r"\bATOMS"), ("REDG", r"\b(REDG|RED|ATOMG)\b"),
         ("FFMA2", r"\bFFMA2"), ("MUFU", r"\bMUFU")]
 
 

@@ -515,3 +515,43 @@ def test_fused_attention_forward(B, N, Nk, heads):
     close(dsb[:, :Nk].reshape(B, heads, N, Nk), dS, 2e-2, 2e-3 * float(dS.abs().max()) + 1e-6, "dS")
     dq_ref = (dsb[:, :Nk].float().reshape(B, heads, N, Nk) @ kf).permute(0, 2, 1, 3).reshape(B * N, C)
     close(dq, dq_ref, 2e-2, 2e-2 * float(dq_ref.abs().max()) + 1e-6, "dQ")
+
+
+# ---------------------------------------------------------------------------------------------
+# EXPERIMENTAL kernels (round-2 work items that have not been run on a GPU yet): selected with CMX_EXPERIMENTAL=1 only,
+# so that the default `-m gpu` run measures the validated path.
+experimental = pytest.mark.skipif(__import__("os").environ.get("CMX_EXPERIMENTAL", "0") != "1",
+                                  reason="experimental kernel: set CMX_EXPERIMENTAL=1")
+
+
+@experimental
+@pytest.mark.parametrize("B,N,Nk,heads", [(1, 128, 128, 1), (1, 130, 4, 2), (1, 333, 77, 1), (2, 1200, 300, 5), (3, 300, 300, 8),
+                                          (2, 4800, 300, 2), (1, 19200, 300, 1), (1, 920, 920, 8)])
+def test_attention_dkv_recompute(B, N, Nk, heads):
+    """key-major dK / dV with recomputed probabilities (cmx_attn_delta + cmx_attn_dkv) against fp32 autograd of
+    softmax(scale q k^T) v on the same bf16 inputs.  Tolerance: 2 % of the gradient's max-abs (bf16 P / dS operands)."""
+    torch.manual_seed(12)
+    d = 64
+    C = heads * d
+    scale = d ** -0.5
+    q = rnd(B * N, C, dtype=bf)
+    kv = rnd(B * Nk, 2 * C, dtype=bf)
+    dO = rnd(B * N, C, dtype=bf)
+    qf = q.float().view(B, N, heads, d).permute(0, 2, 1, 3)
+    kf = kv.float().view(B, Nk, 2, heads, d)[:, :, 0].permute(0, 2, 1, 3).contiguous().requires_grad_(True)
+    vf = kv.float().view(B, Nk, 2, heads, d)[:, :, 1].permute(0, 2, 1, 3).contiguous().requires_grad_(True)
+    s = (qf @ kf.transpose(-1, -2)) * scale
+    of = torch.softmax(s, -1) @ vf
+    dOf = dO.float().view(B, N, heads, d).permute(0, 2, 1, 3)
+    of.backward(dOf)
+    o = of.detach().permute(0, 2, 1, 3).reshape(B * N, C).to(bf)
+    lse = torch.logsumexp(s.detach(), -1).reshape(-1).contiguous()
+    delta = torch.full((B * heads * N,), 7.0, device=DEV)
+    ops.attn_delta(dO, o, delta, B, N, heads)
+    close(delta.view(B, heads, N), (dOf * o.float().view(B, N, heads, d).permute(0, 2, 1, 3)).sum(-1), 1e-4, 1e-4, "delta")
+    dkv32 = torch.zeros(B * Nk, 2 * C, device=DEV)
+    ops.attn_dkv(q, dO, kv, lse, delta, dkv32, B, N, Nk, heads, scale)
+    got = dkv32.view(B, Nk, 2, heads, d)
+    dk_ref, dv_ref = kf.grad.permute(0, 2, 1, 3), vf.grad.permute(0, 2, 1, 3)
+    close(got[:, :, 1], dv_ref, 2e-2, 2e-2 * float(dv_ref.abs().max()), "dV")
+    close(got[:, :, 0], dk_ref, 2e-2, 2e-2 * float(dk_ref.abs().max()), "dK")
