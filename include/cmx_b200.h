@@ -185,6 +185,10 @@ int cmx_attn_delta(const void* d_o, int64_t lddo, const void* o, int64_t ldo, fl
 int cmx_attn_dkv(const void* q, int64_t ldq, const void* d_o, int64_t lddo, const void* kv, int64_t ldkv, const float* lse,
                  const float* delta, float* dkv_acc, int64_t lddkv, int B, int N, int Nk, int heads, float scale,
                  void* stream);
+/* EXPERIMENTAL companion (same status): query-major dQ [B*N, lddq] (bf16) with recomputed probabilities, Nkv <= 384; with
+ * cmx_attn_dkv it makes the stored probabilities (p_out of cmx_attn_fwd) and the dS round trip of cmx_attn_bwd unnecessary. */
+int cmx_attn_dq(const void* q, int64_t ldq, const void* d_o, int64_t lddo, const void* kv, int64_t ldkv, const float* lse,
+                const float* delta, void* dq, int64_t lddq, int B, int N, int Nk, int heads, float scale, void* stream);
 
 /* ---- softmax ---------------------------------------------------------------------------------- */
 /* row softmax of fp32 S [rows, n] (ld) -> bf16 P  (dual_segformer.py:131) and its backward

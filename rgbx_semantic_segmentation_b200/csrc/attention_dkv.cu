@@ -244,6 +244,235 @@ __global__ void __launch_bounds__(DK_THREADS, 1) attn_dkv_kernel(const __grid_co
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// EXPERIMENTAL companion: query-major dQ with recomputed probabilities (no stored P, no dS round trip).
+//   persistent CTAs over 128-query tiles ordered by (sample, head); K and V of the (sample, head) stay in shared memory as
+//   up to three 128-key blocks (Nkv <= 384); per tile and key block:
+//     S  [128 q x 128 k] = Q_i K_blk^T, dP = dO_i V_blk^T            TMEM columns 0..127 / 128..255
+//     dS = scale * exp2(scale*log2e*S - log2e*lse[q]) .* (dP - delta[q])   (keys >= Nkv and queries >= N give 0) -> bf16 staging
+//     dQ += dS K_blk   (B = the K block viewed MN-major)             TMEM columns 256..319, stored as bf16 per tile
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int DQ_MAXKB = 3;
+constexpr uint32_t DQ_K_OFF = 0, DQ_V_OFF = 49152, DQ_Q_OFF = 98304, DQ_DO_OFF = 131072, DQ_DS_OFF = 163840, DQ_BAR_OFF = 196608;
+constexpr uint32_t DQ_SMEM = DQ_BAR_OFF + 256 + 1024;
+constexpr uint32_t DQ_COL_S = 0, DQ_COL_DP = 128, DQ_COL_DQ = 256;
+
+struct DqArgs {
+  const float* lse;
+  const float* delta;
+  bf16* dq;
+  long lddq;
+  int B, N, Nk, heads;
+  int nkb;
+  int tiles_per_bh;
+  long total_tiles;
+  float scale_log2e, scale;
+};
+
+__global__ void __launch_bounds__(DK_THREADS, 1) attn_dq_kernel(const __grid_constant__ CUtensorMap tmQ,
+                                                                const __grid_constant__ CUtensorMap tmDO,
+                                                                const __grid_constant__ CUtensorMap tmKV, DqArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sb = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sK = sb + DQ_K_OFF, sV = sb + DQ_V_OFF, sQ = sb + DQ_Q_OFF, sDO = sb + DQ_DO_OFF, sDS = sb + DQ_DS_OFF;
+  const uint32_t bar = sb + DQ_BAR_OFF;
+  const uint32_t kv_full = bar, kv_empty = bar + 8, qd_full = bar + 16 /*[2]*/, qd_empty = bar + 32 /*[2]*/, s_full = bar + 48,
+                 p_full = bar + 56, ds_empty = bar + 64, o_full = bar + 72, o_empty = bar + 80, tmem_slot = bar + 88;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long per = (a.total_tiles + gridDim.x - 1) / gridDim.x;
+  const long t_begin = (long)blockIdx.x * per;
+  long t_end = t_begin + per;
+  if (t_end > a.total_tiles) t_end = a.total_tiles;
+  const int ntiles = t_end > t_begin ? (int)(t_end - t_begin) : 0;
+  const int nkb = a.nkb;
+  const int C = a.heads * DK_D;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmQ)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmDO)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmKV)) : "memory");
+    mbar_init(kv_full, 1);
+    mbar_init(kv_empty, 1);
+    for (int i = 0; i < 2; i++) { mbar_init(qd_full + 8 * i, 1); mbar_init(qd_empty + 8 * i, 1); }
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 1);
+    mbar_init(ds_empty, 1);
+    mbar_init(o_full, 1);
+    mbar_init(o_empty, 8);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    // ============================ TMA producer ============================
+    if (lane == 0) {
+      int group = -1;
+      long cur_bh = -1;
+      for (int i = 0; i < ntiles; i++) {
+        const long t = t_begin + i;
+        const long bh = t / a.tiles_per_bh;
+        const int q0 = (int)(t % a.tiles_per_bh) * DK_BQ;
+        const int b = (int)(bh / a.heads), h = (int)(bh % a.heads);
+        if (bh != cur_bh) {
+          cur_bh = bh;
+          group++;
+          if (group > 0) mbar_wait(kv_empty, (uint32_t)(group - 1) & 1u);   // every MMA that read the old K / V retired
+          mbar_expect_tx(kv_full, (uint32_t)(2 * nkb) * 16384u);
+          for (int kb = 0; kb < nkb; kb++) {
+            tma_load_3d(sK + kb * 16384, &tmKV, kv_full, h * DK_D, kb * DK_BK, b);
+            tma_load_3d(sV + kb * 16384, &tmKV, kv_full, C + h * DK_D, kb * DK_BK, b);
+          }
+        }
+        const int s = i & 1;
+        mbar_wait(qd_empty + 8 * s, (((uint32_t)i >> 1) & 1u) ^ 1u);
+        mbar_expect_tx(qd_full + 8 * s, 2 * DK_BQ * 128);
+        tma_load_3d(sQ + s * 16384, &tmQ, qd_full + 8 * s, h * DK_D, q0, b);
+        tma_load_3d(sDO + s * 16384, &tmDO, qd_full + 8 * s, h * DK_D, q0, b);
+      }
+    }
+  } else if (warp == 1) {
+    // ============================ MMA issuer ============================
+    if (lane == 0 && ntiles > 0) {
+      constexpr uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(DK_BK >> 3) << 17) | ((uint32_t)(DK_BQ >> 4) << 24);
+      constexpr uint32_t idesc_g = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(DK_D >> 3) << 17) |
+                                   ((uint32_t)(DK_BQ >> 4) << 24);
+      auto tile_bh = [&](int i) { return (t_begin + i) / a.tiles_per_bh; };
+      // dQ_i += dS(i, blk) K_blk, plus the barriers that its retirement releases
+      auto issue_dq = [&](int i, int blk) {
+        if (blk == 0 && i > 0) mbar_wait(o_empty, (uint32_t)(i - 1) & 1u);   // epilogue of tile i-1 drained the accumulator
+        tc_fence_after();
+#pragma unroll
+        for (int kb = 0; kb < 2; kb++)
+#pragma unroll
+          for (int ks = 0; ks < 4; ks++)
+            tc_mma_bf16(tmem + DQ_COL_DQ, umma_desc(sDS + kb * 16384 + ks * 32, 16, 1024),
+                        umma_desc(sK + blk * 16384 + kb * 8192 + ks * 2048, 8192, 1024), idesc_g, (blk > 0 || kb > 0 || ks > 0) ? 1u : 0u);
+        tc_commit(ds_empty);
+        if (blk == nkb - 1) {
+          tc_commit(o_full);
+          tc_commit(qd_empty + 8 * (i & 1));
+          if (i + 1 == ntiles || tile_bh(i + 1) != tile_bh(i)) tc_commit(kv_empty);
+        }
+      };
+      int st = 0, group = 0, pi = 0, pblk = 0;
+      mbar_wait(kv_full, 0);
+      for (int i = 0; i < ntiles; i++) {
+        for (int blk = 0; blk < nkb; blk++) {
+          if (st > 0) {
+            mbar_wait(p_full, (uint32_t)(st - 1) & 1u);   // S / dP of the previous step consumed, its dS staged
+            issue_dq(pi, pblk);
+          }
+          if (blk == 0) {
+            if (i > 0 && tile_bh(i) != tile_bh(i - 1)) {
+              group++;
+              mbar_wait(kv_full, (uint32_t)group & 1u);
+            }
+            mbar_wait(qd_full + 8 * (i & 1), ((uint32_t)i >> 1) & 1u);
+          }
+          tc_fence_after();
+          const uint32_t q = sQ + (i & 1) * 16384, g = sDO + (i & 1) * 16384;
+#pragma unroll
+          for (int ks = 0; ks < 4; ks++)
+            tc_mma_bf16(tmem + DQ_COL_S, umma_desc(q + ks * 32, 16, 1024), umma_desc(sK + blk * 16384 + ks * 32, 16, 1024), idesc_s,
+                        ks > 0 ? 1u : 0u);
+#pragma unroll
+          for (int ks = 0; ks < 4; ks++)
+            tc_mma_bf16(tmem + DQ_COL_DP, umma_desc(g + ks * 32, 16, 1024), umma_desc(sV + blk * 16384 + ks * 32, 16, 1024), idesc_s,
+                        ks > 0 ? 1u : 0u);
+          tc_commit(s_full);
+          pi = i;
+          pblk = blk;
+          st++;
+        }
+      }
+      mbar_wait(p_full, (uint32_t)(st - 1) & 1u);
+      issue_dq(pi, pblk);
+    }
+  } else {
+    // ============================ exp2 / dS warps (2..9) + dQ epilogue ============================
+    const int qd = warp & 3;
+    const int half = (warp - 2) >> 2;      // key-column half of the block: [0,64) or [64,128)
+    const int r = qd * 32 + lane;          // query row inside the tile
+    const int ct = threadIdx.x - 64;
+    const uint32_t t_row = tmem + ((uint32_t)(qd * 32) << 16);
+    const float sl2 = a.scale_log2e, sc = a.scale;
+    int st = 0;
+    for (int i = 0; i < ntiles; i++) {
+      const long t = t_begin + i;
+      const long bh = t / a.tiles_per_bh;
+      const int q0 = (int)(t % a.tiles_per_bh) * DK_BQ;
+      const int b = (int)(bh / a.heads), h = (int)(bh % a.heads);
+      const bool q_ok = q0 + r < a.N;
+      const float l2 = q_ok ? a.lse[bh * a.N + q0 + r] * 1.4426950408889634f : INFINITY;
+      const float dl = q_ok ? a.delta[bh * a.N + q0 + r] : 0.f;
+      for (int blk = 0; blk < nkb; blk++, st++) {
+        mbar_wait(s_full, (uint32_t)st & 1u);
+        if (st > 0) mbar_wait(ds_empty, (uint32_t)(st - 1) & 1u);   // the dQ MMAs of the previous step have read the staging tile
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < 2; c++) {
+          const int col0 = half * 64 + c * 32;
+          const int key0 = blk * DK_BK + col0;
+          uint32_t sv[32], dv[32];
+          tmem_ld32(t_row + DQ_COL_S + (uint32_t)col0, sv);
+          tmem_ld32(t_row + DQ_COL_DP + (uint32_t)col0, dv);
+          tmem_wait_ld();
+#pragma unroll
+          for (int g = 0; g < 4; g++) {
+            uint32_t dk[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+              const int e = g * 8 + 2 * j;
+              const float p0 = key0 + e < a.Nk ? exp2f(fmaf(__uint_as_float(sv[e]), sl2, -l2)) : 0.f;
+              const float p1 = key0 + e + 1 < a.Nk ? exp2f(fmaf(__uint_as_float(sv[e + 1]), sl2, -l2)) : 0.f;
+              __nv_bfloat162 hs = __floats2bfloat162_rn(sc * p0 * (__uint_as_float(dv[e]) - dl), sc * p1 * (__uint_as_float(dv[e + 1]) - dl));
+              dk[j] = *reinterpret_cast<uint32_t*>(&hs);
+            }
+            const uint32_t ch = (uint32_t)(c * 4 + g);
+            st_shared_v4(sDS + (uint32_t)half * 16384u + (uint32_t)r * 128u + ((ch ^ ((uint32_t)r & 7u)) << 4), dk[0], dk[1], dk[2], dk[3]);
+          }
+        }
+        tc_fence_before();
+        fence_async_smem();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (ct == 0) mbar_arrive(p_full);
+      }
+      // ---- epilogue: dQ tile TMEM -> bf16 -> global; each thread of the pair takes 32 of the 64 columns
+      mbar_wait(o_full, (uint32_t)i & 1u);
+      tc_fence_after();
+      {
+        uint32_t v[32];
+        tmem_ld32(t_row + DQ_COL_DQ + (uint32_t)(half * 32), v);
+        tmem_wait_ld();
+        if (q_ok) {
+          bf16* dst = a.dq + ((long)b * a.N + q0 + r) * a.lddq + h * DK_D + half * 32;
+#pragma unroll
+          for (int g = 0; g < 4; g++) {
+            float f[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) f[j] = __uint_as_float(v[g * 8 + j]);
+            store8(dst + g * 8, f);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(o_empty);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+}
+
 // delta[(b*heads + h)*N + n] = sum_j dO[b,n,h*64+j] * O[b,n,h*64+j]   (one warp per token, two elements per lane and head)
 __global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* __restrict__ d_o, long lddo, const bf16* __restrict__ o, long ldo,
                                                          float* __restrict__ delta, long rows, int N, int heads) {
@@ -320,5 +549,46 @@ CMX_API int cmx_attn_dkv(const void* q, int64_t ldq, const void* d_o, int64_t ld
   attn_dkv_kernel<<<(unsigned)grid, DK_THREADS, DK_SMEM, st>>>(tmQ, tmDO, tmKV, a);
   g_cmx_launches++;
   CMX_CHECK_LAUNCH("attn_dkv_kernel");
+  return 0;
+}
+
+CMX_API int cmx_attn_dq(const void* q, int64_t ldq, const void* d_o, int64_t lddo, const void* kv, int64_t ldkv, const float* lse,
+                        const float* delta, void* dq, int64_t lddq, int B, int N, int Nk, int heads, float scale, void* stream) {
+  CMX_REQUIRE(q && d_o && kv && lse && delta && dq, "attn_dq: null operand");
+  CMX_REQUIRE(Nk >= 1 && Nk <= DQ_MAXKB * DK_BK, "attn_dq: Nkv=%d unsupported (max %d) - use the unfused path", Nk, DQ_MAXKB * DK_BK);
+  CMX_REQUIRE(ldq % 8 == 0 && lddo % 8 == 0 && ldkv % 8 == 0 && lddq % 8 == 0, "attn_dq: leading dims must be multiples of 8");
+  CMX_REQUIRE(ldq >= heads * DK_D && lddo >= heads * DK_D && ldkv >= 2 * heads * DK_D && lddq >= heads * DK_D, "attn_dq: head_dim must be 64");
+  CMX_REQUIRE(((uintptr_t)q & 15) == 0 && ((uintptr_t)d_o & 15) == 0 && ((uintptr_t)kv & 15) == 0 && ((uintptr_t)dq & 15) == 0,
+              "attn_dq: pointers must be 16-byte aligned");
+  if (B == 0 || N == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  CUtensorMap tmQ, tmDO, tmKV;
+  int rc = cmx_make_map3(&tmQ, q, (uint64_t)heads * DK_D, (uint64_t)N, (uint64_t)B, (uint64_t)ldq, (uint64_t)N * ldq, DK_D, DK_BQ);
+  if (rc) return rc;
+  rc = cmx_make_map3(&tmDO, d_o, (uint64_t)heads * DK_D, (uint64_t)N, (uint64_t)B, (uint64_t)lddo, (uint64_t)N * lddo, DK_D, DK_BQ);
+  if (rc) return rc;
+  rc = cmx_make_map3(&tmKV, kv, (uint64_t)2 * heads * DK_D, (uint64_t)Nk, (uint64_t)B, (uint64_t)ldkv, (uint64_t)Nk * ldkv, DK_D, DK_BK);
+  if (rc) return rc;
+  DqArgs a;
+  a.lse = lse; a.delta = delta; a.dq = (bf16*)dq; a.lddq = lddq;
+  a.B = B; a.N = N; a.Nk = Nk; a.heads = heads;
+  a.nkb = (int)cdiv(Nk, DK_BK);
+  a.tiles_per_bh = (int)cdiv(N, DK_BQ);
+  a.total_tiles = (long)a.tiles_per_bh * B * heads;
+  a.scale_log2e = scale * 1.4426950408889634f;
+  a.scale = scale;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(attn_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DQ_SMEM);
+    if (e != cudaSuccess) CMX_FAIL((int)e, "cudaFuncSetAttribute(attn_dq): %s", cudaGetErrorString(e));
+    attr_done = true;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const long grid = a.total_tiles < sms ? a.total_tiles : sms;
+  attn_dq_kernel<<<(unsigned)grid, DK_THREADS, DQ_SMEM, st>>>(tmQ, tmDO, tmKV, a);
+  g_cmx_launches++;
+  CMX_CHECK_LAUNCH("attn_dq_kernel");
   return 0;
 }

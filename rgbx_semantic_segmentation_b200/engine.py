@@ -66,8 +66,9 @@ class Engine:
         self.stochastic = True       # DropPath / Dropout2d active in training mode
         self.trace = None            # debug hook: dict filled with fp32 copies of intermediate activations
         self.fused_attention = os.environ.get("CMX_FUSED_ATTENTION", "1") != "0"
-        # EXPERIMENTAL, off by default (round-2 work item, not yet validated on a GPU): dK / dV from the key-major kernel that
-        # recomputes the probabilities (csrc/attention_dkv.cu) instead of the two batched GEMMs over the stored P / dS
+        # EXPERIMENTAL, off by default (round-2 work item, not yet validated on a GPU): flash-style attention backward - dQ and
+        # dK / dV from the two kernels of csrc/attention_dkv.cu that recompute the probabilities from q, k and the forward's
+        # lse; the forward then stores no probabilities and the backward has no dS round trip
         self.attn_dkv_recompute = os.environ.get("CMX_ATTN_DKV_RECOMPUTE", "0") == "1"
         # the RGB and X branch chains of a stage are independent until the FRM: run them on two streams (fork/join is
         # captured into the CUDA graph as two parallel branches) so the small stage-3/4 kernels overlap
@@ -372,8 +373,9 @@ class Engine:
         O = self.E(M, C)
         if d == 64 and Nk <= ops.ATTN_MAX_NK and self.fused_attention:
             # flash-style fused kernel: scores stay in tensor memory; P is only written (by TMA) when backward needs it
-            Pm = self.E(B * heads * N, Np)[:, :Nk] if save else None
             c.lse = self.E(B * heads * N, dtype=f32) if save and self.attn_dkv_recompute else None
+            # the probabilities are only stored when the (default) backward reads them back
+            Pm = self.E(B * heads * N, Np)[:, :Nk] if save and c.lse is None else None
             ops.attn_fwd(q, kv, O, B, N, Nk, heads, scale, p_out=Pm, lse=c.lse)
         else:
             # unfused path (head_dim != 64 or Nkv > 320): S = scale * Q K^T (fp32, transient), P = softmax(S), O = P V
@@ -467,8 +469,10 @@ class Engine:
             ops.gemm_raw(c.Pm, dO, dkv_out, Nk, d, N, Np, C, 2 * C, c_off=C, trans_a=True, trans_b=True, batch=bs, sA=sP,
                          sB=(N * C, d), sC=(Nk * 2 * C, d), accumulate=not direct, split_k=split)
         dq = self.E(M, C)
-        dS = self.E(B * heads * N, Np)[:, :Nk]
-        if d == 64 and Nk <= ops.ATTN_MAX_NK and self.fused_attention:
+        dS = None if recompute else self.E(B * heads * N, Np)[:, :Nk]
+        if recompute:
+            ops.attn_dq(c.q, dO, c.kv, c.lse, delta, dq, B, N, Nk, heads, scale)
+        elif d == 64 and Nk <= ops.ATTN_MAX_NK and self.fused_attention:
             # fused: dP = dO V^T stays in tensor memory, dS in place of the TMA-loaded P tile, dQ = dS K
             ops.attn_bwd(dO, c.kv, c.Pm, dS, dq, B, N, Nk, heads, scale)
         else:

@@ -341,6 +341,18 @@ def attn_dkv(q, d_o, kv, lse, delta, dkv32, B, N, Nk, heads, scale):
     return dkv32
 
 
+def attn_dq(q, d_o, kv, lse, delta, dq, B, N, Nk, heads, scale):
+    """EXPERIMENTAL: query-major dQ (bf16 [B*N, C]) with recomputed probabilities (Nk <= 384)"""
+    _cuda(q, d_o, kv, lse, delta, dq)
+    if lse.dtype != torch.float32 or delta.dtype != torch.float32:
+        raise TypeError("attn_dq: lse and delta must be fp32")
+    nkb = (Nk + 127) // 128
+    _call("cmx_attn_dq", q.data_ptr(), _ld(q), d_o.data_ptr(), _ld(d_o), kv.data_ptr(), _ld(kv), lse.data_ptr(), delta.data_ptr(),
+          dq.data_ptr(), _ld(dq), B, N, Nk, heads, scale, _stream(),
+          flops=6 * B * heads * N * nkb * 128 * 64, nbytes=_nb(q, d_o, kv, dq, lse, delta))
+    return dq
+
+
 # ------------------------------------------------------------------------------------------------
 # softmax
 # ------------------------------------------------------------------------------------------------

@@ -528,7 +528,7 @@ experimental = pytest.mark.skipif(__import__("os").environ.get("CMX_EXPERIMENTAL
 @pytest.mark.parametrize("B,N,Nk,heads", [(1, 128, 128, 1), (1, 130, 4, 2), (1, 333, 77, 1), (2, 1200, 300, 5), (3, 300, 300, 8),
                                           (2, 4800, 300, 2), (1, 19200, 300, 1), (1, 920, 920, 8)])
 def test_attention_dkv_recompute(B, N, Nk, heads):
-    """key-major dK / dV with recomputed probabilities (cmx_attn_delta + cmx_attn_dkv) against fp32 autograd of
+    """key-major dK / dV and query-major dQ with recomputed probabilities (cmx_attn_delta + cmx_attn_dkv + cmx_attn_dq) against fp32 autograd of
     softmax(scale q k^T) v on the same bf16 inputs.  Tolerance: 2 % of the gradient's max-abs (bf16 P / dS operands)."""
     torch.manual_seed(12)
     d = 64
@@ -537,7 +537,7 @@ def test_attention_dkv_recompute(B, N, Nk, heads):
     q = rnd(B * N, C, dtype=bf)
     kv = rnd(B * Nk, 2 * C, dtype=bf)
     dO = rnd(B * N, C, dtype=bf)
-    qf = q.float().view(B, N, heads, d).permute(0, 2, 1, 3)
+    qf = q.float().view(B, N, heads, d).permute(0, 2, 1, 3).contiguous().requires_grad_(True)
     kf = kv.float().view(B, Nk, 2, heads, d)[:, :, 0].permute(0, 2, 1, 3).contiguous().requires_grad_(True)
     vf = kv.float().view(B, Nk, 2, heads, d)[:, :, 1].permute(0, 2, 1, 3).contiguous().requires_grad_(True)
     s = (qf @ kf.transpose(-1, -2)) * scale
@@ -555,3 +555,8 @@ def test_attention_dkv_recompute(B, N, Nk, heads):
     dk_ref, dv_ref = kf.grad.permute(0, 2, 1, 3), vf.grad.permute(0, 2, 1, 3)
     close(got[:, :, 1], dv_ref, 2e-2, 2e-2 * float(dv_ref.abs().max()), "dV")
     close(got[:, :, 0], dk_ref, 2e-2, 2e-2 * float(dk_ref.abs().max()), "dK")
+    if Nk <= 384:   # the query-major companion keeps K / V of one (sample, head) in shared memory
+        dq = torch.full((B * N, C), 9.0, device=DEV, dtype=bf)
+        ops.attn_dq(q, dO, kv, lse, delta, dq, B, N, Nk, heads, scale)
+        dq_ref = qf.grad.permute(0, 2, 1, 3).reshape(B * N, C)
+        close(dq, dq_ref, 2e-2, 2e-2 * float(dq_ref.abs().max()), "dQ")
