@@ -526,7 +526,8 @@ experimental = pytest.mark.skipif(__import__("os").environ.get("CMX_EXPERIMENTAL
 
 @experimental
 @pytest.mark.parametrize("B,N,Nk,heads", [(1, 128, 128, 1), (1, 130, 4, 2), (1, 333, 77, 1), (2, 1200, 300, 5), (3, 300, 300, 8),
-                                          (2, 4800, 300, 2), (1, 19200, 300, 1), (1, 920, 920, 8)])
+                                          (2, 4800, 300, 2), (1, 19200, 300, 1), (1, 920, 920, 8),
+                                          (5, 640, 300, 8)])   # last: 200 tiles on 148 CTAs => (sample, head) changes inside a CTA
 def test_attention_dkv_recompute(B, N, Nk, heads):
     """key-major dK / dV and query-major dQ with recomputed probabilities (cmx_attn_delta + cmx_attn_dkv + cmx_attn_dq) against fp32 autograd of
     softmax(scale q k^T) v on the same bf16 inputs.  Tolerance: 2 % of the gradient's max-abs (bf16 P / dS operands)."""
