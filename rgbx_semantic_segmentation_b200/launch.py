@@ -19,6 +19,7 @@ import os
 import signal
 import subprocess
 import sys
+import threading
 import time
 
 
@@ -49,7 +50,9 @@ def launch(script, script_args=(), nproc=1, port=29500, python=None, poll_s=0.2,
                 if p.poll() is None:
                     p.send_signal(sig)
 
-        old = {s: signal.signal(s, forward) for s in (signal.SIGINT, signal.SIGTERM)}
+        # signal handlers can only be installed from the main thread; elsewhere the ranks are still stopped by the finally below
+        main = threading.current_thread() is threading.main_thread()
+        old = {s: signal.signal(s, forward) for s in (signal.SIGINT, signal.SIGTERM)} if main else {}
         try:
             rc = 0
             alive = set(range(nproc))
