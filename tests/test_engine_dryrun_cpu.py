@@ -142,3 +142,25 @@ def test_autograd_handoff_through_the_module_call(mock_lib, monkeypatch):
     with torch.no_grad():
         out = m(rgb, x)
     assert tuple(out.shape) == (2, 9, 64, 96) and mock_lib["cmx_layernorm_bwd"] == 0
+
+
+@pytest.mark.parametrize("recompute", ["0", "1"])
+@pytest.mark.parametrize("backbone,H,W,fused", [("mit_b0", 72, 104, False),    # head_dim 32: unfused attention, odd sizes
+                                                 ("mit_b1", 608, 608, False)])  # Nkv = 361 > 320 in every stage: unfused
+def test_unfused_attention_shapes_ignore_the_experimental_flag(mock_lib, monkeypatch, recompute, backbone, H, W, fused):
+    monkeypatch.setenv("CMX_ATTN_DKV_RECOMPUTE", recompute)
+
+    class Cfg(_Cfg):
+        pass
+    Cfg.backbone = backbone
+    torch.manual_seed(0)
+    m = EncoderDecoder(cfg=Cfg, criterion=nn.CrossEntropyLoss(reduction='mean', ignore_index=255), norm_layer=nn.BatchNorm2d)
+    m.train()
+    rgb = torch.randn(1, 3, H, W).as_subclass(_ReportsCuda)
+    x = torch.randn(1, 3, H, W).as_subclass(_ReportsCuda)
+    lab = torch.randint(0, 9, (1, H, W))
+    loss = m._eng().forward_loss(rgb, x, lab, 255, with_grad=True, focal=None)
+    assert loss.numel() == 1
+    n_attn = 2 * sum(m.backbone.depths)
+    assert mock_lib["cmx_attn_fwd"] == 0 and mock_lib["cmx_attn_dkv"] == 0 and mock_lib["cmx_attn_dq"] == 0
+    assert mock_lib["cmx_softmax_rows_fwd"] == mock_lib["cmx_softmax_rows_bwd"] == n_attn
