@@ -175,7 +175,8 @@ int cmx_attn_fwd(const void* q, int64_t ldq, const void* kv, int64_t ldkv, void*
 int cmx_attn_bwd(const void* d_o, int64_t lddo, const void* kv, int64_t ldkv, const void* p, int64_t ldp, void* ds_out,
                  int64_t ldds, void* dq, int64_t lddq, int B, int N, int Nk, int heads, float scale, void* stream);
 
-/* EXPERIMENTAL (round-2 work item; the engine calls it only under CMX_ATTN_DKV_RECOMPUTE=1, parity not yet run on a GPU):
+/* EXPERIMENTAL (kernel-level parity green on B200, 9 shapes; the engine calls it only under CMX_ATTN_DKV_RECOMPUTE=1 until the
+ * model-level tests and the bench A/B under that flag have run):
  * key-major dK / dV of the same attention with the probabilities recomputed from q, k and the forward's lse instead of
  * read back from HBM.  delta [B*heads*N] = rowsum(dO .* O) from cmx_attn_delta; dkv_acc: zero-initialised fp32
  * [B*Nk, lddkv] (dK at columns h*64.., dV at heads*64 + h*64.., the layout of the kv projection output), added to

@@ -1,4 +1,5 @@
-// EXPERIMENTAL (round-2 work item, not on the default path; the engine only calls it under CMX_ATTN_DKV_RECOMPUTE=1):
+// EXPERIMENTAL (kernel-level parity green on B200: tests/test_ops_gpu.py::test_attention_dkv_recompute, 9 shapes; not on the default
+// path yet - the engine only calls it under CMX_ATTN_DKV_RECOMPUTE=1 until the model-level tests and the bench A/B have run):
 // key-major attention backward for dK / dV with the probabilities RECOMPUTED from Q, K and the forward's row
 // normaliser instead of being read back from HBM (dual_segformer.py:127-134, backward of softmax(scale Q K^T) V).
 //

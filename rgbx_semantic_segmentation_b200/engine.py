@@ -66,7 +66,8 @@ class Engine:
         self.stochastic = True       # DropPath / Dropout2d active in training mode
         self.trace = None            # debug hook: dict filled with fp32 copies of intermediate activations
         self.fused_attention = os.environ.get("CMX_FUSED_ATTENTION", "1") != "0"
-        # EXPERIMENTAL, off by default (round-2 work item, not yet validated on a GPU): flash-style attention backward - dQ and
+        # EXPERIMENTAL, off by default (kernel-level parity is green on B200; model-level tests and the bench A/B under this flag are
+        # still to be run): flash-style attention backward - dQ and
         # dK / dV from the two kernels of csrc/attention_dkv.cu that recompute the probabilities from q, k and the forward's
         # lse; the forward then stores no probabilities and the backward has no dS round trip
         self.attn_dkv_recompute = os.environ.get("CMX_ATTN_DKV_RECOMPUTE", "0") == "1"

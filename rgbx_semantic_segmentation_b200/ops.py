@@ -321,7 +321,7 @@ def attn_bwd(d_o, kv, p, ds, dq, B, N, Nk, heads, scale):
 
 
 def attn_delta(d_o, o, delta, B, N, heads):
-    """EXPERIMENTAL: delta [B*heads*N] fp32 = rowsum over each head's 64 channels of dO .* O (d_o, o: bf16 [B*N, C])"""
+    """(engine: CMX_ATTN_DKV_RECOMPUTE=1 only) delta [B*heads*N] fp32 = rowsum over each head's 64 channels of dO .* O (d_o, o: bf16 [B*N, C])"""
     _cuda(d_o, o, delta)
     _call("cmx_attn_delta", d_o.data_ptr(), _ld(d_o), o.data_ptr(), _ld(o), delta.data_ptr(), B, N, heads, _stream(),
           nbytes=_nb(d_o, o, delta))
@@ -329,7 +329,7 @@ def attn_delta(d_o, o, delta, B, N, heads):
 
 
 def attn_dkv(q, d_o, kv, lse, delta, dkv32, B, N, Nk, heads, scale):
-    """EXPERIMENTAL: key-major dK / dV with recomputed probabilities, added into the zero-initialised fp32 dkv32 [B*Nk, 2C]
+    """(engine: CMX_ATTN_DKV_RECOMPUTE=1 only) key-major dK / dV with recomputed probabilities, added into the zero-initialised fp32 dkv32 [B*Nk, 2C]
     (q, d_o: bf16 [B*N, C]; kv: bf16 [B*Nk, 2C]; lse, delta: fp32 [B*heads*N])"""
     _cuda(q, d_o, kv, lse, delta, dkv32)
     if dkv32.dtype != torch.float32 or lse.dtype != torch.float32 or delta.dtype != torch.float32:
@@ -342,7 +342,7 @@ def attn_dkv(q, d_o, kv, lse, delta, dkv32, B, N, Nk, heads, scale):
 
 
 def attn_dq(q, d_o, kv, lse, delta, dq, B, N, Nk, heads, scale):
-    """EXPERIMENTAL: query-major dQ (bf16 [B*N, C]) with recomputed probabilities (Nk <= 384)"""
+    """(engine: CMX_ATTN_DKV_RECOMPUTE=1 only) query-major dQ (bf16 [B*N, C]) with recomputed probabilities (Nk <= 384)"""
     _cuda(q, d_o, kv, lse, delta, dq)
     if lse.dtype != torch.float32 or delta.dtype != torch.float32:
         raise TypeError("attn_dq: lse and delta must be fp32")

@@ -1,10 +1,11 @@
 #!/bin/bash
-# Round-2 first GPU call: validate the experimental flash-style attention backward (csrc/attention_dkv.cu) and A/B it.
+# Round-2 first GPU call: model-level validation and A/B of the flash-style attention backward (csrc/attention_dkv.cu;
+# its kernel-level parity test already passed on B200 in round 1).
 #   gpurun --timeout 1500 -- 'bash scripts/gpu_runs/r2_first_call.sh'
 # Every step has its own timeout (the mbarrier watchdog turns protocol bugs into traps, not hangs).
 mkdir -p gpurun_out
 set -x
-CMX_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_ops_gpu.py -q -k dkv_recompute > gpurun_out/r2_dkv_ops.log 2>&1
+timeout 300 python -m pytest tests/test_ops_gpu.py -q -k dkv_recompute > gpurun_out/r2_dkv_ops.log 2>&1
 rc=$?
 tail -15 gpurun_out/r2_dkv_ops.log
 if [ $rc -ne 0 ]; then echo "experimental kernels failed parity (rc=$rc): not benchmarking the flagged path"; exit 0; fi
