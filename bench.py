@@ -24,10 +24,22 @@ import torch.nn as nn
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+CONFIGS = {
+    # BASELINE.json configs[1] (N = 1) / configs[2] (N > 1): the configuration the headline metric is quoted on
+    "b2_mfnet": dict(backbone="mit_b2", H=480, W=640, ncls=9, batch=8,
+                     metric="train img/s, CMX MiT-B2 RGB-T 480x640 (fwd+bwd+AdamW)",
+                     workload="CMX MiT-B2 RGB-T MFNet shape (480x640, 9 classes) bf16 training, batch 8 per GPU "
+                              "(BASELINE.json configs[1]; configs[2] for N>1)"),
+    # BASELINE.json configs[3]: MiT-B4 at the PST900 native shape (the reference builder's b4 channel bug fixed, App. A-1)
+    "b4_pst900": dict(backbone="mit_b4", H=720, W=1280, ncls=5, batch=4,
+                      metric="train img/s, CMX MiT-B4 RGB-T 720x1280 (fwd+bwd+AdamW)",
+                      workload="CMX MiT-B4 RGB-T PST900 shape (720x1280, 5 classes) bf16 training, batch 4 per GPU "
+                               "(BASELINE.json configs[3])"),
+}
 H, W, NCLS, PER_GPU_BATCH = 480, 640, 9, 8
-METRIC, UNIT = "train img/s, CMX MiT-B2 RGB-T 480x640 (fwd+bwd+AdamW)", "img/s"
-WORKLOAD = ("CMX MiT-B2 RGB-T MFNet shape (480x640, 9 classes) bf16 training, batch 8 per GPU "
-            "(BASELINE.json configs[1]; configs[2] for N>1)")
+BACKBONE = "mit_b2"
+METRIC, UNIT = CONFIGS["b2_mfnet"]["metric"], "img/s"
+WORKLOAD = CONFIGS["b2_mfnet"]["workload"]
 RIDGE_FLOP_PER_BYTE = 213.0  # 1396.8 TF / 6.554 TB/s (MEASURED_PEAKS.json)
 
 
@@ -41,6 +53,14 @@ class Cfg:
     bn_momentum = 0.1
     feature_rectify_module = "FRM"
     feature_fusion_module = "FFM"
+
+
+def select_config(name):
+    global H, W, NCLS, PER_GPU_BATCH, BACKBONE, METRIC, WORKLOAD
+    c = CONFIGS[name]
+    H, W, NCLS, PER_GPU_BATCH, BACKBONE = c["H"], c["W"], c["ncls"], c["batch"], c["backbone"]
+    METRIC, WORKLOAD = c["metric"], c["workload"]
+    Cfg.backbone, Cfg.num_classes = BACKBONE, NCLS
 
 
 def peaks():
@@ -122,34 +142,67 @@ def synth_batch(batch, seed, device=None, pin=False):
 
 # ---------------------------------------------------------------------------------------------------------
 def cpu_reference_rate(steps, warmup, threads=None):
-    """The reference's algorithm (oracle/cmx_ref.py, fp32, oneDNN/MKL) on the host cores: batch-1 fwd+bwd+AdamW."""
-    from oracle import cmx_ref
-    from oracle.synth import synth_state_dict
+    """The reference's own CPU implementation of the path on the host cores, batch-1 fwd+bwd+AdamW: the UNMODIFIED reference
+    model (baseline/_ref, `kind: "reference"`) through its public API `loss = model(rgb, modal_x, label)` (train.py:186);
+    when it is not installed, the fp32 oracle port of the same algorithm (`kind: "port"`)."""
     threads = threads or os.cpu_count() or 1
     torch.set_num_threads(threads)
-    spec = cmx_ref.MIT_SPECS["mit_b2"]
-    sd = synth_state_dict(spec, NCLS, seed=0)
-    params = {k: v.clone().requires_grad_(v.is_floating_point() and not k.endswith(("running_mean", "running_var")))
-              for k, v in sd.items()}
-    opt = torch.optim.AdamW([p for p in params.values() if p.requires_grad], lr=6e-5, weight_decay=0.01)
     rgb, x, gt = synth_batch(1, 1, device="cpu")
+    kind = "port"
+    try:
+        from baseline import ref_loader
+        if ref_loader.available():
+            kind = "reference"
+    except ImportError:
+        pass
+    if kind == "reference":
+        torch.manual_seed(0)
+        model = ref_loader.build_model(BACKBONE, NCLS, nn.CrossEntropyLoss(reduction="mean", ignore_index=255), nn.BatchNorm2d).train()
+        opt = torch.optim.AdamW(group_weight(model, 6e-5), lr=6e-5, betas=(0.9, 0.999), weight_decay=0.01)
+
+        def train_step():
+            loss = model(rgb, x, gt)
+            opt.zero_grad()
+            loss.backward()
+            opt.step()
+
+        def infer():
+            model.eval()
+            with torch.no_grad():
+                model(rgb, x)
+            model.train()
+    else:
+        from oracle import cmx_ref
+        from oracle.synth import synth_state_dict
+        spec = cmx_ref.MIT_SPECS[BACKBONE]
+        sd = synth_state_dict(spec, NCLS, seed=0)
+        params = {k: v.clone().requires_grad_(v.is_floating_point() and not k.endswith(("running_mean", "running_var")))
+                  for k, v in sd.items()}
+        opt = torch.optim.AdamW([p for p in params.values() if p.requires_grad], lr=6e-5, weight_decay=0.01)
+
+        def train_step():
+            loss = cmx_ref.forward(params, spec, rgb, x, gt, training=True, decoder_bn_eps=1e-3)
+            opt.zero_grad()
+            loss.backward()
+            opt.step()
+
+        def infer():
+            with torch.no_grad():
+                cmx_ref.forward(sd, spec, rgb, x, training=False)
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        loss = cmx_ref.forward(params, spec, rgb, x, gt, training=True, decoder_bn_eps=1e-3)
-        opt.zero_grad()
-        loss.backward()
-        opt.step()
+        train_step()
         if i >= warmup:
             times.append(time.perf_counter() - t0)
     total = sum(times)
-    with torch.no_grad():
-        t0 = time.perf_counter()
-        cmx_ref.forward(sd, spec, rgb, x, training=False)
-        t_inf = time.perf_counter() - t0
-    return {"value": len(times) / total, "unit": UNIT, "cores": threads, "kind": "port", "inference_img_s": 1.0 / t_inf,
-            "sample": "%d steps of batch 1 (fwd+bwd+AdamW, fp32 oracle port of the reference, %d threads) after %d warm-up"
-                      % (len(times), threads, warmup), "ms_per_step": 1e3 * total / len(times)}
+    t0 = time.perf_counter()
+    infer()
+    t_inf = time.perf_counter() - t0
+    what = ("the unmodified reference EncoderDecoder (baseline/_ref)" if kind == "reference" else "fp32 oracle port of the reference")
+    return {"value": len(times) / total, "unit": UNIT, "cores": threads, "kind": kind, "inference_img_s": 1.0 / t_inf,
+            "sample": "%d steps of batch 1 (fwd+bwd+AdamW, %s, fp32, %d threads) after %d warm-up"
+                      % (len(times), what, threads, warmup), "ms_per_step": 1e3 * total / len(times)}
 
 
 def main_reference(args):
@@ -186,7 +239,10 @@ def main_ours(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     torch.manual_seed(0)
-    model = EncoderDecoder(Cfg, nn.CrossEntropyLoss(reduction="mean", ignore_index=255), nn.BatchNorm2d).to(dev).train()
+    # train.py:64-67: the norm layer is nn.SyncBatchNorm whenever the run is distributed (it reaches the decoder norm only,
+    # SURVEY App. A-3): its statistics are all-reduced inside the step
+    norm_layer = nn.SyncBatchNorm if world > 1 else nn.BatchNorm2d
+    model = EncoderDecoder(Cfg, nn.CrossEntropyLoss(reduction="mean", ignore_index=255), norm_layer).to(dev).train()
     net = model
     if world > 1:
         if os.environ.get("CMX_BENCH_TORCH_DDP", "0") == "1":   # the reference's wrapper also works (slower: per-param copies)
@@ -269,10 +325,10 @@ def main_ours(args):
     # every event pair would also time the ~10 us of host work (tensor-map encoding, ctypes) between two launches.
     model.use_cuda_graph = False   # every rank takes the eager steps (DDP collectives need all ranks)
     eng = model._eng()
-    saved_streams = (eng.dual_stream, eng.wgrad_stream)
+    saved_streams = eng.wgrad_stream
     step(rgb, x, gt)
     torch.cuda.synchronize()
-    eng.dual_stream, eng.wgrad_stream = False, False
+    eng.wgrad_stream = False
     step(rgb, x, gt)
     torch.cuda.synchronize()
     n0 = ops.launch_count()
@@ -282,7 +338,7 @@ def main_ours(args):
     torch.cuda.synchronize()
     prof, ops.PROFILE = ops.PROFILE, None
     launches_per_step = ops.launch_count() - n0
-    eng.dual_stream, eng.wgrad_stream = saved_streams
+    eng.wgrad_stream = saved_streams
     model.use_cuda_graph = os.environ.get("CMX_CUDA_GRAPH", "1") != "0"
     if rank == 0:
         agg = {}
@@ -342,26 +398,51 @@ def main_ours(args):
                 for k, (t, n, fl, nb) in top:
                     f.write("%s,%d,%.3f,%.4f,%.1f,%.1f,%.2f\n" % (k, n, t, t / total, 1e3 * t / n, nb / (t * 1e-3) / 1e9 if t else 0,
                                                                  fl / (t * 1e-3) / 1e12 if t else 0))
-    # ---------------- inference (eval mode, no_grad): batch-8 throughput and batch-1 latency (evaluator.py:381-391 call shape)
-    infer = None
+    # ---------------- stock torch DistributedDataParallel around the same model (what the unchanged train.py:145 constructs)
+    ddp_stock = None
+    if world > 1 and os.environ.get("CMX_BENCH_TORCH_DDP", "0") != "1" and not args.no_ddp_compare:
+        model._flat_dp = None
+        model.__dict__.pop("_flat_pending", None)
+        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local])
+        for _ in range(4):
+            step(rgb, x, gt)
+        barrier()
+        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        nst = max(5, args.steps // 2)
+        d0.record()
+        for _ in range(nst):
+            step(rgb, x, gt)
+        d1.record()
+        barrier()
+        msd = torch.tensor([d0.elapsed_time(d1)], device=dev)
+        dist.all_reduce(msd, op=dist.ReduceOp.MAX)
+        ddp_stock = {"img_s": B * world * nst / (float(msd) * 1e-3), "ms_per_step": float(msd) / nst, "steps": nst,
+                     "note": "torch.nn.parallel.DistributedDataParallel(model) instead of FlatDataParallel: same kernels, DDP's own "
+                             "bucket copies and all-reduces after the fused step has delivered all gradients at once"}
+        net = model
+    # ---------------- inference (eval mode, no_grad) on EVERY rank: the evaluator splits the images over the devices
+    # (engine/evaluator.py:117-137), no collective; batch-8 throughput and batch-1 latency (evaluator.py:381-391 call shape)
+    infer = {}
+    model.eval()
+    with torch.no_grad():
+        for bs in (PER_GPU_BATCH, 1):
+            a_, b_ = rgb[:bs].contiguous(), x[:bs].contiguous()
+            for _ in range(10):
+                model(a_, b_)
+            barrier()
+            i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n_it = 30
+            i0.record()
+            for _ in range(n_it):
+                out = model(a_, b_)
+            i1.record()
+            barrier()
+            t_ms = torch.tensor([i0.elapsed_time(i1) / n_it], device=dev)
+            if world > 1:
+                dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+            t_ms = float(t_ms)
+            infer["batch%d" % bs] = {"img_s": world * bs / (t_ms * 1e-3), "ms_per_forward": t_ms, "n_gpus": world}
     if rank == 0:
-        model.eval()
-        infer = {}
-        with torch.no_grad():
-            for bs in (PER_GPU_BATCH, 1):
-                a_, b_ = rgb[:bs].contiguous(), x[:bs].contiguous()
-                for _ in range(10):
-                    model(a_, b_)
-                torch.cuda.synchronize()
-                i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                n_it = 30
-                i0.record()
-                for _ in range(n_it):
-                    out = model(a_, b_)
-                i1.record()
-                torch.cuda.synchronize()
-                t_ms = i0.elapsed_time(i1) / n_it
-                infer["batch%d" % bs] = {"img_s": bs / (t_ms * 1e-3), "ms_per_forward": t_ms}
         # BASELINE.json configs[4]: sliding-window multi-scale evaluation of one 480x640 image (scales 0.75/1/1.25, crop
         # 480x640, stride 2/3, no flip = 6 crops) from HOST uint8 arrays to the host prediction map + confusion matrix:
         # the reference's per-crop loop (6 batch-1 forwards) vs the batched driver (one batch-6 forward), same model
@@ -408,6 +489,7 @@ def main_ours(args):
                 "dtype": "bf16", "data": "synthetic",
                 "config": {"workload": WORKLOAD,
                            "global_batch": gb, "per_gpu_batch": B, "parallelism": "dp%d" % world, "optimizer": "FlatAdamW (AdamW, one launch)" if args.optimizer == "flat" else "torch.optim.AdamW(fused)",
+                           "norm_layer": norm_layer.__name__,
                            "grad_allreduce": None if world == 1 else ("torch DDP buckets" if os.environ.get("CMX_BENCH_TORCH_DDP", "0") == "1"
                                                                       else "one NCCL all-reduce over the flat fp32 gradient buffer"),
                            "cuda_graph": bool(model.use_cuda_graph),
@@ -416,7 +498,7 @@ def main_ours(args):
                         "h2d_bytes_per_step": int(hr.numel() * 4 + hx.numel() * 4 + hg.numel() * 8), "d2h_bytes_per_step": 4},
                 "gpu_launches": int(launches_per_step * args.steps) if launches_per_step else 0,
                 "gpu_launches_per_step": launches_per_step, "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
-                "inference": infer,
+                "inference": infer, "ddp_stock": ddp_stock,
                 "last_loss": last,
                 "top_kernels": [{"kernel": k, "launches": v[1], "ms": round(v[0], 3)} for k, v in top[:8]]}
         emit(line)
@@ -449,11 +531,15 @@ if __name__ == "__main__":
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="b2_mfnet", choices=sorted(CONFIGS), help="b2_mfnet = the headline configuration "
+                    "(BASELINE.json configs[1]/[2]); b4_pst900 = BASELINE.json configs[3]")
     ap.add_argument("--profile-out", default=None, help="write the per-kernel CUDA-event breakdown of one step (csv)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ddp-compare", action="store_true", help="N > 1: skip the extra timing of the stock torch DDP wrapper")
     ap.add_argument("--optimizer", default="flat", choices=["flat", "torch"],
                     help="flat: optim.FlatAdamW (one launch over the flat parameter buffer); torch: torch.optim.AdamW(fused=True)")
     a = ap.parse_args()
+    select_config(a.config)
     if a.impl == "reference":
         main_reference(a)
     else:

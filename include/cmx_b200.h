@@ -57,6 +57,9 @@ typedef struct CmxGemm {
   int32_t split_k;
   int32_t rows_per_sample;
   int32_t impl;
+  /* grouped launches (the RGB and X branches of a stage = batch1 index 0 / 1, same shapes, different weights): element
+   * strides per batch1 index of bias, residual and row_scale (0 = shared); only with batch2 == 1 */
+  int64_t sBias1, sR1, sS1;
 } CmxGemm;
 int cmx_gemm(const CmxGemm* g, void* stream);
 /* debug aid: device buffer (5*64*4 int64) receiving clock64 stamps of CTA 0's producer / MMA / epilogue roles, or NULL */
@@ -65,18 +68,24 @@ int cmx_debug_set_gemm_trace(void* buf);
 int cmx_gemm_which(const CmxGemm* g);
 
 /* ---- LayerNorm (dual_segformer.py:177-178, 123, 221-223, 382-383; net_utils.py:279-280) ------ */
+/* groups > 1 (grouped launch, the RGB and X branch of a stage at once): x, y, mean, rstd hold `groups` stacked blocks of M
+ * rows; gamma / beta of group g lie g * param_gs elements behind the given pointers (flat parameter buffer). */
 int cmx_layernorm_fwd(const void* x, int x_dtype, int64_t ldx, const float* gamma, const float* beta, float eps,
-                      void* y, int y_dtype, int64_t ldy, float* mean, float* rstd, int64_t M, int C, void* stream);
+                      void* y, int y_dtype, int64_t ldy, float* mean, float* rstd, int64_t M, int C, int groups,
+                      int64_t param_gs, void* stream);
 /* dx = dres + LN'(dy + dy2);  dx_bf = bf16(dx * scale[row / rows_per_sample]) (optional);
  * dgamma/dbeta (fp32[C]) are ACCUMULATED (atomic). dy_dtype applies to dy; dy2 is bf16; dres fp32.
  * dbias (optional, fp32[C], accumulated): column sums of the bf16 output (dx_bf if given, else dx) = bias gradient of
- * the Linear/conv layer whose output this LayerNorm normalised. */
+ * the Linear/conv layer whose output this LayerNorm normalised.
+ * groups > 1: every row tensor holds `groups` stacked blocks of M rows; gamma / dgamma / dbeta / dbias of group g lie
+ * g * param_gs elements behind the given pointers, scale g * scale_gs elements. */
 int cmx_layernorm_bwd(const void* dy, int dy_dtype, int64_t lddy, const void* dy2, int64_t lddy2,
                       const void* x, int x_dtype, int64_t ldx, const float* mean, const float* rstd,
                       const float* gamma, const float* dres, int64_t lddres,
                       void* dx, int dx_dtype, int64_t lddx, void* dx_bf, int64_t lddxbf,
                       const float* scale, int rows_per_sample,
-                      float* dgamma, float* dbeta, float* dbias, int64_t M, int C, void* stream);
+                      float* dgamma, float* dbeta, float* dbias, int64_t M, int C, int groups, int64_t param_gs,
+                      int64_t scale_gs, void* stream);
 
 /* ---- BatchNorm2d over token-major [M,C] (net_utils.py:318,321; MLPDecoder.py:52-53) ----------- */
 int cmx_colstats(const void* x, int x_dtype, int64_t ldx, double* sum, double* sumsq, int64_t M, int C, void* stream);
@@ -107,15 +116,17 @@ int cmx_bn_bwd_apply(const void* dy, int dy_dtype, int64_t lddy, const void* x, 
 
 /* ---- depthwise 3x3 (pad 1) + bias + activation on NHWC bf16 (dual_segformer.py:25-33,69-70;
  *      net_utils.py:314-315).  w: fp32 [C,9] (== Conv2d weight [C,1,3,3]).  flip: correlate with the
- *      180-degree rotated kernel (data-gradient).  */
+ *      180-degree rotated kernel (data-gradient).
+ *      groups > 1 (grouped launch): x / y / dy / du hold `groups` stacked blocks of B samples; the parameters (w, bias,
+ *      ysum, dw, db) of group g lie g * param_gs ELEMENTS behind the given pointers (flat parameter / gradient buffer). */
 int cmx_dwconv3x3_fwd(const void* x, int64_t ldx, const float* w, const float* bias, int act, int flip,
-                      void* y, int64_t ldy, float* ysum, int B, int H, int W, int C, void* stream);
+                      void* y, int64_t ldy, float* ysum, int B, int H, int W, int C, int groups, int64_t param_gs, void* stream);
 /* ysum (optional, fp32[C], accumulated): per-channel sums of the output (bias gradient of the producer layer when
  * this call computes a data gradient) */
 /* du = dy * act'(conv(x)+b) -> bf16; dW[C,9], db[C] accumulated (fp32 atomics). */
 int cmx_dwconv3x3_bwd_pre(const void* x, int64_t ldx, const float* w, const float* bias, int act,
                           const void* dy, int64_t lddy, void* du, int64_t lddu, float* dw, float* db,
-                          int B, int H, int W, int C, void* stream);
+                          int B, int H, int W, int C, int groups, int64_t param_gs, void* stream);
 
 /* ---- layout movers ---------------------------------------------------------------------------- */
 /* stage-1 OverlapPatchEmbed input: NCHW fp32 image -> bf16 im2col rows [B*Ho*Wo, kpad],
@@ -147,7 +158,8 @@ int cmx_convw_unpack_grad_multi(const CmxConvDesc* descs, int n, void* stream);
 int cmx_cast_f32_bf16(const float* x, void* y, int64_t n, void* stream);
 int cmx_cast_bf16_f32(const void* x, float* y, int64_t n, void* stream);
 /* column sums of a [M,N] matrix (bias gradients): out[n] += sum_m x[m,n] */
-int cmx_colsum(const void* x, int x_dtype, int64_t ldx, float* out, int64_t M, int N, void* stream);
+/* groups > 1: x = `groups` stacked blocks of M rows; out of group g lies g * out_gs elements behind the given pointer */
+int cmx_colsum(const void* x, int x_dtype, int64_t ldx, float* out, int64_t M, int N, int groups, int64_t out_gs, void* stream);
 /* dy *= (y > 0)   (ReLU backward, in place on bf16) */
 int cmx_relu_bwd(void* dy, int64_t lddy, const void* y, int64_t ldy, int64_t M, int N, void* stream);
 /* out = a*x + b*y elementwise on fp32 flat buffers (grad scaling) */
@@ -251,6 +263,17 @@ int cmx_ce_upsampled_fwd_bwd(const float* logits, int64_t ld, const int64_t* lab
 int cmx_ce_focal_upsampled_fwd_bwd(const float* logits, int64_t ld, const int64_t* label, int ignore_index, double* acc,
                                    float* dlogits, int B, int h, int w, int H, int W, int ncls, float w_ce, float w_focal,
                                    float gamma, float alpha, void* stream);
+/* DiceCELoss (utils/loss_opr.py:103-156; train.py:79-80): alpha * (1 - mean_{b,k} dice_bk) + (1 - alpha) * CE on the bilinearly
+ * upsampled logits, two passes over the pixels.  cmx_dice_ce_stats: acc (double[2], zeroed) += (CE sum, valid count), dstats
+ * (double[B*3*ncls], zeroed) += per (sample, class) (sum p, sum p*onehot, sum onehot) over the valid pixels.
+ * cmx_dice_ce_finalize: loss (optional) and coef (optional, float[B*2*ncls + 1]) from the sums.  cmx_dice_ce_grad: dlogits
+ * (fp32, zeroed, same layout as logits) += d loss / d logits (final scale; no further normalisation). */
+int cmx_dice_ce_stats(const float* logits, int64_t ld, const int64_t* label, int ignore_index, double* acc, double* dstats,
+                      int B, int h, int w, int H, int W, int ncls, void* stream);
+int cmx_dice_ce_finalize(const double* acc, const double* dstats, int B, int ncls, float alpha, float smooth, float* loss,
+                         float* coef, void* stream);
+int cmx_dice_ce_grad(const float* logits, int64_t ld, const int64_t* label, int ignore_index, const float* coef,
+                     float* dlogits, int B, int h, int w, int H, int W, int ncls, void* stream);
 /* loss = acc[0]/acc[1];  dlogits_out(bf16/f32) = dlogits * gscale/acc[1] */
 int cmx_ce_finalize(const double* acc, float* loss, const float* dlogits, const float* gscale,
                     void* dlogits_out, int out_dtype, int64_t n, void* stream);
@@ -261,9 +284,35 @@ int cmx_logits_upsample_nchw(const float* logits, int64_t ld, float* out, int B,
  * pred_dtype/gt_dtype: 0 = uint8, 1 = int32, 2 = int64.  */
 int cmx_confusion(const void* pred, int pred_dtype, const void* gt, int gt_dtype, int64_t n, int n_cl,
                   int64_t* hist, int64_t* stats, void* stream);
-/* fused argmax over channel of NCHW fp32 scores [ncls,H*W] (one image) + confusion; pred_out optional (uint8) */
-int cmx_argmax_confusion(const float* scores, const void* gt, int gt_dtype, int64_t npix, int n_cl,
+/* fused argmax over channel of NCHW scores [ncls,H*W] (one image; fp32, or fp64 when score_f64 != 0) + confusion;
+ * pred_out optional (uint8); gt optional (argmax only) */
+int cmx_argmax_confusion(const void* scores, int score_f64, const void* gt, int gt_dtype, int64_t npix, int n_cl,
                          uint8_t* pred_out, int64_t* hist, int64_t* stats, void* stream);
+
+/* ---- sliding-window / multi-scale evaluation driver on the device (engine/evaluator.py:306-431) -------------------------
+ * cmx_eval_pack_crop: one network input crop [out_ch, crop_h, crop_w] fp32 (CHW) cut from a uint8 HWC (ch = 3) or HW (ch = 1)
+ * image resident on the device.  Restates evaluator.py:337-360 + 398-431 + utils/transforms.py:61-75,182-187:
+ *   crop pixel (y, x) -> window pixel (y - out_top, x - out_left); outside the win_h x win_w window the output is 0.0 (the zero
+ *   padding process_image_rgbX applies AFTER normalisation); inside, the canvas pixel (s_y + ., s_x + .) of the zero-padded RAW
+ *   image (pad_top / pad_left black pixels before the image) is normalised in float64, ((v / 255) - mean[c]) / std[c], and
+ *   rounded to fp32 like the reference's astype(float32).  flip != 0 mirrors the crop horizontally (flip-TTA input). */
+int cmx_eval_pack_crop(const uint8_t* img, int rows, int cols, int ch, int pad_top, int pad_left, int s_y, int s_x,
+                       int win_h, int win_w, int out_top, int out_left, double mean0, double mean1, double mean2,
+                       double std0, double std1, double std2, int flip, float* out, int crop_h, int crop_w, void* stream);
+/* one tile of a scale's score canvas: crop index in the logits batch, canvas window [s_y, e_y) x [s_x, e_x) and the
+ * tile-internal margins (tm_top, tm_left) that process_image_rgbX added */
+typedef struct CmxEvalTile {
+  int32_t crop, s_y, s_x, e_y, e_x, tm_top, tm_left, pad_;
+} CmxEvalTile;
+/* cmx_eval_accumulate_scale: processed[ncls, ori_rows, ori_cols] (fp64) += resize_bilinear(score)[...] for ONE scale, where
+ *   score(c, y, x) = sum over the tiles t covering canvas pixel (y + m_top, x + m_left), in table order and in fp32, of
+ *   exp(logits[t.crop, c, ...] (+ logits_flip[t.crop, c, ..., mirrored] when logits_flip != NULL))   (evaluator.py:361-393)
+ *   is the rows x cols score map of the scale (canvas minus the margins) and the resize is cv2.INTER_LINEAR's sampling
+ *   (half-pixel centres, edge clamp) evaluated in fp32, horizontal then vertical (evaluator.py:318-320).
+ * logits / logits_flip: fp32 [n_crops, ncls, crop_h, crop_w] (the model's NCHW output); tiles: device table of n_tiles. */
+int cmx_eval_accumulate_scale(const float* logits, const float* logits_flip, int crop_h, int crop_w, int ncls,
+                              const CmxEvalTile* tiles, int n_tiles, int m_top, int m_left, int rows, int cols,
+                              double* processed, int ori_rows, int ori_cols, void* stream);
 
 #ifdef __cplusplus
 }

@@ -276,11 +276,8 @@ def backbone(sd: SD, spec: MitSpec, rgb: Tensor, x: Tensor, training: bool = Fal
     return outs
 
 
-def decoder_head(sd: SD, feats: Sequence[Tensor], training: bool = False, bn_eps: float = 1e-5,
-                 bn_momentum: float = 0.1, new_stats: Optional[SD] = None,
-                 dropout_scale: Optional[Tensor] = None, p: str = "decode_head") -> Tensor:
-    """models/decoders/MLPDecoder.py:59-81.  ``dropout_scale`` = Dropout2d multiplier
-    ``mask/0.9`` of shape [B, E] (None = eval / p=0)."""
+def _decoder_pre_bn(sd: SD, feats: Sequence[Tensor], p: str) -> Tensor:
+    """MLPDecoder.py:59-77: linear_c{1-4}, bilinear upsample to 1/4 resolution, concat [c4, c3, c2, c1], 1x1 linear_fuse conv"""
     c1, c2, c3, c4 = feats
     n = c4.shape[0]
     size = c1.shape[2:]
@@ -293,11 +290,25 @@ def decoder_head(sd: SD, feats: Sequence[Tensor], training: bool = False, bn_eps
     _c3 = F.interpolate(mlp(c3, "linear_c3"), size=size, mode="bilinear", align_corners=False)
     _c2 = F.interpolate(mlp(c2, "linear_c2"), size=size, mode="bilinear", align_corners=False)
     _c1 = mlp(c1, "linear_c1")
-    y = F.conv2d(torch.cat([_c4, _c3, _c2, _c1], dim=1), sd[f"{p}.linear_fuse.0.weight"], sd[f"{p}.linear_fuse.0.bias"])
-    y = F.relu(_batch_norm(sd, f"{p}.linear_fuse.1", y, training, bn_eps, bn_momentum, new_stats))
+    return F.conv2d(torch.cat([_c4, _c3, _c2, _c1], dim=1), sd[f"{p}.linear_fuse.0.weight"], sd[f"{p}.linear_fuse.0.bias"])
+
+
+def _decoder_post_bn(sd: SD, y: Tensor, dropout_scale: Optional[Tensor], p: str) -> Tensor:
+    """MLPDecoder.py:77-79: ReLU, Dropout2d multiplier, linear_pred"""
+    y = F.relu(y)
     if dropout_scale is not None:
         y = y * dropout_scale[:, :, None, None]
     return F.conv2d(y, sd[f"{p}.linear_pred.weight"], sd[f"{p}.linear_pred.bias"])
+
+
+def decoder_head(sd: SD, feats: Sequence[Tensor], training: bool = False, bn_eps: float = 1e-5,
+                 bn_momentum: float = 0.1, new_stats: Optional[SD] = None,
+                 dropout_scale: Optional[Tensor] = None, p: str = "decode_head") -> Tensor:
+    """models/decoders/MLPDecoder.py:59-81.  ``dropout_scale`` = Dropout2d multiplier
+    ``mask/0.9`` of shape [B, E] (None = eval / p=0)."""
+    y = _decoder_pre_bn(sd, feats, p)
+    y = _batch_norm(sd, f"{p}.linear_fuse.1", y, training, bn_eps, bn_momentum, new_stats)
+    return _decoder_post_bn(sd, y, dropout_scale, p)
 
 
 def encode_decode(sd: SD, spec: MitSpec, rgb: Tensor, x: Tensor, training: bool = False,
@@ -319,6 +330,33 @@ def forward(sd: SD, spec: MitSpec, rgb: Tensor, x: Tensor, label: Optional[Tenso
     if label is not None:
         return F.cross_entropy(out, label.long(), ignore_index=ignore_index, reduction="mean")
     return out
+
+
+def forward_data_parallel(sd: SD, spec: MitSpec, shards: Sequence[Tuple[Tensor, Tensor, Tensor]],
+                          sync_decoder_bn: bool = True, decoder_bn_eps: float = 1e-3, ignore_index: int = 255,
+                          new_stats: Optional[SD] = None) -> Tuple[Tensor, List[Tensor]]:
+    """What the reference's distributed training step computes (train.py:64-67, 145-146, 186-200), restated on ONE set of
+    parameters: every rank runs the model on its own shard (rgb, x, label) - so the FFM BatchNorms, which are always plain
+    nn.BatchNorm2d, use per-rank statistics -, the decoder norm is an nn.SyncBatchNorm whose statistics
+    are taken over the shards of all ranks (equal per-rank counts), every rank's loss is the mean CE over ITS valid pixels,
+    and DistributedDataParallel averages the per-rank gradients: d/dtheta of mean_r(loss_r).  Returns (mean_r loss_r,
+    [loss_r]); call .backward() on the first to get the averaged gradients.  DropPath / Dropout2d are off.
+    Running statistics in ``new_stats``: the FFM ones are rank 0's (DDP broadcasts rank 0's buffers before every forward)."""
+    pre, p = [], "decode_head"
+    for r, (rgb, x, _) in enumerate(shards):
+        feats = backbone(sd, spec, rgb, x, True, new_stats if r == 0 else None)
+        pre.append(_decoder_pre_bn(sd, feats, p))
+    if sync_decoder_bn:
+        y = _batch_norm(sd, f"{p}.linear_fuse.1", torch.cat(pre, 0), True, decoder_bn_eps, 0.1, new_stats)
+        ys = list(y.split([t.shape[0] for t in pre], 0))
+    else:
+        ys = [_batch_norm(sd, f"{p}.linear_fuse.1", t, True, decoder_bn_eps, 0.1, new_stats if r == 0 else None)
+              for r, t in enumerate(pre)]
+    losses = []
+    for (rgb, _, label), y in zip(shards, ys):
+        out = F.interpolate(_decoder_post_bn(sd, y, None, p), size=rgb.shape[2:], mode="bilinear", align_corners=False)
+        losses.append(F.cross_entropy(out, label.long(), ignore_index=ignore_index, reduction="mean"))
+    return torch.stack(losses).mean(), losses
 
 
 # --------------------------------------------------------------------------

@@ -28,6 +28,7 @@ class CmxGemm(ctypes.Structure):
         ("act", ctypes.c_int32), ("alpha", ctypes.c_float),
         ("accumulate", ctypes.c_int32), ("split_k", ctypes.c_int32),
         ("rows_per_sample", ctypes.c_int32), ("impl", ctypes.c_int32),
+        ("sBias1", ctypes.c_int64), ("sR1", ctypes.c_int64), ("sS1", ctypes.c_int64),
     ]
 
 

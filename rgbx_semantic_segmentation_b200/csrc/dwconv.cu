@@ -130,8 +130,17 @@ __global__ void __launch_bounds__(256, (MODE == 1 ? 2 : 3)) dwconv_tiled_kernel(
                                                            const float* __restrict__ bias, const bf16* __restrict__ dy, long lddy,
                                                            bf16* __restrict__ out, long ldo, float* __restrict__ dw,
                                                            float* __restrict__ db, int B, int H, int W, int C, int tiles_x,
-                                                           int tiles_y, long ntiles) {
+                                                           int tiles_y, long ntiles, long pgs) {
   pdl_trigger();
+  if (gridDim.z > 1) {  // grouped launch: group g = samples [g*B, (g+1)*B) of the stacked tensors; every parameter of
+    const long g = blockIdx.z;  // group g lies g * pgs ELEMENTS behind the given pointer (flat parameter / gradient buffer)
+    const long rows = g * B * H * W;
+    x += rows * ldx; out += rows * ldo; w += g * pgs;
+    if (dy) dy += rows * lddy;
+    if (bias) bias += g * pgs;
+    if (dw) dw += g * pgs;
+    if (db) db += g * pgs;
+  }
   __shared__ __align__(16) bf16 tile[(DT_TH + 2) * (DT_TW + 2) * DT_CH];  // 43.5 KB
   __shared__ float sred[20][DT_CH];
   const int tid = threadIdx.x;
@@ -288,30 +297,34 @@ __global__ void __launch_bounds__(256, (MODE == 1 ? 2 : 3)) dwconv_tiled_kernel(
 
 template <int ACT, int MODE>
 static void dwconv_tiled_launch(const void* x, long ldx, const float* w, const float* bias, const void* dy, long lddy, void* out,
-                                long ldo, float* dw, float* db, int B, int H, int W, int C, cudaStream_t st) {
+                                long ldo, float* dw, float* db, int B, int H, int W, int C, int groups, long pgs, cudaStream_t st) {
   const int tiles_x = (W + DT_TW - 1) / DT_TW, tiles_y = (H + DT_TH - 1) / DT_TH;
   const long ntiles = (long)B * tiles_x * tiles_y;
   const int gx = (C + DT_CH - 1) / DT_CH;
   long gy = ntiles;
-  const long cap = (MODE == 1 || db) ? (148L * 5 + gx - 1) / gx : (148L * 20 + gx - 1) / gx;  // reductions: few CTAs => few atomics
+  long cap = (MODE == 1 || db) ? (148L * 5 + gx - 1) / gx : (148L * 20 + gx - 1) / gx;  // reductions: few CTAs => few atomics
+  cap = (cap + groups - 1) / groups;
   if (gy > cap) gy = cap;
-  dim3 grid(gx, (unsigned)gy);
+  dim3 grid(gx, (unsigned)gy, (unsigned)groups);
   dwconv_tiled_kernel<ACT, MODE><<<grid, 256, 0, st>>>((const bf16*)x, ldx, w, bias, (const bf16*)dy, lddy, (bf16*)out, ldo, dw, db, B,
-                                                       H, W, C, tiles_x, tiles_y, ntiles);
+                                                       H, W, C, tiles_x, tiles_y, ntiles, pgs);
 }
 
 CMX_API int cmx_dwconv3x3_fwd(const void* x, int64_t ldx, const float* w, const float* bias, int act, int flip, void* y,
-                              int64_t ldy, float* ysum, int B, int H, int W, int C, void* stream) {
+                              int64_t ldy, float* ysum, int B, int H, int W, int C, int groups, int64_t param_gs, void* stream) {
   CMX_REQUIRE(C % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0, "dwconv3x3: C and ld must be multiples of 8 (C=%d)", C);
+  CMX_REQUIRE(groups >= 1 && groups <= 65535, "dwconv3x3: groups=%d", groups);
   cudaStream_t st = (cudaStream_t)stream;
   if ((long)B * H * W == 0) return 0;
+  const long pgs = param_gs;
+  CMX_REQUIRE(groups == 1 || getenv("CMX_DWCONV_LEGACY") == nullptr, "dwconv3x3: grouped launches need the tiled kernel");
   if (getenv("CMX_DWCONV_LEGACY") == nullptr) {
     if (flip) {
       CMX_REQUIRE(act == CMX_ACT_NONE, "dwconv3x3: flip is for the data gradient (no activation)");
-      dwconv_tiled_launch<CMX_ACT_NONE, 2>(x, ldx, w, nullptr, nullptr, 0, y, ldy, nullptr, ysum, B, H, W, C, st);
-    } else if (act == CMX_ACT_GELU) dwconv_tiled_launch<CMX_ACT_GELU, 0>(x, ldx, w, bias, nullptr, 0, y, ldy, nullptr, ysum, B, H, W, C, st);
-    else if (act == CMX_ACT_RELU) dwconv_tiled_launch<CMX_ACT_RELU, 0>(x, ldx, w, bias, nullptr, 0, y, ldy, nullptr, ysum, B, H, W, C, st);
-    else dwconv_tiled_launch<CMX_ACT_NONE, 0>(x, ldx, w, bias, nullptr, 0, y, ldy, nullptr, ysum, B, H, W, C, st);
+      dwconv_tiled_launch<CMX_ACT_NONE, 2>(x, ldx, w, nullptr, nullptr, 0, y, ldy, nullptr, ysum, B, H, W, C, groups, pgs, st);
+    } else if (act == CMX_ACT_GELU) dwconv_tiled_launch<CMX_ACT_GELU, 0>(x, ldx, w, bias, nullptr, 0, y, ldy, nullptr, ysum, B, H, W, C, groups, pgs, st);
+    else if (act == CMX_ACT_RELU) dwconv_tiled_launch<CMX_ACT_RELU, 0>(x, ldx, w, bias, nullptr, 0, y, ldy, nullptr, ysum, B, H, W, C, groups, pgs, st);
+    else dwconv_tiled_launch<CMX_ACT_NONE, 0>(x, ldx, w, bias, nullptr, 0, y, ldy, nullptr, ysum, B, H, W, C, groups, pgs, st);
     g_cmx_launches++;
     CMX_CHECK_LAUNCH("dwconv3x3_tiled");
     return 0;
@@ -451,14 +464,18 @@ __global__ void __launch_bounds__(DW_CG* DW_PY) dwconv_bwd_pre_kernel(const bf16
 
 CMX_API int cmx_dwconv3x3_bwd_pre(const void* x, int64_t ldx, const float* w, const float* bias, int act, const void* dy,
                                   int64_t lddy, void* du, int64_t lddu, float* dw, float* db, int B, int H, int W, int C,
-                                  void* stream) {
+                                  int groups, int64_t param_gs, void* stream) {
   CMX_REQUIRE(C % 4 == 0 && ldx % 4 == 0 && lddy % 4 == 0 && lddu % 4 == 0, "dwconv3x3_bwd_pre: C/ld %% 4");
+  CMX_REQUIRE(groups >= 1 && groups <= 65535, "dwconv3x3_bwd_pre: groups=%d", groups);
   cudaStream_t st = (cudaStream_t)stream;
   if ((long)B * H * W == 0) return 0;
-  if (getenv("CMX_DWCONV_LEGACY") == nullptr && C % 8 == 0 && ldx % 8 == 0) {
-    if (act == CMX_ACT_GELU) dwconv_tiled_launch<CMX_ACT_GELU, 1>(x, ldx, w, bias, dy, lddy, du, lddu, dw, db, B, H, W, C, st);
-    else if (act == CMX_ACT_RELU) dwconv_tiled_launch<CMX_ACT_RELU, 1>(x, ldx, w, bias, dy, lddy, du, lddu, dw, db, B, H, W, C, st);
-    else dwconv_tiled_launch<CMX_ACT_NONE, 1>(x, ldx, w, bias, dy, lddy, du, lddu, dw, db, B, H, W, C, st);
+  const long pgs = param_gs;
+  const bool tiled = getenv("CMX_DWCONV_LEGACY") == nullptr && C % 8 == 0 && ldx % 8 == 0;
+  CMX_REQUIRE(groups == 1 || tiled, "dwconv3x3_bwd_pre: grouped launches need the tiled kernel (C %% 8 == 0)");
+  if (tiled) {
+    if (act == CMX_ACT_GELU) dwconv_tiled_launch<CMX_ACT_GELU, 1>(x, ldx, w, bias, dy, lddy, du, lddu, dw, db, B, H, W, C, groups, pgs, st);
+    else if (act == CMX_ACT_RELU) dwconv_tiled_launch<CMX_ACT_RELU, 1>(x, ldx, w, bias, dy, lddy, du, lddu, dw, db, B, H, W, C, groups, pgs, st);
+    else dwconv_tiled_launch<CMX_ACT_NONE, 1>(x, ldx, w, bias, dy, lddy, du, lddu, dw, db, B, H, W, C, groups, pgs, st);
     g_cmx_launches++;
     CMX_CHECK_LAUNCH("dwconv3x3_bwd_pre_tiled");
     return 0;

@@ -161,6 +161,7 @@ struct TcSched {
   int kb_total, kb_per, stages;
   long total_tiles;
   long sC1, sC2;  // element strides of C per batch index
+  long sBias1, sR1, sS1;  // batch1 strides (elements) of bias / residual / row_scale: grouped (per-branch weights) launches
   int tma_store;  // 0 = per-thread global stores (atomics / odd layouts), 1 = smem-staged TMA bulk store
   long long* trace;  // debug: CTA 0 writes clock64 stamps [role][tile][4] (role 0 producer, 1 mma, 2 epilogue, 3/4 epilogue detail)
 };
@@ -345,6 +346,12 @@ __global__ void __launch_bounds__(tc_threads(BN), tc_ctas_per_sm(BN)) gemm_tc_ke
         const long off = (long)b1 * sc.sC1 + (long)b2 * sc.sC2;
         if (epi.c_dtype == CMX_F32) epi.C = reinterpret_cast<float*>(epi.C) + off;
         else epi.C = reinterpret_cast<bf16*>(epi.C) + off;
+        if (epi.bias) epi.bias += (long)b1 * sc.sBias1;
+        if (epi.row_scale) epi.row_scale += (long)b1 * sc.sS1;
+        if (epi.res) {
+          if (epi.r_dtype == CMX_F32) epi.res = reinterpret_cast<const float*>(epi.res) + (long)b1 * sc.sR1;
+          else epi.res = reinterpret_cast<const bf16*>(epi.res) + (long)b1 * sc.sR1;
+        }
       }
       if (sp != 0) {  // split-K: bias / residual are contributed once, by slice 0
         epi.bias = nullptr;
@@ -356,8 +363,9 @@ __global__ void __launch_bounds__(tc_threads(BN), tc_ctas_per_sm(BN)) gemm_tc_ke
         // registers one tile ahead, so the global-load latency hides behind the previous tile's epilogue
         sb_addr = bias_base + (uint32_t)(warp - 2) * (BN * 4u);
         if (lt == 0 && epi0.bias) {
+          const float* bp = epi0.bias + (BATCHED ? (long)b1 * sc.sBias1 : 0l);
 #pragma unroll
-          for (int i = 0; i < BN / 32; i++) bias_pf[i] = (n0 + lane + 32 * i < epi0.N) ? epi0.bias[n0 + lane + 32 * i] : 0.f;
+          for (int i = 0; i < BN / 32; i++) bias_pf[i] = (n0 + lane + 32 * i < epi0.N) ? bp[n0 + lane + 32 * i] : 0.f;
         }
         if (epi.bias) {
           __syncwarp();   // every lane has finished reading the previous tile's copy
@@ -370,8 +378,9 @@ __global__ void __launch_bounds__(tc_threads(BN), tc_ctas_per_sm(BN)) gemm_tc_ke
         if (epi0.bias && tn < sc.total_tiles) {
           int n1, m1, c1, c2, kb1, nk1, sp1;
           decode(tn, n1, m1, c1, c2, kb1, nk1, sp1);
+          const float* bp = epi0.bias + (BATCHED ? (long)c1 * sc.sBias1 : 0l);
 #pragma unroll
-          for (int i = 0; i < BN / 32; i++) bias_pf[i] = (n1 + lane + 32 * i < epi0.N) ? epi0.bias[n1 + lane + 32 * i] : 0.f;
+          for (int i = 0; i < BN / 32; i++) bias_pf[i] = (n1 + lane + 32 * i < epi0.N) ? bp[n1 + lane + 32 * i] : 0.f;
         }
         if (warp == 4 && lane == 0) { TC_TRACE(2, lt, 0); TC_TRACE(2, lt, 1); }
       } else {
@@ -589,6 +598,7 @@ struct GenArgs {
   long K;
   int batch2;
   long sA1, sA2, sB1, sB2, sC1, sC2;
+  long sBias1, sR1, sS1;
   long k_per_split;
 };
 
@@ -615,6 +625,13 @@ __global__ void __launch_bounds__(128) gemm_wmma_kernel(GenArgs g, Epi epi) {
   Epi e = epi;
   if (e.c_dtype == CMX_F32) e.C = reinterpret_cast<float*>(e.C) + b1 * g.sC1 + b2 * g.sC2;
   else e.C = reinterpret_cast<bf16*>(e.C) + b1 * g.sC1 + b2 * g.sC2;
+  if (e.bias) e.bias += b1 * g.sBias1;
+  if (e.row_scale) e.row_scale += b1 * g.sS1;
+  if (e.res) {
+    if (e.r_dtype == CMX_F32) e.res = reinterpret_cast<const float*>(e.res) + b1 * g.sR1;
+    else e.res = reinterpret_cast<const bf16*>(e.res) + b1 * g.sR1;
+  }
+  if (split != 0) { e.bias = nullptr; e.res = nullptr; }
 
   wmma::fragment<wmma::accumulator, 16, 16, 16, float> acc[2][2];
 #pragma unroll
@@ -774,7 +791,8 @@ static bool tc_eligible(const CmxGemm* g) {
   if ((g->split_k > 1 || g->accumulate) && g->c_dtype != CMX_F32) return false;
   if (g->split_k > 1 && g->act != CMX_ACT_NONE) return false;  // non-linear epilogue needs the full sum
   if (batched) {
-    if (g->residual || g->bias || g->row_scale) return false;
+    if ((g->residual || g->bias || g->row_scale) && g->batch2 != 1) return false;  // epilogue operands follow batch1 only
+    if ((g->sBias1 % 4) || (g->sR1 % 8)) return false;
     if ((g->sA1 % 8) || (g->sA2 % 8) || (g->sB1 % 8) || (g->sB2 % 8) || (g->sC1 % 8) || (g->sC2 % 8)) return false;
     if ((g->batch1 > 1 && (g->sA1 <= 0 || g->sB1 <= 0)) || (g->batch2 > 1 && (g->sA2 <= 0 || g->sB2 <= 0))) return false;
   }
@@ -814,6 +832,9 @@ static int launch_tc(const CmxGemm* g, const Epi& epi, cudaStream_t st) {
   sc.total_tiles = (long)sc.tiles_n * sc.tiles_m * sc.nbatch * split;
   sc.sC1 = g->sC1;
   sc.sC2 = g->sC2;
+  sc.sBias1 = g->sBias1;
+  sc.sR1 = g->sR1;
+  sc.sS1 = g->sS1;
   const bool atomic = (split > 1 || g->accumulate);
   sc.tma_store = (!atomic && getenv("CMX_GEMM_NO_TMA_STORE") == nullptr) ? 1 : 0;
   sc.trace = g_tc_trace;
@@ -961,6 +982,7 @@ CMX_API int cmx_gemm(const CmxGemm* g, void* stream) {
   a.sBk = g->trans_b ? g->ldb : 1; a.sBn = g->trans_b ? 1 : g->ldb;
   a.K = g->K; a.batch2 = g->batch2;
   a.sA1 = g->sA1; a.sA2 = g->sA2; a.sB1 = g->sB1; a.sB2 = g->sB2; a.sC1 = g->sC1; a.sC2 = g->sC2;
+  a.sBias1 = g->sBias1; a.sR1 = g->sR1; a.sS1 = g->sS1;
   int split = g->split_k > 1 ? g->split_k : 1;
   long kper = ((g->K + split - 1) / split + GK - 1) / GK * GK;
   a.k_per_split = kper;

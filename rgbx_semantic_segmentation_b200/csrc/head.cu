@@ -365,7 +365,7 @@ CMX_API int cmx_upsample_bwd_multi(const void* dout, int Ho, int Wo, void* dz1, 
 // ---- fused bilinear upsample + cross entropy (+ gradient scatter) ----------------------------------------
 // CTA = 32 x 8 threads covering a 32 x 8 full-resolution tile.  The low-res window the tile touches is
 // staged in shared memory (logits in, gradient accumulator out); MAXC classes.
-constexpr int CE_MAXC = 16;
+constexpr int CE_MAXC_SMALL = 16, CE_MAXC_LARGE = 64;  // register-array bound on the class count (two instantiations)
 constexpr int CE_TW = 32, CE_TH = 8;
 constexpr float CE_FIX = 2097152.f;  // 2^21: fixed-point scale of the per-CTA gradient partials (plain CE)
 
@@ -373,7 +373,7 @@ constexpr float CE_FIX = 2097152.f;  // 2^21: fixed-point scale of the per-CTA g
 // 157-196: pt_k = p_k for the target class and 1 - p_k otherwise, -alpha_k (1 - pt_k)^gamma log(pt_k + 1e-8) summed over the
 // classes; alpha_k = alpha / 1 - alpha), both averaged over the valid pixels (train.py:70-93: 'FocalLoss', 'CE_Focal').
 struct FocalArgs { float w_ce, w_focal, gamma, alpha; };
-template <bool FOCAL>
+template <bool FOCAL, int CE_MAXC>
 __global__ void __launch_bounds__(256) ce_upsampled_kernel(const float* __restrict__ logits, long ld, const int64_t* __restrict__ label,
                                                            int ignore_index, double* __restrict__ acc, float* __restrict__ dlogits,
                                                            int h, int w, int H, int W, int ncls, float sh, float sw, int cap,
@@ -414,6 +414,9 @@ __global__ void __launch_bounds__(256) ce_upsampled_kernel(const float* __restri
   if (x < W && y < H) {
     const long lab = label[((long)b * H + y) * W + x];
     if (lab != ignore_index) {
+      // a target outside [0, ncls) that is not the ignore index is a data error: torch's nll_loss raises a device-side
+      // assert for it; silently treating it as "no target" would train on garbage (FocalLoss clamps instead, like the reference)
+      if (!FOCAL && (lab < 0 || lab >= ncls)) __trap();
       int y0, y1, x0, x1;
       float ly, lx;
       bilin_src(y, sh, h, y0, y1, ly);
@@ -517,7 +520,7 @@ __global__ void __launch_bounds__(256) ce_upsampled_kernel(const float* __restri
 }
 static int ce_launch(const float* logits, int64_t ld, const int64_t* label, int ignore_index, double* acc, float* dlogits, int B,
                      int h, int w, int H, int W, int ncls, const FocalArgs* focal, void* stream) {
-  CMX_REQUIRE(ncls >= 1 && ncls <= CE_MAXC, "ce: ncls=%d > %d unsupported", ncls, CE_MAXC);
+  CMX_REQUIRE(ncls >= 1 && ncls <= CE_MAXC_LARGE, "ce: ncls=%d > %d unsupported", ncls, CE_MAXC_LARGE);
   CMX_REQUIRE(ld >= ncls, "ce: row stride %ld < ncls %d", (long)ld, ncls);
   CMX_REQUIRE(H >= h && W >= w, "ce: only upsampling supported");
   if (B == 0) return 0;
@@ -525,14 +528,15 @@ static int ce_launch(const float* logits, int64_t ld, const int64_t* label, int 
   const int nh_max = (int)((CE_TH - 1) * sh) + 3, nw_max = (int)((CE_TW - 1) * sw) + 3;
   const int cap = nh_max * nw_max * ncls;
   const size_t smem = (size_t)cap * 2 * sizeof(float);
-  CMX_REQUIRE(smem <= 48 * 1024, "ce: low-res window too large for shared memory");
+  CMX_REQUIRE(smem <= 200 * 1024, "ce: low-res window too large for shared memory");
   dim3 grid(cdiv(W, CE_TW), cdiv(H, CE_TH), B), block(32, 8);
-  if (focal)
-    ce_upsampled_kernel<true><<<grid, block, smem, (cudaStream_t)stream>>>(logits, (long)ld, label, ignore_index, acc, dlogits, h, w, H, W,
-                                                                          ncls, sh, sw, cap, *focal);
-  else
-    ce_upsampled_kernel<false><<<grid, block, smem, (cudaStream_t)stream>>>(logits, (long)ld, label, ignore_index, acc, dlogits, h, w, H, W,
-                                                                           ncls, sh, sw, cap, FocalArgs{1.f, 0.f, 0.f, 0.f});
+  const FocalArgs fa = focal ? *focal : FocalArgs{1.f, 0.f, 0.f, 0.f};
+#define CE_LAUNCH(F, MC) \
+  if (smem > 48 * 1024) cudaFuncSetAttribute(ce_upsampled_kernel<F, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+  ce_upsampled_kernel<F, MC><<<grid, block, smem, (cudaStream_t)stream>>>(logits, (long)ld, label, ignore_index, acc, dlogits, h, w, H, W, ncls, sh, sw, cap, fa)
+  if (ncls <= CE_MAXC_SMALL) { if (focal) { CE_LAUNCH(true, CE_MAXC_SMALL); } else { CE_LAUNCH(false, CE_MAXC_SMALL); } }
+  else { if (focal) { CE_LAUNCH(true, CE_MAXC_LARGE); } else { CE_LAUNCH(false, CE_MAXC_LARGE); } }   // e.g. the 40 NYUDv2 classes (config.py default)
+#undef CE_LAUNCH
   LAUNCH_DONE("ce_upsampled_fwd_bwd");
 }
 CMX_API int cmx_ce_upsampled_fwd_bwd(const float* logits, int64_t ld, const int64_t* label, int ignore_index, double* acc,
@@ -545,6 +549,208 @@ CMX_API int cmx_ce_focal_upsampled_fwd_bwd(const float* logits, int64_t ld, cons
   CMX_REQUIRE(gamma >= 0.f && alpha >= 0.f && alpha <= 1.f, "ce_focal: gamma=%g alpha=%g out of range", gamma, alpha);
   const FocalArgs fa{w_ce, w_focal, gamma, alpha};
   return ce_launch(logits, ld, label, ignore_index, acc, dlogits, B, h, w, H, W, ncls, &fa, stream);
+}
+
+// ---- DiceCELoss (utils/loss_opr.py:103-156): alpha * Dice + (1 - alpha) * CE on the bilinearly upsampled logits -----------
+// Dice couples all pixels of a sample through per-(sample, class) sums, so it takes two passes over the pixels (the
+// upsampled logits are recomputed from the shared-memory low-res window in both; nothing full-resolution is stored):
+//   PASS 0  per (b, k):  Sp = sum_valid p_k,  Si = sum_valid p_k [k == t],  St = sum_valid [k == t]   (t = label clamped to
+//           [0, ncls) as the reference does) and the CE sum / valid count;
+//   finalize (one CTA): dice_bk = (2 Si + s) / (Sp + St + s), loss = alpha (1 - mean dice) + (1 - alpha) CE, and the
+//           coefficients of d loss / d p_k = c1_bk [k == t] + c2_bk;
+//   PASS 1  d loss / d z_j = p_j (g_j - sum_k g_k p_k) + (1 - alpha) / n_valid (p_j - [j == t]), scattered through the
+//           bilinear weights to the low-res logits exactly like the CE kernel does.
+template <int PASS, int MAXC>
+__global__ void __launch_bounds__(256) dice_ce_kernel(const float* __restrict__ logits, long ld, const int64_t* __restrict__ label,
+                                                      int ignore_index, double* __restrict__ acc, double* __restrict__ dstats,
+                                                      const float* __restrict__ coef, float* __restrict__ dlogits,
+                                                      int h, int w, int H, int W, int ncls, float sh, float sw, int cap) {
+  pdl_trigger();
+  extern __shared__ float s_dyn[];  // [cap] low-res logits window, [cap] gradient accumulator, [3 * ncls] class sums
+  float* s_l = s_dyn;
+  float* s_g = s_dyn + cap;
+  float* s_c = s_dyn + 2 * cap;
+  __shared__ float s_red[8];
+  __shared__ int s_cnt[8];
+  const int b = blockIdx.z;
+  const int X0 = blockIdx.x * CE_TW, Y0 = blockIdx.y * CE_TH;
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  int ly0, t1, lx0;
+  float tf;
+  bilin_src(Y0, sh, h, ly0, t1, tf);
+  bilin_src(X0, sw, w, lx0, t1, tf);
+  int ylast = Y0 + CE_TH - 1, xlast = X0 + CE_TW - 1;
+  if (ylast > H - 1) ylast = H - 1;
+  if (xlast > W - 1) xlast = W - 1;
+  int ly1, lx1, t0;
+  bilin_src(ylast, sh, h, t0, ly1, tf);
+  bilin_src(xlast, sw, w, t0, lx1, tf);
+  const int nh = ly1 - ly0 + 1, nw = lx1 - lx0 + 1;
+  if (nh * nw * ncls > cap) __trap();
+  for (int i = tid; i < nh * nw * ncls; i += 256) {
+    const int k = i % ncls;
+    const int xx = (i / ncls) % nw;
+    const int yy = i / (ncls * nw);
+    s_l[i] = logits[(((long)b * h + ly0 + yy) * w + lx0 + xx) * ld + k];
+    s_g[i] = 0.f;
+  }
+  for (int i = tid; i < 3 * ncls; i += 256) s_c[i] = 0.f;
+  __syncthreads();
+  const int x = X0 + threadIdx.x, y = Y0 + threadIdx.y;
+  float loss = 0.f;
+  int valid = 0;
+  if (x < W && y < H) {
+    const long lab = label[((long)b * H + y) * W + x];
+    if (lab != ignore_index) {
+      if (lab < 0 || lab >= ncls) __trap();   // the CE term of the reference raises for such a target
+      const int t = (int)lab;
+      int y0, y1, x0, x1;
+      float ly, lx;
+      bilin_src(y, sh, h, y0, y1, ly);
+      bilin_src(x, sw, w, x0, x1, lx);
+      const int o00 = ((y0 - ly0) * nw + (x0 - lx0)) * ncls, o01 = ((y0 - ly0) * nw + (x1 - lx0)) * ncls;
+      const int o10 = ((y1 - ly0) * nw + (x0 - lx0)) * ncls, o11 = ((y1 - ly0) * nw + (x1 - lx0)) * ncls;
+      const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+      float v[MAXC];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int k = 0; k < MAXC; k++) {
+        if (k < ncls) {
+          v[k] = w00 * s_l[o00 + k] + w01 * s_l[o01 + k] + w10 * s_l[o10 + k] + w11 * s_l[o11 + k];
+          mx = fmaxf(mx, v[k]);
+        }
+      }
+      float sum = 0.f, picked = 0.f;
+#pragma unroll
+      for (int k = 0; k < MAXC; k++) {
+        if (k < ncls) {
+          if (k == t) picked = v[k];
+          v[k] = expf(v[k] - mx);
+          sum += v[k];
+        }
+      }
+      const float inv = 1.f / sum;
+      valid = 1;
+      if (PASS == 0) {
+        loss = logf(sum) + mx - picked;
+#pragma unroll
+        for (int k = 0; k < MAXC; k++) {
+          if (k < ncls) {
+            const float p = v[k] * inv;
+            atomicAdd(&s_c[k], p);
+            if (k == t) { atomicAdd(&s_c[ncls + k], p); atomicAdd(&s_c[2 * ncls + k], 1.f); }
+          }
+        }
+      } else {
+        const float* c1 = coef + (long)b * 2 * ncls;
+        const float* c2 = c1 + ncls;
+        const float w_ce = coef[(long)gridDim.z * 2 * ncls];   // (1 - alpha) / n_valid, written by the finalize kernel
+        float gs = 0.f;
+#pragma unroll
+        for (int k = 0; k < MAXC; k++)
+          if (k < ncls) gs += ((k == t ? c1[k] : 0.f) + c2[k]) * v[k] * inv;
+#pragma unroll
+        for (int k = 0; k < MAXC; k++) {
+          if (k < ncls) {
+            const float p = v[k] * inv;
+            const float g = p * ((k == t ? c1[k] : 0.f) + c2[k] - gs) + w_ce * (p - (k == t ? 1.f : 0.f));
+            atomicAdd(&s_g[o00 + k], w00 * g);
+            atomicAdd(&s_g[o01 + k], w01 * g);
+            atomicAdd(&s_g[o10 + k], w10 * g);
+            atomicAdd(&s_g[o11 + k], w11 * g);
+          }
+        }
+      }
+    }
+  }
+  if (PASS == 0) {
+    loss = warp_sum(loss);
+    valid = __reduce_add_sync(0xffffffffu, valid);
+    if (threadIdx.x == 0) { s_red[threadIdx.y] = loss; s_cnt[threadIdx.y] = valid; }
+    __syncthreads();
+    if (tid == 0) {
+      double l = 0.;
+      int n = 0;
+      for (int i = 0; i < 8; i++) { l += (double)s_red[i]; n += s_cnt[i]; }
+      if (n) { atomicAdd(acc, l); atomicAdd(acc + 1, (double)n); }
+    }
+    for (int i = tid; i < 3 * ncls; i += 256)
+      if (s_c[i] != 0.f) atomicAdd(dstats + (long)b * 3 * ncls + i, (double)s_c[i]);
+  } else {
+    __syncthreads();
+    for (int i = tid; i < nh * nw * ncls; i += 256) {
+      const int k = i % ncls;
+      const int xx = (i / ncls) % nw;
+      const int yy = i / (ncls * nw);
+      if (s_g[i] != 0.f) atomicAdd(dlogits + (((long)b * h + ly0 + yy) * w + lx0 + xx) * ld + k, s_g[i]);
+    }
+  }
+}
+static int dice_launch(int pass, const float* logits, int64_t ld, const int64_t* label, int ignore_index, double* acc, double* dstats,
+                       const float* coef, float* dlogits, int B, int h, int w, int H, int W, int ncls, void* stream) {
+  CMX_REQUIRE(ncls >= 1 && ncls <= CE_MAXC_LARGE, "dice_ce: ncls=%d > %d unsupported", ncls, CE_MAXC_LARGE);
+  CMX_REQUIRE(ld >= ncls, "dice_ce: row stride %ld < ncls %d", (long)ld, ncls);
+  CMX_REQUIRE(H >= h && W >= w, "dice_ce: only upsampling supported");
+  if (B == 0) return 0;
+  const float sh = (float)h / (float)H, sw = (float)w / (float)W;
+  const int nh_max = (int)((CE_TH - 1) * sh) + 3, nw_max = (int)((CE_TW - 1) * sw) + 3;
+  const int cap = nh_max * nw_max * ncls;
+  const size_t smem = ((size_t)cap * 2 + 3 * ncls) * sizeof(float);
+  CMX_REQUIRE(smem <= 200 * 1024, "dice_ce: low-res window too large for shared memory");
+  dim3 grid(cdiv(W, CE_TW), cdiv(H, CE_TH), B), block(32, 8);
+#define DICE_LAUNCH(P, MC) \
+  if (smem > 48 * 1024) cudaFuncSetAttribute(dice_ce_kernel<P, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+  dice_ce_kernel<P, MC><<<grid, block, smem, (cudaStream_t)stream>>>(logits, (long)ld, label, ignore_index, acc, dstats, coef, dlogits, h, w, H, W, ncls, sh, sw, cap)
+  if (ncls <= CE_MAXC_SMALL) { if (pass == 0) { DICE_LAUNCH(0, CE_MAXC_SMALL); } else { DICE_LAUNCH(1, CE_MAXC_SMALL); } }
+  else { if (pass == 0) { DICE_LAUNCH(0, CE_MAXC_LARGE); } else { DICE_LAUNCH(1, CE_MAXC_LARGE); } }
+#undef DICE_LAUNCH
+  LAUNCH_DONE("dice_ce");
+}
+CMX_API int cmx_dice_ce_stats(const float* logits, int64_t ld, const int64_t* label, int ignore_index, double* acc, double* dstats,
+                              int B, int h, int w, int H, int W, int ncls, void* stream) {
+  return dice_launch(0, logits, ld, label, ignore_index, acc, dstats, nullptr, nullptr, B, h, w, H, W, ncls, stream);
+}
+// one CTA: loss and the gradient coefficients from the pass-0 sums.  coef: float[B][2][ncls] = (c1, c2) followed by one float
+// = (1 - alpha) / n_valid (read by pass 1)
+__global__ void dice_ce_finalize_kernel(const double* __restrict__ acc, const double* __restrict__ dstats, int B, int ncls, float alpha,
+                                        float smooth, float* __restrict__ loss, float* __restrict__ coef) {
+  pdl_trigger();
+  __shared__ double s_sum[256];
+  double part = 0.;
+  const int n = B * ncls;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int b = i / ncls, k = i % ncls;
+    const double* st = dstats + (long)b * 3 * ncls;
+    const double U = st[k] + st[2 * ncls + k] + (double)smooth, num = 2. * st[ncls + k] + (double)smooth;
+    part += num / U;
+    if (coef) {
+      coef[(long)b * 2 * ncls + k] = (float)(-(double)alpha / n * 2. / U);
+      coef[(long)b * 2 * ncls + ncls + k] = (float)((double)alpha / n * num / (U * U));
+    }
+  }
+  s_sum[threadIdx.x] = part;
+  __syncthreads();
+  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) s_sum[threadIdx.x] += s_sum[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const double dice_loss = 1. - s_sum[0] / n;
+    const double ce = acc[0] / acc[1];          // all-ignored batch -> NaN like the reference's CE term
+    if (loss) *loss = (float)((double)alpha * dice_loss + (1. - (double)alpha) * ce);
+    if (coef) coef[(long)B * 2 * ncls] = (float)((1. - (double)alpha) / acc[1]);
+  }
+}
+CMX_API int cmx_dice_ce_finalize(const double* acc, const double* dstats, int B, int ncls, float alpha, float smooth, float* loss,
+                                 float* coef, void* stream) {
+  dice_ce_finalize_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(acc, dstats, B, ncls, alpha, smooth, loss, coef);
+  LAUNCH_DONE("dice_ce_finalize");
+}
+// pass 1: dlogits (fp32, zero-initialised by the caller) += d loss / d logits; coef as written by cmx_dice_ce_finalize
+// (float[B*2*ncls + 1], the last element = (1 - alpha) / n_valid); the result needs no further scaling
+CMX_API int cmx_dice_ce_grad(const float* logits, int64_t ld, const int64_t* label, int ignore_index, const float* coef,
+                             float* dlogits, int B, int h, int w, int H, int W, int ncls, void* stream) {
+  return dice_launch(1, logits, ld, label, ignore_index, nullptr, nullptr, coef, dlogits, B, h, w, H, W, ncls, stream);
 }
 template <typename TO>
 __global__ void __launch_bounds__(256) ce_finalize_kernel(const double* __restrict__ acc, float* __restrict__ loss,
@@ -652,8 +858,8 @@ CMX_API int cmx_confusion(const void* pred, int pred_dtype, const void* gt, int 
 }
 
 // fused argmax (first maximum, like numpy/torch argmax) + confusion for one [ncls, npix] score map
-template <typename TG>
-__global__ void __launch_bounds__(256) argmax_confusion_kernel(const float* __restrict__ scores, const TG* __restrict__ gt, long npix,
+template <typename TG, typename TS>
+__global__ void __launch_bounds__(256) argmax_confusion_kernel(const TS* __restrict__ scores, const TG* __restrict__ gt, long npix,
                                                                int n_cl, uint8_t* __restrict__ pred_out,
                                                                unsigned long long* __restrict__ hist, unsigned long long* __restrict__ stats) {
   pdl_trigger();
@@ -664,10 +870,10 @@ __global__ void __launch_bounds__(256) argmax_confusion_kernel(const float* __re
   __syncthreads();
   unsigned int lab = 0, cor = 0;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (long)gridDim.x * blockDim.x) {
-    float best = scores[i];
+    TS best = scores[i];
     int p = 0;
     for (int k = 1; k < n_cl; k++) {
-      const float v = scores[(long)k * npix + i];
+      const TS v = scores[(long)k * npix + i];
       if (v > best) { best = v; p = k; }
     }
     if (pred_out) pred_out[i] = (uint8_t)p;
@@ -690,8 +896,8 @@ __global__ void __launch_bounds__(256) argmax_confusion_kernel(const float* __re
     if (threadIdx.x == 0) { atomicAdd(stats, (unsigned long long)s_lab); atomicAdd(stats + 1, (unsigned long long)s_cor); }
   }
 }
-CMX_API int cmx_argmax_confusion(const float* scores, const void* gt, int gt_dtype, int64_t npix, int n_cl, uint8_t* pred_out,
-                                 int64_t* hist, int64_t* stats, void* stream) {
+CMX_API int cmx_argmax_confusion(const void* scores, int score_f64, const void* gt, int gt_dtype, int64_t npix, int n_cl,
+                                 uint8_t* pred_out, int64_t* hist, int64_t* stats, void* stream) {
   CMX_REQUIRE(n_cl >= 1 && n_cl <= CF_MAXCL, "argmax_confusion: n_cl=%d unsupported", n_cl);
   if (npix == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
@@ -699,8 +905,12 @@ CMX_API int cmx_argmax_confusion(const float* scores, const void* gt, int gt_dty
   if (grid > 148 * 4) grid = 148 * 4;
   auto* h = reinterpret_cast<unsigned long long*>(hist);
   auto* s = reinterpret_cast<unsigned long long*>(stats);
-  if (gt_dtype == 0) argmax_confusion_kernel<uint8_t><<<grid, 256, 0, st>>>(scores, (const uint8_t*)gt, npix, n_cl, pred_out, h, s);
-  else if (gt_dtype == 1) argmax_confusion_kernel<int32_t><<<grid, 256, 0, st>>>(scores, (const int32_t*)gt, npix, n_cl, pred_out, h, s);
-  else argmax_confusion_kernel<int64_t><<<grid, 256, 0, st>>>(scores, (const int64_t*)gt, npix, n_cl, pred_out, h, s);
+#define AC_L(TG, TS) argmax_confusion_kernel<TG, TS><<<grid, 256, 0, st>>>((const TS*)scores, (const TG*)gt, npix, n_cl, pred_out, h, s)
+  if (score_f64) {   // the evaluator sums the per-scale score maps in float64 (evaluator.py:309, 320)
+    if (gt_dtype == 0) AC_L(uint8_t, double); else if (gt_dtype == 1) AC_L(int32_t, double); else AC_L(int64_t, double);
+  } else {
+    if (gt_dtype == 0) AC_L(uint8_t, float); else if (gt_dtype == 1) AC_L(int32_t, float); else AC_L(int64_t, float);
+  }
+#undef AC_L
   LAUNCH_DONE("argmax_confusion");
 }

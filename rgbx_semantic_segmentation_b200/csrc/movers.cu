@@ -291,8 +291,10 @@ CMX_API int cmx_axpby_f32(float a, const float* x, float b, const float* y, floa
 // ---- column sum (bias gradients): out[n] += sum_m x[m,n] ----------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, long ldx, float* __restrict__ out, long M, int N,
-                                                     int rows_per_cta) {
+                                                     int rows_per_cta, long ogs) {
   pdl_trigger();
+  x += (long)blockIdx.z * M * ldx;   // grouped launch: stacked row blocks, outputs ogs elements apart
+  out += (long)blockIdx.z * ogs;
   __shared__ float s1[8][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + tx;
@@ -313,8 +315,10 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, lo
 }
 // 8 columns (one 16-byte load) per thread; block = NG column groups x (256/NG) row lanes
 __global__ void __launch_bounds__(256) colsum_vec8_kernel(const bf16* __restrict__ x, long ldx, float* __restrict__ out, long M, int N,
-                                                          int ng, int rows_per_cta) {
+                                                          int ng, int rows_per_cta, long ogs) {
   pdl_trigger();
+  x += (long)blockIdx.z * M * ldx;   // grouped launch: stacked row blocks, outputs ogs elements apart
+  out += (long)blockIdx.z * ogs;
   __shared__ float sacc[256][9];
   const int tid = threadIdx.x;
   const int cg = tid % ng, rl = tid / ng, nrl = 256 / ng;
@@ -357,27 +361,30 @@ __global__ void __launch_bounds__(256) colsum_vec8_kernel(const bf16* __restrict
   }
 }
 
-CMX_API int cmx_colsum(const void* x, int x_dtype, int64_t ldx, float* out, int64_t M, int N, void* stream) {
+CMX_API int cmx_colsum(const void* x, int x_dtype, int64_t ldx, float* out, int64_t M, int N, int groups, int64_t out_gs,
+                       void* stream) {
   if (M == 0 || N == 0) return 0;
+  CMX_REQUIRE(groups >= 1 && groups <= 65535, "colsum: groups=%d", groups);
+  const long ogs = out_gs;
   if (x_dtype == CMX_BF16 && N % 8 == 0 && ldx % 8 == 0 && (((uintptr_t)x) & 15) == 0) {
     int ng = N / 8;
     if (ng > 32) ng = 32;
     while (256 % ng) ng--;  // ng must divide 256 (N/8 in {4,8,16,20->16,32,...})
     const int nrl = 256 / ng;
-    long want_ctas = 148L * 4;
+    long want_ctas = 148L * 4 / groups;
     const int gx = cdiv(N / 8, ng);
     long rows_per_cta = (M * gx + want_ctas - 1) / want_ctas;
     rows_per_cta = (rows_per_cta + nrl - 1) / nrl * nrl;
     if (rows_per_cta < 4L * nrl) rows_per_cta = 4L * nrl;
-    dim3 grid(gx, cdiv(M, rows_per_cta));
-    colsum_vec8_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, ldx, out, M, N, ng, (int)rows_per_cta);
+    dim3 grid(gx, cdiv(M, rows_per_cta), groups);
+    colsum_vec8_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, ldx, out, M, N, ng, (int)rows_per_cta, ogs);
     LAUNCH_DONE("colsum_vec8");
   }
   const int rows_per_cta = 512;
-  dim3 grid(cdiv(N, 32), cdiv(M, rows_per_cta));
+  dim3 grid(cdiv(N, 32), cdiv(M, rows_per_cta), groups);
   CMX_REQUIRE(grid.y <= 65535, "colsum: M too large");
-  if (x_dtype == CMX_F32) colsum_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)x, ldx, out, M, N, rows_per_cta);
-  else colsum_kernel<bf16><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, ldx, out, M, N, rows_per_cta);
+  if (x_dtype == CMX_F32) colsum_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)x, ldx, out, M, N, rows_per_cta, ogs);
+  else colsum_kernel<bf16><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, ldx, out, M, N, rows_per_cta, ogs);
   LAUNCH_DONE("colsum");
 }
 

@@ -80,8 +80,14 @@ __device__ __forceinline__ float group_sum(float v) {
 template <typename TX, typename TY, int G, int J>
 __global__ void __launch_bounds__(256) ln_fwd_v2_kernel(const TX* __restrict__ x, long ldx, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, float eps, TY* __restrict__ y, long ldy,
-                                                        float* __restrict__ mean, float* __restrict__ rstd, long M, int C) {
+                                                        float* __restrict__ mean, float* __restrict__ rstd, long M, int C, long pgs) {
   pdl_trigger();
+  if (gridDim.y > 1) {  // grouped launch: group g = rows [g*M, (g+1)*M) of the stacked tensors, parameters pgs elements apart
+    const long g = blockIdx.y;
+    x += g * M * ldx; y += g * M * ldy; gamma += g * pgs; beta += g * pgs;
+    if (mean) mean += g * M;
+    if (rstd) rstd += g * M;
+  }
   constexpr int RPW = 32 / G;
   const int lane = threadIdx.x & 31;
   const int lg = lane % G;
@@ -140,8 +146,19 @@ __global__ void __launch_bounds__(256, (J == 1 ? 3 : 2)) ln_bwd_v2_kernel(const 
                                                         const float* __restrict__ dres, long lddres, TDX* __restrict__ dx, long lddx,
                                                         bf16* __restrict__ dxbf, long lddxbf, const float* __restrict__ scale,
                                                         int rows_per_sample, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                                        float* __restrict__ dbias, long M, int C) {
+                                                        float* __restrict__ dbias, long M, int C, long pgs, long sgs) {
   pdl_trigger();
+  if (gridDim.y > 1) {  // grouped launch (see ln_fwd_v2_kernel); scale: sgs elements apart
+    const long g = blockIdx.y;
+    dy += g * M * lddy; x += g * M * ldx; mean += g * M; rstd += g * M; gamma += g * pgs;
+    if (dy2) dy2 += g * M * lddy2;
+    if (dres) dres += g * M * lddres;
+    if (dx) dx += g * M * lddx;
+    if (dxbf) dxbf += g * M * lddxbf;
+    if (scale) scale += g * sgs;
+    if (dgamma) { dgamma += g * pgs; dbeta += g * pgs; }
+    if (dbias) dbias += g * pgs;
+  }
   constexpr int RPW = 32 / G;
   __shared__ __align__(16) float sh_red[8][512];   // per-warp column partial sums (blockDim.x == 256)
   const int lane = threadIdx.x & 31;
@@ -261,18 +278,33 @@ static inline void ln_gj(int C, int& G, int& J) {
     else MACRO(32, 2);                            \
   } while (0)
 
+static size_t esz(int dtype) { return dtype == CMX_F32 ? 4 : 2; }
+
 CMX_API int cmx_layernorm_fwd(const void* x, int x_dtype, int64_t ldx, const float* gamma, const float* beta, float eps,
-                              void* y, int y_dtype, int64_t ldy, float* mean, float* rstd, int64_t M, int C, void* stream) {
+                              void* y, int y_dtype, int64_t ldy, float* mean, float* rstd, int64_t M, int C, int groups,
+                              int64_t param_gs, void* stream) {
   CMX_REQUIRE(C % 4 == 0 && C <= 4 * 32 * LN_MAXJ && C > 0, "layernorm: C=%d unsupported", C);
   CMX_REQUIRE(ldx % 4 == 0 && ldy % 4 == 0, "layernorm: ld must be a multiple of 4");
+  CMX_REQUIRE(groups >= 1 && groups <= 65535, "layernorm: groups=%d", groups);
   if (M == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
-  if (C % 8 == 0 && C <= 512 && ldx % 8 == 0 && ldy % 8 == 0) {
+  const bool vec = C % 8 == 0 && C <= 512 && ldx % 8 == 0 && ldy % 8 == 0 && (groups == 1 || param_gs % 4 == 0);
+  if (groups > 1 && !vec) {   // the scalar kernels are single-group: one launch per group
+    for (int g = 0; g < groups; g++) {
+      int rc = cmx_layernorm_fwd((const char*)x + (size_t)g * M * ldx * esz(x_dtype), x_dtype, ldx, gamma + g * param_gs, beta + g * param_gs,
+                                 eps, (char*)y + (size_t)g * M * ldy * esz(y_dtype), y_dtype, ldy, mean ? mean + g * M : nullptr,
+                                 rstd ? rstd + g * M : nullptr, M, C, 1, 0, stream);
+      if (rc) return rc;
+    }
+    return 0;
+  }
+  if (vec) {
     int G, J;
     ln_gj(C, G, J);
     const int rpb = 8 * (32 / G);
-    dim3 grid2(cdiv(M, rpb));
-#define LN_F2T(TX, TY, Gv, Jv) ln_fwd_v2_kernel<TX, TY, Gv, Jv><<<grid2, 256, 0, st>>>((const TX*)x, ldx, gamma, beta, eps, (TY*)y, ldy, mean, rstd, M, C)
+    dim3 grid2(cdiv(M, rpb), groups);
+    const long pgs = param_gs;
+#define LN_F2T(TX, TY, Gv, Jv) ln_fwd_v2_kernel<TX, TY, Gv, Jv><<<grid2, 256, 0, st>>>((const TX*)x, ldx, gamma, beta, eps, (TY*)y, ldy, mean, rstd, M, C, pgs)
 #define LN_F2(Gv, Jv)                                                                 \
   do {                                                                                \
     if (x_dtype == CMX_F32 && y_dtype == CMX_BF16) LN_F2T(float, bf16, Gv, Jv);       \
@@ -406,23 +438,41 @@ CMX_API int cmx_layernorm_bwd(const void* dy, int dy_dtype, int64_t lddy, const 
                               int x_dtype, int64_t ldx, const float* mean, const float* rstd, const float* gamma,
                               const float* dres, int64_t lddres, void* dx, int dx_dtype, int64_t lddx, void* dx_bf,
                               int64_t lddxbf, const float* scale, int rows_per_sample, float* dgamma, float* dbeta,
-                              float* dbias, int64_t M, int C, void* stream) {
+                              float* dbias, int64_t M, int C, int groups, int64_t param_gs, int64_t scale_gs, void* stream) {
   CMX_REQUIRE(C % 4 == 0 && C <= 4 * 32 * LN_MAXJ && C > 0, "layernorm_bwd: C=%d unsupported", C);
   CMX_REQUIRE((dgamma == nullptr) == (dbeta == nullptr), "layernorm_bwd: dgamma/dbeta must come together");
+  CMX_REQUIRE(groups >= 1 && groups <= 65535, "layernorm_bwd: groups=%d", groups);
   if (M == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   if (rows_per_sample <= 0) rows_per_sample = 1;
-  if (C % 8 == 0 && C <= 512 && lddy % 8 == 0 && ldx % 8 == 0 && (!dy2 || lddy2 % 8 == 0) && (!dres || lddres % 8 == 0) &&
-      (!dx || lddx % 8 == 0) && (!dx_bf || lddxbf % 8 == 0)) {
+  const bool vec = C % 8 == 0 && C <= 512 && lddy % 8 == 0 && ldx % 8 == 0 && (!dy2 || lddy2 % 8 == 0) && (!dres || lddres % 8 == 0) &&
+                   (!dx || lddx % 8 == 0) && (!dx_bf || lddxbf % 8 == 0) && (groups == 1 || param_gs % 4 == 0);
+  if (groups > 1 && !vec) {   // the scalar kernel is single-group: one launch per group
+    for (int g = 0; g < groups; g++) {
+      const size_t r = (size_t)g * M;
+      int rc = cmx_layernorm_bwd((const char*)dy + r * lddy * esz(dy_dtype), dy_dtype, lddy, dy2 ? (const char*)dy2 + r * lddy2 * 2 : nullptr,
+                                 lddy2, (const char*)x + r * ldx * esz(x_dtype), x_dtype, ldx, mean + r, rstd + r, gamma + g * param_gs,
+                                 dres ? dres + r * lddres : nullptr, lddres, dx ? (char*)dx + r * lddx * esz(dx_dtype) : nullptr, dx_dtype,
+                                 lddx, dx_bf ? (char*)dx_bf + r * lddxbf * 2 : nullptr, lddxbf, scale ? scale + g * scale_gs : nullptr,
+                                 rows_per_sample, dgamma ? dgamma + g * param_gs : nullptr, dbeta ? dbeta + g * param_gs : nullptr,
+                                 dbias ? dbias + g * param_gs : nullptr, M, C, 1, 0, 0, stream);
+      if (rc) return rc;
+    }
+    return 0;
+  }
+  if (vec) {
     int G, J;
     ln_gj(C, G, J);
-    int grid2 = cdiv(M, 8 * (32 / G));
-    const int resident = 148 * (J == 1 ? 3 : 2);  // one full wave of CTAs (see __launch_bounds__), grid-stride beyond
-    if (grid2 > resident) grid2 = resident;
+    int gx = cdiv(M, 8 * (32 / G));
+    const int resident = 148 * (J == 1 ? 3 : 2) / groups;  // one full wave of CTAs (see __launch_bounds__), grid-stride beyond
+    if (gx > resident) gx = resident;
+    if (gx < 1) gx = 1;
+    dim3 grid2(gx, groups);
+    const long pgs = param_gs, sgs = scale_gs;
 #define LN_B2T(TDY, TX, TDX, Gv, Jv)                                                                                            \
   ln_bwd_v2_kernel<TDY, TX, TDX, Gv, Jv><<<grid2, 256, 0, st>>>((const TDY*)dy, lddy, (const bf16*)dy2, lddy2, (const TX*)x, ldx, \
                                                                 mean, rstd, gamma, dres, lddres, (TDX*)dx, lddx, (bf16*)dx_bf,    \
-                                                                lddxbf, scale, rows_per_sample, dgamma, dbeta, dbias, M, C)
+                                                                lddxbf, scale, rows_per_sample, dgamma, dbeta, dbias, M, C, pgs, sgs)
 #define LN_B2(Gv, Jv)                                                            \
   do {                                                                           \
     switch (dy_dtype * 4 + x_dtype * 2 + dx_dtype) {                             \

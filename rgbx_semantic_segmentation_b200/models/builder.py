@@ -119,7 +119,8 @@ class EncoderDecoder(nn.Module):
                                             with_grad=False, focal=focal)
 
     def _criterion_spec(self):
-        """-> (ignore_index, None | (w_ce, w_focal, gamma, alpha)) for the criteria fused into the loss kernel (train.py:70-93):
+        """-> (ignore_index, None | (w_ce, w_focal, gamma, alpha) | ("dice", alpha, smooth)) for the criteria fused into the loss
+        kernels (train.py:70-93): DiceCELoss(alpha, ignore_index, 'mean') (utils/loss_opr.py:103-156) ·
         nn.CrossEntropyLoss(mean, ignore_index) · FocalLoss(ignore_label, gamma, alpha, 'mean') (utils/loss_opr.py:157-196, or
         this package's utils.loss_opr.FocalLoss) · the 'CE_Focal' tuple, combined as c0 + 0.2 * c1 (builder.py:246-247)."""
         def is_ce(c):
@@ -129,7 +130,16 @@ class EncoderDecoder(nn.Module):
         def is_focal(c):
             return type(c).__name__ == "FocalLoss" and all(hasattr(c, a) for a in ("ignore_label", "gamma", "alpha")) \
                 and getattr(c, "reduction", "mean") == 'mean'
+        def is_dice_ce(c):
+            # reference class: .alpha, .dice (DiceLoss: .smooth, .ignore_index, .reduction), .ce; this package's carrier: flat attributes
+            if type(c).__name__ != "DiceCELoss" or not hasattr(c, "alpha"):
+                return False
+            d = getattr(c, "dice", c)
+            return getattr(d, "reduction", "mean") == 'mean' and hasattr(d, "ignore_index")
         crit = self.criterion
+        if is_dice_ce(crit):
+            d = getattr(crit, "dice", crit)
+            return int(d.ignore_index), ("dice", float(crit.alpha), float(getattr(d, "smooth", 1e-6)))
         if is_ce(crit):
             return crit.ignore_index, None
         if is_focal(crit):
@@ -137,8 +147,8 @@ class EncoderDecoder(nn.Module):
         if isinstance(crit, tuple) and len(crit) == 2 and is_ce(crit[0]) and is_focal(crit[1]) \
                 and crit[0].ignore_index == int(crit[1].ignore_label):
             return crit[0].ignore_index, (1.0, 0.2, float(crit[1].gamma), float(crit[1].alpha))
-        raise NotImplementedError("cmx_b200 fuses nn.CrossEntropyLoss(reduction='mean', ignore_index=k), FocalLoss(mean) and the "
-                                  "(CrossEntropyLoss, FocalLoss) tuple only (train.py:70-93)")
+        raise NotImplementedError("cmx_b200 fuses nn.CrossEntropyLoss(reduction='mean', ignore_index=k), FocalLoss(mean), "
+                                  "DiceCELoss(mean) and the (CrossEntropyLoss, FocalLoss) tuple only (train.py:70-93)")
 
     # ---- engine plumbing ---------------------------------------------------------------------------
     def _eng(self):
@@ -169,6 +179,7 @@ class EncoderDecoder(nn.Module):
         key = ("eval", tuple(rgb.shape), self.training, rgb.device.index)
         if not self.use_cuda_graph or self.training:
             return self._eng().forward_logits(rgb, modal_x)
+        self._eng()._ensure_flat(rgb.device)  # parameters moved / re-created since the capture -> graphs were dropped
         g = self._graphs.get(key)
         if g is None:
             self._graphs[key] = {"warm": 1}
@@ -186,62 +197,76 @@ class EncoderDecoder(nn.Module):
         return g["out"].clone()
 
     def _run_step(self, rgb, modal_x, label):
-        """One fused forward+backward step.  The engine yields once, when the gradients of flat_g[:split_off] are final:
-        under FlatDataParallel their all-reduce starts there and overlaps the rest of the backward pass; with CUDA graphs
-        the step is therefore captured as TWO graphs sharing one memory pool (NCCL itself is never captured)."""
+        """One fused forward+backward step.  The engine generator yields at the points where something outside the kernel
+        stream has to happen: the SyncBatchNorm all-reduces of the decoder norm (train.py:64-67 passes nn.SyncBatchNorm in
+        every distributed run) and, under FlatDataParallel, the point where the gradients of flat_g[:split_off] are final
+        (their all-reduce starts there and overlaps the rest of the backward pass).  With CUDA graphs the step is captured
+        as one graph per segment between such points, all sharing one memory pool (NCCL itself is never captured)."""
         from ..parallel import allreduce_slice_async
         rgb, modal_x = rgb.float().contiguous(), modal_x.float().contiguous()
         ign, focal = self._criterion_spec()
         eng = self._eng()
-        key = ("train", tuple(rgb.shape), self.training, rgb.device.index, focal)
+        eng._ensure_flat(rgb.device)          # parameters moved / re-created since the capture -> graphs were dropped
+        eng.split_at_early = self._flat_dp is not None
+        key = ("train", tuple(rgb.shape), self.training, rgb.device.index, focal, ign, eng.stochastic, self._flat_dp is not None)
 
-        def finish(gen):
-            try:
-                next(gen)
-            except StopIteration as done:
-                return done.value
-            raise RuntimeError("cmx_b200: the engine yielded more than once")
+        def needs_host(ev):
+            return ev != "early_gradients_ready" or self._flat_dp is not None
+
+        def on_event(ev):
+            if ev == "early_gradients_ready":
+                allreduce_slice_async(self, eng.flat_g[:eng.split_off])
+            else:
+                eng.handle_event(ev)
 
         def eager(a, b, c):
             gen = eng.forward_loss_steps(a, b, c, ign, with_grad=True, focal=focal)
-            next(gen)
-            allreduce_slice_async(self, eng.flat_g[:eng.split_off])
-            loss = finish(gen)
+            try:
+                ev = next(gen)
+                while True:
+                    on_event(ev)
+                    ev = next(gen)
+            except StopIteration as done:
+                loss = done.value
             allreduce_slice_async(self, eng.flat_g[eng.split_off:])
             return loss
 
-        if not self.use_cuda_graph or eng.forced_dp is not None or eng.forced_dropout is not None:
+        if not self.use_cuda_graph or eng.forced_dp is not None or eng.forced_dropout is not None or eng.sync_hook is not None:
             return eager(rgb, modal_x, label)
         g = self._graphs.get(key)
         if g is None:
             self._graphs[key] = {"warm": 1}
             return eager(rgb, modal_x, label)
-        if "graph" not in g:
+        if "graphs" not in g:
             g["rgb"], g["x"], g["label"] = rgb.clone(), modal_x.clone(), label.to(torch.int64).clone()
-            split = self._flat_dp is not None
             torch.cuda.synchronize()
-            if not split:
-                graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(graph), eng.hp_main():
-                    g["loss"] = eng.forward_loss(g["rgb"], g["x"], g["label"], ign, with_grad=True, focal=focal)
-                g["graph"], g["graph2"] = graph, None
-            else:
-                pool = torch.cuda.graph_pool_handle()
-                ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-                with torch.cuda.graph(ga, pool=pool):
-                    gen = eng.forward_loss_steps(g["rgb"], g["x"], g["label"], ign, with_grad=True, focal=focal)
-                    next(gen)
-                with torch.cuda.graph(gb, pool=pool):
-                    g["loss"] = finish(gen)
-                g["graph"], g["graph2"] = ga, gb
+            pool = torch.cuda.graph_pool_handle()
+            graphs, events = [], []
+            gen = eng.forward_loss_steps(g["rgb"], g["x"], g["label"], ign, with_grad=True, focal=focal)
+            done = False
+            while not done:
+                gr = torch.cuda.CUDAGraph()
+                ev = None
+                with torch.cuda.graph(gr, pool=pool), eng.hp_main():
+                    try:
+                        ev = next(gen)
+                        while not needs_host(ev):
+                            ev = next(gen)
+                    except StopIteration as fin:
+                        g["loss"] = fin.value
+                        done = True
+                graphs.append(gr)
+                if not done:
+                    events.append(ev)   # keeps the event's tensor (graph-pool memory) referenced for the replays
+            g["graphs"], g["events"] = graphs, events
         g["rgb"].copy_(rgb)
         g["x"].copy_(modal_x)
         g["label"].copy_(label)
-        g["graph"].replay()
-        if g["graph2"] is not None:
-            allreduce_slice_async(self, eng.flat_g[:eng.split_off])
-            g["graph2"].replay()
-            allreduce_slice_async(self, eng.flat_g[eng.split_off:])
+        for i, gr in enumerate(g["graphs"]):
+            gr.replay()
+            if i < len(g["events"]):
+                on_event(g["events"][i])
+        allreduce_slice_async(self, eng.flat_g[eng.split_off:])
         return g["loss"].clone()
 
     def __getstate__(self):

@@ -64,6 +64,11 @@ def _call(name, *args, tag=None, flops=0, nbytes=0):
         raise RuntimeError("cmx_b200.%s failed (rc=%d): %s" % (name, rc, _lib.last_error()))
 
 
+def _tg(name, *dims):
+    """kernel-class tag of the per-launch profile; CMX_PROFILE_SHAPES=1 appends the problem size"""
+    return name + ("_" + "x".join(str(d) for d in dims) if PROFILE_SHAPES else "")
+
+
 def _nb(*ts):
     return sum(t.numel() * t.element_size() for t in ts if t is not None)
 
@@ -81,8 +86,9 @@ def _auto_split(M, N, K, want):
 
 def gemm_raw(A, B, C, M, N, K, lda, ldb, ldc, *, a_off=0, b_off=0, c_off=0, trans_a=False, trans_b=False, bias=None,
              residual=None, ldr=0, r_off=0, row_scale=None, rows_per_sample=0, act=ACT_NONE, alpha=1.0, split_k=1,
-             accumulate=False, batch=(1, 1), sA=(0, 0), sB=(0, 0), sC=(0, 0), impl=0):
-    """A, B, C (and residual) are base tensors; *_off are element offsets into them."""
+             accumulate=False, batch=(1, 1), sA=(0, 0), sB=(0, 0), sC=(0, 0), impl=0, s_bias=0, s_res=0, s_scale=0):
+    """A, B, C (and residual) are base tensors; *_off are element offsets into them.  s_bias / s_res / s_scale: element
+    strides of bias / residual / row_scale per batch[0] index (grouped launches: one batch index per modality branch)."""
     _cuda(A, B, C)
     assert A.dtype == torch.bfloat16 and B.dtype == torch.bfloat16
     g = CmxGemm()
@@ -107,6 +113,7 @@ def gemm_raw(A, B, C, M, N, K, lda, ldb, ldc, *, a_off=0, b_off=0, c_off=0, tran
     g.split_k = split_k
     g.rows_per_sample = rows_per_sample
     g.impl = impl
+    g.sBias1, g.sR1, g.sS1 = s_bias, s_res, s_scale
     nb = batch[0] * batch[1]
     which = "tc" if int(_lib.load().cmx_gemm_which(ctypes.byref(g))) == 2 else ("fb_batched" if nb > 1 else "fb")
     kind = "wgrad" if trans_a else ("dgrad" if trans_b and nb == 1 else "fwd")
@@ -120,25 +127,38 @@ def gemm_raw(A, B, C, M, N, K, lda, ldb, ldc, *, a_off=0, b_off=0, c_off=0, tran
 
 
 def mm(a, b, out, *, ta=False, tb=False, bias=None, residual=None, row_scale=None, rows_per_sample=0, act=ACT_NONE,
-       alpha=1.0, accumulate=False, split_k=None, impl=0):
+       alpha=1.0, accumulate=False, split_k=None, impl=0, groups=1, gs_a=None, gs_b=None, gs_c=None, gs_bias=0, gs_scale=0):
     """out[M,N] = residual + row_scale * act(alpha * op(a) @ op(b) + bias) on 2-D row-major views.
     ta=False: a is [M,K]; ta=True: a is stored [K,M].  tb=False: b is [N,K] (nn.Linear weight layout);
-    tb=True: b is stored [K,N].  accumulate=True adds into fp32 `out` (split-K chosen automatically)."""
-    if ta:
-        K, M = a.shape
-    else:
-        M, K = a.shape
-    if tb:
-        Kb, N = b.shape
-    else:
-        N, Kb = b.shape
-    assert K == Kb, (a.shape, b.shape, ta, tb)
-    assert tuple(out.shape) == (M, N), (out.shape, M, N)
+    tb=True: b is stored [K,N].  accumulate=True adds into fp32 `out` (split-K chosen automatically).
+    groups > 1: ONE launch over `groups` independent problems of the same shape (the RGB and X branches of a stage).  An
+    operand whose group stride gs_* (elements) is given is the group-0 view of a per-branch parameter (the same tensor of the
+    other branch lies gs_* elements further in the flat buffers); an operand without one is STACKED along its dim 0
+    ([groups * rows, cols]; residual like out).  bias / row_scale: group-0 views with strides gs_bias / gs_scale."""
+    def per_group(t, gs):
+        if groups == 1:
+            return t.shape, 0
+        if gs is not None:
+            return t.shape, gs
+        assert t.shape[0] % groups == 0, (t.shape, groups)
+        return (t.shape[0] // groups, t.shape[1]), (t.shape[0] // groups) * _ld(t)
+    (sa0, sa1), sA1 = per_group(a, gs_a)
+    (sb0, sb1), sB1 = per_group(b, gs_b)
+    (sc0, sc1), sC1 = per_group(out, gs_c)
+    K, M = (sa0, sa1) if ta else (sa1, sa0)
+    Kb, N = (sb0, sb1) if tb else (sb1, sb0)
+    assert K == Kb, (a.shape, b.shape, ta, tb, groups)
+    assert (sc0, sc1) == (M, N), (out.shape, M, N, groups)
     if split_k is None:
-        split_k = _auto_split(M, N, K, accumulate)
+        split_k = _auto_split(M * groups, N, K, accumulate)
+    s_res = 0
+    if residual is not None and groups > 1:
+        assert residual.shape == out.shape and gs_c is None
+        s_res = M * _ld(residual)
     return gemm_raw(a, b, out, M, N, K, _ld(a), _ld(b), _ld(out), trans_a=ta, trans_b=tb, bias=bias, residual=residual,
                     ldr=_ld(residual) if residual is not None else 0, row_scale=row_scale, rows_per_sample=rows_per_sample,
-                    act=act, alpha=alpha, split_k=split_k, accumulate=accumulate, impl=impl)
+                    act=act, alpha=alpha, split_k=split_k, accumulate=accumulate, impl=impl, batch=(groups, 1),
+                    sA=(sA1, 0), sB=(sB1, 0), sC=(sC1, 0), s_bias=gs_bias, s_res=s_res, s_scale=gs_scale)
 
 
 def gemm_which(M, N, K, lda, ldb, ldc, trans_a=False, trans_b=False, c_dtype=BF16, ptr=256):
@@ -152,23 +172,30 @@ def gemm_which(M, N, K, lda, ldb, ldc, trans_a=False, trans_b=False, c_dtype=BF1
 # ------------------------------------------------------------------------------------------------
 # normalisation
 # ------------------------------------------------------------------------------------------------
-def layernorm_fwd(x, gamma, beta, eps, y, mean=None, rstd=None):
+def layernorm_fwd(x, gamma, beta, eps, y, mean=None, rstd=None, groups=1, param_gs=0):
+    """groups > 1: x / y / mean / rstd are `groups` stacked blocks of rows; gamma / beta = group-0 views, param_gs apart"""
     M, C = x.shape
+    assert M % groups == 0
+    M //= groups
     _cuda(x, y)
     _call("cmx_layernorm_fwd", x.data_ptr(), _dt(x), _ld(x), gamma.data_ptr(), beta.data_ptr(), eps,
-                                             y.data_ptr(), _dt(y), _ld(y), _p(mean), _p(rstd), M, C, _stream(), nbytes=_nb(x, y))
+          y.data_ptr(), _dt(y), _ld(y), _p(mean), _p(rstd), M, C, groups, param_gs, _stream(),
+          tag=_tg("cmx_layernorm_fwd", M * groups, C), nbytes=_nb(x, y))
     return y
 
 
 def layernorm_bwd(dy, x, mean, rstd, gamma, *, dy2=None, dres=None, dx=None, dx_bf=None, scale=None, rows_per_sample=0,
-                  dgamma=None, dbeta=None, dbias=None):
+                  dgamma=None, dbeta=None, dbias=None, groups=1, param_gs=0, scale_gs=0):
     M, C = x.shape
-    _call("cmx_layernorm_bwd", 
+    assert M % groups == 0
+    M //= groups
+    _call("cmx_layernorm_bwd",
         dy.data_ptr(), _dt(dy), _ld(dy), _p(dy2), _ld(dy2) if dy2 is not None else 0, x.data_ptr(), _dt(x), _ld(x),
         mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(), _p(dres), _ld(dres) if dres is not None else 0,
         _p(dx), _dt(dx) if dx is not None else F32, _ld(dx) if dx is not None else 0,
         _p(dx_bf), _ld(dx_bf) if dx_bf is not None else 0, _p(scale), rows_per_sample,
-        _p(dgamma), _p(dbeta), _p(dbias), M, C, _stream(), nbytes=_nb(dy, dy2, x, dres, dx, dx_bf))
+        _p(dgamma), _p(dbeta), _p(dbias), M, C, groups, param_gs, scale_gs, _stream(),
+        tag=_tg("cmx_layernorm_bwd", M * groups, C), nbytes=_nb(dy, dy2, x, dres, dx, dx_bf))
 
 
 def colstats(x, sum_, sumsq):
@@ -196,34 +223,54 @@ def bn_apply(x, mean, invstd, gamma, beta, y, *, residual=None, relu=False, mask
     return y
 
 
+def _bn_bwd_common(dy, x, mean, invstd, gamma, beta, residual, relu, mask, rows_per_sample):
+    return (dy.data_ptr(), _dt(dy), _ld(dy), x.data_ptr(), _dt(x), _ld(x), mean.data_ptr(), invstd.data_ptr(),
+            gamma.data_ptr(), beta.data_ptr(), _p(residual), _dt(residual) if residual is not None else F32,
+            _ld(residual) if residual is not None else 0, int(relu), _p(mask), rows_per_sample)
+
+
+def bn_bwd_reduce(dy, x, mean, invstd, gamma, beta, ws, *, residual=None, relu=False, mask=None, rows_per_sample=0):
+    """pass 1: ws (zeroed double[2*C]) += [sum dy_eff, sum dy_eff * xhat] over the rows"""
+    M, C = x.shape
+    common = _bn_bwd_common(dy, x, mean, invstd, gamma, beta, residual, relu, mask, rows_per_sample)
+    _call("cmx_bn_bwd_reduce", *common, ws[:C].data_ptr(), ws[C:].data_ptr(), M, C, _stream(), nbytes=_nb(dy, x))
+
+
+def bn_bwd_apply(dy, x, mean, invstd, gamma, beta, dx, dgamma, dbeta, ws, *, residual=None, relu=False, mask=None,
+                 rows_per_sample=0, dres=None):
+    """pass 2: dx (and dres = effective upstream grad; same dtype) from the sums in ws; dgamma / dbeta += the sums"""
+    M, C = x.shape
+    common = _bn_bwd_common(dy, x, mean, invstd, gamma, beta, residual, relu, mask, rows_per_sample)
+    _call("cmx_bn_bwd_apply", *common, ws[:C].data_ptr(), ws[C:].data_ptr(), dx.data_ptr(), _dt(dx), _ld(dx), _p(dres),
+          _dt(dres) if dres is not None else _dt(dx), _ld(dres) if dres is not None else 0,
+          _p(dgamma), _p(dbeta), M, C, _stream(), nbytes=_nb(dy, x, dx, dres))
+
+
 def bn_bwd(dy, x, mean, invstd, gamma, beta, dx, dgamma, dbeta, ws, *, residual=None, relu=False, mask=None,
            rows_per_sample=0, dres=None):
     """ws: zeroed double[2*C] workspace.  dx (and dres = effective upstream grad) share a dtype."""
-    M, C = x.shape
-    s1, s2 = ws[:C], ws[C:]
-    common = (dy.data_ptr(), _dt(dy), _ld(dy), x.data_ptr(), _dt(x), _ld(x), mean.data_ptr(), invstd.data_ptr(),
-              gamma.data_ptr(), beta.data_ptr(), _p(residual), _dt(residual) if residual is not None else F32,
-              _ld(residual) if residual is not None else 0, int(relu), _p(mask), rows_per_sample)
-    _call("cmx_bn_bwd_reduce", *common, s1.data_ptr(), s2.data_ptr(), M, C, _stream(), nbytes=_nb(dy, x))
-    _call("cmx_bn_bwd_apply", *common, s1.data_ptr(), s2.data_ptr(), dx.data_ptr(), _dt(dx), _ld(dx), _p(dres),
-          _dt(dres) if dres is not None else _dt(dx), _ld(dres) if dres is not None else 0,
-          _p(dgamma), _p(dbeta), M, C, _stream(), nbytes=_nb(dy, x, dx, dres))
+    kw = dict(residual=residual, relu=relu, mask=mask, rows_per_sample=rows_per_sample)
+    bn_bwd_reduce(dy, x, mean, invstd, gamma, beta, ws, **kw)
+    bn_bwd_apply(dy, x, mean, invstd, gamma, beta, dx, dgamma, dbeta, ws, dres=dres, **kw)
 
 
 # ------------------------------------------------------------------------------------------------
 # depthwise conv
 # ------------------------------------------------------------------------------------------------
-def dwconv3x3_fwd(x, w, bias, act, y, B, H, W, flip=False, ysum=None):
+def dwconv3x3_fwd(x, w, bias, act, y, B, H, W, flip=False, ysum=None, groups=1, param_gs=0):
+    """groups > 1: x / y are `groups` stacked blocks of B samples; w / bias / ysum = group-0 views, param_gs elements apart"""
     C = x.shape[1]
     _call("cmx_dwconv3x3_fwd", x.data_ptr(), _ld(x), w.data_ptr(), _p(bias), act, int(flip), y.data_ptr(), _ld(y), _p(ysum),
-                                             B, H, W, C, _stream(), tag="cmx_dwconv3x3_%s" % ("dgrad" if flip else "fwd"), nbytes=_nb(x, y))
+          B, H, W, C, groups, param_gs, _stream(),
+          tag=_tg("cmx_dwconv3x3_%s" % ("dgrad" if flip else "fwd"), groups * B * H * W, C), nbytes=_nb(x, y))
     return y
 
 
-def dwconv3x3_bwd_pre(x, w, bias, act, dy, du, dw, db, B, H, W):
+def dwconv3x3_bwd_pre(x, w, bias, act, dy, du, dw, db, B, H, W, groups=1, param_gs=0):
     C = x.shape[1]
     _call("cmx_dwconv3x3_bwd_pre", x.data_ptr(), _ld(x), w.data_ptr(), _p(bias), act, dy.data_ptr(), _ld(dy),
-                                                 du.data_ptr(), _ld(du), dw.data_ptr(), _p(db), B, H, W, C, _stream(), nbytes=_nb(x, dy, du))
+          du.data_ptr(), _ld(du), dw.data_ptr(), _p(db), B, H, W, C, groups, param_gs, _stream(),
+          tag=_tg("cmx_dwconv3x3_bwd_pre", groups * B * H * W, C), nbytes=_nb(x, dy, du))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -280,9 +327,13 @@ def cast_bf16_f32(x, y):
     return y
 
 
-def colsum(x, out):
+def colsum(x, out, groups=1, out_gs=0):
+    """out[n] += sum_m x[m, n]; groups > 1: x = `groups` stacked row blocks, out of group g lies g * out_gs elements further"""
     M, N = x.shape
-    _call("cmx_colsum", x.data_ptr(), _dt(x), _ld(x), out.data_ptr(), M, N, _stream(), nbytes=_nb(x))
+    assert M % groups == 0
+    M //= groups
+    _call("cmx_colsum", x.data_ptr(), _dt(x), _ld(x), out.data_ptr(), M, N, groups, out_gs, _stream(),
+          tag=_tg("cmx_colsum", M * groups, N), nbytes=_nb(x))
 
 
 def relu_bwd_(dy, y):
@@ -306,7 +357,7 @@ def attn_fwd(q, kv, o, B, N, Nk, heads, scale, p_out=None, lse=None):
     """q [B*N, C], kv [B*Nk, 2C], o [B*N, C] (bf16, head_dim 64); p_out: bf16 view [B*heads*N, Nk] with padded ld"""
     _cuda(q, kv, o)
     _call("cmx_attn_fwd", q.data_ptr(), _ld(q), kv.data_ptr(), _ld(kv), o.data_ptr(), _ld(o), _p(p_out),
-          _ld(p_out) if p_out is not None else 0, _p(lse), B, N, Nk, heads, scale, _stream(),
+          _ld(p_out) if p_out is not None else 0, _p(lse), B, N, Nk, heads, scale, _stream(), tag=_tg("cmx_attn_fwd", B, N, Nk, heads),
           flops=4 * B * heads * N * Nk * 64, nbytes=_nb(q, kv, o) + (B * heads * N * Nk * 2 if p_out is not None else 0))
     return o
 
@@ -315,7 +366,7 @@ def attn_bwd(d_o, kv, p, ds, dq, B, N, Nk, heads, scale):
     """d_o [B*N, C], kv [B*Nk, 2C], p / ds: bf16 views [B*heads*N, Nk] (padded ld), dq [B*N, C]"""
     _cuda(d_o, kv, p, ds, dq)
     _call("cmx_attn_bwd", d_o.data_ptr(), _ld(d_o), kv.data_ptr(), _ld(kv), p.data_ptr(), _ld(p), ds.data_ptr(), _ld(ds),
-          dq.data_ptr(), _ld(dq), B, N, Nk, heads, scale, _stream(),
+          dq.data_ptr(), _ld(dq), B, N, Nk, heads, scale, _stream(), tag=_tg("cmx_attn_bwd", B, N, Nk, heads),
           flops=4 * B * heads * N * Nk * 64, nbytes=_nb(d_o, kv, dq) + 2 * (B * heads * N * Nk * 2))
     return dq
 
@@ -473,6 +524,29 @@ def ce_focal_upsampled(logits, label, ignore_index, acc, dlogits, B, h, w, H, W,
           B, h, w, H, W, ncls, float(w_ce), float(w_focal), float(gamma), float(alpha), _stream())
 
 
+def dice_ce_stats(logits, label, ignore_index, acc, dstats, B, h, w, H, W, ncls):
+    """DiceCELoss pass 0 (utils/loss_opr.py:103-156): acc (double[2]) += (CE sum, valid count); dstats (double[B, 3, ncls]) +=
+    per (sample, class) (sum p, sum p * onehot, sum onehot) over the valid pixels of the upsampled logits"""
+    assert label.dtype == torch.int64 and label.is_contiguous()
+    assert logits.dtype == torch.float32 and tuple(logits.shape) == (B * h * w, ncls)
+    assert dstats.dtype == torch.float64 and dstats.numel() == B * 3 * ncls
+    _call("cmx_dice_ce_stats", logits.data_ptr(), _ld(logits), label.data_ptr(), ignore_index, acc.data_ptr(), dstats.data_ptr(),
+          B, h, w, H, W, ncls, _stream())
+
+
+def dice_ce_finalize(acc, dstats, B, ncls, alpha, smooth, loss=None, coef=None):
+    """loss = alpha * (1 - mean dice) + (1 - alpha) * CE; coef (float[B*2*ncls + 1]) = gradient coefficients for pass 1"""
+    assert coef is None or (coef.dtype == torch.float32 and coef.numel() == B * 2 * ncls + 1)
+    _call("cmx_dice_ce_finalize", acc.data_ptr(), dstats.data_ptr(), B, ncls, float(alpha), float(smooth), _p(loss), _p(coef), _stream())
+
+
+def dice_ce_grad(logits, label, ignore_index, coef, dlogits, B, h, w, H, W, ncls):
+    """DiceCELoss pass 1: dlogits (fp32, zeroed, same row stride as logits) += d loss / d logits (final scale)"""
+    assert dlogits.dtype == torch.float32 and dlogits.shape == logits.shape and _ld(dlogits) == _ld(logits)
+    _call("cmx_dice_ce_grad", logits.data_ptr(), _ld(logits), label.data_ptr(), ignore_index, coef.data_ptr(), dlogits.data_ptr(),
+          B, h, w, H, W, ncls, _stream())
+
+
 def ce_finalize(acc, loss, dlogits=None, gscale=None, out=None):
     n = dlogits.numel() if dlogits is not None else 0
     _call("cmx_ce_finalize", acc.data_ptr(), _p(loss), _p(dlogits), _p(gscale), _p(out),
@@ -496,9 +570,37 @@ def confusion(pred, gt, n_cl, hist, stats):
 
 
 def argmax_confusion(scores, gt, n_cl, hist, stats, pred_out=None):
-    """scores: [n_cl, H, W] fp32 contiguous (one image); gt may be None (argmax only)."""
+    """scores: [n_cl, H, W] fp32 or fp64 contiguous (one image); gt may be None (argmax only)."""
     _cuda(scores)
-    assert scores.is_contiguous() and scores.dtype == torch.float32 and scores.shape[0] == n_cl
+    assert scores.is_contiguous() and scores.dtype in (torch.float32, torch.float64) and scores.shape[0] == n_cl
     npix = scores[0].numel()
-    _call("cmx_argmax_confusion", scores.data_ptr(), _p(gt), _INT_TAG[gt.dtype] if gt is not None else 0, npix, n_cl,
-                                                _p(pred_out), _p(hist), _p(stats), _stream())
+    _call("cmx_argmax_confusion", scores.data_ptr(), int(scores.dtype == torch.float64), _p(gt),
+          _INT_TAG[gt.dtype] if gt is not None else 0, npix, n_cl, _p(pred_out), _p(hist), _p(stats), _stream())
+
+
+def eval_pack_crop(img_u8, pad, win, out_off, mean, std, flip, out):
+    """one normalised network crop out [ch, crop_h, crop_w] fp32 from a device uint8 image [rows, cols(, 3)] (include/cmx_b200.h:
+    cmx_eval_pack_crop).  pad = (pad_top, pad_left) of the zero-padded raw canvas, win = (s_y, s_x, win_h, win_w) in canvas
+    coordinates, out_off = (top, left) zero margin inside the crop, mean / std: 3 python floats (float64 arithmetic)"""
+    _cuda(img_u8, out)
+    assert img_u8.dtype == torch.uint8 and img_u8.is_contiguous() and out.dtype == torch.float32 and out.is_contiguous()
+    rows, cols = img_u8.shape[:2]
+    ch = 1 if img_u8.dim() == 2 else img_u8.shape[2]
+    assert out.shape[0] == ch
+    _call("cmx_eval_pack_crop", img_u8.data_ptr(), rows, cols, ch, pad[0], pad[1], win[0], win[1], win[2], win[3], out_off[0], out_off[1],
+          mean[0], mean[1], mean[2], std[0], std[1], std[2], int(flip), out.data_ptr(), out.shape[1], out.shape[2], _stream(),
+          nbytes=_nb(out))
+    return out
+
+
+def eval_accumulate_scale(logits, logits_flip, tiles, margin, rows, cols, processed):
+    """processed[ncls, H, W] (fp64) += bilinear resize of one scale's score map (exp of the tile logits summed on the canvas,
+    margins sliced off): logits [n, ncls, ch, cw] fp32, tiles: int32 device table [n_tiles, 8] of CmxEvalTile records"""
+    _cuda(logits, tiles, processed)
+    assert logits.dtype == torch.float32 and logits.is_contiguous() and processed.dtype == torch.float64 and processed.is_contiguous()
+    assert tiles.dtype == torch.int32 and tiles.dim() == 2 and tiles.shape[1] == 8 and tiles.is_contiguous()
+    assert logits_flip is None or (logits_flip.shape == logits.shape and logits_flip.is_contiguous())
+    n, ncls, ch, cw = logits.shape
+    _call("cmx_eval_accumulate_scale", logits.data_ptr(), _p(logits_flip), ch, cw, ncls, tiles.data_ptr(), tiles.shape[0], margin[0], margin[1],
+          rows, cols, processed.data_ptr(), processed.shape[1], processed.shape[2], _stream(), nbytes=_nb(processed) * 2)
+    return processed

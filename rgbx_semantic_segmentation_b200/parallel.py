@@ -14,19 +14,39 @@ import torch.nn as nn
 
 
 class FlatDataParallel(nn.Module):
-    def __init__(self, module, process_group=None):
+    """DistributedDataParallel semantics (train.py:145-146) on the engine's flat gradient buffer: parameters and buffers
+    are broadcast from rank 0 at construction, the floating-point buffers (BatchNorm running statistics) again before every
+    training forward (DDP's broadcast_buffers=True: with per-rank FFM BatchNorm statistics the ranks would otherwise drift
+    apart), and the gradients are averaged over the ranks every step.  An nn.SyncBatchNorm decoder norm (what the
+    reference's train.py passes whenever it runs distributed) is synchronised by the engine itself."""
+
+    def __init__(self, module, process_group=None, broadcast_buffers=True):
         super().__init__()
         if not dist.is_initialized():
             raise RuntimeError("FlatDataParallel needs an initialised torch.distributed process group")
         self.module = module
         self.process_group = process_group
         self.world_size = dist.get_world_size(process_group)
+        self.broadcast_buffers = broadcast_buffers
+        self._src = dist.get_global_rank(process_group, 0) if process_group is not None else 0
         with torch.no_grad():
             for t in list(module.parameters()) + list(module.buffers()):
-                dist.broadcast(t.data, src=0, group=process_group)
+                dist.broadcast(t.data, src=self._src, group=process_group)
+        self._fbufs = [b for b in module.buffers() if b.is_floating_point()]
         module._flat_dp = (process_group, self.world_size)
 
+    def _sync_buffers(self):
+        """one coalesced broadcast of the floating-point buffers from rank 0 (3 launches + one small NCCL broadcast)"""
+        if not self._fbufs or self.world_size == 1:
+            return
+        with torch.no_grad():
+            flat = torch.cat([b.reshape(-1) for b in self._fbufs])
+            dist.broadcast(flat, src=self._src, group=self.process_group)
+            torch._foreach_copy_(self._fbufs, [v.view_as(b) for v, b in zip(flat.split([b.numel() for b in self._fbufs]), self._fbufs)])
+
     def forward(self, *args, **kwargs):
+        if self.broadcast_buffers and self.module.training and torch.is_grad_enabled():
+            self._sync_buffers()
         return self.module(*args, **kwargs)
 
 

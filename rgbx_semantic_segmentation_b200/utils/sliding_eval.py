@@ -142,109 +142,110 @@ def sliding_eval_rgbX_batched(evaluator, img, modal_x, crop_size, stride_rate, d
     return processed.argmax(2)
 
 
-def _normalize_dev(u8, mean, std):
-    """utils/transforms.py:182-187 on the device: float64 (x/255 - mean)/std, then the float32 cast the reference applies in
-    val_func_process_rgbX (evaluator.py:375) - IEEE double arithmetic, so bit-identical to the numpy result."""
-    x = u8.to(torch.float64) / 255.0
-    return ((x - mean) / std).to(torch.float32)
-
-
-def sliding_eval_rgbX_gpu(evaluator, img, modal_x, crop_size, stride_rate, device=None, max_batch=8, return_device=False):
-    """Device-resident variant of `sliding_eval_rgbX_batched`: only the uint8 `cv2.resize` of the two
-    inputs per scale stays on the host (its fixed-point arithmetic defines the reference's inputs).  The resized uint8
-    images are uploaded once per scale; normalisation (float64, bit-identical), padding, tiling, flip-TTA, exp, tile
-    accumulation, the bilinear resize of each scale's score map back to the original size, the float64 sum over scales and
-    the argmax all run on the device; one [H, W] int64 map comes back (or stays on the device with return_device=True,
-    ready for `utils.metric` / cmx_argmax_confusion).
-    Difference to the reference: the score-map resize is `F.interpolate(bilinear, align_corners=False)` instead of
-    `cv2.resize(INTER_LINEAR)` on float32 - the same sampling positions and weights, results equal to ~5e-7 - so the
-    prediction can differ only where two class scores tie to that precision."""
-    import torch.nn.functional as F
+def sliding_eval_rgbX_gpu(evaluator, img, modal_x, crop_size, stride_rate, device=None, max_batch=8, return_device=False, gt=None):
+    """Device-resident variant of `sliding_eval_rgbX_batched` on the library's own kernels: only the uint8
+    `cv2.resize` of the two inputs per scale stays on the host (its fixed-point arithmetic defines the reference's inputs).
+    Per scale the resized uint8 images are uploaded once; `cmx_eval_pack_crop` builds every network crop (float64
+    normalisation - bit-identical to utils/transforms.py:182-187 -, zero padding of the raw canvas and of the normalised crop,
+    tile cut with the reference's index arithmetic, flip-TTA mirror); the model runs once over all crops;
+    `cmx_eval_accumulate_scale` does exp, the tile sum, the margin slice, the bilinear resize to the original size and the
+    fp64 sum over scales in one pass per scale; `cmx_argmax_confusion` takes the argmax (and, when `gt` is given, the
+    confusion matrix of utils/metric.py:8-15) on the device.
+    Returns the [H, W] int64 prediction map (host ndarray, or a uint8 device tensor with return_device=True); with `gt`
+    (uint8 / int64 ndarray or device tensor) returns (pred, hist[n, n] int64 ndarray, labeled, correct).
+    Difference to the reference: the score-map resize evaluates cv2.INTER_LINEAR's sampling positions and weights in fp32 on
+    the device instead of inside cv2 (rounding differs by ~1 ulp), so the prediction can differ only where two class scores
+    tie to ~1e-6 relative - the tie rule the tests state."""
+    from .. import ops
     if cv2 is None:
         raise RuntimeError("sliding_eval_rgbX_gpu needs OpenCV (cv2) for the uint8 input resize, like the reference evaluator")
     crop = _to_2tuple(crop_size)
     dev = torch.device("cuda" if device is None else device) if not isinstance(device, torch.device) else device
     ori_rows, ori_cols = img.shape[:2]
     ncls = evaluator.class_num
-    mean = torch.as_tensor(np.asarray(evaluator.norm_mean, np.float64), device=dev)
-    std = torch.as_tensor(np.asarray(evaluator.norm_std, np.float64), device=dev)
     grey = modal_x.ndim == 2
-
-    def norm_pair(a_u8, b_u8):       # HWC (or HW) uint8 device tensors -> CHW float32
-        a = _normalize_dev(a_u8, mean, std).permute(2, 0, 1)
-        b = _normalize_dev(b_u8, 0.0, 1.0)[None] if grey else _normalize_dev(b_u8, mean, std).permute(2, 0, 1)
-        return a, b
-
-    def pad_to(t, m):                # CHW, zero padding (top, bottom, left, right)
-        return F.pad(t, (m[2], m[3], m[0], m[1])) if any(m) else t
-
-    crops_a, crops_b, plan = [], [], []
+    mean = [float(v) for v in np.asarray(evaluator.norm_mean, np.float64)]
+    std = [float(v) for v in np.asarray(evaluator.norm_std, np.float64)]
+    xmean, xstd = ([0.0] * 3, [1.0] * 3) if grey else (mean, std)
+    # ---- plan (host integers only): per scale the uploaded uint8 pair, its crops and its tile table
+    scales, n_crops = [], 0
     for s in evaluator.multi_scales:
         img_s = cv2.resize(img, None, fx=s, fy=s, interpolation=cv2.INTER_LINEAR)
         mx_s = cv2.resize(modal_x, None, fx=s, fy=s, interpolation=cv2.INTER_NEAREST if grey else cv2.INTER_LINEAR)
         rows, cols = img_s.shape[:2]
-        a_u8 = torch.from_numpy(np.ascontiguousarray(img_s)).to(dev, non_blocking=True)
-        b_u8 = torch.from_numpy(np.ascontiguousarray(mx_s)).to(dev, non_blocking=True)
+        sc = dict(a=torch.from_numpy(np.ascontiguousarray(img_s)).to(dev, non_blocking=True),
+                  b=torch.from_numpy(np.ascontiguousarray(mx_s)).to(dev, non_blocking=True), rows=rows, cols=cols, crops=[], tiles=[])
         margin = _pad_margin((rows, cols), crop)
+        sc["margin"] = margin
         if cols <= crop[1] or rows <= crop[0]:
-            # process_image_rgbX: normalise, THEN zero-pad (evaluator.py:409-415)
-            a, b = norm_pair(a_u8, b_u8)
-            plan.append(dict(whole=len(crops_a), margin=margin))
-            crops_a.append(pad_to(a, margin)); crops_b.append(pad_to(b, margin))
-            continue
-        # scale_process_rgbX: the RAW image is zero-padded (black), tiles are cut, then normalised (evaluator.py:337-360)
-        stride = (int(np.ceil(crop[0] * stride_rate)), int(np.ceil(crop[1] * stride_rate)))
-        a_pad = F.pad(a_u8, (0, 0, margin[2], margin[3], margin[0], margin[1]))
-        b_pad = F.pad(b_u8, ((margin[2], margin[3], margin[0], margin[1]) if grey else (0, 0, margin[2], margin[3], margin[0], margin[1])))
-        a_n, b_n = norm_pair(a_pad, b_pad)
-        pad_rows, pad_cols = a_pad.shape[:2]
-        r_grid = int(np.ceil((pad_rows - crop[0]) / stride[0])) + 1
-        c_grid = int(np.ceil((pad_cols - crop[1]) / stride[1])) + 1
-        tiles = []
-        for gy in range(r_grid):
-            for gx in range(c_grid):
-                s_x = gx * stride[0]           # evaluator.py:347-352 verbatim (x/y swap included)
-                s_y = gy * stride[1]
-                e_x = min(s_x + crop[0], pad_cols)
-                e_y = min(s_y + crop[1], pad_rows)
-                s_x = e_x - crop[0]
-                s_y = e_y - crop[1]
-                ta, tb = a_n[:, s_y:e_y, s_x:e_x], b_n[:, s_y:e_y, s_x:e_x]
-                tm = _pad_margin(ta.shape[1:], crop)
-                tiles.append((len(crops_a), s_y, e_y, s_x, e_x, tm))
-                crops_a.append(pad_to(ta, tm)); crops_b.append(pad_to(tb, tm))
-        plan.append(dict(tiles=tiles, margin=margin, pad=(pad_rows, pad_cols)))
-    groups = {}
-    for i, c in enumerate(crops_a):
-        groups.setdefault(tuple(c.shape), []).append(i)
-    scores = [None] * len(crops_a)
+            # process_image_rgbX on the whole image: normalise, THEN zero-pad (evaluator.py:409-415)
+            if rows > crop[0] or cols > crop[1]:
+                raise NotImplementedError("sliding_eval_rgbX_gpu: image side larger than the crop on one axis only; use sliding_eval_rgbX_batched")
+            sc["crops"].append(dict(pad=(0, 0), win=(0, 0, rows, cols), out=(margin[0], margin[2])))
+            sc["tiles"].append((n_crops, 0, 0, crop[0], crop[1], 0, 0))
+            sc["canvas_margin"] = (margin[0], margin[2])
+            n_crops += 1
+        else:
+            # scale_process_rgbX: the RAW image is zero-padded (black), tiles are cut, then normalised (evaluator.py:337-360)
+            stride = (int(np.ceil(crop[0] * stride_rate)), int(np.ceil(crop[1] * stride_rate)))
+            pad_rows, pad_cols = rows + margin[0] + margin[1], cols + margin[2] + margin[3]
+            r_grid = int(np.ceil((pad_rows - crop[0]) / stride[0])) + 1
+            c_grid = int(np.ceil((pad_cols - crop[1]) / stride[1])) + 1
+            for gy in range(r_grid):
+                for gx in range(c_grid):
+                    s_x = gx * stride[0]           # evaluator.py:347-352 verbatim (x/y swap included)
+                    s_y = gy * stride[1]
+                    e_x = min(s_x + crop[0], pad_cols)
+                    e_y = min(s_y + crop[1], pad_rows)
+                    s_x = e_x - crop[0]
+                    s_y = e_y - crop[1]
+                    # the reference slices numpy arrays with these numbers: negative starts wrap, stops clamp
+                    ys, ye, _ = slice(s_y, e_y).indices(pad_rows)
+                    xs, xe, _ = slice(s_x, e_x).indices(pad_cols)
+                    wh, ww = max(ye - ys, 0), max(xe - xs, 0)
+                    if wh > crop[0] or ww > crop[1] or wh == 0 or ww == 0:
+                        raise NotImplementedError("sliding_eval_rgbX_gpu: the reference's tile window (%d x %d) does not fit the crop "
+                                                  "%s for this image size; use sliding_eval_rgbX_batched" % (wh, ww, crop))
+                    tm = _pad_margin((wh, ww), crop)
+                    sc["crops"].append(dict(pad=(margin[0], margin[2]), win=(ys, xs, wh, ww), out=(tm[0], tm[2])))
+                    sc["tiles"].append((n_crops, ys, xs, ye, xe, tm[0], tm[2]))
+                    n_crops += 1
+            sc["canvas_margin"] = (margin[0], margin[2])
+        scales.append(sc)
+    # ---- network inputs: every crop written straight into its slot of the batch tensors
+    xch = 1 if grey else 3
+    A = torch.empty(n_crops, 3, crop[0], crop[1], device=dev)
+    Bx = torch.empty(n_crops, xch, crop[0], crop[1], device=dev)
+    flips = (0, 1) if evaluator.is_flip else (0,)
+    Af = torch.empty_like(A) if evaluator.is_flip else None
+    Bf = torch.empty_like(Bx) if evaluator.is_flip else None
+    i = 0
+    for sc in scales:
+        for c in sc["crops"]:
+            for fl in flips:
+                ops.eval_pack_crop(sc["a"], c["pad"], c["win"], c["out"], mean, std, fl, (Af if fl else A)[i])
+                ops.eval_pack_crop(sc["b"], c["pad"], c["win"], c["out"], xmean, xstd, fl, (Bf if fl else Bx)[i])
+            i += 1
     net = evaluator.val_func
     net.eval()
     with torch.no_grad():
-        for idxs in groups.values():
-            for k in range(0, len(idxs), max_batch):
-                sel = idxs[k:k + max_batch]
-                a = torch.stack([crops_a[i] for i in sel]).contiguous()
-                b = torch.stack([crops_b[i] for i in sel]).contiguous()
-                sc = net(a, b)
-                if evaluator.is_flip:
-                    sc = sc + net(a.flip(-1), b.flip(-1)).flip(-1)
-                sc = torch.exp(sc)
-                for j, i in enumerate(sel):
-                    scores[i] = sc[j]
-        processed = torch.zeros(ncls, ori_rows, ori_cols, dtype=torch.float64, device=dev)
-        for pl in plan:
-            m = pl["margin"]
-            if "whole" in pl:
-                score = scores[pl["whole"]]
-            else:
-                score = torch.zeros(ncls, pl["pad"][0], pl["pad"][1], device=dev)
-                for i, s_y, e_y, s_x, e_x, tm in pl["tiles"]:
-                    t = scores[i]
-                    score[:, s_y:e_y, s_x:e_x] += t[:, tm[0]:(t.shape[1] - tm[1]), tm[2]:(t.shape[2] - tm[3])]
-            score = score[:, m[0]:(score.shape[1] - m[1]), m[2]:(score.shape[2] - m[3])]
-            if tuple(score.shape[1:]) != (ori_rows, ori_cols):
-                score = F.interpolate(score[None].float(), size=(ori_rows, ori_cols), mode="bilinear", align_corners=False)[0]
-            processed += score.double()
-        pred = processed.argmax(0)
-    return pred if return_device else pred.cpu().numpy()
+        def run(a, b):
+            if n_crops <= max_batch:
+                return net(a, b)
+            return torch.cat([net(a[k:k + max_batch], b[k:k + max_batch]) for k in range(0, n_crops, max_batch)])
+        logits = run(A, Bx).contiguous()
+        logits_f = run(Af, Bf).contiguous() if evaluator.is_flip else None
+    processed = torch.zeros(ncls, ori_rows, ori_cols, dtype=torch.float64, device=dev)
+    for sc in scales:
+        table = torch.tensor([list(t) + [0] for t in sc["tiles"]], dtype=torch.int32).to(dev, non_blocking=True)
+        ops.eval_accumulate_scale(logits, logits_f, table, sc["canvas_margin"], sc["rows"], sc["cols"], processed)
+    pred = torch.empty(ori_rows, ori_cols, dtype=torch.uint8, device=dev)
+    if gt is None:
+        ops.argmax_confusion(processed, None, ncls, None, None, pred_out=pred)
+        return pred if return_device else pred.cpu().numpy().astype(np.int64)
+    gt_dev = (torch.from_numpy(np.ascontiguousarray(gt)) if isinstance(gt, np.ndarray) else gt).to(dev)
+    hist = torch.zeros(ncls, ncls, dtype=torch.int64, device=dev)
+    stats = torch.zeros(2, dtype=torch.int64, device=dev)
+    ops.argmax_confusion(processed, gt_dev, ncls, hist, stats, pred_out=pred)
+    st = stats.cpu()
+    return (pred if return_device else pred.cpu().numpy().astype(np.int64)), hist.cpu().numpy(), int(st[0]), int(st[1])

@@ -69,9 +69,9 @@ def disable_stochastic(m):
     m.decode_head.dropout.p = 0.0
 
 
-def case(name, backbone, num_classes, B, H, W, sub=1, stochastic=False):
+def case(name, backbone, num_classes, B, H, W, sub=1, stochastic=False, ctx_gain=1.0):
     spec = cmx_ref.MIT_SPECS[backbone]
-    sd = synth_state_dict(spec, num_classes, seed=0)
+    sd = synth_state_dict(spec, num_classes, seed=0, ctx_gain=ctx_gain)
     rgb, x, gt = synth_inputs(B, H, W, num_classes, seed=1)
     out = {}
 
@@ -179,6 +179,14 @@ def metric_cases():
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "b4_pst900":
+        # BASELINE.json configs[3] shape: MiT-B4, PST900 native 720x1280, 5 classes, batch 1 (about 20 GB of host memory and
+        # a few minutes of CPU time for the fp32 reference; kept out of the default run for that reason)
+        # ctx_gain 0.1 like the full-size MiT-B2 test: with unit-variance synthetic kv weights the FFM context logits (a sum over
+        # N = 57 600 tokens) have std ~400, the dim=-2 softmax is one-hot and ANY bf16 forward - the reference under autocast
+        # included - gives O(1) gradient noise; real initialisation (trunc_normal std 0.02) is in the unsaturated regime
+        case("b4_pst900", "mit_b4", 5, 1, 720, 1280, sub=16, ctx_gain=0.1)
+        sys.exit(0)
     metric_cases()
     case("b2_small", "mit_b2", 9, 2, 64, 96)
     case("b2_small_stochastic", "mit_b2", 9, 2, 64, 96, stochastic=True)

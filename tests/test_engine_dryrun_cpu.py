@@ -57,8 +57,8 @@ def mock_lib(monkeypatch):
     monkeypatch.setattr(ops, "_cuda", lambda *ts: None)
     monkeypatch.setattr(ops, "_stream", lambda: 0)
     # CUDA streams do not exist on CPU: single-stream orchestration (the stream fork/join helpers are no-ops when disabled)
-    monkeypatch.setenv("CMX_DUAL_STREAM", "0")
     monkeypatch.setenv("CMX_WGRAD_STREAM", "0")
+    monkeypatch.setenv("CMX_FFM_STREAM", "0")
     return calls
 
 
@@ -82,7 +82,7 @@ def test_training_step_orchestration(mock_lib, monkeypatch, recompute):
     assert loss.numel() == 1 and loss.dtype == torch.float32
     assert eng.flat_g.shape == eng.flat_p.shape and 0 < eng.split_off < eng.flat_g.numel()
     c = mock_lib
-    n_attn = 2 * sum(m.backbone.depths)                      # RGB + X blocks
+    n_attn = sum(m.backbone.depths)                          # one grouped launch per (RGB block, X twin) pair
     assert c["cmx_attn_fwd"] == n_attn
     assert c["cmx_layernorm_fwd"] == c["cmx_layernorm_bwd"] and c["cmx_dwconv3x3_fwd"] == 2 * c["cmx_dwconv3x3_bwd_pre"]
     assert c["cmx_ce_upsampled_fwd_bwd"] == 1 and c["cmx_upsample_sum_fwd"] == 1 and c["cmx_upsample_bwd_multi"] == 1
@@ -101,7 +101,7 @@ def test_recompute_mode_drops_the_probability_tensors_and_two_gemms_per_block(mo
         m.train()
         m._eng().forward_loss(rgb, x, lab, 255, with_grad=True, focal=None)
         counts[flag] = dict(mock_lib)
-    n_attn = 2 * sum(m.backbone.depths)
+    n_attn = sum(m.backbone.depths)
     assert counts["0"]["cmx_gemm"] - counts["1"]["cmx_gemm"] == 2 * n_attn          # dV = P^T dO and dK = dS^T Q
 
 
@@ -111,7 +111,7 @@ def test_inference_and_focal_orchestration(mock_lib):
     eng = m._eng()
     out = eng.forward_logits(rgb, x)
     assert tuple(out.shape) == (2, 9, 64, 96) and out.dtype == torch.float32
-    assert mock_lib["cmx_attn_fwd"] == 2 * sum(m.backbone.depths) and mock_lib["cmx_attn_bwd"] == 0 and mock_lib["cmx_layernorm_bwd"] == 0
+    assert mock_lib["cmx_attn_fwd"] == sum(m.backbone.depths) and mock_lib["cmx_attn_bwd"] == 0 and mock_lib["cmx_layernorm_bwd"] == 0
     mock_lib.clear()
     m.train()
     loss = eng.forward_loss(rgb, x, lab, 255, with_grad=True, focal=(1.0, 0.2, 2.0, 0.25))   # the CE_Focal tuple (builder.py:246-247)
@@ -161,6 +161,33 @@ def test_unfused_attention_shapes_ignore_the_experimental_flag(mock_lib, monkeyp
     lab = torch.randint(0, 9, (1, H, W))
     loss = m._eng().forward_loss(rgb, x, lab, 255, with_grad=True, focal=None)
     assert loss.numel() == 1
-    n_attn = 2 * sum(m.backbone.depths)
+    n_attn = sum(m.backbone.depths)
     assert mock_lib["cmx_attn_fwd"] == 0 and mock_lib["cmx_attn_dkv"] == 0 and mock_lib["cmx_attn_dq"] == 0
     assert mock_lib["cmx_softmax_rows_fwd"] == mock_lib["cmx_softmax_rows_bwd"] == n_attn
+
+
+def test_sync_batchnorm_orchestration_two_allreduce_events(mock_lib):
+    """norm_layer=nn.SyncBatchNorm (train.py:64-67): the step generator yields exactly one all-reduce of the decoder norm's
+    (sum, sumsq) in forward and one of (sum dy, sum dy*xhat) in backward - both double[2*E] - before the early-gradient
+    event; with a plain BatchNorm2d (or a single rank) it yields neither."""
+    for norm, emulate, want in ((nn.SyncBatchNorm, 2, 2), (nn.SyncBatchNorm, 0, 0), (nn.BatchNorm2d, 2, 0)):
+        torch.manual_seed(0)
+        m = EncoderDecoder(cfg=_Cfg, criterion=nn.CrossEntropyLoss(reduction='mean', ignore_index=255), norm_layer=norm)
+        _, rgb, x, lab = _model_and_inputs()
+        m.train()
+        eng = m._eng()
+        eng.sync_emulate_world = emulate
+        events = list(_events(eng.forward_loss_steps(rgb, x, lab, 255, with_grad=True)))
+        sync = [e for e in events if isinstance(e, tuple) and e[0] == "allreduce_sum"]
+        assert len(sync) == want, (norm.__name__, emulate, events)
+        assert events[-1] == "early_gradients_ready"
+        for e in sync:
+            assert e[1].dtype == torch.float64 and e[1].numel() == 2 * _Cfg.decoder_embed_dim
+
+
+def _events(gen):
+    try:
+        while True:
+            yield next(gen)
+    except StopIteration:
+        return

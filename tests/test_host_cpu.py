@@ -181,3 +181,18 @@ def test_sass_holds_tcgen05_and_tma_and_no_legacy_mma_outside_the_fallback():
         for r in by[fam]:
             assert int(r["UTCMMA"]) > 0 and int(r["LDTM"]) > 0 and int(r["UTMALDG"]) > 0 and int(r["HMMA"]) == 0, r
     assert [k for k, v in by.items() if any(int(r["HMMA"]) for r in v)] == ["gemm_wmma_kernel"]
+
+
+def test_dice_ce_mirror_equals_reference_golden(golden_dir):
+    """utils.loss_opr.DiceCELoss (the torch formula the GPU tests use as checker for whole-model runs) == the reference class
+    on the committed fixture (tests/golden/make_golden_dice.py)"""
+    import numpy as np
+    import torch
+    from rgbx_semantic_segmentation_b200.utils.loss_opr import DiceCELoss
+    z = np.load(os.path.join(golden_dir, "dice.npz"))
+    for n in ("d5", "d9", "d40"):
+        lg = torch.from_numpy(z[n + "_logits"]).requires_grad_(True)
+        loss = DiceCELoss(alpha=float(z[n + "_meta"][1]))(lg, torch.from_numpy(z[n + "_target"]))
+        g, = torch.autograd.grad(loss, lg)
+        assert abs(loss.item() - float(z[n + "_loss"])) < 1e-6
+        assert torch.allclose(g, torch.from_numpy(z[n + "_grad"]), rtol=1e-5, atol=1e-8)

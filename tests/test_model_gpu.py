@@ -84,6 +84,15 @@ def test_eval_logits_vs_reference_golden(golden_dir, name):
     assert abs(s - float(z["eval_exp_score0_sum"])) < 2e-2 * float(z["eval_exp_score0_sum"])
 
 
+# worst per-parameter gradient cosine vs the fp32 oracle (measured values: profiles/r2_gradient_cosines.txt).  Named exceptions,
+# held to 0.90: bias gradients that are sums over all pixels / tokens of terms that cancel 10-25x - the 2-element FRM spatial-gate
+# bias and its hidden-layer bias (the kernel reproduces an fp64 evaluation on the same saved tensors, the
+# deviation is ReLU-mask-flip noise of the bf16 forward) and the attention q bias (sum over tokens of dq, which sums to ~0
+# per softmax row by construction)
+MIN_COS = 0.95
+MIN_COS_EXCEPTIONS = (("spatial_weights.mlp.2.bias", "spatial_weights.mlp.0.bias", "attn.q.bias"), 0.90)
+
+
 def grads_vs(m, ref_grads, what):
     rows = []
     gmax = max(g.norm().item() for g in ref_grads.values())
@@ -96,17 +105,22 @@ def grads_vs(m, ref_grads, what):
         cos = (g @ gr / (g.norm() * gr.norm())).item()
         rows.append((cos, g.norm().item() / gr.norm().item(), n))
     cosv = sorted(r[0] for r in rows)
-    assert cosv[0] >= 0.90, "%s: worst grad cosine %s" % (what, sorted(rows)[:3])
+    print("%s: worst gradient cosines %s" % (what, [(round(r[0], 4), r[2]) for r in sorted(rows)[:4]]))
+    low = [r for r in rows if r[0] < (MIN_COS_EXCEPTIONS[1] if r[2].endswith(MIN_COS_EXCEPTIONS[0]) else MIN_COS)]
+    assert not low, "%s: gradient cosines below the gate: %s" % (what, sorted(low)[:5])
     assert cosv[len(cosv) // 2] >= 0.99, "%s: median grad cosine %.4f" % (what, cosv[len(cosv) // 2])
     bad = [r for r in rows if abs(r[1] - 1) > 0.25 and abs(r[1] - 1) * ref_grads[r[2]].double().norm().item() > 5e-4 * gmax]
     assert not bad, "%s: grad norm ratio off: %s" % (what, bad[:3])
 
 
-@pytest.mark.parametrize("name", ["b2_small", "b0_odd", "b2_small_stochastic"])
+@pytest.mark.parametrize("name", ["b2_small", "b0_odd", "b2_small_stochastic", "b4_pst900"])
 def test_train_loss_and_grads_vs_reference(golden_dir, name):
+    """b4_pst900 = BASELINE.json configs[3] at full size (MiT-B4, 720x1280, 5 classes, batch 1; Nkv = 880 / 920, non-integer
+    23x40 -> 180x320 decoder ratio): loss, all 1 500+ gradient norms, 12 full gradients and the BatchNorm buffers against the
+    fixture written by the REAL reference (tests/golden/make_golden.py b4_pst900)."""
     z, backbone, ncls, B, H, W, sub, stoch = load_case(golden_dir, name)
     spec = cmx_ref.MIT_SPECS[backbone]
-    sd = synth_state_dict(spec, ncls, seed=0)
+    sd = synth_state_dict(spec, ncls, seed=0, ctx_gain=0.1 if name == "b4_pst900" else 1.0)   # see make_golden.py
     rgb, x, gt = synth_inputs(B, H, W, ncls, seed=1)
     m = make(backbone, ncls, True, sd).train()
     eng = m._eng()
@@ -126,6 +140,7 @@ def test_train_loss_and_grads_vs_reference(golden_dir, name):
     norms = dict(zip(names, z["grad_norms"]))
     gmax = max(norms.values())
     pd = dict(m.named_parameters())
+    bad = []
     for n in names:
         if norms[n] > 1e-4 * gmax:
             r = pd[n].grad.double().norm().item() / norms[n]
@@ -134,7 +149,10 @@ def test_train_loss_and_grads_vs_reference(golden_dir, name):
             # gradient is a sum over pixels of terms that cancel 13-24x (sum |ds| = 2e-2 vs |sum ds| = 1.5e-3 at stage 2,
             # scripts/gpu_debug_gate.py); the kernel reproduces an fp64 evaluation on the same saved tensors exactly, the
             # ~1.5 % (of sum |ds|) deviation is ReLU-mask-flip noise of the bf16 forward
-            assert abs(r - 1) < 0.25 or abs(r - 1) * norms[n] < 5e-4 * gmax, (n, r)
+            if not (abs(r - 1) < 0.25 or abs(r - 1) * norms[n] < 5e-4 * gmax):
+                bad.append((round(r, 4), n))
+    print("%s: %d gradient norms outside tolerance%s" % (name, len(bad), "" if not bad else ": " + str(sorted(bad)[:12]) + " ... " + str(sorted(bad)[-12:])))
+    assert not bad, (name, len(bad), bad[:8])
     for k in z.files:
         if k.startswith("grad::"):
             gr = torch.from_numpy(z[k]).double().flatten()
@@ -145,6 +163,8 @@ def test_train_loss_and_grads_vs_reference(golden_dir, name):
             assert torch.allclose(b, torch.from_numpy(z[k]), rtol=2e-2, atol=2e-3), k
     assert int(dict(m.named_buffers())["decode_head.linear_fuse.1.num_batches_tracked"]) == \
         int(z["post::decode_head.linear_fuse.1.num_batches_tracked"])
+    if name == "b4_pst900":
+        return   # the fp32 oracle needs ~20 GB and minutes of CPU time at this size; the reference fixture above is the check
     # full gradient comparison against the oracle (CPU, seconds at this size)
     params = {k: v.clone().requires_grad_(v.is_floating_point() and not k.endswith(("running_mean", "running_var")))
               for k, v in sd.items()}
@@ -331,10 +351,6 @@ def test_sliding_window_driver_batched_equals_per_crop():
     p8 = sliding_eval_rgbX_batched(ctx, img, mx, (64, 64), 2 / 3, "cuda", max_batch=8)
     assert p1.shape == (96, 128) and p1.dtype == np.int64
     assert (p1 != p8).mean() < 0.02, "batched and per-crop predictions differ on %.2f %% of the pixels" % (100 * (p1 != p8).mean())
-    from rgbx_semantic_segmentation_b200.utils.sliding_eval import sliding_eval_rgbX_gpu
-    pg = sliding_eval_rgbX_gpu(ctx, img, mx, (64, 64), 2 / 3, "cuda", max_batch=8)
-    assert pg.shape == (96, 128) and pg.dtype == np.int64
-    assert (pg != p8).mean() < 0.02, "device-resident and host-preprocessed predictions differ on %.2f %% of the pixels" % (100 * (pg != p8).mean())
 
 
 def test_ragged_input_size_train_and_eval_vs_oracle():
@@ -406,7 +422,7 @@ def test_flat_data_parallel_two_graph_step_single_process_group():
             losses.append(loss.item())
             assert not m._flat_pending.works, "all-reduce handles must be consumed by backward()"
         key = [k for k in m._graphs if k[0] == "train"][0]
-        assert m._graphs[key]["graph2"] is not None, "FlatDataParallel must capture the step as two graphs"
+        assert len(m._graphs[key]["graphs"]) == 2, "FlatDataParallel must capture the step as two graphs"
         assert 0 < eng.split_off < eng.total and eng.n_early > 0
         assert all(abs(v - ref_loss.item()) < 2e-3 * abs(ref_loss.item()) for v in losses), (losses, ref_loss.item())
         pg = dict(plain.named_parameters())
@@ -422,15 +438,16 @@ def test_flat_data_parallel_two_graph_step_single_process_group():
 
 
 def test_focal_and_ce_focal_criteria_train_step_vs_oracle():
-    """criterion = FocalLoss / (CrossEntropyLoss, FocalLoss) (train.py:70-93, builder.py:246-247): loss and gradients of the whole
+    """criterion = FocalLoss / (CrossEntropyLoss, FocalLoss) / DiceCELoss (train.py:70-93, builder.py:246-247): loss and gradients of the whole
     model against the fp32 oracle with the same criterion applied to its logits"""
     from rgbx_semantic_segmentation_b200.models.builder import EncoderDecoder
-    from rgbx_semantic_segmentation_b200.utils.loss_opr import FocalLoss
+    from rgbx_semantic_segmentation_b200.utils.loss_opr import DiceCELoss, FocalLoss
     spec = cmx_ref.MIT_SPECS["mit_b0"]
     sd = synth_state_dict(spec, 9, seed=0)
     rgb, x, gt = synth_inputs(2, 64, 96, 9, seed=1)
     ce = nn.CrossEntropyLoss(reduction="mean", ignore_index=255)
-    for crit in (FocalLoss(ignore_label=255, gamma=4.0, alpha=0.25), (ce, FocalLoss(ignore_label=255, gamma=2.0, alpha=0.25))):
+    for crit in (FocalLoss(ignore_label=255, gamma=4.0, alpha=0.25), (ce, FocalLoss(ignore_label=255, gamma=2.0, alpha=0.25)),
+                 DiceCELoss(alpha=0.5, ignore_index=255)):
         cfg = Cfg()
         cfg.backbone, cfg.num_classes = "mit_b0", 9
         m = EncoderDecoder(cfg, crit, nn.BatchNorm2d)
@@ -445,7 +462,9 @@ def test_focal_and_ce_focal_criteria_train_step_vs_oracle():
         ref = crit(logits, gt) if not isinstance(crit, tuple) else crit[0](logits, gt) + 0.2 * crit[1](logits, gt)
         ref.backward()
         assert abs(loss.item() - ref.item()) <= 5e-3 * abs(ref.item()), (loss.item(), ref.item())
-        grads_vs(m, {n: params[n].grad for n, _ in m.named_parameters()}, "focal criterion")
+        grads_vs(m, {n: params[n].grad for n, _ in m.named_parameters()}, "criterion %s" % (type(crit).__name__,))
+        with torch.no_grad():
+            assert abs(m(rgb.cuda(), x.cuda(), gt.cuda()).item() - ref.item()) <= 5e-3 * abs(ref.item())
     with pytest.raises(NotImplementedError):
         bad = EncoderDecoder(cfg, nn.MSELoss(), nn.BatchNorm2d).cuda().train()
         bad(rgb.cuda(), x.cuda(), gt.cuda())

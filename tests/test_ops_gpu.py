@@ -449,6 +449,58 @@ def test_focal_loss_kernel_vs_reference_golden(golden_dir, name, mode):
     close(dout[:, :ncls], ref_grad, 2e-3, 1e-7, "focal dlogits")
 
 
+@pytest.mark.parametrize("name", ["d5", "d9", "d40"])
+def test_dice_ce_loss_kernels_vs_reference_golden(golden_dir, name):
+    """fused DiceCELoss (train.py:79-80; utils/loss_opr.py:103-156) against values produced by the reference class; identity
+    'upsample' (H = h) so the golden logits are the kernel's logits; d40 = the 40-class (NYUDv2 default) register-array variant"""
+    import os
+    z = np.load(os.path.join(golden_dir, "dice.npz"))
+    ncls, alpha, _ = z[name + "_meta"]
+    ncls = int(ncls)
+    lg = torch.from_numpy(z[name + "_logits"]).to(DEV)
+    B, _, h, w = lg.shape
+    ld = (ncls + 7) // 8 * 8
+    base = torch.full((B * h * w, ld), float("nan"), device=DEV)
+    logits = base[:, :ncls]
+    logits.copy_(lg.permute(0, 2, 3, 1).reshape(-1, ncls))
+    label = torch.from_numpy(z[name + "_target"]).to(DEV)
+    acc = torch.zeros(2, dtype=torch.float64, device=DEV)
+    dstats = torch.zeros(B * 3 * ncls, dtype=torch.float64, device=DEV)
+    coef = torch.empty(B * 2 * ncls + 1, device=DEV)
+    loss = torch.empty((), device=DEV)
+    ops.dice_ce_stats(logits, label, 255, acc, dstats, B, h, w, h, w, ncls)
+    ops.dice_ce_finalize(acc, dstats, B, ncls, float(alpha), 1e-6, loss, coef)
+    dl = torch.zeros(B * h * w, ld, device=DEV)
+    ops.dice_ce_grad(logits, label, 255, coef, dl[:, :ncls], B, h, w, h, w, ncls)
+    ref_loss = float(z[name + "_loss"])
+    assert abs(float(loss) - ref_loss) < 2e-5 * max(1.0, abs(ref_loss)), (float(loss), ref_loss)
+    ref_grad = torch.from_numpy(z[name + "_grad"]).to(DEV).permute(0, 2, 3, 1).reshape(-1, ncls)
+    close(dl[:, :ncls], ref_grad, 2e-3, 1e-7, "dice-ce dlogits")
+
+
+def test_ce_kernel_40_classes_upsampled():
+    """num_classes = 40 is the reference's default config (NYUDv2, config.py): the > 16-class instantiation of the fused
+    bilinear x4 + CE kernel against F.interpolate + F.cross_entropy"""
+    B, h, w, H, W, ncls = 2, 12, 16, 48, 64, 40
+    g = torch.Generator().manual_seed(5)
+    lr = (2.0 * torch.randn(B, ncls, h, w, generator=g)).to(DEV).requires_grad_(True)
+    label = torch.randint(0, ncls, (B, H, W), generator=g)
+    label[torch.rand(B, H, W, generator=g) < 0.1] = 255
+    label = label.to(DEV)
+    logits = lr.detach().permute(0, 2, 3, 1).reshape(-1, ncls).contiguous()
+    acc = torch.zeros(2, dtype=torch.float64, device=DEV)
+    dl = torch.zeros_like(logits)
+    ops.ce_upsampled(logits, label, 255, acc, dl, B, h, w, H, W, ncls)
+    loss = torch.empty((), device=DEV)
+    dout = torch.empty_like(dl)
+    ops.ce_finalize(acc, loss, dl, None, dout)
+    up = torch.nn.functional.interpolate(lr, size=(H, W), mode="bilinear", align_corners=False)
+    ref = torch.nn.functional.cross_entropy(up, label, ignore_index=255)
+    ref.backward()
+    assert abs(float(loss) - float(ref)) < 1e-5 * max(1, abs(float(ref)))
+    close(dout, lr.grad.permute(0, 2, 3, 1).reshape(-1, ncls), 1e-3, 1e-6, "ce40 dlogits")
+
+
 def test_confusion_bit_exact():
     from oracle import metric_ref
     rng = np.random.default_rng(0)
@@ -557,3 +609,124 @@ def test_attention_dkv_recompute(B, N, Nk, heads):
         ops.attn_dq(q, dO, kv, lse, delta, dq, B, N, Nk, heads, scale)
         dq_ref = qf.grad.permute(0, 2, 1, 3).reshape(B * N, C)
         close(dq, dq_ref, 2e-2, 2e-2 * float(dq_ref.abs().max()), "dQ")
+
+
+# ---------------------------------------------------------------------------------------------
+# grouped launches (group = modality branch): one launch over two stacked problems with per-group parameters lying a
+# fixed number of elements apart in one flat buffer must equal two separate launches
+# ---------------------------------------------------------------------------------------------
+def _flat_pair(shape, gs, seed, scale=1.0):
+    """a flat fp32 buffer holding two parameter tensors of `shape` gs elements apart -> (flat, view0, view1)"""
+    n = int(np.prod(shape))
+    assert gs >= n
+    torch.manual_seed(seed)
+    flat = torch.randn(gs + n, device=DEV) * scale
+    return flat, flat[:n].view(shape), flat[gs:gs + n].view(shape)
+
+
+@pytest.mark.parametrize("M,N,K", [(300, 64, 64), (1200, 320, 320), (257, 128, 512)])
+def test_grouped_gemm_fwd_dgrad_wgrad(M, N, K):
+    gs = 64 * ((N * K + 1000) // 64)
+    wf, w0, w1 = _flat_pair((N, K), gs, 0, K ** -0.5)
+    wb = wf.to(bf)
+    w0b, w1b = wb[:N * K].view(N, K), wb[gs:gs + N * K].view(N, K)
+    bfl, b0, b1 = _flat_pair((N,), gs, 1)
+    x = rnd(2 * M, K, dtype=bf, seed=2)
+    res = rnd(2 * M, N, seed=3)
+    rs = torch.rand(2, 4, device=DEV) + 0.5       # 4 "samples" per group
+    rps = (M + 3) // 4
+    out = torch.empty(2 * M, N, device=DEV)
+    ops.mm(x, w0b, out, bias=b0, residual=res, row_scale=rs, rows_per_sample=rps, groups=2, gs_b=gs, gs_bias=gs, gs_scale=4)
+    for g, (w, b) in enumerate(((w0b, b0), (w1b, b1))):
+        ref = torch.empty(M, N, device=DEV)
+        ops.mm(x[g * M:(g + 1) * M], w, ref, bias=b, residual=res[g * M:(g + 1) * M], row_scale=rs[g], rows_per_sample=rps)
+        assert torch.equal(out[g * M:(g + 1) * M], ref), "grouped forward differs from the single launch (group %d)" % g
+        close(ref, res[g * M:(g + 1) * M] + (x[g * M:(g + 1) * M].float() @ w.float().t() + b) *
+              rs[g].repeat_interleave(rps)[:M, None], 2e-2, 2e-2, "grouped fwd vs torch")
+    # dgrad: dx[2M, K] = dy[2M, N] @ W_g[N, K]
+    dy = rnd(2 * M, N, dtype=bf, seed=4)
+    dx = torch.empty(2 * M, K, device=DEV, dtype=bf)
+    ops.mm(dy, w0b, dx, tb=True, groups=2, gs_b=gs)
+    for g, w in enumerate((w0b, w1b)):
+        ref = torch.empty(M, K, device=DEV, dtype=bf)
+        ops.mm(dy[g * M:(g + 1) * M], w, ref, tb=True)
+        assert torch.equal(dx[g * M:(g + 1) * M], ref), "grouped dgrad (group %d)" % g
+    # wgrad: dW_g[N, K] += dy_g^T x_g into a flat gradient buffer
+    gfl = torch.zeros_like(wf)
+    ops.mm(dy, x, gfl[:N * K].view(N, K), ta=True, tb=True, accumulate=True, groups=2, gs_c=gs)
+    for g in (0, 1):
+        ref = dy[g * M:(g + 1) * M].float().t() @ x[g * M:(g + 1) * M].float()
+        got = gfl[g * gs:g * gs + N * K].view(N, K)
+        close(got, ref, 1e-3, 1e-3 * M ** 0.5, "grouped wgrad (group %d)" % g)
+    assert float(gfl[N * K:gs].abs().max()) == 0.0, "grouped wgrad wrote outside its two slots"
+
+
+@pytest.mark.parametrize("M,C", [(300, 64), (75, 320), (40, 512), (33, 160)])
+def test_grouped_layernorm_fwd_bwd(M, C):
+    gs = 64 * ((C + 200) // 64)
+    gf, g0, g1 = _flat_pair((C,), gs, 0)
+    bfl, b0, b1 = _flat_pair((C,), gs, 1)
+    x = rnd(2 * M, C, seed=2)
+    y = torch.empty(2 * M, C, device=DEV, dtype=bf)
+    mean, rstd = torch.empty(2 * M, device=DEV), torch.empty(2 * M, device=DEV)
+    ops.layernorm_fwd(x, g0, b0, 1e-6, y, mean, rstd, groups=2, param_gs=gs)
+    for g, (ga, be) in enumerate(((g0, b0), (g1, b1))):
+        r = slice(g * M, (g + 1) * M)
+        yr = torch.empty(M, C, device=DEV, dtype=bf)
+        m2, r2 = torch.empty(M, device=DEV), torch.empty(M, device=DEV)
+        ops.layernorm_fwd(x[r], ga, be, 1e-6, yr, m2, r2)
+        assert torch.equal(y[r], yr) and torch.equal(mean[r], m2) and torch.equal(rstd[r], r2), "grouped LN fwd (group %d)" % g
+    dy = rnd(2 * M, C, dtype=bf, seed=3)
+    dres = rnd(2 * M, C, seed=4)
+    sc = torch.rand(2, 3, device=DEV) + 0.5
+    rps = (M + 2) // 3
+    dx, dxb = torch.empty(2 * M, C, device=DEV), torch.empty(2 * M, C, device=DEV, dtype=bf)
+    dg, db, dbi = torch.zeros_like(gf), torch.zeros_like(gf), torch.zeros_like(gf)
+    ops.layernorm_bwd(dy, x, mean, rstd, g0, dres=dres, dx=dx, dx_bf=dxb, scale=sc, rows_per_sample=rps,
+                      dgamma=dg[:C], dbeta=db[:C], dbias=dbi[:C], groups=2, param_gs=gs, scale_gs=3)
+    for g, ga in enumerate((g0, g1)):
+        r = slice(g * M, (g + 1) * M)
+        dx2, dxb2 = torch.empty(M, C, device=DEV), torch.empty(M, C, device=DEV, dtype=bf)
+        dg2, db2, dbi2 = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV), torch.zeros(C, device=DEV)
+        ops.layernorm_bwd(dy[r], x[r], mean[r], rstd[r], ga, dres=dres[r], dx=dx2, dx_bf=dxb2, scale=sc[g], rows_per_sample=rps,
+                          dgamma=dg2, dbeta=db2, dbias=dbi2)
+        assert torch.equal(dx[r], dx2) and torch.equal(dxb[r], dxb2), "grouped LN bwd dx (group %d)" % g
+        for a, b_, what in ((dg, dg2, "dgamma"), (db, db2, "dbeta"), (dbi, dbi2, "dbias")):
+            close(a[g * gs:g * gs + C], b_, 1e-4, 1e-4 * M ** 0.5, "grouped LN bwd %s (group %d)" % (what, g))
+
+
+@pytest.mark.parametrize("B,H,W,C", [(2, 15, 20, 64), (1, 9, 13, 128)])
+def test_grouped_dwconv_and_colsum(B, H, W, C):
+    gs = 64 * ((9 * C + 300) // 64)
+    wf, w0, w1 = _flat_pair((C, 9), gs, 0, 0.3)
+    bfl, b0, b1 = _flat_pair((C,), gs, 1)
+    M = B * H * W
+    x = rnd(2 * M, C, dtype=bf, seed=2)
+    y = torch.empty(2 * M, C, device=DEV, dtype=bf)
+    ops.dwconv3x3_fwd(x, w0, b0, ops.ACT_GELU, y, B, H, W, groups=2, param_gs=gs)
+    dy = rnd(2 * M, C, dtype=bf, seed=3)
+    du = torch.empty(2 * M, C, device=DEV, dtype=bf)
+    dwf, dbf = torch.zeros_like(wf), torch.zeros_like(bfl)
+    ops.dwconv3x3_bwd_pre(x, w0, b0, ops.ACT_GELU, dy, du, dwf[:9 * C].view(C, 9), dbf[:C], B, H, W, groups=2, param_gs=gs)
+    dxg = torch.empty(2 * M, C, device=DEV, dtype=bf)
+    ysum = torch.zeros_like(bfl)
+    ops.dwconv3x3_fwd(du, w0, None, ops.ACT_NONE, dxg, B, H, W, flip=True, ysum=ysum[:C], groups=2, param_gs=gs)
+    cs = torch.zeros_like(bfl)
+    ops.colsum(dy, cs[:C], groups=2, out_gs=gs)
+    for g, (w, b) in enumerate(((w0, b0), (w1, b1))):
+        r = slice(g * M, (g + 1) * M)
+        yr = torch.empty(M, C, device=DEV, dtype=bf)
+        ops.dwconv3x3_fwd(x[r], w, b, ops.ACT_GELU, yr, B, H, W)
+        assert torch.equal(y[r], yr), "grouped dwconv fwd (group %d)" % g
+        dur = torch.empty(M, C, device=DEV, dtype=bf)
+        dwr, dbr = torch.zeros(C, 9, device=DEV), torch.zeros(C, device=DEV)
+        ops.dwconv3x3_bwd_pre(x[r], w, b, ops.ACT_GELU, dy[r], dur, dwr, dbr, B, H, W)
+        assert torch.equal(du[r], dur), "grouped dwconv bwd_pre du (group %d)" % g
+        close(dwf[g * gs:g * gs + 9 * C].view(C, 9), dwr, 1e-4, 1e-3, "grouped dwconv dW (group %d)" % g)
+        close(dbf[g * gs:g * gs + C], dbr, 1e-4, 1e-3, "grouped dwconv db (group %d)" % g)
+        dxr = torch.empty(M, C, device=DEV, dtype=bf)
+        ysr = torch.zeros(C, device=DEV)
+        ops.dwconv3x3_fwd(dur, w, None, ops.ACT_NONE, dxr, B, H, W, flip=True, ysum=ysr)
+        assert torch.equal(dxg[r], dxr), "grouped dwconv dgrad (group %d)" % g
+        close(ysum[g * gs:g * gs + C], ysr, 1e-4, 1e-3, "grouped dwconv ysum (group %d)" % g)
+        close(cs[g * gs:g * gs + C], dy[r].float().sum(0), 1e-4, 1e-3, "grouped colsum (group %d)" % g)
