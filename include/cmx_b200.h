@@ -133,6 +133,13 @@ int cmx_dwconv3x3_bwd_pre(const void* x, int64_t ldx, const float* w, const floa
  * column = (kh*k+kw)*Cin+ci (dual_segformer.py:219, conv k=7 s=4 p=3) */
 int cmx_im2col_nchw(const float* x, void* col, int B, int Cin, int H, int W, int k, int s, int p,
                     int Ho, int Wo, int kpad, void* stream);
+/* the same gather straight from the RAW uint8 image [B,H,W,ch] (ch = 3 HWC, or 1 = grey X): the reference's host-side input
+ * pipeline - float64 normalisation ((v / 255) - mean[c]) / std[c] rounded to fp32 (utils/transforms.py:182-187), thermal 1 -> 3
+ * replication (RGBXDataset.py:57-59), HWC -> CHW (dataloader.py:85-112) - fused into the stage-1 patch-embed load.  ch = 1 (grey
+ * X): the replicated channels are affine images of one value, so TWO columns per tap are written, (v / 255, 1-inside-the-image);
+ * the caller multiplies by the 7x7x3 weights folded to 7x7x2 (sum_c W_c / std_c, -sum_c W_c mean_c / std_c). */
+int cmx_im2col_u8(const uint8_t* x, void* col, int B, int ch, int H, int W, int k, int s, int p, int Ho, int Wo, int kpad,
+                  double mean0, double mean1, double mean2, double std0, double std1, double std2, void* stream);
 /* NHWC bf16 -> im2col rows [B*Ho*Wo, k*k*C] (stage 2-4 patch embeds k=3 s=2 p=1; SR conv k=s=R p=0) */
 int cmx_im2col_nhwc(const void* x, int64_t ldx, void* col, int B, int H, int W, int C, int k, int s, int p,
                     int Ho, int Wo, void* stream);
@@ -179,7 +186,15 @@ int cmx_adamw_flat(float* p, const float* g, float* m, float* v, void* w_bf16, c
  * p_out (optional, bf16 [B*heads*N, ldp]): the normalised probabilities, written by TMA for the backward pass.
  * lse (optional, fp32 [B*heads*N]): natural-log row normaliser. */
 int cmx_attn_fwd(const void* q, int64_t ldq, const void* kv, int64_t ldkv, void* o, int64_t ldo, void* p_out, int64_t ldp,
-                 float* lse, int B, int N, int Nk, int heads, float scale, void* stream);
+                 float* lse, int B, int N, int Nk, int heads, float scale, int64_t kv_sample_rows, void* stream);
+/* kv_sample_rows (0 = Nk): key rows per sample in kv.  Larger than Nk when the call covers ONE CHUNK of a longer key axis (kv
+ * then points at the chunk's first key row of sample 0): key-chunked attention for Nkv above the resident-K/V limit, combined by
+ * cmx_attn_combine:  o = sum_c exp(lse_c - lse) o_c,  lse = log sum_c exp(lse_c);  o_parts / lse_parts hold nc stacked parts
+ * (part_stride / lse_stride elements apart). */
+int cmx_attn_combine(const void* o_parts, int64_t part_stride, int64_t ldp, const float* lse_parts, int64_t lse_stride, int nc,
+                     void* o, int64_t ldo, float* lse, int B, int N, int heads, void* stream);
+/* out[n] (bf16) = sum over nc stacked bf16 tensors, fp32 accumulation (the per-chunk dQ partials of the chunked backward) */
+int cmx_sum_parts_bf16(const void* parts, int64_t part_stride, int nc, void* out, int64_t n, void* stream);
 
 /* fused attention backward core: dP = dO V^T (tensor memory only), dS = scale * P .* (dP - rowsum(P .* dP)) -> ds_out
  * (bf16, same layout as p; consumed by the split-K dK = dS^T Q GEMM), dQ = dS K -> dq [B*N, lddq].  dV = P^T dO and
@@ -201,7 +216,8 @@ int cmx_attn_dkv(const void* q, int64_t ldq, const void* d_o, int64_t lddo, cons
 /* EXPERIMENTAL companion (same status): query-major dQ [B*N, lddq] (bf16) with recomputed probabilities, Nkv <= 384; with
  * cmx_attn_dkv it makes the stored probabilities (p_out of cmx_attn_fwd) and the dS round trip of cmx_attn_bwd unnecessary. */
 int cmx_attn_dq(const void* q, int64_t ldq, const void* d_o, int64_t lddo, const void* kv, int64_t ldkv, const float* lse,
-                const float* delta, void* dq, int64_t lddq, int B, int N, int Nk, int heads, float scale, void* stream);
+                const float* delta, void* dq, int64_t lddq, int B, int N, int Nk, int heads, float scale,
+                int64_t kv_sample_rows, void* stream);
 
 /* ---- softmax ---------------------------------------------------------------------------------- */
 /* row softmax of fp32 S [rows, n] (ld) -> bf16 P  (dual_segformer.py:131) and its backward

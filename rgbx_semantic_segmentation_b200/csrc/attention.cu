@@ -374,8 +374,9 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_kernel(const __grid_consta
 }
 
 CMX_API int cmx_attn_fwd(const void* q, int64_t ldq, const void* kv, int64_t ldkv, void* o, int64_t ldo, void* p_out, int64_t ldp,
-                         float* lse, int B, int N, int Nk, int heads, float scale, void* stream) {
+                         float* lse, int B, int N, int Nk, int heads, float scale, int64_t kv_sample_rows, void* stream) {
   CMX_REQUIRE(q && kv && o, "attn_fwd: null operand");
+  if (kv_sample_rows <= 0) kv_sample_rows = Nk;   // key rows per sample in kv (> Nk when this call covers one key chunk only)
   CMX_REQUIRE(Nk >= 1 && Nk <= AT_NK, "attn_fwd: Nkv=%d unsupported (max %d) - use the unfused path", Nk, AT_NK);
   CMX_REQUIRE(ldq % 8 == 0 && ldkv % 8 == 0 && ldo % 8 == 0 && (!p_out || ldp % 8 == 0), "attn_fwd: leading dims must be multiples of 8");
   CMX_REQUIRE(ldq >= heads * AT_D && ldkv >= 2 * heads * AT_D, "attn_fwd: head_dim must be 64");
@@ -387,7 +388,7 @@ CMX_API int cmx_attn_fwd(const void* q, int64_t ldq, const void* kv, int64_t ldk
   memset(&tmP, 0, sizeof(tmP));
   int rc = cmx_make_map3(&tmQ, q, (uint64_t)heads * AT_D, (uint64_t)N, (uint64_t)B, (uint64_t)ldq, (uint64_t)N * ldq, AT_D, AT_BM);
   if (rc) return rc;
-  rc = cmx_make_map3(&tmKV, kv, (uint64_t)2 * heads * AT_D, (uint64_t)Nk, (uint64_t)B, (uint64_t)ldkv, (uint64_t)Nk * ldkv, AT_D, 160);
+  rc = cmx_make_map3(&tmKV, kv, (uint64_t)2 * heads * AT_D, (uint64_t)Nk, (uint64_t)B, (uint64_t)ldkv, (uint64_t)kv_sample_rows * ldkv, AT_D, 160);
   if (rc) return rc;
   if (p_out) {
     rc = cmx_make_map3(&tmP, p_out, (uint64_t)Nk, (uint64_t)N, (uint64_t)B * heads, (uint64_t)ldp, (uint64_t)N * ldp, 64, AT_BM);

@@ -554,8 +554,10 @@ CMX_API int cmx_attn_dkv(const void* q, int64_t ldq, const void* d_o, int64_t ld
 }
 
 CMX_API int cmx_attn_dq(const void* q, int64_t ldq, const void* d_o, int64_t lddo, const void* kv, int64_t ldkv, const float* lse,
-                        const float* delta, void* dq, int64_t lddq, int B, int N, int Nk, int heads, float scale, void* stream) {
+                        const float* delta, void* dq, int64_t lddq, int B, int N, int Nk, int heads, float scale,
+                        int64_t kv_sample_rows, void* stream) {
   CMX_REQUIRE(q && d_o && kv && lse && delta && dq, "attn_dq: null operand");
+  if (kv_sample_rows <= 0) kv_sample_rows = Nk;   // key rows per sample in kv (> Nk when this call covers one key chunk only)
   CMX_REQUIRE(Nk >= 1 && Nk <= DQ_MAXKB * DK_BK, "attn_dq: Nkv=%d unsupported (max %d) - use the unfused path", Nk, DQ_MAXKB * DK_BK);
   CMX_REQUIRE(ldq % 8 == 0 && lddo % 8 == 0 && ldkv % 8 == 0 && lddq % 8 == 0, "attn_dq: leading dims must be multiples of 8");
   CMX_REQUIRE(ldq >= heads * DK_D && lddo >= heads * DK_D && ldkv >= 2 * heads * DK_D && lddq >= heads * DK_D, "attn_dq: head_dim must be 64");
@@ -568,7 +570,7 @@ CMX_API int cmx_attn_dq(const void* q, int64_t ldq, const void* d_o, int64_t ldd
   if (rc) return rc;
   rc = cmx_make_map3(&tmDO, d_o, (uint64_t)heads * DK_D, (uint64_t)N, (uint64_t)B, (uint64_t)lddo, (uint64_t)N * lddo, DK_D, DK_BQ);
   if (rc) return rc;
-  rc = cmx_make_map3(&tmKV, kv, (uint64_t)2 * heads * DK_D, (uint64_t)Nk, (uint64_t)B, (uint64_t)ldkv, (uint64_t)Nk * ldkv, DK_D, DK_BK);
+  rc = cmx_make_map3(&tmKV, kv, (uint64_t)2 * heads * DK_D, (uint64_t)Nk, (uint64_t)B, (uint64_t)ldkv, (uint64_t)kv_sample_rows * ldkv, DK_D, DK_BK);
   if (rc) return rc;
   DqArgs a;
   a.lse = lse; a.delta = delta; a.dq = (bf16*)dq; a.lddq = lddq;
@@ -591,5 +593,79 @@ CMX_API int cmx_attn_dq(const void* q, int64_t ldq, const void* d_o, int64_t ldd
   attn_dq_kernel<<<(unsigned)grid, DK_THREADS, DQ_SMEM, st>>>(tmQ, tmDO, tmKV, a);
   g_cmx_launches++;
   CMX_CHECK_LAUNCH("attn_dq_kernel");
+  return 0;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Key-chunked attention (Nkv above the resident-K/V limit of the fused kernels, e.g. 880 / 920 at 720x1280): the fused
+// forward runs once per chunk of <= 320 keys and writes that chunk's normalised output and log-sum-exp; the softmax over all
+// keys is then   O = sum_c exp(lse_c - lse) O_c,   lse = log sum_c exp(lse_c)   (exact; no [N, Nkv] tensor ever exists).
+// thread = 8 channels of one (row, head); parts are stacked [nc][rows, ld] / [nc][B*heads*N]
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) attn_combine_kernel(const bf16* __restrict__ o_parts, long part_stride, long ldp,
+                                                          const float* __restrict__ lse_parts, long lse_stride, int nc,
+                                                          bf16* __restrict__ o, long ldo, float* __restrict__ lse, int B, int N, int heads) {
+  pdl_trigger();
+  const long total = (long)B * N * heads * 8;
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int v = (int)(idx & 7);
+  const int h = (int)((idx >> 3) % heads);
+  const long row = idx / ((long)heads * 8);
+  const long b = row / N, n = row % N;
+  const long li = (b * heads + h) * N + n;
+  float m = -INFINITY;
+  for (int c = 0; c < nc; c++) m = fmaxf(m, lse_parts[c * lse_stride + li]);
+  float den = 0.f;
+  for (int c = 0; c < nc; c++) den += expf(lse_parts[c * lse_stride + li] - m);
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) acc[i] = 0.f;
+  for (int c = 0; c < nc; c++) {
+    const float w = expf(lse_parts[c * lse_stride + li] - m) / den;
+    float t[8];
+    load8(o_parts + c * part_stride + row * ldp + h * 64 + v * 8, t);
+#pragma unroll
+    for (int i = 0; i < 8; i++) acc[i] += w * t[i];
+  }
+  store8(o + row * ldo + h * 64 + v * 8, acc);
+  if (v == 0) lse[li] = m + logf(den);
+}
+CMX_API int cmx_attn_combine(const void* o_parts, int64_t part_stride, int64_t ldp, const float* lse_parts, int64_t lse_stride, int nc,
+                             void* o, int64_t ldo, float* lse, int B, int N, int heads, void* stream) {
+  CMX_REQUIRE(o_parts && lse_parts && o && lse && nc >= 1, "attn_combine: null operand");
+  CMX_REQUIRE(ldp % 8 == 0 && ldo % 8 == 0 && part_stride % 8 == 0, "attn_combine: strides must be multiples of 8");
+  const long total = (long)B * N * heads * 8;
+  if (total == 0) return 0;
+  attn_combine_kernel<<<(unsigned)cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)o_parts, part_stride, ldp, lse_parts,
+                                                                                  lse_stride, nc, (bf16*)o, ldo, lse, B, N, heads);
+  g_cmx_launches++;
+  CMX_CHECK_LAUNCH("attn_combine");
+  return 0;
+}
+
+// out = sum of nc stacked bf16 tensors (fp32 accumulation): the per-chunk dQ partials of the key-chunked backward
+__global__ void __launch_bounds__(256) sum_parts_kernel(const bf16* __restrict__ parts, long part_stride, int nc, bf16* __restrict__ out, long n8) {
+  pdl_trigger();
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  float acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) acc[k] = 0.f;
+  for (int c = 0; c < nc; c++) {
+    float t[8];
+    load8(parts + c * part_stride + i * 8, t);
+#pragma unroll
+    for (int k = 0; k < 8; k++) acc[k] += t[k];
+  }
+  store8(out + i * 8, acc);
+}
+CMX_API int cmx_sum_parts_bf16(const void* parts, int64_t part_stride, int nc, void* out, int64_t n, void* stream) {
+  CMX_REQUIRE(parts && out && nc >= 1 && n % 8 == 0 && part_stride % 8 == 0, "sum_parts: n and the part stride must be multiples of 8");
+  if (n == 0) return 0;
+  sum_parts_kernel<<<(unsigned)cdiv(n / 8, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)parts, part_stride, nc, (bf16*)out, n / 8);
+  g_cmx_launches++;
+  CMX_CHECK_LAUNCH("sum_parts");
   return 0;
 }

@@ -56,6 +56,67 @@ CMX_API int cmx_im2col_nchw(const float* x, void* col, int B, int Cin, int H, in
   LAUNCH_DONE("im2col_nchw");
 }
 
+// ---- input pipeline fused into the stage-1 patch-embed load: raw uint8 HWC image -> im2col rows ------------
+// The reference normalises on the host (utils/transforms.py:182-187: (v / 255 - mean) / std in float64, cast to fp32), replicates
+// the grey thermal image to 3 channels (RGBXDataset.py:57-59; each then normalised with ITS channel's mean / std, dataloader.py:
+// 106) and transposes HWC -> CHW (dataloader.py:109-110); here the uint8 image is resident on the device and the float64
+// normalisation happens while the 7x7/4 patches are gathered.
+// ch = 3: column (tap, c) = normalised value (0 in the conv's zero padding) - bit-identical to the host pipeline + im2col_nchw.
+// ch = 1 (grey X): the three replicated channels are affine images of ONE value, x_c = v/255 / std_c - mean_c / std_c, so the
+//   7x7x3 weights fold into 7x7x2: column (tap, 0) = v / 255, column (tap, 1) = 1 inside the image (both 0 in the padding); the
+//   caller multiplies by  Wa = sum_c W_c / std_c  and  Wb = -sum_c W_c mean_c / std_c  (98 instead of 147 columns).
+template <typename I>
+__global__ void __launch_bounds__(256) im2col_u8_kernel(const uint8_t* __restrict__ x, bf16* __restrict__ col, int B, int ch, int H, int W,
+                                                        int k, int s, int p, int Ho, int Wo, int kpad, double m0, double m1, double m2,
+                                                        double d0, double d1, double d2) {
+  pdl_trigger();
+  const int g8 = kpad >> 3;
+  const I idx = (I)blockIdx.x * blockDim.x + threadIdx.x;
+  const I total = (I)B * Ho * Wo * g8;
+  if (idx >= total) return;
+  const int j0 = (int)(idx % (I)g8) * 8;
+  const I row = idx / (I)g8;
+  const int ox = (int)(row % (I)Wo);
+  const int oy = (int)((row / (I)Wo) % (I)Ho);
+  const int b = (int)(row / ((I)Wo * Ho));
+  const int per_tap = ch == 1 ? 2 : ch;
+  float v[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const int j = j0 + i;
+    v[i] = 0.f;
+    if (j < k * k * per_tap) {
+      const int ci = j % per_tap, tap = j / per_tap;
+      const int kh = tap / k, kw = tap % k;
+      const int iy = oy * s - p + kh, ix = ox * s - p + kw;
+      if (iy >= 0 && iy < H && ix >= 0 && ix < W) {   // the conv's zero padding pads the NORMALISED image: stays 0
+        if (ch == 1) {
+          v[i] = ci == 0 ? (float)((double)x[((long)b * H + iy) * W + ix] / 255.0) : 1.f;
+        } else {
+          const double pv = (double)x[(((long)b * H + iy) * W + ix) * ch + ci];
+          const double mean = ci == 0 ? m0 : (ci == 1 ? m1 : m2), sd = ci == 0 ? d0 : (ci == 1 ? d1 : d2);
+          v[i] = (float)((pv / 255.0 - mean) / sd);
+        }
+      }
+    }
+  }
+  store8(col + (long)row * kpad + j0, v);
+}
+CMX_API int cmx_im2col_u8(const uint8_t* x, void* col, int B, int ch, int H, int W, int k, int s, int p, int Ho, int Wo, int kpad,
+                          double mean0, double mean1, double mean2, double std0, double std1, double std2, void* stream) {
+  CMX_REQUIRE(ch == 1 || ch == 3, "im2col_u8: ch=%d (1 or 3)", ch);
+  CMX_REQUIRE(kpad >= k * k * (ch == 1 ? 2 : ch) && kpad % 8 == 0, "im2col_u8: kpad must be a multiple of 8 and >= the column count");
+  const long total = (long)B * Ho * Wo * (kpad >> 3);
+  if (total == 0) return 0;
+  if (total < (1L << 31))
+    im2col_u8_kernel<unsigned><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(x, (bf16*)col, B, ch, H, W, k, s, p, Ho, Wo, kpad, mean0,
+                                                                                 mean1, mean2, std0, std1, std2);
+  else
+    im2col_u8_kernel<long><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(x, (bf16*)col, B, ch, H, W, k, s, p, Ho, Wo, kpad, mean0, mean1,
+                                                                             mean2, std0, std1, std2);
+  LAUNCH_DONE("im2col_u8");
+}
+
 // ---- NHWC bf16 im2col (8 channels per thread) ------------------------------------------------------
 template <typename I>
 __global__ void __launch_bounds__(256) im2col_nhwc_kernel(const bf16* __restrict__ x, long ldx, bf16* __restrict__ col, int B, int H,

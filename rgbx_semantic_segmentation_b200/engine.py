@@ -93,6 +93,8 @@ class Engine:
         self.hp_streams = os.environ.get("CMX_HP_STREAMS", "0") == "1"
         self._hp = None
         self._side_forked = False
+        self.norm_mean, self.norm_std = [0.485, 0.456, 0.406], [0.229, 0.224, 0.225]   # config.norm_mean / norm_std defaults
+        self._fold_consts = None
         self._wstreams = {}
         self._wkeep = {}
         self._dec_prep = None
@@ -345,6 +347,8 @@ class Engine:
         name = f"backbone.patch_embed{s + 1}"
         C, gs = self.dims[s], self.gs[s]
         wp = self.packed[name + ".proj.weight"]
+        if s == 0 and inp[0].dtype == torch.uint8:
+            return self.pe1_fwd_u8(inp, B, H, W, save)
         if s == 0:
             k, st, pd = 7, 4, 3
             Ho, Wo = conv_out(H, k, st, pd), conv_out(W, k, st, pd)
@@ -367,6 +371,58 @@ class Engine:
         c.name, c.s, c.col, c.y, c.mean, c.rstd, c.Ho, c.Wo, c.H, c.W, c.wp = name, s, col, y, mean, rstd, Ho, Wo, H, W, wp
         return x0, Ho, Wo, c
 
+    # ---- stage-1 patch embed straight from raw uint8 images: the reference's host input pipeline fused into the load --------
+    def set_input_norm(self, mean, std):
+        """ImageNet-style per-channel mean / std of the reference's normalize() (config.norm_mean / norm_std)"""
+        self.norm_mean, self.norm_std = [float(v) for v in mean], [float(v) for v in std]
+        self._fold_consts = None
+
+    def _x_fold(self):
+        """grey X: its three replicated channels are x_c = v/255 / std_c - mean_c / std_c (RGBXDataset.py:57-59 + dataloader.py:
+        106), so conv(W, x) = conv(Wa, v/255) + conv(Wb, inside-mask) with Wa = sum_c W_c / std_c, Wb = -sum_c W_c mean_c / std_c:
+        the 7x7x3 weights folded to the [C, (tap, {value, mask})] operand of cmx_im2col_u8's grey layout (98 of 104 columns)"""
+        if self._fold_consts is None or self._fold_consts[0].device != self.dev:
+            inv = torch.tensor([1.0 / v for v in self.norm_std], device=self.dev, dtype=f32).view(1, 3, 1, 1)
+            nms = torch.tensor([-m / v for m, v in zip(self.norm_mean, self.norm_std)], device=self.dev, dtype=f32).view(1, 3, 1, 1)
+            self._fold_consts = (inv, nms)
+        inv, nms = self._fold_consts
+        Wx = self.P("backbone.extra_patch_embed1.proj.weight")
+        C = Wx.shape[0]
+        fold = self.Z(C, 104, dtype=f32)
+        fold[:, :98].view(C, 49, 2).copy_(torch.stack([(Wx * inv).sum(1), (Wx * nms).sum(1)], dim=-1).view(C, 49, 2))
+        return fold.to(bf16)
+
+    def pe1_fwd_u8(self, inp, B, H, W, save):
+        """inp = (rgb uint8 [B,H,W,3], x uint8 [B,H,W] grey or [B,H,W,3]) resident on the device"""
+        name, xname = "backbone.patch_embed1", "backbone.extra_patch_embed1"
+        C, gs = self.dims[0], self.gs[0]
+        k, st, pd = 7, 4, 3
+        Ho, Wo = conv_out(H, k, st, pd), conv_out(W, k, st, pd)
+        M = B * Ho * Wo
+        wp = self.packed[name + ".proj.weight"]
+        rgb, x = inp
+        grey = x.dim() == 3
+        y = self.E(2 * M, C, dtype=f32)
+        c = _NS()
+        if not grey:
+            col = self.E(2 * M, wp.shape[1])
+            ops.im2col_u8(rgb, col[:M], k, st, pd, Ho, Wo, self.norm_mean, self.norm_std)
+            ops.im2col_u8(x, col[M:], k, st, pd, Ho, Wo, self.norm_mean, self.norm_std)
+            ops.mm(col, wp, y, bias=self.P(name + ".proj.bias"), groups=2, gs_b=self.pk_gs[0], gs_bias=gs)
+            c.col, c.colx = col, None
+        else:
+            col, colx = self.E(M, wp.shape[1]), self.E(M, 104)
+            ops.im2col_u8(rgb, col, k, st, pd, Ho, Wo, self.norm_mean, self.norm_std)
+            ops.im2col_u8(x, colx, k, st, pd, Ho, Wo, self.norm_mean, self.norm_std)
+            ops.mm(col, wp, y[:M], bias=self.P(name + ".proj.bias"))
+            ops.mm(colx, self._x_fold(), y[M:], bias=self.P(xname + ".proj.bias"))
+            c.col, c.colx = col, colx
+        x0 = self.E(2 * M, C, dtype=f32)
+        mean, rstd = (self.E(2 * M, dtype=f32), self.E(2 * M, dtype=f32)) if save else (None, None)
+        ops.layernorm_fwd(y, self.P(name + ".norm.weight"), self.P(name + ".norm.bias"), 1e-5, x0, mean, rstd, groups=2, param_gs=gs)
+        c.name, c.s, c.y, c.mean, c.rstd, c.Ho, c.Wo, c.H, c.W, c.wp = name, 0, y, mean, rstd, Ho, Wo, H, W, wp
+        return x0, Ho, Wo, c
+
     def pe_bwd(self, c, dx0, B):
         """returns dcol (bf16, both branches stacked) for stages >= 1 (the caller scatters it with col2im), None for stage 0"""
         name, s = c.name, c.s
@@ -376,6 +432,19 @@ class Engine:
         ops.layernorm_bwd(dx0, c.y, c.mean, c.rstd, self.P(name + ".norm.weight"), dx=dy,
                           dgamma=self.G(name + ".norm.weight"), dbeta=self.G(name + ".norm.bias"),
                           dbias=self.G(name + ".proj.bias"), groups=2, param_gs=gs)   # conv bias gradient = column sums of dy
+        if getattr(c, "colx", None) is not None:
+            # grey-X input mode: the two branches have different im2col widths; the folded X weight gradient is chained back to
+            # the three channel slices of extra_patch_embed1.proj.weight: dW_c = dWa / std_c - dWb mean_c / std_c
+            M = M2 // 2
+            with self._wgrad_ctx(dy, c.col, c.colx):
+                ops.mm(dy[:M], c.col, self.packed_g[name + ".proj.weight"], ta=True, tb=True, accumulate=True)
+                gfold = self.Z(C, 104)
+                ops.mm(dy[M:], c.colx, gfold, ta=True, tb=True, accumulate=True)
+                inv, nms = self._fold_consts
+                g2 = gfold[:, :98].view(C, 49, 2)
+                self.G("backbone.extra_patch_embed1.proj.weight").add_(g2[:, :, 0].reshape(C, 1, 7, 7) * inv + g2[:, :, 1].reshape(C, 1, 7, 7) * nms)
+            self._wgrad_join()
+            return None
         with self._wgrad_ctx(dy, c.col):   # packed gradient; unpacked for all convs at the end of the backward pass
             ops.mm(dy, c.col, self.packed_g[name + ".proj.weight"], ta=True, tb=True, accumulate=True, groups=2, gs_c=self.pk_gs[s])
         dcol = None
@@ -435,8 +504,15 @@ class Engine:
             # the probabilities are only stored when the (default) backward reads them back
             Pm = self.E(B2 * heads * N, Np)[:, :Nk] if save and c.lse is None else None
             ops.attn_fwd(q, kv, O, B2, N, Nk, heads, scale, p_out=Pm, lse=c.lse)
+        elif d == 64 and self.fused_attention:
+            # long key axis (Nkv = 880 / 920 at 720x1280): the fused kernel per chunk of <= 320 keys + exact combination; the
+            # backward recomputes the probabilities from q, k and the log-sum-exp (no [N, Nkv] tensor in either direction)
+            c.lse = self.E(B2 * heads * N, dtype=f32)
+            Pm = None
+            ops.attn_fwd_chunked(q, kv, O, c.lse, B2, N, Nk, heads, scale)
         else:
-            # unfused path (head_dim != 64 or Nkv > 320): S = scale * Q K^T (fp32, transient), P = softmax(S), O = P V
+            # unfused path (head_dim != 64: mit_b0): S = scale * Q K^T (fp32, transient), P = softmax(S), O = P V
+            c.lse = None
             S = self.E(B2 * heads * N, Np, dtype=f32)[:, :Nk]
             ops.gemm_raw(q, kv, S, N, Nk, d, C, 2 * C, Np, batch=(B2, heads), sA=(N * C, d), sB=(Nk * 2 * C, d),
                          sC=(heads * N * Np, N * Np), alpha=scale)
@@ -533,7 +609,9 @@ class Engine:
                          sB=(N * C, d), sC=(Nk * 2 * C, d), accumulate=not direct, split_k=split)
         dq = self.E(M, C)
         dS = None if recompute else self.E(B2 * heads * N, Np)[:, :Nk]
-        if recompute:
+        if recompute and Nk > ops.ATTN_MAX_NK:
+            ops.attn_dq_chunked(c.q, dO, c.kv, c.lse, delta, dq, B2, N, Nk, heads, scale)
+        elif recompute:
             ops.attn_dq(c.q, dO, c.kv, c.lse, delta, dq, B2, N, Nk, heads, scale)
         elif d == 64 and Nk <= ops.ATTN_MAX_NK and self.fused_attention:
             # fused: dP = dO V^T stays in tensor memory, dS in place of the TMA-loaded P tile, dQ = dS K
@@ -991,7 +1069,7 @@ class Engine:
     def _encode(self, rgb, x, training, save, dp):
         """dual_segformer.py:366-442.  The RGB and X branch of a stage run as ONE chain of grouped launches over the stacked
         tensors [2, B*N, C] (per-branch weights selected by the group stride), not as two chains of half-sized launches."""
-        B, _, H, W = rgb.shape
+        B, H, W = (rgb.shape[0], rgb.shape[1], rgb.shape[2]) if rgb.dtype == torch.uint8 else (rgb.shape[0], rgb.shape[2], rgb.shape[3])
         inp = (rgb, x)
         ctx = _NS()
         ctx.stages = []
@@ -1099,7 +1177,7 @@ class Engine:
         self._begin(rgb, x)
         self.decoder_prep()
         training = self.model.training
-        B, _, H, W = rgb.shape
+        B, H, W = (rgb.shape[0], rgb.shape[1], rgb.shape[2]) if rgb.dtype == torch.uint8 else (rgb.shape[0], rgb.shape[2], rgb.shape[3])
         dp, dm = self._make_dp(B, training)
         feats, sizes, _ = self._encode(rgb, x, training, False, dp)
         logits, _ = self.decoder_fwd(feats, sizes, B, training, dm, False)
@@ -1122,7 +1200,7 @@ class Engine:
         self._begin(rgb, x)
         self.decoder_prep()
         training = self.model.training
-        B, _, H, W = rgb.shape
+        B, H, W = (rgb.shape[0], rgb.shape[1], rgb.shape[2]) if rgb.dtype == torch.uint8 else (rgb.shape[0], rgb.shape[2], rgb.shape[3])
         assert B <= 16, "per-GPU batch > 16 is not supported by the FRM small-M kernels"
         label = label.to(torch.int64).contiguous()
         if with_grad:
@@ -1225,7 +1303,12 @@ class Engine:
     def _begin(self, rgb, x):
         if not rgb.is_cuda:
             raise RuntimeError("cmx_b200: inputs must be CUDA tensors — the hot path has no CPU fallback")
-        assert rgb.shape == x.shape and rgb.dim() == 4 and rgb.shape[1] == 3, "expected two [B,3,H,W] inputs"
+        if rgb.dtype == torch.uint8:   # raw images: [B,H,W,3] + [B,H,W,3] or grey [B,H,W] (input pipeline fused into patch embed 1)
+            assert x.dtype == torch.uint8 and rgb.dim() == 4 and rgb.shape[3] == 3 and tuple(x.shape[:3]) == tuple(rgb.shape[:3]) and \
+                (x.dim() == 3 or tuple(x.shape) == tuple(rgb.shape)), "expected uint8 [B,H,W,3] and [B,H,W] / [B,H,W,3] inputs"
+            assert rgb.is_contiguous() and x.is_contiguous()
+        else:
+            assert rgb.shape == x.shape and rgb.dim() == 4 and rgb.shape[1] == 3, "expected two [B,3,H,W] inputs"
         if rgb.device.type == "cuda" and torch.cuda.current_device() != rgb.device.index:
             # the C launchers enqueue on the current device's stream and never call cudaSetDevice
             raise RuntimeError("cmx_b200: inputs are on %s but the current CUDA device is %d - call torch.cuda.set_device(%d) "

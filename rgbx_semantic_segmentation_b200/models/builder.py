@@ -31,6 +31,15 @@ def _cfg_get(cfg, key, default):
     return getattr(cfg, key, default)
 
 
+def _prep(rgb, modal_x):
+    """fp32 NCHW inputs as the reference gets them from its loader - or RAW uint8 images (rgb [B,H,W,3], modal_x [B,H,W] grey or
+    [B,H,W,3]): the normalisation / thermal replication / HWC->CHW of dataloader.py:85-112 then happens inside the stage-1
+    patch-embed load"""
+    if rgb.dtype == torch.uint8:
+        return rgb.contiguous(), modal_x.contiguous()
+    return rgb.float().contiguous(), modal_x.float().contiguous()
+
+
 class _CMXStep(torch.autograd.Function):
     """Autograd boundary: forward runs the fused forward+backward step on the engine (optionally as one CUDA
     graph replay); backward only hands the finished gradients (times grad_output) to the parameters, so DDP's
@@ -84,6 +93,9 @@ class EncoderDecoder(nn.Module):
         self._engine = None
         self._graphs = {}
         self._flat_dp = None
+        # per-channel mean / std of the reference's normalize() for the raw-uint8 input mode (config.norm_mean / norm_std)
+        self.norm_mean = list(_cfg_get(cfg, "norm_mean", [0.485, 0.456, 0.406]))
+        self.norm_std = list(_cfg_get(cfg, "norm_std", [0.229, 0.224, 0.225]))
         self.use_cuda_graph = os.environ.get("CMX_CUDA_GRAPH", "1") != "0"
 
     # ---- reference API ---------------------------------------------------------------------------
@@ -103,7 +115,7 @@ class EncoderDecoder(nn.Module):
                 nn.init.constant_(m.bias, 0)
 
     def encode_decode(self, rgb, modal_x):
-        return self._eng().forward_logits(rgb.float().contiguous(), modal_x.float().contiguous())
+        return self._eng().forward_logits(*_prep(rgb, modal_x))
 
     def forward(self, rgb, modal_x, label=None):
         if label is None:
@@ -115,8 +127,7 @@ class EncoderDecoder(nn.Module):
             if any(p.requires_grad for p in params):
                 return _CMXStep.apply(self, rgb, modal_x, label, *params)
         with torch.no_grad():
-            return self._eng().forward_loss(rgb.float().contiguous(), modal_x.float().contiguous(), label, ign,
-                                            with_grad=False, focal=focal)
+            return self._eng().forward_loss(*_prep(rgb, modal_x), label, ign, with_grad=False, focal=focal)
 
     def _criterion_spec(self):
         """-> (ignore_index, None | (w_ce, w_focal, gamma, alpha) | ("dice", alpha, smooth)) for the criteria fused into the loss
@@ -154,6 +165,7 @@ class EncoderDecoder(nn.Module):
     def _eng(self):
         if self._engine is None:
             self._engine = Engine(self)
+            self._engine.set_input_norm(self.__dict__.get("norm_mean", [0.485, 0.456, 0.406]), self.__dict__.get("norm_std", [0.229, 0.224, 0.225]))
         return self._engine
 
     def flatten_parameters(self):
@@ -175,8 +187,8 @@ class EncoderDecoder(nn.Module):
         return cache[1]
 
     def _forward_eval(self, rgb, modal_x):
-        rgb, modal_x = rgb.float().contiguous(), modal_x.float().contiguous()
-        key = ("eval", tuple(rgb.shape), self.training, rgb.device.index)
+        rgb, modal_x = _prep(rgb, modal_x)
+        key = ("eval", tuple(rgb.shape), tuple(modal_x.shape), rgb.dtype, self.training, rgb.device.index)
         if not self.use_cuda_graph or self.training:
             return self._eng().forward_logits(rgb, modal_x)
         self._eng()._ensure_flat(rgb.device)  # parameters moved / re-created since the capture -> graphs were dropped
@@ -203,12 +215,13 @@ class EncoderDecoder(nn.Module):
         (their all-reduce starts there and overlaps the rest of the backward pass).  With CUDA graphs the step is captured
         as one graph per segment between such points, all sharing one memory pool (NCCL itself is never captured)."""
         from ..parallel import allreduce_slice_async
-        rgb, modal_x = rgb.float().contiguous(), modal_x.float().contiguous()
+        rgb, modal_x = _prep(rgb, modal_x)
         ign, focal = self._criterion_spec()
         eng = self._eng()
         eng._ensure_flat(rgb.device)          # parameters moved / re-created since the capture -> graphs were dropped
         eng.split_at_early = self._flat_dp is not None
-        key = ("train", tuple(rgb.shape), self.training, rgb.device.index, focal, ign, eng.stochastic, self._flat_dp is not None)
+        key = ("train", tuple(rgb.shape), tuple(modal_x.shape), rgb.dtype, self.training, rgb.device.index, focal, ign, eng.stochastic,
+               self._flat_dp is not None)
 
         def needs_host(ev):
             return ev != "early_gradients_ready" or self._flat_dp is not None

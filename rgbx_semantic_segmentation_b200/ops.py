@@ -283,6 +283,17 @@ def im2col_nchw(x, col, k, s, p, Ho, Wo):
     return col
 
 
+def im2col_u8(x, col, k, s, p, Ho, Wo, mean, std):
+    """raw uint8 image [B,H,W,3] or grey [B,H,W] on the device -> bf16 im2col rows of the normalised image (float64 normalisation
+    in the gather; grey: one column per tap)"""
+    assert x.dtype == torch.uint8 and x.is_contiguous()
+    B, H, W = x.shape[:3]
+    ch = 1 if x.dim() == 3 else x.shape[3]
+    _call("cmx_im2col_u8", x.data_ptr(), col.data_ptr(), B, ch, H, W, k, s, p, Ho, Wo, col.shape[1], mean[0], mean[1], mean[2],
+          std[0], std[1], std[2], _stream(), nbytes=_nb(x, col))
+    return col
+
+
 def im2col_nhwc(x, col, B, H, W, k, s, p, Ho, Wo):
     C = x.shape[1]
     _call("cmx_im2col_nhwc", x.data_ptr(), _ld(x), col.data_ptr(), B, H, W, C, k, s, p, Ho, Wo, _stream(), nbytes=_nb(x, col))
@@ -353,12 +364,33 @@ def axpby(a, x, b, y, out):
 ATTN_MAX_NK = 320
 
 
-def attn_fwd(q, kv, o, B, N, Nk, heads, scale, p_out=None, lse=None):
-    """q [B*N, C], kv [B*Nk, 2C], o [B*N, C] (bf16, head_dim 64); p_out: bf16 view [B*heads*N, Nk] with padded ld"""
+def attn_fwd(q, kv, o, B, N, Nk, heads, scale, p_out=None, lse=None, kv_rows=0, kv_row0=0):
+    """q [B*N, C], kv [B*Nk, 2C], o [B*N, C] (bf16, head_dim 64); p_out: bf16 view [B*heads*N, Nk] with padded ld.
+    kv_rows / kv_row0: this call attends to the Nk keys starting at key row kv_row0 of every sample, whose kv holds kv_rows key
+    rows (key-chunked attention, see attn_fwd_chunked)"""
     _cuda(q, kv, o)
-    _call("cmx_attn_fwd", q.data_ptr(), _ld(q), kv.data_ptr(), _ld(kv), o.data_ptr(), _ld(o), _p(p_out),
-          _ld(p_out) if p_out is not None else 0, _p(lse), B, N, Nk, heads, scale, _stream(), tag=_tg("cmx_attn_fwd", B, N, Nk, heads),
-          flops=4 * B * heads * N * Nk * 64, nbytes=_nb(q, kv, o) + (B * heads * N * Nk * 2 if p_out is not None else 0))
+    _call("cmx_attn_fwd", q.data_ptr(), _ld(q), kv.data_ptr() + 2 * kv_row0 * _ld(kv), _ld(kv), o.data_ptr(), _ld(o), _p(p_out),
+          _ld(p_out) if p_out is not None else 0, _p(lse), B, N, Nk, heads, scale, kv_rows, _stream(), tag=_tg("cmx_attn_fwd", B, N, Nk, heads),
+          flops=4 * B * heads * N * Nk * 64, nbytes=_nb(q, o) + 2 * B * Nk * kv.shape[1] + (B * heads * N * Nk * 2 if p_out is not None else 0))
+    return o
+
+
+ATTN_CHUNK = 320
+
+
+def attn_fwd_chunked(q, kv, o, lse, B, N, Nk, heads, scale):
+    """fused attention over a key axis longer than ATTN_MAX_NK (e.g. Nkv = 880 / 920 at 720x1280): the fused kernel per chunk of
+    <= 320 keys (normalised chunk output + chunk log-sum-exp), then the exact combination over the chunks - no [N, Nkv]
+    score / probability tensor exists.  o (bf16 [B*N, C]) and lse (fp32 [B*heads*N]) are written."""
+    nc = (Nk + ATTN_CHUNK - 1) // ATTN_CHUNK
+    M, C = o.shape
+    o_parts = torch.empty(nc, M, C, device=o.device, dtype=o.dtype)
+    lse_parts = torch.empty(nc, B * heads * N, device=o.device, dtype=torch.float32)
+    for c in range(nc):
+        k0 = c * ATTN_CHUNK
+        attn_fwd(q, kv, o_parts[c], B, N, min(ATTN_CHUNK, Nk - k0), heads, scale, lse=lse_parts[c], kv_rows=Nk, kv_row0=k0)
+    _call("cmx_attn_combine", o_parts.data_ptr(), M * C, C, lse_parts.data_ptr(), B * heads * N, nc, o.data_ptr(), _ld(o), lse.data_ptr(),
+          B, N, heads, _stream(), nbytes=_nb(o_parts, o))
     return o
 
 
@@ -392,15 +424,28 @@ def attn_dkv(q, d_o, kv, lse, delta, dkv32, B, N, Nk, heads, scale):
     return dkv32
 
 
-def attn_dq(q, d_o, kv, lse, delta, dq, B, N, Nk, heads, scale):
-    """(engine: CMX_ATTN_DKV_RECOMPUTE=1 only) query-major dQ (bf16 [B*N, C]) with recomputed probabilities (Nk <= 384)"""
+def attn_dq(q, d_o, kv, lse, delta, dq, B, N, Nk, heads, scale, kv_rows=0, kv_row0=0):
+    """query-major dQ (bf16 [B*N, C]) with recomputed probabilities (Nk <= 384); kv_rows / kv_row0 as in attn_fwd: with the
+    log-sum-exp and delta of the FULL key axis, a call over one key chunk gives that chunk's additive share of dQ"""
     _cuda(q, d_o, kv, lse, delta, dq)
     if lse.dtype != torch.float32 or delta.dtype != torch.float32:
         raise TypeError("attn_dq: lse and delta must be fp32")
     nkb = (Nk + 127) // 128
-    _call("cmx_attn_dq", q.data_ptr(), _ld(q), d_o.data_ptr(), _ld(d_o), kv.data_ptr(), _ld(kv), lse.data_ptr(), delta.data_ptr(),
-          dq.data_ptr(), _ld(dq), B, N, Nk, heads, scale, _stream(),
-          flops=6 * B * heads * N * nkb * 128 * 64, nbytes=_nb(q, d_o, kv, dq, lse, delta))
+    _call("cmx_attn_dq", q.data_ptr(), _ld(q), d_o.data_ptr(), _ld(d_o), kv.data_ptr() + 2 * kv_row0 * _ld(kv), _ld(kv), lse.data_ptr(),
+          delta.data_ptr(), dq.data_ptr(), _ld(dq), B, N, Nk, heads, scale, kv_rows, _stream(),
+          flops=6 * B * heads * N * nkb * 128 * 64, nbytes=_nb(q, d_o, dq, lse, delta) + 2 * B * Nk * kv.shape[1])
+    return dq
+
+
+def attn_dq_chunked(q, d_o, kv, lse, delta, dq, B, N, Nk, heads, scale):
+    """dQ over a key axis longer than the dq kernel's 384 keys: one call per chunk (full-axis lse / delta), partials summed"""
+    nc = (Nk + ATTN_CHUNK - 1) // ATTN_CHUNK
+    M, C = dq.shape
+    parts = torch.empty(nc, M, C, device=dq.device, dtype=dq.dtype)
+    for c in range(nc):
+        k0 = c * ATTN_CHUNK
+        attn_dq(q, d_o, kv, lse, delta, parts[c], B, N, min(ATTN_CHUNK, Nk - k0), heads, scale, kv_rows=Nk, kv_row0=k0)
+    _call("cmx_sum_parts_bf16", parts.data_ptr(), M * C, nc, dq.data_ptr(), M * C, _stream(), nbytes=_nb(parts, dq))
     return dq
 
 

@@ -145,25 +145,44 @@ def test_autograd_handoff_through_the_module_call(mock_lib, monkeypatch):
 
 
 @pytest.mark.parametrize("recompute", ["0", "1"])
-@pytest.mark.parametrize("backbone,H,W,fused", [("mit_b0", 72, 104, False),    # head_dim 32: unfused attention, odd sizes
-                                                 ("mit_b1", 608, 608, False)])  # Nkv = 361 > 320 in every stage: unfused
-def test_unfused_attention_shapes_ignore_the_experimental_flag(mock_lib, monkeypatch, recompute, backbone, H, W, fused):
+def test_head_dim_32_takes_the_unfused_attention_path(mock_lib, monkeypatch, recompute):
+    """mit_b0 (head_dim 32, odd sizes): S-materialising batched GEMM + softmax path, whatever the experimental flag says"""
     monkeypatch.setenv("CMX_ATTN_DKV_RECOMPUTE", recompute)
 
     class Cfg(_Cfg):
         pass
-    Cfg.backbone = backbone
+    Cfg.backbone = "mit_b0"
     torch.manual_seed(0)
     m = EncoderDecoder(cfg=Cfg, criterion=nn.CrossEntropyLoss(reduction='mean', ignore_index=255), norm_layer=nn.BatchNorm2d)
     m.train()
-    rgb = torch.randn(1, 3, H, W).as_subclass(_ReportsCuda)
-    x = torch.randn(1, 3, H, W).as_subclass(_ReportsCuda)
-    lab = torch.randint(0, 9, (1, H, W))
+    rgb = torch.randn(1, 3, 72, 104).as_subclass(_ReportsCuda)
+    x = torch.randn(1, 3, 72, 104).as_subclass(_ReportsCuda)
+    lab = torch.randint(0, 9, (1, 72, 104))
     loss = m._eng().forward_loss(rgb, x, lab, 255, with_grad=True, focal=None)
     assert loss.numel() == 1
     n_attn = sum(m.backbone.depths)
     assert mock_lib["cmx_attn_fwd"] == 0 and mock_lib["cmx_attn_dkv"] == 0 and mock_lib["cmx_attn_dq"] == 0
     assert mock_lib["cmx_softmax_rows_fwd"] == mock_lib["cmx_softmax_rows_bwd"] == n_attn
+
+
+def test_long_key_axis_takes_the_key_chunked_fused_path(mock_lib):
+    """mit_b1 at 608x608: Nkv = 361 > 320 in every stage -> fused kernel per key chunk + combine in forward, recompute kernels
+    (dkv once, dq per chunk + sum) in backward; no score / probability tensor, no softmax kernels"""
+    class Cfg(_Cfg):
+        pass
+    Cfg.backbone = "mit_b1"
+    torch.manual_seed(0)
+    m = EncoderDecoder(cfg=Cfg, criterion=nn.CrossEntropyLoss(reduction='mean', ignore_index=255), norm_layer=nn.BatchNorm2d)
+    m.train()
+    rgb = torch.randn(1, 3, 608, 608).as_subclass(_ReportsCuda)
+    x = torch.randn(1, 3, 608, 608).as_subclass(_ReportsCuda)
+    lab = torch.randint(0, 9, (1, 608, 608))
+    loss = m._eng().forward_loss(rgb, x, lab, 255, with_grad=True, focal=None)
+    assert loss.numel() == 1
+    n_attn = sum(m.backbone.depths)
+    assert mock_lib["cmx_attn_fwd"] == 2 * n_attn and mock_lib["cmx_attn_combine"] == n_attn
+    assert mock_lib["cmx_attn_dkv"] == n_attn and mock_lib["cmx_attn_dq"] == 2 * n_attn and mock_lib["cmx_sum_parts_bf16"] == n_attn
+    assert mock_lib["cmx_softmax_rows_fwd"] == 0 and mock_lib["cmx_softmax_rows_bwd"] == 0 and mock_lib["cmx_attn_bwd"] == 0
 
 
 def test_sync_batchnorm_orchestration_two_allreduce_events(mock_lib):

@@ -611,6 +611,45 @@ def test_attention_dkv_recompute(B, N, Nk, heads):
         close(dq, dq_ref, 2e-2, 2e-2 * float(dq_ref.abs().max()), "dQ")
 
 
+@pytest.mark.parametrize("B,N,Nk,heads", [(2, 700, 880, 2), (1, 920, 920, 8), (1, 3600, 880, 5), (2, 300, 321, 1)])
+def test_attention_key_chunked_fwd_bwd(B, N, Nk, heads):
+    """Nkv above the fused kernels' resident-K/V limit (BASELINE configs[3]: 880 / 920 keys at 720x1280): fused forward per chunk
+    of <= 320 keys + exact log-sum-exp combination, dQ as the sum of per-chunk shares - against fp32 softmax attention and its
+    autograd on the same bf16 inputs.  No [N, Nkv] tensor is allocated by the product path."""
+    torch.manual_seed(13)
+    d = 64
+    C = heads * d
+    scale = d ** -0.5
+    q = rnd(B * N, C, dtype=bf)
+    kv = rnd(B * Nk, 2 * C, dtype=bf)
+    dO = rnd(B * N, C, dtype=bf)
+    qf = q.float().view(B, N, heads, d).permute(0, 2, 1, 3).contiguous().requires_grad_(True)
+    kf = kv.float().view(B, Nk, 2, heads, d)[:, :, 0].permute(0, 2, 1, 3).contiguous().requires_grad_(True)
+    vf = kv.float().view(B, Nk, 2, heads, d)[:, :, 1].permute(0, 2, 1, 3).contiguous().requires_grad_(True)
+    s = (qf @ kf.transpose(-1, -2)) * scale
+    of = torch.softmax(s, -1) @ vf
+    dOf = dO.float().view(B, N, heads, d).permute(0, 2, 1, 3)
+    of.backward(dOf)
+    o = torch.full((B * N, C), 5.0, device=DEV, dtype=bf)
+    lse = torch.full((B * heads * N,), 5.0, device=DEV)
+    ops.attn_fwd_chunked(q, kv, o, lse, B, N, Nk, heads, scale)
+    o_ref = of.detach().permute(0, 2, 1, 3).reshape(B * N, C)
+    close(o, o_ref, 2e-2, 2e-2 * float(o_ref.abs().max()), "chunked attention O")
+    close(lse, torch.logsumexp(s.detach(), -1).reshape(-1), 2e-3, 2e-3, "chunked attention lse")
+    delta = torch.empty(B * heads * N, device=DEV)
+    ops.attn_delta(dO, o, delta, B, N, heads)
+    dq = torch.full((B * N, C), 9.0, device=DEV, dtype=bf)
+    ops.attn_dq_chunked(q, dO, kv, lse, delta, dq, B, N, Nk, heads, scale)
+    dq_ref = qf.grad.permute(0, 2, 1, 3).reshape(B * N, C)
+    close(dq, dq_ref, 2e-2, 2e-2 * float(dq_ref.abs().max()), "chunked dQ")
+    dkv32 = torch.zeros(B * Nk, 2 * C, device=DEV)
+    ops.attn_dkv(q, dO, kv, lse, delta, dkv32, B, N, Nk, heads, scale)
+    got = dkv32.view(B, Nk, 2, heads, d)
+    dk_ref, dv_ref = kf.grad.permute(0, 2, 1, 3), vf.grad.permute(0, 2, 1, 3)
+    close(got[:, :, 1], dv_ref, 2e-2, 2e-2 * float(dv_ref.abs().max()), "dV")
+    close(got[:, :, 0], dk_ref, 2e-2, 2e-2 * float(dk_ref.abs().max()), "dK")
+
+
 # ---------------------------------------------------------------------------------------------
 # grouped launches (group = modality branch): one launch over two stacked problems with per-group parameters lying a
 # fixed number of elements apart in one flat buffer must equal two separate launches
