@@ -150,11 +150,21 @@ constexpr int TC_BK = 64;
 // loads/MMAs/epilogue of the other, and kernels of the other streams (the second modality branch, the weight-gradient
 // companion streams) or the PDL-launched successor can share the SM.  BN > 128: 8 epilogue warps (two per lane quarter,
 // interleaved 32-column chunks), the whole SM.
-__host__ __device__ constexpr int tc_epi_warps(int bn) { return bn <= 128 ? 4 : 8; }
-__host__ __device__ constexpr int tc_threads(int bn) { return 64 + 32 * tc_epi_warps(bn); }
+// EW = epilogue warps per CTA (4 = one per TMEM lane quarter, 8 = two per quarter on interleaved 32-column chunks).  The epilogue
+// of the K <= 256 shapes is the whole kernel (ncu, profiles/r2_gemm_epilogue_*: every warp issues one instruction per ~8 cycles,
+// the MMA issuer waits for the accumulator buffer all the time), so the two-CTA-per-SM shapes can run 8 epilogue warps each
+// (16 per SM = 4 per scheduler) with ONE 4 KB staging buffer per warp instead of two.
+__host__ __device__ constexpr int tc_threads(int ew) { return 64 + 32 * ew; }
 __host__ __device__ constexpr int tc_ctas_per_sm(int bn) { return bn <= 128 ? 2 : 1; }
-__host__ __device__ constexpr uint32_t tc_cstage_bytes(int bn) { return tc_epi_warps(bn) * 2 * 4096; }  // per epilogue warp: 2 x (32 rows x 128 B)
+__host__ __device__ constexpr int tc_nbuf(int bn, int ew) { return (ew == 4 || bn > 128) ? 2 : 1; }  // staging buffers per epilogue warp
+__host__ __device__ constexpr uint32_t tc_cstage_bytes(int bn, int ew) { return ew * tc_nbuf(bn, ew) * 4096; }  // (32 rows x 128 B) each
 __host__ __device__ constexpr int tc_smem_budget(int bn) { return bn <= 128 ? 110 * 1024 : 200 * 1024; }
+
+template <int EMODE_, int CDT_, int RES_, bool FULL_>
+struct EK {   // compile-time description of one epilogue body, see gemm_tc_kernel
+  static constexpr int EMODE = EMODE_, CDT = CDT_, RES = RES_;
+  static constexpr bool FULL = FULL_;
+};
 
 struct TcSched {
   int tiles_n, tiles_m, batch2, nbatch, splits;
@@ -171,8 +181,8 @@ struct TcSched {
   } while (0)
 
 
-template <int BN, bool A_MN, bool B_MN, bool BATCHED>
-__global__ void __launch_bounds__(tc_threads(BN), tc_ctas_per_sm(BN)) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+template <int BN, bool A_MN, bool B_MN, bool BATCHED, int EW>
+__global__ void __launch_bounds__(tc_threads(EW), tc_ctas_per_sm(BN)) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                const __grid_constant__ CUtensorMap tmB,
                                                                const __grid_constant__ CUtensorMap tmC, Epi epi0,
                                                                TcSched sc) {
@@ -183,9 +193,11 @@ __global__ void __launch_bounds__(tc_threads(BN), tc_ctas_per_sm(BN)) gemm_tc_ke
   constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr uint32_t ACC_STRIDE = BN <= 64 ? 64 : BN <= 128 ? 128 : 256;  // TMEM columns per accumulator buffer
   constexpr uint32_t TMEM_COLS = 2 * ACC_STRIDE;
-  constexpr int TC_EPI_WARPS = tc_epi_warps(BN);
+  constexpr int TC_EPI_WARPS = EW;
   constexpr int NH = TC_EPI_WARPS / 4;  // warps per TMEM lane quarter = column interleave factor
-  constexpr uint32_t TC_CSTAGE_BYTES = tc_cstage_bytes(BN);
+  constexpr int NBUF = tc_nbuf(BN, EW);
+  constexpr bool SIMPLE = tc_ctas_per_sm(BN) == 2;  // one register set: the co-resident CTA hides the tcgen05.ld latency
+  constexpr uint32_t TC_CSTAGE_BYTES = tc_cstage_bytes(BN, EW);
   const int stages = sc.stages;
 
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -333,7 +345,7 @@ __global__ void __launch_bounds__(tc_threads(BN), tc_ctas_per_sm(BN)) gemm_tc_ke
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
     const int etid = threadIdx.x - 64;  // 0 .. 32 * TC_EPI_WARPS - 1
-    const uint32_t my_stage = cstage_base + (uint32_t)(warp - 2) * 8192u;
+    const uint32_t my_stage = cstage_base + (uint32_t)(warp - 2) * (NBUF * 4096u);
     uint32_t lt = 0, nstore = 0;
     float bias_pf[BN / 32];  // next tile's bias values (lane-strided), NH == 1 only
 #pragma unroll
@@ -367,11 +379,13 @@ __global__ void __launch_bounds__(tc_threads(BN), tc_ctas_per_sm(BN)) gemm_tc_ke
 #pragma unroll
           for (int i = 0; i < BN / 32; i++) bias_pf[i] = (n0 + lane + 32 * i < epi0.N) ? bp[n0 + lane + 32 * i] : 0.f;
         }
-        if (epi.bias) {
+        {
+          // (the copy is read unconditionally by the alpha / bias epilogue bodies: zeros without a bias, or for split-K
+          // slices other than the first)
           __syncwarp();   // every lane has finished reading the previous tile's copy
 #pragma unroll
           for (int i = 0; i < BN / 32; i++)
-            asm volatile("st.shared.f32 [%0], %1;" ::"r"(sb_addr + 4u * (lane + 32 * i)), "f"(bias_pf[i]) : "memory");
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(sb_addr + 4u * (lane + 32 * i)), "f"(epi.bias ? bias_pf[i] : 0.f) : "memory");
           __syncwarp();
         }
         const long tn = t + gridDim.x;
@@ -386,9 +400,9 @@ __global__ void __launch_bounds__(tc_threads(BN), tc_ctas_per_sm(BN)) gemm_tc_ke
       } else {
         // bias slice of this tile -> shared memory (double-buffered by tile parity; one named barrier per tile)
         sb_addr = bias_base + (lt & 1u) * 1024u;
-        if (epi.bias) {
+        {   // (read unconditionally by the alpha / bias epilogue bodies: zeros without a bias)
           for (int i = etid; i < BN; i += 32 * TC_EPI_WARPS) {
-            const float bv = (n0 + i < epi.N) ? epi.bias[n0 + i] : 0.f;
+            const float bv = (epi.bias && n0 + i < epi.N) ? epi.bias[n0 + i] : 0.f;
             asm volatile("st.shared.f32 [%0], %1;" ::"r"(sb_addr + 4u * i), "f"(bv) : "memory");
           }
         }
@@ -409,41 +423,76 @@ __global__ void __launch_bounds__(tc_threads(BN), tc_ctas_per_sm(BN)) gemm_tc_ke
         // ---- smem-staged TMA store: warp-private [32 rows x 128 B] boxes, SWIZZLE_128B, double buffered.
         // The tcgen05.ld of chunk k+1 is issued before the math / st.shared of chunk k (two register sets).
         const int UC = epi.c_dtype == CMX_F32 ? 1 : 2;   // chunks per store unit: 32 fp32 or 64 bf16 columns = 128 B
-        // k-th chunk of this warp (units half, half+NH, ...), -1 when exhausted; a trailing partial unit
-        // (BN = 160 with bf16) is excluded here and handled by the per-thread store path below
-        auto chunk_of = [&](int k) -> int {
-          const int u = half + NH * (k / UC);
-          const int c = u * UC + (k % UC);
-          if ((u + 1) * UC * 32 > BN || n0 + c * 32 >= epi.N) return -1;
-          return c;
-        };
-        auto process = [&](auto mode_tag, uint32_t* r, int c) {
-          constexpr int EMODE = decltype(mode_tag)::value;
-          const int cc = c % UC;
-          const uint32_t buf = my_stage + (nstore & 1u) * 4096u;
+        // The epilogue is the critical path of every K <= 512 shape (ncu: one instruction per ~8 cycles and warp, a fifth of
+        // them branches), so the three hot combinations are compiled as branch-free bodies, chosen per tile by a warp-uniform
+        // jump; everything else (ragged tiles, other dtype / residual combinations) takes the generic body.
+        //   EK<EMODE, CDT, RES, FULL>: EMODE 0 plain / 1 alpha+bias / 2 also ReLU + row scale; CDT 0 bf16, 1 fp32, 2 runtime;
+        //   RES 0 none, 1 fp32, 2 runtime; FULL: all 128 rows and BN columns of the tile are in range
+        auto process = [&](auto kind_tag, uint32_t* r, int c) {
+          using K = decltype(kind_tag);
+          constexpr int EMODE = K::EMODE;
+          const bool f32out = K::CDT == 2 ? (epi.c_dtype == CMX_F32) : (K::CDT == 1);
+          const int UCk = f32out ? 1 : 2;
+          const int cc = c % UCk;
+          const uint32_t buf = my_stage + (NBUF == 2 ? (nstore & 1u) * 4096u : 0u);
           const bool trc = (warp == 4 && lane == 0);
           if (cc == 0) {
             if (trc) TC_TRACE(3, lt, 0);
-            if (lane == 0) tma_store_wait_read<1>();  // the store that used this buffer two units ago has read it
+            if (lane == 0) tma_store_wait_read<NBUF - 1>();  // the store that last used this buffer has read it
             __syncwarp();
             if (trc) TC_TRACE(3, lt, 1);
           }
+          // residual row segment of this chunk: one 64-bit address computation per chunk
+          const long ccol = (long)n0 + c * 32;
+          const bool cfull = K::FULL || ccol + 32 <= epi.N;
+          const bool rres = K::RES == 0 ? false : (K::FULL && K::RES == 1 ? true : (epi.res != nullptr && row_ok));
+          const bool res_f32 = K::RES == 1 || epi.r_dtype == CMX_F32;
+          const float* res32 = reinterpret_cast<const float*>(epi.res) + row * epi.ldr + ccol;
+          const bf16* res16 = reinterpret_cast<const bf16*>(epi.res) + row * epi.ldr + ccol;
+          float rr[2][8];   // residual values, fetched one 8-column group ahead of the math
+          auto res_fetch = [&](int g) {
+            if (res_f32) load8(res32 + g * 8, rr[g & 1]);
+            else load8(res16 + g * 8, rr[g & 1]);
+          };
+          if (rres && cfull) res_fetch(0);
 #pragma unroll
           for (int g = 0; g < 4; g++) {
             float v[8];
 #pragma unroll
             for (int j = 0; j < 8; j++) v[j] = __uint_as_float(r[g * 8 + j]);
-            float sbv[8];
-#pragma unroll
-            for (int j = 0; j < 8; j++) sbv[j] = 0.f;
-            if (EMODE != 0 && epi.bias) {
+            if (EMODE != 0) {
+              float sbv[8];
               const uint32_t ba = sb_addr + 4u * (c * 32 + g * 8);
               asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(sbv[0]), "=f"(sbv[1]), "=f"(sbv[2]), "=f"(sbv[3]) : "r"(ba));
               asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(sbv[4]), "=f"(sbv[5]), "=f"(sbv[6]), "=f"(sbv[7]) : "r"(ba + 16u));
+              const float2 a2 = make_float2(epi.alpha, epi.alpha);
+#pragma unroll
+              for (int i = 0; i < 4; i++) {
+                float2 t = make_float2(sbv[2 * i], sbv[2 * i + 1]);
+                ffma2(t, make_float2(v[2 * i], v[2 * i + 1]), a2);
+                v[2 * i] = t.x;
+                v[2 * i + 1] = t.y;
+              }
+              if (EMODE == 2) {
+                const float lo = epi.act == CMX_ACT_RELU ? 0.f : -INFINITY;   // ReLU as a clamp: no branch in the unrolled loop
+#pragma unroll
+                for (int i = 0; i < 8; i++) v[i] = fmaxf(v[i], lo) * rs;
+              }
             }
-            epi_math8<EMODE>(epi, row, (long)n0 + c * 32 + g * 8, sbv, row_ok, rs, v);
+            if (rres) {
+              if (cfull) {
+                if (g < 3) res_fetch(g + 1);
+#pragma unroll
+                for (int i = 0; i < 8; i++) v[i] += rr[g & 1][i];
+              } else {
+#pragma unroll
+                for (int i = 0; i < 8; i++)
+                  if (ccol + g * 8 + i < epi.N)
+                    v[i] += res_f32 ? res32[g * 8 + i] : __bfloat162float(res16[g * 8 + i]);
+              }
+            }
             const uint32_t sw = (uint32_t)(lane & 7);
-            if (epi.c_dtype == CMX_F32) {
+            if (f32out) {
               const uint32_t j0 = (uint32_t)(g * 2);
               st_shared_v4(buf + lane * 128u + ((j0 ^ sw) << 4), __float_as_uint(v[0]), __float_as_uint(v[1]),
                            __float_as_uint(v[2]), __float_as_uint(v[3]));
@@ -461,7 +510,7 @@ __global__ void __launch_bounds__(tc_threads(BN), tc_ctas_per_sm(BN)) gemm_tc_ke
             }
           }
           // last chunk of the unit (or the unit is cut short by N): publish the box
-          const bool unit_done = (cc == UC - 1) || (n0 + (c + 1) * 32 >= epi.N);
+          const bool unit_done = (cc == UCk - 1) || (!K::FULL && n0 + (c + 1) * 32 >= epi.N);
           if (trc) TC_TRACE(3, lt, 2 + (cc ? 1 : 0));
           if (unit_done) {
             fence_async_smem();
@@ -477,45 +526,56 @@ __global__ void __launch_bounds__(tc_threads(BN), tc_ctas_per_sm(BN)) gemm_tc_ke
             nstore++;
           }
         };
-        auto run_chunks = [&](auto mode_tag) {
-          if constexpr (NH == 1) {
+        // k-th chunk of this warp (units half, half+NH, ...), -1 when exhausted; a trailing partial unit
+        // (BN = 160 with bf16) is excluded here and handled by the per-thread store path below
+        auto chunk_of = [&](auto kind_tag, int k) -> int {
+          using K = decltype(kind_tag);
+          const int UCk = K::CDT == 2 ? UC : (K::CDT == 1 ? 1 : 2);
+          const int u = half + NH * (k / UCk);
+          const int c = u * UCk + (k % UCk);
+          if ((u + 1) * UCk * 32 > BN || (!K::FULL && n0 + c * 32 >= epi.N)) return -1;
+          return c;
+        };
+        auto run_chunks = [&](auto kind_tag) {
+          if constexpr (SIMPLE) {
             // two resident CTAs per SM hide the tcgen05.ld latency of each other: one register set, no spills
             uint32_t ra[32];
 #pragma unroll 1
             for (int k = 0;; k++) {
-              const int c = chunk_of(k);
+              const int c = chunk_of(kind_tag, k);
               if (c < 0) break;
               tmem_ld32(t_addr + (uint32_t)(c * 32), ra);
               tmem_wait_ld_dep(ra);
-              process(mode_tag, ra, c);
+              process(kind_tag, ra, c);
             }
             return;
           }
           uint32_t ra[32], rb[32];
-          int cA = chunk_of(0);
+          int cA = chunk_of(kind_tag, 0);
           if (cA >= 0) tmem_ld32(t_addr + (uint32_t)(cA * 32), ra);
 #pragma unroll 1
           for (int k = 0; cA >= 0; k += 2) {
             tmem_wait_ld_dep(ra);
-            const int cB = chunk_of(k + 1);
+            const int cB = chunk_of(kind_tag, k + 1);
             if (cB >= 0) tmem_ld32(t_addr + (uint32_t)(cB * 32), rb);
-            process(mode_tag, ra, cA);
+            process(kind_tag, ra, cA);
             if (cB < 0) break;
             tmem_wait_ld_dep(rb);
-            cA = chunk_of(k + 2);
+            cA = chunk_of(kind_tag, k + 2);
             if (cA >= 0) tmem_ld32(t_addr + (uint32_t)(cA * 32), ra);
-            process(mode_tag, rb, cB);
+            process(kind_tag, rb, cB);
           }
         };
-        // warp-uniform choice between two separately compiled epilogue bodies (a real branch, not predication)
+        // warp-uniform choice between separately compiled epilogue bodies (a real branch, not predication)
         const bool m2 = epi.act != CMX_ACT_NONE || epi.row_scale, m1 = epi.alpha != 1.f || epi.bias;
-        if constexpr (NH == 1) {
-          if (m2) run_chunks(std::integral_constant<int, 2>{});
-          else if (m1) run_chunks(std::integral_constant<int, 1>{});
-          else run_chunks(std::integral_constant<int, 0>{});
-        } else {  // whole-SM shapes (off the default policy): two bodies keep the double register set spill-free
-          if (m2 || m1) run_chunks(std::integral_constant<int, 2>{});
-          else run_chunks(std::integral_constant<int, 0>{});
+        if constexpr (SIMPLE) {
+          const bool full = m0 + TC_BM <= epi.M && n0 + BN <= epi.N;
+          if (full && !m1 && !m2 && !epi.res && epi.c_dtype == CMX_BF16) run_chunks(EK<0, 0, 0, true>{});        // data gradients
+          else if (full && !m2 && !epi.res && epi.c_dtype == CMX_BF16) run_chunks(EK<1, 0, 0, true>{});           // x W^T + b
+          else if (full && epi.res && epi.r_dtype == CMX_F32 && epi.c_dtype == CMX_F32) run_chunks(EK<2, 1, 1, true>{});  // residual stream
+          else run_chunks(EK<2, 2, 2, false>{});
+        } else {  // whole-SM shapes (off the default policy)
+          run_chunks(EK<2, 2, 2, false>{});
         }
         if ((BN / 32) % UC != 0) {
           // BN = 160 with 64-column bf16 boxes leaves a 32-column remainder: a full box would spill into the
@@ -799,7 +859,7 @@ static bool tc_eligible(const CmxGemm* g) {
   return true;
 }
 
-template <int BN, bool A_MN, bool B_MN, bool BATCHED>
+template <int BN, bool A_MN, bool B_MN, bool BATCHED, int EW>
 static int launch_tc(const CmxGemm* g, const Epi& epi, cudaStream_t st) {
   CUtensorMap tmA, tmB;
   int rc;
@@ -845,14 +905,14 @@ static int launch_tc(const CmxGemm* g, const Epi& epi, cudaStream_t st) {
     if (rc) return rc;
   }
   constexpr int STAGE_BYTES = (TC_BM + BN) * TC_BK * 2;
-  constexpr uint32_t TC_CSTAGE_BYTES = tc_cstage_bytes(BN);
+  constexpr uint32_t TC_CSTAGE_BYTES = tc_cstage_bytes(BN, EW);
   int stages = (int)((tc_smem_budget(BN) - 4096 - (sc.tma_store ? TC_CSTAGE_BYTES : 0)) / STAGE_BYTES);
   if (stages > 8) stages = 8;
   if (stages < 2) stages = 2;
   sc.stages = stages;
   const size_t smem = (size_t)stages * STAGE_BYTES + (sc.tma_store ? TC_CSTAGE_BYTES : 0) + 2048 + 1024 + 16 * stages + 128;
   static bool attr_done = false;
-  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, BATCHED>;
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, BATCHED, EW>;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) CMX_FAIL((int)e, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
@@ -865,7 +925,7 @@ static int launch_tc(const CmxGemm* g, const Epi& epi, cudaStream_t st) {
   const long grid = sc.total_tiles < slots ? sc.total_tiles : slots;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
-  cfg.blockDim = dim3(tc_threads(BN));
+  cfg.blockDim = dim3(tc_threads(EW));
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -913,27 +973,42 @@ static int pick_bn(const CmxGemm* g) {
   return tiles128 < num_sms() ? 64 : 128;
 }
 
+// epilogue warps of the two-CTA-per-SM shapes: 4 (default) or 8 (CMX_GEMM_EPI_WARPS=8).  Measured on B200 with the branch-free
+// epilogue bodies (scripts/gpu_runs/r2_call9.sh): 8 warps need __launch_bounds__(320, 2) = 96 registers and spill 40-60 bytes;
+// the step runs 20.80 ms with 4 warps against 21.1 ms with 8 (standalone the K <= 256 shapes are equal or faster with 4).
+static int epi_warps_env() {
+  static int v = -1;
+  if (v < 0) {
+    const char* s = getenv("CMX_GEMM_EPI_WARPS");
+    v = (s && atoi(s) == 8) ? 8 : 4;
+  }
+  return v;
+}
+
 static int dispatch_tc(const CmxGemm* g, const Epi& epi, cudaStream_t st) {
   const int bn = pick_bn(g);
   const bool a = g->trans_a != 0, b = g->trans_b != 0;
   const bool batched = g->batch1 != 1 || g->batch2 != 1;
-#define TC_CASE(BNv)                                                                                   \
-  if (bn == BNv) {                                                                                     \
+  const int ew = bn <= 128 ? epi_warps_env() : 8;
+#define TC_CASE2(BNv, EWv)                                                                             \
+  if (bn == BNv && ew == EWv) {                                                                        \
     if (!batched) {                                                                                    \
-      if (!a && !b) return launch_tc<BNv, false, false, false>(g, epi, st);                            \
-      if (!a && b) return launch_tc<BNv, false, true, false>(g, epi, st);                              \
-      return launch_tc<BNv, true, true, false>(g, epi, st);                                            \
+      if (!a && !b) return launch_tc<BNv, false, false, false, EWv>(g, epi, st);                       \
+      if (!a && b) return launch_tc<BNv, false, true, false, EWv>(g, epi, st);                         \
+      return launch_tc<BNv, true, true, false, EWv>(g, epi, st);                                       \
     } else {                                                                                           \
-      if (!a && !b) return launch_tc<BNv, false, false, true>(g, epi, st);                             \
-      if (!a && b) return launch_tc<BNv, false, true, true>(g, epi, st);                               \
-      return launch_tc<BNv, true, true, true>(g, epi, st);                                             \
+      if (!a && !b) return launch_tc<BNv, false, false, true, EWv>(g, epi, st);                        \
+      if (!a && b) return launch_tc<BNv, false, true, true, EWv>(g, epi, st);                          \
+      return launch_tc<BNv, true, true, true, EWv>(g, epi, st);                                        \
     }                                                                                                  \
   }
-  TC_CASE(64)
-  TC_CASE(128)
-  TC_CASE(256)
-#undef TC_CASE
-  if (bn == 160) return batched ? launch_tc<160, false, false, true>(g, epi, st) : launch_tc<160, false, false, false>(g, epi, st);
+  TC_CASE2(64, 8)
+  TC_CASE2(128, 8)
+  TC_CASE2(64, 4)
+  TC_CASE2(128, 4)
+  TC_CASE2(256, 8)
+#undef TC_CASE2
+  if (bn == 160) return batched ? launch_tc<160, false, false, true, 8>(g, epi, st) : launch_tc<160, false, false, false, 8>(g, epi, st);
   CMX_FAIL(-4, "no tcgen05 instantiation for BN=%d", bn);
 }
 
