@@ -26,6 +26,12 @@ constexpr uint32_t AT_BAR_OFF = AT_RED_OFF + 2048;
 constexpr uint32_t AT_SMEM = AT_BAR_OFF + 256 + 1024;  // + alignment slack
 constexpr uint32_t AT_O_COL = 320;
 
+__device__ __forceinline__ float ex2_approx(float x) {   // one MUFU.EX2 (2 ulp; the result is rounded to bf16 anyway)
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 struct AttnArgs {
   bf16* o;
   long ldo;
@@ -172,6 +178,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_kernel(const __grid_consta
     const int r = q * 32 + lane;          // row inside the tile
     const uint32_t t_row = tmem + ((uint32_t)(q * 32) << 16);
     const float sl2 = a.scale_log2e;
+    float o_scale = 1.f;
     for (int i = 0; i < ntiles; i++) {
       const long t = t_begin + i;
       const long bh = t / a.tiles_per_bh;
@@ -259,17 +266,26 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_kernel(const __grid_consta
         if (a.store_p && threadIdx.x == 64) tma_store_wait_read<0>();
         mbar_wait(s_full, (uint32_t)i & 1u);
         tc_fence_after();
-        // ---- pass 1: row maximum over this thread's 160 columns
+        // ---- pass 1: row maximum over this thread's 160 columns.  The softmax warps are instruction-issue bound (ncu: 49 % issue
+        // activity with 10 warps per SM), so chunks that lie completely below Nkv take a predicate-free body
         float mx = -INFINITY;
   #pragma unroll 1
         for (int c = 0; c < 5; c++) {
-          uint32_t v[32];
-          tmem_ld32(t_row + (uint32_t)(half * 160 + c * 32), v);
-          tmem_wait_ld();
           const int col0 = half * 160 + c * 32;
+          if (col0 >= a.Nk) break;
+          uint32_t v[32];
+          tmem_ld32(t_row + (uint32_t)col0, v);
+          tmem_wait_ld();
+          if (col0 + 32 <= a.Nk) {
+            float m4[4] = {mx, -INFINITY, -INFINITY, -INFINITY};   // four independent chains
   #pragma unroll
-          for (int j = 0; j < 32; j++)
-            if (col0 + j < a.Nk) mx = fmaxf(mx, __uint_as_float(v[j]));
+            for (int j = 0; j < 32; j++) m4[j & 3] = fmaxf(m4[j & 3], __uint_as_float(v[j]));
+            mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+          } else {
+  #pragma unroll
+            for (int j = 0; j < 32; j++)
+              if (col0 + j < a.Nk) mx = fmaxf(mx, __uint_as_float(v[j]));
+          }
         }
         asm volatile("st.shared.f32 [%0], %1;" ::"r"(sRed + 4u * (half * 128 + r)), "f"(mx) : "memory");
         asm volatile("bar.sync 1, 256;" ::: "memory");   // also orders thread 64's wait_group.read before any P write
@@ -278,53 +294,77 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_kernel(const __grid_consta
         asm volatile("ld.shared.f32 %0, [%1];" : "=f"(m1) : "r"(sRed + 4u * (128 + r)));
         const float m = fmaxf(m0, m1);
         const float moff = m * sl2;
-        // ---- pass 2: p = 2^(s*scale*log2e - m*scale*log2e), row sum, bf16 P -> shared memory (K-major, SWIZZLE_128B)
-        float sum = 0.f;
+        // ---- pass 2: p = 2^(s*scale*log2e - m*scale*log2e) (one MUFU.EX2 each), row sum, bf16 P -> shared memory (K-major,
+        // SWIZZLE_128B).  The sum is taken over the bf16-rounded values (what the P V MMA sees) in four independent chains.
+        float s4[4] = {0.f, 0.f, 0.f, 0.f};
   #pragma unroll 1
         for (int c = 0; c < 5; c++) {
-          uint32_t v[32];
-          tmem_ld32(t_row + (uint32_t)(half * 160 + c * 32), v);
-          tmem_wait_ld();
           const int col0 = half * 160 + c * 32;
+          const uint32_t rowad = sP + (uint32_t)r * 128;
+          const uint32_t sw = (uint32_t)r & 7u;
+          if (col0 >= a.Nk) {   // keys beyond Nkv: P = 0 (their V rows are zero-filled, but 0 * garbage could be NaN)
+  #pragma unroll
+            for (int g = 0; g < 4; g++) {
+              const int col = col0 + g * 8;
+              const uint32_t kb = (uint32_t)col >> 6, ch = ((uint32_t)col & 63u) >> 3;
+              st_shared_v4(rowad + kb * 16384 + ((ch ^ sw) << 4), 0u, 0u, 0u, 0u);
+            }
+            continue;
+          }
+          uint32_t v[32];
+          tmem_ld32(t_row + (uint32_t)col0, v);
+          tmem_wait_ld();
+          const bool cfull = col0 + 32 <= a.Nk;
   #pragma unroll
           for (int g = 0; g < 4; g++) {
             uint32_t pk[4];
   #pragma unroll
             for (int j = 0; j < 4; j++) {
-              const int cc = col0 + g * 8 + 2 * j;
-              float p0 = cc < a.Nk ? exp2f(fmaf(__uint_as_float(v[g * 8 + 2 * j]), sl2, -moff)) : 0.f;
-              float p1 = cc + 1 < a.Nk ? exp2f(fmaf(__uint_as_float(v[g * 8 + 2 * j + 1]), sl2, -moff)) : 0.f;
+              float p0 = ex2_approx(fmaf(__uint_as_float(v[g * 8 + 2 * j]), sl2, -moff));
+              float p1 = ex2_approx(fmaf(__uint_as_float(v[g * 8 + 2 * j + 1]), sl2, -moff));
+              if (!cfull) {
+                const int cc = col0 + g * 8 + 2 * j;
+                p0 = cc < a.Nk ? p0 : 0.f;
+                p1 = cc + 1 < a.Nk ? p1 : 0.f;
+              }
               __nv_bfloat162 h2 = __floats2bfloat162_rn(p0, p1);
               const float2 back = __bfloat1622float2(h2);
-              sum += back.x + back.y;   // the sum of what the P V MMA will actually see
+              s4[j] += back.x + back.y;
               pk[j] = *reinterpret_cast<uint32_t*>(&h2);
             }
             const int col = col0 + g * 8;
             const uint32_t kb = (uint32_t)col >> 6, ch = ((uint32_t)col & 63u) >> 3;
-            st_shared_v4(sP + kb * 16384 + (uint32_t)r * 128 + ((ch ^ ((uint32_t)r & 7u)) << 4), pk[0], pk[1], pk[2], pk[3]);
+            st_shared_v4(rowad + kb * 16384 + ((ch ^ sw) << 4), pk[0], pk[1], pk[2], pk[3]);
           }
         }
+        const float sum = (s4[0] + s4[1]) + (s4[2] + s4[3]);
         asm volatile("st.shared.f32 [%0], %1;" ::"r"(sRed + 1024u + 4u * (half * 128 + r)), "f"(sum) : "memory");
         asm volatile("bar.sync 2, 256;" ::: "memory");
         float l0, l1;
         asm volatile("ld.shared.f32 %0, [%1];" : "=f"(l0) : "r"(sRed + 1024u + 4u * r));
         asm volatile("ld.shared.f32 %0, [%1];" : "=f"(l1) : "r"(sRed + 1024u + 4u * (128 + r)));
         const float inv = 1.f / (l0 + l1);
-        // ---- normalise this thread's 160 probabilities in place (so that the stored P and the P V product agree)
+        o_scale = 1.f;
+        if (a.store_p) {
+          // ---- training: normalise this thread's 160 probabilities in place (the stored P is what the backward pass consumes)
   #pragma unroll 1
-        for (int cg = 0; cg < 20; cg++) {
-          const int col = half * 160 + cg * 8;
-          const uint32_t kb = (uint32_t)col >> 6, ch = ((uint32_t)col & 63u) >> 3;
-          const uint32_t ad = sP + kb * 16384 + (uint32_t)r * 128 + ((ch ^ ((uint32_t)r & 7u)) << 4);
-          uint32_t w[4];
-          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(ad));
+          for (int cg = 0; cg < 20; cg++) {
+            const int col = half * 160 + cg * 8;
+            if (col >= a.Nk) break;
+            const uint32_t kb = (uint32_t)col >> 6, ch = ((uint32_t)col & 63u) >> 3;
+            const uint32_t ad = sP + kb * 16384 + (uint32_t)r * 128 + ((ch ^ ((uint32_t)r & 7u)) << 4);
+            uint32_t w[4];
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(ad));
   #pragma unroll
-          for (int j = 0; j < 4; j++) {
-            float2 f = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&w[j]));
-            __nv_bfloat162 h2 = __floats2bfloat162_rn(f.x * inv, f.y * inv);
-            w[j] = *reinterpret_cast<uint32_t*>(&h2);
+            for (int j = 0; j < 4; j++) {
+              float2 f = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&w[j]));
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(f.x * inv, f.y * inv);
+              w[j] = *reinterpret_cast<uint32_t*>(&h2);
+            }
+            st_shared_v4(ad, w[0], w[1], w[2], w[3]);
           }
-          st_shared_v4(ad, w[0], w[1], w[2], w[3]);
+        } else {
+          o_scale = inv;   // inference / recompute backward: P stays unnormalised, the 64 output columns are scaled instead
         }
         if (a.lse && half == 0 && q0 + r < a.N)
           a.lse[bh * a.N + q0 + r] = m * (sl2 * 0.69314718055994531f) + logf(l0 + l1);
@@ -344,7 +384,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_kernel(const __grid_consta
           }
         }
       }
-      // ---- epilogue: O (already normalised) TMEM -> bf16 -> global; each thread of the pair takes 32 of the 64 columns
+      // ---- epilogue: O (normalised here when P was not) TMEM -> bf16 -> global; each thread of the pair takes 32 of the 64 columns
       mbar_wait(o_full, (uint32_t)i & 1u);
       tc_fence_after();
       {
@@ -357,7 +397,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_kernel(const __grid_consta
           for (int g = 0; g < 4; g++) {
             float f[8];
 #pragma unroll
-            for (int j = 0; j < 8; j++) f[j] = __uint_as_float(v[g * 8 + j]);
+            for (int j = 0; j < 8; j++) f[j] = __uint_as_float(v[g * 8 + j]) * (MODE == 0 ? o_scale : 1.f);
             store8(dst + g * 8, f);
           }
         }

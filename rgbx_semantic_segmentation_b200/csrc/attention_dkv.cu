@@ -18,6 +18,12 @@
 // 2 x 1.35 GB per training step at MiT-B2 480x640 batch 8).  Warp roles as in attention.cu: warp 0 TMA producer,
 // warp 1 MMA issuer, warps 2-9 (two threads per key row, 64 query columns each) exp2 / dS / bf16 staging.
 #include "tc_common.cuh"
+// one MUFU.EX2 (exp2f() adds a 3-instruction range fix-up; the arguments here are <= ~0 and tiny results may flush to 0)
+__device__ __forceinline__ float ex2_approx_f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 #include "../../include/cmx_b200.h"
 #include <atomic>
 #include <string.h>
@@ -202,8 +208,8 @@ __global__ void __launch_bounds__(DK_THREADS, 1) attn_dkv_kernel(const __grid_co
 #pragma unroll
           for (int j = 0; j < 4; j++) {
             const int e = g * 8 + 2 * j;
-            const float p0 = key_ok ? exp2f(fmaf(__uint_as_float(sv[e]), sl2, -l2[2 * j])) : 0.f;
-            const float p1 = key_ok ? exp2f(fmaf(__uint_as_float(sv[e + 1]), sl2, -l2[2 * j + 1])) : 0.f;
+            const float p0 = key_ok ? ex2_approx_f(fmaf(__uint_as_float(sv[e]), sl2, -l2[2 * j])) : 0.f;
+            const float p1 = key_ok ? ex2_approx_f(fmaf(__uint_as_float(sv[e + 1]), sl2, -l2[2 * j + 1])) : 0.f;
             const float s0 = sc * p0 * (__uint_as_float(dv[e]) - dl[2 * j]);
             const float s1 = sc * p1 * (__uint_as_float(dv[e + 1]) - dl[2 * j + 1]);
             __nv_bfloat162 hp = __floats2bfloat162_rn(p0, p1), hs = __floats2bfloat162_rn(s0, s1);
@@ -432,8 +438,8 @@ __global__ void __launch_bounds__(DK_THREADS, 1) attn_dq_kernel(const __grid_con
 #pragma unroll
             for (int j = 0; j < 4; j++) {
               const int e = g * 8 + 2 * j;
-              const float p0 = key0 + e < a.Nk ? exp2f(fmaf(__uint_as_float(sv[e]), sl2, -l2)) : 0.f;
-              const float p1 = key0 + e + 1 < a.Nk ? exp2f(fmaf(__uint_as_float(sv[e + 1]), sl2, -l2)) : 0.f;
+              const float p0 = key0 + e < a.Nk ? ex2_approx_f(fmaf(__uint_as_float(sv[e]), sl2, -l2)) : 0.f;
+              const float p1 = key0 + e + 1 < a.Nk ? ex2_approx_f(fmaf(__uint_as_float(sv[e + 1]), sl2, -l2)) : 0.f;
               __nv_bfloat162 hs = __floats2bfloat162_rn(sc * p0 * (__uint_as_float(dv[e]) - dl), sc * p1 * (__uint_as_float(dv[e + 1]) - dl));
               dk[j] = *reinterpret_cast<uint32_t*>(&hs);
             }

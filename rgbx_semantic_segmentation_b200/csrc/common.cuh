@@ -111,8 +111,8 @@ __device__ __forceinline__ float2 ffma2r(const float2 a, const float2 b, const f
 __device__ __forceinline__ void gelu_parts2(const float2 x, float2& cdf, float2& e) {
   const float2 x2 = fmul2(x, x);
   const float2 arg = fmul2(x2, make_float2(-0.72134752044448170368f, -0.72134752044448170368f));  // -0.5 * log2(e) * x^2
-  e.x = exp2f(arg.x);  // ex2.approx
-  e.y = exp2f(arg.y);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(arg.x));  // ONE MUFU.EX2 each (exp2f() adds a range fix-up: 3 more
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(arg.y));  // instructions; arg <= 0 here and results below 2^-126 are 0 anyway)
   float2 t;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.x) : "f"(fmaf(0.3275911f * 0.70710678118654752440f, fabsf(x.x), 1.f)));
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.y) : "f"(fmaf(0.3275911f * 0.70710678118654752440f, fabsf(x.y), 1.f)));

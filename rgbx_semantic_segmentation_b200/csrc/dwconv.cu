@@ -191,11 +191,15 @@ __global__ void __launch_bounds__(256, (MODE == 1 ? 2 : 3)) dwconv_tiled_kernel(
     // MODE 1: this thread's 32 dy values of the row are requested before waiting for the tile (independent loads)
     uint32_t gq[DT_TW];
     if (MODE == 1) {
+      // (one 64-bit address per row, then a pointer increment per pixel: the per-pixel index arithmetic was ~10 % of the
+      // kernel's instructions and the kernel is issue bound)
+      const bf16* dyp = dy + ((long)(b * H + (gy < H ? gy : 0)) * W + x0) * lddy + c;
 #pragma unroll
       for (int px = 0; px < DT_TW; px++) {
         const int gx = x0 + px;
         gq[px] = 0u;
-        if (gy < H && c_ok && gx < W) gq[px] = __ldg(reinterpret_cast<const unsigned int*>(dy + ((long)(b * H + gy) * W + gx) * lddy + c));
+        if (gy < H && c_ok && gx < W) gq[px] = __ldg(reinterpret_cast<const unsigned int*>(dyp));
+        dyp += lddy;
       }
     }
     asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
@@ -211,7 +215,7 @@ __global__ void __launch_bounds__(256, (MODE == 1 ? 2 : 3)) dwconv_tiled_kernel(
           win[i][j + 1] = __bfloat1622float2(h2);
         }
       }
-      const long rowbase = (long)(b * H + gy) * W;
+      bf16* orow = out + ((long)(b * H + gy) * W + x0) * ldo + c;   // advanced by ldo per pixel
 #pragma unroll  // fully unrolled: the sliding-window register rotation disappears and gq[] stays in registers
       for (int px = 0; px < DT_TW; px++) {
 #pragma unroll
@@ -242,18 +246,19 @@ __global__ void __launch_bounds__(256, (MODE == 1 ? 2 : 3)) dwconv_tiled_kernel(
           for (int i = 0; i < 3; i++)
 #pragma unroll
             for (int j = 0; j < 3; j++) ffma2(gw[i * 3 + j], g, win[i][j]);
-          *reinterpret_cast<__nv_bfloat162*>(out + (rowbase + gx) * ldo + c) = __floats2bfloat162_rn(g.x, g.y);
+          *reinterpret_cast<__nv_bfloat162*>(orow) = __floats2bfloat162_rn(g.x, g.y);
         } else {
           if (ACT == CMX_ACT_GELU) a = gelu2(a);
           else { a.x = act_f<ACT>(a.x); a.y = act_f<ACT>(a.y); }
           const __nv_bfloat162 o2 = __floats2bfloat162_rn(a.x, a.y);
-          *reinterpret_cast<__nv_bfloat162*>(out + (rowbase + gx) * ldo + c) = o2;
+          *reinterpret_cast<__nv_bfloat162*>(orow) = o2;
           if (db) {  // per-channel sum of what was written (bias gradient of the layer that produced x's gradient)
             const float2 of = __bfloat1622float2(o2);
             gb.x += of.x;
             gb.y += of.y;
           }
         }
+        orow += ldo;
       }
     }
   }

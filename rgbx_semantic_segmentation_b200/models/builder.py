@@ -88,6 +88,10 @@ class EncoderDecoder(nn.Module):
         self.decode_head = DecoderHead(in_channels=self.channels, num_classes=_cfg_get(cfg, "num_classes", 40),
                                        norm_layer=norm_layer, embed_dim=_cfg_get(cfg, "decoder_embed_dim", 512))
         self.criterion = criterion
+        if self.criterion and self.decode_head.num_classes > 64:
+            # the fused loss kernels keep one pixel's class scores in registers (two instantiations: <= 16 and <= 64 classes)
+            raise NotImplementedError("cmx_b200: the fused loss kernels support up to 64 classes (cfg.num_classes=%d)"
+                                      % self.decode_head.num_classes)
         if self.criterion:
             self.init_weights(cfg, pretrained=_cfg_get(cfg, "pretrained_model", None))
         self._engine = None
