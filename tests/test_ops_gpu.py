@@ -551,10 +551,12 @@ def test_fused_attention_forward(B, N, Nk, heads):
         assert bool(((pad == 3.0) | (pad == 0.0)).all())
     close(o, ref, 2e-2, 2e-2, "attention output")
     close(lse.view(B, heads, N), torch.logsumexp(s, -1), 1e-3, 1e-3, "lse")
-    # inference mode (no P, no LSE) gives the same output
+    # inference mode (no P, no LSE): the probabilities stay unnormalised in shared memory and the 64 output columns are scaled
+    # by 1 / rowsum instead - the same result up to the bf16 rounding of P
     o2 = torch.empty_like(o)
     ops.attn_fwd(q, kv, o2, B, N, Nk, heads, scale)
-    assert torch.equal(o, o2)
+    close(o2, ref, 2e-2, 2e-2, "attention output (no stored P)")
+    close(o2, o, 2e-2, 4e-3, "attention output: stored-P vs scaled-O mode")
     # fused backward core: dS and dQ from (dO, K, V, P)
     dO = rnd(B * N, C, dtype=bf)
     dsb = torch.full((B * heads * N, Np), 5.0, device=DEV, dtype=bf)
