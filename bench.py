@@ -338,6 +338,18 @@ def main_ours(args):
     torch.cuda.synchronize()
     prof, ops.PROFILE = ops.PROFILE, None
     launches_per_step = ops.launch_count() - n0
+    # calibration: the same event bracket around a trivial launch (8 elements) - the fixed cost every per-launch duration above
+    # carries (event records between kernels), reported beside the class figures; no figure is corrected with it
+    floor_us = None
+    if rank == 0:
+        x8, y8 = torch.zeros(8, device=dev), torch.zeros(8, device=dev, dtype=torch.bfloat16)
+        ops.PROFILE = []
+        torch.cuda._sleep(int(0.01 * 1.9e9))
+        for _ in range(65):
+            ops.cast_f32_bf16(x8, y8)
+        torch.cuda.synchronize()
+        cal, ops.PROFILE = ops.PROFILE, None
+        floor_us = 1e3 * statistics.median(a_.elapsed_time(b_) for _, a_, b_, _, _ in cal[1:])
     eng.wgrad_stream = saved_streams
     model.use_cuda_graph = os.environ.get("CMX_CUDA_GRAPH", "1") != "0"
     if rank == 0:
@@ -389,6 +401,7 @@ def main_ours(args):
                           "algorithmic_bytes_per_launch": knb / kn, "traffic": traffic.get(kname)})
         roof["kernels"] = klist
         roof.update(kernel=name, launches_per_step=n, avg_us=1e3 * t / n, share_of_step=t / total, peak_src=pk["src"],
+                    event_floor_us=floor_us,
                     timing="CUDA events around every launch of one eager step run on a single stream with the host pre-enqueued "
                            "(isolated kernel durations; their sum is %.1f ms, the graph-replayed multi-stream step overlaps them)" % total,
                     algorithmic_bytes_per_launch=nb / n, algorithmic_flops_per_launch=fl / n)

@@ -155,10 +155,12 @@ constexpr int TC_BK = 64;
 // the MMA issuer waits for the accumulator buffer all the time), so the two-CTA-per-SM shapes can run 8 epilogue warps each
 // (16 per SM = 4 per scheduler) with ONE 4 KB staging buffer per warp instead of two.
 __host__ __device__ constexpr int tc_threads(int ew) { return 64 + 32 * ew; }
-__host__ __device__ constexpr int tc_ctas_per_sm(int bn) { return bn <= 128 ? 2 : 1; }
-__host__ __device__ constexpr int tc_nbuf(int bn, int ew) { return (ew == 4 || bn > 128) ? 2 : 1; }  // staging buffers per epilogue warp
-__host__ __device__ constexpr uint32_t tc_cstage_bytes(int bn, int ew) { return ew * tc_nbuf(bn, ew) * 4096; }  // (32 rows x 128 B) each
-__host__ __device__ constexpr int tc_smem_budget(int bn) { return bn <= 128 ? 110 * 1024 : 200 * 1024; }
+// CPS = CTAs per SM.  2: the default for BN <= 128 (one CTA's epilogue overlaps the other's loads / MMAs; 110 KB each = a
+// 2-deep operand ring).  1: the whole SM for one CTA - required for BN > 128, and an opt-in deep-ring variant of BN = 128
+// (CMX_GEMM_DEEP_K, measured slower, see deep_k_env).
+__host__ __device__ constexpr int tc_nbuf(int ew, int cps) { return ew == 4 ? 2 : 1; }  // staging buffers per epilogue warp
+__host__ __device__ constexpr uint32_t tc_cstage_bytes(int ew, int cps) { return ew * tc_nbuf(ew, cps) * 4096; }  // (32 rows x 128 B) each
+__host__ __device__ constexpr int tc_smem_budget(int cps) { return cps == 2 ? 110 * 1024 : 216 * 1024; }
 
 template <int EMODE_, int CDT_, int RES_, bool FULL_>
 struct EK {   // compile-time description of one epilogue body, see gemm_tc_kernel
@@ -181,8 +183,8 @@ struct TcSched {
   } while (0)
 
 
-template <int BN, bool A_MN, bool B_MN, bool BATCHED, int EW>
-__global__ void __launch_bounds__(tc_threads(EW), tc_ctas_per_sm(BN)) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+template <int BN, bool A_MN, bool B_MN, bool BATCHED, int EW, int CPS>
+__global__ void __launch_bounds__(tc_threads(EW), CPS) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                const __grid_constant__ CUtensorMap tmB,
                                                                const __grid_constant__ CUtensorMap tmC, Epi epi0,
                                                                TcSched sc) {
@@ -195,9 +197,9 @@ __global__ void __launch_bounds__(tc_threads(EW), tc_ctas_per_sm(BN)) gemm_tc_ke
   constexpr uint32_t TMEM_COLS = 2 * ACC_STRIDE;
   constexpr int TC_EPI_WARPS = EW;
   constexpr int NH = TC_EPI_WARPS / 4;  // warps per TMEM lane quarter = column interleave factor
-  constexpr int NBUF = tc_nbuf(BN, EW);
-  constexpr bool SIMPLE = tc_ctas_per_sm(BN) == 2;  // one register set: the co-resident CTA hides the tcgen05.ld latency
-  constexpr uint32_t TC_CSTAGE_BYTES = tc_cstage_bytes(BN, EW);
+  constexpr int NBUF = tc_nbuf(EW, CPS);
+  constexpr bool SIMPLE = CPS == 2;  // one register set: the co-resident CTA hides the tcgen05.ld latency
+  constexpr uint32_t TC_CSTAGE_BYTES = tc_cstage_bytes(EW, CPS);
   const int stages = sc.stages;
 
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -859,7 +861,7 @@ static bool tc_eligible(const CmxGemm* g) {
   return true;
 }
 
-template <int BN, bool A_MN, bool B_MN, bool BATCHED, int EW>
+template <int BN, bool A_MN, bool B_MN, bool BATCHED, int EW, int CPS>
 static int launch_tc(const CmxGemm* g, const Epi& epi, cudaStream_t st) {
   CUtensorMap tmA, tmB;
   int rc;
@@ -905,14 +907,14 @@ static int launch_tc(const CmxGemm* g, const Epi& epi, cudaStream_t st) {
     if (rc) return rc;
   }
   constexpr int STAGE_BYTES = (TC_BM + BN) * TC_BK * 2;
-  constexpr uint32_t TC_CSTAGE_BYTES = tc_cstage_bytes(BN, EW);
-  int stages = (int)((tc_smem_budget(BN) - 4096 - (sc.tma_store ? TC_CSTAGE_BYTES : 0)) / STAGE_BYTES);
+  constexpr uint32_t TC_CSTAGE_BYTES = tc_cstage_bytes(EW, CPS);
+  int stages = (int)((tc_smem_budget(CPS) - 4096 - (sc.tma_store ? TC_CSTAGE_BYTES : 0)) / STAGE_BYTES);
   if (stages > 8) stages = 8;
   if (stages < 2) stages = 2;
   sc.stages = stages;
   const size_t smem = (size_t)stages * STAGE_BYTES + (sc.tma_store ? TC_CSTAGE_BYTES : 0) + 2048 + 1024 + 16 * stages + 128;
   static bool attr_done = false;
-  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, BATCHED, EW>;
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, BATCHED, EW, CPS>;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) CMX_FAIL((int)e, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
@@ -921,7 +923,7 @@ static int launch_tc(const CmxGemm* g, const Epi& epi, cudaStream_t st) {
   }
   Epi e2 = epi;
   e2.atomic = atomic ? 1 : 0;
-  const long slots = (long)num_sms() * tc_ctas_per_sm(BN);
+  const long slots = (long)num_sms() * CPS;
   const long grid = sc.total_tiles < slots ? sc.total_tiles : slots;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
@@ -985,30 +987,50 @@ static int epi_warps_env() {
   return v;
 }
 
+// K from which the BN = 128 forward / data-gradient GEMMs take the deep single-CTA variant (CMX_GEMM_DEEP_K; default 0 = never).
+// EXPERIMENT THAT DID NOT PAY (scripts/gpu_runs/r2_call17.sh, one B200): 5 stages in one CTA per SM are 10-25 % SLOWER than two
+// co-resident CTAs with 2 stages each (M=153600 N=K=512: 134 vs 110 us; M=19200 N=320 K=1280: 44 vs 36 us; step 20.30 vs
+// 20.02 ms) - the long-K shapes are bound by operand traffic out of L2, not by the depth of the ring.
+static long deep_k_env() {
+  static long v = -1;
+  if (v < 0) {
+    const char* s = getenv("CMX_GEMM_DEEP_K");
+    v = s ? atol(s) : 0;
+    if (v <= 0) v = 1L << 60;
+  }
+  return v;
+}
+
 static int dispatch_tc(const CmxGemm* g, const Epi& epi, cudaStream_t st) {
   const int bn = pick_bn(g);
   const bool a = g->trans_a != 0, b = g->trans_b != 0;
   const bool batched = g->batch1 != 1 || g->batch2 != 1;
-  const int ew = bn <= 128 ? epi_warps_env() : 8;
-#define TC_CASE2(BNv, EWv)                                                                             \
-  if (bn == BNv && ew == EWv) {                                                                        \
+  const bool atomic = g->split_k > 1 || g->accumulate;
+  // deep variant: long K, plain (non split-K) output, and enough tiles that one CTA per SM still fills the machine
+  const long tiles = ((g->M + TC_BM - 1) / TC_BM) * ((g->N + 127) / 128) * g->batch1 * g->batch2;
+  const bool deep = bn == 128 && !a && !atomic && g->K >= deep_k_env() && tiles >= num_sms();
+  const int ew = deep ? 8 : (bn <= 128 ? epi_warps_env() : 8);
+  const int cps = (bn > 128 || deep) ? 1 : 2;
+#define TC_CASE3(BNv, EWv, CPSv)                                                                       \
+  if (bn == BNv && ew == EWv && cps == CPSv) {                                                         \
     if (!batched) {                                                                                    \
-      if (!a && !b) return launch_tc<BNv, false, false, false, EWv>(g, epi, st);                       \
-      if (!a && b) return launch_tc<BNv, false, true, false, EWv>(g, epi, st);                         \
-      return launch_tc<BNv, true, true, false, EWv>(g, epi, st);                                       \
+      if (!a && !b) return launch_tc<BNv, false, false, false, EWv, CPSv>(g, epi, st);                 \
+      if (!a && b) return launch_tc<BNv, false, true, false, EWv, CPSv>(g, epi, st);                   \
+      if constexpr (CPSv == 2 || BNv > 128) return launch_tc<BNv, true, true, false, EWv, CPSv>(g, epi, st); \
     } else {                                                                                           \
-      if (!a && !b) return launch_tc<BNv, false, false, true, EWv>(g, epi, st);                        \
-      if (!a && b) return launch_tc<BNv, false, true, true, EWv>(g, epi, st);                          \
-      return launch_tc<BNv, true, true, true, EWv>(g, epi, st);                                        \
+      if (!a && !b) return launch_tc<BNv, false, false, true, EWv, CPSv>(g, epi, st);                  \
+      if (!a && b) return launch_tc<BNv, false, true, true, EWv, CPSv>(g, epi, st);                    \
+      if constexpr (CPSv == 2 || BNv > 128) return launch_tc<BNv, true, true, true, EWv, CPSv>(g, epi, st); \
     }                                                                                                  \
   }
-  TC_CASE2(64, 8)
-  TC_CASE2(128, 8)
-  TC_CASE2(64, 4)
-  TC_CASE2(128, 4)
-  TC_CASE2(256, 8)
-#undef TC_CASE2
-  if (bn == 160) return batched ? launch_tc<160, false, false, true, 8>(g, epi, st) : launch_tc<160, false, false, false, 8>(g, epi, st);
+  TC_CASE3(64, 4, 2)
+  TC_CASE3(128, 4, 2)
+  TC_CASE3(128, 8, 1)
+  TC_CASE3(64, 8, 2)
+  TC_CASE3(128, 8, 2)
+  TC_CASE3(256, 8, 1)
+#undef TC_CASE3
+  if (bn == 160) return batched ? launch_tc<160, false, false, true, 8, 1>(g, epi, st) : launch_tc<160, false, false, false, 8, 1>(g, epi, st);
   CMX_FAIL(-4, "no tcgen05 instantiation for BN=%d", bn);
 }
 

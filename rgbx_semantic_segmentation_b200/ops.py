@@ -116,7 +116,7 @@ def gemm_raw(A, B, C, M, N, K, lda, ldb, ldc, *, a_off=0, b_off=0, c_off=0, tran
     g.sBias1, g.sR1, g.sS1 = s_bias, s_res, s_scale
     nb = batch[0] * batch[1]
     which = "tc" if int(_lib.load().cmx_gemm_which(ctypes.byref(g))) == 2 else ("fb_batched" if nb > 1 else "fb")
-    kind = "wgrad" if trans_a else ("dgrad" if trans_b and nb == 1 else "fwd")
+    kind = "wgrad" if trans_a else ("dgrad" if trans_b else "fwd")   # by operand layout (scripts/ncu_launch_summary.py agrees)
     cbytes = C.element_size() * (2 if (accumulate or split_k > 1) else 1)
     tag = "gemm_%s_%s" % (which, kind)
     if PROFILE_SHAPES:

@@ -16,10 +16,12 @@ import re
 
 def bench_class(name):
     """ncu kernel name -> the class (C-ABI entry point / GEMM kind) that bench.py aggregates by"""
-    m = re.match(r"(?:void )?gemm_tc_kernel<\(?(?:int\))?(\d+), \(?(?:int\))?(\d+), \(?(?:int\))?(\d+), \(?(?:int\))?(\d+)>", name)
+    m = re.match(r"(?:void )?gemm_tc_kernel<\(?(?:int\))?(\d+), \(?(?:\w+\))?(\d+), \(?(?:\w+\))?(\d+), \(?(?:\w+\))?(\d+)[,>]", name)
     if m:
-        a_mn, b_mn, batched = int(m.group(2)), int(m.group(3)), int(m.group(4))
-        return "gemm_tc_wgrad" if a_mn else ("gemm_tc_dgrad" if b_mn and not batched else "gemm_tc_fwd")
+        # classes by operand layout, like ops.gemm_raw: A MN-major = weight gradient (dY^T X), B MN-major = data gradient
+        # (dY W, the untouched [N,K] weight; also the few attention-style products with a transposed B), else forward
+        a_mn, b_mn = int(m.group(2)), int(m.group(3))
+        return "gemm_tc_wgrad" if a_mn else ("gemm_tc_dgrad" if b_mn else "gemm_tc_fwd")
     table = [("attn_kernel<0>", "cmx_attn_fwd"), ("attn_kernel<1>", "cmx_attn_bwd"), ("attn_kernel<(int)0>", "cmx_attn_fwd"),
              ("attn_kernel<(int)1>", "cmx_attn_bwd"), ("ln_bwd", "cmx_layernorm_bwd"), ("ln_fwd", "cmx_layernorm_fwd"),
              ("adamw_flat", "cmx_adamw_flat"), ("col2im_nhwc", "cmx_col2im_nhwc"), ("im2col_nhwc", "cmx_im2col_nhwc"),

@@ -6,6 +6,7 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "scripts"))
 
 
@@ -24,7 +25,10 @@ def test_reference_arm_line_matches_the_contract():
     assert d["higher_is_better"] is True and d["vs_baseline"] is None and d["n_gpus"] == 1
     assert d["value"] > 0 and abs(d["value"] - 1e3 / d["ms_per_step"]) < 1e-6 * d["value"]
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    # "reference" = the unmodified reference model from baseline/_ref (or /root/reference); "port" only when neither exists
+    from baseline import ref_loader
+    assert cb["kind"] == ("reference" if ref_loader.available() else "port")
+    assert cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": bench.UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 
@@ -40,7 +44,8 @@ def test_ncu_kernel_names_map_to_bench_classes():
     cases = {
         "void gemm_tc_kernel<128, 1, 1, 0>(CUtensorMap_st, CUtensorMap_st)": "gemm_tc_wgrad",
         "void gemm_tc_kernel<(int)64, (int)0, (int)1, (int)0>(CUtensorMap_st)": "gemm_tc_dgrad",
-        "void gemm_tc_kernel<64, 0, 1, 1>(CUtensorMap_st)": "gemm_tc_fwd",       # batched attention-style product
+        "void gemm_tc_kernel<64, 0, 1, 1, 4>(CUtensorMap_st)": "gemm_tc_dgrad",    # grouped data gradient (5 template arguments)
+        "void gemm_tc_kernel<(int)128, (bool)0, (bool)0, (bool)1, (int)4>(CUtensorMap_st)": "gemm_tc_fwd",
         "void gemm_tc_kernel<128, 0, 0, 0>(CUtensorMap_st)": "gemm_tc_fwd",
         "void attn_kernel<1>(CUtensorMap_st, AttnArgs)": "cmx_attn_bwd",
         "void dwconv_tiled_kernel<2, 1>(const __nv_bfloat16 *, long)": "cmx_dwconv3x3_bwd_pre",
