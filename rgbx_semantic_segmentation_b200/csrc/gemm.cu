@@ -972,7 +972,12 @@ static int pick_bn(const CmxGemm* g) {
   long split = g->split_k > 1 ? g->split_k : 1;
   if (split > kb_total) split = kb_total;
   const long tiles128 = ((g->M + TC_BM - 1) / TC_BM) * ((N + 127) / 128) * g->batch1 * g->batch2 * split;
-  return tiles128 < num_sms() ? 64 : 128;
+  static long thr = -1;   // CMX_GEMM_BN64_BELOW: use 64-wide tiles while 128-wide ones would give fewer tiles than this
+  if (thr < 0) {
+    const char* e = getenv("CMX_GEMM_BN64_BELOW");
+    thr = e ? atol(e) : num_sms();
+  }
+  return tiles128 < thr ? 64 : 128;
 }
 
 // epilogue warps of the two-CTA-per-SM shapes: 4 (default) or 8 (CMX_GEMM_EPI_WARPS=8).  Measured on B200 with the branch-free

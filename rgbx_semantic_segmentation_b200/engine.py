@@ -99,6 +99,7 @@ class Engine:
         self._wkeep = {}
         self._dec_prep = None
         self._bns = [(n, m) for n, m in model.named_modules() if isinstance(m, torch.nn.modules.batchnorm._BatchNorm)]
+        self.keepalive = None        # measurement hook (bench.py): list that keeps every buffer of a step alive for a replay
         self.poison = None           # debug hook: list of (tensor, allocation site) when NaN-poisoning is on
         self.sync_emulate_world = 0  # test hook: treat the decoder SyncBatchNorm as shared by this many ranks ...
         self.sync_hook = None        # ... whose all-reduce is performed by this callable(tensor) (in-process lock-step emulation)
@@ -247,10 +248,16 @@ class Engine:
             f = sys._getframe(1)
             self.poison.append((t, "%s:%d" % (f.f_code.co_name, f.f_lineno)))
             return t
-        return torch.empty(*shape, device=self.dev, dtype=dtype)
+        t = torch.empty(*shape, device=self.dev, dtype=dtype)
+        if self.keepalive is not None:
+            self.keepalive.append(t)
+        return t
 
     def Z(self, *shape, dtype=f32):
-        return torch.zeros(*shape, device=self.dev, dtype=dtype)
+        t = torch.zeros(*shape, device=self.dev, dtype=dtype)
+        if self.keepalive is not None:
+            self.keepalive.append(t)
+        return t
 
     def tr(self, key, t):
         if self.trace is not None:

@@ -47,11 +47,17 @@ def launch_count():
 # Optional per-launch profiling (bench.py / debugging): when PROFILE is a list every C-ABI call is bracketed
 # by CUDA events on the launching stream and (name, start, stop, flops, bytes) is appended.
 PROFILE = None
+# Optional call recording (bench.py): when RECORD is a list every C-ABI call is appended as (tag, function, argument tuple) so
+# that the launches of one kernel class can be replayed back to back between ONE pair of events (the caller keeps every
+# buffer alive through Engine.keepalive)
+RECORD = None
 PROFILE_SHAPES = bool(int(__import__('os').environ.get('CMX_PROFILE_SHAPES', '0')))
 
 
 def _call(name, *args, tag=None, flops=0, nbytes=0):
     fn = getattr(_lib.load(), name)
+    if RECORD is not None:
+        RECORD.append((tag or name, fn, args))
     if PROFILE is None:
         rc = fn(*args)
     else:
