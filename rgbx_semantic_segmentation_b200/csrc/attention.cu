@@ -20,11 +20,33 @@ extern std::atomic<long long> g_cmx_launches;
 constexpr int AT_BM = 128;      // query rows per tile
 constexpr int AT_D = 64;        // head dim
 constexpr int AT_NK = 320;      // padded key count (5 k-blocks of 64)
-constexpr int AT_THREADS = 64 + 256;
+#ifndef AT_NP
+#define AT_NP 4
+#endif
+// softmax warps per TMEM lane quarter (each takes a contiguous range of the ten 32-column chunks of S).  The softmax warps are
+// instruction-issue / latency bound (ncu: 43-49 % issue activity with 8 of them = 2 per scheduler), so 16 warps split the columns
+constexpr int AT_SW = 4 * AT_NP;             // softmax warps
+constexpr int AT_ST = 32 * AT_SW;            // softmax threads (named-barrier count)
+constexpr int AT_THREADS = 64 + AT_ST;
 constexpr uint32_t AT_K_OFF = 0, AT_V_OFF = 40960, AT_Q_OFF = 81920, AT_P_OFF = 114688, AT_RED_OFF = 196608;
-constexpr uint32_t AT_BAR_OFF = AT_RED_OFF + 2048;
+constexpr uint32_t AT_RED2 = AT_NP * 512u;   // second reduction array (row sums) behind the first (row max / dot)
+constexpr uint32_t AT_BAR_OFF = AT_RED_OFF + 2 * AT_RED2;
 constexpr uint32_t AT_SMEM = AT_BAR_OFF + 256 + 1024;  // + alignment slack
 constexpr uint32_t AT_O_COL = 320;
+
+template <int N>
+__device__ __forceinline__ void tmem_ld_n(uint32_t taddr, uint32_t* r) {   // tcgen05.ld 32x32b of N = 16 or 32 columns
+  if constexpr (N == 32) {
+    tmem_ld32(taddr, r);
+  } else {
+    static_assert(N == 16, "tmem_ld_n: 16 or 32 columns");
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+  }
+}
 
 __device__ __forceinline__ float ex2_approx(float x) {   // one MUFU.EX2 (2 ulp; the result is rounded to bf16 anyway)
   float y;
@@ -77,7 +99,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_kernel(const __grid_consta
     mbar_init(s_full, 1);
     mbar_init(p_full, 1);
     mbar_init(o_full, 1);
-    mbar_init(o_empty, 8);
+    mbar_init(o_empty, AT_SW);
     mbar_init(p_in, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -174,7 +196,8 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_kernel(const __grid_consta
   } else {
     // ============================ softmax + epilogue (warps 2..9) ============================
     const int q = warp & 3;               // TMEM lane quarter
-    const int half = (warp - 2) >> 2;     // column half: [0,160) or [160,320)
+    const int part = (warp - 2) >> 2;     // column part of this warp: chunks [cb, ce) of the ten 32-column chunks
+    const int cb = (10 * part) / AT_NP, ce = (10 * (part + 1)) / AT_NP;
     const int r = q * 32 + lane;          // row inside the tile
     const uint32_t t_row = tmem + ((uint32_t)(q * 32) << 16);
     const float sl2 = a.scale_log2e;
@@ -198,8 +221,8 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_kernel(const __grid_consta
         // ---- pass 1: D = rowsum(P .* dP) over this thread's 160 columns
         float dot = 0.f;
 #pragma unroll 1
-        for (int c = 0; c < 5; c++) {
-          const int col0 = half * 160 + c * 32;
+        for (int c = cb; c < ce; c++) {
+          const int col0 = c * 32;
           if ((col0 >> 3) >= ncg) break;
           uint32_t v[32];
           tmem_ld32(t_row + (uint32_t)col0, v);
@@ -219,16 +242,19 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_kernel(const __grid_consta
             }
           }
         }
-        asm volatile("st.shared.f32 [%0], %1;" ::"r"(sRed + 4u * (half * 128 + r)), "f"(dot) : "memory");
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        float d0, d1;
-        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(d0) : "r"(sRed + 4u * r));
-        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(d1) : "r"(sRed + 4u * (128 + r)));
-        const float D = d0 + d1;
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(sRed + 4u * (part * 128 + r)), "f"(dot) : "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(AT_ST) : "memory");
+        float D = 0.f;
+#pragma unroll
+        for (int pp = 0; pp < AT_NP; pp++) {
+          float dpart;
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(dpart) : "r"(sRed + 4u * (pp * 128 + r)));
+          D += dpart;
+        }
         // ---- pass 2: dS = scale * P .* (dP - D), written in place of P
 #pragma unroll 1
-        for (int c = 0; c < 5; c++) {
-          const int col0 = half * 160 + c * 32;
+        for (int c = cb; c < ce; c++) {
+          const int col0 = c * 32;
           if ((col0 >> 3) >= ncg) break;
           uint32_t v[32];
           tmem_ld32(t_row + (uint32_t)col0, v);
@@ -252,7 +278,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_kernel(const __grid_consta
         }
         tc_fence_before();
         fence_async_smem();
-        asm volatile("bar.sync 3, 256;" ::: "memory");
+        asm volatile("bar.sync 3, %0;" ::"n"(AT_ST) : "memory");
         if (threadIdx.x == 64) {
           mbar_arrive(p_full);
           for (int kb = 0; kb < nkb; kb++)
@@ -270,8 +296,8 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_kernel(const __grid_consta
         // activity with 10 warps per SM), so chunks that lie completely below Nkv take a predicate-free body
         float mx = -INFINITY;
   #pragma unroll 1
-        for (int c = 0; c < 5; c++) {
-          const int col0 = half * 160 + c * 32;
+        for (int c = cb; c < ce; c++) {
+          const int col0 = c * 32;
           if (col0 >= a.Nk) break;
           uint32_t v[32];
           tmem_ld32(t_row + (uint32_t)col0, v);
@@ -287,19 +313,22 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_kernel(const __grid_consta
               if (col0 + j < a.Nk) mx = fmaxf(mx, __uint_as_float(v[j]));
           }
         }
-        asm volatile("st.shared.f32 [%0], %1;" ::"r"(sRed + 4u * (half * 128 + r)), "f"(mx) : "memory");
-        asm volatile("bar.sync 1, 256;" ::: "memory");   // also orders thread 64's wait_group.read before any P write
-        float m0, m1;
-        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(m0) : "r"(sRed + 4u * r));
-        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(m1) : "r"(sRed + 4u * (128 + r)));
-        const float m = fmaxf(m0, m1);
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(sRed + 4u * (part * 128 + r)), "f"(mx) : "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(AT_ST) : "memory");   // also orders thread 64's wait_group.read before any P write
+        float m = -INFINITY;
+#pragma unroll
+        for (int pp = 0; pp < AT_NP; pp++) {
+          float mpart;
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(mpart) : "r"(sRed + 4u * (pp * 128 + r)));
+          m = fmaxf(m, mpart);
+        }
         const float moff = m * sl2;
         // ---- pass 2: p = 2^(s*scale*log2e - m*scale*log2e) (one MUFU.EX2 each), row sum, bf16 P -> shared memory (K-major,
         // SWIZZLE_128B).  The sum is taken over the bf16-rounded values (what the P V MMA sees) in four independent chains.
         float s4[4] = {0.f, 0.f, 0.f, 0.f};
   #pragma unroll 1
-        for (int c = 0; c < 5; c++) {
-          const int col0 = half * 160 + c * 32;
+        for (int c = cb; c < ce; c++) {
+          const int col0 = c * 32;
           const uint32_t rowad = sP + (uint32_t)r * 128;
           const uint32_t sw = (uint32_t)r & 7u;
           if (col0 >= a.Nk) {   // keys beyond Nkv: P = 0 (their V rows are zero-filled, but 0 * garbage could be NaN)
@@ -338,18 +367,22 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_kernel(const __grid_consta
           }
         }
         const float sum = (s4[0] + s4[1]) + (s4[2] + s4[3]);
-        asm volatile("st.shared.f32 [%0], %1;" ::"r"(sRed + 1024u + 4u * (half * 128 + r)), "f"(sum) : "memory");
-        asm volatile("bar.sync 2, 256;" ::: "memory");
-        float l0, l1;
-        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(l0) : "r"(sRed + 1024u + 4u * r));
-        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(l1) : "r"(sRed + 1024u + 4u * (128 + r)));
-        const float inv = 1.f / (l0 + l1);
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(sRed + AT_RED2 + 4u * (part * 128 + r)), "f"(sum) : "memory");
+        asm volatile("bar.sync 2, %0;" ::"n"(AT_ST) : "memory");
+        float lsum = 0.f;
+#pragma unroll
+        for (int pp = 0; pp < AT_NP; pp++) {
+          float lpart;
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(lpart) : "r"(sRed + AT_RED2 + 4u * (pp * 128 + r)));
+          lsum += lpart;
+        }
+        const float inv = 1.f / lsum;
         o_scale = 1.f;
         if (a.store_p) {
           // ---- training: normalise this thread's 160 probabilities in place (the stored P is what the backward pass consumes)
   #pragma unroll 1
-          for (int cg = 0; cg < 20; cg++) {
-            const int col = half * 160 + cg * 8;
+          for (int cg = cb * 4; cg < ce * 4; cg++) {
+            const int col = cg * 8;
             if (col >= a.Nk) break;
             const uint32_t kb = (uint32_t)col >> 6, ch = ((uint32_t)col & 63u) >> 3;
             const uint32_t ad = sP + kb * 16384 + (uint32_t)r * 128 + ((ch ^ ((uint32_t)r & 7u)) << 4);
@@ -366,11 +399,11 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_kernel(const __grid_consta
         } else {
           o_scale = inv;   // inference / recompute backward: P stays unnormalised, the 64 output columns are scaled instead
         }
-        if (a.lse && half == 0 && q0 + r < a.N)
-          a.lse[bh * a.N + q0 + r] = m * (sl2 * 0.69314718055994531f) + logf(l0 + l1);
+        if (a.lse && part == 0 && q0 + r < a.N)
+          a.lse[bh * a.N + q0 + r] = m * (sl2 * 0.69314718055994531f) + logf(lsum);
         tc_fence_before();
         fence_async_smem();
-        asm volatile("bar.sync 3, 256;" ::: "memory");      // P complete (generic-proxy writes fenced for the async proxy)
+        asm volatile("bar.sync 3, %0;" ::"n"(AT_ST) : "memory");      // P complete (generic-proxy writes fenced for the async proxy)
         if (threadIdx.x == 64) {
           mbar_arrive(p_full);
           if (a.store_p) {
@@ -388,13 +421,14 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_kernel(const __grid_consta
       mbar_wait(o_full, (uint32_t)i & 1u);
       tc_fence_after();
       {
-        uint32_t v[32];
-        tmem_ld32(t_row + AT_O_COL + (uint32_t)(half * 32), v);
+        constexpr int OC = AT_D / AT_NP;   // output columns of this warp (16 with four parts)
+        uint32_t v[OC];
+        tmem_ld_n<OC>(t_row + AT_O_COL + (uint32_t)(part * OC), v);
         tmem_wait_ld();
         if (q0 + r < a.N) {
-          bf16* dst = a.o + ((long)b * a.N + q0 + r) * a.ldo + h * AT_D + half * 32;
+          bf16* dst = a.o + ((long)b * a.N + q0 + r) * a.ldo + h * AT_D + part * OC;
 #pragma unroll
-          for (int g = 0; g < 4; g++) {
+          for (int g = 0; g < OC / 8; g++) {
             float f[8];
 #pragma unroll
             for (int j = 0; j < 8; j++) f[j] = __uint_as_float(v[g * 8 + j]) * (MODE == 0 ? o_scale : 1.f);
