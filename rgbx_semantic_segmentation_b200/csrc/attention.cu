@@ -34,20 +34,6 @@ constexpr uint32_t AT_BAR_OFF = AT_RED_OFF + 2 * AT_RED2;
 constexpr uint32_t AT_SMEM = AT_BAR_OFF + 256 + 1024;  // + alignment slack
 constexpr uint32_t AT_O_COL = 320;
 
-template <int N>
-__device__ __forceinline__ void tmem_ld_n(uint32_t taddr, uint32_t* r) {   // tcgen05.ld 32x32b of N = 16 or 32 columns
-  if constexpr (N == 32) {
-    tmem_ld32(taddr, r);
-  } else {
-    static_assert(N == 16, "tmem_ld_n: 16 or 32 columns");
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
-  }
-}
-
 __device__ __forceinline__ float ex2_approx(float x) {   // one MUFU.EX2 (2 ulp; the result is rounded to bf16 anyway)
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));

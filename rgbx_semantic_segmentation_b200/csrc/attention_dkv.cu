@@ -32,7 +32,10 @@ extern std::atomic<long long> g_cmx_launches;
 constexpr int DK_BK = 128;   // keys per CTA
 constexpr int DK_BQ = 128;   // queries per tile
 constexpr int DK_D = 64;     // head dim
-constexpr int DK_THREADS = 64 + 256;
+constexpr int DK_NP = 4;                       // column parts of a 128-wide S / dP tile, one group of four warps each
+constexpr int DK_SW = DK_NP * 128;              // exp2 / dS threads
+constexpr int DK_CPP = 128 / DK_NP;             // columns per part (a multiple of 32)
+constexpr int DK_THREADS = 64 + DK_SW;
 constexpr uint32_t DK_K_OFF = 0, DK_V_OFF = 16384, DK_Q_OFF = 32768, DK_DO_OFF = 65536, DK_P_OFF = 98304, DK_DS_OFF = 131072,
                    DK_LD_OFF = 163840, DK_BAR_OFF = DK_LD_OFF + 2048;
 constexpr uint32_t DK_SMEM = DK_BAR_OFF + 256 + 1024;  // + alignment slack
@@ -164,9 +167,9 @@ __global__ void __launch_bounds__(DK_THREADS, 1) attn_dkv_kernel(const __grid_co
   } else if (ntiles > 0) {
     // ============================ exp2 / dS warps (2..9) ============================
     const int qd = warp & 3;               // TMEM lane quarter
-    const int half = (warp - 2) >> 2;      // query-column half: [0,64) or [64,128)
+    const int part = (warp - 2) >> 2;      // query-column part: [part * DK_CPP, (part + 1) * DK_CPP)
     const int r = qd * 32 + lane;          // key row inside the block
-    const int ct = threadIdx.x - 64;       // 0..255
+    const int ct = threadIdx.x - 64;       // 0..DK_SW-1
     const uint32_t t_row = tmem + ((uint32_t)(qd * 32) << 16);
     const bool key_ok = jb * DK_BK + r < a.Nk;
     const float sl2 = a.scale_log2e, sc = a.scale;
@@ -176,20 +179,20 @@ __global__ void __launch_bounds__(DK_THREADS, 1) attn_dkv_kernel(const __grid_co
       const int q0 = (t_begin + i) * DK_BQ;
       const uint32_t buf = sLD + (uint32_t)(i & 1) * 1024u;   // double-buffered [128 x lse*log2e][128 x delta] (2 x 512 B)
       // stage the per-query constants of this tile: +inf normaliser for queries >= N makes their probability exactly 0
-      {
+      if (ct < 256) {
         const int qi = q0 + (ct & 127);
         float val;
         if (ct < 128) val = qi < a.N ? lse[qi] * 1.4426950408889634f : INFINITY;
         else val = qi < a.N ? dlt[qi] : 0.f;
         asm volatile("st.shared.f32 [%0], %1;" ::"r"(buf + (ct < 128 ? 0u : 512u) + 4u * (uint32_t)(ct & 127)), "f"(val) : "memory");
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(DK_SW) : "memory");
       mbar_wait(s_full, (uint32_t)i & 1u);                     // S^T and dP^T of tile i are in tensor memory
       if (i > 0) mbar_wait(pds_empty, (uint32_t)(i - 1) & 1u); // the gradient MMAs of tile i-1 have read the staging tiles
       tc_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < 2; c++) {
-        const int col0 = half * 64 + c * 32;
+      for (int c = 0; c < DK_CPP / 32; c++) {
+        const int col0 = part * DK_CPP + c * 32;
         uint32_t sv[32], dv[32];
         tmem_ld32(t_row + DK_COL_S + (uint32_t)col0, sv);
         tmem_ld32(t_row + DK_COL_DP + (uint32_t)col0, dv);
@@ -217,24 +220,26 @@ __global__ void __launch_bounds__(DK_THREADS, 1) attn_dkv_kernel(const __grid_co
             dk[j] = *reinterpret_cast<uint32_t*>(&hs);
           }
           // K-major SWIZZLE_128B staging: 64 queries (128 B) per row and k-block, 16-byte chunk index XOR (row & 7)
-          const uint32_t ch = (uint32_t)(c * 4 + g);
-          const uint32_t off = (uint32_t)half * 16384u + (uint32_t)r * 128u + ((ch ^ ((uint32_t)r & 7u)) << 4);
+          const uint32_t ch = (uint32_t)(((col0 & 63) >> 3) + g);
+          const uint32_t off = (uint32_t)(col0 >> 6) * 16384u + (uint32_t)r * 128u + ((ch ^ ((uint32_t)r & 7u)) << 4);
           st_shared_v4(sP + off, pk[0], pk[1], pk[2], pk[3]);
           st_shared_v4(sDS + off, dk[0], dk[1], dk[2], dk[3]);
         }
       }
       tc_fence_before();
       fence_async_smem();
-      asm volatile("bar.sync 2, 256;" ::: "memory");   // staging tiles complete and fenced for the async proxy; TMEM reads done
+      asm volatile("bar.sync 2, %0;" ::"n"(DK_SW) : "memory");   // staging tiles complete and fenced for the async proxy; TMEM reads done
       if (ct == 0) mbar_arrive(p_full);
     }
     // ---- epilogue: dV / dK accumulators (TMEM) -> fp32 adds into the kv-projection gradient
     mbar_wait(acc_full, 0);
     tc_fence_after();
     const int key = jb * DK_BK + r;
-    float* row = a.dkv + ((long)b * a.Nk + key) * a.lddkv + h * DK_D + half * 32;
+    // 2 accumulators x 2 column halves = 4 (accumulator, half) pieces of 32 columns, dealt round-robin to the DK_NP parts
 #pragma unroll 1
-    for (int w = 0; w < 2; w++) {   // w = 0: dV (columns C + ...), w = 1: dK
+    for (int piece = part; piece < 4; piece += DK_NP) {   // w = 0: dV (columns C + ...), w = 1: dK
+      const int w = piece >> 1, half = piece & 1;
+      float* row = a.dkv + ((long)b * a.Nk + key) * a.lddkv + h * DK_D + half * 32;
       uint32_t v[32];
       tmem_ld32(t_row + (w == 0 ? DK_COL_DV : DK_COL_DK) + (uint32_t)(half * 32), v);
       tmem_wait_ld();
@@ -305,7 +310,7 @@ __global__ void __launch_bounds__(DK_THREADS, 1) attn_dq_kernel(const __grid_con
     mbar_init(p_full, 1);
     mbar_init(ds_empty, 1);
     mbar_init(o_full, 1);
-    mbar_init(o_empty, 8);
+    mbar_init(o_empty, 4 * DK_NP);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -406,7 +411,7 @@ __global__ void __launch_bounds__(DK_THREADS, 1) attn_dq_kernel(const __grid_con
   } else {
     // ============================ exp2 / dS warps (2..9) + dQ epilogue ============================
     const int qd = warp & 3;
-    const int half = (warp - 2) >> 2;      // key-column half of the block: [0,64) or [64,128)
+    const int part = (warp - 2) >> 2;      // key-column part of the block: [part * DK_CPP, (part + 1) * DK_CPP)
     const int r = qd * 32 + lane;          // query row inside the tile
     const int ct = threadIdx.x - 64;
     const uint32_t t_row = tmem + ((uint32_t)(qd * 32) << 16);
@@ -425,8 +430,8 @@ __global__ void __launch_bounds__(DK_THREADS, 1) attn_dq_kernel(const __grid_con
         if (st > 0) mbar_wait(ds_empty, (uint32_t)(st - 1) & 1u);   // the dQ MMAs of the previous step have read the staging tile
         tc_fence_after();
 #pragma unroll 1
-        for (int c = 0; c < 2; c++) {
-          const int col0 = half * 64 + c * 32;
+        for (int c = 0; c < DK_CPP / 32; c++) {
+          const int col0 = part * DK_CPP + c * 32;
           const int key0 = blk * DK_BK + col0;
           uint32_t sv[32], dv[32];
           tmem_ld32(t_row + DQ_COL_S + (uint32_t)col0, sv);
@@ -443,26 +448,27 @@ __global__ void __launch_bounds__(DK_THREADS, 1) attn_dq_kernel(const __grid_con
               __nv_bfloat162 hs = __floats2bfloat162_rn(sc * p0 * (__uint_as_float(dv[e]) - dl), sc * p1 * (__uint_as_float(dv[e + 1]) - dl));
               dk[j] = *reinterpret_cast<uint32_t*>(&hs);
             }
-            const uint32_t ch = (uint32_t)(c * 4 + g);
-            st_shared_v4(sDS + (uint32_t)half * 16384u + (uint32_t)r * 128u + ((ch ^ ((uint32_t)r & 7u)) << 4), dk[0], dk[1], dk[2], dk[3]);
+            const uint32_t ch = (uint32_t)(((col0 & 63) >> 3) + g);
+            st_shared_v4(sDS + (uint32_t)(col0 >> 6) * 16384u + (uint32_t)r * 128u + ((ch ^ ((uint32_t)r & 7u)) << 4), dk[0], dk[1], dk[2], dk[3]);
           }
         }
         tc_fence_before();
         fence_async_smem();
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(DK_SW) : "memory");
         if (ct == 0) mbar_arrive(p_full);
       }
       // ---- epilogue: dQ tile TMEM -> bf16 -> global; each thread of the pair takes 32 of the 64 columns
       mbar_wait(o_full, (uint32_t)i & 1u);
       tc_fence_after();
       {
-        uint32_t v[32];
-        tmem_ld32(t_row + DQ_COL_DQ + (uint32_t)(half * 32), v);
+        constexpr int OC = DK_D / DK_NP;   // dQ columns per part
+        uint32_t v[OC];
+        tmem_ld_n<OC>(t_row + DQ_COL_DQ + (uint32_t)(part * OC), v);
         tmem_wait_ld();
         if (q_ok) {
-          bf16* dst = a.dq + ((long)b * a.N + q0 + r) * a.lddq + h * DK_D + half * 32;
+          bf16* dst = a.dq + ((long)b * a.N + q0 + r) * a.lddq + h * DK_D + part * OC;
 #pragma unroll
-          for (int g = 0; g < 4; g++) {
+          for (int g = 0; g < OC / 8; g++) {
             float f[8];
 #pragma unroll
             for (int j = 0; j < 8; j++) f[j] = __uint_as_float(v[g * 8 + j]);
