@@ -461,11 +461,11 @@ CMX_API int cmx_attn_fwd(const void* q, int64_t ldq, const void* kv, int64_t ldk
   a.scale_log2e = scale * 1.4426950408889634f;
   a.scale = scale;
   a.store_p = p_out ? 1 : 0;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static thread_local PerDeviceOnce attr_once;
+  if (attr_once.pending()) {
     cudaError_t e = cudaFuncSetAttribute(attn_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AT_SMEM);
     if (e != cudaSuccess) CMX_FAIL((int)e, "cudaFuncSetAttribute(attn): %s", cudaGetErrorString(e));
-    attr_done = true;
+    attr_once.mark();
   }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -514,11 +514,11 @@ CMX_API int cmx_attn_bwd(const void* d_o, int64_t lddo, const void* kv, int64_t 
   a.scale_log2e = scale * 1.4426950408889634f;
   a.scale = scale;
   a.store_p = 0;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static thread_local PerDeviceOnce attr_once;
+  if (attr_once.pending()) {
     cudaError_t e = cudaFuncSetAttribute(attn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AT_SMEM);
     if (e != cudaSuccess) CMX_FAIL((int)e, "cudaFuncSetAttribute(attn bwd): %s", cudaGetErrorString(e));
-    attr_done = true;
+    attr_once.mark();
   }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);

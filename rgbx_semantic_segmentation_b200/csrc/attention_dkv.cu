@@ -553,11 +553,11 @@ CMX_API int cmx_attn_dkv(const void* q, int64_t ldq, const void* d_o, int64_t ld
   a.scale = scale;
   const long grid = units * a.qsplit;
   CMX_REQUIRE(grid < (1l << 31), "attn_dkv: grid too large");
-  static bool attr_done = false;
-  if (!attr_done) {
+  static thread_local PerDeviceOnce attr_once;
+  if (attr_once.pending()) {
     cudaError_t e = cudaFuncSetAttribute(attn_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DK_SMEM);
     if (e != cudaSuccess) CMX_FAIL((int)e, "cudaFuncSetAttribute(attn_dkv): %s", cudaGetErrorString(e));
-    attr_done = true;
+    attr_once.mark();
   }
   attn_dkv_kernel<<<(unsigned)grid, DK_THREADS, DK_SMEM, st>>>(tmQ, tmDO, tmKV, a);
   g_cmx_launches++;
@@ -592,11 +592,11 @@ CMX_API int cmx_attn_dq(const void* q, int64_t ldq, const void* d_o, int64_t ldd
   a.total_tiles = (long)a.tiles_per_bh * B * heads;
   a.scale_log2e = scale * 1.4426950408889634f;
   a.scale = scale;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static thread_local PerDeviceOnce attr_once;
+  if (attr_once.pending()) {
     cudaError_t e = cudaFuncSetAttribute(attn_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DQ_SMEM);
     if (e != cudaSuccess) CMX_FAIL((int)e, "cudaFuncSetAttribute(attn_dq): %s", cudaGetErrorString(e));
-    attr_done = true;
+    attr_once.mark();
   }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);

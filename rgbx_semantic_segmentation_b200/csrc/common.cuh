@@ -6,6 +6,21 @@
 #include <stdio.h>
 #include <stdarg.h>
 #include <math.h>
+#include <atomic>
+
+// cudaFuncSetAttribute is a per-DEVICE setting: a call site keeps one static PerDeviceOnce and repeats the opt-in for every
+// device ordinal it is first used on (a second GPU in the same process would otherwise launch without its shared-memory opt-in).
+struct PerDeviceOnce {
+  std::atomic<unsigned long long> done{0};
+  unsigned long long bit = 0;
+  bool pending() {
+    int d = 0;
+    cudaGetDevice(&d);
+    bit = 1ull << (d & 63);
+    return !(done.load(std::memory_order_acquire) & bit);
+  }
+  void mark() { done.fetch_or(bit, std::memory_order_release); }
+};
 
 typedef __nv_bfloat16 bf16;
 

@@ -123,10 +123,12 @@ __global__ void __launch_bounds__(DW_CG* DW_PY) dwconv_fwd_kernel(const bf16* __
 //   * global traffic per warp access is one full 128-byte line (64 channels x bf16), for dy reads and y/du writes.
 // MODE 0: y = act(conv(x)+b)   MODE 1: du = dy * act'(conv(x)+b), dW/db reduced   MODE 2: dx = conv_flipped(du)
 // ------------------------------------------------------------------------------------------------
-constexpr int DT_TH = 8, DT_TW = 32, DT_CH = 64;
+constexpr int DT_TH = 8, DT_CH = 64;
+// tile width TW: 32 pixels, or 20 for the narrow late-stage maps (W = 40 / 20 / 80 ...: a 32-wide tile would be 62 % full at W = 40)
+constexpr int dt_min_ctas(int mode, int tw) { return mode == 1 ? 2 : (tw <= 20 ? 4 : 3); }
 
-template <int ACT, int MODE>
-__global__ void __launch_bounds__(256, (MODE == 1 ? 2 : 3)) dwconv_tiled_kernel(const bf16* __restrict__ x, long ldx, const float* __restrict__ w,
+template <int ACT, int MODE, int TW>
+__global__ void __launch_bounds__(256, dt_min_ctas(MODE, TW)) dwconv_tiled_kernel(const bf16* __restrict__ x, long ldx, const float* __restrict__ w,
                                                            const float* __restrict__ bias, const bf16* __restrict__ dy, long lddy,
                                                            bf16* __restrict__ out, long ldo, float* __restrict__ dw,
                                                            float* __restrict__ db, int B, int H, int W, int C, int tiles_x,
@@ -141,7 +143,7 @@ __global__ void __launch_bounds__(256, (MODE == 1 ? 2 : 3)) dwconv_tiled_kernel(
     if (dw) dw += g * pgs;
     if (db) db += g * pgs;
   }
-  __shared__ __align__(16) bf16 tile[(DT_TH + 2) * (DT_TW + 2) * DT_CH];  // 43.5 KB
+  __shared__ __align__(16) bf16 tile[(DT_TH + 2) * (TW + 2) * DT_CH];  // 43.5 KB at TW = 32, 27.5 KB at TW = 20
   __shared__ float sred[20][DT_CH];
   const int tid = threadIdx.x;
   const int r = tid >> 5, cp = tid & 31;
@@ -164,12 +166,12 @@ __global__ void __launch_bounds__(256, (MODE == 1 ? 2 : 3)) dwconv_tiled_kernel(
     const int tx = (int)(tl % tiles_x);
     const int ty = (int)((tl / tiles_x) % tiles_y);
     const int b = (int)(tl / ((long)tiles_x * tiles_y));
-    const int x0 = tx * DT_TW, y0 = ty * DT_TH;
+    const int x0 = tx * TW, y0 = ty * DT_TH;
     __syncthreads();  // previous tile fully consumed
     // ---- stage the halo tile: (TH+2)*(TW+2) pixels x 8 chunks of 8 channels, as asynchronous 16-byte copies
     // (cp.async with zero fill outside the image): all ~11 copies of a thread are in flight together
     {
-      constexpr int NCH = (DT_TH + 2) * (DT_TW + 2) * (DT_CH / 8);
+      constexpr int NCH = (DT_TH + 2) * (TW + 2) * (DT_CH / 8);
       const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(tile);
 #pragma unroll
       for (int k = 0; k < (NCH + 255) / 256; k++) {
@@ -177,7 +179,7 @@ __global__ void __launch_bounds__(256, (MODE == 1 ? 2 : 3)) dwconv_tiled_kernel(
         if (i < NCH) {
           const int ch8 = i & 7;
           const int pix = i >> 3;
-          const int px = pix % (DT_TW + 2), py = pix / (DT_TW + 2);
+          const int px = pix % (TW + 2), py = pix / (TW + 2);
           const int gy = y0 + py - 1, gx = x0 + px - 1;
           const bool inb = gy >= 0 && gy < H && gx >= 0 && gx < W && cbase + ch8 * 8 < C;
           const bf16* src = inb ? x + ((long)(b * H + gy) * W + gx) * ldx + cbase + ch8 * 8 : x;
@@ -189,13 +191,13 @@ __global__ void __launch_bounds__(256, (MODE == 1 ? 2 : 3)) dwconv_tiled_kernel(
     }
     const int gy = y0 + r;
     // MODE 1: this thread's 32 dy values of the row are requested before waiting for the tile (independent loads)
-    uint32_t gq[DT_TW];
+    uint32_t gq[TW];
     if (MODE == 1) {
       // (one 64-bit address per row, then a pointer increment per pixel: the per-pixel index arithmetic was ~10 % of the
       // kernel's instructions and the kernel is issue bound)
       const bf16* dyp = dy + ((long)(b * H + (gy < H ? gy : 0)) * W + x0) * lddy + c;
 #pragma unroll
-      for (int px = 0; px < DT_TW; px++) {
+      for (int px = 0; px < TW; px++) {
         const int gx = x0 + px;
         gq[px] = 0u;
         if (gy < H && c_ok && gx < W) gq[px] = __ldg(reinterpret_cast<const unsigned int*>(dyp));
@@ -211,18 +213,18 @@ __global__ void __launch_bounds__(256, (MODE == 1 ? 2 : 3)) dwconv_tiled_kernel(
       for (int i = 0; i < 3; i++) {
 #pragma unroll
         for (int j = 0; j < 2; j++) {
-          const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&tile[((r + i) * (DT_TW + 2) + j) * DT_CH + cp * 2]);
+          const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&tile[((r + i) * (TW + 2) + j) * DT_CH + cp * 2]);
           win[i][j + 1] = __bfloat1622float2(h2);
         }
       }
       bf16* orow = out + ((long)(b * H + gy) * W + x0) * ldo + c;   // advanced by ldo per pixel
 #pragma unroll  // fully unrolled: the sliding-window register rotation disappears and gq[] stays in registers
-      for (int px = 0; px < DT_TW; px++) {
+      for (int px = 0; px < TW; px++) {
 #pragma unroll
         for (int i = 0; i < 3; i++) {
           win[i][0] = win[i][1];
           win[i][1] = win[i][2];
-          const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&tile[((r + i) * (DT_TW + 2) + px + 2) * DT_CH + cp * 2]);
+          const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&tile[((r + i) * (TW + 2) + px + 2) * DT_CH + cp * 2]);
           win[i][2] = __bfloat1622float2(h2);
         }
         const int gx = x0 + px;
@@ -300,10 +302,10 @@ __global__ void __launch_bounds__(256, (MODE == 1 ? 2 : 3)) dwconv_tiled_kernel(
   }
 }
 
-template <int ACT, int MODE>
-static void dwconv_tiled_launch(const void* x, long ldx, const float* w, const float* bias, const void* dy, long lddy, void* out,
-                                long ldo, float* dw, float* db, int B, int H, int W, int C, int groups, long pgs, cudaStream_t st) {
-  const int tiles_x = (W + DT_TW - 1) / DT_TW, tiles_y = (H + DT_TH - 1) / DT_TH;
+template <int ACT, int MODE, int TW>
+static void dwconv_tiled_launch_tw(const void* x, long ldx, const float* w, const float* bias, const void* dy, long lddy, void* out,
+                                   long ldo, float* dw, float* db, int B, int H, int W, int C, int groups, long pgs, cudaStream_t st) {
+  const int tiles_x = (W + TW - 1) / TW, tiles_y = (H + DT_TH - 1) / DT_TH;
   const long ntiles = (long)B * tiles_x * tiles_y;
   const int gx = (C + DT_CH - 1) / DT_CH;
   long gy = ntiles;
@@ -311,8 +313,27 @@ static void dwconv_tiled_launch(const void* x, long ldx, const float* w, const f
   cap = (cap + groups - 1) / groups;
   if (gy > cap) gy = cap;
   dim3 grid(gx, (unsigned)gy, (unsigned)groups);
-  dwconv_tiled_kernel<ACT, MODE><<<grid, 256, 0, st>>>((const bf16*)x, ldx, w, bias, (const bf16*)dy, lddy, (bf16*)out, ldo, dw, db, B,
-                                                       H, W, C, tiles_x, tiles_y, ntiles, pgs);
+  dwconv_tiled_kernel<ACT, MODE, TW><<<grid, 256, 0, st>>>((const bf16*)x, ldx, w, bias, (const bf16*)dy, lddy, (bf16*)out, ldo, dw, db,
+                                                           B, H, W, C, tiles_x, tiles_y, ntiles, pgs);
+}
+
+// tile width with the fewest staged pixel columns (padded width + 2 halo columns per tile); ties go to the wider tile
+static int dwconv_pick_tw(int W) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("CMX_DWCONV_TW");
+    forced = e ? atoi(e) : 0;
+  }
+  if (forced == 32 || forced == 20) return forced;
+  const long c32 = (long)((W + 31) / 32) * 34, c20 = (long)((W + 19) / 20) * 22;
+  return c20 < c32 ? 20 : 32;
+}
+
+template <int ACT, int MODE>
+static void dwconv_tiled_launch(const void* x, long ldx, const float* w, const float* bias, const void* dy, long lddy, void* out,
+                                long ldo, float* dw, float* db, int B, int H, int W, int C, int groups, long pgs, cudaStream_t st) {
+  if (dwconv_pick_tw(W) == 20) dwconv_tiled_launch_tw<ACT, MODE, 20>(x, ldx, w, bias, dy, lddy, out, ldo, dw, db, B, H, W, C, groups, pgs, st);
+  else dwconv_tiled_launch_tw<ACT, MODE, 32>(x, ldx, w, bias, dy, lddy, out, ldo, dw, db, B, H, W, C, groups, pgs, st);
 }
 
 CMX_API int cmx_dwconv3x3_fwd(const void* x, int64_t ldx, const float* w, const float* bias, int act, int flip, void* y,

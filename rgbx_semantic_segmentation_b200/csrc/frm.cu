@@ -325,9 +325,82 @@ __global__ void __launch_bounds__(256) smallm_dx_kernel(const float* __restrict_
   for (int m = 0; m < SMALLM_MAX; m++)
     if (m < Mb) atomicAdd(dx + (long)m * K + k, acc[m]);
 }
+// ONE launch for the whole backward of a small-M linear (the three kernels above stay for reference / CMX_SMALLM_BWD_SPLIT=1):
+//   CTAs [0, nb_dw):      dW[n,k] += sum_m dpre[m,n] x[m,k], four consecutive k per thread (16-byte accesses)
+//   CTAs [nb_dw, ...):    dx[m,k] += sum_{n in chunk} dpre[m,n] W[n,k] (atomics into the zeroed dx); the k-chunk-0 CTAs also add db
+// with dpre = dy * act'(y) recomputed where it is used (Mb * N values) instead of a workspace round trip.
+__device__ __forceinline__ float smallm_dpre(float g, float yv, int act) {
+  if (act == 1) return yv > 0.f ? g : 0.f;
+  if (act == 3) return g * yv * (1.f - yv);
+  return g;
+}
+__global__ void __launch_bounds__(256) smallm_bwd_fused_kernel(const float* __restrict__ dy, const float* __restrict__ y, int act,
+                                                               const float* __restrict__ x, const float* __restrict__ w,
+                                                               float* __restrict__ dx, float* __restrict__ dw, float* __restrict__ db,
+                                                               int Mb, int N, int K, int nb_dw, int kchunks) {
+  pdl_trigger();
+  __shared__ float sd[SMALLM_MAX][64];
+  if ((int)blockIdx.x < nb_dw) {
+    // ---- dW: K % 4 == 0 (checked by the launcher); one thread = 4 consecutive k of one row n
+    const long q = (long)blockIdx.x * 256 + threadIdx.x;
+    const int kq = K >> 2;
+    if (q >= (long)N * kq) return;
+    const int n = (int)(q / kq), k = (int)(q % kq) * 4;
+    float4 s = *reinterpret_cast<const float4*>(dw + (long)n * K + k);
+    for (int m = 0; m < Mb; m++) {
+      const float g = smallm_dpre(__ldg(dy + (long)m * N + n), __ldg(y + (long)m * N + n), act);
+      const float4 xv = __ldg(reinterpret_cast<const float4*>(x + (long)m * K + k));
+      s.x = fmaf(g, xv.x, s.x); s.y = fmaf(g, xv.y, s.y); s.z = fmaf(g, xv.z, s.z); s.w = fmaf(g, xv.w, s.w);
+    }
+    *reinterpret_cast<float4*>(dw + (long)n * K + k) = s;
+    return;
+  }
+  const int bid = (int)blockIdx.x - nb_dw;
+  const int kc = bid % kchunks, n0 = (bid / kchunks) * 64;
+  for (int i = threadIdx.x; i < SMALLM_MAX * 64; i += 256) {
+    const int m = i >> 6, n = n0 + (i & 63);
+    sd[m][i & 63] = (m < Mb && n < N) ? smallm_dpre(__ldg(dy + (long)m * N + n), __ldg(y + (long)m * N + n), act) : 0.f;
+  }
+  __syncthreads();
+  if (db && kc == 0 && threadIdx.x < 64 && n0 + (int)threadIdx.x < N) {
+    float sb = 0.f;
+    for (int m = 0; m < Mb; m++) sb += sd[m][threadIdx.x];
+    db[n0 + threadIdx.x] += sb;
+  }
+  if (!dx) return;
+  const int k = kc * 256 + threadIdx.x;
+  if (k >= K) return;
+  float acc[SMALLM_MAX];
+#pragma unroll
+  for (int m = 0; m < SMALLM_MAX; m++) acc[m] = 0.f;
+  for (int n = 0; n < 64; n += 8) {
+    if (n0 + n >= N) break;
+    float wv[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) wv[u] = n0 + n + u < N ? __ldg(w + (long)(n0 + n + u) * K + k) : 0.f;
+#pragma unroll
+    for (int u = 0; u < 8; u++)
+#pragma unroll
+      for (int m = 0; m < SMALLM_MAX; m++) acc[m] = fmaf(sd[m][n + u], wv[u], acc[m]);
+  }
+#pragma unroll
+  for (int m = 0; m < SMALLM_MAX; m++)
+    if (m < Mb) atomicAdd(dx + (long)m * K + k, acc[m]);
+}
 CMX_API int cmx_smallm_linear_bwd(const float* dy, const float* y, int act, const float* x, const float* w, float* dx, float* dw,
                                   float* db, float* dpre_ws, int Mb, int N, int K, void* stream) {
+  CMX_REQUIRE(Mb >= 1 && Mb <= SMALLM_MAX, "smallm_linear_bwd: Mb=%d must be in [1,%d]", Mb, SMALLM_MAX);
   cudaStream_t st = (cudaStream_t)stream;
+  static int split = -1;
+  if (split < 0) split = getenv("CMX_SMALLM_BWD_SPLIT") != nullptr ? 1 : 0;
+  if (!split && K % 4 == 0 && ((((uintptr_t)x) | ((uintptr_t)(dw ? dw : x))) & 15) == 0) {
+    if (dx) cudaMemsetAsync(dx, 0, sizeof(float) * (size_t)Mb * K, st);
+    const int nb_dw = dw ? (int)cdiv((long)N * (K / 4), 256) : 0;
+    const int kchunks = (int)cdiv(K, 256);
+    const int nb_dx = (dx || db) ? kchunks * (int)cdiv(N, 64) : 0;
+    smallm_bwd_fused_kernel<<<nb_dw + nb_dx, 256, 0, st>>>(dy, y, act, x, w, dx, dw, db, Mb, N, K, nb_dw, kchunks);
+    LAUNCH_DONE("smallm_linear_bwd");
+  }
   smallm_dpre_kernel<<<cdiv(N, 128), 128, 0, st>>>(dy, y, act, dpre_ws, db, Mb, N);
   g_cmx_launches++;
   if (dw) {

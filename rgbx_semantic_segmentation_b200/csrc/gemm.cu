@@ -913,13 +913,13 @@ static int launch_tc(const CmxGemm* g, const Epi& epi, cudaStream_t st) {
   if (stages < 2) stages = 2;
   sc.stages = stages;
   const size_t smem = (size_t)stages * STAGE_BYTES + (sc.tma_store ? TC_CSTAGE_BYTES : 0) + 2048 + 1024 + 16 * stages + 128;
-  static bool attr_done = false;
+  static thread_local PerDeviceOnce attr_once;
   auto kern = gemm_tc_kernel<BN, A_MN, B_MN, BATCHED, EW, CPS>;
-  if (!attr_done) {
+  if (attr_once.pending()) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) CMX_FAIL((int)e, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    attr_done = true;
+    attr_once.mark();
   }
   Epi e2 = epi;
   e2.atomic = atomic ? 1 : 0;

@@ -23,6 +23,7 @@ m.use_cuda_graph = False
 rgb, x, gt = bench.synth_batch(a.batch, 1, device=dev)
 for i in range(2 + a.steps):
     n0 = ops.launch_count()
+    m.zero_grad(set_to_none=True)   # like optimizer.zero_grad(): without it autograd ADDS into every .grad (one torch kernel per parameter)
     loss = m(rgb, x, gt)
     loss.backward()
     torch.cuda.synchronize()
