@@ -4,6 +4,7 @@
 // owns VEC channels x TW consecutive pixels of one image row and slides a 3 x (TW+2) register window,
 // 16-byte (8-byte for VEC=4) accesses, per-CTA weights staged in shared memory (tap-major).
 #include "common.cuh"
+#include "tc_common.cuh"
 #include "../../include/cmx_b200.h"
 #include <atomic>
 #include <stdlib.h>
@@ -124,6 +125,9 @@ __global__ void __launch_bounds__(DW_CG* DW_PY) dwconv_fwd_kernel(const bf16* __
 // MODE 0: y = act(conv(x)+b)   MODE 1: du = dy * act'(conv(x)+b), dW/db reduced   MODE 2: dx = conv_flipped(du)
 // ------------------------------------------------------------------------------------------------
 constexpr int DT_TH = 8, DT_CH = 64;
+// bf16 pair -> float2 in two integer ops (shift, mask); __bfloat1622float2 compiles to three (PRMT + 2 shifts) and the kernels
+// below unpack 3-4 pairs per pixel
+__device__ __forceinline__ float2 bf2_unpack(uint32_t u) { return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u)); }
 // tile width TW: 32 pixels, or 20 for the narrow late-stage maps (W = 40 / 20 / 80 ...: a 32-wide tile would be 62 % full at W = 40)
 constexpr int dt_min_ctas(int mode, int tw) { return mode == 1 ? 2 : (tw <= 20 ? 4 : 3); }
 
@@ -213,8 +217,7 @@ __global__ void __launch_bounds__(256, dt_min_ctas(MODE, TW)) dwconv_tiled_kerne
       for (int i = 0; i < 3; i++) {
 #pragma unroll
         for (int j = 0; j < 2; j++) {
-          const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&tile[((r + i) * (TW + 2) + j) * DT_CH + cp * 2]);
-          win[i][j + 1] = __bfloat1622float2(h2);
+          win[i][j + 1] = bf2_unpack(*reinterpret_cast<const uint32_t*>(&tile[((r + i) * (TW + 2) + j) * DT_CH + cp * 2]));
         }
       }
       bf16* orow = out + ((long)(b * H + gy) * W + x0) * ldo + c;   // advanced by ldo per pixel
@@ -224,8 +227,7 @@ __global__ void __launch_bounds__(256, dt_min_ctas(MODE, TW)) dwconv_tiled_kerne
         for (int i = 0; i < 3; i++) {
           win[i][0] = win[i][1];
           win[i][1] = win[i][2];
-          const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&tile[((r + i) * (TW + 2) + px + 2) * DT_CH + cp * 2]);
-          win[i][2] = __bfloat1622float2(h2);
+          win[i][2] = bf2_unpack(*reinterpret_cast<const uint32_t*>(&tile[((r + i) * (TW + 2) + px + 2) * DT_CH + cp * 2]));
         }
         const int gx = x0 + px;
         if (gx >= W) break;
@@ -235,7 +237,7 @@ __global__ void __launch_bounds__(256, dt_min_ctas(MODE, TW)) dwconv_tiled_kerne
 #pragma unroll
           for (int j = 0; j < 3; j++) ffma2(a, wt[i * 3 + j], win[i][j]);
         if (MODE == 1) {
-          float2 g = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&gq[px]));
+          float2 g = bf2_unpack(gq[px]);
           if (ACT == CMX_ACT_GELU) {
             g = fmul2(g, gelu_grad2(a));
           } else {
@@ -302,6 +304,260 @@ __global__ void __launch_bounds__(256, dt_min_ctas(MODE, TW)) dwconv_tiled_kerne
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// TMA-staged variant (the production path).  Same thread mapping and arithmetic as dwconv_tiled_kernel, but
+//   * the (8+2) x (TW+2) halo tile of x - and in MODE 1 the 8 x TW tile of dy - arrive by ONE cp.async.bulk.tensor each from a
+//     rank-4 tensor map [C, W, H, images]: the image border (coordinates -1 / W / H) and channels >= C are zero-filled by the
+//     copy engine, so the ~25 instructions per 16-byte chunk of index arithmetic and bounds tests of the cp.async loop are gone
+//     (ncu, stage 1: they were 28 % of the executed instructions of a kernel that is issue / FP32-pipe bound);
+//   * two stages: the copy of tile i+1 is in flight while tile i is computed (mbarrier complete_tx), so the load latency is
+//     hidden inside one CTA instead of across co-resident CTAs;
+//   * dy is read from shared memory (one LDS per pixel) instead of 32 prefetched registers: 96 instead of 128 registers.
+// ------------------------------------------------------------------------------------------------
+template <int MODE, int TW>
+struct DtmCfg {
+  static constexpr uint32_t XB = (uint32_t)(DT_TH + 2) * (TW + 2) * DT_CH * 2;
+  static constexpr uint32_t DB = MODE == 1 ? (uint32_t)DT_TH * TW * DT_CH * 2 : 0u;
+  static constexpr uint32_t STAGE = XB + DB;             // multiples of 128 B
+  static constexpr uint32_t SMEM = 2 * STAGE + 128;      // + alignment slack
+  static constexpr int MIN_CTAS = MODE == 1 ? 2 : 4;
+};
+
+template <int ACT, int MODE, int TW>
+__global__ void __launch_bounds__(256, (DtmCfg<MODE, TW>::MIN_CTAS)) dwconv_tma_kernel(const __grid_constant__ CUtensorMap tmX,
+                                                           const __grid_constant__ CUtensorMap tmDY, const float* __restrict__ w,
+                                                           const float* __restrict__ bias, bf16* __restrict__ out, long ldo,
+                                                           float* __restrict__ dw, float* __restrict__ db, int B, int H, int W, int C,
+                                                           int tiles_x, int tiles_y, long ntiles, long pgs) {
+  using Cfg = DtmCfg<MODE, TW>;
+  pdl_trigger();
+  extern __shared__ uint8_t dsm_raw[];
+  __shared__ float sred[20][DT_CH];
+  __shared__ __align__(8) uint64_t bars[2];
+  const uint32_t sbase = (smem_u32(dsm_raw) + 127u) & ~127u;
+  const uint32_t bar0 = smem_u32(&bars[0]);
+  const long g = blockIdx.z;   // group: samples [g*B, (g+1)*B) of the stacked tensors, parameters g * pgs elements further
+  out += g * B * H * W * ldo; w += g * pgs;
+  if (bias) bias += g * pgs;
+  if (dw) dw += g * pgs;
+  if (db) db += g * pgs;
+  const int tid = threadIdx.x;
+  const int r = tid >> 5, cp = tid & 31;
+  const int cbase = blockIdx.x * DT_CH;
+  const int c = cbase + cp * 2;
+  const bool c_ok = c < C;  // C is even
+  if (tid == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmX)) : "memory");
+    if (MODE == 1) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmDY)) : "memory");
+    mbar_init(bar0, 1);
+    mbar_init(bar0 + 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  float2 wt[9], bs = make_float2(0.f, 0.f);  // .x = channel c, .y = channel c + 1: every FMA below is one packed FFMA2
+#pragma unroll
+  for (int t = 0; t < 9; t++) {
+    const int tt = MODE == 2 ? 8 - t : t;
+    wt[t].x = c_ok ? w[(long)c * 9 + tt] : 0.f;
+    wt[t].y = c_ok ? w[(long)(c + 1) * 9 + tt] : 0.f;
+  }
+  if (MODE != 2 && bias && c_ok) { bs.x = bias[c]; bs.y = bias[c + 1]; }
+  float2 gw[9], gb = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int t = 0; t < 9; t++) gw[t] = make_float2(0.f, 0.f);
+  __syncthreads();
+
+  const int per_img = tiles_x * tiles_y;
+  auto issue = [&](long tl, int stage) {   // thread 0 only
+    const int tx = (int)(tl % tiles_x);
+    const int ty = (int)((tl / tiles_x) % tiles_y);
+    const int img = (int)(g * B + tl / per_img);
+    const uint32_t bar = bar0 + 8u * (uint32_t)stage;
+    const uint32_t dst = sbase + (uint32_t)stage * Cfg::STAGE;
+    mbar_expect_tx(bar, Cfg::STAGE);
+    tma_load_4d(dst, &tmX, bar, cbase, tx * TW - 1, ty * DT_TH - 1, img);
+    if (MODE == 1) tma_load_4d(dst + Cfg::XB, &tmDY, bar, cbase, tx * TW, ty * DT_TH, img);
+  };
+  if (tid == 0 && (long)blockIdx.y < ntiles) issue(blockIdx.y, 0);
+  int it = 0;
+  for (long tl = blockIdx.y; tl < ntiles; tl += gridDim.y, it++) {
+    const int stage = it & 1;
+    // the other stage was last read in iteration it-1, which ended with a __syncthreads
+    if (tid == 0 && tl + gridDim.y < ntiles) issue(tl + gridDim.y, stage ^ 1);
+    const int tx = (int)(tl % tiles_x);
+    const int ty = (int)((tl / tiles_x) % tiles_y);
+    const int b = (int)(tl / per_img);
+    const int x0 = tx * TW, y0 = ty * DT_TH;
+    const int gy = y0 + r;
+    mbar_wait(bar0 + 8u * (uint32_t)stage, (uint32_t)(it >> 1) & 1u);
+    if (gy < H && c_ok) {
+      // shared-memory addresses: x tile [(TH+2)][(TW+2)][64 ch], dy tile [TH][TW][64 ch], 128 B per pixel
+      const uint32_t xs = sbase + (uint32_t)stage * Cfg::STAGE + (uint32_t)(r * (TW + 2) * DT_CH + cp * 2) * 2u;
+      const uint32_t ds = sbase + (uint32_t)stage * Cfg::STAGE + Cfg::XB + (uint32_t)(r * TW * DT_CH + cp * 2) * 2u;
+      auto lds32 = [](uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; };
+      float2 win[3][3];
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 2; j++) win[i][j + 1] = bf2_unpack(lds32(xs + (uint32_t)((i * (TW + 2) + j) * DT_CH) * 2u));
+      bf16* orow = out + ((long)(b * H + gy) * W + x0) * ldo + c;   // advanced by ldo per pixel
+#pragma unroll
+      for (int px = 0; px < TW; px++) {
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+          win[i][0] = win[i][1];
+          win[i][1] = win[i][2];
+          win[i][2] = bf2_unpack(lds32(xs + (uint32_t)((i * (TW + 2) + px + 2) * DT_CH) * 2u));
+        }
+        if (x0 + px >= W) break;
+        // three independent row chains (3 deep) + two adds instead of one 9-deep FFMA2 chain: the kernel stalls on
+        // fixed-latency dependencies with 16-32 warps per SM
+        float2 a = bs, a1 = make_float2(0.f, 0.f), a2 = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+          ffma2(a, wt[j], win[0][j]);
+          ffma2(a1, wt[3 + j], win[1][j]);
+          ffma2(a2, wt[6 + j], win[2][j]);
+        }
+        a = fadd2(a, fadd2(a1, a2));
+        if (MODE == 1) {
+          float2 gq = bf2_unpack(lds32(ds + (uint32_t)(px * DT_CH) * 2u));
+          if (ACT == CMX_ACT_GELU) {
+            gq = fmul2(gq, gelu_grad2(a));
+          } else {
+            gq.x *= act_grad_f<ACT>(a.x);
+            gq.y *= act_grad_f<ACT>(a.y);
+          }
+          gb = fadd2(gb, gq);
+#pragma unroll
+          for (int i = 0; i < 3; i++)
+#pragma unroll
+            for (int j = 0; j < 3; j++) ffma2(gw[i * 3 + j], gq, win[i][j]);
+          *reinterpret_cast<__nv_bfloat162*>(orow) = __floats2bfloat162_rn(gq.x, gq.y);
+        } else {
+          if (ACT == CMX_ACT_GELU) a = gelu2(a);
+          else { a.x = act_f<ACT>(a.x); a.y = act_f<ACT>(a.y); }
+          const __nv_bfloat162 o2 = __floats2bfloat162_rn(a.x, a.y);
+          *reinterpret_cast<__nv_bfloat162*>(orow) = o2;
+          if (db) {  // per-channel sum of what was written (bias gradient of the layer that produced x's gradient)
+            const float2 of = __bfloat1622float2(o2);
+            gb.x += of.x;
+            gb.y += of.y;
+          }
+        }
+        orow += ldo;
+      }
+    }
+    __syncthreads();  // every thread is done with this stage: it may be refilled at the top of the next iteration
+  }
+  if (MODE != 1 && db) {
+    for (int i = tid; i < DT_CH; i += 256) sred[9][i] = 0.f;
+    __syncthreads();
+    if (c_ok) {
+      atomicAdd(&sred[9][cp * 2], gb.x);
+      atomicAdd(&sred[9][cp * 2 + 1], gb.y);
+    }
+    __syncthreads();
+    for (int i = tid; i < DT_CH; i += 256)
+      if (cbase + i < C) atomicAdd(db + cbase + i, sred[9][i]);
+  }
+  if (MODE == 1) {
+    // reduce the 8 row-threads of every channel pair, then one atomicAdd per (channel, tap) per CTA
+    for (int i = tid; i < 20 * DT_CH; i += 256) (&sred[0][0])[i] = 0.f;
+    __syncthreads();
+    if (c_ok) {
+#pragma unroll
+      for (int t = 0; t < 9; t++) {
+        atomicAdd(&sred[t][cp * 2], gw[t].x);
+        atomicAdd(&sred[t][cp * 2 + 1], gw[t].y);
+      }
+      atomicAdd(&sred[9][cp * 2], gb.x);
+      atomicAdd(&sred[9][cp * 2 + 1], gb.y);
+    }
+    __syncthreads();
+    for (int i = tid; i < 10 * DT_CH; i += 256) {
+      const int t = i / DT_CH, l = i % DT_CH;
+      const int cc = cbase + l;
+      if (cc < C) {
+        if (t < 9) atomicAdd(dw + (long)cc * 9 + t, sred[t][l]);
+        else if (db) atomicAdd(db + cc, sred[9][l]);
+      }
+    }
+  }
+}
+
+// rank-4 bf16 tensor map [C, W, H, images] over a token-major [images*H*W, ld] tensor, box [64, bw, bh, 1], no swizzle, zero fill
+static int dwconv_make_map(CUtensorMap* tm, const void* ptr, long ld, int C, int W, int H, long images, int bw, int bh) {
+  PFN_cmxEncodeTiled enc = cmx_get_encode();
+  if (!enc) { cmx_set_error("cuTensorMapEncodeTiled unavailable"); return -2; }
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)images};
+  cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)ld * 2 * W, (cuuint64_t)ld * 2 * W * H};
+  cuuint32_t box[4] = {(cuuint32_t)DT_CH, (cuuint32_t)bw, (cuuint32_t)bh, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { cmx_set_error("dwconv3x3: cuTensorMapEncodeTiled failed (%d)", (int)r); return -3; }
+  return 0;
+}
+
+template <int ACT, int MODE, int TW>
+static int dwconv_tma_launch_tw(const void* x, long ldx, const float* w, const float* bias, const void* dy, long lddy, void* out,
+                                long ldo, float* dw, float* db, int B, int H, int W, int C, int groups, long pgs, cudaStream_t st) {
+  using Cfg = DtmCfg<MODE, TW>;
+  CUtensorMap tmX, tmDY;
+  int rc = dwconv_make_map(&tmX, x, ldx, C, W, H, (long)groups * B, TW + 2, DT_TH + 2);
+  if (rc) return rc;
+  if (MODE == 1) {
+    rc = dwconv_make_map(&tmDY, dy, lddy, C, W, H, (long)groups * B, TW, DT_TH);
+    if (rc) return rc;
+  } else {
+    tmDY = tmX;
+  }
+  auto kern = dwconv_tma_kernel<ACT, MODE, TW>;
+  static thread_local PerDeviceOnce once;
+  static thread_local int occ = 1, sms = 148;
+  if (once.pending()) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+    if (e != cudaSuccess) CMX_FAIL((int)e, "cudaFuncSetAttribute(dwconv_tma): %s", cudaGetErrorString(e));
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, Cfg::SMEM);
+    if (occ < 1) occ = 1;
+    once.mark();
+  }
+  const int tiles_x = (W + TW - 1) / TW, tiles_y = (H + DT_TH - 1) / DT_TH;
+  const long ntiles = (long)B * tiles_x * tiles_y;
+  const int gx = (C + DT_CH - 1) / DT_CH;
+  static int waves_env = -1;
+  if (waves_env < 0) {
+    const char* e = getenv("CMX_DWCONV_WAVES");
+    waves_env = e ? atoi(e) : 0;
+  }
+  const int waves = waves_env > 0 ? waves_env : ((MODE == 1 || db) ? 1 : 2);   // reducing kernels: one wave = fewest atomics
+  long gy = (long)sms * occ * waves / ((long)gx * groups);
+  if (gy < 1) gy = 1;
+  if (gy > ntiles) gy = ntiles;
+  dim3 grid(gx, (unsigned)gy, (unsigned)groups);
+  kern<<<grid, 256, Cfg::SMEM, st>>>(tmX, tmDY, w, bias, (bf16*)out, ldo, dw, db, B, H, W, C, tiles_x, tiles_y, ntiles, pgs);
+  return 0;
+}
+
+// tile width of the TMA path: 16 or 20 pixels, whichever stages fewer pixel columns (padded width + 2 halo columns per tile)
+static int dwconv_tma_pick_tw(int W) {
+  const long c16 = (long)((W + 15) / 16) * 18, c20 = (long)((W + 19) / 20) * 22;
+  return c20 < c16 ? 20 : 16;
+}
+static bool dwconv_tma_ok(const void* x, long ldx, const void* dy, long lddy, int C) {
+  static int off = -1;
+  if (off < 0) off = getenv("CMX_DWCONV_TMA") != nullptr && getenv("CMX_DWCONV_TMA")[0] == '0' ? 1 : 0;
+  if (off) return false;
+  if (C % 8 || ldx % 8 || (((uintptr_t)x) & 15)) return false;          // tensor-map strides / base: multiples of 16 bytes
+  if (dy && (lddy % 8 || (((uintptr_t)dy) & 15))) return false;
+  return true;
+}
+
 template <int ACT, int MODE, int TW>
 static void dwconv_tiled_launch_tw(const void* x, long ldx, const float* w, const float* bias, const void* dy, long lddy, void* out,
                                    long ldo, float* dw, float* db, int B, int H, int W, int C, int groups, long pgs, cudaStream_t st) {
@@ -309,8 +565,33 @@ static void dwconv_tiled_launch_tw(const void* x, long ldx, const float* w, cons
   const long ntiles = (long)B * tiles_x * tiles_y;
   const int gx = (C + DT_CH - 1) / DT_CH;
   long gy = ntiles;
-  long cap = (MODE == 1 || db) ? (148L * 5 + gx - 1) / gx : (148L * 20 + gx - 1) / gx;  // reductions: few CTAs => few atomics
-  cap = (cap + groups - 1) / groups;
+  // grid = whole waves of resident CTAs (every CTA walks ntiles / gy tiles of equal cost): the earlier fixed caps (5 or 20 CTAs
+  // per SM) left a 2.5-wave grid for the 2-resident-CTA backward kernel, i.e. a last wave with half the SMs idle.
+  // CMX_DWCONV_WAVES: waves per launch (default 1 for the reducing kernels - fewest atomics -, 2 otherwise); 0 = the old caps.
+  static int waves_env = -1;
+  if (waves_env < 0) {
+    const char* e = getenv("CMX_DWCONV_WAVES");
+    waves_env = e ? atoi(e) : 100;
+  }
+  long cap;
+  if (waves_env == 0) {
+    cap = (MODE == 1 || db) ? (148L * 5 + gx - 1) / gx : (148L * 20 + gx - 1) / gx;  // reductions: few CTAs => few atomics
+    cap = (cap + groups - 1) / groups;
+  } else {
+    static thread_local PerDeviceOnce occ_once;
+    static thread_local int occ = 0, sms = 148;
+    if (occ_once.pending()) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dwconv_tiled_kernel<ACT, MODE, TW>, 256, 0);
+      if (occ < 1) occ = 1;
+      occ_once.mark();
+    }
+    const int waves = waves_env == 100 ? ((MODE == 1 || db) ? 1 : 2) : waves_env;
+    cap = (long)sms * occ * waves / ((long)gx * groups);
+    if (cap < 1) cap = 1;
+  }
   if (gy > cap) gy = cap;
   dim3 grid(gx, (unsigned)gy, (unsigned)groups);
   dwconv_tiled_kernel<ACT, MODE, TW><<<grid, 256, 0, st>>>((const bf16*)x, ldx, w, bias, (const bf16*)dy, lddy, (bf16*)out, ldo, dw, db,
@@ -330,10 +611,15 @@ static int dwconv_pick_tw(int W) {
 }
 
 template <int ACT, int MODE>
-static void dwconv_tiled_launch(const void* x, long ldx, const float* w, const float* bias, const void* dy, long lddy, void* out,
-                                long ldo, float* dw, float* db, int B, int H, int W, int C, int groups, long pgs, cudaStream_t st) {
+static int dwconv_tiled_launch(const void* x, long ldx, const float* w, const float* bias, const void* dy, long lddy, void* out,
+                               long ldo, float* dw, float* db, int B, int H, int W, int C, int groups, long pgs, cudaStream_t st) {
+  if (dwconv_tma_ok(x, ldx, MODE == 1 ? dy : nullptr, lddy, C)) {
+    if (dwconv_tma_pick_tw(W) == 20) return dwconv_tma_launch_tw<ACT, MODE, 20>(x, ldx, w, bias, dy, lddy, out, ldo, dw, db, B, H, W, C, groups, pgs, st);
+    return dwconv_tma_launch_tw<ACT, MODE, 16>(x, ldx, w, bias, dy, lddy, out, ldo, dw, db, B, H, W, C, groups, pgs, st);
+  }
   if (dwconv_pick_tw(W) == 20) dwconv_tiled_launch_tw<ACT, MODE, 20>(x, ldx, w, bias, dy, lddy, out, ldo, dw, db, B, H, W, C, groups, pgs, st);
   else dwconv_tiled_launch_tw<ACT, MODE, 32>(x, ldx, w, bias, dy, lddy, out, ldo, dw, db, B, H, W, C, groups, pgs, st);
+  return 0;
 }
 
 CMX_API int cmx_dwconv3x3_fwd(const void* x, int64_t ldx, const float* w, const float* bias, int act, int flip, void* y,
@@ -345,12 +631,14 @@ CMX_API int cmx_dwconv3x3_fwd(const void* x, int64_t ldx, const float* w, const 
   const long pgs = param_gs;
   CMX_REQUIRE(groups == 1 || getenv("CMX_DWCONV_LEGACY") == nullptr, "dwconv3x3: grouped launches need the tiled kernel");
   if (getenv("CMX_DWCONV_LEGACY") == nullptr) {
+    int rc;
     if (flip) {
       CMX_REQUIRE(act == CMX_ACT_NONE, "dwconv3x3: flip is for the data gradient (no activation)");
-      dwconv_tiled_launch<CMX_ACT_NONE, 2>(x, ldx, w, nullptr, nullptr, 0, y, ldy, nullptr, ysum, B, H, W, C, groups, pgs, st);
-    } else if (act == CMX_ACT_GELU) dwconv_tiled_launch<CMX_ACT_GELU, 0>(x, ldx, w, bias, nullptr, 0, y, ldy, nullptr, ysum, B, H, W, C, groups, pgs, st);
-    else if (act == CMX_ACT_RELU) dwconv_tiled_launch<CMX_ACT_RELU, 0>(x, ldx, w, bias, nullptr, 0, y, ldy, nullptr, ysum, B, H, W, C, groups, pgs, st);
-    else dwconv_tiled_launch<CMX_ACT_NONE, 0>(x, ldx, w, bias, nullptr, 0, y, ldy, nullptr, ysum, B, H, W, C, groups, pgs, st);
+      rc = dwconv_tiled_launch<CMX_ACT_NONE, 2>(x, ldx, w, nullptr, nullptr, 0, y, ldy, nullptr, ysum, B, H, W, C, groups, pgs, st);
+    } else if (act == CMX_ACT_GELU) rc = dwconv_tiled_launch<CMX_ACT_GELU, 0>(x, ldx, w, bias, nullptr, 0, y, ldy, nullptr, ysum, B, H, W, C, groups, pgs, st);
+    else if (act == CMX_ACT_RELU) rc = dwconv_tiled_launch<CMX_ACT_RELU, 0>(x, ldx, w, bias, nullptr, 0, y, ldy, nullptr, ysum, B, H, W, C, groups, pgs, st);
+    else rc = dwconv_tiled_launch<CMX_ACT_NONE, 0>(x, ldx, w, bias, nullptr, 0, y, ldy, nullptr, ysum, B, H, W, C, groups, pgs, st);
+    if (rc) return rc;
     g_cmx_launches++;
     CMX_CHECK_LAUNCH("dwconv3x3_tiled");
     return 0;
@@ -499,9 +787,11 @@ CMX_API int cmx_dwconv3x3_bwd_pre(const void* x, int64_t ldx, const float* w, co
   const bool tiled = getenv("CMX_DWCONV_LEGACY") == nullptr && C % 8 == 0 && ldx % 8 == 0;
   CMX_REQUIRE(groups == 1 || tiled, "dwconv3x3_bwd_pre: grouped launches need the tiled kernel (C %% 8 == 0)");
   if (tiled) {
-    if (act == CMX_ACT_GELU) dwconv_tiled_launch<CMX_ACT_GELU, 1>(x, ldx, w, bias, dy, lddy, du, lddu, dw, db, B, H, W, C, groups, pgs, st);
-    else if (act == CMX_ACT_RELU) dwconv_tiled_launch<CMX_ACT_RELU, 1>(x, ldx, w, bias, dy, lddy, du, lddu, dw, db, B, H, W, C, groups, pgs, st);
-    else dwconv_tiled_launch<CMX_ACT_NONE, 1>(x, ldx, w, bias, dy, lddy, du, lddu, dw, db, B, H, W, C, groups, pgs, st);
+    int rc;
+    if (act == CMX_ACT_GELU) rc = dwconv_tiled_launch<CMX_ACT_GELU, 1>(x, ldx, w, bias, dy, lddy, du, lddu, dw, db, B, H, W, C, groups, pgs, st);
+    else if (act == CMX_ACT_RELU) rc = dwconv_tiled_launch<CMX_ACT_RELU, 1>(x, ldx, w, bias, dy, lddy, du, lddu, dw, db, B, H, W, C, groups, pgs, st);
+    else rc = dwconv_tiled_launch<CMX_ACT_NONE, 1>(x, ldx, w, bias, dy, lddy, du, lddu, dw, db, B, H, W, C, groups, pgs, st);
+    if (rc) return rc;
     g_cmx_launches++;
     CMX_CHECK_LAUNCH("dwconv3x3_bwd_pre_tiled");
     return 0;
