@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_kernel(const __grid_consta
   const uint32_t sK = sb + AT_K_OFF, sV = sb + AT_V_OFF, sQ = sb + AT_Q_OFF, sP = sb + AT_P_OFF, sRed = sb + AT_RED_OFF;
   const uint32_t bar = sb + AT_BAR_OFF;
   const uint32_t kv_full = bar, kv_empty = bar + 8, q_full = bar + 16 /*[2]*/, q_empty = bar + 32 /*[2]*/, s_full = bar + 48,
-                 p_full = bar + 56, o_full = bar + 64, o_empty = bar + 72, p_in = bar + 80, tmem_slot = bar + 88;
+                 p_full = bar + 56, o_full = bar + 64, o_empty = bar + 72, p_in = bar + 80, tmem_slot = bar + 88, p_free = bar + 96;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   // contiguous tile range of this CTA
@@ -83,7 +83,8 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_kernel(const __grid_consta
     mbar_init(kv_empty, 1);
     for (int i = 0; i < 2; i++) { mbar_init(q_full + 8 * i, 1); mbar_init(q_empty + 8 * i, 1); }
     mbar_init(s_full, 1);
-    mbar_init(p_full, 1);
+    mbar_init(p_full, MODE == 0 ? AT_SW : 1);
+    mbar_init(p_free, 1);
     mbar_init(o_full, 1);
     mbar_init(o_empty, AT_SW);
     mbar_init(p_in, 1);
@@ -130,6 +131,25 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_kernel(const __grid_consta
         mbar_expect_tx(q_full + 8 * s, AT_BM * 128);
         tma_load_3d(sQ + s * 16384, &tmQ, q_full + 8 * s, h * AT_D, q0, b);
       }
+    } else if (MODE == 0 && lane == 1 && a.store_p) {
+      // ---- P store (training forward): once the sixteen softmax warps have completed tile i's normalised probabilities, TMA-store
+      // them for the backward pass and release the staging tile (p_free) when the copy engine has finished reading it
+      for (int i = 0; i < ntiles; i++) {
+        const long t = t_begin + i;
+        const long bh = t / a.tiles_per_bh;
+        const int q0 = (int)(t % a.tiles_per_bh) * AT_BM;
+        mbar_wait(p_full, (uint32_t)i & 1u);
+#pragma unroll
+        for (int kb = 0; kb < AT_NK / 64; kb++)
+          if (kb * 64 < a.Nk)
+            asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                         ::"l"(reinterpret_cast<uint64_t>(&tmP)), "r"(sP + kb * 16384), "r"(kb * 64), "r"(q0), "r"((int)bh)
+                         : "memory");
+        tma_store_commit();
+        tma_store_wait_read<0>();
+        mbar_arrive(p_free);
+      }
+      tma_store_wait_all();
     }
   } else if (warp == 1) {
     // ============================ MMA issuer ============================
@@ -274,33 +294,80 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_kernel(const __grid_consta
           tma_store_commit();
         }
       } else {
-        // the TMA store of the previous tile's P must have finished READING shared memory before P is overwritten
-        if (a.store_p && threadIdx.x == 64) tma_store_wait_read<0>();
+        // ---- forward softmax.  Every warp owns the 128 rows of its TMEM lane quarter q and 80 of the 320 score columns (part),
+        // walked as five 16-column chunks with software-pipelined tcgen05.ld (the load of chunk k+1 is in flight while chunk k
+        // is processed: ncu showed the warps stalled on the scoreboard of the TMEM / shared-memory loads, 30 % issue activity).
+        // Row reductions go through shared memory between the four warps of a quarter only (128-thread named barriers), and the
+        // "P complete" signal is one mbarrier arrive per warp - no CTA-wide barrier is left in the tile loop.
         mbar_wait(s_full, (uint32_t)i & 1u);
         tc_fence_after();
-        // ---- pass 1: row maximum over this thread's 160 columns.  The softmax warps are instruction-issue bound (ncu: 49 % issue
-        // activity with 10 warps per SM), so chunks that lie completely below Nkv take a predicate-free body
-        float mx = -INFINITY;
-  #pragma unroll 1
-        for (int c = cb; c < ce; c++) {
-          const int col0 = c * 32;
-          if (col0 >= a.Nk) break;
-          uint32_t v[32];
-          tmem_ld32(t_row + (uint32_t)col0, v);
-          tmem_wait_ld();
-          if (col0 + 32 <= a.Nk) {
-            float m4[4] = {mx, -INFINITY, -INFINITY, -INFINITY};   // four independent chains
-  #pragma unroll
-            for (int j = 0; j < 32; j++) m4[j & 3] = fmaxf(m4[j & 3], __uint_as_float(v[j]));
-            mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
-          } else {
-  #pragma unroll
-            for (int j = 0; j < 32; j++)
-              if (col0 + j < a.Nk) mx = fmaxf(mx, __uint_as_float(v[j]));
-          }
-        }
+        const int colb = part * 80;
+        const uint32_t t_base = t_row + (uint32_t)colb;
+        const int bar_max = 1 + q, bar_sum = 5 + q;
+        // AT_WALK(BODY): BODY(values[16], first column) for this warp's chunks below Nkv; two register buffers with fixed roles,
+        // the loop walks chunk PAIRS and is not unrolled (macros, not lambdas: the buffers must stay in registers)
+#define AT_WALK(BODY)                                                                              \
+  {                                                                                                \
+    uint32_t v0[16], v1[16];                                                                       \
+    tmem_ld_n<16>(t_base, v0);                                                                     \
+    _Pragma("unroll 1") for (int k = 0; k < 5; k += 2) {                                           \
+      const int col0 = colb + 16 * k;                                                              \
+      /* the loads are unconditional (a chunk past this warp's range or past Nkv is read and ignored: the columns exist) */ \
+      tmem_wait_ld_dep16(v0);                                                                      \
+      tmem_ld_n<16>(t_base + (uint32_t)(16 * (k + 1)), v1);                                        \
+      if (col0 < a.Nk) { BODY(v0, col0) }                                                          \
+      tmem_wait_ld_dep16(v1);                                                                      \
+      if (k + 2 < 5) tmem_ld_n<16>(t_base + (uint32_t)(16 * (k + 2)), v0);                         \
+      if (k + 1 < 5 && col0 + 16 < a.Nk) { BODY(v1, (col0 + 16)) }                                 \
+    }                                                                                              \
+  }
+#define AT_BODY_MAX(v, c0)                                                                         \
+  if ((c0) + 16 <= a.Nk) {                                                                         \
+    _Pragma("unroll") for (int j = 0; j < 16; j++) m4[j & 3] = fmaxf(m4[j & 3], __uint_as_float(v[j])); \
+  } else {                                                                                         \
+    _Pragma("unroll") for (int j = 0; j < 16; j++)                                                 \
+      if ((c0) + j < a.Nk) m4[j & 3] = fmaxf(m4[j & 3], __uint_as_float(v[j]));                    \
+  }
+#define AT_BODY_SUM(v, c0)                                                                         \
+  if ((c0) + 16 <= a.Nk) {                                                                         \
+    _Pragma("unroll") for (int j = 0; j < 16; j++) s4[j & 3] += ex2_approx(fmaf(__uint_as_float(v[j]), sl2, -moff)); \
+  } else {                                                                                         \
+    _Pragma("unroll") for (int j = 0; j < 16; j++)                                                 \
+      if ((c0) + j < a.Nk) s4[j & 3] += ex2_approx(fmaf(__uint_as_float(v[j]), sl2, -moff));       \
+  }
+  // P = 2^(s*scale*log2e - eoff) as bf16 -> K-major SWIZZLE_128B staging tile; ACC: also the row sum over the ROUNDED values
+#define AT_BODY_P(v, c0, ACC)                                                                      \
+  {                                                                                                \
+    uint32_t pk[8];                                                                                \
+    const bool cfull = (c0) + 16 <= a.Nk;                                                          \
+    _Pragma("unroll") for (int j = 0; j < 8; j++) {                                                \
+      float p0 = ex2_approx(fmaf(__uint_as_float(v[2 * j]), sl2, -eoff));                          \
+      float p1 = ex2_approx(fmaf(__uint_as_float(v[2 * j + 1]), sl2, -eoff));                      \
+      if (!cfull) {                                                                                \
+        p0 = (c0) + 2 * j < a.Nk ? p0 : 0.f;                                                       \
+        p1 = (c0) + 2 * j + 1 < a.Nk ? p1 : 0.f;                                                   \
+      }                                                                                            \
+      __nv_bfloat162 h2 = __floats2bfloat162_rn(p0, p1);                                           \
+      if (ACC) {                                                                                   \
+        const float2 back = __bfloat1622float2(h2);                                                \
+        s4[j & 3] += back.x + back.y;                                                              \
+      }                                                                                            \
+      pk[j] = *reinterpret_cast<uint32_t*>(&h2);                                                   \
+    }                                                                                              \
+    _Pragma("unroll") for (int g = 0; g < 2; g++) {                                                \
+      const int col = (c0) + g * 8;                                                                \
+      const uint32_t kb = (uint32_t)col >> 6, ch = ((uint32_t)col & 63u) >> 3;                     \
+      st_shared_v4(rowad + kb * 16384 + ((ch ^ sw) << 4), pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]); \
+    }                                                                                              \
+  }
+#define AT_BODY_P_ACC(v, c0) AT_BODY_P(v, c0, true)
+#define AT_BODY_P_NOACC(v, c0) AT_BODY_P(v, c0, false)
+        // ---- pass 1: row maximum
+        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // four independent chains
+        AT_WALK(AT_BODY_MAX)
+        const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
         asm volatile("st.shared.f32 [%0], %1;" ::"r"(sRed + 4u * (part * 128 + r)), "f"(mx) : "memory");
-        asm volatile("bar.sync 1, %0;" ::"n"(AT_ST) : "memory");   // also orders thread 64's wait_group.read before any P write
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_max) : "memory");
         float m = -INFINITY;
 #pragma unroll
         for (int pp = 0; pp < AT_NP; pp++) {
@@ -309,52 +376,24 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_kernel(const __grid_consta
           m = fmaxf(m, mpart);
         }
         const float moff = m * sl2;
-        // ---- pass 2: p = 2^(s*scale*log2e - m*scale*log2e) (one MUFU.EX2 each), row sum, bf16 P -> shared memory (K-major,
-        // SWIZZLE_128B).  The sum is taken over the bf16-rounded values (what the P V MMA sees) in four independent chains.
+        const uint32_t rowad = sP + (uint32_t)r * 128;
+        const uint32_t sw = (uint32_t)r & 7u;
         float s4[4] = {0.f, 0.f, 0.f, 0.f};
-  #pragma unroll 1
-        for (int c = cb; c < ce; c++) {
-          const int col0 = c * 32;
-          const uint32_t rowad = sP + (uint32_t)r * 128;
-          const uint32_t sw = (uint32_t)r & 7u;
-          if (col0 >= a.Nk) {   // keys beyond Nkv: P = 0 (their V rows are zero-filled, but 0 * garbage could be NaN)
-  #pragma unroll
-            for (int g = 0; g < 4; g++) {
-              const int col = col0 + g * 8;
-              const uint32_t kb = (uint32_t)col >> 6, ch = ((uint32_t)col & 63u) >> 3;
-              st_shared_v4(rowad + kb * 16384 + ((ch ^ sw) << 4), 0u, 0u, 0u, 0u);
-            }
-            continue;
-          }
-          uint32_t v[32];
-          tmem_ld32(t_row + (uint32_t)col0, v);
-          tmem_wait_ld();
-          const bool cfull = col0 + 32 <= a.Nk;
-  #pragma unroll
-          for (int g = 0; g < 4; g++) {
-            uint32_t pk[4];
-  #pragma unroll
-            for (int j = 0; j < 4; j++) {
-              float p0 = ex2_approx(fmaf(__uint_as_float(v[g * 8 + 2 * j]), sl2, -moff));
-              float p1 = ex2_approx(fmaf(__uint_as_float(v[g * 8 + 2 * j + 1]), sl2, -moff));
-              if (!cfull) {
-                const int cc = col0 + g * 8 + 2 * j;
-                p0 = cc < a.Nk ? p0 : 0.f;
-                p1 = cc + 1 < a.Nk ? p1 : 0.f;
-              }
-              __nv_bfloat162 h2 = __floats2bfloat162_rn(p0, p1);
-              const float2 back = __bfloat1622float2(h2);
-              s4[j] += back.x + back.y;
-              pk[j] = *reinterpret_cast<uint32_t*>(&h2);
-            }
-            const int col = col0 + g * 8;
-            const uint32_t kb = (uint32_t)col >> 6, ch = ((uint32_t)col & 63u) >> 3;
-            st_shared_v4(rowad + kb * 16384 + ((ch ^ sw) << 4), pk[0], pk[1], pk[2], pk[3]);
-          }
+        float eoff = moff;
+        if (a.store_p) {
+          // ---- training, pass 2: row sum of p = 2^(s*scale*log2e - m*scale*log2e) only (one FFMA + one MUFU.EX2 + one FADD per
+          // element); pass 3 recomputes the exponential with the normaliser folded into the offset and writes the NORMALISED bf16
+          // probabilities once - instead of storing unnormalised values and rescaling them in place (a shared-memory round trip
+          // with two conversions per element).
+          AT_WALK(AT_BODY_SUM)
+        } else {
+          // ---- inference / recompute backward, pass 2: unnormalised bf16 P -> shared memory + row sum over the rounded values
+          // (what the P V MMA sees); the 64 output columns are scaled by 1 / sum in the epilogue instead
+          AT_WALK(AT_BODY_P_ACC)
         }
         const float sum = (s4[0] + s4[1]) + (s4[2] + s4[3]);
         asm volatile("st.shared.f32 [%0], %1;" ::"r"(sRed + AT_RED2 + 4u * (part * 128 + r)), "f"(sum) : "memory");
-        asm volatile("bar.sync 2, %0;" ::"n"(AT_ST) : "memory");
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_sum) : "memory");
         float lsum = 0.f;
 #pragma unroll
         for (int pp = 0; pp < AT_NP; pp++) {
@@ -362,46 +401,30 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_kernel(const __grid_consta
           asm volatile("ld.shared.f32 %0, [%1];" : "=f"(lpart) : "r"(sRed + AT_RED2 + 4u * (pp * 128 + r)));
           lsum += lpart;
         }
-        const float inv = 1.f / lsum;
         o_scale = 1.f;
         if (a.store_p) {
-          // ---- training: normalise this thread's 160 probabilities in place (the stored P is what the backward pass consumes)
-  #pragma unroll 1
-          for (int cg = cb * 4; cg < ce * 4; cg++) {
-            const int col = cg * 8;
-            if (col >= a.Nk) break;
-            const uint32_t kb = (uint32_t)col >> 6, ch = ((uint32_t)col & 63u) >> 3;
-            const uint32_t ad = sP + kb * 16384 + (uint32_t)r * 128 + ((ch ^ ((uint32_t)r & 7u)) << 4);
-            uint32_t w[4];
-            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(ad));
-  #pragma unroll
-            for (int j = 0; j < 4; j++) {
-              float2 f = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&w[j]));
-              __nv_bfloat162 h2 = __floats2bfloat162_rn(f.x * inv, f.y * inv);
-              w[j] = *reinterpret_cast<uint32_t*>(&h2);
-            }
-            st_shared_v4(ad, w[0], w[1], w[2], w[3]);
-          }
+          // the TMA store of the previous tile's P must have finished READING the staging tile before it is overwritten
+          if (i > 0) mbar_wait(p_free, (uint32_t)(i - 1) & 1u);
+          eoff = moff + __log2f(lsum);   // p / sum = 2^(s*scale*log2e - eoff)
+          AT_WALK(AT_BODY_P_NOACC)
         } else {
-          o_scale = inv;   // inference / recompute backward: P stays unnormalised, the 64 output columns are scaled instead
+          o_scale = 1.f / lsum;
+        }
+        // keys beyond Nkv: P = 0 (their V rows are zero-filled, but 0 * garbage could be NaN)
+#pragma unroll
+        for (int k = 0; k < 10; k++) {
+          const int col = colb + 8 * k;
+          if (col >= ((a.Nk + 15) & ~15)) {
+            const uint32_t kb = (uint32_t)col >> 6, ch = ((uint32_t)col & 63u) >> 3;
+            st_shared_v4(rowad + kb * 16384 + ((ch ^ sw) << 4), 0u, 0u, 0u, 0u);
+          }
         }
         if (a.lse && part == 0 && q0 + r < a.N)
           a.lse[bh * a.N + q0 + r] = m * (sl2 * 0.69314718055994531f) + logf(lsum);
         tc_fence_before();
-        fence_async_smem();
-        asm volatile("bar.sync 3, %0;" ::"n"(AT_ST) : "memory");      // P complete (generic-proxy writes fenced for the async proxy)
-        if (threadIdx.x == 64) {
-          mbar_arrive(p_full);
-          if (a.store_p) {
-  #pragma unroll
-            for (int kb = 0; kb < AT_NK / 64; kb++)
-              if (kb * 64 < a.Nk)
-                asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
-                             ::"l"(reinterpret_cast<uint64_t>(&tmP)), "r"(sP + kb * 16384), "r"(kb * 64), "r"(q0), "r"((int)bh)
-                             : "memory");
-            tma_store_commit();
-          }
-        }
+        fence_async_smem();          // generic-proxy writes of P fenced for the async proxy (MMA operand fetch, TMA store)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_full);   // AT_SW arrivals complete the phase
       }
       // ---- epilogue: O (normalised here when P was not) TMEM -> bf16 -> global; each thread of the pair takes 32 of the 64 columns
       mbar_wait(o_full, (uint32_t)i & 1u);
@@ -426,7 +449,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_kernel(const __grid_consta
       __syncwarp();
       if (lane == 0) mbar_arrive(o_empty);
     }
-    if ((a.store_p || MODE == 1) && threadIdx.x == 64) tma_store_wait_all();
+    if (MODE == 1 && threadIdx.x == 64) tma_store_wait_all();
   }
   tc_fence_before();
   __syncthreads();

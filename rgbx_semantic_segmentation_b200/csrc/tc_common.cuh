@@ -101,6 +101,14 @@ __device__ __forceinline__ void tmem_ld_n(uint32_t taddr, uint32_t* r) {   // tc
   }
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// 16-register variant of tmem_wait_ld_dep (below) for pipelined x16 loads
+__device__ __forceinline__ void tmem_wait_ld_dep16(uint32_t* r) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
+}
 // wait that also threads the 32 destination registers through the asm statement, so that no consumer of r[] can be
 // scheduled above the wait when other work is placed between the tcgen05.ld and its wait (software pipelining)
 __device__ __forceinline__ void tmem_wait_ld_dep(uint32_t* r) {
