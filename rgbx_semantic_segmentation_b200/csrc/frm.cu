@@ -493,6 +493,8 @@ CMX_API int cmx_frm_rectify_fwd(const void* a, int64_t lda, const void* t, int64
 
 // backward.  grid (ctas_per_sample, B): every CTA stays inside one sample so the per-(b,c) channel-weight
 // gradients can be reduced in shared memory before one atomicAdd per channel per CTA.
+// J = ceil(C / 128) register slices per lane (compile time: the per-lane accumulators are 16 floats per slice)
+template <int J>
 __global__ void __launch_bounds__(256) frm_rectify_bwd_kernel(const float* __restrict__ dr1, long lddr1, const float* __restrict__ dr2,
                                                               long lddr2, const bf16* __restrict__ a, long lda,
                                                               const bf16* __restrict__ t, long ldt, const float* __restrict__ w2,
@@ -509,9 +511,9 @@ __global__ void __launch_bounds__(256) frm_rectify_bwd_kernel(const float* __res
   for (int i = threadIdx.x; i < 2 * 512; i += blockDim.x) { (&s_dcw[0][0])[i] = 0.f; (&s_dw2[0][0])[i] = 0.f; }
   if (threadIdx.x < 2) s_db2[threadIdx.x] = 0.f;
   __syncthreads();
-  float acw0[FR_MAXJ][4], acw1[FR_MAXJ][4], aw0[FR_MAXJ][4], aw1[FR_MAXJ][4];
+  float acw0[J][4], acw1[J][4], aw0[J][4], aw1[J][4];
 #pragma unroll
-  for (int j = 0; j < FR_MAXJ; j++)
+  for (int j = 0; j < J; j++)
 #pragma unroll
     for (int i = 0; i < 4; i++) { acw0[j][i] = 0.f; acw1[j][i] = 0.f; aw0[j][i] = 0.f; aw1[j][i] = 0.f; }
   float ab0 = 0.f, ab1 = 0.f;
@@ -521,10 +523,10 @@ __global__ void __launch_bounds__(256) frm_rectify_bwd_kernel(const float* __res
     const bool valid = r < HW;
     const long row = (long)b * HW + (valid ? r : rb);  // invalid sub-rows shadow a valid one, contribute nothing, store nothing
     const float s0 = sw[row * 2], s1 = sw[row * 2 + 1];
-    float g1[FR_MAXJ][4], g2[FR_MAXJ][4], a1[FR_MAXJ][4], a2[FR_MAXJ][4];
+    float g1[J][4], g2[J][4], a1[J][4], a2[J][4];
     float ds0 = 0.f, ds1 = 0.f;
 #pragma unroll
-    for (int j = 0; j < FR_MAXJ; j++) {
+    for (int j = 0; j < J; j++) {
       const int c = 4 * (sl + 32 * j);
       if (c < C && valid) {
         load4(dr1 + row * lddr1 + c, g1[j]);
@@ -552,7 +554,7 @@ __global__ void __launch_bounds__(256) frm_rectify_bwd_kernel(const float* __res
     ds1 = 0.5f * group_sum(ds1, G) * s1 * (1.f - s1);
     if (sl == 0) { ab0 += ds0; ab1 += ds1; }
 #pragma unroll
-    for (int j = 0; j < FR_MAXJ; j++) {
+    for (int j = 0; j < J; j++) {
       const int c = 4 * (sl + 32 * j);
       if (c < C && valid) {
         float tv[4], wa[4], wb[4], o[4];
@@ -570,7 +572,7 @@ __global__ void __launch_bounds__(256) frm_rectify_bwd_kernel(const float* __res
     }
   }
 #pragma unroll
-  for (int j = 0; j < FR_MAXJ; j++) {
+  for (int j = 0; j < J; j++) {
     const int c = 4 * (sl + 32 * j);
     if (c < C) {
 #pragma unroll
@@ -603,7 +605,14 @@ CMX_API int cmx_frm_rectify_bwd(const float* dr1, int64_t lddr1, const float* dr
   if (gx < 1) gx = 1;
   if (gx > 296) gx = 296;
   dim3 grid(gx, B);
-  frm_rectify_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dr1, lddr1, dr2, lddr2, (const bf16*)a, lda, (const bf16*)t, ldt, w2,
-                                                                 cw, sw, da, ldda, (bf16*)dt, lddt, dcw, dw2, db2, HW, C, G);
+#define FRB(Jv)                                                                                                              \
+  frm_rectify_bwd_kernel<Jv><<<grid, 256, 0, (cudaStream_t)stream>>>(dr1, lddr1, dr2, lddr2, (const bf16*)a, lda, (const bf16*)t, ldt, \
+                                                                     w2, cw, sw, da, ldda, (bf16*)dt, lddt, dcw, dw2, db2, HW, C, G)
+  const int nj = (C + 127) / 128;
+  if (nj <= 1) FRB(1);
+  else if (nj == 2) FRB(2);
+  else if (nj == 3) FRB(3);
+  else FRB(4);
+#undef FRB
   LAUNCH_DONE("frm_rectify_bwd");
 }

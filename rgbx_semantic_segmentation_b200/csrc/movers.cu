@@ -16,10 +16,13 @@ extern std::atomic<long long> g_cmx_launches;
 // ---- stage-1 im2col from the NCHW fp32 image ------------------------------------------------------
 // I = index type of the thread -> (row, column group) decomposition: unsigned 32-bit whenever the element count allows
 // (64-bit divisions cost ~100 instructions each and these kernels move 16-32 bytes per thread)
-template <typename I>
-__global__ void __launch_bounds__(256) im2col_nchw_kernel(const float* __restrict__ x, bf16* __restrict__ col, int B, int Cin, int H,
-                                                          int W, int k, int s, int p, int Ho, int Wo, int kpad) {
+// CIN / KK > 0: compile-time channel count and kernel size (the 7x7 stride-4 stage-1 patch embed over 3 channels is the only
+// caller that matters: 147 runtime divisions per output pixel otherwise); 0 = runtime values
+template <typename I, int CIN, int KK>
+__global__ void __launch_bounds__(256) im2col_nchw_kernel(const float* __restrict__ x, bf16* __restrict__ col, int B, int Cin_, int H,
+                                                          int W, int k_, int s, int p, int Ho, int Wo, int kpad) {
   pdl_trigger();
+  const int Cin = CIN > 0 ? CIN : Cin_, k = KK > 0 ? KK : k_;
   // one thread = 8 consecutive im2col columns of one output pixel (one 16-byte store)
   const int g8 = kpad >> 3;
   const I idx = (I)blockIdx.x * blockDim.x + threadIdx.x;
@@ -30,6 +33,8 @@ __global__ void __launch_bounds__(256) im2col_nchw_kernel(const float* __restric
   const int ox = (int)(row % (I)Wo);
   const int oy = (int)((row / (I)Wo) % (I)Ho);
   const int b = (int)(row / ((I)Wo * Ho));
+  const float* xb = x + (long)b * Cin * H * W;
+  const int iy0 = oy * s - p, ix0 = ox * s - p;
   float v[8];
 #pragma unroll
   for (int i = 0; i < 8; i++) {
@@ -38,8 +43,8 @@ __global__ void __launch_bounds__(256) im2col_nchw_kernel(const float* __restric
     if (j < k * k * Cin) {
       const int ci = j % Cin, tap = j / Cin;
       const int kh = tap / k, kw = tap % k;
-      const int iy = oy * s - p + kh, ix = ox * s - p + kw;
-      if (iy >= 0 && iy < H && ix >= 0 && ix < W) v[i] = x[(((long)b * Cin + ci) * H + iy) * W + ix];
+      const int iy = iy0 + kh, ix = ix0 + kw;
+      if (iy >= 0 && iy < H && ix >= 0 && ix < W) v[i] = __ldg(xb + ((long)ci * H + iy) * W + ix);
     }
   }
   store8(col + (long)row * kpad + j0, v);
@@ -49,10 +54,12 @@ CMX_API int cmx_im2col_nchw(const float* x, void* col, int B, int Cin, int H, in
   CMX_REQUIRE(kpad >= k * k * Cin && kpad % 8 == 0, "im2col_nchw: kpad must be a multiple of 8 and >= k*k*Cin");
   const long total = (long)B * Ho * Wo * (kpad >> 3);
   if (total == 0) return 0;
-  if (total < (1L << 31))
-    im2col_nchw_kernel<unsigned><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(x, (bf16*)col, B, Cin, H, W, k, s, p, Ho, Wo, kpad);
+  if (total < (1L << 31) && Cin == 3 && k == 7)
+    im2col_nchw_kernel<unsigned, 3, 7><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(x, (bf16*)col, B, Cin, H, W, k, s, p, Ho, Wo, kpad);
+  else if (total < (1L << 31))
+    im2col_nchw_kernel<unsigned, 0, 0><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(x, (bf16*)col, B, Cin, H, W, k, s, p, Ho, Wo, kpad);
   else
-    im2col_nchw_kernel<long><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(x, (bf16*)col, B, Cin, H, W, k, s, p, Ho, Wo, kpad);
+    im2col_nchw_kernel<long, 0, 0><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(x, (bf16*)col, B, Cin, H, W, k, s, p, Ho, Wo, kpad);
   LAUNCH_DONE("im2col_nchw");
 }
 
