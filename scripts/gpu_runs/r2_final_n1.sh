@@ -4,7 +4,7 @@
 #   gpurun --timeout 2400 -- 'bash scripts/gpu_runs/r2_final_n1.sh'
 mkdir -p gpurun_out
 set -x
-# (the full GPU suite ran green on the same code in scripts/gpu_runs/r2_call14.sh: profiles/r2_gpu_tests_180_passed.log)
+# (the full GPU suite ran green on the same code in scripts/gpu_runs/r2_call27.sh: profiles/r2_gpu_tests_180_passed.log)
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2_final_smoke.log 2>&1
 echo "smoke rc=$?"; tail -1 gpurun_out/r2_final_smoke.log
 timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -s 1500 -c 9000 --csv --log-file /tmp/r2_launches_final.csv python scripts/ncu_step.py --steps 1 > gpurun_out/r2_ncu_list.log 2>&1
@@ -27,7 +27,7 @@ for f in ("gpurun_out/r2_bench_n1_final.json", "gpurun_out/r2_bench_b4_pst900_n1
     print("   cpu", d.get("cpu_baseline"))
     print("   infer", {k: v.get("img_s") for k, v in d["inference"].items()})
 P
-K='regex:gemm_tc_kernel|dwconv_tiled|ln_bwd_v2|ln_fwd_v2|attn_kernel'
+K='regex:gemm_tc_kernel|dwconv_tma|ln_bwd_v2|ln_fwd_v2|attn_kernel'
 timeout 900 ncu --set full --clock-control none --import-source on -k "$K" -s 1526 -c 24 -o /tmp/r2_final_s1_fwd python scripts/ncu_step.py --steps 1 > gpurun_out/r2_ncu_final_fwd.log 2>&1
 echo "ncu full rc=$?"
 python scripts/ncu_brief.py /tmp/r2_final_s1_fwd.ncu-rep > gpurun_out/r2_ncu_full_stage1_forward_kernels.txt 2>&1

@@ -31,10 +31,10 @@ def bench_class(name):
              ("ce_upsampled", "cmx_ce_upsampled_fwd_bwd"), ("frm_rectify_bwd", "cmx_frm_rectify_bwd"),
              ("frm_rectify_fwd", "cmx_frm_rectify_fwd"), ("pool_avgmax_bwd", "cmx_pool_avgmax_bwd"),
              ("pool_partial", "cmx_pool_avgmax_fwd"), ("pool_finalize", "cmx_pool_avgmax_fwd"),
-             ("smallm_linear_fwd", "cmx_smallm_linear_fwd"), ("smallm_d", "cmx_smallm_linear_bwd"),
+             ("smallm_linear_fwd", "cmx_smallm_linear_fwd"), ("smallm_d", "cmx_smallm_linear_bwd"), ("smallm_bwd_fused", "cmx_smallm_linear_bwd"),
              ("cast_f32_bf16", "cmx_cast_f32_bf16"), ("relu_bwd", "cmx_relu_bwd"), ("softmax_dim2_fwd", "cmx_softmax_dim2_fwd"),
              ("softmax_dim2_bwd", "cmx_softmax_dim2_bwd")]
-    m = re.match(r"(?:void )?dwconv_tiled_kernel<\(?(?:int\))?(\d+), \(?(?:int\))?(\d+)>", name)
+    m = re.match(r"(?:void )?dwconv_(?:tiled|tma)_kernel<\(?(?:int\))?(\d+), \(?(?:int\))?(\d+)(?:, \(?(?:int\))?\d+)?>", name)
     if m:
         return {0: "cmx_dwconv3x3_fwd", 1: "cmx_dwconv3x3_bwd_pre", 2: "cmx_dwconv3x3_dgrad"}[int(m.group(2))]
     for key, cls in table:
