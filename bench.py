@@ -519,6 +519,23 @@ def main_ours(args):
                      "same host pre/post-processing, one batch-6 forward"),
                     ("device", lambda: sliding_eval_rgbX_gpu(ctx, im, mx, (H, W), 2 / 3, dev, max_batch=8),
                      "device-resident: uint8 upload, normalise/pad/tile, one batch-6 forward, exp, resize, sum, argmax on the GPU"))
+            # dataset streaming (what an evaluation run over a dataset does): confusion matrix accumulated on the device, no
+            # read-back per image - the host work of image i+1 overlaps the kernels of image i; one synchronisation at the end
+            acc_h = torch.zeros(NCLS, NCLS, dtype=torch.int64, device=dev)
+            acc_s = torch.zeros(2, dtype=torch.int64, device=dev)
+            for _ in range(2):
+                sliding_eval_rgbX_gpu(ctx, im, mx, (H, W), 2 / 3, dev, max_batch=8, gt=gtm, accum=(acc_h, acc_s))
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            n_stream = 20
+            for _ in range(n_stream):
+                sliding_eval_rgbX_gpu(ctx, im, mx, (H, W), 2 / 3, dev, max_batch=8, gt=gtm, accum=(acc_h, acc_s))
+            torch.cuda.synchronize()
+            acc_h.cpu()
+            dt = (time.perf_counter() - t0) / n_stream
+            infer["sliding_eval_device_stream"] = {"img_s": 1.0 / dt, "ms_per_image": dt * 1e3, "crops_per_image": 6, "images": n_stream,
+                                                   "note": "device driver over a stream of images: confusion matrix accumulated on the device, "
+                                                           "one synchronisation + read-back after the last image; host wall clock per image"}
             for tag, fn, note in runs:
                 for _ in range(2):
                     pred = fn()

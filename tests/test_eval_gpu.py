@@ -84,6 +84,13 @@ def test_device_driver_vs_reference_evaluator_golden_stub_network(golden_dir, na
     assert np.array_equal(p2, pred)
     hr, lr, cr = metric_ref.hist_info(case["ncls"], pred, gt)
     assert np.array_equal(hist, hr) and (labeled, correct) == (lr, cr)
+    # dataset streaming: device accumulators, no read-back per image; two images == twice the single-image sums
+    acc_h = torch.zeros(case["ncls"], case["ncls"], dtype=torch.int64, device="cuda")
+    acc_s = torch.zeros(2, dtype=torch.int64, device="cuda")
+    for _ in range(2):
+        p3 = sliding_eval_rgbX_gpu(ctx, img, mx, case["crop"], case["stride_rate"], device="cuda", gt=gt, accum=(acc_h, acc_s))
+    assert p3.is_cuda and np.array_equal(p3.cpu().numpy().astype(np.int64), pred)
+    assert np.array_equal(acc_h.cpu().numpy(), 2 * hr) and acc_s.tolist() == [2 * lr, 2 * cr]
 
 
 def test_device_driver_through_the_real_model_vs_reference_evaluator_golden(golden_dir):
