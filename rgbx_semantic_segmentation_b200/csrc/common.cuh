@@ -57,6 +57,31 @@ enum { CMX_ACT_NONE = 0, CMX_ACT_RELU = 1, CMX_ACT_GELU = 2 };
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// ---- division of a 31-bit index by a runtime constant: q = umulhi(n, mul) >> shr (two instructions instead of the ~20 of a
+// 32-bit hardware-less division; the movers decode a linear thread index into 4-6 coordinates per 16 bytes moved) -----------------
+struct FastDiv {
+  unsigned d, mul, shr;
+};
+static inline FastDiv make_fastdiv(unsigned d) {   // valid for dividends < 2^31
+  FastDiv f;
+  f.d = d;
+  f.mul = 0;
+  f.shr = 0;
+  if (d > 1) {
+    unsigned lg = 0;
+    while ((1ull << lg) < d) lg++;
+    const unsigned p = 31 + lg;
+    f.mul = (unsigned)(((1ull << p) + d - 1) / d);
+    f.shr = p - 32;
+  }
+  return f;
+}
+__device__ __forceinline__ unsigned fdiv(unsigned n, const FastDiv& f) { return f.d == 1 ? n : (__umulhi(n, f.mul) >> f.shr); }
+__device__ __forceinline__ void fdivmod(unsigned n, const FastDiv& f, unsigned& q, unsigned& r) {
+  q = fdiv(n, f);
+  r = n - q * f.d;
+}
+
 // ---- device helpers ------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

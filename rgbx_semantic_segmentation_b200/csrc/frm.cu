@@ -220,6 +220,22 @@ __global__ void __launch_bounds__(256) smallm_linear_fwd_v4_kernel(const float* 
   for (int m = 0; m < SMALLM_MAX; m++) acc[m] = 0.f;
   const float* wr = w + (long)n * K;
   int k = lane * 4;
+  // eight, then four independent 16-byte weight loads in flight per lane (ncu: the kernel is a chain of DRAM round trips -
+  // long-scoreboard stalls 10-20x the issue time - so the depth of each round trip is what counts)
+  for (; k + 7 * 128 < K; k += 8 * 128) {
+    float4 wv[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) wv[u] = __ldg(reinterpret_cast<const float4*>(wr + k + u * 128));
+#pragma unroll
+    for (int m = 0; m < SMALLM_MAX; m++)
+      if (m < Mb) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+          const float4 xv = __ldg(reinterpret_cast<const float4*>(x + (long)m * K + k + u * 128));
+          acc[m] = fmaf(wv[u].x, xv.x, fmaf(wv[u].y, xv.y, fmaf(wv[u].z, xv.z, fmaf(wv[u].w, xv.w, acc[m]))));
+        }
+      }
+  }
   for (; k + 3 * 128 < K; k += 4 * 128) {
     float4 wv[4];
 #pragma unroll
@@ -347,19 +363,42 @@ __global__ void __launch_bounds__(256) smallm_bwd_fused_kernel(const float* __re
     if (q >= (long)N * kq) return;
     const int n = (int)(q / kq), k = (int)(q % kq) * 4;
     float4 s = *reinterpret_cast<const float4*>(dw + (long)n * K + k);
-    for (int m = 0; m < Mb; m++) {
-      const float g = smallm_dpre(__ldg(dy + (long)m * N + n), __ldg(y + (long)m * N + n), act);
-      const float4 xv = __ldg(reinterpret_cast<const float4*>(x + (long)m * K + k));
-      s.x = fmaf(g, xv.x, s.x); s.y = fmaf(g, xv.y, s.y); s.z = fmaf(g, xv.z, s.z); s.w = fmaf(g, xv.w, s.w);
+    // all loads of the (predicated, fully unrolled) sample loop are issued before the first use: one memory round trip
+    float gy[SMALLM_MAX], gv[SMALLM_MAX];
+    float4 xv[SMALLM_MAX];
+#pragma unroll
+    for (int m = 0; m < SMALLM_MAX; m++) {
+      gy[m] = 0.f; gv[m] = 0.f; xv[m] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (m < Mb) {
+        gy[m] = __ldg(dy + (long)m * N + n);
+        gv[m] = __ldg(y + (long)m * N + n);
+        xv[m] = __ldg(reinterpret_cast<const float4*>(x + (long)m * K + k));
+      }
+    }
+#pragma unroll
+    for (int m = 0; m < SMALLM_MAX; m++) {
+      const float g = smallm_dpre(gy[m], gv[m], act);   // rows >= Mb: g = dpre(0, 0) = 0
+      s.x = fmaf(g, xv[m].x, s.x); s.y = fmaf(g, xv[m].y, s.y); s.z = fmaf(g, xv[m].z, s.z); s.w = fmaf(g, xv[m].w, s.w);
     }
     *reinterpret_cast<float4*>(dw + (long)n * K + k) = s;
     return;
   }
   const int bid = (int)blockIdx.x - nb_dw;
   const int kc = bid % kchunks, n0 = (bid / kchunks) * 64;
-  for (int i = threadIdx.x; i < SMALLM_MAX * 64; i += 256) {
-    const int m = i >> 6, n = n0 + (i & 63);
-    sd[m][i & 63] = (m < Mb && n < N) ? smallm_dpre(__ldg(dy + (long)m * N + n), __ldg(y + (long)m * N + n), act) : 0.f;
+  {
+    float a_[4], b_[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {   // SMALLM_MAX * 64 / 256 = 4 entries per thread, loads first
+      const int i = threadIdx.x + u * 256, m = i >> 6, n = n0 + (i & 63);
+      const bool ok = m < Mb && n < N;
+      a_[u] = ok ? __ldg(dy + (long)m * N + n) : 0.f;
+      b_[u] = ok ? __ldg(y + (long)m * N + n) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int i = threadIdx.x + u * 256;
+      sd[i >> 6][i & 63] = smallm_dpre(a_[u], b_[u], act);
+    }
   }
   __syncthreads();
   if (db && kc == 0 && threadIdx.x < 64 && n0 + (int)threadIdx.x < N) {
@@ -373,13 +412,13 @@ __global__ void __launch_bounds__(256) smallm_bwd_fused_kernel(const float* __re
   float acc[SMALLM_MAX];
 #pragma unroll
   for (int m = 0; m < SMALLM_MAX; m++) acc[m] = 0.f;
-  for (int n = 0; n < 64; n += 8) {
+  for (int n = 0; n < 64; n += 32) {   // 32 weight loads in flight per round (two rounds per 64-row chunk)
     if (n0 + n >= N) break;
-    float wv[8];
+    float wv[32];
 #pragma unroll
-    for (int u = 0; u < 8; u++) wv[u] = n0 + n + u < N ? __ldg(w + (long)(n0 + n + u) * K + k) : 0.f;
+    for (int u = 0; u < 32; u++) wv[u] = n0 + n + u < N ? __ldg(w + (long)(n0 + n + u) * K + k) : 0.f;
 #pragma unroll
-    for (int u = 0; u < 8; u++)
+    for (int u = 0; u < 32; u++)
 #pragma unroll
       for (int m = 0; m < SMALLM_MAX; m++) acc[m] = fmaf(sd[m][n + u], wv[u], acc[m]);
   }

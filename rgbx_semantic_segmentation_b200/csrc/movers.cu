@@ -146,13 +146,34 @@ __global__ void __launch_bounds__(256) im2col_nhwc_kernel(const bf16* __restrict
   if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = *reinterpret_cast<const uint4*>(x + ((long)(b * H + iy) * W + ix) * ldx + cg * 8);
   *reinterpret_cast<uint4*>(col + ((long)row * (k * k) + tap) * C + cg * 8) = v;
 }
+// 32-bit variant with precomputed divisions (the production path: every call of the model has < 2^31 vectors)
+struct Im2colDivs { FastDiv c8, kk, k, Wo, Ho; };
+__global__ void __launch_bounds__(256) im2col_nhwc_fast_kernel(const bf16* __restrict__ x, long ldx, bf16* __restrict__ col, int H, int W, int C,
+                                                               int s, int p, unsigned total, Im2colDivs dv) {
+  pdl_trigger();
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  unsigned t, cg, row, tap, kh, kw, q, ox, b, oy;
+  fdivmod(idx, dv.c8, t, cg);
+  fdivmod(t, dv.kk, row, tap);
+  fdivmod(tap, dv.k, kh, kw);
+  fdivmod(row, dv.Wo, q, ox);
+  fdivmod(q, dv.Ho, b, oy);
+  const int iy = (int)oy * s - p + (int)kh, ix = (int)ox * s - p + (int)kw;
+  uint4 v = make_uint4(0, 0, 0, 0);
+  if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = *reinterpret_cast<const uint4*>(x + ((long)((int)b * H + iy) * W + ix) * ldx + cg * 8);
+  *reinterpret_cast<uint4*>(col + (long)t * C + cg * 8) = v;   // t = row * k*k + tap
+}
 CMX_API int cmx_im2col_nhwc(const void* x, int64_t ldx, void* col, int B, int H, int W, int C, int k, int s, int p, int Ho,
                             int Wo, void* stream) {
   CMX_REQUIRE(C % 8 == 0 && ldx % 8 == 0, "im2col_nhwc: C %% 8");
   const long total = (long)B * Ho * Wo * k * k * (C >> 3);
   if (total == 0) return 0;
-  if (total < (1L << 31))
-    im2col_nhwc_kernel<unsigned><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, ldx, (bf16*)col, B, H, W, C, k, s, p, Ho, Wo);
+  if (total < (1L << 31)) {
+    Im2colDivs dv{make_fastdiv((unsigned)(C >> 3)), make_fastdiv((unsigned)(k * k)), make_fastdiv((unsigned)k), make_fastdiv((unsigned)Wo),
+                  make_fastdiv((unsigned)Ho)};
+    im2col_nhwc_fast_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, ldx, (bf16*)col, H, W, C, s, p, (unsigned)total, dv);
+  }
   else
     im2col_nhwc_kernel<long><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, ldx, (bf16*)col, B, H, W, C, k, s, p, Ho, Wo);
   LAUNCH_DONE("im2col_nhwc");
@@ -197,6 +218,38 @@ __global__ void __launch_bounds__(256) col2im_nhwc_kernel(const bf16* __restrict
   }
   store8(dx + (long)pix * lddx + cg * 8, acc);
 }
+struct Col2imDivs { FastDiv c8, W, H, s; };
+template <typename TA, typename TO>
+__global__ void __launch_bounds__(256) col2im_nhwc_fast_kernel(const bf16* __restrict__ dcol, const TA* __restrict__ add, long ldadd,
+                                                               TO* __restrict__ dx, long lddx, int C, int k, int s, int p, int Ho, int Wo,
+                                                               unsigned total, Col2imDivs dv) {
+  pdl_trigger();
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  unsigned pix, cg, q, ix, b, iy;
+  fdivmod(idx, dv.c8, pix, cg);
+  fdivmod(pix, dv.W, q, ix);
+  fdivmod(q, dv.H, b, iy);
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) acc[i] = 0.f;
+  if (add) load8(add + (long)pix * ldadd + cg * 8, acc);
+  // only taps with (iy + p - kh) divisible by the stride contribute (one tap for the non-overlapping SR convolutions k = s = R)
+  unsigned qy, ry, qx, rx;
+  fdivmod(iy + (unsigned)p, dv.s, qy, ry);   // iy + p = qy * s + ry: tap kh = ry + j*s reads output row qy - j
+  fdivmod(ix + (unsigned)p, dv.s, qx, rx);
+  for (int kh = (int)ry, oy = (int)qy; kh < k && oy >= 0; kh += s, oy--) {
+    if (oy >= Ho) continue;
+    for (int kw = (int)rx, ox = (int)qx; kw < k && ox >= 0; kw += s, ox--) {
+      if (ox >= Wo) continue;
+      float v[8];
+      load8(dcol + ((((long)b * Ho + oy) * Wo + ox) * (k * k) + kh * k + kw) * C + cg * 8, v);
+#pragma unroll
+      for (int i = 0; i < 8; i++) acc[i] += v[i];
+    }
+  }
+  store8(dx + (long)pix * lddx + cg * 8, acc);
+}
 CMX_API int cmx_col2im_nhwc(const void* dcol, const void* add, int add_dtype, int64_t ldadd, void* dx, int dx_dtype, int64_t lddx,
                             int B, int H, int W, int C, int k, int s, int p, int Ho, int Wo, void* stream) {
   CMX_REQUIRE(C % 8 == 0 && lddx % 8 == 0, "col2im_nhwc: C %% 8");
@@ -206,9 +259,11 @@ CMX_API int cmx_col2im_nhwc(const void* dcol, const void* add, int add_dtype, in
   dim3 grid(cdiv(total, 256));
 #define C2I(TA, TO)                                                                                                            \
   do {                                                                                                                         \
-    if (total < (1L << 31))                                                                                                    \
-      col2im_nhwc_kernel<TA, TO, unsigned><<<grid, 256, 0, st>>>((const bf16*)dcol, (const TA*)add, ldadd, (TO*)dx, lddx, B, H, \
-                                                                 W, C, k, s, p, Ho, Wo);                                        \
+    if (total < (1L << 31)) {                                                                                                  \
+      Col2imDivs dv{make_fastdiv((unsigned)(C >> 3)), make_fastdiv((unsigned)W), make_fastdiv((unsigned)H), make_fastdiv((unsigned)s)}; \
+      col2im_nhwc_fast_kernel<TA, TO><<<grid, 256, 0, st>>>((const bf16*)dcol, (const TA*)add, ldadd, (TO*)dx, lddx, C, k, s, p, Ho, \
+                                                            Wo, (unsigned)total, dv);                                             \
+    }                                                                                                                          \
     else                                                                                                                       \
       col2im_nhwc_kernel<TA, TO, long><<<grid, 256, 0, st>>>((const bf16*)dcol, (const TA*)add, ldadd, (TO*)dx, lddx, B, H, W,  \
                                                              C, k, s, p, Ho, Wo);                                               \
