@@ -27,6 +27,7 @@ for f in ("gpurun_out/r2_bench_n1_final.json", "gpurun_out/r2_bench_b4_pst900_n1
     print("   cpu", d.get("cpu_baseline"))
     print("   infer", {k: v.get("img_s") for k, v in d["inference"].items()})
 P
+if [ "$FULL" != "0" ]; then
 K='regex:gemm_tc_kernel|dwconv_tma|ln_bwd_v2|ln_fwd_v2|attn_kernel'
 timeout 900 ncu --set full --clock-control none --import-source on -k "$K" -s 1526 -c 24 -o /tmp/r2_final_s1_fwd python scripts/ncu_step.py --steps 1 > gpurun_out/r2_ncu_final_fwd.log 2>&1
 echo "ncu full rc=$?"
@@ -36,3 +37,4 @@ timeout 300 python scripts/timeline.py r2_timeline_final.csv > gpurun_out/r2_tim
 python scripts/timeline_analyze.py gpurun_out/r2_timeline_final.csv > gpurun_out/r2_timeline_summary_final.txt 2>&1
 head -12 gpurun_out/r2_timeline_summary_final.txt
 rm -f gpurun_out/timeline_trace.json gpurun_out/r2_timeline_final.csv
+fi
