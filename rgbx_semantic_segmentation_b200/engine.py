@@ -238,7 +238,7 @@ class Engine:
     # ------------------------------------------------------------------------------------------
     def E(self, *shape, dtype=bf16):
         if self.poison is not None:
-            # debug aid (scripts/gpu_poison.py): NaN-fill every fresh buffer and remember where it was allocated,
+            # debug aid (tests/tools/gpu_poison.py): NaN-fill every fresh buffer and remember where it was allocated,
             # so that buffers that are read before being (fully) written can be found without compute-sanitizer
             import sys
             if len(shape) == 1 and isinstance(shape[0], (tuple, list)):

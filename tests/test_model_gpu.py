@@ -147,7 +147,7 @@ def test_train_loss_and_grads_vs_reference(golden_dir, name):
             # 25 % on the norm, or - for tensors that are themselves ~1e-3 of the largest gradient - an absolute slack of
             # 5e-4 of the largest gradient norm.  The case that needs it: the 2-element FRM spatial-gate biases, whose
             # gradient is a sum over pixels of terms that cancel 13-24x (sum |ds| = 2e-2 vs |sum ds| = 1.5e-3 at stage 2,
-            # scripts/gpu_debug_gate.py); the kernel reproduces an fp64 evaluation on the same saved tensors exactly, the
+            # tests/tools/gpu_debug_gate.py); the kernel reproduces an fp64 evaluation on the same saved tensors exactly, the
             # ~1.5 % (of sum |ds|) deviation is ReLU-mask-flip noise of the bf16 forward
             if not (abs(r - 1) < 0.25 or abs(r - 1) * norms[n] < 5e-4 * gmax):
                 bad.append((round(r, 4), n))

@@ -8,13 +8,13 @@ FFM context logits K^T V * scale (net_utils.py:209, a sum over N = 19 200 tokens
 the softmax over dim -2 is one-hot, and the gradient is discontinuous in the activations: the fp32 arithmetic itself cannot
 reproduce its own gradients under a 0.2 % input perturbation.  The reference's real initialisation (trunc_normal std 0.02,
 dual_segformer.py:52-65) gives logit std < 1.
-    python scripts/ctx_softmax_conditioning.py > profiles/r2_ctx_softmax_conditioning.txt"""
+    python tests/tools/ctx_softmax_conditioning.py > profiles/r2_ctx_softmax_conditioning.txt"""
 import os
 import sys
 
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import cmx_ref  # noqa: E402
 from oracle.synth import synth_inputs, synth_state_dict  # noqa: E402
 

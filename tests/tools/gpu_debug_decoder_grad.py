@@ -1,7 +1,7 @@
 """debug: gradients inside the decoder head (low-res logits, post-BN activation, pre-BN fuse tensor) vs the fp32 oracle"""
 import os, sys
 import torch, torch.nn as nn, torch.nn.functional as F
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import cmx_ref
 from oracle.synth import synth_inputs, synth_state_dict
 from rgbx_semantic_segmentation_b200.models.builder import EncoderDecoder

@@ -2,7 +2,7 @@
 the decoder's output gradient (d fused feature) and the FFM input gradients of the engine with the fp32 oracle's."""
 import os, sys
 import torch, torch.nn as nn
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import cmx_ref
 from oracle.synth import synth_inputs, synth_state_dict
 from rgbx_semantic_segmentation_b200.models.builder import EncoderDecoder

@@ -1,12 +1,12 @@
 """GPU debugging aid: gradient parity of the whole training step against the fp32 oracle at growing sizes.
-Prints every parameter whose gradient cosine falls below 0.98.  Usage: python scripts/gpu_debug_fullsize.py [HxW ...]"""
+Prints every parameter whose gradient cosine falls below 0.98.  Usage: python tests/tools/gpu_debug_fullsize.py [HxW ...]"""
 import os
 import sys
 
 import torch
 import torch.nn as nn
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import cmx_ref  # noqa: E402
 from oracle.synth import synth_inputs, synth_state_dict  # noqa: E402
 from rgbx_semantic_segmentation_b200.models.builder import EncoderDecoder  # noqa: E402

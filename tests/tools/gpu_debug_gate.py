@@ -2,7 +2,7 @@
 saved tensors vs the fp32 oracle."""
 import os, sys
 import numpy as np, torch, torch.nn as nn
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import cmx_ref
 from oracle.synth import synth_inputs, synth_state_dict
 from rgbx_semantic_segmentation_b200.models.builder import EncoderDecoder

@@ -1,5 +1,5 @@
 """GPU debugging aid: layer-by-layer comparison of the CUDA engine against the fp32 oracle (same weights,
-same inputs), then loss / gradient comparison.  Usage: python scripts/gpu_debug_model.py [case ...]"""
+same inputs), then loss / gradient comparison.  Usage: python tests/tools/gpu_debug_model.py [case ...]"""
 import os
 import sys
 import time
@@ -7,7 +7,7 @@ import time
 import torch
 import torch.nn as nn
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import cmx_ref  # noqa: E402
 from oracle.synth import synth_inputs, synth_state_dict  # noqa: E402
 from rgbx_semantic_segmentation_b200.models.builder import EncoderDecoder  # noqa: E402

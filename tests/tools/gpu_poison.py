@@ -7,7 +7,7 @@ import sys
 import torch
 import torch.nn as nn
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import cmx_ref  # noqa: E402
 from oracle.synth import synth_inputs, synth_state_dict  # noqa: E402
 from rgbx_semantic_segmentation_b200.models.builder import EncoderDecoder  # noqa: E402
