@@ -1,8 +1,13 @@
-// Depthwise 3x3 (pad 1) + bias + activation on channels-last bf16 — the Mix-FFN DWConv+GELU
+// Depthwise 3x3 (pad 1) + bias + activation on channels-last bf16 - the Mix-FFN DWConv+GELU
 // (dual_segformer.py:25-33, 69-70) and the FFM ChannelEmbed DWConv+ReLU (net_utils.py:314-315),
-// computed directly in the token-major layout (no NLC<->NCHW copies).  Memory-bound: each thread
-// owns VEC channels x TW consecutive pixels of one image row and slides a 3 x (TW+2) register window,
-// 16-byte (8-byte for VEC=4) accesses, per-CTA weights staged in shared memory (tap-major).
+// computed directly in the token-major layout (no NLC<->NCHW copies).  Three generations live here:
+//   1. dwconv_fwd_kernel / dwconv_bwd_pre_kernel: register-window kernels reading global memory directly
+//      (CMX_DWCONV_LEGACY=1, single-group launches only; kept as the simplest correct form for A/B runs);
+//   2. dwconv_tiled_kernel: halo tile staged by cp.async, thread = (row, channel pair), packed FFMA2
+//      (CMX_DWCONV_TMA=0, or tensors a tensor map cannot address);
+//   3. dwconv_tma_kernel: the PRODUCTION path - the same arithmetic, tiles delivered by TMA with a zero-filled halo,
+//      two stages on mbarriers, dy through shared memory (see the comment above it).
+// All are issue / FP32-pipe bound, not HBM bound (profiles/r2_ncu_full_dwconv_cpasync_pipes.txt).
 #include "common.cuh"
 #include "tc_common.cuh"
 #include "../../include/cmx_b200.h"
@@ -115,7 +120,7 @@ __global__ void __launch_bounds__(DW_CG* DW_PY) dwconv_fwd_kernel(const bf16* __
 
 
 // ------------------------------------------------------------------------------------------------
-// Shared-memory tiled variant (the production path).  CTA = 8 rows x 32 pixels x 64 channels:
+// Shared-memory tiled variant (the production path of round 1; now the fallback).  CTA = 8 rows x TW pixels x 64 channels:
 //   * the (8+2) x (32+2) halo tile of x is staged once in shared memory with 16-byte loads ([pixel][64 ch] bf16,
 //     128 B per pixel => a warp reading one pixel's channel pairs is one conflict-free 128 B wavefront);
 //   * thread (row r = tid/32, channel pair cp = tid%32) walks its row with a 3x3 register window (3 LDS.32 per
