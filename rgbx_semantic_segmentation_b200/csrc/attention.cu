@@ -8,9 +8,13 @@
 //   * warp 1 issues tcgen05.mma: S[128 x 320] = Q K^T (two N=160 UMMAs x 4 k-steps, fp32 in TMEM columns 0..319) and
 //     O[128 x 64] = P V (A = P from shared memory, B = V viewed MN-major - the same bytes as the K-major tile -
 //     TMEM columns 320..383).  The QK^T of tile i+1 is issued before the epilogue of tile i finishes.
-//   * warps 2-9 (two threads per row, 160 columns each): pass 1 row max from TMEM, pass 2 exp2 + row sum, P (bf16) to
-//     shared memory in the K-major SWIZZLE_128B layout, normalised in place, which then feeds BOTH the P V MMA and -
-//     for training - a TMA bulk store of the probabilities the backward pass consumes.
+//   * warps 2-17 (16 softmax warps = 4 TMEM lane quarters x 4 column parts of 80 columns, walked as 16-column chunks with
+//     software-pipelined tcgen05.ld): pass 1 row max, pass 2 row sum of exp2 (training) or unnormalised bf16 P + row sum
+//     (inference / recompute backward / key chunks: the 64 output columns are scaled instead), pass 3 (training only) recomputes
+//     the exponentials with the normaliser folded in and writes the NORMALISED bf16 P once into the K-major SWIZZLE_128B tile
+//     that feeds BOTH the P V MMA and the TMA bulk store of the probabilities the backward pass consumes (issued by lane 1 of
+//     warp 0, which also releases the tile).  Row reductions stay inside a quarter (128-thread named barriers); "P complete"
+//     is one mbarrier arrive per warp.
 #include "tc_common.cuh"
 #include "../../include/cmx_b200.h"
 #include <atomic>
@@ -200,7 +204,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_kernel(const __grid_consta
       }
     }
   } else {
-    // ============================ softmax + epilogue (warps 2..9) ============================
+    // ============================ softmax + epilogue (warps 2..17) ============================
     const int q = warp & 3;               // TMEM lane quarter
     const int part = (warp - 2) >> 2;     // column part of this warp: chunks [cb, ce) of the ten 32-column chunks
     const int cb = (10 * part) / AT_NP, ce = (10 * (part + 1)) / AT_NP;
