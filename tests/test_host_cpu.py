@@ -101,6 +101,16 @@ def test_cpu_inputs_fail_loudly_and_model_pickles():
         EncoderDecoder(c, nn.MSELoss(), nn.BatchNorm2d)(z, z, torch.zeros(1, 32, 32, dtype=torch.long))
     m2 = pickle.loads(pickle.dumps(m))                              # engine/evaluator.py:131 pickles the model
     assert list(m2.state_dict().keys()) == list(m.state_dict().keys())
+    # after the first step the parameters are views of ONE flat buffer; a pickle must not carry that buffer per tensor
+    m._eng()._flatten(torch.device("cpu"))
+    n_bytes = sum(p.numel() * 4 for p in m.parameters())
+    assert next(m.parameters()).untyped_storage().nbytes() >= n_bytes
+    blob = pickle.dumps(m)
+    assert len(blob) < 2 * n_bytes + (4 << 20), len(blob)
+    m3 = pickle.loads(blob)
+    assert all(torch.equal(a, b) for a, b in zip(m.state_dict().values(), m3.state_dict().values()))
+    assert m3._engine is None and next(m3.parameters()).untyped_storage().nbytes() < (1 << 20)
+    assert next(m.parameters()).untyped_storage().nbytes() >= n_bytes          # the live model keeps its flat views
 
 
 DDP_WORKER = r'''
