@@ -191,15 +191,30 @@ class EncoderDecoder(nn.Module):
             self.__dict__["_params_cache"] = cache
         return cache[1]
 
+    def _graph_entry(self, key):
+        """captured graphs by (mode, shapes, ...) key, least recently used first.  Every entry pins the activation memory of its
+        capture, so a caller that keeps feeding new shapes (whole-image evaluation of a dataset with mixed image sizes) must not
+        grow the cache without bound: beyond CMX_MAX_GRAPHS (default 24) entries the least recently used one is dropped."""
+        g = self._graphs.pop(key, None)
+        if g is None:
+            cap = max(1, int(os.environ.get("CMX_MAX_GRAPHS", "24")))
+            if len(self._graphs) >= cap:
+                torch.cuda.synchronize()            # the graph about to be destroyed may still be replaying
+                while len(self._graphs) >= cap:
+                    self._graphs.pop(next(iter(self._graphs)))
+            self._graphs[key] = {"warm": 1}
+            return None
+        self._graphs[key] = g                       # most recently used -> last
+        return g
+
     def _forward_eval(self, rgb, modal_x):
         rgb, modal_x = _prep(rgb, modal_x)
         key = ("eval", tuple(rgb.shape), tuple(modal_x.shape), rgb.dtype, self.training, rgb.device.index)
         if not self.use_cuda_graph or self.training:
             return self._eng().forward_logits(rgb, modal_x)
         self._eng()._ensure_flat(rgb.device)  # parameters moved / re-created since the capture -> graphs were dropped
-        g = self._graphs.get(key)
+        g = self._graph_entry(key)
         if g is None:
-            self._graphs[key] = {"warm": 1}
             return self._eng().forward_logits(rgb, modal_x)
         if "graph" not in g:
             g["rgb"], g["x"] = rgb.clone(), modal_x.clone()
@@ -251,9 +266,8 @@ class EncoderDecoder(nn.Module):
 
         if not self.use_cuda_graph or eng.forced_dp is not None or eng.forced_dropout is not None or eng.sync_hook is not None:
             return eager(rgb, modal_x, label)
-        g = self._graphs.get(key)
+        g = self._graph_entry(key)
         if g is None:
-            self._graphs[key] = {"warm": 1}
             return eager(rgb, modal_x, label)
         if "graphs" not in g:
             g["rgb"], g["x"], g["label"] = rgb.clone(), modal_x.clone(), label.to(torch.int64).clone()

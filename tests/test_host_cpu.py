@@ -113,6 +113,19 @@ def test_cpu_inputs_fail_loudly_and_model_pickles():
     assert next(m.parameters()).untyped_storage().nbytes() >= n_bytes          # the live model keeps its flat views
 
 
+def test_graph_cache_is_least_recently_used_and_bounded(monkeypatch):
+    monkeypatch.setenv("CMX_MAX_GRAPHS", "3")
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    m = EncoderDecoder(CfgB0, None, nn.BatchNorm2d)
+    for k in "abc":
+        assert m._graph_entry(k) is None                 # first sight: warm-up entry, caller runs eagerly
+    assert m._graph_entry("a") == {"warm": 1}            # hit -> most recently used
+    assert m._graph_entry("d") is None and list(m._graphs) == ["c", "a", "d"]    # "b" was the least recently used
+    assert m._graph_entry("b") is None and list(m._graphs) == ["a", "d", "b"]
+    m._eng()._flatten(torch.device("cpu"))               # re-flattening drops every capture (raw pointers into the old buffers)
+    assert m._graphs == {}
+
+
 DDP_WORKER = r'''
 import os, sys, torch, torch.nn as nn, torch.distributed as dist
 sys.path.insert(0, sys.argv[1])

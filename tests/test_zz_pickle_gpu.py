@@ -38,3 +38,23 @@ def test_model_pickles_and_deep_copies_after_training_steps():
     # the live model still trains on its captured graphs afterwards
     m.train()
     assert torch.isfinite(m(rgb, x, gt)).item()
+
+
+def test_graph_cache_is_bounded_and_evicted_shapes_recapture(monkeypatch):
+    """every captured CUDA graph pins its activation memory: feeding ever new input shapes (whole-image evaluation of a dataset
+    with mixed sizes, engine/evaluator.py:306-327) must not grow the cache; an evicted shape is simply captured again."""
+    monkeypatch.setenv("CMX_MAX_GRAPHS", "2")
+    spec = cmx_ref.MIT_SPECS["mit_b0"]
+    sd = synth_state_dict(spec, 5, seed=0)
+    m = make("mit_b0", 5, False, sd).eval()
+    shapes = [(64, 64), (64, 96), (96, 64)]
+    ins = [tuple(t.cuda() for t in synth_inputs(1, h, w, 5, seed=7 + i)[:2]) for i, (h, w) in enumerate(shapes)]
+    m.use_cuda_graph = False
+    want = [m(a, b).clone() for a, b in ins]
+    m.use_cuda_graph = True
+    for rnd in range(3):                       # warm / capture / replay of each shape, interleaved so that entries get evicted
+        for k in (0, 0, 0, 1, 1, 1, 2, 2, 2, 0):
+            got = m(*ins[k])
+            assert len(m._graphs) <= 2
+            assert got.shape == want[k].shape and ((got - want[k]).norm() / want[k].norm()).item() < 1e-2, (rnd, k)
+    assert any("graph" in g for g in m._graphs.values())
