@@ -140,6 +140,14 @@ def synth_batch(batch, seed, device=None, pin=False):
     return rgb.to(device), x.to(device), gt.to(device)
 
 
+def workload_config(world):
+    """`config` of the JSON line - the WORKLOAD both arms are quoted on (`--impl reference` prints the same dict: it times a
+    bounded sample of this workload, described in its `cpu_baseline.sample`); what is specific to this repo's run (optimizer,
+    norm layer, gradient all-reduce, CUDA graphs) goes into the separate `impl_config` key"""
+    return {"workload": WORKLOAD, "global_batch": PER_GPU_BATCH * world, "per_gpu_batch": PER_GPU_BATCH, "parallelism": "dp%d" % world,
+            "l2": "per-step working set (>5 GB of activations at batch 8) exceeds the 126 MB L2; no explicit flush"}
+
+
 # ---------------------------------------------------------------------------------------------------------
 def cpu_reference_rate(steps, warmup, threads=None):
     """The reference's own CPU implementation of the path on the host cores, batch-1 fwd+bwd+AdamW: the UNMODIFIED reference
@@ -214,9 +222,9 @@ def main_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
             "warmup": max(1, args.warmup), "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD,
-                       "sample": "the same training step (fwd+bwd+AdamW) on one image of the batch per step: the reference's fp32 "
-                                 "algorithm on the host CPU, all host threads (img/s does not depend on the batch size there)"},
+            "config": workload_config(max(1, args.gpus)),
+            "sample": "the same training step (fwd+bwd+AdamW) on one image of the batch per step: the reference's fp32 "
+                      "algorithm on the host CPU, all host threads (img/s does not depend on the batch size there)",
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
@@ -561,13 +569,12 @@ def main_ours(args):
         line = {"metric": METRIC, "value": gb * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": warm, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "bf16", "data": "synthetic",
-                "config": {"workload": WORKLOAD,
-                           "global_batch": gb, "per_gpu_batch": B, "parallelism": "dp%d" % world, "optimizer": "FlatAdamW (AdamW, one launch)" if args.optimizer == "flat" else "torch.optim.AdamW(fused)",
-                           "norm_layer": norm_layer.__name__,
-                           "grad_allreduce": None if world == 1 else ("torch DDP buckets" if os.environ.get("CMX_BENCH_TORCH_DDP", "0") == "1"
-                                                                      else "one NCCL all-reduce over the flat fp32 gradient buffer"),
-                           "cuda_graph": bool(model.use_cuda_graph),
-                           "l2": "per-step working set (>5 GB of activations at batch 8) exceeds the 126 MB L2; no explicit flush"},
+                "config": workload_config(world),
+                "impl_config": {"optimizer": "FlatAdamW (AdamW, one launch)" if args.optimizer == "flat" else "torch.optim.AdamW(fused)",
+                                "norm_layer": norm_layer.__name__,
+                                "grad_allreduce": None if world == 1 else ("torch DDP buckets" if os.environ.get("CMX_BENCH_TORCH_DDP", "0") == "1"
+                                                                           else "two NCCL all-reduces over slices of the flat fp32 gradient buffer, the first overlapped with the backward pass"),
+                                "cuda_graph": bool(model.use_cuda_graph)},
                 "e2e": {"value": gb * args.steps / (ms2 * 1e-3), "unit": UNIT, "ms_per_step": ms2 / args.steps,
                         "h2d_bytes_per_step": int(hr.numel() * 4 + hx.numel() * 4 + hg.numel() * 8), "d2h_bytes_per_step": 4},
                 "gpu_launches": int(launches_per_step * args.steps) if launches_per_step else 0,

@@ -21,7 +21,9 @@ def test_reference_arm_line_matches_the_contract():
     d = json.loads(lines[0])
     import bench
     assert d["impl"] == "reference" and d["metric"] == bench.METRIC and d["unit"] == bench.UNIT
-    assert d["config"]["workload"] == bench.WORKLOAD and "sample" in d["config"]
+    # the reference arm is quoted on OUR arm's config (the dict both arms print), its bounded sample is described separately
+    assert d["config"] == bench.workload_config(1) and d["config"]["workload"] == bench.WORKLOAD and d["sample"]
+    assert set(d["config"]) == {"workload", "global_batch", "per_gpu_batch", "parallelism", "l2"}
     assert d["higher_is_better"] is True and d["vs_baseline"] is None and d["n_gpus"] == 1
     assert d["value"] > 0 and abs(d["value"] - 1e3 / d["ms_per_step"]) < 1e-6 * d["value"]
     cb = d["cpu_baseline"]
@@ -88,3 +90,32 @@ def test_committed_traffic_file_covers_the_dominant_classes():
         t = json.load(f)["by_class"]
     for k in ("gemm_tc_wgrad", "gemm_tc_fwd", "gemm_tc_dgrad", "cmx_layernorm_bwd", "cmx_dwconv3x3_bwd_pre", "cmx_attn_fwd"):
         assert t[k]["dram_bytes_per_launch"] > 0 and t[k]["launches"] > 0
+
+
+def test_bench_has_no_undefined_names():
+    """bench.py's GPU arm cannot run here; at least every name it loads must be bound somewhere (a typo in the line assembly
+    would only surface on the GPU box)"""
+    import ast
+    import builtins
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    tree = ast.parse(src)
+    bound = set(dir(builtins)) | {"__file__", "__name__"}
+    for node in ast.walk(tree):
+        if isinstance(node, (ast.FunctionDef, ast.ClassDef)):
+            bound.add(node.name)
+            if isinstance(node, ast.FunctionDef):
+                a = node.args
+                bound.update(x.arg for x in a.args + a.kwonlyargs + a.posonlyargs)
+                bound.update(x.arg for x in (a.vararg, a.kwarg) if x)
+        elif isinstance(node, ast.Lambda):
+            bound.update(x.arg for x in node.args.args)
+        elif isinstance(node, ast.Name) and isinstance(node.ctx, (ast.Store, ast.Del)):
+            bound.add(node.id)
+        elif isinstance(node, (ast.Import, ast.ImportFrom)):
+            bound.update((al.asname or al.name).split(".")[0] for al in node.names)
+        elif isinstance(node, ast.ExceptHandler) and node.name:
+            bound.add(node.name)
+        elif isinstance(node, ast.Global):
+            bound.update(node.names)
+    loads = {n.id for n in ast.walk(tree) if isinstance(n, ast.Name) and isinstance(n.ctx, ast.Load)}
+    assert not (loads - bound), sorted(loads - bound)
